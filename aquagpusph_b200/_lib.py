@@ -1,0 +1,345 @@
+"""ctypes binding of libaquacuda.so (the C-ABI in include/aquacuda.h).
+
+This is the thin Python host used by the tests and bench.py; the C++ host
+(aquagpusph_b200/host) binds the same symbols.  There is no CPU fallback: if the
+library is missing it is built with nvcc, and creating a Context without a CUDA
+device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libaquacuda.so")
+_lib = None
+
+# every symbol include/aquacuda.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "aqc_ctx_create", "aqc_ctx_destroy", "aqc_last_error", "aqc_set_stream", "aqc_get_stream",
+    "aqc_sync", "aqc_launch_count", "aqc_device_sm_count", "aqc_define_round6", "aqc_set_defs",
+    "aqc_alloc", "aqc_free", "aqc_host_alloc", "aqc_host_free", "aqc_memcpy_h2d",
+    "aqc_memcpy_d2h", "aqc_memcpy_d2d", "aqc_fill", "aqc_linklist_build", "aqc_radix_sort",
+    "aqc_scatter_fields", "aqc_reduce", "aqc_kernel_lookup", "aqc_kernel_count",
+    "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
+    "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
+]
+
+OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
+T_F32, T_U32, T_I32, T_VEC2, T_VEC4 = 0, 1, 2, 3, 4
+ARG_ARRAY_IN, ARG_ARRAY_OUT, ARG_SCALAR = 0, 1, 2
+
+
+class Defs(C.Structure):
+    _fields_ = [("dims", C.c_int), ("H", C.c_float), ("CONW", C.c_float), ("CONF", C.c_float),
+                ("SUPPORT", C.c_float), ("DIMS", C.c_float)]
+
+
+class ArgInfo(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_char_p), ("kind", C.c_int)]
+
+
+class AquaError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(_LIBPATH)
+    L.aqc_last_error.restype = C.c_char_p
+    L.aqc_last_error.argtypes = [C.c_void_p]
+    L.aqc_get_stream.restype = C.c_void_p
+    L.aqc_get_stream.argtypes = [C.c_void_p]
+    L.aqc_launch_count.restype = C.c_uint64
+    L.aqc_launch_count.argtypes = [C.c_void_p]
+    L.aqc_define_round6.restype = C.c_float
+    L.aqc_define_round6.argtypes = [C.c_float]
+    L.aqc_kernel_name.restype = C.c_char_p
+    L.aqc_kernel_args.restype = C.POINTER(ArgInfo)
+    L.aqc_kernel_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.aqc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.aqc_ctx_destroy.argtypes = [C.c_void_p]
+    L.aqc_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.aqc_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.aqc_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.aqc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.aqc_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.aqc_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.aqc_set_defs.argtypes = [C.c_void_p, C.POINTER(Defs)]
+    L.aqc_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_sync.argtypes = [C.c_void_p]
+    L.aqc_device_sm_count.argtypes = [C.c_void_p]
+    L.aqc_linklist_build.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_int,
+        C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_void_p,
+        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+    L.aqc_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                 C.c_void_p]
+    L.aqc_scatter_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_size_t)]
+    L.aqc_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                             C.c_void_p]
+    L.aqc_launch.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_int]
+    for n in ("aqc_event_create",):
+        getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    for n in ("aqc_event_destroy", "aqc_event_record", "aqc_event_sync"):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def kernel_table():
+    """[(name, [(argname, type, kind), ...]), ...] of the registry (no GPU needed)."""
+    L = lib()
+    out = []
+    for k in range(L.aqc_kernel_count()):
+        n = L.aqc_kernel_nargs(k)
+        a = L.aqc_kernel_args(k)
+        out.append((L.aqc_kernel_name(k).decode(),
+                    [(a[i].name.decode(), a[i].type.decode(), a[i].kind) for i in range(n)]))
+    return out
+
+
+def define_round6(v):
+    return float(lib().aqc_define_round6(C.c_float(v)))
+
+
+class DevArray:
+    """A device buffer owned through aqc_alloc (ArrayVariable, Variable.cpp:1739-1822)."""
+
+    def __init__(self, ctx, shape, dtype):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        ctx._chk(lib().aqc_alloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self._owned = True
+
+    @property
+    def elem_bytes(self):
+        n = self.shape[0] if self.shape else 1
+        return self.nbytes // max(n, 1)
+
+    def set(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype).reshape(self.shape)
+        self.ctx._chk(lib().aqc_memcpy_h2d(self.ctx.h, self.ptr, host.ctypes.data, self.nbytes, 1))
+        return self
+
+    def get(self):
+        out = np.empty(self.shape, self.dtype)
+        self.ctx._chk(lib().aqc_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.nbytes, 1))
+        return out
+
+    def free(self):
+        if self._owned and self.ptr:
+            lib().aqc_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _scalar_bytes(value, typ, dims):
+    """Pack a python scalar/sequence according to the reference type string."""
+    t = typ.replace("unsigned int", "uint").strip()
+    if t in ("float",):
+        return np.array([value], np.float32).tobytes()
+    if t in ("uint", "usize", "size_t"):
+        return np.array([value], np.uint32).tobytes()
+    if t == "int":
+        return np.array([value], np.int32).tobytes()
+    if t == "vec":
+        v = np.zeros(4 if dims == 3 else 2, np.float32)
+        a = np.asarray(value, np.float32).ravel()
+        v[:min(len(a), len(v))] = a[:len(v)]
+        return v.tobytes()
+    if t in ("svec4", "uivec4"):
+        return np.asarray(value, np.uint32).reshape(4).tobytes()
+    if t == "vec4":
+        return np.asarray(value, np.float32).reshape(4).tobytes()
+    raise AquaError("unsupported scalar type '%s'" % typ)
+
+
+class Context:
+    """One CUDA device + stream (CalcServer::setupOpenCL, CalcServer.cpp:858-886)."""
+
+    def __init__(self, device=0, dims=3, h=None):
+        self.h = C.c_void_p()
+        rc = lib().aqc_ctx_create(int(device), C.byref(self.h))
+        if rc:
+            raise AquaError("aqc_ctx_create failed: %s" % lib().aqc_last_error(None).decode())
+        self.dims = dims
+        self.defs = None
+        if h is not None:
+            self.set_defs_from_h(dims, h)
+
+    def close(self):
+        if self.h:
+            lib().aqc_ctx_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc:
+            raise AquaError("libaquacuda error %d: %s" % (rc, lib().aqc_last_error(self.h).decode()))
+
+    # -- definitions (basic.xml:119-123 evaluated as CalcServer.cpp:245-257 does)
+    def set_defs_from_h(self, dims, h):
+        h32 = float(np.float32(h))
+        d = Defs()
+        d.dims = dims
+        d.H = define_round6(h32)
+        d.CONW = define_round6(float(np.float32(1.0 / (h32 ** dims))))
+        d.CONF = define_round6(float(np.float32(1.0 / (h32 ** (dims + 2)))))
+        d.SUPPORT = 2.0
+        d.DIMS = define_round6(float(dims))
+        self.set_defs(d)
+
+    def set_defs(self, d):
+        self.defs = d
+        self.dims = d.dims
+        self._chk(lib().aqc_set_defs(self.h, C.byref(d)))
+
+    # -- memory
+    def array(self, host):
+        host = np.ascontiguousarray(host)
+        return DevArray(self, host.shape, host.dtype).set(host)
+
+    def empty(self, shape, dtype):
+        return DevArray(self, shape, dtype)
+
+    def zeros(self, shape, dtype):
+        a = DevArray(self, shape, dtype)
+        z = np.zeros(1, np.uint32)
+        self._chk(lib().aqc_fill(self.h, a.ptr, a.nbytes // 4, 4, z.ctypes.data))
+        return a
+
+    def fill(self, arr, value_bytes):
+        eb = len(value_bytes)
+        buf = C.create_string_buffer(value_bytes, eb)
+        self._chk(lib().aqc_fill(self.h, arr.ptr, arr.nbytes // eb, eb, buf))
+
+    def copy(self, dst, src):
+        self._chk(lib().aqc_memcpy_d2d(self.h, dst.ptr, src.ptr, min(dst.nbytes, src.nbytes)))
+
+    def sync(self):
+        self._chk(lib().aqc_sync(self.h))
+
+    def launch_count(self):
+        return int(lib().aqc_launch_count(self.h))
+
+    def sm_count(self):
+        return int(lib().aqc_device_sm_count(self.h))
+
+    # -- tools
+    def linklist(self, r, support, h, icell, ihoc, perm, inv_perm, rmin=None, rmax=None,
+                 recompute=True):
+        """LinkList tool. ihoc is a DevArray that may be replaced (grown); returns
+        (rmin, rmax, ncells, ihoc)."""
+        N = r.shape[0]
+        fmin = (C.c_float * 4)(*(list(rmin) + [0.0] * 4)[:4]) if rmin is not None else (C.c_float * 4)()
+        fmax = (C.c_float * 4)(*(list(rmax) + [0.0] * 4)[:4]) if rmax is not None else (C.c_float * 4)()
+        nc = (C.c_uint32 * 4)()
+        p = C.c_void_p(ihoc.ptr if ihoc is not None else None)
+        cap = C.c_size_t(ihoc.shape[0] if ihoc is not None else 0)
+        self._chk(lib().aqc_linklist_build(self.h, r.ptr, N, self.dims, float(support), float(h),
+                                           1 if recompute else 0, fmin, fmax, nc, icell.ptr,
+                                           C.byref(p), C.byref(cap), perm.ptr, inv_perm.ptr))
+        if ihoc is None or p.value != ihoc.ptr:
+            if ihoc is not None:
+                ihoc.ptr = None  # freed by the library
+            new = DevArray.__new__(DevArray)
+            new.ctx, new.shape, new.dtype = self, (int(cap.value),), np.dtype(np.uint32)
+            new.nbytes, new.ptr, new._owned = int(cap.value) * 4, p.value, True
+            ihoc = new
+        vs = 4 if self.dims == 3 else 2
+        return (np.array(fmin[:vs], np.float32), np.array(fmax[:vs], np.float32),
+                np.array(nc[:], np.uint32), ihoc)
+
+    def radix_sort(self, keys, key_max=0, perm=None, inv_perm=None):
+        self._chk(lib().aqc_radix_sort(self.h, keys.ptr, keys.shape[0], int(key_max),
+                                       perm.ptr if perm is not None else None,
+                                       inv_perm.ptr if inv_perm is not None else None))
+
+    def scatter_fields(self, idx, pairs):
+        """dst[idx[i]] = src[i] for every (src, dst) pair."""
+        n = len(pairs)
+        src = (C.c_void_p * n)(*[s.ptr for s, _ in pairs])
+        dst = (C.c_void_p * n)(*[d.ptr for _, d in pairs])
+        eb = (C.c_size_t * n)(*[s.elem_bytes for s, _ in pairs])
+        self._chk(lib().aqc_scatter_fields(self.h, idx.ptr, idx.shape[0], n, src, dst, eb))
+
+    def reduce(self, op, arr, out_dev=None, host=True):
+        dt = arr.dtype
+        ncomp = arr.shape[1] if len(arr.shape) > 1 else 1
+        if dt == np.float32:
+            typ = {1: T_F32, 2: T_VEC2, 4: T_VEC4}[ncomp]
+        elif dt == np.uint32:
+            typ = T_U32
+        elif dt == np.int32:
+            typ = T_I32
+        else:
+            raise AquaError("reduce: unsupported dtype %s" % dt)
+        out = np.zeros(ncomp, dt)
+        self._chk(lib().aqc_reduce(self.h, op, typ, arr.ptr, arr.shape[0],
+                                   out_dev.ptr if out_dev is not None else None,
+                                   out.ctypes.data if host else None))
+        return out if ncomp > 1 else out[0]
+
+    def lookup(self, script, entry="entry"):
+        kid = lib().aqc_kernel_lookup(script.encode(), entry.encode(), self.dims)
+        if kid < 0:
+            raise AquaError("kernel %s::%s is not in the registry" % (script, entry))
+        return kid
+
+    def launch(self, script, entry, variables, n=None):
+        """Kernel tool: bind arguments by NAME from `variables` (dict name ->
+        DevArray | python scalar), like Kernel.cpp:497-556."""
+        L = lib()
+        kid = self.lookup(script, entry)
+        na = L.aqc_kernel_nargs(kid)
+        info = L.aqc_kernel_args(kid)
+        argv = (C.c_void_p * na)()
+        keep = []
+        for k in range(na):
+            name = info[k].name.decode()
+            if name not in variables:
+                raise AquaError("kernel %s::%s needs variable '%s'" % (script, entry, name))
+            v = variables[name]
+            if info[k].kind == ARG_SCALAR:
+                b = C.create_string_buffer(_scalar_bytes(v, info[k].type.decode(), self.dims))
+                keep.append(b)
+                argv[k] = C.cast(b, C.c_void_p)
+            else:
+                argv[k] = v.ptr
+        if n is None:
+            n = int(variables["N"])
+        self._chk(L.aqc_launch(self.h, kid, int(n), argv, na))
+
+    # -- events
+    def event(self):
+        e = C.c_void_p()
+        self._chk(lib().aqc_event_create(self.h, C.byref(e)))
+        return e
+
+    def record(self, e):
+        self._chk(lib().aqc_event_record(self.h, e))
+
+    def elapsed_ms(self, a, b):
+        self._chk(lib().aqc_event_sync(self.h, b))
+        ms = C.c_float()
+        self._chk(lib().aqc_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,369 @@
+// aqc_api.cu -- context, memory, fill, events and the kernel registry of the
+// C-ABI declared in include/aquacuda.h.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "aqc_common.cuh"
+
+int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+static char g_create_err[512] = "";
+
+extern "C" int aqc_ctx_create(int device, aqc_ctx** out)
+{
+    if (!out)
+        return AQC_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "no usable CUDA device %d (count=%d, %s); libaquacuda has no "
+                 "CPU fallback", device, n,
+                 e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+        return AQC_ERR_CUDA;
+    }
+    aqc_ctx* ctx = new aqc_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "cannot initialise device %d", device);
+        delete ctx;
+        return AQC_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMalloc(&ctx->minmax_dev, 8 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMallocHost(&ctx->minmax_host, 8 * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost(&ctx->red_host, 64) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "cannot allocate context scratch");
+        delete ctx;
+        return AQC_ERR_CUDA;
+    }
+    *out = ctx;
+    return AQC_OK;
+}
+
+extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(ctx->sort_keys[k]);
+        cudaFree(ctx->sort_vals[k]);
+    }
+    cudaFree(ctx->sort_hist);
+    cudaFree(ctx->minmax_dev);
+    cudaFreeHost(ctx->minmax_host);
+    cudaFree(ctx->red_dev);
+    cudaFreeHost(ctx->red_host);
+    if (ctx->own_stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* aqc_last_error(const aqc_ctx* ctx)
+{
+    return ctx ? ctx->err : g_create_err;
+}
+
+extern "C" int aqc_set_stream(aqc_ctx* ctx, void* s)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+    } else {
+        AQC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return AQC_OK;
+}
+
+extern "C" void* aqc_get_stream(aqc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int aqc_sync(aqc_ctx* ctx)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AQC_OK;
+}
+
+extern "C" uint64_t aqc_launch_count(const aqc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int aqc_device_sm_count(const aqc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// CalcServer.cpp:245-257: snprintf("%#G") + "f", parsed back by the compiler.
+extern "C" float aqc_define_round6(float value)
+{
+    char s[128];
+    snprintf(s, sizeof(s), "%#G", (double)value);
+    return strtof(s, nullptr);
+}
+
+extern "C" int aqc_set_defs(aqc_ctx* ctx, const aqc_defs* defs)
+{
+    if (!ctx || !defs || (defs->dims != 2 && defs->dims != 3))
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_set_defs: dims must be 2 or 3");
+    ctx->defs = *defs;
+    return AQC_OK;
+}
+
+extern "C" int aqc_alloc(aqc_ctx* ctx, size_t bytes, void** dptr)
+{
+    if (!ctx || !dptr)
+        return AQC_ERR_ARG;
+    *dptr = nullptr;
+    if (!bytes)
+        bytes = 16;
+    AQC_CUDA(ctx, cudaMalloc(dptr, bytes));
+    return AQC_OK;
+}
+
+extern "C" int aqc_free(aqc_ctx* ctx, void* dptr)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    if (dptr) {
+        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_CUDA(ctx, cudaFree(dptr));
+    }
+    return AQC_OK;
+}
+
+extern "C" int aqc_host_alloc(aqc_ctx* ctx, size_t bytes, void** hptr)
+{
+    if (!ctx || !hptr)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 16));
+    return AQC_OK;
+}
+
+extern "C" int aqc_host_free(aqc_ctx* ctx, void* hptr)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    if (hptr)
+        AQC_CUDA(ctx, cudaFreeHost(hptr));
+    return AQC_OK;
+}
+
+extern "C" int aqc_memcpy_h2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int blocking)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (blocking)
+        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AQC_OK;
+}
+
+extern "C" int aqc_memcpy_d2h(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int blocking)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (blocking)
+        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AQC_OK;
+}
+
+extern "C" int aqc_memcpy_d2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return AQC_OK;
+}
+
+// ---- Set tool -------------------------------------------------------------
+template <typename T>
+__global__ void fill_kernel(T* __restrict__ p, size_t n, T v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+__global__ void fill64_kernel(uint4* __restrict__ p, size_t n4, uint4 a, uint4 b, uint4 c, uint4 d)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned k = (unsigned)(i & 3);
+        p[i] = k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d));
+    }
+}
+
+template <typename T>
+static int fill_launch(aqc_ctx* ctx, void* p, size_t n, const void* value)
+{
+    T v;
+    memcpy(&v, value, sizeof(T));
+    unsigned bs = 256;
+    unsigned grid = aqc_blocks(n, bs);
+    unsigned cap = (unsigned)ctx->sm_count * 16;
+    if (grid > cap)
+        grid = cap;
+    fill_kernel<T><<<grid, bs, 0, ctx->stream>>>((T*)p, n, v);
+    AQC_LAUNCH_CHECK(ctx);
+    return AQC_OK;
+}
+
+extern "C" int aqc_fill(aqc_ctx* ctx, void* dptr, size_t n, size_t elem_bytes, const void* value)
+{
+    if (!ctx || !value)
+        return AQC_ERR_ARG;
+    if (!n)
+        return AQC_OK;
+    switch (elem_bytes) {
+        case 4: return fill_launch<uint32_t>(ctx, dptr, n, value);
+        case 8: return fill_launch<uint2>(ctx, dptr, n, value);
+        case 16: return fill_launch<uint4>(ctx, dptr, n, value);
+        case 64: {
+            // matrix (float16): four uint4 per element
+            uint4 v[4];
+            memcpy(v, value, 64);
+            unsigned grid = aqc_blocks(n * 4, 256);
+            unsigned cap = (unsigned)ctx->sm_count * 16;
+            fill64_kernel<<<grid > cap ? cap : grid, 256, 0, ctx->stream>>>(
+                (uint4*)dptr, n * 4, v[0], v[1], v[2], v[3]);
+            AQC_LAUNCH_CHECK(ctx);
+            return AQC_OK;
+        }
+        default:
+            return aqc_fail(ctx, AQC_ERR_ARG, "aqc_fill: unsupported element size %zu", elem_bytes);
+    }
+}
+
+// ---- events ---------------------------------------------------------------
+extern "C" int aqc_event_create(aqc_ctx* ctx, void** ev)
+{
+    if (!ctx || !ev)
+        return AQC_ERR_ARG;
+    cudaEvent_t e;
+    AQC_CUDA(ctx, cudaEventCreate(&e));
+    *ev = (void*)e;
+    return AQC_OK;
+}
+extern "C" int aqc_event_destroy(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaEventDestroy((cudaEvent_t)ev));
+    return AQC_OK;
+}
+extern "C" int aqc_event_record(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+    return AQC_OK;
+}
+extern "C" int aqc_event_sync(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)ev));
+    return AQC_OK;
+}
+extern "C" int aqc_event_elapsed_ms(aqc_ctx* ctx, void* a, void* b, float* ms)
+{
+    if (!ctx || !ms)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return AQC_OK;
+}
+
+// ---- kernel registry --------------------------------------------------------
+std::vector<aqc_kernel_entry>& aqc_registry()
+{
+    static std::vector<aqc_kernel_entry> reg;
+    return reg;
+}
+
+// Presets name scripts as "../Scripts/cfd/Interactions.cl" (cfd.xml:60) or with
+// an absolute resources path; keep what follows the last "Scripts/".
+static const char* strip_script_path(const char* p)
+{
+    const char* best = p;
+    for (const char* s = p; (s = strstr(s, "Scripts/")) != nullptr; s += 8)
+        best = s + 8;
+    return best;
+}
+
+extern "C" int aqc_kernel_lookup(const char* script_path, const char* entry, int dims)
+{
+    if (!script_path)
+        return AQC_ERR_ARG;
+    const char* rel = strip_script_path(script_path);
+    const char* ent = (entry && *entry) ? entry : "entry"; // State.cpp:1058-1059
+    auto& reg = aqc_registry();
+    for (size_t k = 0; k < reg.size(); k++)
+        if (!strcmp(reg[k].script, rel) && !strcmp(reg[k].entry, ent) &&
+            (reg[k].dims == 0 || reg[k].dims == dims))
+            return (int)k;
+    return AQC_ERR_NOKERNEL;
+}
+
+extern "C" int aqc_kernel_count(void) { return (int)aqc_registry().size(); }
+
+extern "C" const char* aqc_kernel_name(int id)
+{
+    static thread_local std::string s;
+    auto& reg = aqc_registry();
+    if (id < 0 || id >= (int)reg.size())
+        return nullptr;
+    s = std::string(reg[id].script) + "::" + reg[id].entry;
+    return s.c_str();
+}
+
+extern "C" int aqc_kernel_nargs(int id)
+{
+    auto& reg = aqc_registry();
+    if (id < 0 || id >= (int)reg.size())
+        return AQC_ERR_ARG;
+    return (int)reg[id].args.size();
+}
+
+extern "C" const aqc_arg_info* aqc_kernel_args(int id)
+{
+    auto& reg = aqc_registry();
+    if (id < 0 || id >= (int)reg.size())
+        return nullptr;
+    return reg[id].args.data();
+}
+
+extern "C" int aqc_launch(aqc_ctx* ctx, int id, size_t n, void* const* args, int nargs)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    auto& reg = aqc_registry();
+    if (id < 0 || id >= (int)reg.size())
+        return aqc_fail(ctx, AQC_ERR_NOKERNEL, "aqc_launch: bad kernel id %d", id);
+    if (nargs != (int)reg[id].args.size())
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch(%s::%s): expected %zu args, got %d",
+                        reg[id].script, reg[id].entry, reg[id].args.size(), nargs);
+    for (int k = 0; k < nargs; k++)
+        if (!args[k])
+            return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch(%s::%s): argument %d (%s) is NULL",
+                            reg[id].script, reg[id].entry, k, reg[id].args[k].name);
+    if (!n)
+        return AQC_OK;
+    return reg[id].fn(ctx, n, args);
+}

@@ -1,0 +1,95 @@
+// aqc_common.cuh -- internals shared by the translation units of libaquacuda.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "aquacuda.h"
+
+struct aqc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    aqc_defs defs{ 3, 1.f, 1.f, 1.f, 2.f, 3.f };
+    char err[512] = { 0 };
+
+    // link-list scratch (grown on demand, never shrunk)
+    uint32_t* sort_keys[2] = { nullptr, nullptr };
+    uint32_t* sort_vals[2] = { nullptr, nullptr };
+    size_t sort_cap = 0;
+    uint32_t* sort_hist = nullptr; // [256][nblocks] + [256] totals
+    size_t sort_hist_cap = 0;
+    uint32_t* minmax_dev = nullptr; // 8 ordered-uint keys
+    float* minmax_host = nullptr;   // pinned, 8 floats
+    // reduction scratch
+    void* red_dev = nullptr; // partials
+    size_t red_cap = 0;
+    void* red_host = nullptr; // pinned 64 B
+};
+
+int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...);
+
+#define AQC_CUDA(ctx, call)                                                    \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess)                                                \
+            return aqc_fail((ctx), AQC_ERR_CUDA, "%s failed: %s (%s:%d)",      \
+                            #call, cudaGetErrorString(e__), __FILE__,          \
+                            __LINE__);                                         \
+    } while (0)
+
+#define AQC_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        cudaError_t e__ = cudaGetLastError();                                  \
+        if (e__ != cudaSuccess)                                                \
+            return aqc_fail((ctx), AQC_ERR_CUDA, "kernel launch failed: %s "   \
+                            "(%s:%d)", cudaGetErrorString(e__), __FILE__,      \
+                            __LINE__);                                         \
+    } while (0)
+
+static inline unsigned aqc_blocks(size_t n, unsigned bs)
+{
+    return (unsigned)((n + bs - 1) / bs);
+}
+
+// ---- kernel registry (registry.cu) ----------------------------------------
+typedef int (*aqc_launcher)(aqc_ctx* ctx, size_t n, void* const* args);
+struct aqc_kernel_entry {
+    const char* script; // path relative to resources/Scripts/
+    const char* entry;
+    int dims; // 0 = both, 2, 3
+    std::vector<aqc_arg_info> args;
+    aqc_launcher fn;
+};
+std::vector<aqc_kernel_entry>& aqc_registry();
+struct aqc_registrar {
+    aqc_registrar(const char* script, const char* entry, int dims,
+                  std::vector<aqc_arg_info> args, aqc_launcher fn)
+    {
+        aqc_registry().push_back({ script, entry, dims, std::move(args), fn });
+    }
+};
+
+// scalar argument helpers for launchers: args[k] is a host pointer
+template <typename T>
+static inline T aqc_scalar(void* const* args, int k)
+{
+    T v;
+    memcpy(&v, args[k], sizeof(T));
+    return v;
+}
+struct aqc_u4 { uint32_t x, y, z, w; };
+struct aqc_f4 { float x, y, z, w; };
+// vec scalar (g, domain_min, ...): 2 floats in 2-D, 4 in 3-D; returned padded
+static inline aqc_f4 aqc_vec_scalar(void* const* args, int k, int dims)
+{
+    aqc_f4 v{ 0.f, 0.f, 0.f, 0.f };
+    memcpy(&v, args[k], sizeof(float) * (dims == 3 ? 4 : 2));
+    return v;
+}

@@ -1,0 +1,805 @@
+// elementwise.cu -- the per-particle (no neighbour loop) script kernels of the
+// hot path, one HBM pass each, with their Kernel-tool registry entries.
+// Compiled with -fmad=false: these kernels are bandwidth bound, so keeping the
+// reference's operation order without FMA contraction is free and makes them
+// bit-exact against the (uncontracted) oracle.
+//
+// vec = float4 in 3-D (w carried along exactly as the OpenCL float4 arithmetic
+// does), float2 in 2-D.
+#include <math.h>
+
+#include "aqc_common.cuh"
+
+namespace {
+
+template <int D> struct V;
+template <> struct V<3> {
+    float4 v;
+    __device__ V() {}
+    __device__ V(float4 a) : v(a) {}
+    __device__ static V splat(float s) { return V(make_float4(s, s, s, s)); }
+    __device__ static V ld(const void* p, size_t i) { return V(reinterpret_cast<const float4*>(p)[i]); }
+    __device__ void st(void* p, size_t i) const { reinterpret_cast<float4*>(p)[i] = v; }
+    __device__ float dot(const V& o) const { return v.x * o.v.x + v.y * o.v.y + v.z * o.v.z + v.w * o.v.w; }
+};
+template <> struct V<2> {
+    float2 v;
+    __device__ V() {}
+    __device__ V(float2 a) : v(a) {}
+    __device__ static V splat(float s) { return V(make_float2(s, s)); }
+    __device__ static V ld(const void* p, size_t i) { return V(reinterpret_cast<const float2*>(p)[i]); }
+    __device__ void st(void* p, size_t i) const { reinterpret_cast<float2*>(p)[i] = v; }
+    __device__ float dot(const V& o) const { return v.x * o.v.x + v.y * o.v.y; }
+};
+__device__ inline V<3> operator+(V<3> a, V<3> b) { return V<3>(make_float4(a.v.x + b.v.x, a.v.y + b.v.y, a.v.z + b.v.z, a.v.w + b.v.w)); }
+__device__ inline V<3> operator-(V<3> a, V<3> b) { return V<3>(make_float4(a.v.x - b.v.x, a.v.y - b.v.y, a.v.z - b.v.z, a.v.w - b.v.w)); }
+__device__ inline V<3> operator*(float s, V<3> a) { return V<3>(make_float4(s * a.v.x, s * a.v.y, s * a.v.z, s * a.v.w)); }
+__device__ inline V<3> operator/(V<3> a, float s) { return V<3>(make_float4(a.v.x / s, a.v.y / s, a.v.z / s, a.v.w / s)); }
+__device__ inline V<3> operator-(V<3> a) { return V<3>(make_float4(-a.v.x, -a.v.y, -a.v.z, -a.v.w)); }
+__device__ inline V<2> operator+(V<2> a, V<2> b) { return V<2>(make_float2(a.v.x + b.v.x, a.v.y + b.v.y)); }
+__device__ inline V<2> operator-(V<2> a, V<2> b) { return V<2>(make_float2(a.v.x - b.v.x, a.v.y - b.v.y)); }
+__device__ inline V<2> operator*(float s, V<2> a) { return V<2>(make_float2(s * a.v.x, s * a.v.y)); }
+__device__ inline V<2> operator/(V<2> a, float s) { return V<2>(make_float2(a.v.x / s, a.v.y / s)); }
+__device__ inline V<2> operator-(V<2> a) { return V<2>(make_float2(-a.v.x, -a.v.y)); }
+
+template <int D> __device__ V<D> from_f4(aqc_f4 g);
+template <> __device__ inline V<3> from_f4<3>(aqc_f4 g) { V<3> r; r.v = make_float4(g.x, g.y, g.z, g.w); return r; }
+template <> __device__ inline V<2> from_f4<2>(aqc_f4 g) { V<2> r; r.v = make_float2(g.x, g.y); return r; }
+
+#define GID                                                                     \
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;            \
+    if (i >= N)                                                                 \
+        return;
+
+#define LAUNCH(ctx, KERNEL, N, ...)                                            \
+    do {                                                                       \
+        KERNEL<<<aqc_blocks((N), 256), 256, 0, (ctx)->stream>>>(__VA_ARGS__);  \
+        AQC_LAUNCH_CHECK(ctx);                                                 \
+    } while (0)
+
+#define DISPATCH(ctx, KERNEL, N, ...)                                          \
+    do {                                                                       \
+        if ((ctx)->defs.dims == 3)                                             \
+            LAUNCH(ctx, KERNEL<3>, N, __VA_ARGS__);                            \
+        else                                                                   \
+            LAUNCH(ctx, KERNEL<2>, N, __VA_ARGS__);                            \
+        return AQC_OK;                                                         \
+    } while (0)
+
+// ---- basic/time_scheme/euler.cl:65-87 and midpoint.cl:53-75 (same body) -------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_copy_state(const void* r, const void* u, const void* dudt, const float* rho,
+             const float* drhodt, void* r_in, void* u_in, void* dudt_in, float* rho_in,
+             float* drhodt_in, uint32_t N)
+{
+    GID;
+    V<D>::ld(dudt, i).st(dudt_in, i);
+    V<D>::ld(u, i).st(u_in, i);
+    V<D>::ld(r, i).st(r_in, i);
+    drhodt_in[i] = drhodt[i];
+    rho_in[i] = rho[i];
+}
+int l_copy_state(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 10);
+    DISPATCH(c, k_copy_state, N, a[0], a[1], a[2], (const float*)a[3], (const float*)a[4], a[5],
+             a[6], a[7], (float*)a[8], (float*)a[9], N);
+}
+
+// ---- basic/time_scheme/euler.cl:105-124 ------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_euler_corrector(const int* imove, void* r, void* u, const void* dudt, float* rho,
+                  const float* drhodt, uint32_t N, float dt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    const V<D> U = V<D>::ld(u, i), A = V<D>::ld(dudt, i);
+    (V<D>::ld(r, i) + (dt * U + (0.5f * dt * dt) * A)).st(r, i);
+    (U + dt * A).st(u, i);
+    rho[i] = rho[i] + dt * drhodt[i];
+}
+int l_euler_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 7);
+    DISPATCH(c, k_euler_corrector, N, (const int*)a[0], a[2], a[3], a[4], (float*)a[5],
+             (const float*)a[6], N, aqc_scalar<float>(a, 8));
+}
+
+// ---- basic/time_scheme/improved_euler.cl:75-103 ----------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ie_predictor(const int* imove, const void* r, const void* u, const void* dudt,
+               const float* rho, const float* drhodt, void* r_in, void* u_in, void* dudt_in,
+               float* rho_in, float* drhodt_in, uint32_t N, float dt)
+{
+    GID;
+    const float DT = (imove[i] <= 0) ? 0.f : dt;
+    const V<D> A = V<D>::ld(dudt, i), U = V<D>::ld(u, i), R = V<D>::ld(r, i);
+    A.st(dudt_in, i);
+    (U + DT * A).st(u_in, i);
+    ((R + DT * U) + (0.5f * DT * DT) * A).st(r_in, i);
+    const float dr = drhodt[i];
+    drhodt_in[i] = dr;
+    rho_in[i] = rho[i] + DT * dr;
+}
+int l_ie_predictor(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 11);
+    DISPATCH(c, k_ie_predictor, N, (const int*)a[0], a[1], a[2], a[3], (const float*)a[4],
+             (const float*)a[5], a[6], a[7], a[8], (float*)a[9], (float*)a[10], N,
+             aqc_scalar<float>(a, 12));
+}
+
+// ---- basic/time_scheme/improved_euler.cl:125-147 ---------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ie_corrector(const int* imove, void* r, void* u, const void* dudt, float* rho,
+               const float* drhodt, const void* dudt_in, const float* drhodt_in, uint32_t N,
+               float dt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    const float DT = 0.5f * dt;
+    const V<D> dA = V<D>::ld(dudt, i) - V<D>::ld(dudt_in, i);
+    (V<D>::ld(u, i) + DT * dA).st(u, i);
+    (V<D>::ld(r, i) + (DT * DT) * dA).st(r, i);
+    rho[i] = rho[i] + DT * (drhodt[i] - drhodt_in[i]);
+}
+int l_ie_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 9);
+    DISPATCH(c, k_ie_corrector, N, (const int*)a[0], a[2], a[3], a[4], (float*)a[5],
+             (const float*)a[6], a[7], (const float*)a[8], N, aqc_scalar<float>(a, 10));
+}
+
+// ---- basic/time_scheme/midpoint.cl:93-111 ----------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mp_midpoint(const int* imove, const void* u_in, void* u, const void* dudt,
+              const float* rho_in, float* rho, const float* drhodt, uint32_t N, float dt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    (V<D>::ld(u_in, i) + (0.5f * dt) * V<D>::ld(dudt, i)).st(u, i);
+    rho[i] = rho_in[i] + 0.5f * dt * drhodt[i];
+}
+int l_mp_midpoint(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 7);
+    DISPATCH(c, k_mp_midpoint, N, (const int*)a[0], a[1], a[2], a[3], (const float*)a[4],
+             (float*)a[5], (const float*)a[6], N, aqc_scalar<float>(a, 8));
+}
+
+// ---- basic/time_scheme/midpoint.cl:124-138 ---------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mp_midpoint_r(const int* imove, const void* r_in, void* r, const void* u, uint32_t N, float dt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    (V<D>::ld(r_in, i) + (0.5f * dt) * V<D>::ld(u, i)).st(r, i);
+}
+int l_mp_midpoint_r(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    DISPATCH(c, k_mp_midpoint_r, N, (const int*)a[0], a[1], a[2], a[3], N, aqc_scalar<float>(a, 5));
+}
+
+// ---- basic/time_scheme/midpoint.cl:141-157 ---------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mp_relax(const int* imove, const void* dudt_in, void* dudt, const float* drhodt_in,
+           float* drhodt, uint32_t N, float f)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    (f * V<D>::ld(dudt_in, i) + (1.f - f) * V<D>::ld(dudt, i)).st(dudt, i);
+    drhodt[i] = f * drhodt_in[i] + (1.f - f) * drhodt[i];
+}
+int l_mp_relax(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    DISPATCH(c, k_mp_relax, N, (const int*)a[0], a[1], a[2], (const float*)a[3], (float*)a[4], N,
+             aqc_scalar<float>(a, 6));
+}
+
+// ---- basic/time_scheme/midpoint.cl:159-184 ---------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mp_residuals(const int* imove, const float* m, const void* u, const void* dudt_in,
+               const void* dudt, const float* rho, const float* p, const float* drhodt_in,
+               const float* drhodt, float* res, uint32_t N)
+{
+    GID;
+    if (imove[i] <= 0) {
+        res[i] = 0.f;
+        return;
+    }
+    const float rho2 = rho[i] * rho[i];
+    res[i] = m[i] * (fabsf(V<D>::ld(u, i).dot(V<D>::ld(dudt, i) - V<D>::ld(dudt_in, i))) +
+                     fabsf(p[i] / rho2 * (drhodt[i] - drhodt_in[i])));
+}
+int l_mp_residuals(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 10);
+    DISPATCH(c, k_mp_residuals, N, (const int*)a[0], (const float*)a[1], a[2], a[3], a[4],
+             (const float*)a[5], (const float*)a[6], (const float*)a[7], (const float*)a[8],
+             (float*)a[9], N);
+}
+
+// ---- basic/time_scheme/midpoint.cl:206-227 ---------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mp_corrector(const int* imove, const void* r_in, void* r, const void* u_in, void* u,
+               const void* dudt, const float* rho_in, float* rho, const float* drhodt, uint32_t N,
+               float dt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    const V<D> U0 = V<D>::ld(u_in, i), A = V<D>::ld(dudt, i);
+    ((V<D>::ld(r_in, i) + dt * U0) + (0.5f * dt * dt) * A).st(r, i);
+    (U0 + dt * A).st(u, i);
+    rho[i] = rho_in[i] + dt * drhodt[i];
+}
+int l_mp_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 9);
+    DISPATCH(c, k_mp_corrector, N, (const int*)a[0], a[1], a[2], a[3], a[4], a[5],
+             (const float*)a[6], (float*)a[7], (const float*)a[8], N, aqc_scalar<float>(a, 10));
+}
+
+// ---- basic/Domain.cl:48-90 ---------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_domain(int* imove, void* r_in, void* u_in, void* dudt_in, float* m, uint32_t N, aqc_f4 dmin,
+         aqc_f4 dmax)
+{
+    GID;
+    if (imove[i] <= -255)
+        return;
+    const V<D> c = V<D>::ld(r_in, i);
+    bool out = isnan(c.v.x) || isinf(c.v.x) || isnan(c.v.y) || isinf(c.v.y) || (c.v.x < dmin.x) ||
+               (c.v.y < dmin.y) || (c.v.x > dmax.x) || (c.v.y > dmax.y);
+    if constexpr (D == 3)
+        out = out || isnan(c.v.z) || isinf(c.v.z) || (c.v.z < dmin.z) || (c.v.z > dmax.z);
+    if (!out)
+        return;
+    imove[i] = -256;
+    m[i] = 0.f;
+    V<D>::splat(0.f).st(u_in, i);
+    V<D>::splat(0.f).st(dudt_in, i);
+    from_f4<D>(dmax).st(r_in, i);
+}
+int l_domain(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_domain, N, (int*)a[0], a[1], a[2], a[3], (float*)a[4], N,
+             aqc_vec_scalar(a, 6, d), aqc_vec_scalar(a, 7, d));
+}
+
+// ---- basic/Sort.cl:57-78 (stage1) and :102-124 (stage2) ----------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sort_stage1(const uint32_t* id_in, uint32_t* id, const uint32_t* iset_in, uint32_t* iset,
+              const int* imove_in, int* imove, const void* r_in, void* r, const void* normal_in,
+              void* normal, const void* tangent_in, void* tangent, const uint32_t* id_sorted,
+              uint32_t N)
+{
+    GID;
+    const uint32_t o = id_sorted[i];
+    id[o] = id_in[i];
+    iset[o] = iset_in[i];
+    imove[o] = imove_in[i];
+    V<D>::ld(r_in, i).st(r, o);
+    V<D>::ld(normal_in, i).st(normal, o);
+    V<D>::ld(tangent_in, i).st(tangent, o);
+}
+int l_sort_stage1(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 13);
+    DISPATCH(c, k_sort_stage1, N, (const uint32_t*)a[0], (uint32_t*)a[1], (const uint32_t*)a[2],
+             (uint32_t*)a[3], (const int*)a[4], (int*)a[5], a[6], a[7], a[8], a[9], a[10], a[11],
+             (const uint32_t*)a[12], N);
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sort_stage2(const float* rho_in, float* rho, const float* m_in, float* m, const void* u_in,
+              void* u, const void* dudt, void* dudt_in, const float* drhodt, float* drhodt_in,
+              const uint32_t* id_sorted, uint32_t N)
+{
+    GID;
+    const uint32_t o = id_sorted[i];
+    rho[o] = rho_in[i];
+    m[o] = m_in[i];
+    V<D>::ld(u_in, i).st(u, o);
+    // the rates travel the other way round (Sort.cl:119-123)
+    V<D>::ld(dudt, i).st(dudt_in, o);
+    drhodt_in[o] = drhodt[i];
+}
+int l_sort_stage2(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 11);
+    DISPATCH(c, k_sort_stage2, N, (const float*)a[0], (float*)a[1], (const float*)a[2],
+             (float*)a[3], a[4], a[5], a[6], a[7], (const float*)a[8], (float*)a[9],
+             (const uint32_t*)a[10], N);
+}
+
+// ---- basic/EOS.cl:57-73 ------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_eos(const uint32_t* iset, const int* imove, const float* rho, float* p, const float* refd,
+      uint32_t N, float cs, float p0)
+{
+    GID;
+    const int mv = imove[i];
+    if ((mv <= 0) && (mv != -1))
+        return;
+    p[i] = p0 + cs * cs * (rho[i] - refd[iset[i]]);
+}
+int l_eos(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    LAUNCH(c, k_eos, N, (const uint32_t*)a[0], (const int*)a[1], (const float*)a[2], (float*)a[3],
+           (const float*)a[4], N, aqc_scalar<float>(a, 6), aqc_scalar<float>(a, 7));
+    return AQC_OK;
+}
+
+// ---- basic/Binormal.cl:37-53 -------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_binormal(const void* normal, void* tangent, void* binormal, uint32_t N)
+{
+    GID;
+    if constexpr (D == 2) {
+        const float2 n = reinterpret_cast<const float2*>(normal)[i];
+        reinterpret_cast<float2*>(binormal)[i] = make_float2(0.f, 0.f);
+        reinterpret_cast<float2*>(tangent)[i] = make_float2(n.y, -n.x);
+    } else {
+        const float4 a = reinterpret_cast<const float4*>(normal)[i];
+        const float4 b = reinterpret_cast<const float4*>(tangent)[i];
+        reinterpret_cast<float4*>(binormal)[i] =
+            make_float4(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x, 0.f);
+    }
+}
+int l_binormal(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    DISPATCH(c, k_binormal, N, a[0], a[1], a[2], N);
+}
+
+// ---- cfd/Rates.cl:55-77 ------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_rates(const uint32_t* iset, const int* imove, const void* grad_p, const void* lap_u,
+        const float* div_u, void* dudt, float* drhodt, const float* visc_dyn, uint32_t N, aqc_f4 g)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    ((-V<D>::ld(grad_p, i) + visc_dyn[iset[i]] * V<D>::ld(lap_u, i)) + from_f4<D>(g)).st(dudt, i);
+    drhodt[i] = -div_u[i];
+}
+int l_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 9);
+    DISPATCH(c, k_rates, N, (const uint32_t*)a[0], (const int*)a[1], a[3], a[4],
+             (const float*)a[5], a[6], (float*)a[7], (const float*)a[8], N,
+             aqc_vec_scalar(a, 10, c->defs.dims));
+}
+
+// ---- cfd/TimeStep.cl:56-77 ---------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_timestep(const int* imove, const void* u, float* dt_var, uint32_t N, float dt, float dt_min,
+           float courant, float dt_Ma, float h)
+{
+    GID;
+    if (imove[i] <= 0) {
+        dt_var[i] = dt;
+        return;
+    }
+    const V<D> U = V<D>::ld(u, i);
+    const float dr_max = dt_Ma * h;
+    const float dt_u = courant * dr_max / sqrtf(U.dot(U));
+    dt_var[i] = fmaxf(fminf(dt, dt_u), dt_min);
+}
+int l_timestep(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    DISPATCH(c, k_timestep, N, (const int*)a[0], a[1], (float*)a[2], N, aqc_scalar<float>(a, 4),
+             aqc_scalar<float>(a, 5), aqc_scalar<float>(a, 6), aqc_scalar<float>(a, 7),
+             aqc_scalar<float>(a, 8));
+}
+
+// ---- cfd/SensorsRenormalization.cl:42-67 -------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sensors_renorm(const int* imove, const float* shepard, void* u, float* rho, float* p, uint32_t N)
+{
+    GID;
+    if (imove[i] != 0)
+        return;
+    float s = shepard[i];
+    if (s < 1.0E-6f)
+        s = 1.f;
+    (V<D>::ld(u, i) / s).st(u, i);
+    rho[i] = rho[i] / s;
+    p[i] = p[i] / s;
+}
+int l_sensors_renorm(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    DISPATCH(c, k_sensors_renorm, N, (const int*)a[0], (const float*)a[1], a[2], (float*)a[3],
+             (float*)a[4], N);
+}
+
+// ---- basic/deltaSPH.cl:57-71 (simple), :160-173 (full_mls), :330-350 (deltaSPH) -----
+template <int D>
+__global__ void __launch_bounds__(256)
+k_dsph_simple(const uint32_t* iset, const int* imove, void* lap_p_corr, const float* refd,
+              uint32_t N, aqc_f4 g)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    (refd[iset[i]] * from_f4<D>(g)).st(lap_p_corr, i);
+}
+int l_dsph_simple(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    DISPATCH(c, k_dsph_simple, N, (const uint32_t*)a[0], (const int*)a[1], a[2],
+             (const float*)a[3], N, aqc_vec_scalar(a, 5, c->defs.dims));
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_dsph_full_mls(const int* imove, const float* mls, void* lap_p_corr, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    if constexpr (D == 3) {
+        const float4* M = reinterpret_cast<const float4*>(mls) + 4 * i;
+        const float4 a = M[0], b = M[1], c = M[2];
+        const float4 v = reinterpret_cast<const float4*>(lap_p_corr)[i];
+        reinterpret_cast<float4*>(lap_p_corr)[i] =
+            make_float4(a.x * v.x + a.y * v.y + a.z * v.z, b.x * v.x + b.y * v.y + b.z * v.z,
+                        c.x * v.x + c.y * v.y + c.z * v.z, 0.f);
+    } else {
+        const float4 M = reinterpret_cast<const float4*>(mls)[i];
+        const float2 v = reinterpret_cast<const float2*>(lap_p_corr)[i];
+        reinterpret_cast<float2*>(lap_p_corr)[i] =
+            make_float2(M.x * v.x + M.y * v.y, M.z * v.x + M.w * v.y);
+    }
+}
+int l_dsph_full_mls(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    DISPATCH(c, k_dsph_full_mls, N, (const int*)a[0], (const float*)a[1], a[2], N);
+}
+__global__ void __launch_bounds__(256)
+k_dsph_apply(const uint32_t* iset, const int* imove, const float* rho, const float* lap_p,
+             float* drhodt, const float* refd, const float* delta, uint32_t N, float dt)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const uint32_t s = iset[i];
+    const float delta_f = delta[s] * dt * rho[i] / refd[s];
+    drhodt[i] = drhodt[i] + delta_f * lap_p[i];
+}
+int l_dsph_apply(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 7);
+    LAUNCH(c, k_dsph_apply, N, (const uint32_t*)a[0], (const int*)a[1], (const float*)a[2],
+           (const float*)a[3], (float*)a[4], (const float*)a[5], (const float*)a[6], N,
+           aqc_scalar<float>(a, 8));
+    return AQC_OK;
+}
+
+// ---- basic/MLS.cl:130-143 (mls_inv); types/3D.h:300-341, 2D.h:250-282 ---------------
+__device__ inline void mat3_mul(const float* A, const float* B, float* C)
+{
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+            C[a * 3 + b] = A[a * 3 + 0] * B[0 * 3 + b] + A[a * 3 + 1] * B[1 * 3 + b] +
+                           A[a * 3 + 2] * B[2 * 3 + b];
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mls_inv(const int* imove, float* mls, uint32_t N, uint32_t mls_imove)
+{
+    GID;
+    if ((uint32_t)imove[i] != mls_imove)
+        return;
+    if constexpr (D == 3) {
+        float4* Mp = reinterpret_cast<float4*>(mls) + 4 * i;
+        const float4 r0 = Mp[0], r1 = Mp[1], r2 = Mp[2];
+        const float M[9] = { r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z };
+        float T[9], m[9], I[9], R[9];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+                T[a * 3 + b] = M[b * 3 + a];
+        mat3_mul(T, M, m);
+        const float det = m[0] * (m[4] * m[8] - m[5] * m[7]) + m[1] * (m[5] * m[6] - m[3] * m[8]) +
+                          m[2] * (m[3] * m[7] - m[4] * m[6]);
+        const float d = 1.f / det;
+        if (fabsf(d) > 1.e16f) {
+            I[0] = 1.f; I[1] = 0.f; I[2] = 0.f; I[3] = 0.f; I[4] = 1.f; I[5] = 0.f;
+            I[6] = 0.f; I[7] = 0.f; I[8] = 1.f;
+        } else {
+            I[0] = (m[4] * m[8] - m[5] * m[7]) * d;
+            I[1] = (m[2] * m[7] - m[1] * m[8]) * d;
+            I[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+            I[3] = (m[5] * m[6] - m[3] * m[8]) * d;
+            I[4] = (m[0] * m[8] - m[2] * m[6]) * d;
+            I[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+            I[6] = (m[3] * m[7] - m[4] * m[6]) * d;
+            I[7] = (m[1] * m[6] - m[0] * m[7]) * d;
+            I[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+        }
+        mat3_mul(I, T, R);
+        Mp[0] = make_float4(R[0], R[1], R[2], 0.f);
+        Mp[1] = make_float4(R[3], R[4], R[5], 0.f);
+        Mp[2] = make_float4(R[6], R[7], R[8], 0.f);
+        Mp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        float4* Mp = reinterpret_cast<float4*>(mls) + i;
+        const float4 M = *Mp;
+        const float T0 = M.x, T1 = M.z, T2 = M.y, T3 = M.w; // M.s0213
+        const float a = T0 * M.x + T1 * M.z, b = T0 * M.y + T1 * M.w, c = T2 * M.x + T3 * M.z,
+                    e = T2 * M.y + T3 * M.w;
+        const float d = 1.f / (a * e - b * c);
+        float I0, I1, I2, I3;
+        if (fabsf(d) > 1.e16f) {
+            I0 = 1.f; I1 = 0.f; I2 = 0.f; I3 = 1.f;
+        } else {
+            I0 = e * d; I1 = -b * d; I2 = -c * d; I3 = a * d;
+        }
+        *Mp = make_float4(I0 * T0 + I1 * T2, I0 * T1 + I1 * T3, I2 * T0 + I3 * T2,
+                          I2 * T1 + I3 * T3);
+    }
+}
+int l_mls_inv(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    DISPATCH(c, k_mls_inv, N, (const int*)a[0], (float*)a[1], N, aqc_scalar<uint32_t>(a, 3));
+}
+
+// ---- cfd/Boundary/BIe/Rates.cl:44-62, 76-91, 109-135 --------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_bie_rates(const int* imove, const float* rho, const float* p, const void* u,
+            const void* grad_w_bi, const float* div_u_bi, void* grad_p, float* div_u, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const V<D> G = V<D>::ld(grad_w_bi, i);
+    (V<D>::ld(grad_p, i) + (2.f * p[i] / rho[i]) * G).st(grad_p, i);
+    div_u[i] = div_u[i] - 2.f * rho[i] * (V<D>::ld(u, i).dot(G) + div_u_bi[i]);
+}
+int l_bie_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    DISPATCH(c, k_bie_rates, N, (const int*)a[0], (const float*)a[1], (const float*)a[2], a[3],
+             a[4], (const float*)a[5], a[6], (float*)a[7], N);
+}
+__global__ void __launch_bounds__(256)
+k_bie_filter_press(const uint32_t* iset, const int* imove, float* p, uint32_t forces_iset,
+                   uint32_t N)
+{
+    GID;
+    if (imove[i] != -3)
+        return;
+    if (iset[i] != forces_iset)
+        p[i] = 0.f;
+}
+int l_bie_filter_press(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_bie_filter_press, N, (const uint32_t*)a[0], (const int*)a[1], (float*)a[2],
+           aqc_scalar<uint32_t>(a, 3), N);
+    return AQC_OK;
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_bie_force_press(const int* imove, const void* r, const void* normal, const float* m,
+                  const float* p, void* force_p, float4* moment_p, aqc_f4 fr, uint32_t N)
+{
+    GID;
+    if (imove[i] != -3) {
+        V<D>::splat(0.f).st(force_p, i);
+        moment_p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float pm = p[i] * m[i];
+    if constexpr (D == 3) {
+        const float4 n = reinterpret_cast<const float4*>(normal)[i];
+        const float4 rr = reinterpret_cast<const float4*>(r)[i];
+        const float Fx = pm * n.x, Fy = pm * n.y, Fz = pm * n.z;
+        const float Rx = rr.x - fr.x, Ry = rr.y - fr.y, Rz = rr.z - fr.z;
+        float* f = reinterpret_cast<float*>(force_p) + 4 * i;
+        f[0] = Fx; f[1] = Fy; f[2] = Fz; // force_p[i].XYZ = F.XYZ (w untouched)
+        moment_p[i] = make_float4(Ry * Fz - Rz * Fy, Rz * Fx - Rx * Fz, Rx * Fy - Ry * Fx, 0.f);
+    } else {
+        const float2 n = reinterpret_cast<const float2*>(normal)[i];
+        const float2 rr = reinterpret_cast<const float2*>(r)[i];
+        const float Fx = pm * n.x, Fy = pm * n.y;
+        const float Rx = rr.x - fr.x, Ry = rr.y - fr.y;
+        reinterpret_cast<float2*>(force_p)[i] = make_float2(Fx, Fy);
+        moment_p[i] = make_float4(Ry * 0.f - 0.f * Fy, 0.f * Fx - Rx * 0.f, Rx * Fy - Ry * Fx, 0.f);
+    }
+}
+int l_bie_force_press(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    DISPATCH(c, k_bie_force_press, N, (const int*)a[0], a[1], a[2], (const float*)a[3],
+             (const float*)a[4], a[5], (float4*)a[6], aqc_vec_scalar(a, 7, c->defs.dims), N);
+}
+
+// ---- cfd/Boundary/BIe/ElasticBounce.cl:168-184 (force_bound) ------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_bie_force_bound(const int* imove, const float* m, const void* pre, const void* post,
+                  void* force, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1) {
+        V<D>::splat(0.f).st(force, i);
+        return;
+    }
+    ((-m[i]) * (V<D>::ld(post, i) - V<D>::ld(pre, i))).st(force, i);
+}
+int l_bie_force_bound(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    DISPATCH(c, k_bie_force_bound, N, (const int*)a[0], (const float*)a[1], a[2], a[3], a[4], N);
+}
+
+// ---- basic/SetBuffer.cl:37-49 (count), :64-73 (set_imove) ---------------------------
+__global__ void __launch_bounds__(256)
+k_setbuffer_count(const int* imove, uint32_t* ibuffer, uint32_t N)
+{
+    GID;
+    ibuffer[i] = (imove[i] == -255) ? 1u : 0u;
+}
+int l_setbuffer_count(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    LAUNCH(c, k_setbuffer_count, N, (const int*)a[0], (uint32_t*)a[1], N);
+    return AQC_OK;
+}
+__global__ void __launch_bounds__(256)
+k_setbuffer_set_imove(int* imove, uint32_t N)
+{
+    GID;
+    if (imove[i] == -256)
+        imove[i] = -255;
+}
+int l_setbuffer_set_imove(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 1);
+    LAUNCH(c, k_setbuffer_set_imove, N, (int*)a[0], N);
+    return AQC_OK;
+}
+
+#define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
+#define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
+#define SC(n, t) { n, t, AQC_ARG_SCALAR }
+
+#define STATE_COPY_ARGS                                                          \
+    { IN("r", "vec*"), IN("u", "vec*"), IN("dudt", "vec*"), IN("rho", "float*"),   \
+      IN("drhodt", "float*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"),            \
+      OUT("dudt_in", "vec*"), OUT("rho_in", "float*"), OUT("drhodt_in", "float*"), \
+      SC("N", "usize") }
+aqc_registrar r_eu_p("basic/time_scheme/euler.cl", "predictor", 0, STATE_COPY_ARGS, l_copy_state);
+aqc_registrar r_mp_p("basic/time_scheme/midpoint.cl", "predictor", 0, STATE_COPY_ARGS, l_copy_state);
+aqc_registrar r_eu_c("basic/time_scheme/euler.cl", "corrector", 0,
+    { OUT("imove", "int*"), OUT("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"),
+      OUT("dudt", "vec*"), OUT("rho", "float*"), OUT("drhodt", "float*"), SC("N", "usize"),
+      SC("dt", "float") }, l_euler_corrector);
+aqc_registrar r_ie_p("basic/time_scheme/improved_euler.cl", "predictor", 0,
+    { OUT("imove", "int*"), OUT("r", "vec*"), OUT("u", "vec*"), OUT("dudt", "vec*"),
+      OUT("rho", "float*"), OUT("drhodt", "float*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"),
+      OUT("dudt_in", "vec*"), OUT("rho_in", "float*"), OUT("drhodt_in", "float*"),
+      SC("N", "usize"), SC("dt", "float") }, l_ie_predictor);
+aqc_registrar r_ie_c("basic/time_scheme/improved_euler.cl", "corrector", 0,
+    { OUT("imove", "int*"), OUT("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"),
+      OUT("dudt", "vec*"), OUT("rho", "float*"), OUT("drhodt", "float*"), OUT("dudt_in", "vec*"),
+      OUT("drhodt_in", "float*"), SC("N", "usize"), SC("dt", "float") }, l_ie_corrector);
+aqc_registrar r_mp_m("basic/time_scheme/midpoint.cl", "midpoint", 0,
+    { IN("imove", "int*"), IN("u_in", "vec*"), OUT("u", "vec*"), IN("dudt", "vec*"),
+      IN("rho_in", "float*"), OUT("rho", "float*"), IN("drhodt", "float*"), SC("N", "usize"),
+      SC("dt", "float") }, l_mp_midpoint);
+aqc_registrar r_mp_mr("basic/time_scheme/midpoint.cl", "midpoint_r", 0,
+    { IN("imove", "int*"), IN("r_in", "vec*"), OUT("r", "vec*"), IN("u", "vec*"), SC("N", "usize"),
+      SC("dt", "float") }, l_mp_midpoint_r);
+aqc_registrar r_mp_rx("basic/time_scheme/midpoint.cl", "relax", 0,
+    { IN("imove", "int*"), OUT("dudt_in", "vec*"), OUT("dudt", "vec*"), OUT("drhodt_in", "float*"),
+      OUT("drhodt", "float*"), SC("N", "usize"), SC("relax_midpoint", "float") }, l_mp_relax);
+aqc_registrar r_mp_rs("basic/time_scheme/midpoint.cl", "residuals", 0,
+    { IN("imove", "int*"), IN("m", "float*"), IN("u", "vec*"), IN("dudt_in", "vec*"),
+      IN("dudt", "vec*"), IN("rho", "float*"), IN("p", "float*"), IN("drhodt_in", "float*"),
+      IN("drhodt", "float*"), OUT("residual_midpoint", "float*"), SC("N", "usize") },
+    l_mp_residuals);
+aqc_registrar r_mp_c("basic/time_scheme/midpoint.cl", "corrector", 0,
+    { IN("imove", "int*"), IN("r_in", "vec*"), OUT("r", "vec*"), IN("u_in", "vec*"),
+      OUT("u", "vec*"), IN("dudt", "vec*"), IN("rho_in", "float*"), OUT("rho", "float*"),
+      IN("drhodt", "float*"), SC("N", "usize"), SC("dt", "float") }, l_mp_corrector);
+aqc_registrar r_domain("basic/Domain.cl", "entry", 0,
+    { OUT("imove", "int*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"),
+      OUT("m", "float*"), SC("N", "usize"), SC("domain_min", "vec"), SC("domain_max", "vec") },
+    l_domain);
+aqc_registrar r_sort1("basic/Sort.cl", "stage1", 0,
+    { IN("id_in", "usize*"), OUT("id", "usize*"), IN("iset_in", "uint*"), OUT("iset", "uint*"),
+      IN("imove_in", "int*"), OUT("imove", "int*"), IN("r_in", "vec*"), OUT("r", "vec*"),
+      IN("normal_in", "vec*"), OUT("normal", "vec*"), IN("tangent_in", "vec*"),
+      OUT("tangent", "vec*"), IN("id_sorted", "usize*"), SC("N", "usize") }, l_sort_stage1);
+aqc_registrar r_sort2("basic/Sort.cl", "stage2", 0,
+    { IN("rho_in", "float*"), OUT("rho", "float*"), IN("m_in", "float*"), OUT("m", "float*"),
+      IN("u_in", "vec*"), OUT("u", "vec*"), IN("dudt", "vec*"), OUT("dudt_in", "vec*"),
+      IN("drhodt", "float*"), OUT("drhodt_in", "float*"), IN("id_sorted", "usize*"),
+      SC("N", "usize") }, l_sort_stage2);
+aqc_registrar r_eos("basic/EOS.cl", "entry", 0,
+    { OUT("iset", "unsigned int*"), OUT("imove", "int*"), OUT("rho", "float*"), OUT("p", "float*"),
+      IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"), SC("p0", "float") }, l_eos);
+aqc_registrar r_binormal("basic/Binormal.cl", "entry", 0,
+    { IN("normal", "vec*"), OUT("tangent", "vec*"), OUT("binormal", "vec*"), SC("N", "usize") },
+    l_binormal);
+aqc_registrar r_rates("cfd/Rates.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("rho", "float*"), IN("grad_p", "vec*"),
+      IN("lap_u", "vec*"), IN("div_u", "float*"), OUT("dudt", "vec*"), OUT("drhodt", "float*"),
+      IN("visc_dyn", "float*"), SC("N", "usize"), SC("g", "vec") }, l_rates);
+aqc_registrar r_timestep("cfd/TimeStep.cl", "entry", 0,
+    { IN("imove", "int*"), IN("u", "vec*"), OUT("dt_var", "float*"), SC("N", "usize"),
+      SC("dt", "float"), SC("dt_min", "float"), SC("courant", "float"), SC("dt_Ma", "float"),
+      SC("h", "float") }, l_timestep);
+aqc_registrar r_sens_rn("cfd/SensorsRenormalization.cl", "entry", 0,
+    { IN("imove", "int*"), IN("shepard", "float*"), OUT("u", "vec*"), OUT("rho", "float*"),
+      OUT("p", "float*"), SC("N", "usize"), SC("dt", "float"), SC("g", "vec") }, l_sensors_renorm);
+aqc_registrar r_ds_simple("cfd/deltaSPH.cl", "simple", 0,
+    { IN("iset", "unsigned int*"), IN("imove", "int*"), OUT("lap_p_corr", "vec*"),
+      IN("refd", "float*"), SC("N", "usize"), SC("g", "vec") }, l_dsph_simple);
+aqc_registrar r_ds_fmls("cfd/deltaSPH.cl", "full_mls", 0,
+    { IN("imove", "int*"), IN("mls", "matrix*"), OUT("lap_p_corr", "vec*"), SC("N", "usize") },
+    l_dsph_full_mls);
+aqc_registrar r_ds_apply("cfd/deltaSPH.cl", "deltaSPH", 0,
+    { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("rho", "float*"), IN("lap_p", "float*"),
+      OUT("drhodt", "float*"), IN("refd", "float*"), IN("delta", "float*"), SC("N", "usize"),
+      SC("dt", "float") }, l_dsph_apply);
+aqc_registrar r_mls_inv("basic/MLS.cl", "mls_inv", 0,
+    { IN("imove", "int*"), OUT("mls", "matrix*"), SC("N", "usize"), SC("mls_imove", "uint") },
+    l_mls_inv);
+aqc_registrar r_bie_r("cfd/Boundary/BIe/Rates.cl", "entry", 0,
+    { IN("imove", "int*"), IN("rho", "float*"), IN("p", "float*"), IN("u", "vec*"),
+      IN("grad_w_bi", "vec*"), IN("div_u_bi", "float*"), OUT("grad_p", "vec*"),
+      OUT("div_u", "float*"), SC("N", "usize") }, l_bie_rates);
+aqc_registrar r_bie_fp("cfd/Boundary/BIe/Rates.cl", "filter_press", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), OUT("p", "float*"),
+      SC("forces_iset", "unsigned int"), SC("N", "usize") }, l_bie_filter_press);
+aqc_registrar r_bie_frp("cfd/Boundary/BIe/Rates.cl", "force_press", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
+      IN("p", "float*"), OUT("force_p", "vec*"), OUT("moment_p", "vec4*"), SC("forces_r", "vec"),
+      SC("N", "usize") }, l_bie_force_press);
+aqc_registrar r_bie_fb("cfd/Boundary/BIe/ElasticBounce.cl", "force_bound", 0,
+    { IN("imove", "int*"), IN("m", "float*"), IN("dudt_preelastic", "vec*"),
+      IN("dudt_elastic", "vec*"), OUT("force_elastic", "vec*"), SC("N", "usize") },
+    l_bie_force_bound);
+aqc_registrar r_sb_count("basic/SetBuffer.cl", "count", 0,
+    { IN("imove", "int*"), OUT("ibuffer", "unsigned int*"), SC("N", "usize") }, l_setbuffer_count);
+aqc_registrar r_sb_set("basic/SetBuffer.cl", "set_imove", 0,
+    { OUT("imove", "int*"), SC("N", "usize") }, l_setbuffer_set_imove);
+
+} // namespace

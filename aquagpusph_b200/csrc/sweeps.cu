@@ -1,0 +1,831 @@
+// sweeps.cu -- policies of the neighbour sweep (sweep.cuh) for every
+// BEGIN_NEIGHS kernel on the hot path, and their Kernel-tool registry entries.
+// Argument lists (names, order) are those of the reference kernels, so the
+// host binds Variables by name exactly as Kernel.cpp:497-556 does.
+//
+// Arithmetic notes (all inside the stated fp32 tolerance):
+//  * per-j factors are hoisted to the staging step: w_j = wcon*CON*m_j/rho_j;
+//  * per-i factors (1/rho_i, rho_i, __CLEARY__) are applied once after the loop;
+//  * q = sqrt(d2)/H is evaluated as d2*rsqrt(d2)*(1/H); the candidate filter is
+//    d2 < (SUPPORT*H)^2 instead of q >= SUPPORT (differs only for pairs within
+//    an ulp of the cut-off, where the Wendland factors (2-q)^3,(2-q)^4 vanish);
+//  * the i == j exclusion of the reference is implicit wherever the pair term is
+//    exactly zero for r_ij = 0 (all kernels below that exclude it).
+#include "sweep.cuh"
+
+namespace {
+
+constexpr float iM_PI = 0.318309886f; // KernelFunctions/Wendland3D.hcl:34-39
+
+template <int DIMS> struct Wend; // Wendland{2D,3D}.hcl:44-66
+template <> struct Wend<3> {
+    static constexpr float W = 0.08203125f * iM_PI;
+    static constexpr float F = 0.8203125f * iM_PI;
+    static constexpr float CLEARY = 10.f; // cfd/Interactions.cl:33-39
+};
+template <> struct Wend<2> {
+    static constexpr float W = 0.109375f * iM_PI;
+    static constexpr float F = 1.09375f * iM_PI;
+    static constexpr float CLEARY = 8.f;
+};
+
+template <int DIMS> struct VecT;
+template <> struct VecT<3> { using T = float4; };
+template <> struct VecT<2> { using T = float2; };
+
+template <int DIMS>
+__device__ __forceinline__ float4 ldvec(const void* base, uint32_t i)
+{
+    if constexpr (DIMS == 3) {
+        return __ldg(reinterpret_cast<const float4*>(base) + i);
+    } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(base) + i);
+        return make_float4(t.x, t.y, 0.f, 0.f);
+    }
+}
+// plain (coherent) load for arrays the same kernel also writes
+template <int DIMS>
+__device__ __forceinline__ float4 ldvec_rw(const void* base, uint32_t i)
+{
+    if constexpr (DIMS == 3) {
+        return reinterpret_cast<const float4*>(base)[i];
+    } else {
+        const float2 t = reinterpret_cast<const float2*>(base)[i];
+        return make_float4(t.x, t.y, 0.f, 0.f);
+    }
+}
+// write only the XYZ (XY) components, like "v[i].XYZ = ..." in the reference
+template <int DIMS>
+__device__ __forceinline__ void stvec_xyz(void* base, uint32_t i, float x, float y, float z)
+{
+    if constexpr (DIMS == 3) {
+        float* p = reinterpret_cast<float*>(base) + 4 * (size_t)i;
+        p[0] = x; p[1] = y; p[2] = z;
+    } else {
+        reinterpret_cast<float2*>(base)[i] = make_float2(x, y);
+    }
+}
+
+// q from d2 (see header note); d2 == 0 -> q = 0
+__device__ __forceinline__ float q_of(float d2, float invH)
+{
+    const float s = d2 > 0.f ? d2 * rsqrtf(d2) : 0.f;
+    return s * invH;
+}
+
+struct PBase {
+    const int* __restrict__ imove;
+    float invH, cut2;
+};
+
+// ------------------------------------------------------------------------
+// cfd/Interactions.cl:60-145
+template <int D>
+struct PInteractions : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *u;
+    const float *rho, *m, *p;
+    void *grad_p, *lap_u;
+    float* div_u;
+    float cF;     // wconF * CONF
+    float eps2;   // 0.01 * H * H
+    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.p = __ldg(p + i);
+        s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == 1;
+        const float w = cF * __ldg(m + j) / __ldg(rho + j);
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, w);
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(p + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float t = 2.f - q_of(d2, invH);
+        const float fr = (t * t) * (t * A.w); // kernelF(q)*CONF*m_j / rho_j
+        float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
+        if constexpr (D == 3)
+            udr += (B.z - s.uz) * dz;
+        const float a = (s.p + B.w) * fr;
+        const float b0 = udr * fr;
+        const float b = b0 * __frcp_rn(d2 + eps2);
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+        s.du += b0;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float cl = Wend<D>::CLEARY * ir;
+        stvec_xyz<D>(grad_p, i, s.gx * ir, s.gy * ir, s.gz * ir);
+        stvec_xyz<D>(lap_u, i, s.lx * cl, s.ly * cl, s.lz * cl);
+        div_u[i] = s.du * rho_i;
+    }
+};
+
+// ------------------------------------------------------------------------
+// basic/Shepard.cl:76-125 (MODE 0) and cfd/Shepard.cl:29-35 (MODE 1)
+template <int D, int MODE>
+struct PShepard : PBase {
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void* r;
+    const float *rho, *m;
+    float* shepard;
+    float cW; // wconW * CONW
+    struct IState { float x, y, z, s; };
+    __device__ static bool excl(int mv) { return MODE ? (mv != 1) : (mv >= 3); }
+    __device__ bool i_active(int mv) const { return !((mv < -3) || ((mv > 0) && excl(mv))); }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.s = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = !excl(__ldg(imove + j));
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j) / __ldg(rho + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        s.s += (1.f + 2.f * q) * (t2 * t2) * A.w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { shepard[i] = s.s; }
+};
+
+// ------------------------------------------------------------------------
+// basic/deltaSPH.cl:94-145 (full, VECOUT) and :191-242 (lapp); EXCLUDED = imove != 1
+template <int D, bool VECOUT>
+struct PDeltaGrad : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void* r;
+    const float *rho, *m, *p;
+    void* out; // lap_p_corr (vec) or lap_p (float)
+    float cF;
+    struct IState { float x, y, z, p, ax, ay, az; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.p = __ldg(p + i);
+        s.ax = s.ay = s.az = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = __ldg(imove + j) == 1;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * __ldg(m + j) / __ldg(rho + j));
+        o[1] = make_float4(__ldg(p + j), 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0];
+        const float pj = row[stride].x;
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float t = 2.f - q_of(dist2<D>(dx, dy, dz), invH);
+        const float c = (pj - s.p) * ((t * t) * (t * A.w));
+        if constexpr (VECOUT) {
+            s.ax += c * dx; s.ay += c * dy; s.az += c * dz;
+        } else {
+            s.ax += c;
+        }
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if constexpr (VECOUT)
+            stvec_xyz<D>(out, i, s.ax, s.ay, s.az);
+        else
+            reinterpret_cast<float*>(out)[i] = s.ax;
+    }
+};
+
+// basic/deltaSPH.cl:261-313 (lapp_corr): starts from the old lap_p[i] (:287)
+template <int D>
+struct PLappCorr : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void* r;
+    const float *rho, *m;
+    const void* lap_p_corr;
+    float* lap_p;
+    float cF;
+    struct IState { float x, y, z, gx, gy, gz, acc; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), g = ldvec<D>(lap_p_corr, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.gx = g.x; s.gy = g.y; s.gz = g.z;
+        s.acc = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), g = ldvec<D>(lap_p_corr, j);
+        const bool ok = __ldg(imove + j) == 1;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * __ldg(m + j) / __ldg(rho + j));
+        o[1] = make_float4(g.x, g.y, g.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], G = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float t = 2.f - q_of(dist2<D>(dx, dy, dz), invH);
+        float gr = (G.x + s.gx) * dx + (G.y + s.gy) * dy;
+        if constexpr (D == 3)
+            gr += (G.z + s.gz) * dz;
+        s.acc += gr * ((t * t) * (t * A.w));
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { lap_p[i] -= 0.5f * s.acc; }
+};
+
+// ------------------------------------------------------------------------
+// basic/MLS.cl:58-112
+template <int D>
+struct PMLS : PBase {
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void* r;
+    const float *rho, *m;
+    float* mls;
+    uint32_t mls_imove;
+    float cF;
+    struct IState { float x, y, z, a[D * D]; };
+    __device__ bool i_active(int mv) const { return (uint32_t)mv == mls_imove; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+#pragma unroll
+        for (int k = 0; k < D * D; k++)
+            s.a[k] = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = (uint32_t)__ldg(imove + j) == mls_imove;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * __ldg(m + j) / __ldg(rho + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        float d[3] = { A.x - s.x, A.y - s.y, A.z - s.z };
+        const float t = 2.f - q_of(dist2<D>(d[0], d[1], d[2]), invH);
+        const float f = (t * t) * (t * A.w);
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+            for (int b = 0; b < D; b++)
+                s.a[a * D + b] += d[a] * (f * d[b]);
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if constexpr (D == 3) {
+            float4* o = reinterpret_cast<float4*>(mls) + 4 * (size_t)i;
+            o[0] = make_float4(s.a[0], s.a[1], s.a[2], 0.f);
+            o[1] = make_float4(s.a[3], s.a[4], s.a[5], 0.f);
+            o[2] = make_float4(s.a[6], s.a[7], s.a[8], 0.f);
+            o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            reinterpret_cast<float4*>(mls)[i] = make_float4(s.a[0], s.a[1], s.a[2], s.a[3]);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------
+// cfd/Sensors.cl:57-130
+template <int D>
+struct PSensors : PBase {
+    static constexpr int DIMS = D, NJ4 = 3;
+    const void* r;
+    const float* m;
+    void* u;
+    float *rho, *p;
+    float cW;
+    struct IState { float x, y, z, ux, uy, uz, rho, p; };
+    __device__ bool i_active(int mv) const { return mv == 0; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.ux = s.uy = s.uz = s.rho = s.p = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec_rw<D>(u, j);
+        const bool ok = __ldg(imove + j) == 1;
+        const float rj = rho[j];
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j) / rj);
+        o[1] = make_float4(b.x, b.y, b.z, p[j]);
+        o[2] = make_float4(rj, 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float rj = row[2 * stride].x;
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        const float w = (1.f + 2.f * q) * (t2 * t2) * A.w;
+        s.ux += B.x * w; s.uy += B.y * w; s.uz += B.z * w;
+        s.rho += rj * w;
+        s.p += B.w * w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        stvec_xyz<D>(u, i, s.ux, s.uy, s.uz);
+        rho[i] = s.rho;
+        p[i] = s.p;
+    }
+};
+
+// ------------------------------------------------------------------------
+// cfd/Boundary/BIe/Interactions.cl:48-108
+template <int D>
+struct PBIeInteractions : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *normal, *u;
+    const float* m;
+    void* grad_w_bi;
+    float* div_u_bi;
+    float cW;
+    struct IState { float x, y, z, gx, gy, gz, du; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.gx = s.gy = s.gz = s.du = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), n = ldvec<D>(normal, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == -3;
+        float un = b.x * n.x + b.y * n.y;
+        if constexpr (D == 3)
+            un += b.z * n.z;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j));
+        o[1] = make_float4(n.x, n.y, n.z, un);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        const float w = (1.f + 2.f * q) * (t2 * t2) * A.w; // kernelW*CONW*area_j
+        s.gx += Nn.x * w; s.gy += Nn.y * w; s.gz += Nn.z * w;
+        s.du -= Nn.w * w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        stvec_xyz<D>(grad_w_bi, i, s.gx, s.gy, s.gz);
+        div_u_bi[i] = s.du;
+    }
+};
+
+// cfd/Boundary/BIe/Interactions.cl:124-170 (p_boundary)
+template <int D>
+struct PBIePBoundary : PBase {
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void* r;
+    const float *m, *rho;
+    float* p;
+    float cW;
+    struct IState { float x, y, z, p; };
+    __device__ bool i_active(int mv) const { return mv == -3; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.p = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = __ldg(imove + j) == 1;
+        // p is read for fluid j and written for boundary i: disjoint rows
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z,
+                           ok ? 2.f * p[j] * cW * __ldg(m + j) / __ldg(rho + j) : 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        s.p += (1.f + 2.f * q) * (t2 * t2) * A.w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { p[i] = s.p; }
+};
+
+// cfd/Boundary/BIe/ElasticBounce.cl:64-152 -- order dependent
+template <int D>
+struct PBIeElasticBounce : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r_in, *normal, *u_in;
+    const float* m;
+    void* dudt;
+    float dt;
+    struct IState { float x, y, z, u0x, u0y, u0z, ax, ay, az, Ux, Uy, Uz; };
+    __device__ bool i_active(int mv) const { return mv == 1 && dt != 0.f; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r_in, i), b = ldvec<D>(u_in, i), c = ldvec_rw<D>(dudt, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.u0x = b.x; s.u0y = b.y; s.u0z = b.z;
+        s.ax = c.x; s.ay = c.y; s.az = c.z;
+        s.Ux = s.u0x + 0.5f * dt * s.ax;
+        s.Uy = s.u0y + 0.5f * dt * s.ay;
+        s.Uz = s.u0z + 0.5f * dt * s.az;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r_in, j), n = ldvec<D>(normal, j);
+        const bool ok = __ldg(imove + j) == -3;
+        const float mj = __ldg(m + j);
+        const float dr = (D == 3) ? sqrtf(mj) : mj;
+        const float R = 0.5f * dr; // __DR_FACTOR__ (:31-33)
+        o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
+        o[1] = make_float4(n.x, n.y, n.z, dr);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        // cheap necessary condition: |rt|^2 < R^2 implies |r_ij|^2 - rn^2 < R^2; the
+        // exact tests run in body().  Excluded j carry R^2 = -1.
+        return A.w >= 0.f;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = (D == 3) ? A.z - s.z : 0.f;
+        float rn = dx * Nn.x + dy * Nn.y;
+        if constexpr (D == 3)
+            rn += dz * Nn.z;
+        if (rn < 0.f)
+            return;
+        const float tx = dx - rn * Nn.x, ty = dy - rn * Nn.y, tz = dz - rn * Nn.z;
+        if (dist2<D>(tx, ty, tz) >= A.w)
+            return;
+        float Un = s.Ux * Nn.x + s.Uy * Nn.y;
+        if constexpr (D == 3)
+            Un += s.Uz * Nn.z;
+        const float drn = dt * Un;
+        if (drn < 0.f)
+            return;
+        if (rn - drn <= 0.0f * Nn.w) { // __MIN_BOUND_DIST__ = 0 (:34-36)
+            const float ux = s.u0x + dt * s.ax, uy = s.u0y + dt * s.ay, uz = s.u0z + dt * s.az;
+            float un = ux * Nn.x + uy * Nn.y;
+            if constexpr (D == 3)
+                un += uz * Nn.z;
+            const float rx = ux - 2.f * un * Nn.x, ry = uy - 2.f * un * Nn.y,
+                        rz = uz - 2.f * un * Nn.z;
+            s.ax = (rx - s.u0x) / dt; s.ay = (ry - s.u0y) / dt; s.az = (rz - s.u0z) / dt;
+            s.Ux = s.u0x + 0.5f * dt * s.ax;
+            s.Uy = s.u0y + 0.5f * dt * s.ay;
+            s.Uz = s.u0z + 0.5f * dt * s.az;
+        }
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        stvec_xyz<D>(dudt, i, s.ax, s.ay, s.az);
+    }
+};
+
+// cfd/Boundary/BIe/PST.cl:62-110 -- order dependent (r_i moves inside the loop)
+template <int D>
+struct PBIePST : PBase {
+    static constexpr int DIMS = D, NJ4 = 2;
+    void* r;
+    const void* normal;
+    const float *m, *rho;
+    float inv_dims; // 1.f / DIMS
+    struct IState { float x, y, z, Ri; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec_rw<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.Ri = 0.5f * powf(__ldg(m + i) / __ldg(rho + i), inv_dims);
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        // r is read for boundary j (never moved: only imove == 1 rows are written)
+        const float4 a = ldvec_rw<D>(r, j), n = ldvec<D>(normal, j);
+        const bool ok = __ldg(imove + j) == -3;
+        const float mj = __ldg(m + j);
+        const float dr = (D == 3) ? sqrtf(mj) : mj;
+        const float R = 0.5f * dr;
+        o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
+        o[1] = make_float4(n.x, n.y, n.z, 0.f);
+    }
+    __device__ bool test(const IState&, const float4& A) const { return A.w >= 0.f; }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = (D == 3) ? A.z - s.z : 0.f;
+        float rn = dx * Nn.x + dy * Nn.y;
+        if constexpr (D == 3)
+            rn += dz * Nn.z;
+        if (fabsf(rn) > s.Ri)
+            return;
+        const float tx = dx - rn * Nn.x, ty = dy - rn * Nn.y, tz = dz - rn * Nn.z;
+        if (dist2<D>(tx, ty, tz) >= A.w)
+            return;
+        const float k = rn - s.Ri;
+        s.x += k * Nn.x; s.y += k * Nn.y;
+        if constexpr (D == 3)
+            s.z += k * Nn.z;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        stvec_xyz<D>(r, i, s.x, s.y, s.z);
+    }
+};
+
+// ------------------------------------------------------------------------
+// basic/neighs.cl:52-91: candidates are counted without any distance test, so
+// the count is the clamped sum of the neighbour cells' populations.
+template <int D>
+__global__ void __launch_bounds__(256)
+neighs_kernel(const int* __restrict__ imove, uint32_t* __restrict__ n_neighs, uint32_t limit,
+              const LLParams ll)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ll.N)
+        return;
+    if (imove[i] <= -255) {
+        n_neighs[i] = 0;
+        return;
+    }
+    const uint32_t c = __ldg(ll.icell + i);
+    constexpr int KZ = (D == 3) ? 1 : 0;
+    uint32_t n = 0;
+    for (int ci = -1; ci <= 1; ci++)
+        for (int cj = -1; cj <= 1; cj++)
+            for (int ck = -KZ; ck <= KZ; ck++) {
+                const uint32_t cell =
+                    c + (uint32_t)ci + (uint32_t)cj * ll.nx + (uint32_t)ck * ll.nx * ll.ny;
+                uint32_t j = __ldg(ll.ihoc + cell);
+                while (j < ll.N && __ldg(ll.icell + j) == cell) {
+                    n++;
+                    if (n >= limit) {
+                        n_neighs[i] = n;
+                        return;
+                    }
+                    j++;
+                }
+            }
+    n_neighs[i] = n;
+}
+
+// ---- launch glue -------------------------------------------------------------
+LLParams make_ll(void* const* a, int k_icell, size_t N)
+{
+    // LINKLIST_LOCAL_PARAMS = icell, ihoc, n_cells (types.h:106-109)
+    LLParams ll;
+    ll.icell = (const uint32_t*)a[k_icell];
+    ll.ihoc = (const uint32_t*)a[k_icell + 1];
+    const aqc_u4 nc = aqc_scalar<aqc_u4>(a, k_icell + 2);
+    ll.nx = nc.x; ll.ny = nc.y; ll.nz = nc.z; ll.nw = nc.w;
+    ll.N = (uint32_t)N;
+    return ll;
+}
+
+template <class P>
+void set_base(P& p, const aqc_ctx* ctx, const void* imove)
+{
+    p.imove = (const int*)imove;
+    p.invH = 1.f / ctx->defs.H;
+    const float s = ctx->defs.SUPPORT * ctx->defs.H;
+    p.cut2 = s * s;
+}
+
+#define DIMS_DISPATCH(ctx, FN, ...)                                            \
+    ((ctx)->defs.dims == 3 ? FN<3>(__VA_ARGS__) : FN<2>(__VA_ARGS__))
+
+template <int D> int run_interactions(aqc_ctx* ctx, size_t n, void* const* a)
+{
+    PInteractions<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.m = (const float*)a[4];
+    p.p = (const float*)a[5]; p.grad_p = a[6]; p.lap_u = a[7]; p.div_u = (float*)a[8];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    const uint32_t N = aqc_scalar<uint32_t>(a, 9);
+    (void)n;
+    return launch_sweep(ctx, p, make_ll(a, 10, N));
+}
+int l_interactions(aqc_ctx* c, size_t n, void* const* a) { return DIMS_DISPATCH(c, run_interactions, c, n, a); }
+
+template <int D, int MODE> int run_shepard(aqc_ctx* ctx, void* const* a)
+{
+    PShepard<D, MODE> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.rho = (const float*)a[2]; p.m = (const float*)a[3]; p.shepard = (float*)a[4];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 6, aqc_scalar<uint32_t>(a, 5)));
+}
+int l_shepard_basic(aqc_ctx* c, size_t, void* const* a)
+{
+    return c->defs.dims == 3 ? run_shepard<3, 0>(c, a) : run_shepard<2, 0>(c, a);
+}
+int l_shepard_cfd(aqc_ctx* c, size_t, void* const* a)
+{
+    return c->defs.dims == 3 ? run_shepard<3, 1>(c, a) : run_shepard<2, 1>(c, a);
+}
+
+template <int D, bool V> int run_deltagrad(aqc_ctx* ctx, void* const* a)
+{
+    PDeltaGrad<D, V> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.rho = (const float*)a[2]; p.m = (const float*)a[3]; p.p = (const float*)a[4];
+    p.out = a[5];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 6)));
+}
+int l_dsph_full(aqc_ctx* c, size_t, void* const* a)
+{
+    return c->defs.dims == 3 ? run_deltagrad<3, true>(c, a) : run_deltagrad<2, true>(c, a);
+}
+int l_dsph_lapp(aqc_ctx* c, size_t, void* const* a)
+{
+    return c->defs.dims == 3 ? run_deltagrad<3, false>(c, a) : run_deltagrad<2, false>(c, a);
+}
+
+template <int D> int run_lapp_corr(aqc_ctx* ctx, void* const* a)
+{
+    PLappCorr<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.rho = (const float*)a[2]; p.m = (const float*)a[3]; p.lap_p_corr = a[4];
+    p.lap_p = (float*)a[5];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 6)));
+}
+int l_dsph_lapp_corr(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_lapp_corr, c, a); }
+
+template <int D> int run_mls(aqc_ctx* ctx, void* const* a)
+{
+    PMLS<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.rho = (const float*)a[2]; p.m = (const float*)a[3]; p.mls = (float*)a[4];
+    p.mls_imove = aqc_scalar<uint32_t>(a, 6);
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 5)));
+}
+int l_mls(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mls, c, a); }
+
+template <int D> int run_sensors(aqc_ctx* ctx, void* const* a)
+{
+    PSensors<D> p;
+    set_base(p, ctx, a[1]);
+    p.r = a[2]; p.m = (const float*)a[3]; p.u = a[4]; p.rho = (float*)a[5]; p.p = (float*)a[6];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 9, aqc_scalar<uint32_t>(a, 7)));
+}
+int l_sensors(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_sensors, c, a); }
+
+template <int D> int run_bie_inter(aqc_ctx* ctx, void* const* a)
+{
+    PBIeInteractions<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.normal = a[2]; p.u = a[3]; p.m = (const float*)a[4]; p.grad_w_bi = a[5];
+    p.div_u_bi = (float*)a[6];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 8, aqc_scalar<uint32_t>(a, 7)));
+}
+int l_bie_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_inter, c, a); }
+
+template <int D> int run_bie_pb(aqc_ctx* ctx, void* const* a)
+{
+    PBIePBoundary<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.m = (const float*)a[2]; p.rho = (const float*)a[3]; p.p = (float*)a[4];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 6, aqc_scalar<uint32_t>(a, 5)));
+}
+int l_bie_pb(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_pb, c, a); }
+
+template <int D> int run_bie_eb(aqc_ctx* ctx, void* const* a)
+{
+    PBIeElasticBounce<D> p;
+    set_base(p, ctx, a[0]);
+    p.r_in = a[1]; p.normal = a[2]; p.m = (const float*)a[3]; p.u_in = a[4]; p.dudt = a[5];
+    p.dt = aqc_scalar<float>(a, 7);
+    return launch_sweep(ctx, p, make_ll(a, 8, aqc_scalar<uint32_t>(a, 6)));
+}
+int l_bie_eb(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_eb, c, a); }
+
+template <int D> int run_bie_pst(aqc_ctx* ctx, void* const* a)
+{
+    PBIePST<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.normal = a[2]; p.m = (const float*)a[3]; p.rho = (const float*)a[4];
+    p.inv_dims = 1.f / ctx->defs.DIMS;
+    return launch_sweep(ctx, p, make_ll(a, 6, aqc_scalar<uint32_t>(a, 5)));
+}
+int l_bie_pst(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_pst, c, a); }
+
+int l_neighs(aqc_ctx* ctx, size_t, void* const* a)
+{
+    const uint32_t limit = aqc_scalar<uint32_t>(a, 2);
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    const LLParams ll = make_ll(a, 4, N);
+    if (ctx->defs.dims == 3)
+        neighs_kernel<3><<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>((const int*)a[0],
+                                                                       (uint32_t*)a[1], limit, ll);
+    else
+        neighs_kernel<2><<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>((const int*)a[0],
+                                                                       (uint32_t*)a[1], limit, ll);
+    AQC_LAUNCH_CHECK(ctx);
+    return AQC_OK;
+}
+
+#define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
+#define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
+#define SC(n, t) { n, t, AQC_ARG_SCALAR }
+#define LL_ARGS IN("icell", "usize*"), IN("ihoc", "usize*"), SC("n_cells", "svec4")
+
+aqc_registrar r_inter("cfd/Interactions.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
+      IN("m", "float*"), IN("p", "float*"), OUT("grad_p", "vec*"), OUT("lap_u", "vec*"),
+      OUT("div_u", "float*"), SC("N", "usize"), LL_ARGS }, l_interactions);
+aqc_registrar r_shep_b("basic/Shepard.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      OUT("shepard", "float*"), SC("N", "usize"), LL_ARGS }, l_shepard_basic);
+aqc_registrar r_shep_c("cfd/Shepard.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      OUT("shepard", "float*"), SC("N", "usize"), LL_ARGS }, l_shepard_cfd);
+#define DSPH_GRAD_ARGS(outname, outtype)                                       \
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"), \
+      IN("p", "float*"), OUT(outname, outtype), SC("N", "usize"), LL_ARGS }
+aqc_registrar r_full_c("cfd/deltaSPH.cl", "full", 0, DSPH_GRAD_ARGS("lap_p_corr", "vec*"), l_dsph_full);
+aqc_registrar r_lapp_c("cfd/deltaSPH.cl", "lapp", 0, DSPH_GRAD_ARGS("lap_p", "float*"), l_dsph_lapp);
+#define LAPP_CORR_ARGS                                                          \
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"), \
+      IN("lap_p_corr", "vec*"), OUT("lap_p", "float*"), SC("N", "usize"), LL_ARGS }
+aqc_registrar r_lappc_c("cfd/deltaSPH.cl", "lapp_corr", 0, LAPP_CORR_ARGS, l_dsph_lapp_corr);
+aqc_registrar r_mls("basic/MLS.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      OUT("mls", "matrix*"), SC("N", "usize"), SC("mls_imove", "uint"), LL_ARGS }, l_mls);
+aqc_registrar r_sensors("cfd/Sensors.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("m", "float*"),
+      OUT("u", "vec*"), OUT("rho", "float*"), OUT("p", "float*"), SC("N", "usize"),
+      SC("g", "vec"), LL_ARGS }, l_sensors);
+aqc_registrar r_bie_i("cfd/Boundary/BIe/Interactions.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), IN("u", "vec*"),
+      IN("m", "float*"), OUT("grad_w_bi", "vec*"), OUT("div_u_bi", "float*"),
+      SC("N", "usize"), LL_ARGS }, l_bie_inter);
+aqc_registrar r_bie_pb("cfd/Boundary/BIe/Interactions.cl", "p_boundary", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("m", "float*"), IN("rho", "float*"),
+      OUT("p", "float*"), SC("N", "usize"), LL_ARGS }, l_bie_pb);
+aqc_registrar r_bie_eb("cfd/Boundary/BIe/ElasticBounce.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r_in", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
+      IN("u_in", "vec*"), OUT("dudt", "vec*"), SC("N", "usize"), SC("dt", "float"), LL_ARGS },
+    l_bie_eb);
+aqc_registrar r_bie_pst("cfd/Boundary/BIe/PST.cl", "entry", 0,
+    { IN("imove", "int*"), OUT("r", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
+      IN("rho", "float*"), SC("N", "usize"), LL_ARGS }, l_bie_pst);
+aqc_registrar r_neighs("basic/neighs.cl", "entry", 0,
+    { IN("imove", "int*"), OUT("n_neighs", "uint*"), SC("neighs_limit", "uint"),
+      SC("N", "usize"), LL_ARGS }, l_neighs);
+
+} // namespace

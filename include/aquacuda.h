@@ -1,0 +1,156 @@
+/* aquacuda.h -- C-ABI of libaquacuda.so: the B200 (sm_100a) device layer that
+ * replaces the OpenCL back-end of AQUAgpusph's CalcServer tools.
+ *
+ * The reference has no FFI; its "device boundary" is the OpenCL host API called
+ * from the tool classes (aquagpusph/CalcServer/{Kernel,LinkList,RadixSort,
+ * Reduction,Set,Copy,UnSort,MPISync}.cpp).  Every entry point below names the
+ * reference interface it stands in for.  A maintainer of the reference would
+ * call these from Tool::_execute() overrides (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *  - plain C: opaque context, raw device pointers (void*), sizes; no C++/torch
+ *    types.  Every function returns 0 on success, <0 on error and stores a
+ *    message retrievable with aqc_last_error() (the reference's equivalent is
+ *    CHECK_OCL_OR_THROW, CalcServer.hpp:44-49: the C++ side turns non-zero into
+ *    std::runtime_error at the same places).
+ *  - all work is enqueued on the context's CUDA stream (in order); nothing
+ *    blocks the host unless stated ("syncs").
+ *  - "usize" is 32 bit (the reference default when <Device> has no addr_bits,
+ *    State.cpp:499-502); vec = float4 in 3-D, float2 in 2-D
+ *    (resources/Scripts/types/3D.h:23-31, 2D.h:23-31); matrix = float16/float4.
+ *  - there is NO CPU fallback: without a CUDA device aqc_ctx_create fails.
+ */
+#ifndef AQUACUDA_H
+#define AQUACUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aqc_ctx aqc_ctx;
+typedef uint32_t aqc_usize;
+
+#define AQC_OK 0
+#define AQC_ERR_CUDA (-1)     /* a CUDA runtime call failed */
+#define AQC_ERR_ARG (-2)      /* invalid argument */
+#define AQC_ERR_NOKERNEL (-3) /* (script, entry) not in the registry */
+#define AQC_ERR_NCCL (-4)
+#define AQC_ERR_STATE (-5)
+
+/* ---- context: replaces CalcServer::setupOpenCL (CalcServer.cpp:858-886) and
+ * the command-queue pool (CalcServer.cpp:674-705) ------------------------- */
+int aqc_ctx_create(int device, aqc_ctx** out);
+void aqc_ctx_destroy(aqc_ctx* ctx);
+const char* aqc_last_error(const aqc_ctx* ctx);
+/* Run on an externally owned cudaStream_t (e.g. the caller's). NULL = own. */
+int aqc_set_stream(aqc_ctx* ctx, void* cuda_stream);
+void* aqc_get_stream(aqc_ctx* ctx);
+int aqc_sync(aqc_ctx* ctx); /* clFinish */
+/* number of kernels this library launched on ctx since creation */
+uint64_t aqc_launch_count(const aqc_ctx* ctx);
+int aqc_device_sm_count(const aqc_ctx* ctx);
+
+/* ---- "-D" definitions baked into every OpenCL kernel by the reference
+ * (CalcServer.cpp:240-265, basic.xml:119-123, cfd.xml:52-54).  Here they are
+ * constant-bank parameters of the context; H/CONW/CONF must already be the
+ * 6-significant-digit values the reference would print (see
+ * aqc_define_round6). ------------------------------------------------------ */
+typedef struct {
+    int dims;      /* 2 | 3  (-DHAVE_2D / -DHAVE_3D, Tool.cpp:330-333) */
+    float H;       /* -DH */
+    float CONW;    /* -DCONW */
+    float CONF;    /* -DCONF */
+    float SUPPORT; /* -DSUPPORT (2.f) */
+    float DIMS;    /* -DDIMS (evaluated => float literal) */
+} aqc_defs;
+float aqc_define_round6(float value); /* CalcServer.cpp:245-257 "%#G" + "f" */
+int aqc_set_defs(aqc_ctx* ctx, const aqc_defs* defs);
+
+/* ---- device memory: ArrayVariable storage (Variable.cpp:1739-1822) ------- */
+int aqc_alloc(aqc_ctx* ctx, size_t bytes, void** dptr);
+int aqc_free(aqc_ctx* ctx, void* dptr);
+int aqc_host_alloc(aqc_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int aqc_host_free(aqc_ctx* ctx, void* hptr);
+/* clEnqueueWriteBuffer / ReadBuffer / CopyBuffer (Copy.cpp:62-91); blocking!=0 syncs */
+int aqc_memcpy_h2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int blocking);
+int aqc_memcpy_d2h(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int blocking);
+int aqc_memcpy_d2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- Set tool (Set.cpp:197-226, Set.cl.in:32-47): fill n elements of
+ * elem_bytes (4, 8, 16 or 64) with the value at *value ---------------------- */
+int aqc_fill(aqc_ctx* ctx, void* dptr, size_t n, size_t elem_bytes, const void* value);
+
+/* ---- LinkList tool (LinkList.cpp:326-494; kernels LinkList.cl.in:32-113).
+ * r: N vec; icell, perm (= id_unsorted), inv_perm (= id_sorted): N usize.
+ * recompute_grid != 0: r_min/r_max are reduced from r (LinkList.cpp:338-356),
+ * else the host values passed in are used.  rmin/rmax/ncells are HOST arrays of
+ * 4 entries (in/out).  *ihoc / *ihoc_capacity (elements) are in/out: when
+ * n_cells.w exceeds the capacity the library frees *ihoc, allocates a larger
+ * buffer and returns it (LinkList::allocate, LinkList.cpp:234-271).
+ * Syncs once (the reference blocks at the same place, LinkList.cpp:350-356). */
+int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int dims,
+                       float support, float h, int recompute_grid,
+                       float rmin[4], float rmax[4], aqc_usize ncells[4],
+                       aqc_usize* icell, aqc_usize** ihoc, size_t* ihoc_capacity,
+                       aqc_usize* perm, aqc_usize* inv_perm);
+
+/* ---- RadixSort tool (RadixSort.cpp:129-303): stable ascending sort of n usize
+ * keys in place; perm[k] = input index of the k-th output
+ * (RadixSort.cl.in:295-296), inv_perm[perm[k]] = k (:313-323).  key_max is an
+ * upper bound of the key values (n_cells.w for "icell", else 0 => full 32 bit;
+ * RadixSort.cpp:152-176).  perm / inv_perm may be NULL. */
+int aqc_radix_sort(aqc_ctx* ctx, aqc_usize* keys, aqc_usize n, aqc_usize key_max,
+                   aqc_usize* perm, aqc_usize* inv_perm);
+
+/* ---- UnSort tool (UnSort.cl.in:30-42) and the particle permutation of
+ * basic/Sort.cl:57-124: for f < nfields, dst[f][idx[i]] = src[f][i] --------- */
+int aqc_scatter_fields(aqc_ctx* ctx, const aqc_usize* idx, aqc_usize N, int nfields,
+                       const void* const* src, void* const* dst,
+                       const size_t* elem_bytes);
+
+/* ---- Reduction tool (Reduction.cpp:143-258; Reduction.cl.in:35-66).
+ * op: see enum; type: see enum.  The result is written to out_dev (device, may
+ * be NULL) and, when out_host != NULL, copied there (that variant syncs).
+ * Sums are evaluated in a fixed order (run-to-run deterministic). */
+enum { AQC_OP_SUM = 0, AQC_OP_MIN = 1, AQC_OP_MAX = 2 };
+enum { AQC_T_F32 = 0, AQC_T_U32 = 1, AQC_T_I32 = 2, AQC_T_VEC2 = 3, AQC_T_VEC4 = 4 };
+int aqc_reduce(aqc_ctx* ctx, int op, int type, const void* in, size_t n,
+               void* out_dev, void* out_host);
+
+/* ---- Kernel tool (Kernel.cpp:301-352, 497-556).  The reference compiles an
+ * OpenCL script and reflects the argument NAMES with clGetKernelArgInfo; here
+ * the hot-path scripts are pre-built CUDA kernels kept in a registry keyed by
+ * the script path (as written in the presets, e.g. "cfd/Interactions.cl" --
+ * any leading directories up to "Scripts/" are ignored) and entry point. ----- */
+enum { AQC_ARG_ARRAY_IN = 0, AQC_ARG_ARRAY_OUT = 1, AQC_ARG_SCALAR = 2 };
+typedef struct {
+    const char* name; /* Variable name to bind (Kernel.cpp:497-556) */
+    const char* type; /* reference type string: "vec*", "float", "usize", "svec4", ... */
+    int kind;         /* AQC_ARG_* ; ARRAY_OUT = non-const __global pointer */
+} aqc_arg_info;
+/* returns kernel id >= 0, or AQC_ERR_NOKERNEL */
+int aqc_kernel_lookup(const char* script_path, const char* entry, int dims);
+int aqc_kernel_count(void);
+const char* aqc_kernel_name(int kernel_id); /* "cfd/Interactions.cl::entry" */
+int aqc_kernel_nargs(int kernel_id);
+const aqc_arg_info* aqc_kernel_args(int kernel_id);
+/* clSetKernelArg + clEnqueueNDRangeKernel (Kernel.cpp:324-352): args[k] is the
+ * device pointer for array arguments, or a HOST pointer to the scalar value
+ * (float, uint, vec = 2/4 floats, svec4 = 4 uints) for scalar arguments, in
+ * registry order.  n = global work size (Kernel.cpp:558-594). */
+int aqc_launch(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nargs);
+
+/* ---- events / profiling (Tool.cpp:296-310, Kernel.cpp:48-116) ------------ */
+int aqc_event_create(aqc_ctx* ctx, void** ev);
+int aqc_event_destroy(aqc_ctx* ctx, void* ev);
+int aqc_event_record(aqc_ctx* ctx, void* ev);
+int aqc_event_sync(aqc_ctx* ctx, void* ev);
+int aqc_event_elapsed_ms(aqc_ctx* ctx, void* start, void* stop, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

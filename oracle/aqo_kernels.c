@@ -1,0 +1,1060 @@
+/* aqo_kernels.c -- CPU ORACLE (test infrastructure, not product code).
+ * Restates the preset script kernels of AQUAgpusph 5.0.4 that sit on the
+ * per-time-step hot path (paths below are under resources/Scripts/).
+ * See aqo.h for conventions.  Summation order follows the reference exactly:
+ * cells x-outer / y / z-inner, ascending sorted index inside a cell
+ * (types/3D.h:197-219, types/2D.h:174-193). */
+#include "aqo.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define VS(dims) ((dims) == 3 ? 4 : 2)
+#define MS(dims) ((dims) == 3 ? 16 : 4)
+#define iM_PI 0.318309886f /* KernelFunctions/Wendland3D.hcl:34-39 */
+
+/* BEGIN_NEIGHS / END_NEIGHS, types/3D.h:197-219 and types/2D.h:174-193.
+ * Cell ids use unsigned wrap-around arithmetic like the OpenCL source. */
+#define NEIGHS_BEGIN(L, i, dims)                                               \
+    {                                                                          \
+        const aqo_usize c_i__ = (L)->icell[i];                                 \
+        const aqo_usize nx__ = (L)->ncells[0], ny__ = (L)->ncells[1];          \
+        const int kz__ = ((dims) == 3) ? 1 : 0;                                \
+        for (int ci__ = -1; ci__ <= 1; ci__++)                                 \
+            for (int cj__ = -1; cj__ <= 1; cj__++)                             \
+                for (int ck__ = -kz__; ck__ <= kz__; ck__++) {                 \
+                    const aqo_usize c_j__ =                                    \
+                        c_i__ + (aqo_usize)ci__ + (aqo_usize)cj__ * nx__ +     \
+                        (aqo_usize)ck__ * nx__ * ny__;                         \
+                    for (aqo_usize j = (L)->ihoc[c_j__];                       \
+                         (j < (L)->N) && ((L)->icell[j] == c_j__); j++) {
+#define NEIGHS_END                                                             \
+                    }                                                          \
+                }                                                              \
+    }
+
+static inline float dotv(const float* a, const float* b, int dims)
+{
+    float s = a[0] * b[0] + a[1] * b[1];
+    if (dims == 3)
+        s += a[2] * b[2];
+    return s;
+}
+
+/* KernelFunctions/Wendland3D.hcl:44-66, Wendland2D.hcl:44-66 */
+static inline float kernelW(float q, int dims)
+{
+    const float wcon = (dims == 3 ? 0.08203125f : 0.109375f) * iM_PI;
+    return wcon * (1.f + 2.f * q) * (2.f - q) * (2.f - q) * (2.f - q) * (2.f - q);
+}
+static inline float kernelF(float q, int dims)
+{
+    const float wcon = (dims == 3 ? 0.8203125f : 1.09375f) * iM_PI;
+    return wcon * (2.f - q) * (2.f - q) * (2.f - q);
+}
+
+/* r_ij = r_j - r_i, q = length(r_ij) / H; returns 0 when q >= SUPPORT */
+static inline int pair_q(const aqo_defs* D, const float* ri, const float* rj,
+                         float* r_ij, float* q)
+{
+    for (int d = 0; d < D->dims; d++)
+        r_ij[d] = rj[d] - ri[d];
+    *q = sqrtf(dotv(r_ij, r_ij, D->dims)) / D->H;
+    return *q < D->SUPPORT;
+}
+
+/* ======================= element-wise kernels ============================ */
+
+/* basic/EOS.cl:57-73; EXCLUDED_PARTICLE = (imove <= 0) && (imove != -1) */
+void aqo_eos(const aqo_usize* iset, const int* imove, const float* rho,
+             float* p, const float* refd, aqo_usize N, float cs, float p0)
+{
+    for (aqo_usize i = 0; i < N; i++) {
+        if ((imove[i] <= 0) && (imove[i] != -1))
+            continue;
+        p[i] = p0 + cs * cs * (rho[i] - refd[iset[i]]);
+    }
+}
+
+/* cfd/Rates.cl:55-77 (whole vec, incl. w in 3D) */
+void aqo_rates(const aqo_usize* iset, const int* imove, const float* rho,
+               const float* grad_p, const float* lap_u, const float* div_u,
+               float* dudt, float* drhodt, const float* visc_dyn, aqo_usize N,
+               const float* g, int dims)
+{
+    (void)rho;
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float mu = visc_dyn[iset[i]];
+        for (int c = 0; c < vs; c++)
+            dudt[(size_t)i * vs + c] = -grad_p[(size_t)i * vs + c] +
+                                       mu * lap_u[(size_t)i * vs + c] + g[c];
+        drhodt[i] = -div_u[i];
+    }
+}
+
+/* cfd/TimeStep.cl:56-77; length(u[i]) is over the whole vec (4 comps in 3D) */
+void aqo_timestep(const int* imove, const float* u, float* dt_var, aqo_usize N,
+                  float dt, float dt_min, float courant, float dt_Ma, float h,
+                  int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0) {
+            dt_var[i] = dt;
+            continue;
+        }
+        const float* ui = u + (size_t)i * vs;
+        float s = ui[0] * ui[0] + ui[1] * ui[1];
+        if (dims == 3)
+            s = s + ui[2] * ui[2] + ui[3] * ui[3];
+        const float dr_max = dt_Ma * h;
+        const float dt_u = courant * dr_max / sqrtf(s);
+        dt_var[i] = fmaxf(fminf(dt, dt_u), dt_min);
+    }
+}
+
+/* cfd/variableTimeStep.xml:11-16: reduction "c = min(a, b)" null INFINITY */
+float aqo_reduce_min(const float* v, aqo_usize N)
+{
+    float m = INFINITY;
+    for (aqo_usize i = 0; i < N; i++)
+        m = fminf(m, v[i]);
+    return m;
+}
+float aqo_reduce_max(const float* v, aqo_usize N)
+{
+    float m = -INFINITY;
+    for (aqo_usize i = 0; i < N; i++)
+        m = fmaxf(m, v[i]);
+    return m;
+}
+aqo_usize aqo_reduce_max_u32(const aqo_usize* v, aqo_usize N)
+{
+    aqo_usize m = 0;
+    for (aqo_usize i = 0; i < N; i++)
+        m = v[i] > m ? v[i] : m;
+    return m;
+}
+
+/* Reduction.cl.in:35-66 + Reduction.cpp:376-436: each pass reduces groups of
+ * wg consecutive items with a halving tree (lmem[t] += lmem[t + s],
+ * s = wg/2 ... 1), out-of-range items hold the identity; passes repeat on the
+ * per-group results until one value is left. */
+void aqo_reduce_sum_vec_tree(const float* v, aqo_usize N, int ncomp,
+                             aqo_usize wg, float* out)
+{
+    size_t n = N;
+    float* cur = (float*)malloc(sizeof(float) * ncomp * (n ? n : 1));
+    memcpy(cur, v, sizeof(float) * ncomp * n);
+    float* lmem = (float*)malloc(sizeof(float) * ncomp * wg);
+    if (n == 0)
+        for (int c = 0; c < ncomp; c++)
+            cur[c] = 0.f;
+    while (n > 1) {
+        const size_t groups = (n + wg - 1) / wg;
+        for (size_t g = 0; g < groups; g++) {
+            for (aqo_usize t = 0; t < wg; t++)
+                for (int c = 0; c < ncomp; c++) {
+                    const size_t gid = g * wg + t;
+                    lmem[t * ncomp + c] = gid < n ? cur[gid * ncomp + c] : 0.f;
+                }
+            for (aqo_usize s = wg / 2; s > 0; s >>= 1)
+                for (aqo_usize t = 0; t < s; t++)
+                    for (int c = 0; c < ncomp; c++)
+                        lmem[t * ncomp + c] =
+                            lmem[t * ncomp + c] + lmem[(t + s) * ncomp + c];
+            for (int c = 0; c < ncomp; c++)
+                cur[g * ncomp + c] = lmem[c];
+        }
+        n = groups;
+    }
+    for (int c = 0; c < ncomp; c++)
+        out[c] = cur[c];
+    free(cur);
+    free(lmem);
+}
+float aqo_reduce_sum_tree(const float* v, aqo_usize N, aqo_usize wg)
+{
+    float out;
+    aqo_reduce_sum_vec_tree(v, N, 1, wg, &out);
+    return out;
+}
+
+/* basic/Domain.cl:48-90 */
+void aqo_domain(int* imove, float* r_in, float* u_in, float* dudt_in, float* m,
+                aqo_usize N, const float* domain_min, const float* domain_max,
+                int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= -255)
+            continue;
+        const float* c = r_in + (size_t)i * vs;
+        int out = 0;
+        for (int d = 0; d < dims; d++)
+            out |= isnan(c[d]) || isinf(c[d]) || (c[d] < domain_min[d]) ||
+                   (c[d] > domain_max[d]);
+        if (!out)
+            continue;
+        imove[i] = -256;
+        m[i] = 0.f;
+        for (int d = 0; d < vs; d++) {
+            u_in[(size_t)i * vs + d] = 0.f;
+            dudt_in[(size_t)i * vs + d] = 0.f;
+            r_in[(size_t)i * vs + d] = domain_max[d];
+        }
+    }
+}
+
+/* basic/Binormal.cl:37-53 */
+void aqo_binormal(const float* normal, float* tangent, float* binormal,
+                  aqo_usize N, int dims)
+{
+    for (aqo_usize i = 0; i < N; i++) {
+        if (dims == 2) {
+            binormal[2 * (size_t)i] = 0.f;
+            binormal[2 * (size_t)i + 1] = 0.f;
+            tangent[2 * (size_t)i] = normal[2 * (size_t)i + 1];
+            tangent[2 * (size_t)i + 1] = -normal[2 * (size_t)i];
+        } else {
+            const float* a = normal + 4 * (size_t)i;
+            const float* b = tangent + 4 * (size_t)i;
+            float* o = binormal + 4 * (size_t)i;
+            /* OpenCL cross(float4, float4): w = 0 */
+            const float x = a[1] * b[2] - a[2] * b[1];
+            const float y = a[2] * b[0] - a[0] * b[2];
+            const float z = a[0] * b[1] - a[1] * b[0];
+            o[0] = x;
+            o[1] = y;
+            o[2] = z;
+            o[3] = 0.f;
+        }
+    }
+}
+
+/* ----------------------------- time schemes ------------------------------ */
+static void copy_state(const float* r, const float* u, const float* dudt,
+                       const float* rho, const float* drhodt, float* r_in,
+                       float* u_in, float* dudt_in, float* rho_in,
+                       float* drhodt_in, aqo_usize N, int dims)
+{
+    const size_t vb = sizeof(float) * VS(dims) * (size_t)N;
+    memcpy(dudt_in, dudt, vb);
+    memcpy(u_in, u, vb);
+    memcpy(r_in, r, vb);
+    memcpy(drhodt_in, drhodt, sizeof(float) * (size_t)N);
+    memcpy(rho_in, rho, sizeof(float) * (size_t)N);
+}
+
+/* basic/time_scheme/euler.cl:65-87 */
+void aqo_euler_predictor(const float* r, const float* u, const float* dudt,
+                         const float* rho, const float* drhodt, float* r_in,
+                         float* u_in, float* dudt_in, float* rho_in,
+                         float* drhodt_in, aqo_usize N, int dims)
+{
+    copy_state(r, u, dudt, rho, drhodt, r_in, u_in, dudt_in, rho_in, drhodt_in,
+               N, dims);
+}
+
+/* basic/time_scheme/euler.cl:105-124 */
+void aqo_euler_corrector(const int* imove, float* r, float* u,
+                         const float* dudt, float* rho, const float* drhodt,
+                         aqo_usize N, float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0)
+            continue;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            r[k] += dt * u[k] + 0.5f * dt * dt * dudt[k];
+            u[k] += dt * dudt[k];
+        }
+        rho[i] += dt * drhodt[i];
+    }
+}
+
+/* basic/time_scheme/improved_euler.cl:75-103 */
+void aqo_ie_predictor(const int* imove, const float* r, const float* u,
+                      const float* dudt, const float* rho, const float* drhodt,
+                      float* r_in, float* u_in, float* dudt_in, float* rho_in,
+                      float* drhodt_in, aqo_usize N, float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        const float DT = (imove[i] <= 0) ? 0.f : dt;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            dudt_in[k] = dudt[k];
+            u_in[k] = u[k] + DT * dudt[k];
+            r_in[k] = r[k] + DT * u[k] + 0.5f * DT * DT * dudt[k];
+        }
+        drhodt_in[i] = drhodt[i];
+        rho_in[i] = rho[i] + DT * drhodt[i];
+    }
+}
+
+/* basic/time_scheme/improved_euler.cl:125-147 */
+void aqo_ie_corrector(const int* imove, float* r, float* u, const float* dudt,
+                      float* rho, const float* drhodt, const float* dudt_in,
+                      const float* drhodt_in, aqo_usize N, float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0)
+            continue;
+        const float DT = 0.5f * dt;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            u[k] += DT * (dudt[k] - dudt_in[k]);
+            r[k] += DT * DT * (dudt[k] - dudt_in[k]);
+        }
+        rho[i] += DT * (drhodt[i] - drhodt_in[i]);
+    }
+}
+
+/* basic/time_scheme/midpoint.cl:53-75 */
+void aqo_mp_predictor(const float* r, const float* u, const float* dudt,
+                      const float* rho, const float* drhodt, float* r_in,
+                      float* u_in, float* dudt_in, float* rho_in,
+                      float* drhodt_in, aqo_usize N, int dims)
+{
+    copy_state(r, u, dudt, rho, drhodt, r_in, u_in, dudt_in, rho_in, drhodt_in,
+               N, dims);
+}
+
+/* basic/time_scheme/midpoint.cl:93-111 */
+void aqo_mp_midpoint(const int* imove, const float* u_in, float* u,
+                     const float* dudt, const float* rho_in, float* rho,
+                     const float* drhodt, aqo_usize N, float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0)
+            continue;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            u[k] = u_in[k] + 0.5f * dt * dudt[k];
+        }
+        rho[i] = rho_in[i] + 0.5f * dt * drhodt[i];
+    }
+}
+
+/* basic/time_scheme/midpoint.cl:141-157 */
+void aqo_mp_relax(const int* imove, const float* dudt_in, float* dudt,
+                  const float* drhodt_in, float* drhodt, aqo_usize N,
+                  float relax, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0)
+            continue;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            dudt[k] = relax * dudt_in[k] + (1.f - relax) * dudt[k];
+        }
+        drhodt[i] = relax * drhodt_in[i] + (1.f - relax) * drhodt[i];
+    }
+}
+
+/* basic/time_scheme/midpoint.cl:159-184; dot() over the whole vec */
+void aqo_mp_residuals(const int* imove, const float* m, const float* u,
+                      const float* dudt_in, const float* dudt, const float* rho,
+                      const float* p, const float* drhodt_in,
+                      const float* drhodt, float* residual, aqo_usize N,
+                      int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0) {
+            residual[i] = 0.f;
+            continue;
+        }
+        const float rho2 = rho[i] * rho[i];
+        float d = 0.f;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            const float t = u[k] * (dudt[k] - dudt_in[k]);
+            d = (c == 0) ? t : d + t;
+        }
+        residual[i] = m[i] * (fabsf(d) +
+                              fabsf(p[i] / rho2 * (drhodt[i] - drhodt_in[i])));
+    }
+}
+
+/* basic/time_scheme/midpoint.cl:206-227 */
+void aqo_mp_corrector(const int* imove, const float* r_in, float* r,
+                      const float* u_in, float* u, const float* dudt,
+                      const float* rho_in, float* rho, const float* drhodt,
+                      aqo_usize N, float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= 0)
+            continue;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            r[k] = r_in[k] + dt * u_in[k] + 0.5f * dt * dt * dudt[k];
+            u[k] = u_in[k] + dt * dudt[k];
+        }
+        rho[i] = rho_in[i] + dt * drhodt[i];
+    }
+}
+
+/* ========================== neighbour sweeps ============================= */
+
+/* cfd/Interactions.cl:60-145, __LAP_FORMULATION__ == __LAP_MONAGHAN__
+ * (cfd.xml:52-54), __CLEARY__ = 8 (2D) / 10 (3D) (:33-39).  Built with
+ * LOCAL_MEM_SIZE, i.e. the outputs are overwritten, not accumulated
+ * (:140-144); only the XYZ components are written (w untouched). */
+void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                      const float* r, const float* u, const float* rho,
+                      const float* m, const float* p, float* grad_p,
+                      float* lap_u, float* div_u)
+{
+    const int dims = D->dims, vs = VS(dims);
+    const float cleary = (dims == 3) ? 10.f : 8.f;
+    const float H = D->H;
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* u_i = u + (size_t)i * vs;
+        const float p_i = p[i], rho_i = rho[i];
+        float gp[3] = { 0.f, 0.f, 0.f }, lu[3] = { 0.f, 0.f, 0.f }, du = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (i == j)
+                continue;
+            if (imove[j] != 1)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float rho_j = rho[j], p_j = p[j];
+            float u_ij[3];
+            for (int d = 0; d < dims; d++)
+                u_ij[d] = u[(size_t)j * vs + d] - u_i[d];
+            const float udr = dotv(u_ij, r_ij, dims);
+            const float f_ij = kernelF(q, dims) * D->CONF * m[j];
+            const float pf = (p_i + p_j) / (rho_i * rho_j) * f_ij;
+            const float r2 = (q * q + 0.01f) * H * H;
+            const float lf = f_ij * cleary * udr / (r2 * rho_i * rho_j);
+            for (int d = 0; d < dims; d++) {
+                gp[d] += pf * r_ij[d];
+                lu[d] += lf * r_ij[d];
+            }
+            du += udr * f_ij * rho_i / rho_j;
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++) {
+            grad_p[(size_t)i * vs + d] = gp[d];
+            lap_u[(size_t)i * vs + d] = lu[d];
+        }
+        div_u[i] = du;
+    }
+}
+
+/* basic/Shepard.cl:76-125 (cfd_mode 0, EXCLUDED = imove >= 3) and
+ * cfd/Shepard.cl:29-35 (cfd_mode 1, EXCLUDED = imove != 1).  The self term is
+ * included (no i == j test). */
+void aqo_shepard(const aqo_defs* D, const aqo_ll* L, int cfd_mode,
+                 const int* imove, const float* r, const float* rho,
+                 const float* m, float* shepard)
+{
+    const int dims = D->dims, vs = VS(dims);
+#define SH_EXCL(k) (cfd_mode ? (imove[k] != 1) : (imove[k] >= 3))
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if ((imove[i] < -3) || ((imove[i] > 0) && SH_EXCL(i)))
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float s = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (SH_EXCL(j))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            s += kernelW(q, dims) * D->CONW * m[j] / rho[j];
+        }
+        NEIGHS_END
+        shepard[i] = s;
+    }
+#undef SH_EXCL
+}
+
+/* basic/neighs.cl:52-91 */
+void aqo_neighs(const aqo_ll* L, const int* imove, aqo_usize* n_neighs,
+                aqo_usize neighs_limit, int dims)
+{
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] <= -255) {
+            n_neighs[i] = 0;
+            continue;
+        }
+        aqo_usize n = 0;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            n += 1;
+            if (n >= neighs_limit)
+                goto done;
+        }
+        NEIGHS_END
+    done:
+        n_neighs[i] = n;
+    }
+}
+
+/* cfd/Sensors.cl:57-130 */
+void aqo_sensors(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                 const float* r, const float* m, float* u, float* rho,
+                 float* p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 0)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float ua[3] = { 0.f, 0.f, 0.f }, ra = 0.f, pa = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (i == j)
+                continue;
+            if (imove[j] != 1)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float rho_j = rho[j], m_j = m[j], p_j = p[j];
+            const float w_ij = kernelW(q, dims) * D->CONW * m_j / rho_j;
+            for (int d = 0; d < dims; d++)
+                ua[d] += u[(size_t)j * vs + d] * w_ij;
+            ra += rho_j * w_ij;
+            pa += p_j * w_ij;
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            u[(size_t)i * vs + d] = ua[d];
+        rho[i] = ra;
+        p[i] = pa;
+    }
+}
+
+/* cfd/SensorsRenormalization.cl:42-67 (whole vec divided) */
+void aqo_sensors_renorm(const int* imove, const float* shepard, float* u,
+                        float* rho, float* p, aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 0)
+            continue;
+        float s = shepard[i];
+        if (s < 1.0E-6f)
+            s = 1.f;
+        for (int c = 0; c < vs; c++)
+            u[(size_t)i * vs + c] /= s;
+        rho[i] /= s;
+        p[i] /= s;
+    }
+}
+
+/* ------------------------------ delta-SPH -------------------------------- */
+/* basic/deltaSPH.cl:57-71 */
+void aqo_dsph_simple(const aqo_usize* iset, const int* imove, float* lap_p_corr,
+                     const float* refd, aqo_usize N, const float* g, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 1)
+            continue;
+        for (int c = 0; c < vs; c++)
+            lap_p_corr[(size_t)i * vs + c] = refd[iset[i]] * g[c];
+    }
+}
+
+/* basic/deltaSPH.cl:94-145 */
+void aqo_dsph_full(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                   const float* r, const float* rho, const float* m,
+                   const float* p, float* lap_p_corr)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float p_i = p[i];
+        float gp[3] = { 0.f, 0.f, 0.f };
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((i == j) || (imove[j] != 1))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float f_ij = kernelF(q, dims) * D->CONF * m[j] / rho[j];
+            const float c = (p[j] - p_i) * f_ij;
+            for (int d = 0; d < dims; d++)
+                gp[d] += c * r_ij[d];
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            lap_p_corr[(size_t)i * vs + d] = gp[d];
+    }
+}
+
+/* basic/deltaSPH.cl:160-173; MATRIX_DOT types/3D.h:225-229, 2D.h:199-201 */
+void aqo_dsph_full_mls(const int* imove, const float* mls, float* lap_p_corr,
+                       aqo_usize N, int dims)
+{
+    const int vs = VS(dims), ms = MS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* M = mls + (size_t)i * ms;
+        float* v = lap_p_corr + (size_t)i * vs;
+        if (dims == 3) {
+            const float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
+            const float y = M[4] * v[0] + M[5] * v[1] + M[6] * v[2];
+            const float z = M[8] * v[0] + M[9] * v[1] + M[10] * v[2];
+            v[0] = x;
+            v[1] = y;
+            v[2] = z;
+            v[3] = 0.f;
+        } else {
+            const float x = M[0] * v[0] + M[1] * v[1];
+            const float y = M[2] * v[0] + M[3] * v[1];
+            v[0] = x;
+            v[1] = y;
+        }
+    }
+}
+
+/* basic/deltaSPH.cl:191-242 */
+void aqo_dsph_lapp(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                   const float* r, const float* rho, const float* m,
+                   const float* p, float* lap_p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float p_i = p[i];
+        float lp = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((i == j) || (imove[j] != 1))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float f_ij = kernelF(q, dims) * D->CONF * m[j] / rho[j];
+            lp += (p[j] - p_i) * f_ij;
+        }
+        NEIGHS_END
+        lap_p[i] = lp;
+    }
+}
+
+/* basic/deltaSPH.cl:261-313: starts from the old lap_p[i] (:287) */
+void aqo_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                        const float* r, const float* rho, const float* m,
+                        const float* lap_p_corr, float* lap_p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* g_i = lap_p_corr + (size_t)i * vs;
+        float lp = lap_p[i];
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((i == j) || (imove[j] != 1))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            float g_ij[3];
+            for (int d = 0; d < dims; d++)
+                g_ij[d] = lap_p_corr[(size_t)j * vs + d] + g_i[d];
+            const float f_ij = kernelF(q, dims) * D->CONF * m[j] / rho[j];
+            lp -= 0.5f * dotv(g_ij, r_ij, dims) * f_ij;
+        }
+        NEIGHS_END
+        lap_p[i] = lp;
+    }
+}
+
+/* basic/deltaSPH.cl:330-350 */
+void aqo_dsph_apply(const aqo_usize* iset, const int* imove, const float* rho,
+                    const float* lap_p, float* drhodt, const float* refd,
+                    const float* delta, aqo_usize N, float dt)
+{
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const aqo_usize s = iset[i];
+        const float delta_f = delta[s] * dt * rho[i] / refd[s];
+        drhodt[i] += delta_f * lap_p[i];
+    }
+}
+
+/* --------------------------------- MLS ----------------------------------- */
+/* basic/MLS.cl:58-112; outer(): types/3D.h:290-297, 2D.h:241-247.  imove is
+ * compared with the unsigned mls_imove (int -> uint conversion). */
+void aqo_mls(const aqo_defs* D, const aqo_ll* L, const int* imove,
+             const float* r, const float* rho, const float* m, float* mls,
+             aqo_usize mls_imove)
+{
+    const int dims = D->dims, vs = VS(dims), ms = MS(dims);
+    const int rs = (dims == 3) ? 4 : 2; /* row stride of the matrix */
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if ((aqo_usize)imove[i] != mls_imove)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float M[16];
+        for (int k = 0; k < 16; k++)
+            M[k] = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (i == j)
+                continue;
+            if ((aqo_usize)imove[j] != mls_imove)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float f_ij = kernelF(q, dims) * D->CONF * m[j] / rho[j];
+            for (int a = 0; a < dims; a++)
+                for (int b = 0; b < dims; b++)
+                    M[a * rs + b] += r_ij[a] * (f_ij * r_ij[b]);
+        }
+        NEIGHS_END
+        memcpy(mls + (size_t)i * ms, M, sizeof(float) * ms);
+    }
+}
+
+/* types/3D.h:300-341 (det, inv, MATRIX_INV), 2D.h:250-282 */
+static void mat3_mul(const float* A, const float* B, float* C)
+{
+    /* MATRIX_MUL, 3D.h:241-245: 3x3 block, last row/col zero */
+    for (int k = 0; k < 16; k++)
+        C[k] = 0.f;
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++)
+            C[a * 4 + b] = A[a * 4 + 0] * B[0 * 4 + b] +
+                           A[a * 4 + 1] * B[1 * 4 + b] +
+                           A[a * 4 + 2] * B[2 * 4 + b];
+}
+static void mat3_T(const float* A, float* T)
+{
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++)
+            T[a * 4 + b] = A[b * 4 + a];
+}
+static void mat3_inv(const float* m, float* o)
+{
+    const float det = m[0] * (m[5] * m[10] - m[6] * m[9]) +
+                      m[1] * (m[6] * m[8] - m[4] * m[10]) +
+                      m[2] * (m[4] * m[9] - m[5] * m[8]);
+    const float d = 1.f / det;
+    for (int k = 0; k < 16; k++)
+        o[k] = 0.f;
+    if (fabsf(d) > 1.e16f) {
+        o[0] = o[5] = o[10] = o[15] = 1.f; /* MAT_ALL_EYE */
+        return;
+    }
+    o[0] = (m[5] * m[10] - m[6] * m[9]) * d;
+    o[1] = (m[2] * m[9] - m[1] * m[10]) * d;
+    o[2] = (m[1] * m[6] - m[2] * m[5]) * d;
+    o[4] = (m[6] * m[8] - m[4] * m[10]) * d;
+    o[5] = (m[0] * m[10] - m[2] * m[8]) * d;
+    o[6] = (m[2] * m[4] - m[0] * m[6]) * d;
+    o[8] = (m[4] * m[9] - m[5] * m[8]) * d;
+    o[9] = (m[1] * m[8] - m[0] * m[9]) * d;
+    o[10] = (m[0] * m[5] - m[1] * m[4]) * d;
+    o[15] = 1.f;
+}
+
+/* basic/MLS.cl:130-143 */
+void aqo_mls_inv(const int* imove, float* mls, aqo_usize N,
+                 aqo_usize mls_imove, int dims)
+{
+    for (aqo_usize i = 0; i < N; i++) {
+        if ((aqo_usize)imove[i] != mls_imove)
+            continue;
+        if (dims == 3) {
+            float* M = mls + 16 * (size_t)i;
+            float T[16], TM[16], I[16], R[16];
+            mat3_T(M, T);
+            mat3_mul(T, M, TM);
+            mat3_inv(TM, I);
+            mat3_mul(I, T, R);
+            memcpy(M, R, sizeof(R));
+        } else {
+            float* M = mls + 4 * (size_t)i;
+            /* T = M.s0213 ; TM = MATRIX_MUL(T, M) (2D.h:205-208) */
+            const float T[4] = { M[0], M[2], M[1], M[3] };
+            float TM[4] = { T[0] * M[0] + T[1] * M[2], T[0] * M[1] + T[1] * M[3],
+                            T[2] * M[0] + T[3] * M[2], T[2] * M[1] + T[3] * M[3] };
+            const float d = 1.f / (TM[0] * TM[3] - TM[1] * TM[2]);
+            float I[4];
+            if (fabsf(d) > 1.e16f) {
+                /* 2D.h:274 returns MAT_ALL_EYE, which 2D.h never defines: the
+                 * reference would not compile that branch in 2-D; the
+                 * Reduction header's MAT_EYE (1,0,0,1) is the evident intent */
+                I[0] = 1.f; I[1] = 0.f; I[2] = 0.f; I[3] = 1.f;
+            } else {
+                I[0] = TM[3] * d; I[1] = -TM[1] * d;
+                I[2] = -TM[2] * d; I[3] = TM[0] * d;
+            }
+            const float R[4] = { I[0] * T[0] + I[1] * T[2], I[0] * T[1] + I[1] * T[3],
+                                 I[2] * T[0] + I[3] * T[2], I[2] * T[1] + I[3] * T[3] };
+            memcpy(M, R, sizeof(R));
+        }
+    }
+}
+
+/* ------------------------------- BIe ------------------------------------- */
+/* cfd/Boundary/BIe/Interactions.cl:48-108 */
+void aqo_bie_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                          const float* r, const float* normal, const float* u,
+                          const float* m, float* grad_w_bi, float* div_u_bi)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float gw[3] = { 0.f, 0.f, 0.f }, du = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (imove[j] != -3)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float* n_j = normal + (size_t)j * vs;
+            const float* u_j = u + (size_t)j * vs;
+            const float area_j = m[j];
+            const float w = kernelW(q, dims) * D->CONW * area_j;
+            float grad_w[3];
+            for (int d = 0; d < dims; d++) {
+                grad_w[d] = n_j[d] * w;
+                gw[d] += grad_w[d];
+            }
+            du -= dotv(u_j, grad_w, dims);
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            grad_w_bi[(size_t)i * vs + d] = gw[d];
+        div_u_bi[i] = du;
+    }
+}
+
+/* cfd/Boundary/BIe/Interactions.cl:124-170 */
+void aqo_bie_p_boundary(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                        const float* r, const float* m, const float* rho,
+                        float* p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != -3)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float pa = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (imove[j] != 1)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            pa += 2.f * p[j] * kernelW(q, dims) * D->CONW * m[j] / rho[j];
+        }
+        NEIGHS_END
+        p[i] = pa;
+    }
+}
+
+/* cfd/Boundary/BIe/Rates.cl:44-62 (whole vec arithmetic) */
+void aqo_bie_rates(const int* imove, const float* rho, const float* p,
+                   const float* u, const float* grad_w_bi,
+                   const float* div_u_bi, float* grad_p, float* div_u,
+                   aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float f = 2.f * p[i] / rho[i];
+        float d = 0.f;
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            grad_p[k] += f * grad_w_bi[k];
+            const float t = u[k] * grad_w_bi[k];
+            d = (c == 0) ? t : d + t;
+        }
+        div_u[i] -= 2.f * rho[i] * (d + div_u_bi[i]);
+    }
+}
+
+/* cfd/Boundary/BIe/Rates.cl:76-91 */
+void aqo_bie_filter_press(const aqo_usize* iset, const int* imove, float* p,
+                          aqo_usize forces_iset, aqo_usize N)
+{
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] != -3)
+            continue;
+        if (iset[i] != forces_iset)
+            p[i] = 0.f;
+    }
+}
+
+/* cfd/Boundary/BIe/Rates.cl:109-135; moment_p is always a vec4 */
+void aqo_bie_force_press(const int* imove, const float* r, const float* normal,
+                         const float* m, const float* p, float* force_p,
+                         float* moment_p, const float* forces_r, aqo_usize N,
+                         int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        float* fo = force_p + (size_t)i * vs;
+        float* mo = moment_p + (size_t)i * 4;
+        if (imove[i] != -3) {
+            for (int c = 0; c < vs; c++)
+                fo[c] = 0.f;
+            mo[0] = mo[1] = mo[2] = mo[3] = 0.f;
+            continue;
+        }
+        float F[4] = { 0.f, 0.f, 0.f, 0.f }, R[4] = { 0.f, 0.f, 0.f, 0.f };
+        for (int d = 0; d < dims; d++) {
+            F[d] = p[i] * m[i] * normal[(size_t)i * vs + d];
+            R[d] = r[(size_t)i * vs + d] - forces_r[d];
+            fo[d] = F[d];
+        }
+        mo[0] = R[1] * F[2] - R[2] * F[1];
+        mo[1] = R[2] * F[0] - R[0] * F[2];
+        mo[2] = R[0] * F[1] - R[1] * F[0];
+        mo[3] = 0.f;
+    }
+}
+
+/* cfd/Boundary/BIe/ElasticBounce.cl:64-152; __DR_FACTOR__ = 0.5f (:31-33),
+ * __MIN_BOUND_DIST__ = 0.0f (:34-36).  Order dependent: state is mutated
+ * inside the neighbour loop. */
+void aqo_bie_elastic_bounce(const aqo_ll* L, const int* imove,
+                            const float* r_in, const float* normal,
+                            const float* m, const float* u_in, float* dudt,
+                            float dt, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        if (!dt)
+            continue;
+        const float* r_i = r_in + (size_t)i * vs;
+        const float* ui = u_in + (size_t)i * vs;
+        float dudt_l[3], U[3];
+        for (int d = 0; d < dims; d++) {
+            dudt_l[d] = dudt[(size_t)i * vs + d];
+            U[d] = ui[d] + 0.5f * dt * dudt_l[d];
+        }
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (imove[j] != -3)
+                continue;
+            float r_ij[3];
+            const float* n_j = normal + (size_t)j * vs;
+            for (int d = 0; d < dims; d++)
+                r_ij[d] = r_in[(size_t)j * vs + d] - r_i[d];
+            const float rn = dotv(r_ij, n_j, dims);
+            if (rn < 0.f)
+                continue;
+            const float dr = (dims == 3) ? sqrtf(m[j]) : m[j];
+            const float R = 0.5f * dr;
+            float rt[3];
+            for (int d = 0; d < dims; d++)
+                rt[d] = r_ij[d] - rn * n_j[d];
+            if (dotv(rt, rt, dims) >= R * R)
+                continue;
+            const float drn = dt * dotv(U, n_j, dims);
+            if (drn < 0.f)
+                continue;
+            if (rn - drn <= 0.0f * dr) {
+                float uu[3], u_r[3];
+                for (int d = 0; d < dims; d++)
+                    uu[d] = ui[d] + dt * dudt_l[d];
+                const float un = dotv(uu, n_j, dims);
+                for (int d = 0; d < dims; d++)
+                    u_r[d] = uu[d] - 2.f * un * n_j[d];
+                for (int d = 0; d < dims; d++) {
+                    dudt_l[d] = (u_r[d] - ui[d]) / dt;
+                    U[d] = ui[d] + 0.5f * dt * dudt_l[d];
+                }
+            }
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            dudt[(size_t)i * vs + d] = dudt_l[d];
+    }
+}
+
+/* cfd/Boundary/BIe/ElasticBounce.cl:168-184 */
+void aqo_bie_force_bound(const int* imove, const float* m,
+                         const float* dudt_preelastic,
+                         const float* dudt_elastic, float* force_elastic,
+                         aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++)
+        for (int c = 0; c < vs; c++) {
+            const size_t k = (size_t)i * vs + c;
+            force_elastic[k] = (imove[i] != 1) ? 0.f
+                : -m[i] * (dudt_elastic[k] - dudt_preelastic[k]);
+        }
+}
+
+/* cfd/Boundary/BIe/PST.cl:62-110.  DIMS is the evaluated define (a float
+ * literal, basic.xml:119).  Order dependent: r[i] moves inside the loop and is
+ * re-read for the next element. */
+void aqo_bie_pst(const aqo_ll* L, const int* imove, float* r,
+                 const float* normal, const float* m, const float* rho,
+                 float DIMS_define, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < L->N; i++) {
+        if (imove[i] != 1)
+            continue;
+        const float Ri = 0.5f * powf(m[i] / rho[i], 1.f / DIMS_define);
+        float* r_i = r + (size_t)i * vs;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (imove[j] != -3)
+                continue;
+            float r_ij[3];
+            const float* n_j = normal + (size_t)j * vs;
+            for (int d = 0; d < dims; d++)
+                r_ij[d] = r[(size_t)j * vs + d] - r_i[d];
+            const float rn = dotv(r_ij, n_j, dims);
+            if (fabsf(rn) > Ri)
+                continue;
+            const float dr = (dims == 3) ? sqrtf(m[j]) : m[j];
+            const float Rj = 0.5f * dr;
+            float rt[3];
+            for (int d = 0; d < dims; d++)
+                rt[d] = r_ij[d] - rn * n_j[d];
+            if (dotv(rt, rt, dims) >= Rj * Rj)
+                continue;
+            for (int d = 0; d < dims; d++)
+                r_i[d] += (rn - Ri) * n_j[d];
+        }
+        NEIGHS_END
+    }
+}
