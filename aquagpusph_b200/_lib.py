@@ -187,10 +187,28 @@ class Context:
         if h is not None:
             self.set_defs_from_h(dims, h)
 
+    @classmethod
+    def borrow(cls, handle, dims):
+        """Wrap an aqc_ctx* owned by someone else (the C++ host): never destroyed here."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(handle)
+        self.dims = dims
+        self.defs = None
+        self._borrowed = True
+        return self
+
+    def wrap(self, devptr, shape, dtype):
+        """A DevArray view over device memory owned elsewhere."""
+        a = DevArray.__new__(DevArray)
+        a.ctx, a.shape, a.dtype = self, tuple(shape), np.dtype(dtype)
+        a.nbytes = int(np.prod(a.shape)) * a.dtype.itemsize
+        a.ptr, a._owned = devptr, False
+        return a
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             lib().aqc_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def _chk(self, rc):
         if rc:

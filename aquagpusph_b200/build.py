@@ -70,7 +70,48 @@ def build(force=False, verbose=False):
     if force or jobs or _stale(LIB, objs):
         cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
         run(cmd)
+    build_host(force, verbose)
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+HOSTLIB = os.path.join(HERE, "libaquahost.so")
+HOSTEXE = os.path.join(HERE, "AQUAgpusph-b200")
+
+
+def build_host(force=False, verbose=False):
+    """C++ host (XML front-end, Variables, tools, scheduler) -> libaquahost.so + CLI."""
+    os.makedirs(OBJ, exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    flags = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-I" + os.path.join(ROOT, "include"),
+             "-I" + HOST]
+    hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
+    hdrs += [os.path.join(ROOT, "include", f) for f in ("aquacuda.h", "aquahost.h")]
+    hdrs.append(os.path.abspath(__file__))
+    srcs = sorted(f for f in os.listdir(HOST) if f.endswith(".cpp") and f != "main.cpp")
+    jobs, objs = [], []
+    for src in srcs + ["main.cpp"]:
+        obj = os.path.join(OBJ, "host_" + src[:-4] + ".o")
+        if src != "main.cpp":
+            objs.append(obj)
+        if force or _stale(obj, [os.path.join(HOST, src)] + hdrs):
+            jobs.append([cxx] + flags + ["-c", os.path.join(HOST, src), "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    link = ["-L" + HERE, "-laquacuda", "-Wl,-rpath,$ORIGIN"]
+    if force or jobs or _stale(HOSTLIB, objs + [LIB]):
+        run([cxx, "-shared", "-o", HOSTLIB] + objs + link)
+    main_o = os.path.join(OBJ, "host_main.o")
+    if force or jobs or _stale(HOSTEXE, [main_o, HOSTLIB]):
+        run([cxx, "-o", HOSTEXE, main_o, "-L" + HERE, "-laquahost", "-laquacuda",
+             "-Wl,-rpath,$ORIGIN"])
+    return HOSTLIB
 
 
 if __name__ == "__main__":

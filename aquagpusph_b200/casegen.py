@@ -1,0 +1,84 @@
+"""Instantiate the resolved case templates (aquagpusph_b200/cases_xml/*.xml) for a
+synthetic particle set and hand them to the C++ host.
+
+The templates are the reference's example pipelines flattened by
+tools/resolve_case.py; here the {{KEY}} placeholders of the example generators
+(examples/*/src/Create.py `data = {...}`) are filled, the <Load>/<Save> file
+references are dropped (arrays are uploaded from memory instead of FastASCII
+files) and a Simulation is created.
+"""
+import os
+import re
+import tempfile
+
+import numpy as np
+
+from . import host
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+TEMPLATES = os.path.join(_HERE, "cases_xml")
+
+STATE_FIELDS = ("r", "normal", "tangent", "u", "dudt", "rho", "drhodt", "m", "imove")
+
+
+def _vec(v):
+    return ", ".join(repr(float(x)) for x in v)
+
+
+def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
+    """Returns the XML text of `template` for the dict `case` (cases.py)."""
+    txt = open(os.path.join(TEMPLATES, template + ".xml")).read()
+    rep = {
+        "DR": repr(case["dr"]), "HFAC": repr(case.get("hfac", case["h"] / case["dr"])),
+        "CS": repr(case["cs"]), "COURANT": repr(case["courant"]),
+        "DOMAIN_MIN": _vec(case["domain_min"]), "DOMAIN_MAX": _vec(case["domain_max"]),
+        "REFD": repr(float(case["refd"][0])), "VISC_DYN": repr(float(case["visc_dyn"][0])),
+        "DELTA": repr(float(case["delta"][0])), "G": repr(float(-case["g"][case["dims"] - 1])),
+        "N": str(int(set_sizes[0])),
+        "N_SENSORS": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
+    }
+    for k, v in rep.items():
+        txt = txt.replace("{{%s}}" % k, v)
+    # particle data travel through aqh_array_upload, not through files
+    txt = re.sub(r"\s*<Load [^>]*/>", "", txt)
+    txt = re.sub(r"\s*<Save [^>]*/>", "", txt)
+    if not keep_reports:
+        # file/screen reports only cost host time; drop them like `-l 3` runs would hide them
+        txt = re.sub(r"\s*<Report [^>]*/>", "", txt)
+        txt = re.sub(r"\s*<Tool [^>]*type=\"report_(file|screen|performance)\"[^>]*/>", "", txt)
+    for name, value in (overrides or {}).items():
+        pat = r'(<Variable name="%s" [^>]*value=")[^"]*(")' % re.escape(name)
+        if not re.search(pat, txt):
+            raise KeyError("variable %s not found in template %s" % (name, template))
+        txt = re.sub(pat, lambda m: m.group(1) + str(value) + m.group(2), txt)
+    return txt
+
+
+def load(template, case, set_sizes, overrides=None, device=0, workdir=None, keep_reports=False,
+         mpi_rank=0, mpi_size=1):
+    """Create a Simulation for `case` and upload its particle arrays."""
+    txt = instantiate(template, case, set_sizes, overrides, keep_reports)
+    d = workdir or tempfile.mkdtemp(prefix="aqua_case_")
+    path = os.path.join(d, "%s.rank%d.xml" % (template, mpi_rank))
+    with open(path, "w") as f:
+        f.write(txt)
+    cwd = os.getcwd()
+    os.chdir(d)  # report files are written relative to the working directory
+    try:
+        sim = host.Simulation(path, dims=case["dims"], device=device, mpi_rank=mpi_rank,
+                              mpi_size=mpi_size)
+    finally:
+        os.chdir(cwd)
+    for k in STATE_FIELDS:
+        sim.upload(k, case[k])
+    sim.xml_path = path
+    return sim
+
+
+def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, **kw):
+    """BASELINE config 2 (3-D SPHERIC test 2 dam break) through the unchanged
+    116-tool pipeline of examples/3D/spheric_testcase2_dambreak."""
+    from . import cases
+    c = cases.spheric2_dam_break(n, hfac, seed=seed)
+    sim = load("spheric2_dambreak_3d", c, (c["N"] - 8, 8), overrides, device, **kw)
+    return sim, c

@@ -1,0 +1,230 @@
+"""Synthetic particle sets shared by the CPU and GPU tests and by bench.py.
+
+`dam_break(dims, n_side, ...)` builds a small version of the SPHERIC dam-break
+geometry of the reference examples (examples/{2D,3D}/spheric_testcase*_dambreak):
+a jittered fluid lattice (imove = 1) resting on boundary-integral elements
+(imove = -3, normals pointing out of the fluid, m = element area), a couple of
+sensors (imove = 0) and a few buffer particles (imove = -255) parked at
+domain_max, with a hydrostatic-ish density field and random velocities.
+"""
+import numpy as np
+
+
+def vs(dims):
+    return 4 if dims == 3 else 2
+
+
+def dam_break(dims=3, n_side=12, hfac=2.0, seed=1234, jitter=0.2, n_sensors=3, n_buffer=5,
+              shuffle=True):
+    rng = np.random.default_rng(seed)
+    dr = np.float32(0.01)
+    h = np.float32(hfac * dr)
+    cs, refd = np.float32(40.0), np.float32(998.0)
+    V = vs(dims)
+    # fluid block
+    ax = [np.arange(n_side) for _ in range(dims)]
+    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, dims).astype(np.float64)
+    rf = (g + 0.5) * dr + jitter * dr * rng.uniform(-1, 1, g.shape)
+    nf = rf.shape[0]
+    L = n_side * dr
+    # boundary elements: floor (last axis = 0 plane) and one wall (axis 0 = 0 plane)
+    bax = [np.arange(-2, n_side + 2) for _ in range(dims - 1)]
+    bg = np.stack(np.meshgrid(*bax, indexing="ij"), -1).reshape(-1, dims - 1).astype(np.float64)
+    nb1 = bg.shape[0]
+    floor = np.zeros((nb1, dims))
+    floor[:, :dims - 1] = (bg + 0.5) * dr
+    nfloor = np.zeros((nb1, dims)); nfloor[:, dims - 1] = -1.0
+    wall = np.zeros((nb1, dims))
+    wall[:, 1:] = (bg + 0.5) * dr
+    nwall = np.zeros((nb1, dims)); nwall[:, 0] = -1.0
+    rb = np.concatenate([floor, wall]); nrm = np.concatenate([nfloor, nwall])
+    nb = rb.shape[0]
+    # sensors inside the fluid, buffer particles far away
+    rs = rng.uniform(0.2 * L, 0.8 * L, (n_sensors, dims))
+    domain_min = np.full(dims, -0.5 * L - 0.1)
+    domain_max = np.full(dims, 2.0 * L + 0.1)
+    rbuf = np.tile(domain_max, (n_buffer, 1))
+
+    N = nf + nb + n_sensors + n_buffer
+    r = np.zeros((N, V), np.float32)
+    r[:, :dims] = np.concatenate([rf, rb, rs, rbuf]).astype(np.float32)
+    imove = np.concatenate([np.ones(nf), -3 * np.ones(nb), np.zeros(n_sensors),
+                            -255 * np.ones(n_buffer)]).astype(np.int32)
+    iset = np.concatenate([np.zeros(nf), np.ones(nb), 2 * np.ones(n_sensors),
+                           np.zeros(n_buffer)]).astype(np.uint32)
+    normal = np.zeros((N, V), np.float32)
+    normal[nf:nf + nb, :dims] = nrm
+    tangent = np.zeros((N, V), np.float32)
+    tangent[nf:nf + nb, (1 if dims == 3 else 0)] = 1.0
+    depth = np.clip(L - r[:, dims - 1], 0, None)
+    rho = (refd * (1.0 + 9.81 * depth / cs ** 2) *
+           (1.0 + 1e-3 * rng.uniform(-1, 1, N))).astype(np.float32)
+    rho[imove == -255] = refd
+    m = np.zeros(N, np.float32)
+    m[:nf] = refd * dr ** dims
+    m[nf:nf + nb] = dr ** (dims - 1)            # element area (length in 2-D)
+    m[nf + nb:nf + nb + n_sensors] = refd * dr ** dims
+    u = np.zeros((N, V), np.float32)
+    u[:nf, :dims] = 0.5 * rng.uniform(-1, 1, (nf, dims))
+    dudt = np.zeros((N, V), np.float32)
+    dudt[:nf, :dims] = 5.0 * rng.uniform(-1, 1, (nf, dims))
+    drhodt = np.zeros(N, np.float32)
+    drhodt[:nf] = 10.0 * rng.uniform(-1, 1, nf)
+
+    if shuffle:
+        perm = rng.permutation(N)
+        r, imove, iset, normal, tangent, rho, m, u, dudt, drhodt = (
+            a[perm] for a in (r, imove, iset, normal, tangent, rho, m, u, dudt, drhodt))
+
+    g = np.zeros(V, np.float32); g[dims - 1] = -9.81
+    dmin = np.zeros(V, np.float32); dmin[:dims] = domain_min
+    dmax = np.zeros(V, np.float32); dmax[:dims] = domain_max
+    return dict(
+        dims=dims, N=N, h=float(h), dr=float(dr), cs=float(cs), p0=0.0, support=2.0,
+        refd=np.array([refd, refd, refd], np.float32),
+        visc_dyn=np.array([1e-3, 0.0, 0.0], np.float32),
+        delta=np.array([0.1, 0.0, 0.0], np.float32),
+        g=g, domain_min=dmin, domain_max=dmax, courant=0.25, dt_Ma=0.1, dt_min=1e-7,
+        id=np.arange(N, dtype=np.uint32), r=r, imove=imove, iset=iset, normal=normal,
+        tangent=tangent, rho=rho, m=m, u=u, dudt=dudt, drhodt=drhodt,
+    )
+
+
+def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0):
+    """BASELINE config 5 shape: uniform lattice dr = 1, all fluid, rho = refd,
+    u = 0.01*cs*U(-1,1); no boundary (the ref has no periodic BC)."""
+    rng = np.random.default_rng(seed)
+    V = vs(dims)
+    ax = [np.arange(n_side, dtype=np.float32) for _ in range(dims)]
+    gpos = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, dims)
+    N = gpos.shape[0]
+    r = np.zeros((N, V), np.float32)
+    r[:, :dims] = gpos + 0.5
+    u = np.zeros((N, V), np.float32)
+    u[:, :dims] = (0.01 * cs * rng.uniform(-1, 1, (N, dims))).astype(np.float32)
+    refd = np.float32(1000.0)
+    z = np.zeros(V, np.float32)
+    return dict(
+        dims=dims, N=N, h=float(hfac), dr=1.0, cs=float(cs), p0=0.0, support=2.0,
+        refd=np.array([refd], np.float32), visc_dyn=np.array([1e-3], np.float32),
+        delta=np.array([0.1], np.float32), g=z.copy(), domain_min=z.copy() - 10.0,
+        domain_max=z.copy() + n_side + 10.0, courant=0.25, dt_Ma=0.1, dt_min=1e-7,
+        id=np.arange(N, dtype=np.uint32), r=r, imove=np.ones(N, np.int32),
+        iset=np.zeros(N, np.uint32), normal=np.zeros((N, V), np.float32),
+        tangent=np.zeros((N, V), np.float32),
+        rho=(refd * (1.0 + 1e-3 * rng.uniform(-1, 1, N))).astype(np.float32),
+        m=np.full(N, refd, np.float32), u=u, dudt=np.zeros((N, V), np.float32),
+        drhodt=np.zeros(N, np.float32),
+    )
+
+
+def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
+    """BASELINE config 2: the 3-D SPHERIC test 2 dam break with obstacle, same
+    geometry and field initialisation as the reference's case generator
+    (examples/3D/spheric_testcase2_dambreak/src/Create.py:39-462): fluid block
+    l x d x h = 1.228 x 1.0 x 0.55 m, box obstacle, closed tank, boundary-integral
+    elements (imove = -3, m = dr^2) with outward normals, 8 pressure sensors.
+    `n` is the requested number of FLUID particles (Create.py:62)."""
+    g, cs, courant, refd = 9.81, 40.0, 0.25, 998.0
+    delta, visc_dyn = 1.0, 0.000894
+    h, l, d = 0.55, 1.228, 1.0
+    H_box, L_box, D_box, x_box = 0.161, 0.161, 0.403, -1.248
+    H, L, D = 1.0, l + abs(x_box) + 0.744, d
+    dr = (l * d * h / n) ** (1.0 / 3.0)
+    nx, ny, nz = int(round(l / dr)), int(round(d / dr)), int(round(h / dr))
+    hFluid = nz * dr
+    Nx_box, Ny_box, Nz_box = (int(round(v / dr)) for v in (L_box, D_box, H_box))
+    x_box = (int(round(x_box / dr - 0.5 * Nx_box)) + 0.5 * Nx_box) * dr
+    Nx, Ny, Nz = int(round(L / dr)), int(round(D / dr)), int(round(H / dr))
+
+    def grid(*axes):
+        return np.stack(np.meshgrid(*axes, indexing="ij"), -1).reshape(-1, len(axes))
+
+    parts = []  # (pos[n,3], normal, tangent, imove)
+
+    def face(pos, normal, tangent):
+        parts.append((pos, np.tile(normal, (len(pos), 1)), np.tile(tangent, (len(pos), 1)),
+                      np.full(len(pos), -3, np.int32)))
+
+    # fluid (x outer, y, z inner like Create.py:107-134)
+    gi = grid(np.arange(nx), np.arange(ny), np.arange(nz)).astype(np.float64)
+    pf = np.stack([(gi[:, 0] + 0.5) * dr, -0.5 * Ny * dr + (gi[:, 1] + 0.5) * dr,
+                   (gi[:, 2] + 0.5) * dr], 1)
+    nfluid = len(pf)
+    press = refd * g * (hFluid - pf[:, 2]) * np.cos(0.5 * np.pi * (l - pf[:, 0]) / l)
+    dens_f = refd + press / cs ** 2
+    parts.append((pf, np.zeros((nfluid, 3)), np.zeros((nfluid, 3)), np.ones(nfluid, np.int32)))
+    # box obstacle (Create.py:136-252)
+    x0, y0, z0 = x_box - 0.5 * Nx_box * dr, -0.5 * Ny_box * dr, 0.0
+    ix, iy, iz = np.arange(Nx_box), np.arange(Ny_box), np.arange(Nz_box)
+    q = grid(ix, iy).astype(np.float64)
+    face(np.stack([x0 + (q[:, 0] + .5) * dr, y0 + (q[:, 1] + .5) * dr,
+                   np.full(len(q), z0 + Nz_box * dr)], 1), (0, 0, 1), (-1, 0, 0))
+    q = grid(iy, iz).astype(np.float64)
+    face(np.stack([np.full(len(q), x0), y0 + (q[:, 0] + .5) * dr, z0 + (q[:, 1] + .5) * dr], 1),
+         (1, 0, 0), (0, -1, 0))
+    face(np.stack([np.full(len(q), x0 + Nx_box * dr), y0 + (q[:, 0] + .5) * dr,
+                   z0 + (q[:, 1] + .5) * dr], 1), (-1, 0, 0), (0, -1, 0))
+    q = grid(ix, iz).astype(np.float64)
+    face(np.stack([x0 + (q[:, 0] + .5) * dr, np.full(len(q), y0), z0 + (q[:, 1] + .5) * dr], 1),
+         (0, 1, 0), (1, 0, 0))
+    face(np.stack([x0 + (q[:, 0] + .5) * dr, np.full(len(q), y0 + Ny_box * dr),
+                   z0 + (q[:, 1] + .5) * dr], 1), (0, -1, 0), (-1, 0, 0))
+    # tank (Create.py:254-430)
+    xbmin, xbmax = x_box - 0.5 * Nx_box * dr, x_box + 0.5 * Nx_box * dr
+    ybmin, ybmax = -0.5 * Ny_box * dr, 0.5 * Ny_box * dr
+    x0, y0, z0 = -(Nx - nx) * dr, -0.5 * Ny * dr, 0.0
+    IX, IY, IZ = np.arange(Nx), np.arange(Ny), np.arange(Nz)
+    q = grid(IX, IY).astype(np.float64)
+    bx, by = x0 + (q[:, 0] + .5) * dr, y0 + (q[:, 1] + .5) * dr
+    keep = ~((bx > xbmin) & (bx < xbmax) & (by > ybmin) & (by < ybmax))
+    face(np.stack([bx[keep], by[keep], np.full(keep.sum(), z0)], 1), (0, 0, -1), (-1, 0, 0))
+    face(np.stack([bx, by, np.full(len(q), z0 + Nz * dr)], 1), (0, 0, 1), (1, 0, 0))
+    q = grid(IY, IZ).astype(np.float64)
+    face(np.stack([np.full(len(q), x0), y0 + (q[:, 0] + .5) * dr, z0 + (q[:, 1] + .5) * dr], 1),
+         (-1, 0, 0), (0, -1, 0))
+    face(np.stack([np.full(len(q), x0 + Nx * dr), y0 + (q[:, 0] + .5) * dr,
+                   z0 + (q[:, 1] + .5) * dr], 1), (1, 0, 0), (0, 1, 0))
+    q = grid(IX, IZ).astype(np.float64)
+    face(np.stack([x0 + (q[:, 0] + .5) * dr, np.full(len(q), y0), z0 + (q[:, 1] + .5) * dr], 1),
+         (0, -1, 0), (1, 0, 0))
+    face(np.stack([x0 + (q[:, 0] + .5) * dr, np.full(len(q), y0 + Ny * dr),
+                   z0 + (q[:, 1] + .5) * dr], 1), (0, 1, 0), (-1, 0, 0))
+    nset0 = sum(len(p[0]) for p in parts)
+    # sensors (Create.py:432-470): set 1
+    zz = Nz_box * dr
+    spos = [(xbmax, 0.0, 0.021 + i * 0.04) for i in range(4)] + \
+           [(xbmax - 0.021 - i * 0.04, 0.0, zz) for i in range(4)]
+    snrm = [(-1, 0, 0)] * 4 + [(0, 0, 1)] * 4
+    stan = [(0, 1, 0)] * 4 + [(1, 0, 0)] * 4
+    parts.append((np.array(spos), np.array(snrm, float), np.array(stan, float),
+                  np.zeros(8, np.int32)))
+
+    pos = np.concatenate([p[0] for p in parts])
+    N = len(pos)
+    r = np.zeros((N, 4), np.float32); r[:, :3] = pos
+    normal = np.zeros((N, 4), np.float32); normal[:, :3] = np.concatenate([p[1] for p in parts])
+    tangent = np.zeros((N, 4), np.float32); tangent[:, :3] = np.concatenate([p[2] for p in parts])
+    imove = np.concatenate([p[3] for p in parts]).astype(np.int32)
+    rho = np.full(N, refd, np.float32); rho[:nfluid] = dens_f
+    m = np.full(N, dr ** 2, np.float32); m[:nfluid] = dens_f * dr ** 3; m[nset0:] = 0.0
+    iset = np.zeros(N, np.uint32); iset[nset0:] = 1
+    s = 10.0 * hfac * dr
+    dmin = np.array([-(L - l + s), -(0.5 * D + s), -s, 0.0], np.float32)
+    dmax = np.array([l + s, 0.5 * D + s, H + s, 0.0], np.float32)
+    hh = float(np.float32(np.float32(hfac) * np.float32(dr)))
+    u = np.zeros((N, 4), np.float32)
+    if seed is not None:  # optional perturbation so that every term is exercised
+        rng = np.random.default_rng(seed)
+        u[:nfluid, :3] = 0.1 * rng.uniform(-1, 1, (nfluid, 3))
+    return dict(
+        dims=3, N=N, n_fluid=nfluid, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs, p0=0.0,
+        support=2.0, refd=np.array([refd, refd], np.float32),
+        visc_dyn=np.array([visc_dyn, visc_dyn], np.float32),
+        delta=np.array([delta, delta], np.float32),
+        g=np.array([0, 0, -g, 0], np.float32), domain_min=dmin, domain_max=dmax,
+        courant=courant, dt_Ma=0.1, dt_min=float(np.float32(0.05 * courant * hh / cs)),
+        id=np.arange(N, dtype=np.uint32), r=r, imove=imove, iset=iset, normal=normal,
+        tangent=tangent, rho=rho, m=m, u=u, dudt=np.zeros((N, 4), np.float32),
+        drhodt=np.zeros(N, np.float32),
+    )

@@ -125,6 +125,39 @@ extern "C" int aqc_set_defs(aqc_ctx* ctx, const aqc_defs* defs)
     return AQC_OK;
 }
 
+static float parse_define_float(const char* v)
+{
+    std::string s(v ? v : "");
+    while (!s.empty() && (s.back() == 'f' || s.back() == 'F' || isspace((unsigned char)s.back())))
+        s.pop_back();
+    return strtof(s.c_str(), nullptr);
+}
+
+extern "C" int aqc_set_define(aqc_ctx* ctx, const char* name, const char* value)
+{
+    if (!ctx || !name)
+        return AQC_ERR_ARG;
+    const std::string n(name), v(value ? value : "");
+    if (n == "H") ctx->defs.H = parse_define_float(value);
+    else if (n == "CONW") ctx->defs.CONW = parse_define_float(value);
+    else if (n == "CONF") ctx->defs.CONF = parse_define_float(value);
+    else if (n == "SUPPORT") ctx->defs.SUPPORT = parse_define_float(value);
+    else if (n == "DIMS") ctx->defs.DIMS = parse_define_float(value);
+    else if (n == "__DR_FACTOR__") ctx->dr_factor = parse_define_float(value);
+    else if (n == "__MIN_BOUND_DIST__") ctx->min_bound_dist = parse_define_float(value);
+    else if (n == "KERNEL_NAME") {
+        if (v != "Wendland")
+            return aqc_fail(ctx, AQC_ERR_ARG, "KERNEL_NAME=%s: only the Wendland kernel is built",
+                            v.c_str());
+    } else if (n == "__LAP_FORMULATION__") {
+        if (v != "1" && v != "__LAP_MONAGHAN__")
+            return aqc_fail(ctx, AQC_ERR_ARG,
+                            "__LAP_FORMULATION__=%s: only __LAP_MONAGHAN__ is built", v.c_str());
+    } else
+        return 1;
+    return AQC_OK;
+}
+
 extern "C" int aqc_alloc(aqc_ctx* ctx, size_t bytes, void** dptr)
 {
     if (!ctx || !dptr)
@@ -317,6 +350,13 @@ extern "C" int aqc_kernel_lookup(const char* script_path, const char* entry, int
     for (size_t k = 0; k < reg.size(); k++)
         if (!strcmp(reg[k].script, rel) && !strcmp(reg[k].entry, ent) &&
             (reg[k].dims == 0 || reg[k].dims == dims))
+            return (int)k;
+    // case-local scripts (outside resources/Scripts) are registered by file name
+    const char* base = strrchr(rel, '/');
+    base = base ? base + 1 : rel;
+    for (size_t k = 0; k < reg.size(); k++)
+        if (!strchr(reg[k].script, '/') && !strcmp(reg[k].script, base) &&
+            !strcmp(reg[k].entry, ent) && (reg[k].dims == 0 || reg[k].dims == dims))
             return (int)k;
     return AQC_ERR_NOKERNEL;
 }

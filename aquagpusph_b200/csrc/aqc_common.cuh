@@ -16,6 +16,8 @@ struct aqc_ctx {
     bool own_stream = false;
     uint64_t launches = 0;
     aqc_defs defs{ 3, 1.f, 1.f, 1.f, 2.f, 3.f };
+    float dr_factor = 0.5f;      // __DR_FACTOR__ (BIe/ElasticBounce.cl:31-33)
+    float min_bound_dist = 0.f;  // __MIN_BOUND_DIST__ (BIe/ElasticBounce.cl:34-36)
     char err[512] = { 0 };
 
     // link-list scratch (grown on demand, never shrunk)

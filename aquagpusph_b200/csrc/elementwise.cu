@@ -695,9 +695,40 @@ int l_setbuffer_set_imove(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// ---- case-local script of the 3-D dam-break example (wave height probes):
+// examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60 ------------
+__global__ void __launch_bounds__(256)
+k_h_sensor(const int* imove, const float4* r, float* h_sensorz, uint32_t N, float h_sensorx,
+           float dr)
+{
+    GID;
+    if (imove[i] <= 0) {
+        h_sensorz[i] = 0.f;
+        return;
+    }
+    const float4 ri = r[i];
+    const float x = ri.x - h_sensorx;
+    if ((fabsf(x) > 2.f * dr) || (fabsf(ri.y) > 2.f * dr)) {
+        h_sensorz[i] = 0.f;
+        return;
+    }
+    h_sensorz[i] = ri.z + 0.5f * dr;
+}
+int l_h_sensor(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    LAUNCH(c, k_h_sensor, N, (const int*)a[0], (const float4*)a[1], (float*)a[2], N,
+           aqc_scalar<float>(a, 4), aqc_scalar<float>(a, 5));
+    return AQC_OK;
+}
+
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
+
+aqc_registrar r_h_sensor("h_sensor.cl", "entry", 3,
+    { IN("imove", "int*"), IN("r", "vec*"), OUT("h_sensorz", "float*"), SC("N", "uint"),
+      SC("h_sensorx", "float"), SC("dr", "float") }, l_h_sensor);
 
 #define STATE_COPY_ARGS                                                          \
     { IN("r", "vec*"), IN("u", "vec*"), IN("dudt", "vec*"), IN("rho", "float*"),   \

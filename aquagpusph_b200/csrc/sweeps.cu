@@ -464,7 +464,7 @@ struct PBIeElasticBounce : PBase {
     const void *r_in, *normal, *u_in;
     const float* m;
     void* dudt;
-    float dt;
+    float dt, dr_factor, min_bound;
     struct IState { float x, y, z, u0x, u0y, u0z, ax, ay, az, Ux, Uy, Uz; };
     __device__ bool i_active(int mv) const { return mv == 1 && dt != 0.f; }
     __device__ void load_i(IState& s, uint32_t i) const
@@ -483,7 +483,7 @@ struct PBIeElasticBounce : PBase {
         const bool ok = __ldg(imove + j) == -3;
         const float mj = __ldg(m + j);
         const float dr = (D == 3) ? sqrtf(mj) : mj;
-        const float R = 0.5f * dr; // __DR_FACTOR__ (:31-33)
+        const float R = dr_factor * dr; // __DR_FACTOR__ (:31-33)
         o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
         o[1] = make_float4(n.x, n.y, n.z, dr);
     }
@@ -511,7 +511,7 @@ struct PBIeElasticBounce : PBase {
         const float drn = dt * Un;
         if (drn < 0.f)
             return;
-        if (rn - drn <= 0.0f * Nn.w) { // __MIN_BOUND_DIST__ = 0 (:34-36)
+        if (rn - drn <= min_bound * Nn.w) { // __MIN_BOUND_DIST__ (:34-36)
             const float ux = s.u0x + dt * s.ax, uy = s.u0y + dt * s.ay, uz = s.u0z + dt * s.az;
             float un = ux * Nn.x + uy * Nn.y;
             if constexpr (D == 3)
@@ -538,6 +538,7 @@ struct PBIePST : PBase {
     const void* normal;
     const float *m, *rho;
     float inv_dims; // 1.f / DIMS
+    float dr_factor;
     struct IState { float x, y, z, Ri; };
     __device__ bool i_active(int mv) const { return mv == 1; }
     __device__ void load_i(IState& s, uint32_t i) const
@@ -553,7 +554,7 @@ struct PBIePST : PBase {
         const bool ok = __ldg(imove + j) == -3;
         const float mj = __ldg(m + j);
         const float dr = (D == 3) ? sqrtf(mj) : mj;
-        const float R = 0.5f * dr;
+        const float R = dr_factor * dr;
         o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
         o[1] = make_float4(n.x, n.y, n.z, 0.f);
     }
@@ -579,6 +580,34 @@ struct PBIePST : PBase {
     {
         stvec_xyz<D>(r, i, s.x, s.y, s.z);
     }
+};
+
+// ------------------------------------------------------------------------
+// Diagnostic (not a reference script): number of fluid neighbours within the kernel
+// support of every fluid particle, i.e. the pair count the roofline figures use.
+template <int D>
+struct PCountPairs : PBase {
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void* r;
+    uint32_t* n_pairs;
+    struct IState { float x, y, z; uint32_t n; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.n = 0;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        o[0] = make_float4(__ldg(imove + j) == 1 ? a.x : AQC_FAR, a.y, a.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4*, int) const { s.n++; }
+    __device__ void store_i(const IState& s, uint32_t i) const { n_pairs[i] = s.n; }
 };
 
 // ------------------------------------------------------------------------
@@ -750,6 +779,8 @@ template <int D> int run_bie_eb(aqc_ctx* ctx, void* const* a)
     set_base(p, ctx, a[0]);
     p.r_in = a[1]; p.normal = a[2]; p.m = (const float*)a[3]; p.u_in = a[4]; p.dudt = a[5];
     p.dt = aqc_scalar<float>(a, 7);
+    p.dr_factor = ctx->dr_factor;
+    p.min_bound = ctx->min_bound_dist;
     return launch_sweep(ctx, p, make_ll(a, 8, aqc_scalar<uint32_t>(a, 6)));
 }
 int l_bie_eb(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_eb, c, a); }
@@ -760,6 +791,7 @@ template <int D> int run_bie_pst(aqc_ctx* ctx, void* const* a)
     set_base(p, ctx, a[0]);
     p.r = a[1]; p.normal = a[2]; p.m = (const float*)a[3]; p.rho = (const float*)a[4];
     p.inv_dims = 1.f / ctx->defs.DIMS;
+    p.dr_factor = ctx->dr_factor;
     return launch_sweep(ctx, p, make_ll(a, 6, aqc_scalar<uint32_t>(a, 5)));
 }
 int l_bie_pst(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bie_pst, c, a); }
@@ -824,6 +856,18 @@ aqc_registrar r_bie_eb("cfd/Boundary/BIe/ElasticBounce.cl", "entry", 0,
 aqc_registrar r_bie_pst("cfd/Boundary/BIe/PST.cl", "entry", 0,
     { IN("imove", "int*"), OUT("r", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
       IN("rho", "float*"), SC("N", "usize"), LL_ARGS }, l_bie_pst);
+template <int D> int run_count_pairs(aqc_ctx* ctx, void* const* a)
+{
+    PCountPairs<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.n_pairs = (uint32_t*)a[2];
+    return launch_sweep(ctx, p, make_ll(a, 4, aqc_scalar<uint32_t>(a, 3)));
+}
+int l_count_pairs(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_count_pairs, c, a); }
+aqc_registrar r_count_pairs("aqua/diag.cl", "count_pairs", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), OUT("n_pairs", "uint*"), SC("N", "usize"), LL_ARGS },
+    l_count_pairs);
+
 aqc_registrar r_neighs("basic/neighs.cl", "entry", 0,
     { IN("imove", "int*"), OUT("n_neighs", "uint*"), SC("neighs_limit", "uint"),
       SC("N", "usize"), LL_ARGS }, l_neighs);

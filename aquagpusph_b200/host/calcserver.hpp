@@ -1,0 +1,319 @@
+// calcserver.hpp -- the scheduler and the tool types of the C++ host.
+//
+// Counterpart of aquagpusph/CalcServer/{CalcServer,Tool,Kernel,LinkList,
+// RadixSort,UnSort,Reduction,Set,SetScalar,Copy,Conditional,Assert}.* and
+// Reports/{Screen,TabFile,Dump}: same XML tool types and attributes, same
+// per-step pipeline semantics (CalcServer::update, CalcServer.cpp:592-621), but
+// every device operation goes through the C-ABI of libaquacuda.so
+// (include/aquacuda.h) on ONE in-order CUDA stream instead of a pool of OpenCL
+// queues stitched together with events.  Stream order subsumes the
+// read/write-event graph of Tool.cpp:405-444; the host blocks only where a
+// scalar computed on the device is needed by host logic (reductions, the
+// link-list grid), which is where the reference blocks too.
+#pragma once
+#include <chrono>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "aquacuda.h"
+#include "problem.hpp"
+#include "variables.hpp"
+
+namespace Aqua {
+namespace CalcServer {
+
+class CalcServer;
+
+/// Base class of every tool (Tool.hpp:173-567)
+class Tool {
+  public:
+    Tool(CalcServer* C, const std::string& name, bool once = false)
+      : _C(C), _name(name), _once(once) {}
+    virtual ~Tool() {}
+    const std::string& name() const { return _name; }
+    virtual void setup() {}
+    /// Run the tool (honouring once="true") and account its host time
+    void execute();
+    /// Tool to run next; default: the following one in the pipeline
+    virtual Tool* next_tool() { return _next; }
+    void next_tool(Tool* t) { _next = t; }
+    /// +1 for tools opening a scope (if/while), -1 for end (Tool.hpp:351-357)
+    virtual int scope_modifier() const { return 0; }
+    void id_in_pipeline(int i) { _id = i; }
+    int id_in_pipeline() const { return _id; }
+    unsigned used_times() const { return _n_iters; }
+    double elapsed_ms() const { return _elapsed_ms; }
+
+  protected:
+    virtual void _execute() {}
+    InputOutput::Variable* variable(const std::string& name, bool must_be_array,
+                                    bool must_be_scalar = false) const;
+    void check(int rc) const; // C-ABI status -> std::runtime_error
+    CalcServer* _C;
+
+  private:
+    std::string _name;
+    bool _once;
+    Tool* _next = nullptr;
+    int _id = -1;
+    unsigned _n_iters = 0;
+    double _elapsed_ms = 0.0;
+};
+
+/// type="kernel" (Kernel.cpp:301-352, 497-594): one registry kernel whose
+/// arguments are bound to Variables by name
+class Kernel : public Tool {
+  public:
+    Kernel(CalcServer* C, const std::string& name, const std::string& path,
+           const std::string& entry, const std::string& n, bool once);
+    void setup() override;
+    const std::string& path() const { return _path; }
+    const std::string& entry() const { return _entry; }
+    const std::vector<InputOutput::Variable*>& arguments() const { return _vars; }
+  protected:
+    void _execute() override;
+  private:
+    std::string _path, _entry, _n;
+    int _kid = -1;
+    std::vector<InputOutput::Variable*> _vars;
+    std::vector<int> _kinds;
+    size_t _global = 0;
+};
+
+/// type="copy" (Copy.cpp:62-91)
+class Copy : public Tool {
+  public:
+    Copy(CalcServer* C, const std::string& name, const std::string& in, const std::string& out, bool once)
+      : Tool(C, name, once), _in_name(in), _out_name(out) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _in_name, _out_name;
+    InputOutput::Variable *_in = nullptr, *_out = nullptr;
+};
+
+/// type="set" (Set.cpp:197-226, Set.cl.in:32-47)
+class Set : public Tool {
+  public:
+    Set(CalcServer* C, const std::string& name, const std::string& var, const std::string& value, bool once)
+      : Tool(C, name, once), _var_name(var), _value(value) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _var_name, _value;
+    InputOutput::Variable* _var = nullptr;
+    bool _literal = false;        // OpenCL literal/macro: constant bytes in _data
+    std::vector<char> _data;
+};
+
+/// Shared by set_scalar / if / while / assert (SetScalar.hpp ScalarExpression)
+class ScalarExpression : public Tool {
+  public:
+    ScalarExpression(CalcServer* C, const std::string& name, const std::string& expr,
+                     const std::string& type, bool once)
+      : Tool(C, name, once), _expr(expr), _type(type) {}
+    void setup() override;
+  protected:
+    void solve();                 // evaluates _expr into _value
+    std::string _expr, _type;
+    std::vector<char> _value;
+};
+
+/// type="set_scalar" (SetScalar.cpp:146-242)
+class SetScalar : public ScalarExpression {
+  public:
+    SetScalar(CalcServer* C, const std::string& name, const std::string& var, const std::string& value, bool once)
+      : ScalarExpression(C, name, value, "float", once), _var_name(var) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _var_name;
+    InputOutput::Variable* _var = nullptr;
+};
+
+/// type="assert" (Assert.cpp)
+class Assert : public ScalarExpression {
+  public:
+    Assert(CalcServer* C, const std::string& name, const std::string& cond, bool once)
+      : ScalarExpression(C, name, cond, "int", once) {}
+  protected:
+    void _execute() override;
+};
+
+/// type="if" / "while" (Conditional.cpp:40-144)
+class Conditional : public ScalarExpression {
+  public:
+    Conditional(CalcServer* C, const std::string& name, const std::string& cond, bool once)
+      : ScalarExpression(C, name, cond, "int", once) {}
+    void setup() override;
+    Tool* next_tool() override;
+    int scope_modifier() const override { return 1; }
+  protected:
+    void _execute() override;
+    bool _result = true;
+    Tool* _ending_tool = nullptr;
+};
+class While : public Conditional {
+  public:
+    using Conditional::Conditional;
+};
+class If : public Conditional {
+  public:
+    using Conditional::Conditional;
+    Tool* next_tool() override;
+  protected:
+    void _execute() override;
+};
+/// type="end" / "endif" (Conditional.cpp:155-181): jumps back to the opening tool
+class End : public Tool {
+  public:
+    End(CalcServer* C, const std::string& name, bool once) : Tool(C, name, once) {}
+    void setup() override;
+    int scope_modifier() const override { return -1; }
+};
+
+/// type="reduction" (Reduction.cpp:143-437)
+class Reduction : public Tool {
+  public:
+    Reduction(CalcServer* C, const std::string& name, const std::string& in, const std::string& out,
+              const std::string& operation, const std::string& null_val, bool once)
+      : Tool(C, name, once), _in_name(in), _out_name(out), _operation(operation), _null(null_val) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _in_name, _out_name, _operation, _null;
+    InputOutput::Variable *_in = nullptr, *_out = nullptr;
+    int _op = 0, _atype = 0;
+    std::vector<char> _identity;
+};
+
+/// type="link-list" (LinkList.cpp:326-494)
+class LinkList : public Tool {
+  public:
+    LinkList(CalcServer* C, const std::string& name, const InputOutput::ProblemSetup::Tool& t, bool once);
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _in_name, _min_name, _max_name, _ihoc_name, _icell_name, _ncells_name, _perm_name,
+        _inv_name;
+    bool _recompute;
+    InputOutput::Variable *_in, *_min, *_max, *_ihoc, *_icell, *_ncells, *_perm, *_inv, *_N, *_support, *_h;
+};
+
+/// type="radix-sort" / "sort" (RadixSort.cpp:129-303)
+class RadixSort : public Tool {
+  public:
+    RadixSort(CalcServer* C, const std::string& name, const std::string& var, const std::string& perm,
+              const std::string& inv, bool once)
+      : Tool(C, name, once), _var_name(var), _perm_name(perm), _inv_name(inv) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _var_name, _perm_name, _inv_name;
+    InputOutput::Variable *_var = nullptr, *_perm = nullptr, *_inv = nullptr;
+};
+
+/// type="unsort" (UnSort.cl.in:30-42): out[perm[i]] = in[i]
+class UnSort : public Tool {
+  public:
+    UnSort(CalcServer* C, const std::string& name, const std::string& in, const std::string& out,
+           const std::string& perm, bool once)
+      : Tool(C, name, once), _in_name(in), _out_name(out), _perm_name(perm) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _in_name, _out_name, _perm_name;
+    InputOutput::Variable *_in = nullptr, *_out = nullptr, *_perm = nullptr;
+};
+
+/// report_screen / report_file / report_dump / report_performance, and <Reports>
+class Report : public Tool {
+  public:
+    Report(CalcServer* C, const std::string& name, const std::string& kind,
+           const InputOutput::ProblemSetup::Tool& t, bool once);
+    void setup() override;
+    ~Report() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _kind, _fields, _path;
+    std::vector<InputOutput::Variable*> _vars;
+    FILE* _f = nullptr;
+};
+
+/// End / print criteria (TimeManager.cpp:33-160)
+class TimeManager {
+  public:
+    TimeManager(CalcServer* C, const InputOutput::ProblemSetup& sim_data);
+    bool mustStop();
+    bool mustPrintOutput();
+    float time() const { return *_time; }
+    float dt() const { return *_dt; }
+    unsigned step() const { return *_step; }
+    unsigned frame() const { return *_frame; }
+  private:
+    float *_time, *_dt, *_time_max;
+    unsigned *_step, *_frame, *_steps_max, *_frames_max;
+    float _output_time = 0.f, _output_fps = -1.f;
+    unsigned _output_step = 0;
+    int _output_ipf = -1;
+};
+
+/// The simulation: variables + tools on one device (CalcServer.cpp:139-621)
+class CalcServer {
+  public:
+    CalcServer(InputOutput::ProblemSetup& sim_data, int device = -1, int mpi_rank = 0,
+               int mpi_size = 1);
+    ~CalcServer();
+    /// Particle files -> device arrays (FileManager::load, Particles::loadDefault)
+    void loadParticles();
+    /// h check, per-set scalars, definitions, tool->setup() (CalcServer.cpp:1436-1534)
+    void setup();
+    /// Run time steps until an output frame is due or the end criteria is met
+    void update(TimeManager& t);
+    /// Run exactly one pass over the pipeline (one time step)
+    void step();
+
+    InputOutput::Variables* variables() { return _vars.get(); }
+    aqc_ctx* ctx() { return _ctx; }
+    const std::vector<std::unique_ptr<Tool>>& tools() const { return _tools; }
+    Tool* tool(size_t i) { return i < _tools.size() ? _tools[i].get() : nullptr; }
+    InputOutput::ProblemSetup& sim_data() { return _sim_data; }
+    int dims() const { return _sim_data.dims; }
+    int mpi_rank() const { return _mpi_rank; }
+    int mpi_size() const { return _mpi_size; }
+    const std::vector<std::pair<std::string, std::string>>& definitions() const { return _defs; }
+    /// Download an array in the ORIGINAL particle order (CalcServer::getUnsortedMem,
+    /// CalcServer.cpp:772-830); `out` must hold length*typesize bytes
+    void getUnsortedMem(const std::string& var, void* out);
+    void download(const std::string& var, void* out);
+    void upload(const std::string& var, const void* in);
+    /// ASCII dump of the <Save> fields of every set (ASCII.cpp:240-333 layout)
+    void saveParticles(const std::string& suffix);
+    uint64_t steps_done() const { return _steps; }
+
+  private:
+    void buildDefinitions();
+    Tool* makeTool(const InputOutput::ProblemSetup::Tool& t);
+    InputOutput::ProblemSetup& _sim_data;
+    aqc_ctx* _ctx = nullptr;
+    std::unique_ptr<InputOutput::Variables> _vars;
+    std::vector<std::unique_ptr<Tool>> _tools;
+    std::vector<std::pair<std::string, std::string>> _defs; // name -> value as "-D" text
+    int _mpi_rank, _mpi_size;
+    uint64_t _steps = 0;
+    void* _unsort_scratch = nullptr;
+    size_t _unsort_cap = 0;
+};
+
+} // namespace CalcServer
+} // namespace Aqua

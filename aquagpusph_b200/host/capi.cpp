@@ -1,0 +1,216 @@
+// capi.cpp -- C entry points of libaquahost.so (include/aquahost.h)
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "aquahost.h"
+#include "calcserver.hpp"
+
+using namespace Aqua;
+
+struct aqh_sim {
+    InputOutput::ProblemSetup sim_data;
+    std::unique_ptr<CalcServer::CalcServer> C;
+    std::unique_ptr<CalcServer::TimeManager> T;
+    std::vector<std::string> tool_types, tool_names;
+};
+
+static thread_local std::string g_err;
+
+#define AQH_TRY try {
+#define AQH_CATCH                                                              \
+    }                                                                          \
+    catch (std::exception & e)                                                 \
+    {                                                                          \
+        g_err = e.what();                                                      \
+        return -1;                                                             \
+    }                                                                          \
+    catch (...)                                                                \
+    {                                                                          \
+        g_err = "unknown error";                                               \
+        return -1;                                                             \
+    }
+
+extern "C" const char* aqh_last_error(void) { return g_err.c_str(); }
+extern "C" void aqh_set_log_level(int level) { logLevel() = level; }
+
+static std::unique_ptr<aqh_sim> parse_only(const char* xml_path, int dims, const char* root_path)
+{
+    if (dims != 2 && dims != 3)
+        throw std::runtime_error("dims must be 2 or 3");
+    auto sim = std::make_unique<aqh_sim>();
+    sim->sim_data.dims = dims;
+    if (root_path && *root_path)
+        sim->sim_data.settings.base_path = root_path;
+    else if (getenv("AQUAGPUSPH_ROOT"))
+        sim->sim_data.settings.base_path = getenv("AQUAGPUSPH_ROOT");
+    InputOutput::State state;
+    state.load(xml_path, sim->sim_data);
+    for (auto& t : sim->sim_data.tools) {
+        sim->tool_types.push_back(t->get("type"));
+        sim->tool_names.push_back(t->get("name"));
+    }
+    for (auto& r : sim->sim_data.reports) {
+        sim->tool_types.push_back("report_" + r->get("type"));
+        sim->tool_names.push_back(r->get("name"));
+    }
+    return sim;
+}
+
+extern "C" int aqh_parse(const char* xml_path, int dims, const char* root_path, aqh_sim** out)
+{
+    if (!out || !xml_path) {
+        g_err = "aqh_parse: NULL argument";
+        return -1;
+    }
+    *out = nullptr;
+    AQH_TRY
+    *out = parse_only(xml_path, dims, root_path).release();
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_load(const char* xml_path, int dims, int device, const char* root_path,
+                        int mpi_rank, int mpi_size, aqh_sim** out)
+{
+    if (!out || !xml_path) {
+        g_err = "aqh_load: NULL argument";
+        return -1;
+    }
+    *out = nullptr;
+    AQH_TRY
+    auto sim = parse_only(xml_path, dims, root_path);
+    sim->C = std::make_unique<CalcServer::CalcServer>(sim->sim_data, device, mpi_rank, mpi_size);
+    sim->C->loadParticles();
+    sim->C->setup();
+    sim->T = std::make_unique<CalcServer::TimeManager>(sim->C.get(), sim->sim_data);
+    *out = sim.release();
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" void aqh_destroy(aqh_sim* sim) { delete sim; }
+
+extern "C" int aqh_write_resolved(aqh_sim* sim, const char* path)
+{
+    AQH_TRY
+    InputOutput::State().write(path, sim->sim_data);
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_n_tools(aqh_sim* sim) { return sim ? (int)sim->tool_names.size() : 0; }
+extern "C" const char* aqh_tool_name(aqh_sim* sim, int i)
+{
+    return (i >= 0 && (size_t)i < sim->tool_names.size()) ? sim->tool_names[i].c_str() : nullptr;
+}
+extern "C" const char* aqh_tool_type(aqh_sim* sim, int i)
+{
+    return (i >= 0 && (size_t)i < sim->tool_types.size()) ? sim->tool_types[i].c_str() : nullptr;
+}
+extern "C" double aqh_tool_elapsed_ms(aqh_sim* sim, int i)
+{
+    auto* t = sim->C ? sim->C->tool(i) : nullptr;
+    return t ? t->elapsed_ms() : 0.0;
+}
+extern "C" unsigned aqh_tool_used_times(aqh_sim* sim, int i)
+{
+    auto* t = sim->C ? sim->C->tool(i) : nullptr;
+    return t ? t->used_times() : 0;
+}
+
+extern "C" int aqh_step(aqh_sim* sim, int n)
+{
+    AQH_TRY
+    for (int k = 0; k < n; k++)
+        sim->C->step();
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_run(aqh_sim* sim)
+{
+    AQH_TRY
+    while (!sim->T->mustStop())
+        sim->C->update(*sim->T);
+    if (aqc_sync(sim->C->ctx()))
+        throw std::runtime_error(aqc_last_error(sim->C->ctx()));
+    sim->C->saveParticles("");
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_sync(aqh_sim* sim)
+{
+    AQH_TRY
+    if (aqc_sync(sim->C->ctx()))
+        throw std::runtime_error(aqc_last_error(sim->C->ctx()));
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" uint64_t aqh_launch_count(aqh_sim* sim) { return aqc_launch_count(sim->C->ctx()); }
+extern "C" void* aqh_cuda_ctx(aqh_sim* sim) { return sim->C->ctx(); }
+
+extern "C" int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes)
+{
+    AQH_TRY
+    auto* v = sim->C->variables()->get(name);
+    if (!v || v->isArray())
+        throw std::runtime_error(std::string("No such scalar variable \"") + name + "\"");
+    if (bytes < v->typesize())
+        throw std::runtime_error(std::string("Buffer too small for \"") + name + "\"");
+    memcpy(out, v->get(), v->typesize());
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_scalar_set(aqh_sim* sim, const char* name, const char* expression)
+{
+    AQH_TRY
+    auto* v = sim->C->variables()->get(name);
+    if (!v || v->isArray())
+        throw std::runtime_error(std::string("No such scalar variable \"") + name + "\"");
+    sim->C->variables()->solve(v->type(), expression, v->get(), name);
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_array_info(aqh_sim* sim, const char* name, size_t* length, size_t* elem_bytes)
+{
+    AQH_TRY
+    auto* v = sim->C->variables()->get(name);
+    if (!v || !v->isArray())
+        throw std::runtime_error(std::string("No such array variable \"") + name + "\"");
+    if (length)
+        *length = v->length();
+    if (elem_bytes)
+        *elem_bytes = v->typesize();
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_array_download(aqh_sim* sim, const char* name, void* host_out, int unsorted)
+{
+    AQH_TRY
+    if (unsorted)
+        sim->C->getUnsortedMem(name, host_out);
+    else
+        sim->C->download(name, host_out);
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_array_upload(aqh_sim* sim, const char* name, const void* host_in)
+{
+    AQH_TRY
+    sim->C->upload(name, host_in);
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" void* aqh_array_devptr(aqh_sim* sim, const char* name)
+{
+    auto* v = sim->C->variables()->get(name);
+    return (v && v->isArray()) ? v->dptr() : nullptr;
+}

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the per-time-step particle pipeline (BASELINE.json metric:
+particle-steps/s on the 3-D SPHERIC test 2 dam break).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours      : the reference's unchanged 116-tool pipeline (resolved XML of
+            examples/3D/spheric_testcase2_dambreak) driven by the C++ host
+            (libaquahost.so) on the sm_100a kernels of libaquacuda.so.
+reference : the CPU restatement of the same pipeline (oracle/, "port": the
+            reference itself needs OpenCL/Xerces/VTK and cannot be built here)
+            on all host threads, on a bounded sample of the same workload.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/s"
+WORKLOAD = "3D SPHERIC test 2 dam break with obstacle (examples/3D/spheric_testcase2_dambreak)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class Clocks(threading.Thread):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_port(n_sample, steps, warmup, threads, maxiter):
+    """Oracle interpreter (CPU) on the same pipeline; returns (particle-steps/s, N, ms/step)."""
+    from aquagpusph_b200 import cases, casegen
+    from oracle import interp, oracle as O
+    O.build()
+    O.set_threads(threads)
+    c = cases.spheric2_dam_break(n_sample, 3.0)
+    ov = {"iter_midpoint_max": maxiter} if maxiter > 0 else None
+    xml = casegen.instantiate("spheric2_dambreak_3d", c, (c["N"] - 8, 8), ov)
+    I = interp.Interpreter(xml, 3)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = c[k]
+    for _ in range(warmup):
+        I.step()
+    t0 = time.time()
+    for _ in range(steps):
+        I.step()
+    dt = time.time() - t0
+    return c["N"] * steps / dt, c["N"], 1e3 * dt / steps
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    v, N, ms = cpu_port(a.cpu_n, a.steps, a.warmup, threads, a.maxiter)
+    sample = ("same case generator and 116-tool pipeline at n_fluid=%d (N=%d), %d steps after %d "
+              "warm-up" % (a.cpu_n, N, a.steps, a.warmup))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "particle-steps/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_particles": N, "iter_midpoint_max": a.maxiter or 30},
+        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def pinned(actx, shape, dtype):
+    from aquagpusph_b200 import _lib
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    actx._chk(_lib.lib().aqc_host_alloc(actx.h, nbytes, ctypes.byref(p)))
+    buf = (ctypes.c_char * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def run_ours(a, rank, world, local_rank):
+    from aquagpusph_b200 import _lib, casegen, host
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    host.set_log_level(3)
+    ov = {"iter_midpoint_max": a.maxiter} if a.maxiter > 0 else None
+    sim, case = casegen.spheric2(a.n, overrides=ov, device=local_rank)
+    N = case["N"]
+    actx = _lib.Context.borrow(sim.cuda_ctx(), 3)
+
+    def barrier():
+        sim.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        sim.step(1)
+    barrier()
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+    # ---- device-resident timing: K steps between CUDA events on the stream
+    e0, e1 = actx.event(), actx.event()
+    l0 = sim.launch_count()
+    inner = 0
+    barrier()
+    actx.record(e0)
+    for _ in range(a.steps):
+        sim.step(1)
+        inner += int(sim.scalar("iter_midpoint", np.uint32)) - 1
+    actx.record(e1)
+    barrier()
+    ms = max_over_ranks(actx.elapsed_ms(e0, e1))
+    launches = sim.launch_count() - l0
+    value = world * N * a.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, every step
+    fields = ["r", "u", "dudt", "rho", "drhodt", "m", "imove"]
+    outs = ["r", "u", "rho", "p"]
+    hin = {}
+    for k in fields:
+        cur = sim.download(k, np.int32 if k == "imove" else np.float32)
+        hin[k] = pinned(actx, cur.shape, cur.dtype)
+        hin[k][...] = cur
+    hout = {k: pinned(actx, hin[k].shape if k in hin else (N,), np.float32) for k in outs}
+    h2d = sum(v.nbytes for v in hin.values())
+    d2h = sum(v.nbytes for v in hout.values()) + 4
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        for k in fields:
+            sim.upload(k, hin[k])
+        sim.step(1)
+        for k in outs:
+            sim.download(k, np.float32, out=hout[k])
+        dt_now = float(sim.scalar("dt"))
+        for k in ("r", "u", "rho"):
+            hin[k][...] = hout[k]   # next step starts from this step's result
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    e2e = world * N * a.steps / (e2e_ms * 1e-3)
+    clocks.stop_flag = True
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (cfd/Interactions.cl::entry), timed alone
+    pk, pk_kind = peaks()
+    V = {}
+    for k, dt_ in (("imove", np.int32), ("r", np.float32), ("u", np.float32), ("rho", np.float32),
+                   ("m", np.float32), ("p", np.float32), ("grad_p", np.float32),
+                   ("lap_u", np.float32), ("div_u", np.float32), ("icell", np.uint32),
+                   ("ihoc", np.uint32)):
+        n_, eb = sim.array_info(k)
+        V[k] = actx.wrap(lib_ptr(sim, k), (n_, eb // 4) if eb > 4 else (n_,), dt_)
+    V["N"] = N
+    V["n_cells"] = sim.scalar("n_cells", np.uint32, 4)
+    d = _lib.Defs()
+    hh = float(sim.scalar("h"))
+    actx.dims = 3
+    n_pairs = actx.zeros(N, np.uint32)
+    V["n_pairs"] = n_pairs
+    actx.launch("aqua/diag.cl", "count_pairs", V)
+    pairs = int(n_pairs.get().astype(np.uint64).sum())
+    for _ in range(2):
+        actx.launch("cfd/Interactions.cl", "entry", V)
+    k0, k1 = actx.event(), actx.event()
+    reps = 5
+    actx.record(k0)
+    for _ in range(reps):
+        actx.launch("cfd/Interactions.cl", "entry", V)
+    actx.record(k1)
+    kms = actx.elapsed_ms(k0, k1) / reps
+    alg_bytes = 88.0 * N          # Interactions 88 B/particle (3-D, 32-bit idx)
+    alg_flops = 52.0 * pairs      # 52 flop per true neighbour pair
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "interactions_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "kernel": "sweep_kernel<PInteractions<3>> (cfd/Interactions.cl::entry)",
+            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": traffic,
+            "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
+            "fp32": {"algorithmic_flops": alg_flops, "pairs": pairs,
+                     "achieved_tflops": alg_flops / (kms * 1e-3) / 1e12,
+                     "nominal_peak_tflops_at_max_clock": 148 * 128 * 2 * 1.965e-3,
+                     "note": "the sweep is FP32-issue bound (530 flop/B vs ridge ~11.5), SURVEY 8(d)"}}
+    del d, hh
+    # ---- CPU baseline (oracle port), bounded sample
+    threads = os.cpu_count() or 1
+    cv, cN, cms = cpu_port(a.cpu_n, 1, 1, threads, a.maxiter)
+    line = {
+        "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+        "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_particles": N, "n_fluid": case["n_fluid"],
+                   "hfac": 3.0, "pipeline_tools": len(sim.tools()),
+                   "mean_inner_iterations": inner / a.steps,
+                   "iter_midpoint_max": a.maxiter or 30,
+                   "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
+                   "multi_gpu": "independent replicas" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "cpu_baseline": {"value": cv, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                         "sample": "same pipeline at n_fluid=%d (N=%d), 1 step after 1 warm-up, "
+                                   "%.0f ms/step" % (a.cpu_n, cN, cms)},
+    }
+    print(json.dumps(line), flush=True)
+    _ = dt_now
+
+
+def lib_ptr(sim, name):
+    from aquagpusph_b200 import host
+    return host.lib().aqh_array_devptr(sim.h, name.encode())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1000000, help="fluid particles (Create.py n)")
+    ap.add_argument("--cpu-n", type=int, default=30000, help="fluid particles of the CPU sample")
+    ap.add_argument("--maxiter", type=int, default=0, help="pin iter_midpoint_max (0: case default 30)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

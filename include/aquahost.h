@@ -1,0 +1,65 @@
+/* aquahost.h -- C entry points of libaquahost.so, the C++ host that keeps the
+ * reference's XML problem/tool API (aquagpusph/main.cpp:108-200,
+ * FileManager.cpp:60-143, CalcServer.cpp:592-621) on top of libaquacuda.so.
+ *
+ * It is what `AQUAgpusph -i Main.xml -d 3` does, split so that another process
+ * (bench.py, the tests) can drive it: load a case, step it, move particle
+ * arrays in and out with HOST buffers.  Every function returns 0 on success and
+ * <0 on error (message in aqh_last_error()); no C++ exception crosses it. */
+#ifndef AQUAHOST_H
+#define AQUAHOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aqh_sim aqh_sim;
+
+const char* aqh_last_error(void);
+void aqh_set_log_level(int level); /* 0 debug .. 3 error (ArgumentsManager.cpp:98-110) */
+
+/* FileManager::load + new CalcServer + setup: parse xml_path (dims = 2|3, the -d
+ * flag), create the device context (device < 0: take it from <Device>), register
+ * variables/tools, load the particle files and set every tool up.  root_path is the
+ * folder holding "resources/" (may be NULL: AQUAGPUSPH_ROOT, then <RootPath>). */
+int aqh_load(const char* xml_path, int dims, int device, const char* root_path, int mpi_rank,
+             int mpi_size, aqh_sim** out);
+/* XML front-end only (no device needed): parse and resolve the includes, presets
+ * and tool placement; the result serves aqh_write_resolved / aqh_n_tools /
+ * aqh_tool_name / aqh_tool_type. */
+int aqh_parse(const char* xml_path, int dims, const char* root_path, aqh_sim** out);
+void aqh_destroy(aqh_sim* sim);
+/* State::write: the resolved problem as one flat XML (checkpoint format) */
+int aqh_write_resolved(aqh_sim* sim, const char* path);
+
+/* pipeline introspection */
+int aqh_n_tools(aqh_sim* sim);
+const char* aqh_tool_name(aqh_sim* sim, int i);
+const char* aqh_tool_type(aqh_sim* sim, int i); /* XML type attribute */
+double aqh_tool_elapsed_ms(aqh_sim* sim, int i); /* accumulated host time */
+unsigned aqh_tool_used_times(aqh_sim* sim, int i);
+
+/* CalcServer::update split in steps: run n passes over the pipeline */
+int aqh_step(aqh_sim* sim, int n);
+/* main.cpp:162-179: run until the end criteria; saves the <Save> sets at the end */
+int aqh_run(aqh_sim* sim);
+int aqh_sync(aqh_sim* sim);
+uint64_t aqh_launch_count(aqh_sim* sim); /* CUDA kernels launched so far */
+void* aqh_cuda_ctx(aqh_sim* sim);         /* the aqc_ctx* underneath */
+
+/* variables */
+int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes);
+int aqh_scalar_set(aqh_sim* sim, const char* name, const char* expression);
+int aqh_array_info(aqh_sim* sim, const char* name, size_t* length, size_t* elem_bytes);
+/* unsorted != 0: original particle order (CalcServer::getUnsortedMem) */
+int aqh_array_download(aqh_sim* sim, const char* name, void* host_out, int unsorted);
+int aqh_array_upload(aqh_sim* sim, const char* name, const void* host_in);
+void* aqh_array_devptr(aqh_sim* sim, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -48,6 +48,11 @@ float aqo_define_round6(float v);
 /* Fill defs from the full precision h as basic.xml:119-123 does. */
 void aqo_make_defs(aqo_defs* d, int dims, float h);
 
+/* Restrict the particle loops of the kernels in aqo_kernels.c to rows [lo, hi) for
+ * the CALLING thread (thread-local; default: every row).  Lets a driver spread one
+ * kernel over several host threads for the CPU baseline. */
+void aqo_set_range(aqo_usize lo, aqo_usize hi);
+
 /* ---- link-list (aquagpusph/CalcServer/LinkList.cpp:326-494) ------------- */
 void aqo_minmax(const float* r, aqo_usize N, int dims, float* rmin, float* rmax);
 int aqo_ncells(const float* rmin, const float* rmax, int dims, float support,
@@ -190,14 +195,14 @@ void aqo_bie_force_press(const int* imove, const float* r, const float* normal,
 void aqo_bie_elastic_bounce(const aqo_ll* L, const int* imove,
                             const float* r_in, const float* normal,
                             const float* m, const float* u_in, float* dudt,
-                            float dt, int dims);
+                            float dt, float dr_factor, int dims);
 void aqo_bie_force_bound(const int* imove, const float* m,
                          const float* dudt_preelastic,
                          const float* dudt_elastic, float* force_elastic,
                          aqo_usize N, int dims);
 void aqo_bie_pst(const aqo_ll* L, const int* imove, float* r,
                  const float* normal, const float* m, const float* rho,
-                 float DIMS_define, int dims);
+                 float DIMS_define, float dr_factor, int dims);
 
 /* Reduction tool, sum in the reference's tree order (Reduction.cl.in:35-66,
  * Reduction.cpp:376-436) with work-group size wg (power of two). */

@@ -9,6 +9,19 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Outer particle loops honour a per-thread [lo, hi) window (aqo_set_range) so a
+ * caller can spread one kernel over several host threads; default = everything.
+ * Every kernel below only writes row i inside its i-loop, so windows are
+ * independent. */
+static __thread aqo_usize aqo_lo = 0, aqo_hi = 0xFFFFFFFFu;
+void aqo_set_range(aqo_usize lo, aqo_usize hi)
+{
+    aqo_lo = lo;
+    aqo_hi = hi;
+}
+#define AQO_FOR_I(n)                                                           \
+    for (aqo_usize i = aqo_lo, i_end__ = ((n) < aqo_hi ? (n) : aqo_hi); i < i_end__; i++)
+
 #define VS(dims) ((dims) == 3 ? 4 : 2)
 #define MS(dims) ((dims) == 3 ? 16 : 4)
 #define iM_PI 0.318309886f /* KernelFunctions/Wendland3D.hcl:34-39 */
@@ -69,7 +82,7 @@ static inline int pair_q(const aqo_defs* D, const float* ri, const float* rj,
 void aqo_eos(const aqo_usize* iset, const int* imove, const float* rho,
              float* p, const float* refd, aqo_usize N, float cs, float p0)
 {
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if ((imove[i] <= 0) && (imove[i] != -1))
             continue;
         p[i] = p0 + cs * cs * (rho[i] - refd[iset[i]]);
@@ -84,7 +97,7 @@ void aqo_rates(const aqo_usize* iset, const int* imove, const float* rho,
 {
     (void)rho;
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 1)
             continue;
         const float mu = visc_dyn[iset[i]];
@@ -101,7 +114,7 @@ void aqo_timestep(const int* imove, const float* u, float* dt_var, aqo_usize N,
                   int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0) {
             dt_var[i] = dt;
             continue;
@@ -120,21 +133,21 @@ void aqo_timestep(const int* imove, const float* u, float* dt_var, aqo_usize N,
 float aqo_reduce_min(const float* v, aqo_usize N)
 {
     float m = INFINITY;
-    for (aqo_usize i = 0; i < N; i++)
+    AQO_FOR_I(N)
         m = fminf(m, v[i]);
     return m;
 }
 float aqo_reduce_max(const float* v, aqo_usize N)
 {
     float m = -INFINITY;
-    for (aqo_usize i = 0; i < N; i++)
+    AQO_FOR_I(N)
         m = fmaxf(m, v[i]);
     return m;
 }
 aqo_usize aqo_reduce_max_u32(const aqo_usize* v, aqo_usize N)
 {
     aqo_usize m = 0;
-    for (aqo_usize i = 0; i < N; i++)
+    AQO_FOR_I(N)
         m = v[i] > m ? v[i] : m;
     return m;
 }
@@ -189,7 +202,7 @@ void aqo_domain(int* imove, float* r_in, float* u_in, float* dudt_in, float* m,
                 int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= -255)
             continue;
         const float* c = r_in + (size_t)i * vs;
@@ -213,7 +226,7 @@ void aqo_domain(int* imove, float* r_in, float* u_in, float* dudt_in, float* m,
 void aqo_binormal(const float* normal, float* tangent, float* binormal,
                   aqo_usize N, int dims)
 {
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (dims == 2) {
             binormal[2 * (size_t)i] = 0.f;
             binormal[2 * (size_t)i + 1] = 0.f;
@@ -265,7 +278,7 @@ void aqo_euler_corrector(const int* imove, float* r, float* u,
                          aqo_usize N, float dt, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0)
             continue;
         for (int c = 0; c < vs; c++) {
@@ -284,7 +297,7 @@ void aqo_ie_predictor(const int* imove, const float* r, const float* u,
                       float* drhodt_in, aqo_usize N, float dt, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         const float DT = (imove[i] <= 0) ? 0.f : dt;
         for (int c = 0; c < vs; c++) {
             const size_t k = (size_t)i * vs + c;
@@ -303,7 +316,7 @@ void aqo_ie_corrector(const int* imove, float* r, float* u, const float* dudt,
                       const float* drhodt_in, aqo_usize N, float dt, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0)
             continue;
         const float DT = 0.5f * dt;
@@ -332,7 +345,7 @@ void aqo_mp_midpoint(const int* imove, const float* u_in, float* u,
                      const float* drhodt, aqo_usize N, float dt, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0)
             continue;
         for (int c = 0; c < vs; c++) {
@@ -349,7 +362,7 @@ void aqo_mp_relax(const int* imove, const float* dudt_in, float* dudt,
                   float relax, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0)
             continue;
         for (int c = 0; c < vs; c++) {
@@ -368,7 +381,7 @@ void aqo_mp_residuals(const int* imove, const float* m, const float* u,
                       int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0) {
             residual[i] = 0.f;
             continue;
@@ -392,7 +405,7 @@ void aqo_mp_corrector(const int* imove, const float* r_in, float* r,
                       aqo_usize N, float dt, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] <= 0)
             continue;
         for (int c = 0; c < vs; c++) {
@@ -418,7 +431,7 @@ void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
     const int dims = D->dims, vs = VS(dims);
     const float cleary = (dims == 3) ? 10.f : 8.f;
     const float H = D->H;
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -467,7 +480,7 @@ void aqo_shepard(const aqo_defs* D, const aqo_ll* L, int cfd_mode,
 {
     const int dims = D->dims, vs = VS(dims);
 #define SH_EXCL(k) (cfd_mode ? (imove[k] != 1) : (imove[k] >= 3))
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if ((imove[i] < -3) || ((imove[i] > 0) && SH_EXCL(i)))
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -491,7 +504,7 @@ void aqo_shepard(const aqo_defs* D, const aqo_ll* L, int cfd_mode,
 void aqo_neighs(const aqo_ll* L, const int* imove, aqo_usize* n_neighs,
                 aqo_usize neighs_limit, int dims)
 {
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] <= -255) {
             n_neighs[i] = 0;
             continue;
@@ -515,7 +528,7 @@ void aqo_sensors(const aqo_defs* D, const aqo_ll* L, const int* imove,
                  float* p)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 0)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -549,7 +562,7 @@ void aqo_sensors_renorm(const int* imove, const float* shepard, float* u,
                         float* rho, float* p, aqo_usize N, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 0)
             continue;
         float s = shepard[i];
@@ -568,7 +581,7 @@ void aqo_dsph_simple(const aqo_usize* iset, const int* imove, float* lap_p_corr,
                      const float* refd, aqo_usize N, const float* g, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 1)
             continue;
         for (int c = 0; c < vs; c++)
@@ -582,7 +595,7 @@ void aqo_dsph_full(const aqo_defs* D, const aqo_ll* L, const int* imove,
                    const float* p, float* lap_p_corr)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -611,7 +624,7 @@ void aqo_dsph_full_mls(const int* imove, const float* mls, float* lap_p_corr,
                        aqo_usize N, int dims)
 {
     const int vs = VS(dims), ms = MS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 1)
             continue;
         const float* M = mls + (size_t)i * ms;
@@ -639,7 +652,7 @@ void aqo_dsph_lapp(const aqo_defs* D, const aqo_ll* L, const int* imove,
                    const float* p, float* lap_p)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -666,7 +679,7 @@ void aqo_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const int* imove,
                         const float* lap_p_corr, float* lap_p)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -695,7 +708,7 @@ void aqo_dsph_apply(const aqo_usize* iset, const int* imove, const float* rho,
                     const float* lap_p, float* drhodt, const float* refd,
                     const float* delta, aqo_usize N, float dt)
 {
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 1)
             continue;
         const aqo_usize s = iset[i];
@@ -713,7 +726,7 @@ void aqo_mls(const aqo_defs* D, const aqo_ll* L, const int* imove,
 {
     const int dims = D->dims, vs = VS(dims), ms = MS(dims);
     const int rs = (dims == 3) ? 4 : 2; /* row stride of the matrix */
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if ((aqo_usize)imove[i] != mls_imove)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -785,7 +798,7 @@ static void mat3_inv(const float* m, float* o)
 void aqo_mls_inv(const int* imove, float* mls, aqo_usize N,
                  aqo_usize mls_imove, int dims)
 {
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if ((aqo_usize)imove[i] != mls_imove)
             continue;
         if (dims == 3) {
@@ -827,7 +840,7 @@ void aqo_bie_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
                           const float* m, float* grad_w_bi, float* div_u_bi)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -863,7 +876,7 @@ void aqo_bie_p_boundary(const aqo_defs* D, const aqo_ll* L, const int* imove,
                         float* p)
 {
     const int dims = D->dims, vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != -3)
             continue;
         const float* r_i = r + (size_t)i * vs;
@@ -889,7 +902,7 @@ void aqo_bie_rates(const int* imove, const float* rho, const float* p,
                    aqo_usize N, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != 1)
             continue;
         const float f = 2.f * p[i] / rho[i];
@@ -908,7 +921,7 @@ void aqo_bie_rates(const int* imove, const float* rho, const float* p,
 void aqo_bie_filter_press(const aqo_usize* iset, const int* imove, float* p,
                           aqo_usize forces_iset, aqo_usize N)
 {
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         if (imove[i] != -3)
             continue;
         if (iset[i] != forces_iset)
@@ -923,7 +936,7 @@ void aqo_bie_force_press(const int* imove, const float* r, const float* normal,
                          int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++) {
+    AQO_FOR_I(N) {
         float* fo = force_p + (size_t)i * vs;
         float* mo = moment_p + (size_t)i * 4;
         if (imove[i] != -3) {
@@ -945,16 +958,16 @@ void aqo_bie_force_press(const int* imove, const float* r, const float* normal,
     }
 }
 
-/* cfd/Boundary/BIe/ElasticBounce.cl:64-152; __DR_FACTOR__ = 0.5f (:31-33),
+/* cfd/Boundary/BIe/ElasticBounce.cl:64-152; dr_factor = __DR_FACTOR__ (default 0.5f, :31-33),
  * __MIN_BOUND_DIST__ = 0.0f (:34-36).  Order dependent: state is mutated
  * inside the neighbour loop. */
 void aqo_bie_elastic_bounce(const aqo_ll* L, const int* imove,
                             const float* r_in, const float* normal,
                             const float* m, const float* u_in, float* dudt,
-                            float dt, int dims)
+                            float dt, float dr_factor, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         if (!dt)
@@ -978,7 +991,7 @@ void aqo_bie_elastic_bounce(const aqo_ll* L, const int* imove,
             if (rn < 0.f)
                 continue;
             const float dr = (dims == 3) ? sqrtf(m[j]) : m[j];
-            const float R = 0.5f * dr;
+            const float R = dr_factor * dr;
             float rt[3];
             for (int d = 0; d < dims; d++)
                 rt[d] = r_ij[d] - rn * n_j[d];
@@ -1013,7 +1026,7 @@ void aqo_bie_force_bound(const int* imove, const float* m,
                          aqo_usize N, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < N; i++)
+    AQO_FOR_I(N)
         for (int c = 0; c < vs; c++) {
             const size_t k = (size_t)i * vs + c;
             force_elastic[k] = (imove[i] != 1) ? 0.f
@@ -1026,10 +1039,10 @@ void aqo_bie_force_bound(const int* imove, const float* m,
  * re-read for the next element. */
 void aqo_bie_pst(const aqo_ll* L, const int* imove, float* r,
                  const float* normal, const float* m, const float* rho,
-                 float DIMS_define, int dims)
+                 float DIMS_define, float dr_factor, int dims)
 {
     const int vs = VS(dims);
-    for (aqo_usize i = 0; i < L->N; i++) {
+    AQO_FOR_I(L->N) {
         if (imove[i] != 1)
             continue;
         const float Ri = 0.5f * powf(m[i] / rho[i], 1.f / DIMS_define);
@@ -1046,7 +1059,7 @@ void aqo_bie_pst(const aqo_ll* L, const int* imove, float* r,
             if (fabsf(rn) > Ri)
                 continue;
             const float dr = (dims == 3) ? sqrtf(m[j]) : m[j];
-            const float Rj = 0.5f * dr;
+            const float Rj = dr_factor * dr;
             float rt[3];
             for (int d = 0; d < dims; d++)
                 rt[d] = r_ij[d] - rn * n_j[d];

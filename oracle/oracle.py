@@ -64,6 +64,40 @@ def call(name, *args):
     return getattr(lib(), "aqo_" + name)(*[_arg(a) for a in args])
 
 
+_POOL = None
+THREADS = 1
+
+
+def set_threads(n):
+    """Spread the particle loops of `pcall` kernels over n host threads."""
+    global _POOL, THREADS
+    from concurrent.futures import ThreadPoolExecutor
+    THREADS = max(1, int(n))
+    _POOL = ThreadPoolExecutor(THREADS) if THREADS > 1 else None
+
+
+def pcall(name, N, *args):
+    """call() with the rows [0, N) split across the thread pool (ctypes drops the
+    GIL; every oracle kernel only writes row i inside its i-loop)."""
+    if _POOL is None or N < 4096:
+        return call(name, *args)
+    L = lib()
+    fn = getattr(L, "aqo_" + name)
+    cargs = [_arg(a) for a in args]
+    # more chunks than threads: sorted particle sets are far from uniform in cost
+    chunks = THREADS * 8
+    step = (N + chunks - 1) // chunks
+
+    def work(k):
+        L.aqo_set_range(C.c_uint32(k * step), C.c_uint32(min(N, (k + 1) * step)))
+        try:
+            fn(*cargs)
+        finally:
+            L.aqo_set_range(C.c_uint32(0), C.c_uint32(0xFFFFFFFF))
+
+    list(_POOL.map(work, range(chunks)))
+
+
 def vs(dims):
     return 4 if dims == 3 else 2
 

@@ -1,118 +1,2 @@
-"""Synthetic particle sets shared by the CPU and GPU tests and by bench.py.
-
-`dam_break(dims, n_side, ...)` builds a small version of the SPHERIC dam-break
-geometry of the reference examples (examples/{2D,3D}/spheric_testcase*_dambreak):
-a jittered fluid lattice (imove = 1) resting on boundary-integral elements
-(imove = -3, normals pointing out of the fluid, m = element area), a couple of
-sensors (imove = 0) and a few buffer particles (imove = -255) parked at
-domain_max, with a hydrostatic-ish density field and random velocities.
-"""
-import numpy as np
-
-
-def vs(dims):
-    return 4 if dims == 3 else 2
-
-
-def dam_break(dims=3, n_side=12, hfac=2.0, seed=1234, jitter=0.2, n_sensors=3, n_buffer=5,
-              shuffle=True):
-    rng = np.random.default_rng(seed)
-    dr = np.float32(0.01)
-    h = np.float32(hfac * dr)
-    cs, refd = np.float32(40.0), np.float32(998.0)
-    V = vs(dims)
-    # fluid block
-    ax = [np.arange(n_side) for _ in range(dims)]
-    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, dims).astype(np.float64)
-    rf = (g + 0.5) * dr + jitter * dr * rng.uniform(-1, 1, g.shape)
-    nf = rf.shape[0]
-    L = n_side * dr
-    # boundary elements: floor (last axis = 0 plane) and one wall (axis 0 = 0 plane)
-    bax = [np.arange(-2, n_side + 2) for _ in range(dims - 1)]
-    bg = np.stack(np.meshgrid(*bax, indexing="ij"), -1).reshape(-1, dims - 1).astype(np.float64)
-    nb1 = bg.shape[0]
-    floor = np.zeros((nb1, dims))
-    floor[:, :dims - 1] = (bg + 0.5) * dr
-    nfloor = np.zeros((nb1, dims)); nfloor[:, dims - 1] = -1.0
-    wall = np.zeros((nb1, dims))
-    wall[:, 1:] = (bg + 0.5) * dr
-    nwall = np.zeros((nb1, dims)); nwall[:, 0] = -1.0
-    rb = np.concatenate([floor, wall]); nrm = np.concatenate([nfloor, nwall])
-    nb = rb.shape[0]
-    # sensors inside the fluid, buffer particles far away
-    rs = rng.uniform(0.2 * L, 0.8 * L, (n_sensors, dims))
-    domain_min = np.full(dims, -0.5 * L - 0.1)
-    domain_max = np.full(dims, 2.0 * L + 0.1)
-    rbuf = np.tile(domain_max, (n_buffer, 1))
-
-    N = nf + nb + n_sensors + n_buffer
-    r = np.zeros((N, V), np.float32)
-    r[:, :dims] = np.concatenate([rf, rb, rs, rbuf]).astype(np.float32)
-    imove = np.concatenate([np.ones(nf), -3 * np.ones(nb), np.zeros(n_sensors),
-                            -255 * np.ones(n_buffer)]).astype(np.int32)
-    iset = np.concatenate([np.zeros(nf), np.ones(nb), 2 * np.ones(n_sensors),
-                           np.zeros(n_buffer)]).astype(np.uint32)
-    normal = np.zeros((N, V), np.float32)
-    normal[nf:nf + nb, :dims] = nrm
-    tangent = np.zeros((N, V), np.float32)
-    tangent[nf:nf + nb, (1 if dims == 3 else 0)] = 1.0
-    depth = np.clip(L - r[:, dims - 1], 0, None)
-    rho = (refd * (1.0 + 9.81 * depth / cs ** 2) *
-           (1.0 + 1e-3 * rng.uniform(-1, 1, N))).astype(np.float32)
-    rho[imove == -255] = refd
-    m = np.zeros(N, np.float32)
-    m[:nf] = refd * dr ** dims
-    m[nf:nf + nb] = dr ** (dims - 1)            # element area (length in 2-D)
-    m[nf + nb:nf + nb + n_sensors] = refd * dr ** dims
-    u = np.zeros((N, V), np.float32)
-    u[:nf, :dims] = 0.5 * rng.uniform(-1, 1, (nf, dims))
-    dudt = np.zeros((N, V), np.float32)
-    dudt[:nf, :dims] = 5.0 * rng.uniform(-1, 1, (nf, dims))
-    drhodt = np.zeros(N, np.float32)
-    drhodt[:nf] = 10.0 * rng.uniform(-1, 1, nf)
-
-    if shuffle:
-        perm = rng.permutation(N)
-        r, imove, iset, normal, tangent, rho, m, u, dudt, drhodt = (
-            a[perm] for a in (r, imove, iset, normal, tangent, rho, m, u, dudt, drhodt))
-
-    g = np.zeros(V, np.float32); g[dims - 1] = -9.81
-    dmin = np.zeros(V, np.float32); dmin[:dims] = domain_min
-    dmax = np.zeros(V, np.float32); dmax[:dims] = domain_max
-    return dict(
-        dims=dims, N=N, h=float(h), dr=float(dr), cs=float(cs), p0=0.0, support=2.0,
-        refd=np.array([refd, refd, refd], np.float32),
-        visc_dyn=np.array([1e-3, 0.0, 0.0], np.float32),
-        delta=np.array([0.1, 0.0, 0.0], np.float32),
-        g=g, domain_min=dmin, domain_max=dmax, courant=0.25, dt_Ma=0.1, dt_min=1e-7,
-        id=np.arange(N, dtype=np.uint32), r=r, imove=imove, iset=iset, normal=normal,
-        tangent=tangent, rho=rho, m=m, u=u, dudt=dudt, drhodt=drhodt,
-    )
-
-
-def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0):
-    """BASELINE config 5 shape: uniform lattice dr = 1, all fluid, rho = refd,
-    u = 0.01*cs*U(-1,1); no boundary (the ref has no periodic BC)."""
-    rng = np.random.default_rng(seed)
-    V = vs(dims)
-    ax = [np.arange(n_side, dtype=np.float32) for _ in range(dims)]
-    gpos = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, dims)
-    N = gpos.shape[0]
-    r = np.zeros((N, V), np.float32)
-    r[:, :dims] = gpos + 0.5
-    u = np.zeros((N, V), np.float32)
-    u[:, :dims] = (0.01 * cs * rng.uniform(-1, 1, (N, dims))).astype(np.float32)
-    refd = np.float32(1000.0)
-    z = np.zeros(V, np.float32)
-    return dict(
-        dims=dims, N=N, h=float(hfac), dr=1.0, cs=float(cs), p0=0.0, support=2.0,
-        refd=np.array([refd], np.float32), visc_dyn=np.array([1e-3], np.float32),
-        delta=np.array([0.1], np.float32), g=z.copy(), domain_min=z.copy() - 10.0,
-        domain_max=z.copy() + n_side + 10.0, courant=0.25, dt_Ma=0.1, dt_min=1e-7,
-        id=np.arange(N, dtype=np.uint32), r=r, imove=np.ones(N, np.int32),
-        iset=np.zeros(N, np.uint32), normal=np.zeros((N, V), np.float32),
-        tangent=np.zeros((N, V), np.float32),
-        rho=(refd * (1.0 + 1e-3 * rng.uniform(-1, 1, N))).astype(np.float32),
-        m=np.full(N, refd, np.float32), u=u, dudt=np.zeros((N, V), np.float32),
-        drhodt=np.zeros(N, np.float32),
-    )
+"""Re-export of the synthetic case generators (aquagpusph_b200/cases.py)."""
+from aquagpusph_b200.cases import *  # noqa: F401,F403

@@ -96,7 +96,7 @@ def oracle_sweeps(s, dt=1e-4):
     fp = np.zeros((N, V), np.float32); mp = np.zeros((N, 4), np.float32)
     O.call("bie_force_press", imove, r, s["normal"], m, p, fp, mp, s["g"] * 0, N, dims)
     o["force_p"], o["moment_p"] = fp, mp
-    O.call("bie_elastic_bounce", L, imove, r, s["normal"], m, s["u"], dudt, float(dt) * 200, dims)
+    O.call("bie_elastic_bounce", L, imove, r, s["normal"], m, s["u"], dudt, float(dt) * 200, 0.5, dims)
     o["dudt"] = dudt
     fe = np.zeros((N, V), np.float32)
     O.call("bie_force_bound", imove, m, o["dudt_pre"], dudt, fe, N, dims)
@@ -106,7 +106,7 @@ def oracle_sweeps(s, dt=1e-4):
            N, dims)
     o["residual"] = res
     r2 = r.copy()
-    O.call("bie_pst", L, imove, r2, s["normal"], m, rho, float(D.dims), dims)
+    O.call("bie_pst", L, imove, r2, s["normal"], m, rho, float(D.dims), 0.5, dims)
     o["r_pst"] = r2
     dtv = np.zeros(N, np.float32)
     O.call("timestep", imove, s["u"], dtv, N, 1.0, s["dt_min"], s["courant"], s["dt_Ma"], s["h"], dims)
@@ -211,7 +211,7 @@ def cuda_sweeps(ctx, s, dt=1e-4):
 
 
 # tolerance per output: |a - b| <= atol_rel * max|b| + rtol * |b|
-EXACT = {"n_neighs", "binormal", "tangent", "force_p", "moment_p", "dt_var", "dt"}
+EXACT = {"n_neighs", "binormal", "tangent", "dt_var", "dt"}
 ORDER_DEP = {"dudt", "force_elastic", "r_pst", "residual"}
 
 

@@ -1,0 +1,124 @@
+"""Per-kernel timing of the hot-path kernels on a sorted dam-break state.
+
+    python tools/kbench.py [--n 1000000] [--reps 5] [--only NAME] [--hfac 3]
+
+Prints one JSON line per kernel (CUDA-event time, algorithmic bytes, pair counts).
+Used under gpurun / ncu; not part of the product."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aquagpusph_b200 import _lib, cases  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--warm", type=int, default=2)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--hfac", type=float, default=3.0)
+    ap.add_argument("--case", default="spheric2")
+    a = ap.parse_args()
+    t0 = time.time()
+    if a.case == "spheric2":
+        c = cases.spheric2_dam_break(a.n, a.hfac, seed=1)
+    else:
+        c = cases.lattice(int(round(a.n ** (1 / 3))), a.hfac)
+    N, dims = c["N"], c["dims"]
+    ctx = _lib.Context(0, dims=dims, h=c["h"])
+    V, M = (4 if dims == 3 else 2), (16 if dims == 3 else 4)
+    v = {k: ctx.array(c[k]) for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m",
+                                      "u", "dudt", "drhodt", "refd", "visc_dyn", "delta")}
+    for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m", "u", "dudt", "drhodt"):
+        v[k + "_in"] = ctx.empty(c[k].shape, c[k].dtype)
+    for k in ("binormal", "grad_p", "lap_u", "lap_p_corr", "grad_w_bi", "r_bak"):
+        v[k] = ctx.zeros((N, V), np.float32)
+    for k in ("p", "div_u", "shepard", "lap_p", "div_u_bi", "dt_var", "residual_midpoint"):
+        v[k] = ctx.zeros(N, np.float32)
+    v["mls"] = ctx.zeros((N, M), np.float32)
+    v["n_neighs"] = ctx.zeros(N, np.uint32)
+    for k in ("icell", "id_sorted", "id_unsorted"):
+        v[k] = ctx.empty(N, np.uint32)
+    for k in ("N", "cs", "p0", "g", "courant", "dt_Ma", "dt_min", "h", "domain_min", "domain_max"):
+        v[k] = c[k]
+    v.update(dt=1e-4, neighs_limit=100000, mls_imove=1, relax_midpoint=0.1)
+    ihoc = None
+
+    def linklist():
+        nonlocal ihoc
+        _, _, nc, ihoc = ctx.linklist(v["r_in"], 2.0, c["h"], v["icell"], ihoc, v["id_unsorted"],
+                                      v["id_sorted"])
+        v["ihoc"], v["n_cells"] = ihoc, nc
+
+    def backup():
+        for k in ("id", "iset", "imove", "normal", "tangent", "m"):
+            ctx.copy(v[k + "_in"], v[k])
+
+    K = lambda s, e="entry": (lambda: ctx.launch(s, e, v))  # noqa: E731
+    # prepare: predictor, link-list, sort, EOS
+    K("basic/time_scheme/midpoint.cl", "predictor")()
+    linklist(); backup(); K("basic/Sort.cl", "stage1")(); K("basic/Sort.cl", "stage2")()
+    ctx.copy(v["dudt"], v["dudt_in"]); ctx.copy(v["drhodt"], v["drhodt_in"])
+    K("basic/EOS.cl")()
+    ctx.sync()
+    nc = v["n_cells"]
+    imv = v["imove"].get()
+    nfl = int((imv == 1).sum())
+    print(json.dumps(dict(case=a.case, N=N, n_fluid=nfl, n_cells=[int(x) for x in nc], h=c["h"],
+                          setup_s=round(time.time() - t0, 2), sm=ctx.sm_count())), flush=True)
+
+    def relink():
+        # state is already sorted: re-running measures the steady-state (nearly sorted) case
+        K("basic/time_scheme/midpoint.cl", "predictor")()
+        linklist()
+
+    vb = 16 if dims == 3 else 8
+    tests = [
+        ("linklist", relink, (vb + 20 + 4 + 16 * 2 + 8 + 4) * N),
+        ("sort_stage1+2", lambda: (backup(), K("basic/Sort.cl", "stage1")(), K("basic/Sort.cl", "stage2")()), 212 * N),
+        ("predictor", K("basic/time_scheme/midpoint.cl", "predictor"), 112 * N),
+        ("eos", K("basic/EOS.cl"), 16 * N),
+        ("neighs", K("basic/neighs.cl"), 8 * N),
+        ("interactions", K("cfd/Interactions.cl"), 88 * N),
+        ("shepard", K("cfd/Shepard.cl"), 36 * N),
+        ("lapp", K("cfd/deltaSPH.cl", "lapp"), 40 * N),
+        ("full", K("cfd/deltaSPH.cl", "full"), 52 * N),
+        ("lapp_corr", K("cfd/deltaSPH.cl", "lapp_corr"), 60 * N),
+        ("mls", K("basic/MLS.cl"), 92 * N),
+        ("bie_interactions", K("cfd/Boundary/BIe/Interactions.cl"), 76 * N),
+        ("bie_p_boundary", K("cfd/Boundary/BIe/Interactions.cl", "p_boundary"), 36 * N),
+        ("rates", K("cfd/Rates.cl"), 64 * N),
+        ("corrector", K("basic/time_scheme/midpoint.cl", "corrector"), 96 * N),
+        ("timestep", K("cfd/TimeStep.cl"), 24 * N),
+        ("reduce_min", lambda: ctx.reduce(_lib.OP_MIN, v["dt_var"], host=False), 4 * N),
+    ]
+    for name, fn, nbytes in tests:
+        if a.only and a.only not in name:
+            continue
+        if name == "corrector":
+            ctx.copy(v["r_bak"], v["r"])
+        for _ in range(a.warm):
+            fn()
+        e0, e1 = ctx.event(), ctx.event()
+        l0 = ctx.launch_count()
+        ctx.record(e0)
+        for _ in range(a.reps):
+            fn()
+        ctx.record(e1)
+        ms = ctx.elapsed_ms(e0, e1) / a.reps
+        if name == "corrector":
+            ctx.copy(v["r"], v["r_bak"])
+        print(json.dumps(dict(kernel=name, ms=round(ms, 4), launches=(ctx.launch_count() - l0) // a.reps,
+                              alg_GBs=round(nbytes / ms / 1e6, 1),
+                              Mparticles_s=round(N / ms / 1e3, 1))), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

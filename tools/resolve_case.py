@@ -1,0 +1,75 @@
+"""Flattens a reference example (Main.xml + the presets it includes) into ONE
+resolved XML template, using this repo's own XML front-end
+(AQUAgpusph-b200 --resolve = State::parse + State::write).
+
+Build-container only (reads /root/reference); the output is committed under
+aquagpusph_b200/cases_xml/ so that the GPU box, which has no reference tree,
+can run the unchanged pipeline.  The template keeps the example's {{KEY}}
+placeholders; aquagpusph_b200.casegen fills them at run time.
+
+    python tools/resolve_case.py
+"""
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+EXE = os.path.join(ROOT, "aquagpusph_b200", "AQUAgpusph-b200")
+OUT = os.path.join(ROOT, "aquagpusph_b200", "cases_xml")
+
+CASES = {
+    # name: (example dir, dims)
+    "spheric2_dambreak_3d": ("examples/3D/spheric_testcase2_dambreak/src/templates", 3),
+    "spheric5_dambreak_2d": ("examples/2D/spheric_testcase5_dambreak/src/templates", 2),
+}
+
+
+def installed_root(tmp):
+    """resources/ laid out as `make install` does (Presets/src -> Presets)."""
+    r = os.path.join(tmp, "root", "resources")
+    os.makedirs(r)
+    os.symlink(os.path.join(REF, "resources/Presets/src"), os.path.join(r, "Presets"))
+    os.symlink(os.path.join(REF, "resources/Scripts"), os.path.join(r, "Scripts"))
+    return os.path.join(tmp, "root")
+
+
+def resolve(name, src, dims):
+    with tempfile.TemporaryDirectory() as tmp:
+        root = installed_root(tmp)
+        case = os.path.join(tmp, "case")
+        shutil.copytree(os.path.join(REF, src), case)
+        keys = {}
+        for fn in os.listdir(case):
+            if not fn.endswith(".xml"):
+                continue
+            p = os.path.join(case, fn)
+            txt = open(p).read()
+            # the shipped 3-D Main.xml includes a root_path.xml that does not exist
+            txt = "\n".join(l for l in txt.split("\n") if "root_path.xml" not in l)
+            for k in set(re.findall(r"\{\{(\w+)\}\}", txt)):
+                if k not in keys:
+                    keys[k] = "9%06d" % (len(keys) + 1) if k in ("N", "N_SENSORS") \
+                        else "0.9%05d1" % (len(keys) + 1)
+                txt = txt.replace("{{%s}}" % k, keys[k])
+            open(p, "w").write(txt)
+        out = os.path.join(OUT, name + ".xml")
+        subprocess.check_call([EXE, "-i", "Main.xml", "-d", str(dims), "-l", "2", "--root", root,
+                               "--resolve", out], cwd=case)
+        txt = open(out).read()
+        for k, v in keys.items():
+            txt = txt.replace(v, "{{%s}}" % k)
+        hdr = ("<!-- Resolved by tools/resolve_case.py from %s of AQUAgpusph 5.0.4 with the\n"
+               "     presets it includes; generated file, placeholders filled by casegen.py -->\n" % src)
+        txt = txt.replace("<sphInput>\n", hdr + "<sphInput>\n", 1)
+        open(out, "w").write(txt)
+        n = txt.count("<Tool ")
+        print("%s: %d tools, placeholders %s" % (name, n, sorted(keys)))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for name, (src, dims) in CASES.items():
+        resolve(name, src, dims)
