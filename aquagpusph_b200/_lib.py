@@ -14,10 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libaquacuda.so")
 _lib = None
 
-# every symbol include/aquacuda.h declares (checked by tests/test_abi.py)
+# every symbol include/aquacuda.h declares (checked by tests/test_host_cpu.py)
 SYMBOLS = [
     "aqc_ctx_create", "aqc_ctx_destroy", "aqc_last_error", "aqc_set_stream", "aqc_get_stream",
     "aqc_sync", "aqc_launch_count", "aqc_device_sm_count", "aqc_define_round6", "aqc_set_defs",
+    "aqc_set_define",
     "aqc_alloc", "aqc_free", "aqc_host_alloc", "aqc_host_free", "aqc_memcpy_h2d",
     "aqc_memcpy_d2h", "aqc_memcpy_d2d", "aqc_fill", "aqc_linklist_build", "aqc_radix_sort",
     "aqc_scatter_fields", "aqc_reduce", "aqc_kernel_lookup", "aqc_kernel_count",
@@ -61,6 +62,10 @@ def lib():
     L.aqc_define_round6.argtypes = [C.c_float]
     L.aqc_kernel_name.restype = C.c_char_p
     L.aqc_kernel_args.restype = C.POINTER(ArgInfo)
+    L.aqc_kernel_nargs.argtypes = [C.c_int]
+    L.aqc_kernel_args.argtypes = [C.c_int]
+    L.aqc_kernel_name.argtypes = [C.c_int]
+    L.aqc_set_define.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     L.aqc_kernel_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.aqc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.aqc_ctx_destroy.argtypes = [C.c_void_p]

@@ -17,7 +17,7 @@ SYMBOLS = [
     "aqh_last_error", "aqh_set_log_level", "aqh_load", "aqh_parse", "aqh_destroy",
     "aqh_write_resolved", "aqh_n_tools", "aqh_tool_name", "aqh_tool_type", "aqh_tool_elapsed_ms",
     "aqh_tool_used_times", "aqh_step", "aqh_run", "aqh_sync", "aqh_launch_count", "aqh_cuda_ctx",
-    "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
+    "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr",
 ]
 
@@ -57,6 +57,7 @@ def lib():
     L.aqh_launch_count.restype = C.c_uint64
     L.aqh_cuda_ctx.argtypes = [C.c_void_p]
     L.aqh_cuda_ctx.restype = C.c_void_p
+    L.aqh_eval.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
     L.aqh_scalar_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
     L.aqh_scalar_set.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     L.aqh_array_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t),
@@ -76,6 +77,14 @@ def _chk(rc):
 
 def set_log_level(level):
     lib().aqh_set_log_level(int(level))
+
+
+def evaluate(expr, type="float", decls="", dims=3, dtype=np.float32, n=1):
+    """Variables::solve on the host: `decls` = "type name=value;..." (no device)."""
+    out = np.zeros(n, dtype)
+    _chk(lib().aqh_eval(dims, decls.encode(), type.encode(), expr.encode(), out.ctypes.data,
+                        out.nbytes))
+    return out[0] if n == 1 else out
 
 
 class Simulation:

@@ -152,6 +152,42 @@ extern "C" int aqh_sync(aqh_sim* sim)
 extern "C" uint64_t aqh_launch_count(aqh_sim* sim) { return aqc_launch_count(sim->C->ctx()); }
 extern "C" void* aqh_cuda_ctx(aqh_sim* sim) { return sim->C->ctx(); }
 
+extern "C" int aqh_eval(int dims, const char* decls, const char* type, const char* expr,
+                        void* out, size_t bytes)
+{
+    AQH_TRY
+    if (!type || !expr || !out)
+        throw std::runtime_error("aqh_eval: NULL argument");
+    InputOutput::Variables vars(dims, nullptr);
+    std::string d(decls ? decls : "");
+    size_t pos = 0;
+    while (pos < d.size()) {
+        size_t end = d.find(';', pos);
+        if (end == std::string::npos)
+            end = d.size();
+        const std::string item = trimCopy(d.substr(pos, end - pos));
+        pos = end + 1;
+        if (item.empty())
+            continue;
+        const size_t eq = item.find('=');
+        if (eq == std::string::npos)
+            throw std::runtime_error("aqh_eval: \"" + item + "\" is not \"type name=value\"");
+        const std::string lhs = trimCopy(item.substr(0, eq));
+        const size_t sp = lhs.find_last_of(" \t");
+        if (sp == std::string::npos)
+            throw std::runtime_error("aqh_eval: \"" + item + "\" is not \"type name=value\"");
+        vars.registerVariable(trimCopy(lhs.substr(sp + 1)), trimCopy(lhs.substr(0, sp)), "",
+                              trimCopy(item.substr(eq + 1)));
+    }
+    vars.exprVariables(expr); // unknown names are an error (Variable.cpp:1230-1237)
+    const size_t ts = vars.typeToBytes(type);
+    if (!ts || ts > bytes)
+        throw std::runtime_error(std::string("aqh_eval: bad type or buffer for \"") + type + "\"");
+    vars.solve(type, expr, out);
+    return 0;
+    AQH_CATCH
+}
+
 extern "C" int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes)
 {
     AQH_TRY

@@ -45,7 +45,9 @@ class Tokenizer {
     }
 
     /// Names of the variables an expression reads
-    std::vector<std::string> exprVariables(const std::string& eq) const
+    /// (all = true: every identifier that is not a function call or a constant,
+    /// registered or not, so that the caller can reject unknown names at setup)
+    std::vector<std::string> exprVariables(const std::string& eq, bool all = false) const
     {
         std::vector<std::string> out;
         std::set<std::string> seen;
@@ -60,7 +62,7 @@ class Tokenizer {
                 while (k < eq.size() && isspace((unsigned char)eq[k]))
                     k++;
                 const bool is_call = k < eq.size() && eq[k] == '(';
-                if (!is_call && _vars.count(id) && !seen.count(id) && id != "pi" && id != "e" &&
+                if (!is_call && (all || _vars.count(id)) && !seen.count(id) && id != "pi" && id != "e" &&
                     id != "_pi" && id != "_e" && id != "INFINITY") {
                     seen.insert(id);
                     out.push_back(id);

@@ -279,7 +279,7 @@ std::vector<Variable*> Variables::exprVariables(const std::string& expr) const
 {
     std::vector<Variable*> out;
     for (auto part : split_formulae(expr))
-        for (auto id : tok.exprVariables(part)) {
+        for (auto id : tok.exprVariables(part, true)) {
             std::string vn = id;
             for (auto suf : { "_x", "_y", "_z", "_w" })
                 if (endswith(vn, suf) && !get(vn)) {
@@ -287,6 +287,10 @@ std::vector<Variable*> Variables::exprVariables(const std::string& expr) const
                     break;
                 }
             Variable* v = get(vn);
+            // Variable.cpp:1230-1237: an expression naming an unknown variable is an error
+            if (!v && !tok.isVariable(id))
+                throw std::runtime_error("Variable \"" + id + "\", referenced on the expression " +
+                                         expr + ", cannot be found");
             if (v && std::find(out.begin(), out.end(), v) == out.end())
                 out.push_back(v);
         }

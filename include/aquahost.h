@@ -50,6 +50,13 @@ int aqh_sync(aqh_sim* sim);
 uint64_t aqh_launch_count(aqh_sim* sim); /* CUDA kernels launched so far */
 void* aqh_cuda_ctx(aqh_sim* sim);         /* the aqc_ctx* underneath */
 
+/* Variables + Tokenizer without a device (Variable.cpp:1321-1435): register the
+ * scalar variables listed in `decls` ("type name=value;type name=value;...", in
+ * order, values are expressions that may use the earlier names), then evaluate
+ * `expr` as a value of `type` into out.  What `set_scalar` does on the host. */
+int aqh_eval(int dims, const char* decls, const char* type, const char* expr, void* out,
+             size_t bytes);
+
 /* variables */
 int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes);
 int aqh_scalar_set(aqh_sim* sim, const char* name, const char* expression);

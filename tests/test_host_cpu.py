@@ -1,0 +1,240 @@
+"""CPU (no GPU): the C-ABI libraries load and export every symbol the headers
+declare, they refuse to run without a device (no CPU fallback), and the C++
+host's XML front-end / Variables / Tokenizer behave like the reference's
+(State.cpp:276-389,739-1217; Variable.cpp:1321-1545; tests/*/SetScalar)."""
+import ctypes
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+from aquagpusph_b200 import _lib, cases, casegen, host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(aq[ch]_\w+)\s*\(", txt)))
+
+
+def test_aquacuda_exports_every_declared_symbol():
+    names = _declared("aquacuda.h")
+    assert len(names) >= 30
+    L = ctypes.CDLL(os.path.join(ROOT, "aquagpusph_b200", "libaquacuda.so"))
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_aquahost_exports_every_declared_symbol():
+    names = _declared("aquahost.h")
+    L = host.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(host.SYMBOLS) == set(names)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (it never routes to the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.AquaError, match="no CPU fallback"):
+        _lib.Context(0, dims=3, h=0.1)
+    c = cases.spheric2_dam_break(2000, 3.0)
+    with pytest.raises(host.HostError, match="no CPU fallback"):
+        casegen.load("spheric2_dambreak_3d", c, (c["N"] - 8, 8))
+    for mod in ("_lib", "host", "casegen", "cases", "build"):
+        src = open(os.path.join(ROOT, "aquagpusph_b200", mod + ".py")).read()
+        assert "oracle" not in src.replace("the oracle", ""), mod + ".py must not touch oracle/"
+
+
+def test_kernel_registry_matches_reference_signatures():
+    """Appendix D of SURVEY.md: argument names/order the Kernel tool binds by name
+    (Kernel.cpp:497-556).  A few representative hot-path entries."""
+    L = _lib.lib()
+    want = {
+        ("cfd/Interactions.cl", "entry"): ["imove", "r", "u", "rho", "m", "p", "grad_p", "lap_u",
+                                           "div_u", "N", "icell", "ihoc", "n_cells"],
+        ("cfd/Rates.cl", "entry"): ["iset", "imove", "rho", "grad_p", "lap_u", "div_u", "dudt",
+                                    "drhodt", "visc_dyn", "N", "g"],
+        ("cfd/TimeStep.cl", "entry"): ["imove", "u", "dt_var", "N", "dt", "dt_min", "courant",
+                                       "dt_Ma", "h"],
+        ("basic/time_scheme/midpoint.cl", "corrector"): ["imove", "r_in", "r", "u_in", "u", "dudt",
+                                                         "rho_in", "rho", "drhodt", "N", "dt"],
+        ("basic/Sort.cl", "stage2"): ["rho_in", "rho", "m_in", "m", "u_in", "u", "dudt", "dudt_in",
+                                      "drhodt", "drhodt_in", "id_sorted", "N"],
+        ("basic/EOS.cl", "entry"): ["iset", "imove", "rho", "p", "refd", "N", "cs", "p0"],
+    }
+    for (script, entry), names in want.items():
+        # presets write "../Scripts/<path>" or an absolute resources path
+        kid = L.aqc_kernel_lookup(("/x/resources/Scripts/" + script).encode(), entry.encode(), 3)
+        assert kid >= 0, (script, entry)
+        n = L.aqc_kernel_nargs(kid)
+        args = L.aqc_kernel_args(kid)
+        assert [args[k].name.decode() for k in range(n)] == names
+    assert L.aqc_kernel_lookup(b"cfd/NoSuch.cl", b"entry", 3) == -3
+
+
+# ---- Variables / Tokenizer -----------------------------------------------------
+def test_set_scalar_sequence_of_the_reference_test():
+    """tests/3D/SetScalar/cMake/main.xml + check.py: h=1, i=-1, v=(3,4,5,6);
+    set float, recursive float, vector swap, float*int, vector*float ->
+    'i h v' == '-1 -4 (-16,-0.75,5,6)'."""
+    d = "float h=1.0;int i=-1;vec v=3.0, 4.0, 5.0, 6.0"
+    h = host.evaluate("2.0", decls=d)
+    h = host.evaluate("2.0 * h", decls=d.replace("h=1.0", "h=%r" % float(h)))
+    assert h == 4.0
+    v = host.evaluate("v_y,v_x,v_z,v_w", "vec", d, n=4)
+    assert list(v) == [4.0, 3.0, 5.0, 6.0]
+    d2 = "float h=4.0;int i=-1;vec v=4.0, 3.0, 5.0, 6.0"
+    h = host.evaluate("h * i", decls=d2)
+    assert h == -4.0
+    v = host.evaluate("v_x * h,v_y / h,v_z,v_w", "vec", d2.replace("h=4.0", "h=-4.0"), n=4)
+    assert list(v) == [-16.0, -0.75, 5.0, 6.0]
+
+
+def test_expression_semantics():
+    ev = host.evaluate
+    assert ev("1/3") == np.float32(1.0 / 3.0)              # double, narrowed once
+    assert ev("2^3^2") == 512.0                           # right associative
+    assert ev("-2^2") == -4.0
+    assert ev("a < b ? a : b", decls="float a=3;float b=2") == 2.0
+    assert ev("(a > 1) && !(b > 5) || 0", decls="float a=3;float b=2") == 1.0
+    assert ev("sqrt(16) + abs(-1) + max(1,2,3) + min(4,2)") == 10.0
+    assert ev("2.f * 0.5f") == 1.0                        # OpenCL-style literals
+    assert ev("pi") == np.float32(np.pi)
+    assert ev("7 % 4") == 3.0
+    assert ev("7.9", "unsigned int", dtype=np.uint32) == 7  # truncation like numeric_cast
+    assert ev("0.25*h/cs", decls="float dr=0.01;float hfac=3;float h=hfac*dr;float cs=40") == \
+        np.float32(0.25 * float(np.float32(3 * 0.01)) / 40)
+    nc = ev("n_x*n_y, 2, 3, n_w", "uivec4", "uivec4 n=4,5,6,120", dtype=np.uint32, n=4)
+    assert list(nc) == [20, 2, 3, 120]
+    # vec is 2 floats in 2-D and 4 in 3-D (Variable.cpp:1547-1624)
+    assert ev("1,2", "vec", dims=2, n=2).tolist() == [1.0, 2.0]
+    with pytest.raises(host.HostError, match="Invalid number of fields"):
+        ev("1,2", "vec", dims=3, n=4)
+    with pytest.raises(host.HostError, match="cannot be found"):
+        ev("2*nope")
+    with pytest.raises(host.HostError):
+        ev("2*(3")
+    with pytest.raises(host.HostError, match="overflows"):
+        ev("-1", "unsigned int", dtype=np.uint32)
+
+
+# ---- XML front-end ---------------------------------------------------------------
+KEY_ORDER_3D = ["predictor", "Domain", "link-list", "sort stage1", "sort stage2", "EOS",
+                "midpoint loop", "cfd Shepard", "cfd interactions", "cfd lap p", "cfd rates",
+                "midpoint residual", "midpoint loop end", "corrector", "cfd variable time step",
+                "cfd minimum time step", "cfd check time step", "t = t + dt", "iter += 1"]
+
+
+def _parse(txt, dims):
+    d = tempfile.mkdtemp(prefix="aqua_xml_")
+    p = os.path.join(d, "case.xml")
+    open(p, "w").write(txt)
+    return host.Simulation(p, dims=dims, parse_only=True)
+
+
+def test_resolved_dam_break_3d_pipeline():
+    c = cases.spheric2_dam_break(2000, 3.0)
+    sim = _parse(casegen.instantiate("spheric2_dambreak_3d", c, (c["N"] - 8, 8),
+                                     keep_reports=True), 3)
+    tools = sim.tools()
+    names = [t[0] for t in tools]
+    types = [t[1] for t in tools]
+    # 116 tools (indices 0..115) followed by the example's 6 reports
+    assert len(tools) == 122 and names[115] == "End" and types[116:] == [
+        "report_screen", "report_file", "report_performance", "report_particles", "report_screen",
+        "report_file"]
+    assert types.count("link-list") == 1 and types.count("while") == 1 and types.count("end") == 2
+    assert (names[4], names[44], names[50], names[70], names[91], names[93], names[98]) == (
+        "link-list", "midpoint loop", "cfd interactions", "cfd rates", "midpoint loop end",
+        "corrector", "cfd minimum time step")
+    pos = []
+    for key in KEY_ORDER_3D:
+        hits = [i for i, n in enumerate(names) if n.lower() == key.lower()]
+        assert hits, "tool %r missing; have %r" % (key, names)
+        pos.append(hits[0])
+    assert pos == sorted(pos), list(zip(KEY_ORDER_3D, pos))
+    # the midpoint sub-iteration encloses the neighbour sweeps
+    w, e = types.index("while"), names.index("midpoint loop end")
+    inner = names[w:e]
+    assert "cfd interactions" in inner and "cfd rates" in inner
+    sweeps = [n for n, t in tools if t == "kernel"]
+    assert len(sweeps) == 37
+    # flat XML round trip (State::write -> State::parse) keeps the pipeline
+    out = os.path.join(tempfile.mkdtemp(), "resolved.xml")
+    sim.write_resolved(out)
+    again = host.Simulation(out, dims=3, parse_only=True).tools()
+    assert again == tools
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"),
+                    reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("name,src,dims", [
+    ("spheric2_dambreak_3d", "examples/3D/spheric_testcase2_dambreak/src/templates", 3),
+    ("spheric5_dambreak_2d", "examples/2D/spheric_testcase5_dambreak/src/templates", 2),
+])
+def test_committed_templates_match_the_reference_examples(name, src, dims):
+    """The committed resolved templates are what our front-end makes of the
+    reference's unchanged Main.xml + presets (include/prefix/insert semantics of
+    State.cpp:739-1217, lenient handling of the malformed kernel presets)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("resolve_case",
+                                                  os.path.join(ROOT, "tools", "resolve_case.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    out = tempfile.mkdtemp()
+    old = rc.OUT
+    rc.OUT = out
+    try:
+        rc.resolve(name, src, dims)
+    finally:
+        rc.OUT = old
+    fresh = open(os.path.join(out, name + ".xml")).read()
+    committed = open(os.path.join(ROOT, "aquagpusph_b200", "cases_xml", name + ".xml")).read()
+
+    def tools(t):
+        return re.findall(r'<Tool [^>]*name="([^"]*)"[^>]*type="([^"]*)"', t)
+    assert tools(fresh) == tools(committed)
+    n = len(tools(committed))
+    # 116 tools + the example's reports (3-D), 57 (2-D)
+    assert (dims == 3 and n >= 116) or (dims == 2 and n >= 57)
+
+
+def test_tool_placement_semantics():
+    """<Tool action=insert before/after=..., remove, replace> and ifdef gating
+    (State.cpp:778-1021) on a hand-written pipeline."""
+    xml = """<?xml version="1.0" ?>
+<sphInput>
+  <Variables>
+    <Variable name="h" type="float" value="0.1" />
+    <Variable name="a" type="float" value="1" />
+  </Variables>
+  <Definitions>
+    <Define name="WITH_X" value="1" />
+  </Definitions>
+  <Tools>
+    <Tool action="add" name="t1" type="set_scalar" in="a" value="1" />
+    <Tool action="add" name="t3" type="set_scalar" in="a" value="3" />
+    <Tool action="insert" before="t3" name="t2" type="set_scalar" in="a" value="2" />
+    <Tool action="insert" after="t3" name="t4" type="set_scalar" in="a" value="4" />
+    <Tool action="add" name="gone" type="set_scalar" in="a" value="0" />
+    <Tool action="remove" name="gone" type="dummy" />
+    <Tool action="replace" name="t1" type="set_scalar" in="a" value="10" />
+    <Tool action="add" name="gated in" type="dummy" ifdef="WITH_X" />
+    <Tool action="add" name="gated out" type="dummy" ifdef="WITHOUT_X" />
+    <Tool action="try_remove" name="never existed" type="dummy" />
+  </Tools>
+  <Timing><Option name="End" type="Steps" value="1" /></Timing>
+  <ParticlesSet n="4" />
+</sphInput>
+"""
+    names = [t[0] for t in _parse(xml, 2).tools()]
+    assert names == ["t1", "t2", "t3", "t4", "gated in"]
+    with pytest.raises(host.HostError):
+        _parse(xml.replace('before="t3"', 'before="nowhere"'), 2)
