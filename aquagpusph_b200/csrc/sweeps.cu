@@ -6,7 +6,7 @@
 // Arithmetic notes (all inside the stated fp32 tolerance):
 //  * per-j factors are hoisted to the staging step: w_j = wcon*CON*m_j/rho_j;
 //  * per-i factors (1/rho_i, rho_i, __CLEARY__) are applied once after the loop;
-//  * q = sqrt(d2)/H is evaluated as d2*rsqrt(d2)*(1/H); the candidate filter is
+//  * q = sqrt(d2)/H is evaluated as sqrt.approx(d2)*(1/H) (1 ulp); the filter is
 //    d2 < (SUPPORT*H)^2 instead of q >= SUPPORT (differs only for pairs within
 //    an ulp of the cut-off, where the Wendland factors (2-q)^3,(2-q)^4 vanish);
 //  * the i == j exclusion of the reference is implicit wherever the pair term is
@@ -66,11 +66,24 @@ __device__ __forceinline__ void stvec_xyz(void* base, uint32_t i, float x, float
     }
 }
 
-// q from d2 (see header note); d2 == 0 -> q = 0
+// q from d2 (see header note).  sqrt.approx.ftz is one MUFU.SQRT with a maximum
+// relative error of 2^-23 (1 ulp) and maps 0 -> 0, so no special case is needed.
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 1 / x, one MUFU.RCP (maximum relative error 2^-23)
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float q_of(float d2, float invH)
 {
-    const float s = d2 > 0.f ? d2 * rsqrtf(d2) : 0.f;
-    return s * invH;
+    return sqrt_fast(d2) * invH;
 }
 
 struct PBase {
@@ -82,6 +95,7 @@ struct PBase {
 // cfd/Interactions.cl:60-145
 template <int D>
 struct PInteractions : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u;
     const float *rho, *m, *p;
@@ -122,7 +136,7 @@ struct PInteractions : PBase {
             udr += (B.z - s.uz) * dz;
         const float a = (s.p + B.w) * fr;
         const float b0 = udr * fr;
-        const float b = b0 * __frcp_rn(d2 + eps2);
+        const float b = b0 * rcp_fast(d2 + eps2);
         s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
         s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
         s.du += b0;
@@ -142,6 +156,7 @@ struct PInteractions : PBase {
 // basic/Shepard.cl:76-125 (MODE 0) and cfd/Shepard.cl:29-35 (MODE 1)
 template <int D, int MODE>
 struct PShepard : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *rho, *m;
@@ -179,6 +194,7 @@ struct PShepard : PBase {
 // basic/deltaSPH.cl:94-145 (full, VECOUT) and :191-242 (lapp); EXCLUDED = imove != 1
 template <int D, bool VECOUT>
 struct PDeltaGrad : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
     const float *rho, *m, *p;
@@ -228,6 +244,7 @@ struct PDeltaGrad : PBase {
 // basic/deltaSPH.cl:261-313 (lapp_corr): starts from the old lap_p[i] (:287)
 template <int D>
 struct PLappCorr : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
     const float *rho, *m;
@@ -270,6 +287,7 @@ struct PLappCorr : PBase {
 // basic/MLS.cl:58-112
 template <int D>
 struct PMLS : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *rho, *m;
@@ -326,6 +344,7 @@ struct PMLS : PBase {
 // cfd/Sensors.cl:57-130
 template <int D>
 struct PSensors : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 3;
     const void* r;
     const float* m;
@@ -376,6 +395,7 @@ struct PSensors : PBase {
 // cfd/Boundary/BIe/Interactions.cl:48-108
 template <int D>
 struct PBIeInteractions : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *normal, *u;
     const float* m;
@@ -423,6 +443,7 @@ struct PBIeInteractions : PBase {
 // cfd/Boundary/BIe/Interactions.cl:124-170 (p_boundary)
 template <int D>
 struct PBIePBoundary : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *m, *rho;
@@ -460,6 +481,7 @@ struct PBIePBoundary : PBase {
 // cfd/Boundary/BIe/ElasticBounce.cl:64-152 -- order dependent
 template <int D>
 struct PBIeElasticBounce : PBase {
+    static constexpr bool SPHERE = false;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r_in, *normal, *u_in;
     const float* m;
@@ -533,6 +555,7 @@ struct PBIeElasticBounce : PBase {
 // cfd/Boundary/BIe/PST.cl:62-110 -- order dependent (r_i moves inside the loop)
 template <int D>
 struct PBIePST : PBase {
+    static constexpr bool SPHERE = false;
     static constexpr int DIMS = D, NJ4 = 2;
     void* r;
     const void* normal;
@@ -587,6 +610,7 @@ struct PBIePST : PBase {
 // support of every fluid particle, i.e. the pair count the roofline figures use.
 template <int D>
 struct PCountPairs : PBase {
+    static constexpr bool SPHERE = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     uint32_t* n_pairs;
