@@ -147,11 +147,77 @@ class CudaState:
     def get(self, k):
         return self.v[k].get()
 
+    def zero(self, k):
+        a = self.v[k]
+        self.ctx.fill(a, np.zeros(a.elem_bytes // 4, np.float32).tobytes())
+
+    def copy(self, dst, src):
+        self.ctx.copy(self.v[dst], self.v[src])
+
+    def set(self, k, host):
+        self.v[k].set(host)
+
+    def reduce_min(self, k):
+        from aquagpusph_b200 import _lib
+        return np.float32(self.ctx.reduce(_lib.OP_MIN, self.v[k]))
+
+
+class RefState:
+    """The same name-bound state on host arrays, run by the reference's OWN scripts
+    compiled behind the shim (oracle/ref.py)."""
+
+    def __init__(self, R, s):
+        self.R = R
+        self.s = s
+        self.v = {}
+        dims, N = s["dims"], s["N"]
+        V, M = (4 if dims == 3 else 2), (16 if dims == 3 else 4)
+        for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m", "u", "dudt",
+                  "drhodt", "dudt_in", "drhodt_in", "icell", "ihoc", "refd", "visc_dyn", "delta"):
+            self.v[k] = np.ascontiguousarray(s[k]).copy()
+        for k in ("binormal", "grad_p", "lap_u", "lap_p_corr", "grad_w_bi", "force_p",
+                  "force_elastic", "dudt_preelastic", "u_in", "r_in"):
+            self.v[k] = np.zeros((N, V), np.float32)
+        for k in ("p", "div_u", "shepard", "lap_p", "div_u_bi", "residual_midpoint", "dt_var"):
+            self.v[k] = np.zeros(N, np.float32)
+        self.v["n_neighs"] = np.zeros(N, np.uint32)
+        self.v["mls"] = np.zeros((N, M), np.float32)
+        self.v["moment_p"] = np.zeros((N, 4), np.float32)
+        for k in ("N", "cs", "p0", "g", "courant", "dt_Ma", "dt_min", "h"):
+            self.v[k] = s[k]
+        self.v["n_cells"] = s["n_cells"]
+
+    def run(self, script, entry="entry", **over):
+        self.R.run(script, entry, self.s["N"], self.v, **over)
+
+    def get(self, k):
+        return self.v[k].copy()
+
+    def zero(self, k):
+        self.v[k][...] = 0
+
+    def copy(self, dst, src):
+        self.v[dst][...] = self.v[src]
+
+    def set(self, k, host):
+        self.v[k][...] = host
+
+    def reduce_min(self, k):
+        return np.float32(self.v[k].min())
+
 
 def cuda_sweeps(ctx, s, dt=1e-4):
     """Same sequence as oracle_sweeps through libaquacuda (Kernel tool, by name)."""
-    c = CudaState(ctx, s)
-    v = c.v
+    return named_sweeps(CudaState(ctx, s), dt)
+
+
+def ref_sweeps(R, s, dt=1e-4):
+    """Same sequence through the reference's own .cl scripts (oracle/_ref)."""
+    return named_sweeps(RefState(R, s), dt)
+
+
+def named_sweeps(c, dt=1e-4):
+    s = c.s
     o = {}
     c.run("basic/EOS.cl")
     c.run("basic/Binormal.cl")
@@ -181,32 +247,30 @@ def cuda_sweeps(ctx, s, dt=1e-4):
     c.run("cfd/deltaSPH.cl", "full_mls")
     c.run("cfd/deltaSPH.cl", "lapp_corr")
     o["lap_p_corr"], o["lap_p"] = c.get("lap_p_corr"), c.get("lap_p")
-    zero_v = np.zeros(4 if s["dims"] == 3 else 2, np.float32)
-    ctx.fill(v["dudt"], zero_v.tobytes())
-    ctx.fill(v["drhodt"], np.zeros(1, np.float32).tobytes())
+    c.zero("dudt")
+    c.zero("drhodt")
     c.run("cfd/Rates.cl")
     c.run("cfd/deltaSPH.cl", "deltaSPH", dt=dt)
     o["grad_p"], o["div_u"] = c.get("grad_p"), c.get("div_u")
-    ctx.copy(v["dudt_preelastic"], v["dudt"])
+    c.copy("dudt_preelastic", "dudt")
     o["dudt_pre"], o["drhodt"] = c.get("dudt"), c.get("drhodt")
     c.run("cfd/Boundary/BIe/Rates.cl", "force_press", forces_r=s["g"] * 0)
     o["force_p"], o["moment_p"] = c.get("force_p"), c.get("moment_p")
     # ElasticBounce reads r_in / u_in: the un-advanced state
-    ctx.copy(v["r_in"], v["r"])
-    v["u_in"].set(s["u"])
+    c.copy("r_in", "r")
+    c.set("u_in", s["u"])
     c.run("cfd/Boundary/BIe/ElasticBounce.cl", dt=float(dt) * 200)
     o["dudt"] = c.get("dudt")
-    c.run("cfd/Boundary/BIe/ElasticBounce.cl", "force_bound", dudt_elastic=v["dudt"])
+    c.run("cfd/Boundary/BIe/ElasticBounce.cl", "force_bound", dudt_elastic=c.v["dudt"])
     o["force_elastic"] = c.get("force_elastic")
     c.run("basic/time_scheme/midpoint.cl", "residuals")
     o["residual"] = c.get("residual_midpoint")
     c.run("cfd/Boundary/BIe/PST.cl")
     o["r_pst"] = c.get("r")
-    v["u"].set(s["u"])
+    c.set("u", s["u"])
     c.run("cfd/TimeStep.cl", dt=1.0)
     o["dt_var"] = c.get("dt_var")
-    from aquagpusph_b200 import _lib
-    o["dt"] = np.float32(ctx.reduce(_lib.OP_MIN, v["dt_var"]))
+    o["dt"] = c.reduce_min("dt_var")
     return o
 
 

@@ -1,0 +1,105 @@
+"""CPU: pins the oracle (oracle/aqo_*.c, the plain-C restatement) against the
+reference's OWN device scripts, compiled as C++ behind oracle/ref_shim from
+/root/reference/resources/Scripts (oracle/_ref/libaquaref{2,3}d.so; built in the
+build container by __graft_entry__.build()).  Both run the same sequence of
+script kernels, arguments bound by name, on the same cell-sorted dam-break
+state: fluid, boundary-integral elements, sensors and buffer particles.
+
+Both sides are fp32 without FMA contraction and the restatement keeps the
+reference's operation order, so EVERY output must be bit-identical."""
+import numpy as np
+import pytest
+
+import cases
+import pipeline
+from oracle import ref
+
+pytestmark = pytest.mark.skipif(not ref.available() and not ref.build(),
+                                reason="oracle/_ref not built (needs /root/reference once)")
+
+@pytest.mark.parametrize("dims,n,hfac", [(3, 12, 2.0), (2, 50, 3.0), (3, 9, 3.0), (2, 36, 4.0)])
+def test_restatement_matches_reference_scripts(oracle, dims, n, hfac):
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    want = pipeline.ref_sweeps(ref.Ref(dims, case["h"]), s)
+    got = pipeline.oracle_sweeps(s)
+    bad = []
+    for k, a in want.items():
+        b = got[k]
+        a64, b64 = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        if not np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True):
+            bad.append("%s: max err %.3e (scale %.3e)" % (k, np.abs(a64 - b64).max(), np.abs(a64).max()))
+    assert not bad, "\n".join(bad)
+    assert np.abs(want["grad_p"]).max() > 0 and np.abs(want["grad_w_bi"]).max() > 0
+    assert np.abs(want["lap_p"]).max() > 0 and np.abs(want["dudt"] - want["dudt_pre"]).max() > 0
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_time_schemes_and_permutation_match_reference_scripts(oracle, dims):
+    """Element-wise kernels: integrators, Domain, Sort stages, SetBuffer -- bit-exact."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    R = ref.Ref(dims, case["h"])
+    rng = np.random.default_rng(5)
+    base = {k: np.ascontiguousarray(case[k]).copy() for k in
+            ("imove", "iset", "r", "u", "dudt", "rho", "drhodt", "m", "id", "normal", "tangent")}
+
+    def fresh():
+        v = {k: a.copy() for k, a in base.items()}
+        for k in ("r", "u", "dudt"):
+            v[k + "_in"] = rng.normal(size=(N, V)).astype(np.float32)
+        for k in ("rho", "drhodt"):
+            v[k + "_in"] = rng.normal(size=N).astype(np.float32)
+        v.update(N=N, dt=1e-3, relax_midpoint=0.25, domain_min=case["domain_min"],
+                 domain_max=case["domain_max"])
+        return v
+
+    # midpoint scheme pieces, each against the restatement
+    for entry, ofn, outs in (
+            ("predictor", lambda v: oracle.call("mp_predictor", v["r"], v["u"], v["dudt"], v["rho"],
+                                                v["drhodt"], v["r_in"], v["u_in"], v["dudt_in"],
+                                                v["rho_in"], v["drhodt_in"], N, dims),
+             ("r_in", "u_in", "dudt_in", "rho_in", "drhodt_in")),
+            ("midpoint", lambda v: oracle.call("mp_midpoint", v["imove"], v["u_in"], v["u"], v["dudt"],
+                                               v["rho_in"], v["rho"], v["drhodt"], N, 1e-3, dims),
+             ("u", "rho")),
+            ("relax", lambda v: oracle.call("mp_relax", v["imove"], v["dudt_in"], v["dudt"],
+                                            v["drhodt_in"], v["drhodt"], N, 0.25, dims),
+             ("dudt", "drhodt")),
+            ("corrector", lambda v: oracle.call("mp_corrector", v["imove"], v["r_in"], v["r"], v["u_in"],
+                                                v["u"], v["dudt"], v["rho_in"], v["rho"], v["drhodt"],
+                                                N, 1e-3, dims),
+             ("r", "u", "rho"))):
+        rng = np.random.default_rng(5)
+        a = fresh()
+        rng = np.random.default_rng(5)
+        b = fresh()
+        R.run("basic/time_scheme/midpoint.cl", entry, N, a)
+        ofn(b)
+        for k in outs:
+            assert np.array_equal(a[k], b[k]), (entry, k)
+    # Domain
+    rng = np.random.default_rng(5)
+    a = fresh()
+    a["r_in"][::7] *= 100.0
+    a["r_in"][3, 0] = np.nan
+    b = {k: (x.copy() if isinstance(x, np.ndarray) else x) for k, x in a.items()}
+    R.run("basic/Domain.cl", "entry", N, a)
+    oracle.call("domain", b["imove"], b["r_in"], b["u_in"], b["dudt_in"], b["m"], N,
+                b["domain_min"], b["domain_max"], dims)
+    for k in ("imove", "r_in", "u_in", "dudt_in", "m"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert (a["imove"] == -256).any()
+    # basic/Sort.cl stage1 + stage2 == the generic scatter of the restatement
+    ll = oracle.linklist(base["r"], dims, 2.0, case["h"])
+    v = fresh()
+    v["id_sorted"] = ll["inv_perm"]
+    for k in ("id", "iset", "imove", "normal", "tangent", "m"):
+        v[k + "_in"] = base[k].copy()
+    v["r_in"], v["u_in"], v["rho_in"] = base["r"].copy(), base["u"].copy(), base["rho"].copy()
+    R.run("basic/Sort.cl", "stage1", N, v)
+    R.run("basic/Sort.cl", "stage2", N, v)
+    for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m", "u"):
+        assert np.array_equal(v[k], oracle.scatter(base[k], ll["inv_perm"])), k
+    assert np.array_equal(v["dudt_in"], oracle.scatter(base["dudt"], ll["inv_perm"]))   # Sort.cl:119-123
+    assert np.array_equal(v["drhodt_in"], oracle.scatter(base["drhodt"], ll["inv_perm"]))
