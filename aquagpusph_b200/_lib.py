@@ -24,6 +24,8 @@ SYMBOLS = [
     "aqc_scatter_fields", "aqc_reduce", "aqc_kernel_lookup", "aqc_kernel_count",
     "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
+    "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
+    "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -97,6 +99,15 @@ def lib():
         getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     for n in ("aqc_event_destroy", "aqc_event_record", "aqc_event_sync"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_comm_unique_id.argtypes = [C.c_void_p]
+    L.aqc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.aqc_comm_destroy.argtypes = [C.c_void_p]
+    L.aqc_comm_rank.argtypes = [C.c_void_p]
+    L.aqc_comm_size.argtypes = [C.c_void_p]
+    L.aqc_mpi_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint32)]
+    L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     _lib = L
     return L

@@ -75,6 +75,82 @@ def load(template, case, set_sizes, overrides=None, device=0, workdir=None, keep
     return sim
 
 
+def move_tool(txt, name, after):
+    """Re-place one <Tool> of a resolved XML right after the tool called `after`
+    (what <Tool action="insert" after=...> would have produced)."""
+    m = re.search(r'\n[ \t]*<Tool [^>]*name="%s" [^>]*?(/>|>.*?</Tool>)' % re.escape(name), txt, flags=re.S)
+    if not m:
+        raise KeyError("tool %s not found" % name)
+    line = m.group(0)
+    txt = txt[:m.start()] + txt[m.end():]
+    a = re.search(r'\n[ \t]*<Tool [^>]*name="%s" [^>]*?(/>|>.*?</Tool>)' % re.escape(after), txt, flags=re.S)
+    if not a:
+        raise KeyError("tool %s not found" % after)
+    return txt[:a.end()] + line + txt[a.end():]
+
+
+def halo_mask_after_sort(txt):
+    """The reference computes `mpi_neigh_mask` BEFORE the link-list sort of the same
+    step (cfd/MPI/planes.xml:50 inserts it after "mpi remove") and uses it after
+    the particles have been permuted, so the halo selection is stale whenever the
+    sort moves particles (always on the first step).  Multi-device cases of this
+    repository place the tool after the "Sort" stage instead; with that, N-device
+    runs reproduce the single-device run to fp32 summation order."""
+    names = re.findall(r'<Tool [^>]*name="([^"]*mpi neighs mask)"', txt)
+    for nm in names:
+        # keep the set_scalar tools that feed a prefixed plane (MPI.xml of the example)
+        feeders = re.findall(r'<Tool [^>]*name="(%s mpi_plane_[rnp]\w*)"' % re.escape(nm.replace(" mask", "")), txt)
+        anchor = "Sort"
+        for f in feeders:
+            txt = move_tool(txt, f, anchor)
+            anchor = f
+        txt = move_tool(txt, nm, anchor)
+    return txt
+
+
+def instantiate_plain(template, overrides=None, n=None):
+    """A resolved template without placeholders (the reference's own test cases, e.g.
+    tests/2D/MPI_plane): drops <Load>/<Save>/reports, optionally overrides variable
+    values and the particle count."""
+    txt = open(os.path.join(TEMPLATES, template + ".xml")).read()
+    txt = re.sub(r"\s*<Load [^>]*/>", "", txt)
+    txt = re.sub(r"\s*<Save [^>]*/>", "", txt)
+    txt = re.sub(r"\s*<Report [^>]*/>", "", txt)
+    txt = re.sub(r"\s*<Tool [^>]*type=\"report_(file|screen|performance)\"[^>]*/>", "", txt)
+    if n is not None:
+        txt = re.sub(r'(<ParticlesSet n=")\d+(")', lambda m: m.group(1) + str(int(n)) + m.group(2), txt)
+    for name, value in (overrides or {}).items():
+        pat = r'(<Variable name="%s" [^>]*value=")[^"]*(")' % re.escape(name)
+        hits = list(re.finditer(pat, txt))
+        if not hits:
+            raise KeyError("variable %s not found in template %s" % (name, template))
+        m = hits[-1]    # the last definition wins (Variable.cpp:1058-1064)
+        txt = txt[:m.start()] + m.group(1) + str(value) + m.group(2) + txt[m.end():]
+    return txt
+
+
+def load_plain(template, arrays, dims, overrides=None, device=0, mpi_rank=0, mpi_size=1, n=None,
+               unique_id=None):
+    """Simulation for a placeholder-free template; `arrays` = {variable: host array}."""
+    txt = instantiate_plain(template, overrides, n)
+    d = tempfile.mkdtemp(prefix="aqua_case_")
+    path = os.path.join(d, "%s.rank%d.xml" % (template, mpi_rank))
+    with open(path, "w") as f:
+        f.write(txt)
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        sim = host.Simulation(path, dims=dims, device=device, mpi_rank=mpi_rank, mpi_size=mpi_size)
+    finally:
+        os.chdir(cwd)
+    for k, a in arrays.items():
+        sim.upload(k, a)
+    if mpi_size > 1:
+        sim.comm_init(unique_id)
+    sim.xml_path = path
+    return sim
+
+
 def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, **kw):
     """BASELINE config 2 (3-D SPHERIC test 2 dam break) through the unchanged
     116-tool pipeline of examples/3D/spheric_testcase2_dambreak."""

@@ -228,3 +228,30 @@ def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
         tangent=tangent, rho=rho, m=m, u=u, dudt=np.zeros((N, 4), np.float32),
         drhodt=np.zeros(N, np.float32),
     )
+
+
+MPI_PLANE_FIELDS = ("r", "u", "dudt", "rho", "drhodt", "m", "imove")
+
+
+def mpi_plane(table, rank=None):
+    """The reference's multi-device parity case (tests/2D/MPI_plane): `table` is its
+    particles.dat (10000 x 10: r(2) u(2) dudt(2) rho drhodt m imove,
+    main_serial.xml:26).  rank=None: the serial set; rank=0|1: that process' set as
+    tests/2D/MPI_plane/cMake/Create.py:33-60 builds it -- its own particles (x <= 0
+    for rank 0) followed by one buffer particle (imove = -255, parked at (1, 1)) per
+    particle of the other process, so that both hold 10000 rows.
+    Returns (arrays, own) with own = indices of the rows in the serial table."""
+    t = np.asarray(table, np.float32)
+    x = t[:, 0]
+    if rank is None:
+        own = np.arange(len(t))
+        rows = t
+    else:
+        own = np.flatnonzero(x <= 0.0) if rank == 0 else np.flatnonzero(x > 0.0)
+        buf = np.tile(np.array([1, 1, 0, 0, 0, 0, 1, 0, 0, -255], np.float32), (len(t) - len(own), 1))
+        rows = np.concatenate([t[own], buf])
+    arrays = dict(r=np.ascontiguousarray(rows[:, 0:2]), u=np.ascontiguousarray(rows[:, 2:4]),
+                  dudt=np.ascontiguousarray(rows[:, 4:6]), rho=np.ascontiguousarray(rows[:, 6]),
+                  drhodt=np.ascontiguousarray(rows[:, 7]), m=np.ascontiguousarray(rows[:, 8]),
+                  imove=np.ascontiguousarray(rows[:, 9].astype(np.int32)))
+    return arrays, own

@@ -59,6 +59,7 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    aqc_comm_destroy(ctx);
     for (int k = 0; k < 2; k++) {
         cudaFree(ctx->sort_keys[k]);
         cudaFree(ctx->sort_vals[k]);

@@ -32,7 +32,18 @@ struct aqc_ctx {
     void* red_dev = nullptr; // partials
     size_t red_cap = 0;
     void* red_host = nullptr; // pinned 64 B
+    // multi-device (mpi.cu): one process per GPU, NCCL communicator loaded on demand
+    int rank = 0, nranks = 1;
+    void* comm = nullptr;              // ncclComm_t
+    uint32_t* comm_counts = nullptr;   // device: [P] own counts + [P][P] gathered
+    uint32_t* comm_counts_host = nullptr; // pinned mirror
+    uint32_t* comm_perm = nullptr;     // sort permutation of the mask
+    size_t comm_perm_cap = 0;
+    void* comm_send = nullptr;         // packed outgoing fields
+    size_t comm_send_cap = 0;
 };
+
+int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
 
 int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...);
 

@@ -695,6 +695,168 @@ int l_setbuffer_set_imove(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// ---- cfd/MPI.cl:64-91 (copy), :118-157 (append), :173-198 (remove), :212-228
+// (backup_r), :248-267 (sort), :282-295 (eos); cfd/MPI/planes.cl:41-61, 80-99 --------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_copy(uint32_t* mpi_iset, void* mpi_r, void* mpi_u, void* mpi_dudt, float* mpi_rho,
+           float* mpi_drhodt, float* mpi_m, const uint32_t* iset, const void* r, const void* u,
+           const void* dudt, const float* rho, const float* drhodt, const float* m, uint32_t N)
+{
+    GID;
+    mpi_iset[i] = iset[i];
+    V<D>::ld(r, i).st(mpi_r, i);
+    V<D>::ld(u, i).st(mpi_u, i);
+    V<D>::ld(dudt, i).st(mpi_dudt, i);
+    mpi_rho[i] = rho[i];
+    mpi_drhodt[i] = drhodt[i];
+    mpi_m[i] = m[i];
+}
+int l_mpi_copy(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 14);
+    DISPATCH(c, k_mpi_copy, N, (uint32_t*)a[0], a[1], a[2], a[3], (float*)a[4], (float*)a[5],
+             (float*)a[6], (const uint32_t*)a[7], a[8], a[9], a[10], (const float*)a[11],
+             (const float*)a[12], (const float*)a[13], N);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_append(uint32_t* iset, void* r, void* u, void* dudt, float* rho, float* drhodt, float* m,
+             int* imove, const uint32_t* mpi_local_mask, const uint32_t* mpi_iset, const void* mpi_r,
+             const void* mpi_u, const void* mpi_dudt, const float* mpi_rho, const float* mpi_drhodt,
+             const float* mpi_m, uint32_t mpi_rank, uint32_t nbuffer, uint32_t N)
+{
+    GID;
+    if (mpi_local_mask[i] == mpi_rank)
+        return;
+    const size_t o = (size_t)(N - nbuffer) + i; // MPI.cl:148: buffer particles sit at the end
+    imove[o] = 1;
+    iset[o] = mpi_iset[i];
+    V<D>::ld(mpi_r, i).st(r, o);
+    V<D>::ld(mpi_u, i).st(u, o);
+    V<D>::ld(mpi_dudt, i).st(dudt, o);
+    rho[o] = mpi_rho[i];
+    drhodt[o] = mpi_drhodt[i];
+    m[o] = mpi_m[i];
+}
+int l_mpi_append(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 18);
+    DISPATCH(c, k_mpi_append, N, (uint32_t*)a[0], a[1], a[2], a[3], (float*)a[4], (float*)a[5],
+             (float*)a[6], (int*)a[7], (const uint32_t*)a[8], (const uint32_t*)a[9], a[10], a[11],
+             a[12], (const float*)a[13], (const float*)a[14], (const float*)a[15],
+             aqc_scalar<uint32_t>(a, 16), aqc_scalar<uint32_t>(a, 17), N);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_remove(int* imove, void* r, void* u, void* dudt, float* m, const uint32_t* mpi_local_mask,
+             uint32_t mpi_rank, aqc_f4 domain_max, uint32_t N)
+{
+    GID;
+    if (mpi_local_mask[i] == mpi_rank)
+        return;
+    imove[i] = -256;
+    m[i] = 0.f;
+    V<D>::splat(0.f).st(u, i);
+    V<D>::splat(0.f).st(dudt, i);
+    from_f4<D>(domain_max).st(r, i);
+}
+int l_mpi_remove(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    DISPATCH(c, k_mpi_remove, N, (int*)a[0], a[1], a[2], a[3], (float*)a[4], (const uint32_t*)a[5],
+             aqc_scalar<uint32_t>(a, 6), aqc_vec_scalar(a, 7, c->defs.dims), N);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_backup_r(const uint32_t* mpi_neigh_mask, const void* mpi_r, void* mpi_r_in, aqc_f4 r_max,
+               uint32_t mpi_rank, uint32_t N, uint32_t n_radix)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_radix)
+        return;
+    if ((i >= N) || (mpi_neigh_mask[i] == mpi_rank)) {
+        from_f4<D>(r_max).st(mpi_r_in, i);
+        return;
+    }
+    V<D>::ld(mpi_r, i).st(mpi_r_in, i);
+}
+int l_mpi_backup_r(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t n_radix = aqc_scalar<uint32_t>(a, 6);
+    DISPATCH(c, k_mpi_backup_r, n_radix, (const uint32_t*)a[0], a[1], a[2],
+             aqc_vec_scalar(a, 3, c->defs.dims), aqc_scalar<uint32_t>(a, 4),
+             aqc_scalar<uint32_t>(a, 5), n_radix);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_sort(const uint32_t* mpi_iset_in, uint32_t* mpi_iset, const void* mpi_r_in, void* mpi_r,
+           const void* mpi_u_in, void* mpi_u, const float* mpi_rho_in, float* mpi_rho,
+           const float* mpi_m_in, float* mpi_m, const uint32_t* mpi_id_sorted, uint32_t N)
+{
+    GID;
+    const size_t o = mpi_id_sorted[i];
+    mpi_iset[o] = mpi_iset_in[i];
+    V<D>::ld(mpi_r_in, i).st(mpi_r, o);
+    V<D>::ld(mpi_u_in, i).st(mpi_u, o);
+    mpi_rho[o] = mpi_rho_in[i];
+    mpi_m[o] = mpi_m_in[i];
+}
+int l_mpi_sort(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 11);
+    DISPATCH(c, k_mpi_sort, N, (const uint32_t*)a[0], (uint32_t*)a[1], a[2], a[3], a[4], a[5],
+             (const float*)a[6], (float*)a[7], (const float*)a[8], (float*)a[9],
+             (const uint32_t*)a[10], N);
+}
+
+__global__ void __launch_bounds__(256)
+k_mpi_eos(const uint32_t* mpi_iset, const float* mpi_rho, float* mpi_p, const float* refd,
+          uint32_t N, float cs, float p0)
+{
+    GID;
+    mpi_p[i] = p0 + cs * cs * (mpi_rho[i] - refd[mpi_iset[i]]);
+}
+int l_mpi_eos(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_mpi_eos, N, (const uint32_t*)a[0], (const float*)a[1], (float*)a[2],
+           (const float*)a[3], N, aqc_scalar<float>(a, 5), aqc_scalar<float>(a, 6));
+    return AQC_OK;
+}
+
+// planes.cl: HALO = false -> local_mask (d > 0), true -> neigh_mask (d >= -SUPPORT*H)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_plane_mask(const int* imove, const void* r, uint32_t* mask, aqc_f4 plane_r, aqc_f4 plane_n,
+                 uint32_t proc, uint32_t N, int halo, float reach)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    const float d = (V<D>::ld(r, i) - from_f4<D>(plane_r)).dot(from_f4<D>(plane_n));
+    if (halo ? (d >= -reach) : (d > 0.f))
+        mask[i] = proc;
+}
+int l_mpi_local_mask(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    DISPATCH(c, k_mpi_plane_mask, N, (const int*)a[0], a[1], (uint32_t*)a[2],
+             aqc_vec_scalar(a, 3, c->defs.dims), aqc_vec_scalar(a, 4, c->defs.dims),
+             aqc_scalar<uint32_t>(a, 5), N, 0, 0.f);
+}
+int l_mpi_neigh_mask(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    DISPATCH(c, k_mpi_plane_mask, N, (const int*)a[0], a[1], (uint32_t*)a[2],
+             aqc_vec_scalar(a, 3, c->defs.dims), aqc_vec_scalar(a, 4, c->defs.dims),
+             aqc_scalar<uint32_t>(a, 5), N, 1, c->defs.SUPPORT * c->defs.H);
+}
+
 // ---- case-local script of the 3-D dam-break example (wave height probes):
 // examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60 ------------
 __global__ void __launch_bounds__(256)
@@ -725,6 +887,48 @@ int l_h_sensor(aqc_ctx* c, size_t, void* const* a)
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
+
+#define MPI_FIELDS_OUT                                                            \
+    OUT("mpi_iset", "unsigned int*"), OUT("mpi_r", "vec*"), OUT("mpi_u", "vec*"),  \
+    OUT("mpi_dudt", "vec*"), OUT("mpi_rho", "float*"), OUT("mpi_drhodt", "float*"), \
+    OUT("mpi_m", "float*")
+#define MPI_FIELDS_IN                                                             \
+    IN("mpi_iset", "unsigned int*"), IN("mpi_r", "vec*"), IN("mpi_u", "vec*"),     \
+    IN("mpi_dudt", "vec*"), IN("mpi_rho", "float*"), IN("mpi_drhodt", "float*"),   \
+    IN("mpi_m", "float*")
+aqc_registrar r_mpi_copy("cfd/MPI.cl", "copy", 0,
+    { MPI_FIELDS_OUT, IN("iset", "unsigned int*"), IN("r", "vec*"), IN("u", "vec*"),
+      IN("dudt", "vec*"), IN("rho", "float*"), IN("drhodt", "float*"), IN("m", "float*"),
+      SC("N", "usize") }, l_mpi_copy);
+aqc_registrar r_mpi_append("cfd/MPI.cl", "append", 0,
+    { OUT("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"), OUT("dudt", "vec*"),
+      OUT("rho", "float*"), OUT("drhodt", "float*"), OUT("m", "float*"), OUT("imove", "int*"),
+      IN("mpi_local_mask", "usize*"), MPI_FIELDS_IN, SC("mpi_rank", "unsigned int"),
+      SC("nbuffer", "usize"), SC("N", "usize") }, l_mpi_append);
+aqc_registrar r_mpi_remove("cfd/MPI.cl", "remove", 0,
+    { OUT("imove", "int*"), OUT("r", "vec*"), OUT("u", "vec*"), OUT("dudt", "vec*"),
+      OUT("m", "float*"), IN("mpi_local_mask", "usize*"), SC("mpi_rank", "unsigned int"),
+      SC("domain_max", "vec"), SC("N", "usize") }, l_mpi_remove);
+aqc_registrar r_mpi_backup_r("cfd/MPI.cl", "backup_r", 0,
+    { IN("mpi_neigh_mask", "usize*"), IN("mpi_r", "vec*"), OUT("mpi_r_in", "vec*"),
+      SC("r_max", "vec"), SC("mpi_rank", "unsigned int"), SC("N", "usize"),
+      SC("n_radix", "usize") }, l_mpi_backup_r);
+aqc_registrar r_mpi_sort("cfd/MPI.cl", "sort", 0,
+    { IN("mpi_iset_in", "unsigned int*"), OUT("mpi_iset", "unsigned int*"), IN("mpi_r_in", "vec*"),
+      OUT("mpi_r", "vec*"), IN("mpi_u_in", "vec*"), OUT("mpi_u", "vec*"),
+      IN("mpi_rho_in", "float*"), OUT("mpi_rho", "float*"), IN("mpi_m_in", "float*"),
+      OUT("mpi_m", "float*"), IN("mpi_id_sorted", "usize*"), SC("N", "usize") }, l_mpi_sort);
+aqc_registrar r_mpi_eos("cfd/MPI.cl", "eos", 0,
+    { OUT("mpi_iset", "unsigned int*"), OUT("mpi_rho", "float*"), OUT("mpi_p", "float*"),
+      IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"), SC("p0", "float") }, l_mpi_eos);
+aqc_registrar r_mpi_lmask("cfd/MPI/planes.cl", "local_mask", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), OUT("mpi_local_mask", "usize*"),
+      SC("mpi_plane_r", "vec"), SC("mpi_plane_n", "vec"), SC("mpi_plane_proc", "unsigned int"),
+      SC("N", "usize") }, l_mpi_local_mask);
+aqc_registrar r_mpi_nmask("cfd/MPI/planes.cl", "neigh_mask", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), OUT("mpi_neigh_mask", "usize*"),
+      SC("mpi_plane_r", "vec"), SC("mpi_plane_n", "vec"), SC("mpi_plane_proc", "unsigned int"),
+      SC("N", "usize") }, l_mpi_neigh_mask);
 
 aqc_registrar r_h_sensor("h_sensor.cl", "entry", 3,
     { IN("imove", "int*"), IN("r", "vec*"), OUT("h_sensorz", "float*"), SC("N", "uint"),

@@ -481,6 +481,9 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
         else
             minmax_kernel<2><<<grid, 256, 0, ctx->stream>>>((const float*)r, N, ctx->minmax_dev);
         AQC_LAUNCH_CHECK(ctx);
+        // multi-device: one global grid (addition to the reference, see mpi.cu)
+        if (int rcc = aqc_comm_minmax(ctx, ctx->minmax_dev))
+            return rcc;
         AQC_CUDA(ctx, cudaMemcpyAsync(ctx->minmax_host, ctx->minmax_dev, 8 * sizeof(uint32_t),
                                       cudaMemcpyDeviceToHost, ctx->stream));
         // the reference blocks here too (LinkList.cpp:350-356)

@@ -28,6 +28,9 @@
 #include "aqc_common.cuh"
 
 struct LLParams {
+    // cell of the i particles: the same array as `icell`, except for the remote
+    // (halo) lists of cfd/MPI.cl, LINKLIST_REMOTE_PARAMS (types.h:117-122)
+    const uint32_t* __restrict__ icell_i;
     const uint32_t* __restrict__ icell;
     const uint32_t* __restrict__ ihoc;
     uint32_t nx, ny, nz, nw; // n_cells (svec4)
@@ -69,7 +72,7 @@ sweep_kernel(const P p, const LLParams ll)
     uint32_t remaining = __ballot_sync(0xffffffffu, active);
     if (!remaining)
         return;
-    const uint32_t c_i = active ? __ldg(ll.icell + i) : 0xFFFFFFFFu;
+    const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
     typename P::IState st;
     if (active)
         p.load_i(st, i);
@@ -199,7 +202,7 @@ sweep2_kernel(const P p, const LLParams ll)
     uint32_t remaining = __ballot_sync(0xffffffffu, active);
     if (!remaining)
         return;
-    const uint32_t c_i = active ? __ldg(ll.icell + i) : 0xFFFFFFFFu;
+    const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
     typename P::IState st;
     st.x = st.y = st.z = 0.f;
     if (active)

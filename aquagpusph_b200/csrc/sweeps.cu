@@ -606,6 +606,102 @@ struct PBIePST : PBase {
 };
 
 // ------------------------------------------------------------------------
+// cfd/MPI.cl:328-374 (gamma) and :404-485 (interactions): the halo particles
+// received from the neighbour processes have their own link-list on the local
+// grid; every remote j counts (no imove test) and the result is ADDED to what
+// the local sweeps left in the output arrays.
+template <int D>
+struct PMpiGamma : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void *r, *mpi_r;
+    const float *mpi_rho, *mpi_m;
+    float* shepard;
+    float cW;
+    struct IState { float x, y, z, s; };
+    __device__ bool i_active(int mv) const { return !((mv < -3) || ((mv > 0) && (mv != 1))); }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.s = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j);
+        o[0] = make_float4(a.x, a.y, a.z, cW * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        s.s += (1.f + 2.f * q) * (t2 * t2) * A.w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { shepard[i] += s.s; }
+};
+
+template <int D>
+struct PMpiInteractions : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *u, *mpi_r, *mpi_u;
+    const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
+    void *grad_p, *lap_u;
+    float* div_u;
+    float cF, eps2;
+    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.p = __ldg(p + i);
+        s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j), b = ldvec<D>(mpi_u, j);
+        o[0] = make_float4(a.x, a.y, a.z, cF * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(mpi_p + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float t = 2.f - q_of(d2, invH);
+        const float fr = (t * t) * (t * A.w);
+        float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
+        if constexpr (D == 3)
+            udr += (B.z - s.uz) * dz;
+        const float a = (s.p + B.w) * fr;
+        const float b0 = udr * fr;
+        const float b = b0 * rcp_fast(d2 + eps2);
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+        s.du += b0;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float cl = Wend<D>::CLEARY * ir;
+        const float4 g0 = ldvec_rw<D>(grad_p, i), l0 = ldvec_rw<D>(lap_u, i);
+        stvec_xyz<D>(grad_p, i, g0.x + s.gx * ir, g0.y + s.gy * ir, g0.z + s.gz * ir);
+        stvec_xyz<D>(lap_u, i, l0.x + s.lx * cl, l0.y + s.ly * cl, l0.z + s.lz * cl);
+        div_u[i] += s.du * rho_i;
+    }
+};
+
+// ------------------------------------------------------------------------
 // Diagnostic (not a reference script): number of fluid neighbours within the kernel
 // support of every fluid particle, i.e. the pair count the roofline figures use.
 template <int D>
@@ -675,7 +771,7 @@ LLParams make_ll(void* const* a, int k_icell, size_t N)
 {
     // LINKLIST_LOCAL_PARAMS = icell, ihoc, n_cells (types.h:106-109)
     LLParams ll;
-    ll.icell = (const uint32_t*)a[k_icell];
+    ll.icell_i = ll.icell = (const uint32_t*)a[k_icell];
     ll.ihoc = (const uint32_t*)a[k_icell + 1];
     const aqc_u4 nc = aqc_scalar<aqc_u4>(a, k_icell + 2);
     ll.nx = nc.x; ll.ny = nc.y; ll.nz = nc.z; ll.nw = nc.w;
@@ -835,6 +931,41 @@ int l_neighs(aqc_ctx* ctx, size_t, void* const* a)
     return AQC_OK;
 }
 
+// LINKLIST_REMOTE_PARAMS = icell, mpi_icell, mpi_ihoc, n_cells (types.h:117-122)
+LLParams make_ll_remote(void* const* a, int k_icell, size_t N)
+{
+    LLParams ll;
+    ll.icell_i = (const uint32_t*)a[k_icell];
+    ll.icell = (const uint32_t*)a[k_icell + 1];
+    ll.ihoc = (const uint32_t*)a[k_icell + 2];
+    const aqc_u4 nc = aqc_scalar<aqc_u4>(a, k_icell + 3);
+    ll.nx = nc.x; ll.ny = nc.y; ll.nz = nc.z; ll.nw = nc.w;
+    ll.N = (uint32_t)N;
+    return ll;
+}
+template <int D> int run_mpi_gamma(aqc_ctx* ctx, void* const* a)
+{
+    PMpiGamma<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.mpi_r = a[4]; p.mpi_rho = (const float*)a[5]; p.mpi_m = (const float*)a[6];
+    p.shepard = (float*)a[7];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll_remote(a, 9, aqc_scalar<uint32_t>(a, 8)));
+}
+int l_mpi_gamma(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_gamma, c, a); }
+template <int D> int run_mpi_inter(aqc_ctx* ctx, void* const* a)
+{
+    PMpiInteractions<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.p = (const float*)a[4];
+    p.mpi_r = a[5]; p.mpi_u = a[6]; p.mpi_rho = (const float*)a[7]; p.mpi_p = (const float*)a[8];
+    p.mpi_m = (const float*)a[9]; p.grad_p = a[10]; p.lap_u = a[11]; p.div_u = (float*)a[12];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, make_ll_remote(a, 14, aqc_scalar<uint32_t>(a, 13)));
+}
+int l_mpi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_inter, c, a); }
+
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
@@ -880,6 +1011,16 @@ aqc_registrar r_bie_eb("cfd/Boundary/BIe/ElasticBounce.cl", "entry", 0,
 aqc_registrar r_bie_pst("cfd/Boundary/BIe/PST.cl", "entry", 0,
     { IN("imove", "int*"), OUT("r", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
       IN("rho", "float*"), SC("N", "usize"), LL_ARGS }, l_bie_pst);
+#define LL_REMOTE_ARGS IN("icell", "usize*"), IN("mpi_icell", "usize*"), IN("mpi_ihoc", "usize*"), SC("n_cells", "svec4")
+aqc_registrar r_mpi_gamma("cfd/MPI.cl", "gamma", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      IN("mpi_r", "vec*"), IN("mpi_rho", "float*"), IN("mpi_m", "float*"), OUT("shepard", "float*"),
+      SC("N", "usize"), LL_REMOTE_ARGS }, l_mpi_gamma);
+aqc_registrar r_mpi_inter("cfd/MPI.cl", "interactions", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"), IN("p", "float*"),
+      IN("mpi_r", "vec*"), IN("mpi_u", "vec*"), IN("mpi_rho", "float*"), IN("mpi_p", "float*"),
+      IN("mpi_m", "float*"), OUT("grad_p", "vec*"), OUT("lap_u", "vec*"), OUT("div_u", "float*"),
+      SC("N", "usize"), LL_REMOTE_ARGS }, l_mpi_inter);
 template <int D> int run_count_pairs(aqc_ctx* ctx, void* const* a)
 {
     PCountPairs<D> p;

@@ -15,6 +15,7 @@ _lib = None
 
 SYMBOLS = [
     "aqh_last_error", "aqh_set_log_level", "aqh_load", "aqh_parse", "aqh_destroy",
+    "aqh_comm_unique_id", "aqh_comm_init",
     "aqh_write_resolved", "aqh_n_tools", "aqh_tool_name", "aqh_tool_type", "aqh_tool_elapsed_ms",
     "aqh_tool_used_times", "aqh_step", "aqh_run", "aqh_sync", "aqh_launch_count", "aqh_cuda_ctx",
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
@@ -40,6 +41,8 @@ def lib():
                            C.POINTER(C.c_void_p)]
     L.aqh_parse.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     L.aqh_destroy.argtypes = [C.c_void_p]
+    L.aqh_comm_unique_id.argtypes = [C.c_void_p]
+    L.aqh_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     L.aqh_write_resolved.argtypes = [C.c_void_p, C.c_char_p]
     L.aqh_n_tools.argtypes = [C.c_void_p]
     L.aqh_tool_name.argtypes = [C.c_void_p, C.c_int]
@@ -87,6 +90,13 @@ def evaluate(expr, type="float", decls="", dims=3, dtype=np.float32, n=1):
     return out[0] if n == 1 else out
 
 
+def comm_unique_id():
+    """ncclGetUniqueId on this process (rank 0); distribute the bytes to every rank."""
+    buf = C.create_string_buffer(128)
+    _chk(lib().aqh_comm_unique_id(buf))
+    return buf.raw
+
+
 class Simulation:
     """FileManager::load + CalcServer (parse_only=True: XML front-end only, no GPU)."""
 
@@ -100,6 +110,11 @@ class Simulation:
         else:
             _chk(lib().aqh_load(xml_path.encode(), dims, device, r, mpi_rank, mpi_size,
                                 C.byref(self.h)))
+
+    def comm_init(self, unique_id):
+        """Join the run's NCCL communicator (unique_id: 128 bytes from comm_unique_id() of rank 0)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _chk(lib().aqh_comm_init(self.h, buf))
 
     def close(self):
         if self.h:

@@ -511,6 +511,80 @@ void UnSort::_execute()
                              src, dst, eb));
 }
 
+// ------------------------------------------------------------------ MPISync --
+void MPISync::setup()
+{
+    // MPISync::variables (MPISync.cpp:232-298): mask must be size_t*, fields arrays of its length
+    _mask = variable(_mask_name, true);
+    if (!_C->variables()->isSameType(_mask->type(), "size_t*"))
+        throw std::runtime_error("The tool \"" + name() + "\" is asking the variable \"" + _mask_name +
+                                 "\", which has an invalid type (\"size_t*\" was expected)");
+    for (auto& f : split(_fields_txt)) {
+        if (trimCopy(f).empty())
+            continue;
+        InputOutput::Variable* v = variable(trimCopy(f), true);
+        if (v->length() != _mask->length())
+            throw std::runtime_error("Wrong variable length in the tool \"" + name() + "\": \"" +
+                                     _mask_name + "\" has length " + std::to_string(_mask->length()) +
+                                     ", \"" + v->name() + "\" has length " + std::to_string(v->length()));
+        _fields.push_back(v);
+    }
+    // processes="" -> every other rank (CalcServer.cpp:354-374)
+    for (auto& p : split(_procs_txt)) {
+        if (trimCopy(p).empty())
+            continue;
+        unsigned v = 0;
+        _C->variables()->solve("unsigned int", p, &v);
+        if ((int)v >= _C->mpi_size())
+            throw std::runtime_error("The tool \"" + name() + "\": process " + std::to_string(v) +
+                                     " does not exist");
+        _procs.push_back(v);
+    }
+}
+
+void MPISync::_execute()
+{
+    if (_C->mpi_size() <= 1)
+        return; // MPISync.cpp:186-187
+    std::vector<void*> ptrs;
+    std::vector<size_t> eb;
+    for (auto v : _fields) {
+        ptrs.push_back(v->dptr());
+        eb.push_back(v->typesize());
+    }
+    check(aqc_mpi_sync(_C->ctx(), (aqc_usize*)_mask->dptr(), (aqc_usize)_mask->length(),
+                       (int)ptrs.size(), ptrs.data(), eb.data(), (int)_procs.size(),
+                       _procs.empty() ? nullptr : _procs.data(), nullptr));
+}
+
+// ------------------------------------------------------------- MPIAllReduce --
+void MPIAllReduce::setup()
+{
+    _var = variable(_var_name, false, true);
+    const std::string op = toLowerCopy(trimCopy(_op_txt));
+    if (op == "min") _op = AQC_OP_MIN;
+    else if (op == "max") _op = AQC_OP_MAX;
+    else if (op == "sum" || op == "add") _op = AQC_OP_SUM;
+    else
+        throw std::runtime_error("The tool \"" + name() + "\": unknown operation \"" + _op_txt + "\"");
+    if (_var->compsize() != 4 || _var->typesize() > 64)
+        throw std::runtime_error("The tool \"" + name() + "\": \"" + _var_name +
+                                 "\" must be made of 32-bit components");
+    _type = _var->kind() == 'f' ? AQC_T_F32 : (_var->kind() == 'u' ? AQC_T_U32 : AQC_T_I32);
+    _count = _var->ncomp();
+}
+
+void MPIAllReduce::_execute()
+{
+    if (_C->mpi_size() <= 1)
+        return;
+    std::vector<char> v(_var->typesize());
+    memcpy(v.data(), _var->get(), v.size());
+    check(aqc_allreduce_host(_C->ctx(), _op, _type, v.data(), _count));
+    _var->set(v.data());
+    _C->variables()->populate(_var);
+}
+
 // ------------------------------------------------------------------- Report --
 Report::Report(CalcServer* C, const std::string& name, const std::string& kind,
                const ProblemSetup::Tool& t, bool once)
@@ -829,6 +903,10 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
         return new While(this, name, t.get("condition"), once);
     if (type == "endif" || type == "end")
         return new End(this, name, once);
+    if (type == "mpi-sync")
+        return new MPISync(this, name, t.get("mask"), t.get("fields"), t.get("processes"), once);
+    if (type == "mpi-allreduce")
+        return new MPIAllReduce(this, name, t.get("in"), t.get("operation"), once);
     if (type == "dummy")
         return new Tool(this, name, once);
     if (startswith(type, "report_"))
@@ -866,6 +944,12 @@ void CalcServer::setup()
         }
     for (auto& t : _tools)
         t->setup();
+}
+
+void CalcServer::commInit(const void* unique_id)
+{
+    if (aqc_comm_init(_ctx, _mpi_rank, _mpi_size, unique_id))
+        throw std::runtime_error(std::string("Cannot join the communicator: ") + aqc_last_error(_ctx));
 }
 
 void CalcServer::step()

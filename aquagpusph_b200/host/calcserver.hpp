@@ -235,6 +235,43 @@ class UnSort : public Tool {
     InputOutput::Variable *_in = nullptr, *_out = nullptr, *_perm = nullptr;
 };
 
+/// type="mpi-sync" (MPISync.cpp:183-232): particles whose `mask` names another
+/// process travel there; what arrives is packed at the front of the same arrays.
+/// The exchange runs over NCCL between device buffers (aqc_mpi_sync).
+class MPISync : public Tool {
+  public:
+    MPISync(CalcServer* C, const std::string& name, const std::string& mask,
+            const std::string& fields, const std::string& procs, bool once)
+      : Tool(C, name, once), _mask_name(mask), _fields_txt(fields), _procs_txt(procs) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _mask_name, _fields_txt, _procs_txt;
+    InputOutput::Variable* _mask = nullptr;
+    std::vector<InputOutput::Variable*> _fields;
+    std::vector<unsigned> _procs;
+};
+
+/// type="mpi-allreduce" in="var" operation="min|max|sum" -- NOT a reference tool:
+/// the reference has no collective, so dt / residuals are per process there
+/// (SURVEY 5.8); multi-device cases of this repository add it after the
+/// reductions whose result must be the same on every rank.
+class MPIAllReduce : public Tool {
+  public:
+    MPIAllReduce(CalcServer* C, const std::string& name, const std::string& var,
+                 const std::string& op, bool once)
+      : Tool(C, name, once), _var_name(var), _op_txt(op) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _var_name, _op_txt;
+    InputOutput::Variable* _var = nullptr;
+    int _op = 0, _type = 0;
+    size_t _count = 1;
+};
+
 /// report_screen / report_file / report_dump / report_performance, and <Reports>
 class Report : public Tool {
   public:
@@ -300,6 +337,9 @@ class CalcServer {
     /// ASCII dump of the <Save> fields of every set (ASCII.cpp:240-333 layout)
     void saveParticles(const std::string& suffix);
     uint64_t steps_done() const { return _steps; }
+    /// Join the NCCL communicator of the run (id = 128 bytes made by rank 0 with
+    /// aqc_comm_unique_id and distributed by the launcher); replaces MPI_Init
+    void commInit(const void* unique_id);
 
   private:
     void buildDefinitions();

@@ -89,6 +89,23 @@ extern "C" int aqh_load(const char* xml_path, int dims, int device, const char* 
     AQH_CATCH
 }
 
+extern "C" int aqh_comm_unique_id(void* id_out)
+{
+    if (aqc_comm_unique_id(id_out)) {
+        g_err = "cannot create a NCCL unique id (libnccl.so.2 missing?)";
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int aqh_comm_init(aqh_sim* sim, const void* unique_id)
+{
+    AQH_TRY
+    sim->C->commInit(unique_id);
+    return 0;
+    AQH_CATCH
+}
+
 extern "C" void aqh_destroy(aqh_sim* sim) { delete sim; }
 
 extern "C" int aqh_write_resolved(aqh_sim* sim, const char* path)

@@ -150,6 +150,38 @@ const aqc_arg_info* aqc_kernel_args(int kernel_id);
  * registry order.  n = global work size (Kernel.cpp:558-594). */
 int aqc_launch(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nargs);
 
+/* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI
+ * rank/size queries and wrappers (AuxiliarMethods.cpp:388-516) and the MPISync
+ * tool (MPISync.cpp:183-232; kernels MPISync.cl.in:31-80), whose host-staged
+ * clEnqueueReadBuffer -> MPI_Isend / MPI_Recv -> clEnqueueWriteBuffer per field
+ * (MPISync.cpp:564-638, 932-1052) becomes grouped ncclSend/ncclRecv between
+ * device buffers.  NCCL is dlopen'ed on first use. ---------------------------- */
+#define AQC_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId); the caller distributes the 128 bytes
+ * (torch.distributed broadcast, a file, MPI ...) and every rank calls init */
+int aqc_comm_unique_id(void* id_out);
+int aqc_comm_init(aqc_ctx* ctx, int rank, int size, const void* unique_id);
+int aqc_comm_destroy(aqc_ctx* ctx);
+int aqc_comm_rank(const aqc_ctx* ctx);
+int aqc_comm_size(const aqc_ctx* ctx);
+/* MPISync::_execute.  mask: n usize, the destination process of every element
+ * (elements with mask == own rank stay).  The mask is sorted (stable), the fields
+ * are gathered in that order, the block bound to each process of `procs`
+ * (NULL/0: every other rank) is sent, and what the peers send is packed at the
+ * FRONT of the same field arrays in process order; on return mask[k] = sender
+ * rank over the received blocks and = own rank elsewhere.  *n_received (host,
+ * may be NULL) = number of elements received.  Syncs once (counts).  With one
+ * rank nothing happens, like MPISync.cpp:186-187. */
+int aqc_mpi_sync(aqc_ctx* ctx, aqc_usize* mask, aqc_usize n, int nfields, void* const* fields,
+                 const size_t* elem_bytes, int nprocs, const unsigned* procs,
+                 aqc_usize* n_received);
+/* ADDITIONS to the reference, which has no collective: element-wise
+ * all-reduce (AQC_OP_*, AQC_T_*) of a device array in place / of a small host
+ * value (<= 64 bytes; syncs).  aqc_linklist_build all-reduces r_min / r_max by
+ * itself when a communicator exists, so every rank hashes on one global grid. */
+int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, size_t count);
+int aqc_allreduce_host(aqc_ctx* ctx, int op, int type, void* host_inout, size_t count);
+
 /* ---- events / profiling (Tool.cpp:296-310, Kernel.cpp:48-116) ------------ */
 int aqc_event_create(aqc_ctx* ctx, void** ev);
 int aqc_event_destroy(aqc_ctx* ctx, void* ev);

@@ -31,6 +31,11 @@ int aqh_load(const char* xml_path, int dims, int device, const char* root_path, 
  * and tool placement; the result serves aqh_write_resolved / aqh_n_tools /
  * aqh_tool_name / aqh_tool_type. */
 int aqh_parse(const char* xml_path, int dims, const char* root_path, aqh_sim** out);
+/* Multi-device runs (one process per GPU; replaces Aqua::MPI::init, main.cpp:112):
+ * rank 0 makes the 128-byte id, the launcher distributes it (torch.distributed
+ * broadcast, a file ...), every rank loaded with mpi_size > 1 joins before stepping. */
+int aqh_comm_unique_id(void* id_out_128_bytes);
+int aqh_comm_init(aqh_sim* sim, const void* unique_id);
 void aqh_destroy(aqh_sim* sim);
 /* State::write: the resolved problem as one flat XML (checkpoint format) */
 int aqh_write_resolved(aqh_sim* sim, const char* path);

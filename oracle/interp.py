@@ -172,9 +172,44 @@ _LITERALS = {"VEC_ZERO": (0.0, True), "VEC_ONE": (1.0, False), "VEC_ALL_ONE": (1
              "INFINITY": (math.inf, True), "MAT_ZERO": (0.0, True)}
 
 
+class LocalTransport:
+    """N interpreter ranks inside one process (one Python thread per rank)."""
+
+    def __init__(self, size):
+        import threading
+        self.size = size
+        self._slots = [None] * size
+        self._barrier = threading.Barrier(size)
+
+    def allgather(self, rank, obj):
+        self._slots[rank] = obj
+        self._barrier.wait()
+        out = list(self._slots)
+        self._barrier.wait()
+        return out
+
+
+class TorchTransport:
+    """One interpreter rank per process over torch.distributed (gloo on CPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.size = dist.get_world_size()
+
+    def allgather(self, rank, obj):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
 class Interpreter:
-    def __init__(self, xml_text, dims):
+    def __init__(self, xml_text, dims, rank=0, size=1, transport=None):
         self.dims = dims
+        self.rank, self.size, self.transport = rank, size, transport
+        if size > 1 and transport is None:
+            raise ValueError("a multi-rank interpreter needs a transport")
+        self._ref = None
         self.root = ET.fromstring(re.sub(r"<!--.*?-->", "", xml_text, flags=re.S))
         self.sets = []
         for s in self.root.iter("ParticlesSet"):
@@ -187,7 +222,7 @@ class Interpreter:
         n_radix = 1
         while n_radix < ((N + 1023) // 1024) * 1024:
             n_radix *= 2
-        for name, typ, val in [("mpi_rank", "unsigned int", "0"), ("mpi_size", "unsigned int", "1"),
+        for name, typ, val in [("mpi_rank", "unsigned int", str(rank)), ("mpi_size", "unsigned int", str(size)),
                                ("dims", "unsigned int", str(dims)), ("t", "float", "0"),
                                ("dt", "float", "0"), ("iter", "unsigned int", "0"),
                                ("frame", "unsigned int", "0"), ("N", "size_t", str(N)),
@@ -371,6 +406,10 @@ class Interpreter:
             self.reduction(t)
         elif typ == "link-list":
             self.linklist(t)
+        elif typ == "mpi-sync":
+            self.mpi_sync(t)
+        elif typ == "mpi-allreduce":
+            self.mpi_allreduce(t)
         else:
             raise NotImplementedError("oracle interpreter: tool type %s" % typ)
         return i + 1
@@ -398,15 +437,87 @@ class Interpreter:
         self.publish(t["out"])
 
     def linklist(self, t):
+        """LinkList tool with the attribute defaults of State.cpp:1104-1114."""
         V = self.V
         r = V[t.get("in", "r")]
-        res = O.linklist(r, self.dims, float(V["support"]), float(V["h"]))
-        V["r_min"], V["r_max"] = res["rmin"], res["rmax"]
-        V["n_cells"] = res["ncells"]
-        V["icell"], V["ihoc"] = res["icell"], res["ihoc"]
-        V["id_unsorted"], V["id_sorted"] = res["perm"], res["inv_perm"]
-        for k in ("r_min", "r_max", "n_cells"):
-            self.publish(k)
+        vmin, vmax = t.get("min", "r_min"), t.get("max", "r_max")
+        recompute = (t.get("recompute_grid", "true").lower() != "false")
+        rmin = rmax = None
+        if recompute:
+            rmin = np.zeros(O.vs(self.dims), np.float32)
+            rmax = np.zeros(O.vs(self.dims), np.float32)
+            O.call("minmax", np.ascontiguousarray(r), r.shape[0], self.dims, rmin, rmax)
+            if self.size > 1:
+                # ADDITION to the reference (one global grid, see csrc/mpi.cu aqc_comm_minmax)
+                allmm = self.transport.allgather(self.rank, (rmin, rmax))
+                rmin = np.min([a for a, _ in allmm], axis=0)
+                rmax = np.max([b for _, b in allmm], axis=0)
+        else:
+            rmin, rmax = np.array(V[vmin], np.float32), np.array(V[vmax], np.float32)
+        res = O.linklist(r, self.dims, float(V["support"]), float(V["h"]), rmin, rmax, recompute=False)
+        if recompute:
+            V[vmin], V[vmax] = res["rmin"], res["rmax"]
+            self.publish(vmin)
+            self.publish(vmax)
+        nc = t.get("n_cells", "n_cells")
+        V[nc] = res["ncells"]
+        self.publish(nc)
+        icell, ihoc = t.get("icell", "icell"), t.get("ihoc", "ihoc")
+        perm, inv = t.get("perm", "id_unsorted"), t.get("inv_perm", "id_sorted")
+        n = r.shape[0]
+        for name, val in ((icell, res["icell"]), (perm, res["perm"]), (inv, res["inv_perm"])):
+            if V[name].shape[0] == n:
+                V[name] = val
+            else:
+                V[name][:n] = val
+        if ihoc == "ihoc" or V[ihoc].shape[0] < res["ihoc"].shape[0]:
+            V[ihoc] = res["ihoc"]       # reallocatable (LinkList.cpp:234-271)
+        else:
+            V[ihoc][:res["ihoc"].shape[0]] = res["ihoc"]
+
+    def mpi_sync(self, t):
+        """MPISync::_execute (MPISync.cpp:183-232) on host arrays."""
+        if self.size <= 1:
+            return
+        V = self.V
+        mask = V[t["mask"]]
+        fields = [f.strip() for f in t["fields"].split(",") if f.strip()]
+        procs = [int(self.eval(p)) for p in t.get("processes", "").split(",") if p.strip()]
+        if not procs:
+            procs = [p for p in range(self.size) if p != self.rank]
+        perm = np.argsort(mask, kind="stable")
+        smask = mask[perm]
+        sends = {}
+        for p in procs:
+            if p == self.rank:
+                continue
+            sel = perm[smask == p]          # sorted block bound to p, original order kept
+            sends[p] = [V[f][sel].copy() for f in fields]
+        got = self.transport.allgather(self.rank, sends)
+        mask[...] = self.rank
+        off = 0
+        for p in sorted(procs):
+            if p == self.rank:
+                continue
+            data = got[p].get(self.rank) if isinstance(got[p], dict) else None
+            if not data or not len(data[0]):
+                continue
+            n = len(data[0])
+            for f, a in zip(fields, data):
+                V[f][off:off + n] = a
+            mask[off:off + n] = p
+            off += n
+
+    def mpi_allreduce(self, t):
+        if self.size <= 1:
+            return
+        name, op = t["in"], t.get("operation", "min").strip().lower()
+        vals = self.transport.allgather(self.rank, np.array(self.V[name]))
+        fn = {"min": np.min, "max": np.max, "sum": np.sum, "add": np.sum}[op]
+        r = fn(np.array(vals), axis=0)
+        dt, n = self._base(self.types[name])
+        self.V[name] = np.asarray(r, dt) if n > 1 else dt(r)
+        self.publish(name)
 
     # -- script kernels
     def kernel(self, path, entry):
@@ -516,7 +627,23 @@ class Interpreter:
             keep = (V["imove"] > 0) & ~((np.abs(x) > np.float32(2) * dr) | (np.abs(r[:, 1]) > np.float32(2) * dr))
             V["h_sensorz"][...] = np.where(keep, r[:, 2] + np.float32(0.5) * dr, np.float32(0))
         else:
+            self._ref_kernel(rel, entry)
+
+    def _ref_kernel(self, rel, entry, n=None):
+        """Kernels without a plain-C restatement (cfd/MPI.cl, cfd/MPI/planes.cl,
+        basic/SetBuffer.cl) run through the reference's OWN script compiled behind
+        the shim (oracle/ref.py), arguments bound by name like Kernel.cpp:497-556."""
+        from . import ref
+        if self._ref is None:
+            if not ref.available() and not ref.build():
+                raise NotImplementedError("oracle interpreter: kernel %s::%s needs oracle/_ref" % (rel, entry))
+            self._ref = ref.Ref(self.dims, float(self.V["h"]))
+        if (rel, entry) not in self._ref.index:
             raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
+        names, kinds = self._ref.index[(rel, entry)]
+        if n is None:   # Kernel::computeGlobalWorkSize (Kernel.cpp:558-594)
+            n = max([self.V[k].shape[0] for k, kd in zip(names, kinds) if kd == "ptr"] + [1])
+        self._ref.run(rel, entry, n, self.V)
 
     def _bie_eb(self):
         V = self.V

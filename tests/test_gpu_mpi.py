@@ -1,0 +1,192 @@
+"""GPU: the multi-device path.  (a) one GPU: every cfd/MPI.cl and cfd/MPI/planes.cl
+kernel through the Kernel-tool C-ABI against the reference's own scripts
+(oracle/_ref); (b) two GPUs (skipped with fewer): the reference's tests/2D/MPI_plane
+case on two processes -- mpi-sync over NCCL, one process per GPU -- against the
+two-rank CPU oracle and against the single-GPU run."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import mpi_common
+from aquagpusph_b200 import _lib
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("dims", [2, 3])
+def test_mpi_kernels_match_reference_scripts(oracle, dims):
+    case = cases.dam_break(dims, 14 if dims == 3 else 60, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    n_radix = 1
+    while n_radix < ((N + 1023) // 1024) * 1024:
+        n_radix *= 2
+    rng = np.random.default_rng(11)
+    ll = oracle.linklist(case["r"], dims, 2.0, case["h"])
+    inv = ll["inv_perm"]
+    s = {k: oracle.scatter(case[k], inv) for k in ("imove", "iset", "r", "u", "dudt", "rho", "drhodt", "m")}
+    nrecv = N // 3
+    host = dict(s)
+    host["p"] = rng.normal(size=N).astype(np.float32) * 100
+    for k, shape in (("mpi_r", (n_radix, V)), ("mpi_u", (n_radix, V)), ("mpi_dudt", (n_radix, V)),
+                     ("mpi_r_in", (n_radix, V)), ("mpi_u_in", (n_radix, V))):
+        host[k] = np.zeros(shape, np.float32)
+    for k in ("mpi_rho", "mpi_drhodt", "mpi_m", "mpi_p", "mpi_rho_in", "mpi_m_in"):
+        host[k] = np.ones(n_radix, np.float32)
+    for k in ("mpi_iset", "mpi_iset_in", "mpi_local_mask", "mpi_neigh_mask", "mpi_icell", "mpi_ihoc",
+              "mpi_id_sorted", "mpi_id_unsorted"):
+        host[k] = np.zeros(n_radix, np.uint32)
+    host.update(icell=ll["icell"], ihoc=ll["ihoc"], n_cells=ll["ncells"], N=N, n_radix=n_radix,
+                mpi_rank=1, nbuffer=int((s["imove"] == -255).sum()) + nrecv, cs=case["cs"], p0=0.0,
+                refd=case["refd"], domain_max=case["domain_max"], r_max=ll["rmax"],
+                mpi_plane_proc=0)
+    pr = np.zeros(V, np.float32)
+    pr[0] = float(np.median(s["r"][s["imove"] == 1][:, 0]))
+    pn = np.zeros(V, np.float32)
+    pn[0] = -1.0
+    host.update(mpi_plane_r=pr, mpi_plane_n=pn)
+    host["grad_p"] = rng.normal(size=(N, V)).astype(np.float32)
+    host["lap_u"] = rng.normal(size=(N, V)).astype(np.float32)
+    host["div_u"] = rng.normal(size=N).astype(np.float32)
+    host["shepard"] = rng.uniform(0.5, 1, N).astype(np.float32)
+
+    R = ref.Ref(dims, case["h"])
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    dev = {k: (ctx.array(v) if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] in (N, n_radix)
+               else v) for k, v in host.items()}
+    dev["refd"] = ctx.array(case["refd"])
+    hostv = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in host.items()}
+
+    def both(script, entry, n=None, exact=True, outs=()):
+        R.run(script, entry, n if n is not None else n_radix, hostv)
+        ctx.launch(script, entry, dev, n=n if n is not None else n_radix)
+        for k in outs:
+            a, b = hostv[k], dev[k].get()
+            if exact:
+                assert np.array_equal(a, b, equal_nan=True), (script, entry, k)
+            else:
+                sc = np.abs(a).max()
+                assert np.abs(a.astype(np.float64) - b).max() <= 5e-6 * sc + 1e-30, (script, entry, k)
+
+    for name in ("mpi_local_mask", "mpi_neigh_mask"):
+        hostv[name][...] = 1
+        dev[name].set(hostv[name])
+    both("cfd/MPI/planes.cl", "local_mask", outs=("mpi_local_mask",))
+    both("cfd/MPI/planes.cl", "neigh_mask", outs=("mpi_neigh_mask",))
+    assert 0 < (hostv["mpi_neigh_mask"][:N] == 0).sum() < N
+    both("cfd/MPI.cl", "copy", outs=("mpi_iset", "mpi_r", "mpi_u", "mpi_dudt", "mpi_rho", "mpi_drhodt", "mpi_m"))
+    # pretend the first nrecv rows arrived from process 0
+    m = np.ones(n_radix, np.uint32)
+    m[:nrecv] = 0
+    for name in ("mpi_local_mask", "mpi_neigh_mask"):
+        hostv[name][...] = m
+        dev[name].set(m)
+    both("cfd/MPI.cl", "append", outs=("iset", "r", "u", "dudt", "rho", "drhodt", "m", "imove"))
+    both("cfd/MPI.cl", "remove", outs=("imove", "r", "u", "dudt", "m"))
+    both("cfd/MPI.cl", "backup_r", n=n_radix, outs=("mpi_r_in",))
+    for k in ("mpi_iset", "mpi_u", "mpi_rho", "mpi_m"):
+        hostv[k + "_in"][...] = hostv[k]
+        dev[k + "_in"].set(hostv[k])
+    # remote link-list on the LOCAL grid (recompute_grid="false")
+    icell, perm, invp = (ctx.empty(n_radix, np.uint32) for _ in range(3))
+    _, _, nc, ihoc = ctx.linklist(dev["mpi_r_in"], 2.0, case["h"], icell, None, perm, invp,
+                                  rmin=ll["rmin"], rmax=ll["rmax"], recompute=False)
+    rl = oracle.linklist(hostv["mpi_r_in"], dims, 2.0, case["h"], ll["rmin"], ll["rmax"], recompute=False)
+    assert np.array_equal(icell.get(), rl["icell"]) and np.array_equal(invp.get(), rl["inv_perm"])
+    assert np.array_equal(ihoc.get()[:nc[3]], rl["ihoc"][:nc[3]])
+    hostv.update(mpi_icell=rl["icell"], mpi_ihoc=rl["ihoc"], mpi_id_sorted=rl["inv_perm"])
+    dev.update(mpi_icell=icell, mpi_ihoc=ihoc, mpi_id_sorted=invp)
+    both("cfd/MPI.cl", "sort", outs=("mpi_iset", "mpi_r", "mpi_u", "mpi_rho", "mpi_m"))
+    both("cfd/MPI.cl", "eos", outs=("mpi_p",))
+    both("cfd/MPI.cl", "gamma", n=N, exact=False, outs=("shepard",))
+    both("cfd/MPI.cl", "interactions", n=N, exact=False, outs=("grad_p", "lap_u", "div_u"))
+    ctx.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gpu_rank(rank, port, q, fixed_mask, overrides, steps):
+    import torch.distributed as dist
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=2)
+    from aquagpusph_b200 import cases as cs, casegen, host
+    host.set_log_level(3)
+    table = np.load(os.path.join(HERE, "golden", "reference_inputs.npz"))["mpi_plane_2D"]
+    uid = [host.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    arrays, own = cs.mpi_plane(table, rank)
+    import mpi_common as mc
+    import tempfile
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "mpi.rank%d.xml" % rank)
+    open(path, "w").write(mc.mpi_xml(overrides, fixed_mask))
+    sim = host.Simulation(path, dims=2, device=rank, mpi_rank=rank, mpi_size=2)
+    for k, a in arrays.items():
+        sim.upload(k, a)
+    sim.comm_init(uid[0])
+    sim.step(steps)
+    res = {k: sim.download(k, np.int32 if k == "imove" else np.float32, unsorted=True) for k in mc.FIELDS}
+    res["own"] = own
+    res["launches"] = sim.launch_count()
+    q.put((rank, res))
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+def _run_two_gpus(fixed_mask, overrides, steps=1):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_rank, args=(r, port, q, fixed_mask, overrides, steps)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=600) for _ in range(2))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    return got
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_mpi_plane_two_gpus(golden, oracle):
+    if not _two_gpus():
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    table = golden["mpi_plane_2D"]
+    # (1) the reference's test as shipped: serial == 2 processes to 1e-6, and GPU == oracle
+    got = _run_two_gpus(False, None)
+    assert all(got[r]["launches"] > 0 for r in range(2))
+    mpi_common.check_against_serial(mpi_common.oracle_serial(table), got, 1e-6)
+    want = mpi_common.oracle_two_ranks_threads(table)
+    for r in range(2):
+        for k in mpi_common.FIELDS:
+            a, b = np.asarray(want[r][k], np.float64), np.asarray(got[r][k], np.float64)
+            assert np.abs(a - b).max() <= 1e-6 * max(np.abs(a).max(), 1e-30), (r, k)
+    # (2) rates that count (relax 0) and the halo mask taken after the sort:
+    #     two GPUs reproduce the serial run and the two-rank oracle
+    ov = {"relax_midpoint": "0.0"}
+    got = _run_two_gpus(True, ov)
+    serial = mpi_common.oracle_serial(table, 1, ov)
+    mpi_common.check_against_serial(serial, got, 2e-5, relative=True)
+    want = mpi_common.oracle_two_ranks_threads(table, 1, ov, fixed_mask=True)
+    for r in range(2):
+        for k in mpi_common.FIELDS:
+            a, b = np.asarray(want[r][k], np.float64), np.asarray(got[r][k], np.float64)
+            assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-30), (r, k)

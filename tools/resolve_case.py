@@ -21,9 +21,13 @@ EXE = os.path.join(ROOT, "aquagpusph_b200", "AQUAgpusph-b200")
 OUT = os.path.join(ROOT, "aquagpusph_b200", "cases_xml")
 
 CASES = {
-    # name: (example dir, dims)
+    # name: (example dir, dims[, main file])
     "spheric2_dambreak_3d": ("examples/3D/spheric_testcase2_dambreak/src/templates", 3),
     "spheric5_dambreak_2d": ("examples/2D/spheric_testcase5_dambreak/src/templates", 2),
+    "spheric2_dambreak_mpi_3d": ("examples/3D/spheric_testcase2_dambreak_mpi/src/templates", 3),
+    # the reference's own multi-device parity test (tests/2D/MPI_plane)
+    "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
+    "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
 }
 
 
@@ -36,7 +40,7 @@ def installed_root(tmp):
     return os.path.join(tmp, "root")
 
 
-def resolve(name, src, dims):
+def resolve(name, src, dims, main="Main.xml"):
     with tempfile.TemporaryDirectory() as tmp:
         root = installed_root(tmp)
         case = os.path.join(tmp, "case")
@@ -49,6 +53,8 @@ def resolve(name, src, dims):
             txt = open(p).read()
             # the shipped 3-D Main.xml includes a root_path.xml that does not exist
             txt = "\n".join(l for l in txt.split("\n") if "root_path.xml" not in l)
+            # CTest placeholders of the reference's tests (cMake/Test.cmake:3-19)
+            txt = txt.replace("@RESOURCES_DIR@", os.path.join(root, "resources"))
             for k in set(re.findall(r"\{\{(\w+)\}\}", txt)):
                 if k not in keys:
                     keys[k] = "9%06d" % (len(keys) + 1) if k in ("N", "N_SENSORS") \
@@ -56,9 +62,10 @@ def resolve(name, src, dims):
                 txt = txt.replace("{{%s}}" % k, keys[k])
             open(p, "w").write(txt)
         out = os.path.join(OUT, name + ".xml")
-        subprocess.check_call([EXE, "-i", "Main.xml", "-d", str(dims), "-l", "2", "--root", root,
+        subprocess.check_call([EXE, "-i", main, "-d", str(dims), "-l", "2", "--root", root,
                                "--resolve", out], cwd=case)
         txt = open(out).read()
+        txt = txt.replace(root, "")
         for k, v in keys.items():
             txt = txt.replace(v, "{{%s}}" % k)
         hdr = ("<!-- Resolved by tools/resolve_case.py from %s of AQUAgpusph 5.0.4 with the\n"
@@ -71,5 +78,5 @@ def resolve(name, src, dims):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for name, (src, dims) in CASES.items():
-        resolve(name, src, dims)
+    for name, spec in CASES.items():
+        resolve(name, *spec)
