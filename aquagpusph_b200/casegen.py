@@ -36,9 +36,12 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
         "DELTA": repr(float(case["delta"][0])), "G": repr(float(-case["g"][case["dims"] - 1])),
         "N": str(int(set_sizes[0])),
         "N_SENSORS": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
+        "CLTYPE": "GPU", "CLDEVICE": "0", "CLPLATFORM": "0",
     }
     for k, v in rep.items():
         txt = txt.replace("{{%s}}" % k, v)
+    # the MPI example's Fluids.xml leaves the size of set 0 to the particle file
+    txt = txt.replace("<ParticlesSet>", '<ParticlesSet n="%d">' % int(set_sizes[0]), 1)
     # particle data travel through aqh_array_upload, not through files
     txt = re.sub(r"\s*<Load [^>]*/>", "", txt)
     txt = re.sub(r"\s*<Save [^>]*/>", "", txt)
@@ -55,9 +58,11 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
 
 
 def load(template, case, set_sizes, overrides=None, device=0, workdir=None, keep_reports=False,
-         mpi_rank=0, mpi_size=1):
+         mpi_rank=0, mpi_size=1, unique_id=None, transform=None, extra_tools=None):
     """Create a Simulation for `case` and upload its particle arrays."""
     txt = instantiate(template, case, set_sizes, overrides, keep_reports)
+    if transform:
+        txt = transform(txt)
     d = workdir or tempfile.mkdtemp(prefix="aqua_case_")
     path = os.path.join(d, "%s.rank%d.xml" % (template, mpi_rank))
     with open(path, "w") as f:
@@ -71,6 +76,8 @@ def load(template, case, set_sizes, overrides=None, device=0, workdir=None, keep
         os.chdir(cwd)
     for k in STATE_FIELDS:
         sim.upload(k, case[k])
+    if mpi_size > 1:
+        sim.comm_init(unique_id)
     sim.xml_path = path
     return sim
 
@@ -149,6 +156,57 @@ def load_plain(template, arrays, dims, overrides=None, device=0, mpi_rank=0, mpi
         sim.comm_init(unique_id)
     sim.xml_path = path
     return sim
+
+
+def add_tool_after(txt, after, tool_xml):
+    """Insert one <Tool .../> line after the tool called `after` in a resolved XML."""
+    a = re.search(r'\n[ \t]*<Tool [^>]*name="%s" [^>]*?(/>|>.*?</Tool>)' % re.escape(after), txt, flags=re.S)
+    if not a:
+        raise KeyError("tool %s not found" % after)
+    return txt[:a.end()] + "\n        " + tool_xml + txt[a.end():]
+
+
+def multi_device_fixes(txt):
+    """What this repository changes in the reference's MPI example pipeline so that an
+    N-device run is a consistent simulation: the halo mask is taken after
+    the sort (halo_mask_after_sort) and dt / the midpoint residual are all-reduced, so
+    every rank advances with the same time step and leaves the inner loop together.
+    When the halo exchange sits outside the midpoint loop (the example's include order,
+    TODO at cfd/MPI.xml:21-23) it is moved inside, right after "midpoint eos": the
+    reference exchanges u and rho of the halo once per step and iterates on stale
+    copies, which makes the N-device result differ from the 1-device one by ~1e-2 next
+    to the cuts; refreshed every sub-iteration the two agree to fp32 summation order."""
+    txt = halo_mask_after_sort(txt)
+    order = [m.group(1) for m in re.finditer(r'<Tool [^>]*name="([^"]*)"', txt)]
+    if "midpoint eos" in order and "mpi neighs sync" in order and \
+            order.index("mpi neighs sync") < order.index("midpoint loop"):
+        chain = ["mpi neighs mask reset"]
+        for nm in [n for n in order if n.endswith("mpi neighs mask")]:
+            chain += [n for n in order if re.match(re.escape(nm.replace(" mask", "")) + r" mpi_plane_", n)]
+            chain.append(nm)
+        chain += ["mpi neighs copy", "mpi neighs sync"]
+        anchor = "midpoint eos"
+        for nm in chain:
+            txt = move_tool(txt, nm, anchor)
+            anchor = nm
+    txt = add_tool_after(txt, "cfd minimum time step",
+                         '<Tool action="add" name="mpi global dt" type="mpi-allreduce" once="false" '
+                         'in="dt" operation="min" />')
+    txt = add_tool_after(txt, "midpoint residual",
+                         '<Tool action="add" name="mpi global residual" type="mpi-allreduce" '
+                         'once="false" in="Residual_midpoint" operation="sum" />')
+    return txt
+
+
+def spheric2_slab(n_total, rank, size, hfac=3.0, overrides=None, device=0, unique_id=None, **kw):
+    """BASELINE config 3: the 3-D dam break on `size` devices (y slabs) through the
+    pipeline of examples/3D/spheric_testcase2_dambreak_mpi (131 tools: midpoint, BIe
+    boundaries, variable time step, cfd/MPI.xml migration + halo)."""
+    from . import cases
+    c = cases.spheric2_dam_break_slab(n_total, hfac, rank, size)
+    sim = load("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), overrides, device,
+               mpi_rank=rank, mpi_size=size, unique_id=unique_id, transform=multi_device_fixes, **kw)
+    return sim, c
 
 
 def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, **kw):

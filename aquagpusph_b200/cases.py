@@ -230,6 +230,59 @@ def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
     )
 
 
+def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None):
+    """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way
+    examples/3D/spheric_testcase2_dambreak_mpi/src/Create.py:140-200 does it: rank k
+    owns the fluid with y in (y_min + k dy, y_min + (k+1) dy), dy = (domain_max_y -
+    domain_min_y) / size (templates/MPI.xml:24-38), carries boundary elements and the
+    sensors itself (the reference replicates ALL of them on every rank; here only those
+    within `boundary_margin` of the slab, default 4 h, which is every element a particle
+    of the slab or of its halo can see) and ends set 0 with buffer particles
+    (imove = -255 parked at domain_max, Create.py:170-190) that receive migrating
+    particles.  The y limits of the domain hug the tank (2 dr of slack) so that the
+    slabs hold the same amount of fluid.  Returns the case dict of this rank with
+    n_set0 (fluid + boundary + buffer) and the global particle count."""
+    c = spheric2_dam_break(n_total, hfac)
+    dr, h = c["dr"], c["h"]
+    dmin, dmax = c["domain_min"].copy(), c["domain_max"].copy()
+    dmin[1], dmax[1] = -0.5 - 2.0 * dr, 0.5 + 2.0 * dr
+    dy = (float(dmax[1]) - float(dmin[1])) / size
+    y0, y1 = float(dmin[1]) + rank * dy, float(dmin[1]) + (rank + 1) * dy
+    margin = 4.0 * h if boundary_margin is None else boundary_margin
+    y = c["r"][:, 1]
+    imove = c["imove"]
+    fluid = np.flatnonzero((imove == 1) & (y > y0) & (y <= y1))
+    bound = np.flatnonzero((imove == -3) & (y > y0 - margin) & (y <= y1 + margin))
+    sens = np.flatnonzero(imove == 0)
+    nbuf = max(1024, int(buffer_frac * len(fluid)))
+    keep0 = np.concatenate([fluid, bound])
+    N0 = len(keep0) + nbuf
+    N = N0 + len(sens)
+    out = dict(c)
+    for k in ("r", "normal", "tangent", "u", "dudt"):
+        a = np.zeros((N, 4), np.float32)
+        a[:len(keep0)] = c[k][keep0]
+        a[N0:] = c[k][sens]
+        if k == "r":
+            a[len(keep0):N0] = dmax
+        out[k] = a
+    for k, fill in (("rho", c["refd"][0]), ("drhodt", 0.0), ("m", c["refd"][0] * dr ** 3)):
+        a = np.full(N, fill, np.float32)
+        a[:len(keep0)] = c[k][keep0]
+        a[N0:] = c[k][sens]
+        out[k] = a
+    im = np.full(N, -255, np.int32)
+    im[:len(keep0)] = imove[keep0]
+    im[N0:] = 0
+    iset = np.zeros(N, np.uint32)
+    iset[N0:] = 1
+    out.update(imove=im, iset=iset, id=np.arange(N, dtype=np.uint32), N=N, n_set0=N0,
+               n_fluid=len(fluid), n_fluid_global=int((imove == 1).sum()), n_buffer=nbuf,
+               fluid_index=fluid, boundary_index=bound,
+               domain_min=dmin, domain_max=dmax, slab=(y0, y1))
+    return out
+
+
 MPI_PLANE_FIELDS = ("r", "u", "dudt", "rho", "drhodt", "m", "imove")
 
 

@@ -231,6 +231,9 @@ void State::configureTool(ProblemSetup::Tool* tool, const Xml::Node* e, ProblemS
         toolAttr(tool, e, "mask");
         toolAttr(tool, e, "fields");
         toolAttr(tool, e, "processes", "");
+    } else if (type == "mpi-allreduce") { // not a reference tool, see calcserver.hpp
+        toolAttr(tool, e, "in");
+        toolAttr(tool, e, "operation", "min");
     } else if (type == "report_screen") {
         toolAttr(tool, e, "fields");
         toolAttr(tool, e, "bold", "false");

@@ -130,8 +130,21 @@ def run_ours(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     host.set_log_level(3)
     ov = {"iter_midpoint_max": a.maxiter} if a.maxiter > 0 else None
-    sim, case = casegen.spheric2(a.n, overrides=ov, device=local_rank)
-    N = case["N"]
+    if world > 1:
+        # BASELINE config 3: the dam break cut in y slabs, one per GPU, the reference's MPI
+        # example pipeline with migration + halo exchange over NCCL (weak scaling: a.n fluid
+        # particles per GPU); the 128-byte NCCL id travels over torch.distributed
+        uid = [host.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim, case = casegen.spheric2_slab(a.n * world, rank, world, overrides=ov,
+                                          device=local_rank, unique_id=uid[0])
+        N = case["N"] - case["n_buffer"]      # buffer rows are not particles
+        workload = ("3D SPHERIC test 2 dam break, %d y-slabs (examples/3D/spheric_testcase2_dambreak_mpi "
+                    "pipeline: migration + halo over NCCL)" % world)
+    else:
+        sim, case = casegen.spheric2(a.n, overrides=ov, device=local_rank)
+        N = case["N"]
+        workload = WORKLOAD
     actx = _lib.Context.borrow(sim.cuda_ctx(), 3)
 
     def barrier():
@@ -146,6 +159,16 @@ def run_ours(a, rank, world, local_rank):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    N_all = int(sum_over_ranks(N))
 
     for _ in range(a.warmup):
         sim.step(1)
@@ -172,17 +195,21 @@ def run_ours(a, rank, world, local_rank):
     inner += sweeps_done()
     ms = max_over_ranks(actx.elapsed_ms(e0, e1))
     launches = sim.launch_count() - l0
-    value = world * N * a.steps / (ms * 1e-3)
+    value = N_all * a.steps / (ms * 1e-3)
 
     # ---- end to end: host buffers in, host buffers out, every step
     fields = ["r", "u", "dudt", "rho", "drhodt", "m", "imove"]
     outs = ["r", "u", "rho", "p"]
+    if world > 1:   # particles may migrate: the whole state comes back and is fed forward
+        outs += ["dudt", "drhodt", "m", "imove"]
+    NA = case["N"]   # array length on this rank (includes the buffer rows of a slab)
     hin = {}
     for k in fields:
         cur = sim.download(k, np.int32 if k == "imove" else np.float32)
         hin[k] = pinned(actx, cur.shape, cur.dtype)
         hin[k][...] = cur
-    hout = {k: pinned(actx, hin[k].shape if k in hin else (N,), np.float32) for k in outs}
+    hout = {k: pinned(actx, hin[k].shape if k in hin else (NA,),
+                      np.int32 if k == "imove" else np.float32) for k in outs}
     h2d = sum(v.nbytes for v in hin.values())
     d2h = sum(v.nbytes for v in hout.values()) + 4
     barrier()
@@ -192,16 +219,20 @@ def run_ours(a, rank, world, local_rank):
             sim.upload(k, hin[k])
         sim.step(1)
         for k in outs:
-            sim.download(k, np.float32, out=hout[k])
+            sim.download(k, hout[k].dtype, out=hout[k])
         dt_now = float(sim.scalar("dt"))
-        for k in ("r", "u", "rho"):
-            hin[k][...] = hout[k]   # next step starts from this step's result
+        for k in outs:
+            if k in hin:
+                hin[k][...] = hout[k]   # next step starts from this step's result
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    e2e = world * N * a.steps / (e2e_ms * 1e-3)
+    e2e = N_all * a.steps / (e2e_ms * 1e-3)
     clocks.stop_flag = True
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (cfd/Interactions.cl::entry), timed alone
     pk, pk_kind = peaks()
@@ -212,12 +243,12 @@ def run_ours(a, rank, world, local_rank):
                    ("ihoc", np.uint32)):
         n_, eb = sim.array_info(k)
         V[k] = actx.wrap(lib_ptr(sim, k), (n_, eb // 4) if eb > 4 else (n_,), dt_)
-    V["N"] = N
+    V["N"] = NA
     V["n_cells"] = sim.scalar("n_cells", np.uint32, 4)
     d = _lib.Defs()
     hh = float(sim.scalar("h"))
     actx.dims = 3
-    n_pairs = actx.zeros(N, np.uint32)
+    n_pairs = actx.zeros(NA, np.uint32)
     V["n_pairs"] = n_pairs
     actx.launch("aqua/diag.cl", "count_pairs", V)
     pairs = int(n_pairs.get().astype(np.uint64).sum())
@@ -230,13 +261,15 @@ def run_ours(a, rank, world, local_rank):
         actx.launch("cfd/Interactions.cl", "entry", V)
     actx.record(k1)
     kms = actx.elapsed_ms(k0, k1) / reps
-    alg_bytes = 88.0 * N          # Interactions 88 B/particle (3-D, 32-bit idx)
+    alg_bytes = 88.0 * NA         # Interactions 88 B/particle (3-D, 32-bit idx)
     alg_flops = 52.0 * pairs      # 52 flop per true neighbour pair
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "interactions_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        rec = json.load(open(tp))
+        if rec.get("n_particles") == NA:   # ncu capture of this very workload
+            traffic = rec.get("dram_bytes_per_launch")
     roof = {"bound": "hbm", "kernel": "sweep_kernel<PInteractions<3>> (cfd/Interactions.cl::entry)",
             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": traffic,
@@ -254,12 +287,14 @@ def run_ours(a, rank, world, local_rank):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_particles": N, "n_fluid": case["n_fluid"],
+        "config": {"workload": workload, "n_particles": N_all, "n_particles_rank0": N,
+                   "n_fluid": case.get("n_fluid_global", case["n_fluid"]),
                    "hfac": 3.0, "pipeline_tools": len(sim.tools()),
                    "mean_inner_iterations": inner / a.steps,
                    "iter_midpoint_max": a.maxiter or 30,
                    "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
-                   "multi_gpu": "independent replicas" if world > 1 else "single GPU"},
+                   "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv, dt and residual "
+                                 "all-reduced") if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": launches,
@@ -271,6 +306,9 @@ def run_ours(a, rank, world, local_rank):
     }
     print(json.dumps(line), flush=True)
     _ = dt_now
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def lib_ptr(sim, name):
@@ -284,7 +322,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1000000, help="fluid particles (Create.py n)")
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=1000000,
+                    help="fluid particles per GPU (Create.py n)")
     ap.add_argument("--cpu-n", type=int, default=30000, help="fluid particles of the CPU sample")
     ap.add_argument("--maxiter", type=int, default=0, help="pin iter_midpoint_max (0: case default 30)")
     a = ap.parse_args()

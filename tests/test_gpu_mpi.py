@@ -190,3 +190,71 @@ def test_mpi_plane_two_gpus(golden, oracle):
         for k in mpi_common.FIELDS:
             a, b = np.asarray(want[r][k], np.float64), np.asarray(got[r][k], np.float64)
             assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-30), (r, k)
+
+
+def _slab_rank(rank, size, port, q, n_total, steps):
+    import torch.distributed as dist
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from aquagpusph_b200 import casegen, host
+    host.set_log_level(3)
+    uid = [None]
+    if size > 1:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=size)
+        uid = [host.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+    ov = {"iter_midpoint_max": int(os.environ.get("AQ_DIAG_MAXITER", "2"))}
+    sim, c = casegen.spheric2_slab(n_total, rank, size, overrides=ov, device=rank, unique_id=uid[0])
+    sim.step(steps)
+    nf = c["n_fluid"]
+    res = {k: sim.download(k, np.float32, unsorted=True)[:nf] for k in ("r", "u", "rho", "dudt")}
+    res["imove"] = sim.download("imove", np.int32, unsorted=True)[:nf]
+    res["fluid_index"] = c["fluid_index"]
+    res["dt"] = float(sim.scalar("dt"))
+    res["slab"] = c["slab"]
+    res["h"] = c["h"]
+    q.put((rank, res))
+    if size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sim.close()
+
+
+def _run_slabs(size, n_total, steps):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_rank, args=(r, size, port, q, n_total, steps)) for r in range(size)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=900) for _ in range(size))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    return got
+
+
+def test_dam_break_slabs_two_gpus_match_one_gpu():
+    """BASELINE config 3 shape at test size: the 3-D dam break through the reference's MPI
+    example pipeline on 2 GPUs (y slabs, halo + migration over NCCL, global dt, halo
+    refreshed every midpoint sub-iteration: casegen.multi_device_fixes) against the same
+    pipeline on 1 GPU, two steps of two sub-iterations.  Particles farther than the kernel
+    support from the cut never see a remote term: they must be bit-identical; next to the
+    cut the remote terms are added after the local ones (fp32 summation order)."""
+    if not _two_gpus():
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    n_total, steps = 40000, 2
+    one = _run_slabs(1, n_total, steps)[0]
+    two = _run_slabs(2, n_total, steps)
+    assert two[0]["dt"] == two[1]["dt"] == one["dt"], "dt must be global and equal to the 1-GPU value"
+    pos1 = {int(g): k for k, g in enumerate(one["fluid_index"])}
+    for r in range(2):
+        rows = np.array([pos1[int(g)] for g in two[r]["fluid_index"]])
+        assert np.array_equal(two[r]["imove"], one["imove"][rows])
+        far = np.abs(one["r"][rows][:, 1] - two[0]["slab"][1]) > 6.0 * two[r]["h"]
+        assert far.any() and (~far).any()
+        for k, tol in (("r", 1e-6), ("u", 5e-5), ("rho", 2e-5), ("dudt", 5e-5)):
+            a = one[k][rows].astype(np.float64)
+            b = two[r][k].astype(np.float64)
+            err = np.abs(a - b).max() / max(np.abs(a).max(), 1e-30)
+            assert err <= tol, "rank %d field %s: rel err %.3e" % (r, k, err)
+            assert np.array_equal(one[k][rows][far], two[r][k][far]), "rank %d field %s far from the cut" % (r, k)
