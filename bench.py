@@ -130,12 +130,13 @@ def run_ours(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     host.set_log_level(3)
     ov = {"iter_midpoint_max": a.maxiter} if a.maxiter > 0 else None
-    if world > 1:
+    if world > 1 or a.slab_pipeline:
         # BASELINE config 3: the dam break cut in y slabs, one per GPU, the reference's MPI
         # example pipeline with migration + halo exchange over NCCL (weak scaling: a.n fluid
         # particles per GPU); the 128-byte NCCL id travels over torch.distributed
-        uid = [host.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
+        uid = [host.comm_unique_id() if (rank == 0 and world > 1) else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
         sim, case = casegen.spheric2_slab(a.n * world, rank, world, overrides=ov,
                                           device=local_rank, unique_id=uid[0])
         N = case["N"] - case["n_buffer"]      # buffer rows are not particles
@@ -325,6 +326,8 @@ def main():
     ap.add_argument("--particles", "--n", dest="n", type=int, default=1000000,
                     help="fluid particles per GPU (Create.py n)")
     ap.add_argument("--cpu-n", type=int, default=30000, help="fluid particles of the CPU sample")
+    ap.add_argument("--slab-pipeline", action="store_true",
+                    help="run the multi-GPU (slab) pipeline also on one GPU, for scaling studies")
     ap.add_argument("--maxiter", type=int, default=0, help="pin iter_midpoint_max (0: case default 30)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
