@@ -230,6 +230,79 @@ def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
     )
 
 
+def spheric5_dam_break_2d(n=50000, hfac=3.0, seed=None):
+    """BASELINE config 1: the 2-D SPHERIC test 5 dam break over a wet bed, geometry and field
+    initialisation of examples/2D/spheric_testcase5_dambreak/src/Create.py:41-190: reservoir
+    l0 x h0 = 0.38 x 0.15 m (n particles), wetted bed l1 x h1 = 9.55 x 0.038 m, floor and
+    two walls of boundary-integral elements (imove = -3, m = dr), hydrostatic density."""
+    g, cs, courant, refd = 9.81, 45.0, 0.1, 998.0
+    delta, visc_dyn = 10.0, 0.000894
+    h0, h1, l0, l1 = 15e-2, 38e-3, 38e-2, 955e-2
+    H = 2.0 * h0
+    dr = (l0 * h0 / n) ** 0.5
+
+    def column(y_top):
+        k = np.arange(int(np.ceil(y_top / dr)) + 2)
+        y = 0.5 * dr + k * dr
+        return y[y < y_top]
+
+    # reservoir: x = -0.5 dr, -1.5 dr, ... > -l0 ; y = 0.5 dr ... < h0 (x outer, y inner)
+    k = np.arange(int(np.ceil(l0 / dr)) + 2)
+    xr = -0.5 * dr - k * dr
+    xr = xr[xr > -l0]
+    yr = column(h0)
+    X, Y = np.meshgrid(xr, yr, indexing="ij")
+    res = np.stack([X.ravel(), Y.ravel()], 1)
+    xmin = xr[-1]
+    k = np.arange(int(np.ceil(l1 / dr)) + 2)
+    xb = 0.5 * dr + k * dr
+    xb = xb[xb < l1]
+    yb = column(h1)
+    X, Y = np.meshgrid(xb, yb, indexing="ij")
+    bed = np.stack([X.ravel(), Y.ravel()], 1)
+    xmax = xb[-1]
+    fluid = np.concatenate([res, bed])
+    nf = len(fluid)
+    # boundary elements: floor, left wall, right wall
+    k = np.arange(int(np.ceil((l1 - xmin) / dr)) + 2)
+    xf = xmin + k * dr
+    xf = xf[xf < l1]
+    floor = np.stack([xf, np.zeros_like(xf)], 1)
+    yw = column(H)
+    left = np.stack([np.full_like(yw, xmin - 0.5 * dr), yw], 1)
+    right = np.stack([np.full_like(yw, xmax + 0.5 * dr), yw], 1)
+    bnd = np.concatenate([floor, left, right])
+    nrm = np.concatenate([np.tile([0.0, -1.0], (len(floor), 1)), np.tile([-1.0, 0.0], (len(left), 1)),
+                          np.tile([1.0, 0.0], (len(right), 1))])
+    N = nf + len(bnd)
+    r = np.concatenate([fluid, bnd]).astype(np.float32)
+    y = np.concatenate([fluid, bnd])[:, 1]
+    press = refd * g * (h0 - y)
+    press[nf + len(floor):] = np.maximum(0.0, press[nf + len(floor):])
+    rho = (refd + press / cs ** 2).astype(np.float32)
+    m = np.full(N, refd * dr ** 2, np.float32)
+    m[nf:] = dr
+    imove = np.ones(N, np.int32)
+    imove[nf:] = -3
+    normal = np.zeros((N, 2), np.float32)
+    normal[nf:] = nrm
+    u = np.zeros((N, 2), np.float32)
+    if seed is not None:
+        rng = np.random.default_rng(seed)
+        u[:nf] = 0.05 * rng.uniform(-1, 1, (nf, 2))
+    hh = float(np.float32(np.float32(hfac) * np.float32(dr)))
+    return dict(
+        dims=2, N=N, n_fluid=nf, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs, p0=0.0, support=2.0,
+        refd=np.array([refd], np.float32), visc_dyn=np.array([visc_dyn], np.float32),
+        delta=np.array([delta], np.float32), g=np.array([0, -g], np.float32),
+        domain_min=np.array([-1.5 * l0, -0.5 * H], np.float32),
+        domain_max=np.array([1.5 * l1, 2.0 * H], np.float32), courant=courant, dt_Ma=0.1,
+        dt_min=float(np.float32(0.05 * courant * hh / cs)), id=np.arange(N, dtype=np.uint32), r=r,
+        imove=imove, iset=np.zeros(N, np.uint32), normal=normal, tangent=np.zeros((N, 2), np.float32),
+        rho=rho, m=m, u=u, dudt=np.zeros((N, 2), np.float32), drhodt=np.zeros(N, np.float32),
+    )
+
+
 def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None):
     """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way
     examples/3D/spheric_testcase2_dambreak_mpi/src/Create.py:140-200 does it: rank k

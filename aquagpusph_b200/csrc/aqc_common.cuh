@@ -16,8 +16,13 @@ struct aqc_ctx {
     bool own_stream = false;
     uint64_t launches = 0;
     aqc_defs defs{ 3, 1.f, 1.f, 1.f, 2.f, 3.f };
-    float dr_factor = 0.5f;      // __DR_FACTOR__ (BIe/ElasticBounce.cl:31-33)
-    float min_bound_dist = 0.f;  // __MIN_BOUND_DIST__ (BIe/ElasticBounce.cl:34-36)
+    // __DR_FACTOR__ / __MIN_BOUND_DIST__ / __ELASTIC_FACTOR__: script-specific defaults
+    // (BIe/ElasticBounce.cl:31-45: 0.5, 0; Boundary/ElasticBounce.cl:31-58: 1.5, 0.3, 0)
+    // unless the problem defines them (has_* set by aqc_set_define)
+    float dr_factor = 0.5f;
+    float min_bound_dist = 0.f;
+    float elastic_factor = 0.f;
+    bool has_dr_factor = false, has_min_bound_dist = false;
     char err[512] = { 0 };
 
     // link-list scratch (grown on demand, never shrunk)

@@ -857,6 +857,72 @@ int l_mpi_neigh_mask(aqc_ctx* c, size_t, void* const* a)
              aqc_scalar<uint32_t>(a, 5), N, 1, c->defs.SUPPORT * c->defs.H);
 }
 
+// ---- cfd/Boundary/BI/GradP.cl:55-83, InterpolationShepard.cl:48-76, Shepard.cl:173-195 ----
+template <int D>
+__global__ void __launch_bounds__(256)
+k_bi_gradp(const uint32_t* iset, const int* imove, const float* shepard, const void* lap_u,
+           const void* dudt, void* grad_p, const float* visc_dyn, const float* refd, uint32_t N,
+           aqc_f4 g)
+{
+    GID;
+    if (imove[i] != -3)
+        return;
+    float sh = shepard[i];
+    if (sh < 1.0e-6f)
+        sh = 1.f;
+    const uint32_t s = iset[i];
+    const float f = visc_dyn[s] / refd[s];
+    (((f * V<D>::ld(lap_u, i)) / sh + from_f4<D>(g)) - V<D>::ld(dudt, i)).st(grad_p, i);
+}
+int l_bi_gradp(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 9);
+    DISPATCH(c, k_bi_gradp, N, (const uint32_t*)a[0], (const int*)a[1], (const float*)a[2], a[4], a[5],
+             a[6], (const float*)a[7], (const float*)a[8], N, aqc_vec_scalar(a, 10, c->defs.dims));
+}
+
+__global__ void __launch_bounds__(256)
+k_bi_interp_shepard(const uint32_t* iset, const int* imove, const float* shepard, float* rho,
+                    float* p, const float* refd, uint32_t N, float cs, float p0)
+{
+    GID;
+    if (imove[i] != -3)
+        return;
+    float sh = shepard[i];
+    if (sh < 1.0e-6f)
+        sh = 1.f;
+    const float pi = p[i] / sh;
+    p[i] = pi;
+    rho[i] = refd[iset[i]] + (pi - p0) / (cs * cs);
+}
+int l_bi_interp_shepard(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    LAUNCH(c, k_bi_interp_shepard, N, (const uint32_t*)a[0], (const int*)a[1], (const float*)a[2],
+           (float*)a[3], (float*)a[4], (const float*)a[5], N, aqc_scalar<float>(a, 7),
+           aqc_scalar<float>(a, 8));
+    return AQC_OK;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_bi_shepard_apply(const int* imove, const float* shepard, void* grad_p, void* lap_u, float* div_u,
+                   uint32_t N)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const float sh = shepard[i];
+    (V<D>::ld(grad_p, i) / sh).st(grad_p, i);
+    (V<D>::ld(lap_u, i) / sh).st(lap_u, i);
+    div_u[i] = div_u[i] / sh;
+}
+int l_bi_shepard_apply(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    DISPATCH(c, k_bi_shepard_apply, N, (const int*)a[0], (const float*)a[1], a[2], a[3], (float*)a[4], N);
+}
+
 // ---- case-local script of the 3-D dam-break example (wave height probes):
 // examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60 ------------
 __global__ void __launch_bounds__(256)
@@ -929,6 +995,18 @@ aqc_registrar r_mpi_nmask("cfd/MPI/planes.cl", "neigh_mask", 0,
     { IN("imove", "int*"), IN("r", "vec*"), OUT("mpi_neigh_mask", "usize*"),
       SC("mpi_plane_r", "vec"), SC("mpi_plane_n", "vec"), SC("mpi_plane_proc", "unsigned int"),
       SC("N", "usize") }, l_mpi_neigh_mask);
+
+aqc_registrar r_bi_gradp("cfd/Boundary/BI/GradP.cl", "freeslip", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("shepard", "float*"), IN("rho", "float*"),
+      IN("lap_u", "vec*"), IN("dudt", "vec*"), OUT("grad_p", "vec*"), IN("visc_dyn", "float*"),
+      IN("refd", "float*"), SC("N", "usize"), SC("g", "vec") }, l_bi_gradp);
+aqc_registrar r_bi_ishep("cfd/Boundary/BI/InterpolationShepard.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("shepard", "float*"), OUT("rho", "float*"),
+      OUT("p", "float*"), IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"),
+      SC("p0", "float") }, l_bi_interp_shepard);
+aqc_registrar r_bi_shapply("cfd/Boundary/BI/Shepard.cl", "apply", 0,
+    { IN("imove", "int*"), IN("shepard", "float*"), OUT("grad_p", "vec*"), OUT("lap_u", "vec*"),
+      OUT("div_u", "float*"), SC("N", "usize"), SC("cs", "float") }, l_bi_shepard_apply);
 
 aqc_registrar r_h_sensor("h_sensor.cl", "entry", 3,
     { IN("imove", "int*"), IN("r", "vec*"), OUT("h_sensorz", "float*"), SC("N", "uint"),

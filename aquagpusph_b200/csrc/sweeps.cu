@@ -702,6 +702,324 @@ struct PMpiInteractions : PBase {
 };
 
 // ------------------------------------------------------------------------
+// Boundary integrals, cfd/Boundary/BI/*.cl (2-D dam break, BASELINE config 1)
+
+// KernelFunctions/Wendland{2D,3D}.hcl:107-185: analytic Shepard terms of a flat element
+template <int D> __device__ __forceinline__ float kernelS_P(float q);
+template <> __device__ __forceinline__ float kernelS_P<2>(float q)
+{
+    const float wcon = 0.109375f * iM_PI;
+    const float q2 = q * q, q3 = q2 * q;
+    return wcon * (0.285714f * q3 * q2 - 2.5f * q2 * q2 + 8.f * q3 - 10.f * q2 + 8.f);
+}
+template <> __device__ __forceinline__ float kernelS_P<3>(float q)
+{
+    const float wcon = 0.08203125f * iM_PI;
+    const float q2 = q * q, q3 = q2 * q;
+    return wcon * (0.25f * q3 * q2 - 2.142857f * q2 * q2 + 6.666667f * q3 - 8.f * q2 + 5.333333f);
+}
+__device__ __forceinline__ float omega3(float a, float b)
+{
+    const float a2 = a * a, b2 = b * b;
+    const float v = sqrtf((1.f + a2 + b2) / ((1.f + a2) * (1.f + b2)));
+    return acosf(v < 1.f ? v : 1.f) * iM_PI; // acospi(min(.., 1))
+}
+__device__ __forceinline__ float signf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : x); }
+template <int D> __device__ __forceinline__ float kernelS_D(float d, float t, float b, float s);
+template <> __device__ __forceinline__ float kernelS_D<2>(float d, float t, float, float s)
+{
+    const float dr = 0.5f * s;
+    return -(0.5f * iM_PI) * (atanf((t + dr) / d) - atanf((t - dr) / d));
+}
+template <> __device__ __forceinline__ float kernelS_D<3>(float d, float t, float b, float s)
+{
+    const float dr = 0.5f * sqrtf(s);
+    const float t1 = (t - dr) / d, t2 = (t + dr) / d, b1 = (b - dr) / d, b2 = (b + dr) / d;
+    const float st = signf(t1), sb = signf(b1);
+    return -0.25f * (omega3(t2, b2) - st * omega3(t1, b2) - sb * omega3(t2, b1) +
+                     st * sb * omega3(t1, b1));
+}
+
+// BI/Shepard.cl:61-150 (compute)
+template <int D>
+struct PBIShepard : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 4;
+    const void *r, *normal, *tangent, *binormal;
+    const float* m;
+    float* shepard;
+    float H, CONW, inv_dm1; // 1 / (DIMS - 1)
+    struct IState { float x, y, z, s; uint32_t i; bool self; };
+    __device__ bool i_active(int mv) const { return !((mv < -3) || (mv > 1)); }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.s = 1.f; s.i = i; s.self = false;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), n = ldvec<D>(normal, j), t = ldvec<D>(tangent, j),
+                     b = ldvec<D>(binormal, j);
+        const bool ok = __ldg(imove + j) == -3;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, __ldg(m + j));
+        o[1] = make_float4(n.x, n.y, n.z, __uint_as_float(j));
+        o[2] = make_float4(t.x, t.y, t.z, 0.f);
+        o[3] = make_float4(b.x, b.y, b.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride], T = row[2 * stride], B = row[3 * stride];
+        if (__float_as_uint(Nn.w) == s.i) { // a boundary element meeting itself
+            if (!s.self) {
+                s.self = true;
+                s.s -= 0.5f;
+            }
+            return;
+        }
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = (D == 3) ? A.z - s.z : 0.f;
+        const float q = sqrtf(dist2<D>(dx, dy, dz)) / H;
+        float rn = dx * Nn.x + dy * Nn.y, rt = dx * T.x + dy * T.y, rb = dx * B.x + dy * B.y;
+        if constexpr (D == 3) {
+            rn += dz * Nn.z; rt += dz * T.z; rb += dz * B.z;
+        }
+        rt = fabsf(rt);
+        rb = fabsf(rb);
+        const float area = A.w;
+        if ((rn > -1e-8f * H) && (rn < 1e-8f * H)) { // lying on the boundary
+            if (!s.self) {
+                const float dr = 0.55f * ((D == 3) ? powf(area, inv_dm1) : area);
+                if ((rt <= dr) && (rb <= dr)) {
+                    s.self = true;
+                    s.s -= 0.5f;
+                }
+            }
+            return;
+        }
+        s.s += rn * CONW * kernelS_P<D>(q) * area + kernelS_D<D>(fabsf(rn), rt, rb, area);
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { shepard[i] = s.s; }
+};
+
+// BI/LapU.cl:58-123 (freeslip): boundary elements gather the fluid's velocity Laplacian
+template <int D>
+struct PBILapU : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *u;
+    const float *rho, *m;
+    void* lap_u;
+    float cF, eps2;
+    struct IState { float x, y, z, ux, uy, uz, lx, ly, lz; };
+    __device__ bool i_active(int mv) const { return mv == -3; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.lx = s.ly = s.lz = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == 1;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z,
+                           cF * Wend<D>::CLEARY * __ldg(m + j) / __ldg(rho + j));
+        o[1] = make_float4(b.x, b.y, b.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float t = 2.f - q_of(d2, invH);
+        float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
+        if constexpr (D == 3)
+            udr += (B.z - s.uz) * dz;
+        const float b = udr * ((t * t) * (t * A.w)) * rcp_fast(d2 + eps2);
+        s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { stvec_xyz<D>(lap_u, i, s.lx, s.ly, s.lz); }
+};
+
+// BI/Interpolation.cl:54-107: pressure of the boundary elements from the fluid,
+// corrected with the element's own pressure gradient
+template <int D>
+struct PBIInterpolation : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *grad_p;
+    const float *m, *rho;
+    float* p;
+    float cW;
+    struct IState { float x, y, z, gx, gy, gz, p; };
+    __device__ bool i_active(int mv) const { return mv == -3; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), g = ldvec<D>(grad_p, i);
+        const float ri = __ldg(rho + i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.gx = ri * g.x; s.gy = ri * g.y; s.gz = ri * g.z;
+        s.p = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        // p is read for fluid j and written for boundary i: disjoint rows
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = __ldg(imove + j) == 1;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j) / __ldg(rho + j));
+        o[1] = make_float4(ok ? p[j] : 0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0];
+        const float pj = row[stride].x;
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float q = q_of(dist2<D>(dx, dy, dz), invH);
+        const float t = 2.f - q, t2 = t * t;
+        const float w = (1.f + 2.f * q) * (t2 * t2) * A.w;
+        float gr = s.gx * dx + s.gy * dy;
+        if constexpr (D == 3)
+            gr += s.gz * dz;
+        s.p += (pj - gr) * w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { p[i] = s.p; }
+};
+
+// BI/Interactions.cl:51-133: fluid i against boundary elements j; starts from the values the
+// fluid-fluid sweep left in grad_p / div_u (:92-93)
+template <int D>
+struct PBIInteractions : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 3;
+    const void *r, *normal, *u;
+    const float *rho, *m, *p;
+    void* grad_p;
+    float* div_u;
+    float cW;
+    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, du; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.p = __ldg(p + i);
+        s.gx = s.gy = s.gz = s.du = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), n = ldvec<D>(normal, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == -3;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j));
+        o[1] = make_float4(n.x, n.y, n.z, __ldg(p + j));
+        o[2] = make_float4(b.x, b.y, b.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride], U = row[2 * stride];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        const float w = (1.f + 2.f * q) * (t2 * t2) * A.w; // kernelW*CONW*area_j
+        const float a = (s.p + Nn.w) * w;
+        float dun = (U.x - s.ux) * Nn.x + (U.y - s.uy) * Nn.y;
+        if constexpr (D == 3)
+            dun += (U.z - s.uz) * Nn.z;
+        s.gx += a * Nn.x; s.gy += a * Nn.y; s.gz += a * Nn.z;
+        s.du += dun * w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float4 g0 = ldvec_rw<D>(grad_p, i);
+        stvec_xyz<D>(grad_p, i, g0.x + s.gx * ir, g0.y + s.gy * ir, g0.z + s.gz * ir);
+        div_u[i] += rho_i * s.du;
+    }
+};
+
+// cfd/Boundary/ElasticBounce.cl:77-148 -- order dependent (u_i, dudt_i change inside the loop)
+template <int D>
+struct PElasticBounce : PBase {
+    static constexpr bool SPHERE = false;
+    static constexpr int DIMS = D, NJ4 = 4;
+    const void *r, *normal;
+    void *u, *dudt;
+    float dt, R2, min_dist, one_plus_e;
+    struct IState { float x, y, z, ux, uy, uz, ax, ay, az; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec_rw<D>(u, i), c = ldvec_rw<D>(dudt, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.ax = c.x; s.ay = c.y; s.az = c.z;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        // u / dudt are read for boundary j and written for fluid i: disjoint rows
+        const float4 a = ldvec<D>(r, j), n = ldvec<D>(normal, j), b = ldvec_rw<D>(u, j),
+                     c = ldvec_rw<D>(dudt, j);
+        const int mv = __ldg(imove + j);
+        o[0] = make_float4(a.x, a.y, a.z, (mv == -2 || mv == -3) ? 1.f : -1.f);
+        o[1] = make_float4(n.x, n.y, n.z, 0.f);
+        o[2] = make_float4(b.x, b.y, b.z, 0.f);
+        o[3] = make_float4(c.x, c.y, c.z, 0.f);
+    }
+    __device__ bool test(const IState&, const float4& A) const { return A.w >= 0.f; }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride], U = row[2 * stride], Acc = row[3 * stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = (D == 3) ? A.z - s.z : 0.f;
+        float r0 = dx * Nn.x + dy * Nn.y;
+        if constexpr (D == 3)
+            r0 += dz * Nn.z;
+        if (r0 < 0.f)
+            return;
+        const float tx = dx - r0 * Nn.x, ty = dy - r0 * Nn.y, tz = dz - r0 * Nn.z;
+        float rt2 = tx * tx + ty * ty;
+        if constexpr (D == 3)
+            rt2 += tz * tz;
+        if (rt2 >= R2)
+            return;
+        float un = (s.ux - U.x) * Nn.x + (s.uy - U.y) * Nn.y;
+        float an = (s.ax - Acc.x) * Nn.x + (s.ay - Acc.y) * Nn.y;
+        if constexpr (D == 3) {
+            un += (s.uz - U.z) * Nn.z;
+            an += (s.az - Acc.z) * Nn.z;
+        }
+        const float dist = dt * un + 0.5f * dt * dt * an;
+        if (dist < 0.f)
+            return;
+        if (r0 - dist <= min_dist) {
+            const float ka = one_plus_e * an, ku = one_plus_e * un;
+            s.ax -= ka * Nn.x; s.ay -= ka * Nn.y;
+            s.ux -= ku * Nn.x; s.uy -= ku * Nn.y;
+            if constexpr (D == 3) {
+                s.az -= ka * Nn.z;
+                s.uz -= ku * Nn.z;
+            }
+        }
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        stvec_xyz<D>(u, i, s.ux, s.uy, s.uz);
+        stvec_xyz<D>(dudt, i, s.ax, s.ay, s.az);
+    }
+};
+
+// ------------------------------------------------------------------------
 // Diagnostic (not a reference script): number of fluid neighbours within the kernel
 // support of every fluid particle, i.e. the pair count the roofline figures use.
 template <int D>
@@ -931,6 +1249,68 @@ int l_neighs(aqc_ctx* ctx, size_t, void* const* a)
     return AQC_OK;
 }
 
+template <int D> int run_bi_shepard(aqc_ctx* ctx, void* const* a)
+{
+    PBIShepard<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.normal = a[2]; p.tangent = a[3]; p.binormal = a[4]; p.m = (const float*)a[5];
+    p.shepard = (float*)a[6];
+    p.H = ctx->defs.H; p.CONW = ctx->defs.CONW; p.inv_dm1 = 1.f / (ctx->defs.DIMS - 1.f);
+    return launch_sweep(ctx, p, make_ll(a, 8, aqc_scalar<uint32_t>(a, 7)));
+}
+int l_bi_shepard(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_shepard, c, a); }
+template <int D> int run_bi_lapu(aqc_ctx* ctx, void* const* a)
+{
+    PBILapU<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.m = (const float*)a[4]; p.lap_u = a[5];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 6)));
+}
+int l_bi_lapu(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_lapu, c, a); }
+template <int D> int run_bi_interp(aqc_ctx* ctx, void* const* a)
+{
+    PBIInterpolation<D> p;
+    set_base(p, ctx, a[1]);
+    p.r = a[2]; p.m = (const float*)a[3]; p.rho = (const float*)a[4]; p.grad_p = a[5];
+    p.p = (float*)a[6];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 9, aqc_scalar<uint32_t>(a, 8)));
+}
+int l_bi_interp(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_interp, c, a); }
+template <int D> int run_bi_inter(aqc_ctx* ctx, void* const* a)
+{
+    // (iset, imove, r, normal, u, rho, m, p, refd, grad_p, div_u, icell, ihoc, N, n_cells, g)
+    PBIInteractions<D> p;
+    set_base(p, ctx, a[1]);
+    p.r = a[2]; p.normal = a[3]; p.u = a[4]; p.rho = (const float*)a[5]; p.m = (const float*)a[6];
+    p.p = (const float*)a[7]; p.grad_p = a[9]; p.div_u = (float*)a[10];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    LLParams ll;
+    ll.icell_i = ll.icell = (const uint32_t*)a[11];
+    ll.ihoc = (const uint32_t*)a[12];
+    const aqc_u4 nc = aqc_scalar<aqc_u4>(a, 14);
+    ll.nx = nc.x; ll.ny = nc.y; ll.nz = nc.z; ll.nw = nc.w;
+    ll.N = aqc_scalar<uint32_t>(a, 13);
+    return launch_sweep(ctx, p, ll);
+}
+int l_bi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_inter, c, a); }
+template <int D> int run_elastic_bounce(aqc_ctx* ctx, void* const* a)
+{
+    PElasticBounce<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.normal = a[2]; p.u = a[3]; p.dudt = a[4];
+    const float dr = aqc_scalar<float>(a, 6);
+    p.dt = aqc_scalar<float>(a, 7);
+    const float R = (ctx->has_dr_factor ? ctx->dr_factor : 1.5f) * dr; // ElasticBounce.cl:31-37
+    p.R2 = R * R;
+    p.min_dist = (ctx->has_min_bound_dist ? ctx->min_bound_dist : 0.3f) * dr;
+    p.one_plus_e = 1.f + ctx->elastic_factor;
+    return launch_sweep(ctx, p, make_ll(a, 8, aqc_scalar<uint32_t>(a, 5)));
+}
+int l_elastic_bounce(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_elastic_bounce, c, a); }
+
 // LINKLIST_REMOTE_PARAMS = icell, mpi_icell, mpi_ihoc, n_cells (types.h:117-122)
 LLParams make_ll_remote(void* const* a, int k_icell, size_t N)
 {
@@ -1011,6 +1391,27 @@ aqc_registrar r_bie_eb("cfd/Boundary/BIe/ElasticBounce.cl", "entry", 0,
 aqc_registrar r_bie_pst("cfd/Boundary/BIe/PST.cl", "entry", 0,
     { IN("imove", "int*"), OUT("r", "vec*"), IN("normal", "vec*"), IN("m", "float*"),
       IN("rho", "float*"), SC("N", "usize"), LL_ARGS }, l_bie_pst);
+aqc_registrar r_bi_shep("cfd/Boundary/BI/Shepard.cl", "compute", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), IN("tangent", "vec*"),
+      IN("binormal", "vec*"), IN("m", "float*"), OUT("shepard", "float*"), SC("N", "usize"),
+      LL_ARGS }, l_bi_shepard);
+aqc_registrar r_bi_lapu("cfd/Boundary/BI/LapU.cl", "freeslip", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      OUT("lap_u", "vec*"), SC("N", "usize"), LL_ARGS }, l_bi_lapu);
+aqc_registrar r_bi_interp("cfd/Boundary/BI/Interpolation.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("m", "float*"),
+      IN("rho", "float*"), IN("grad_p", "vec*"), OUT("p", "float*"), IN("refd", "float*"),
+      SC("N", "usize"), LL_ARGS }, l_bi_interp);
+aqc_registrar r_bi_inter("cfd/Boundary/BI/Interactions.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"),
+      IN("u", "vec*"), IN("rho", "float*"), IN("m", "float*"), IN("p", "float*"),
+      IN("refd", "float*"), OUT("grad_p", "vec*"), OUT("div_u", "float*"), OUT("icell", "uint*"),
+      OUT("ihoc", "uint*"), SC("N", "usize"), SC("n_cells", "uivec4"), SC("g", "vec") },
+    l_bi_inter);
+aqc_registrar r_elastic("cfd/Boundary/ElasticBounce.cl", "entry", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), OUT("u", "vec*"),
+      OUT("dudt", "vec*"), SC("N", "usize"), SC("dr", "float"), SC("dt", "float"), LL_ARGS },
+    l_elastic_bounce);
 #define LL_REMOTE_ARGS IN("icell", "usize*"), IN("mpi_icell", "usize*"), IN("mpi_ihoc", "usize*"), SC("n_cells", "svec4")
 aqc_registrar r_mpi_gamma("cfd/MPI.cl", "gamma", 0,
     { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),

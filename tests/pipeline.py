@@ -274,6 +274,38 @@ def named_sweeps(c, dt=1e-4):
     return o
 
 
+def named_bi_sequence(c, dt=2e-4):
+    """The boundary-integral (BI) part of the 2-D dam-break pipeline (BASELINE config 1,
+    examples/2D/spheric_testcase5_dambreak: tools "cfd Shepard" ... "cfd elastic bounce"),
+    by script name, on a CudaState or a RefState."""
+    s = c.s
+    o = {}
+    c.run("basic/EOS.cl")
+    c.run("basic/Binormal.cl")
+    c.run("cfd/Boundary/BI/Shepard.cl", "compute")
+    o["shepard"] = c.get("shepard")
+    c.run("cfd/Interactions.cl")
+    c.run("cfd/Boundary/BI/LapU.cl", "freeslip")
+    o["lap_u_bi"] = c.get("lap_u")
+    c.run("cfd/Boundary/BI/GradP.cl", "freeslip")
+    o["grad_p_bi"] = c.get("grad_p")
+    c.run("cfd/Boundary/BI/Interpolation.cl")
+    o["p_interp"] = c.get("p")
+    c.run("cfd/Boundary/BI/InterpolationShepard.cl")
+    o["p_bound"], o["rho_bound"] = c.get("p"), c.get("rho")
+    c.run("cfd/Boundary/BI/Interactions.cl")
+    o["grad_p_sum"], o["div_u_sum"] = c.get("grad_p"), c.get("div_u")
+    c.run("cfd/Boundary/BI/Shepard.cl", "apply")
+    o["grad_p"], o["lap_u"], o["div_u"] = c.get("grad_p"), c.get("lap_u"), c.get("div_u")
+    c.zero("dudt")
+    c.zero("drhodt")
+    c.run("cfd/Rates.cl")
+    o["dudt_pre"] = c.get("dudt")
+    c.run("cfd/Boundary/ElasticBounce.cl", dr=s["dr"], dt=float(dt) * 50)
+    o["u_bounce"], o["dudt_bounce"] = c.get("u"), c.get("dudt")
+    return o
+
+
 # tolerance per output: |a - b| <= atol_rel * max|b| + rtol * |b|
 EXACT = {"n_neighs", "binormal", "tangent", "dt_var", "dt"}
 ORDER_DEP = {"dudt", "force_elastic", "r_pst", "residual"}
