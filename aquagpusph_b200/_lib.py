@@ -25,7 +25,8 @@ SYMBOLS = [
     "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
-    "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host",
+    "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
+    "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -99,6 +100,8 @@ def lib():
         getattr(L, n).argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     for n in ("aqc_event_destroy", "aqc_event_record", "aqc_event_sync"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_fused_lookup.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.aqc_launch_fused.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]
     L.aqc_comm_unique_id.argtypes = [C.c_void_p]
     L.aqc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.aqc_comm_destroy.argtypes = [C.c_void_p]
@@ -362,6 +365,29 @@ class Context:
         if n is None:
             n = int(variables["N"])
         self._chk(L.aqc_launch(self.h, kid, int(n), argv, na))
+
+    def launch_fused(self, members, variables):
+        """Fused launch of [(script, entry), ...] (pipeline order), arguments by name."""
+        L = lib()
+        ids = [self.lookup(s_, e_) for s_, e_ in members]
+        arr = (C.c_int * len(ids))(*ids)
+        fid = L.aqc_fused_lookup(arr, len(ids), self.dims)
+        if fid < 0:
+            raise AquaError("no fused kernel for %s" % (members,))
+        argv, keep = [], []
+        for kid in ids:
+            na = L.aqc_kernel_nargs(kid)
+            info = L.aqc_kernel_args(kid)
+            for k in range(na):
+                v = variables[info[k].name.decode()]
+                if info[k].kind == ARG_SCALAR:
+                    b = C.create_string_buffer(_scalar_bytes(v, info[k].type.decode(), self.dims))
+                    keep.append(b)
+                    argv.append(C.cast(b, C.c_void_p))
+                else:
+                    argv.append(C.c_void_p(v.ptr))
+        a = (C.c_void_p * len(argv))(*argv)
+        self._chk(L.aqc_launch_fused(self.h, fid, a, len(argv)))
 
     # -- events
     def event(self):

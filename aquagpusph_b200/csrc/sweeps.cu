@@ -1020,6 +1020,113 @@ struct PElasticBounce : PBase {
 };
 
 // ------------------------------------------------------------------------
+// FUSED fluid sweep.  The reference runs cfd/Shepard, cfd/Interactions, deltaSPH::full
+// and deltaSPH::lapp as four separate neighbour sweeps over the SAME (i, j) pairs
+// (j fluid), each re-reading r, imove, icell and recomputing |r_ij|, q and the
+// kernel factors (SURVEY 2.4 "fusion targets").  Here one pass filters the
+// candidates once and evaluates every member's pair term from the shared
+// geometry.  Each member's arithmetic is exactly that of its stand-alone policy
+// (same expressions, same order), so the outputs are bit-identical to running the
+// members one after the other.  The host asks for a fusion with
+// aqc_fused_lookup(); members: Interactions always, Shepard / full / lapp optional.
+template <int D, bool SHEP, bool FULL, bool LAPP>
+struct PFusedFluid : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = SHEP ? 3 : 2;
+    const void *r, *u;
+    const float *rho, *m, *p;
+    void *grad_p, *lap_u, *lap_p_corr;
+    float *div_u, *shepard, *lap_p;
+    float cF, cW, eps2;
+    struct IState {
+        float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du, sh, cx, cy, cz, lp;
+        bool fluid;
+    };
+    // union of the members' i sets: Shepard also serves sensors and boundary elements
+    __device__ bool i_active(int mv) const
+    {
+        return SHEP ? !((mv < -3) || ((mv > 0) && (mv != 1))) : (mv == 1);
+    }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.fluid = !SHEP || (__ldg(imove + i) == 1);
+        s.ux = s.uy = s.uz = s.p = 0.f;
+        if (s.fluid) {
+            const float4 b = ldvec<D>(u, i);
+            s.ux = b.x; s.uy = b.y; s.uz = b.z;
+            s.p = __ldg(p + i);
+        }
+        s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = s.sh = s.cx = s.cy = s.cz = s.lp = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == 1;
+        const float mj = __ldg(m + j), rj = __ldg(rho + j);
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * mj / rj);
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(p + j));
+        if constexpr (SHEP)
+            o[2] = make_float4(cW * mj / rj, 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float q = q_of(d2, invH);
+        const float t = 2.f - q;
+        if constexpr (SHEP) {
+            const float t2 = t * t;
+            s.sh += (1.f + 2.f * q) * (t2 * t2) * row[2 * stride].x;
+            if (!s.fluid)
+                return;
+        }
+        const float4 B = row[stride];
+        const float fr = (t * t) * (t * A.w); // kernelF(q)*CONF*m_j / rho_j
+        float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
+        if constexpr (D == 3)
+            udr += (B.z - s.uz) * dz;
+        const float a = (s.p + B.w) * fr;
+        const float b0 = udr * fr;
+        const float b = b0 * rcp_fast(d2 + eps2);
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+        s.du += b0;
+        if constexpr (FULL || LAPP) {
+            const float c = (B.w - s.p) * fr;
+            if constexpr (FULL) {
+                s.cx += c * dx; s.cy += c * dy; s.cz += c * dz;
+            }
+            if constexpr (LAPP)
+                s.lp += c;
+        }
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if constexpr (SHEP)
+            shepard[i] = s.sh;
+        if (!s.fluid)
+            return;
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float cl = Wend<D>::CLEARY * ir;
+        stvec_xyz<D>(grad_p, i, s.gx * ir, s.gy * ir, s.gz * ir);
+        stvec_xyz<D>(lap_u, i, s.lx * cl, s.ly * cl, s.lz * cl);
+        div_u[i] = s.du * rho_i;
+        if constexpr (FULL)
+            stvec_xyz<D>(lap_p_corr, i, s.cx, s.cy, s.cz);
+        if constexpr (LAPP)
+            lap_p[i] = s.lp;
+    }
+};
+
+// ------------------------------------------------------------------------
 // Diagnostic (not a reference script): number of fluid neighbours within the kernel
 // support of every fluid particle, i.e. the pair count the roofline figures use.
 template <int D>
@@ -1346,6 +1453,64 @@ template <int D> int run_mpi_inter(aqc_ctx* ctx, void* const* a)
 }
 int l_mpi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_inter, c, a); }
 
+// ---- fused launches -----------------------------------------------------------
+// Members are given in pipeline order; the argument list of a fused launch is the
+// concatenation of the members' own argument lists (same names, same order).
+struct FusedEntry {
+    std::vector<const char*> members; // "script::entry"
+    int (*fn)(aqc_ctx*, void* const*);
+};
+template <int D, bool SHEP, bool FULL, bool LAPP> int run_fused_fluid(aqc_ctx* ctx, void* const* a)
+{
+    // [Shepard: imove r rho m shepard N icell ihoc n_cells (9)]
+    // Interactions: imove r u rho m p grad_p lap_u div_u N icell ihoc n_cells (13)
+    // [full: imove r rho m p lap_p_corr N icell ihoc n_cells (10)] [lapp: ... lap_p ... (10)]
+    int k = 0;
+    PFusedFluid<D, SHEP, FULL, LAPP> p;
+    p.shepard = nullptr; p.lap_p_corr = nullptr; p.lap_p = nullptr;
+    if (SHEP) {
+        p.shepard = (float*)a[k + 4];
+        k += 9;
+    }
+    void* const* ia = a + k;
+    set_base(p, ctx, ia[0]);
+    p.r = ia[1]; p.u = ia[2]; p.rho = (const float*)ia[3]; p.m = (const float*)ia[4];
+    p.p = (const float*)ia[5]; p.grad_p = ia[6]; p.lap_u = ia[7]; p.div_u = (float*)ia[8];
+    const uint32_t N = aqc_scalar<uint32_t>(ia, 9);
+    const LLParams ll = make_ll(ia, 10, N);
+    k += 13;
+    if (FULL) {
+        p.lap_p_corr = a[k + 5];
+        k += 10;
+    }
+    if (LAPP) {
+        p.lap_p = (float*)a[k + 5];
+        k += 10;
+    }
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, ll);
+}
+template <bool SHEP, bool FULL, bool LAPP> int l_fused_fluid(aqc_ctx* c, void* const* a)
+{
+    return c->defs.dims == 3 ? run_fused_fluid<3, SHEP, FULL, LAPP>(c, a)
+                             : run_fused_fluid<2, SHEP, FULL, LAPP>(c, a);
+}
+#define K_SHEP "cfd/Shepard.cl::entry"
+#define K_INTER "cfd/Interactions.cl::entry"
+#define K_FULL "cfd/deltaSPH.cl::full"
+#define K_LAPP "cfd/deltaSPH.cl::lapp"
+const std::vector<FusedEntry>& fused_table()
+{
+    static const std::vector<FusedEntry> t = {
+        { { K_SHEP, K_INTER, K_FULL, K_LAPP }, l_fused_fluid<true, true, true> },
+        { { K_SHEP, K_INTER }, l_fused_fluid<true, false, false> },
+        { { K_INTER, K_FULL, K_LAPP }, l_fused_fluid<false, true, true> },
+    };
+    return t;
+}
+
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
@@ -1439,3 +1604,82 @@ aqc_registrar r_neighs("basic/neighs.cl", "entry", 0,
       SC("N", "usize"), LL_ARGS }, l_neighs);
 
 } // namespace
+
+extern "C" int aqc_fused_lookup(const int* kernel_ids, int n, int dims)
+{
+    (void)dims;
+    if (!kernel_ids || n < 2)
+        return AQC_ERR_NOKERNEL;
+    const auto& tab = fused_table();
+    for (size_t f = 0; f < tab.size(); f++) {
+        if ((int)tab[f].members.size() != n)
+            continue;
+        bool ok = true;
+        for (int k = 0; k < n && ok; k++) {
+            const char* nm = aqc_kernel_name(kernel_ids[k]);
+            ok = nm && !strcmp(nm, tab[f].members[k]);
+        }
+        if (ok)
+            return (int)f;
+    }
+    return AQC_ERR_NOKERNEL;
+}
+
+extern "C" int aqc_fused_prefix(const int* kernel_ids, int n, int dims)
+{
+    (void)dims;
+    if (!kernel_ids || n < 1)
+        return 0;
+    for (auto& e : fused_table()) {
+        if ((int)e.members.size() < n)
+            continue;
+        bool ok = true;
+        for (int k = 0; k < n && ok; k++) {
+            const char* nm = aqc_kernel_name(kernel_ids[k]);
+            ok = nm && !strcmp(nm, e.members[k]);
+        }
+        if (ok)
+            return 1;
+    }
+    return 0;
+}
+
+// every fused fluid sweep reads, apart from the positions, only rows of fluid particles
+extern "C" int aqc_fused_read_rows(int fused_id)
+{
+    (void)fused_id;
+    return AQC_ROWS_FLUID;
+}
+
+extern "C" int aqc_kernel_write_rows(int kernel_id)
+{
+    const char* nm = aqc_kernel_name(kernel_id);
+    if (!nm)
+        return AQC_ROWS_ANY;
+    // cfd/Sensors.cl:57-130 and SensorsRenormalization.cl:42-67 return unless imove == 0
+    if (!strcmp(nm, "cfd/Sensors.cl::entry") || !strcmp(nm, "cfd/SensorsRenormalization.cl::entry"))
+        return AQC_ROWS_SENSOR;
+    return AQC_ROWS_ANY;
+}
+
+extern "C" int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    const auto& tab = fused_table();
+    if (fused_id < 0 || fused_id >= (int)tab.size())
+        return aqc_fail(ctx, AQC_ERR_NOKERNEL, "aqc_launch_fused: bad id %d", fused_id);
+    int want = 0;
+    for (auto nm : tab[fused_id].members) {
+        const char* sep = strstr(nm, "::");
+        const std::string script(nm, sep - nm);
+        want += aqc_kernel_nargs(aqc_kernel_lookup(script.c_str(), sep + 2, ctx->defs.dims));
+    }
+    if (nargs != want)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: expected %d args, got %d", want, nargs);
+    for (int k = 0; k < nargs; k++)
+        if (!args[k])
+            return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: argument %d is NULL", k);
+    return tab[fused_id].fn(ctx, args);
+}
+

@@ -18,6 +18,7 @@ SYMBOLS = [
     "aqh_comm_unique_id", "aqh_comm_init",
     "aqh_write_resolved", "aqh_n_tools", "aqh_tool_name", "aqh_tool_type", "aqh_tool_elapsed_ms",
     "aqh_tool_used_times", "aqh_step", "aqh_run", "aqh_sync", "aqh_launch_count", "aqh_cuda_ctx",
+    "aqh_fused_groups",
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr",
 ]
@@ -58,6 +59,8 @@ def lib():
     L.aqh_sync.argtypes = [C.c_void_p]
     L.aqh_launch_count.argtypes = [C.c_void_p]
     L.aqh_launch_count.restype = C.c_uint64
+    L.aqh_fused_groups.argtypes = [C.c_void_p]
+    L.aqh_fused_groups.restype = C.c_uint
     L.aqh_cuda_ctx.argtypes = [C.c_void_p]
     L.aqh_cuda_ctx.restype = C.c_void_p
     L.aqh_eval.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
@@ -152,6 +155,9 @@ class Simulation:
 
     def launch_count(self):
         return int(lib().aqh_launch_count(self.h))
+
+    def fused_groups(self):
+        return int(lib().aqh_fused_groups(self.h))
 
     def cuda_ctx(self):
         return lib().aqh_cuda_ctx(self.h)

@@ -85,8 +85,26 @@ void Kernel::setup()
     }
 }
 
+bool Kernel::dependencies(std::vector<Variable*>& in, std::vector<Variable*>& out) const
+{
+    // Kernel.cpp:464-556: const / non-global arguments are inputs, the rest outputs
+    for (size_t k = 0; k < _vars.size(); k++)
+        (_kinds[k] == AQC_ARG_ARRAY_OUT ? out : in).push_back(_vars[k]);
+    return true;
+}
+
 void Kernel::_execute()
 {
+    if (_leader)
+        return; // computed by the fused launch of the group's leader
+    if (_fused_id >= 0) {
+        std::vector<void*> args;
+        for (auto k : _group)
+            for (auto v : k->_vars)
+                args.push_back(v->isArray() ? v->dptr() : v->get());
+        check(aqc_launch_fused(_C->ctx(), _fused_id, args.data(), (int)args.size()));
+        return;
+    }
     // global size: n="" -> longest array argument (Kernel.cpp:558-594)
     size_t N = 0;
     if (_n.empty()) {
@@ -944,6 +962,109 @@ void CalcServer::setup()
         }
     for (auto& t : _tools)
         t->setup();
+    planFusion();
+}
+
+// Sweep fusion planner.  A group {M0 < M1 < ...} of kernel tools is executed by ONE fused
+// launch at M0's position when, for every member M and every tool T of the pipeline that
+// sits between M0 and M (other members included):
+//   * T's dependencies are known (kernel, copy; anything else ends the search),
+//   * T does not write what M reads -- unless T is a kernel that only writes rows of a
+//     particle class the fused sweep never reads (aqc_kernel_write_rows vs
+//     aqc_fused_read_rows: cfd/Sensors.cl writes u, rho, p of the sensors only),
+//   * T neither reads nor writes what M writes,
+// and no member reads or writes another member's output.  Otherwise the tools run
+// one by one exactly as listed.
+void CalcServer::planFusion()
+{
+    if (getenv("AQUA_NO_FUSION"))
+        return;
+    auto has = [](const std::vector<Variable*>& v, Variable* x) {
+        return std::find(v.begin(), v.end(), x) != v.end();
+    };
+    auto overlap = [&](const std::vector<Variable*>& a, const std::vector<Variable*>& b) {
+        for (auto x : a)
+            if (has(b, x))
+                return true;
+        return false;
+    };
+    for (size_t i = 0; i < _tools.size(); i++) {
+        Kernel* lead = dynamic_cast<Kernel*>(_tools[i].get());
+        if (!lead || lead->fused())
+            continue;
+        std::vector<Kernel*> members{ lead };
+        std::vector<size_t> pos{ i };
+        std::vector<int> ids{ lead->kernel_id() };
+        if (aqc_fused_prefix(ids.data(), 1, dims()) <= 0)
+            continue;
+        int best_fid = -1;
+        size_t best_n = 0;
+        for (size_t j = i + 1; j < _tools.size() && j < i + 16; j++) {
+            Tool* t = _tools[j].get();
+            if (t->scope_modifier() != 0)
+                break;
+            Kernel* k = dynamic_cast<Kernel*>(t);
+            if (k && !k->fused()) {
+                ids.push_back(k->kernel_id());
+                if (aqc_fused_prefix(ids.data(), (int)ids.size(), dims()) > 0) {
+                    members.push_back(k);
+                    pos.push_back(j);
+                    const int fid = aqc_fused_lookup(ids.data(), (int)ids.size(), dims());
+                    if (fid >= 0) {
+                        best_fid = fid;
+                        best_n = members.size();
+                    }
+                    continue;
+                }
+                ids.pop_back();
+            }
+            std::vector<Variable*> in, out;
+            if (!t->dependencies(in, out))
+                break;
+        }
+        if (best_fid < 0)
+            continue;
+        members.resize(best_n);
+        pos.resize(best_n);
+        // safety
+        bool ok = true;
+        const unsigned read_rows = (unsigned)aqc_fused_read_rows(best_fid);
+        std::vector<std::vector<Variable*>> min(best_n), mout(best_n);
+        for (size_t m = 0; m < best_n; m++)
+            members[m]->dependencies(min[m], mout[m]);
+        for (size_t m = 0; m < best_n && ok; m++) {
+            for (size_t j = pos[0] + 1; j < pos[m] && ok; j++) {
+                Tool* t = _tools[j].get();
+                std::vector<Variable*> tin, tout;
+                t->dependencies(tin, tout);
+                const bool is_member = std::find(pos.begin(), pos.end(), j) != pos.end();
+                if (is_member) {
+                    // an earlier member must not produce what M consumes, nor share outputs
+                    if (overlap(tout, min[m]) || overlap(tout, mout[m]) || overlap(tin, mout[m]))
+                        ok = false;
+                    continue;
+                }
+                Kernel* tk = dynamic_cast<Kernel*>(t);
+                const unsigned wr = tk ? (unsigned)aqc_kernel_write_rows(tk->kernel_id()) : 7u;
+                if (overlap(tout, min[m]) && (wr & read_rows))
+                    ok = false;
+                if (overlap(tin, mout[m]) || overlap(tout, mout[m]))
+                    ok = false;
+            }
+        }
+        if (!ok)
+            continue;
+        lead->fuse_lead(best_fid, members);
+        for (size_t m = 1; m < best_n; m++)
+            members[m]->fuse_follow(lead);
+        _fused_groups++;
+        if (logLevel() <= 1) {
+            std::string msg = "Fused sweep:";
+            for (auto k : members)
+                msg += " \"" + k->name() + "\"";
+            fprintf(stderr, "INFO: %s\n", msg.c_str());
+        }
+    }
 }
 
 void CalcServer::commInit(const void* unique_id)

@@ -45,6 +45,14 @@ class Tool {
     int id_in_pipeline() const { return _id; }
     unsigned used_times() const { return _n_iters; }
     double elapsed_ms() const { return _elapsed_ms; }
+    /// Variables the tool reads / writes (Tool::setDependencies, Tool.hpp:520-567).
+    /// false: unknown -- the tool is a barrier for the sweep-fusion planner.
+    virtual bool dependencies(std::vector<InputOutput::Variable*>& in,
+                              std::vector<InputOutput::Variable*>& out) const
+    {
+        (void)in; (void)out;
+        return false;
+    }
 
   protected:
     virtual void _execute() {}
@@ -72,9 +80,20 @@ class Kernel : public Tool {
     const std::string& path() const { return _path; }
     const std::string& entry() const { return _entry; }
     const std::vector<InputOutput::Variable*>& arguments() const { return _vars; }
+    int kernel_id() const { return _kid; }
+    bool dependencies(std::vector<InputOutput::Variable*>& in,
+                      std::vector<InputOutput::Variable*>& out) const override;
+    /// Sweep fusion (aqc_fused_lookup): the leader launches the fused kernel for the
+    /// whole group at its own position, the followers then have nothing left to do
+    void fuse_lead(int fused_id, const std::vector<Kernel*>& group) { _fused_id = fused_id; _group = group; }
+    void fuse_follow(Kernel* leader) { _leader = leader; }
+    bool fused() const { return _fused_id >= 0 || _leader; }
   protected:
     void _execute() override;
   private:
+    int _fused_id = -1;
+    std::vector<Kernel*> _group;
+    Kernel* _leader = nullptr;
     std::string _path, _entry, _n;
     int _kid = -1;
     std::vector<InputOutput::Variable*> _vars;
@@ -88,6 +107,13 @@ class Copy : public Tool {
     Copy(CalcServer* C, const std::string& name, const std::string& in, const std::string& out, bool once)
       : Tool(C, name, once), _in_name(in), _out_name(out) {}
     void setup() override;
+    bool dependencies(std::vector<InputOutput::Variable*>& in,
+                      std::vector<InputOutput::Variable*>& out) const override
+    {
+        in.push_back(_in);
+        out.push_back(_out);
+        return true;
+    }
   protected:
     void _execute() override;
   private:
@@ -315,6 +341,10 @@ class CalcServer {
     void loadParticles();
     /// h check, per-set scalars, definitions, tool->setup() (CalcServer.cpp:1436-1534)
     void setup();
+    /// Group neighbour sweeps that walk the same pairs (aqc_fused_lookup) when nothing
+    /// between them in the pipeline reads their outputs or writes their inputs
+    void planFusion();
+    unsigned fused_groups() const { return _fused_groups; }
     /// Run time steps until an output frame is due or the end criteria is met
     void update(TimeManager& t);
     /// Run exactly one pass over the pipeline (one time step)
@@ -351,6 +381,7 @@ class CalcServer {
     std::vector<std::pair<std::string, std::string>> _defs; // name -> value as "-D" text
     int _mpi_rank, _mpi_size;
     uint64_t _steps = 0;
+    unsigned _fused_groups = 0;
     void* _unsort_scratch = nullptr;
     size_t _unsort_cap = 0;
 };

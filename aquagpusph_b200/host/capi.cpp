@@ -168,6 +168,7 @@ extern "C" int aqh_sync(aqh_sim* sim)
 
 extern "C" uint64_t aqh_launch_count(aqh_sim* sim) { return aqc_launch_count(sim->C->ctx()); }
 extern "C" void* aqh_cuda_ctx(aqh_sim* sim) { return sim->C->ctx(); }
+extern "C" unsigned aqh_fused_groups(aqh_sim* sim) { return sim->C ? sim->C->fused_groups() : 0; }
 
 extern "C" int aqh_eval(int dims, const char* decls, const char* type, const char* expr,
                         void* out, size_t bytes)

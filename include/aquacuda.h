@@ -150,6 +150,27 @@ const aqc_arg_info* aqc_kernel_args(int kernel_id);
  * registry order.  n = global work size (Kernel.cpp:558-594). */
 int aqc_launch(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nargs);
 
+/* ---- fusion of neighbour sweeps.  The reference launches one sweep per script
+ * kernel (9 per midpoint sub-iteration in the 3-D dam break); sweeps
+ * that walk the same (i, j) pairs can share the candidate filter and the pair
+ * geometry.  kernel_ids: n kernel ids in pipeline order.  Returns a fused id, or
+ * AQC_ERR_NOKERNEL when this set is not fused (the caller then launches the
+ * members one by one).  The arguments of aqc_launch_fused are the members'
+ * argument lists concatenated in the same order; the results are bit-identical
+ * to launching the members one after the other.  It is the CALLER's business to
+ * check that nothing between the members' positions in its pipeline reads the
+ * outputs or writes the inputs (the C++ host does, calcserver.cpp). */
+int aqc_fused_lookup(const int* kernel_ids, int n, int dims);
+/* 1 when the list is the beginning of (or all of) some fused set, else 0 */
+int aqc_fused_prefix(const int* kernel_ids, int n, int dims);
+/* particle classes (imove) whose ROWS a kernel writes / a fused sweep reads besides the
+ * positions; lets a caller see that cfd/Sensors.cl (sensor rows of u, rho, p) does not
+ * disturb a sweep over fluid pairs */
+enum { AQC_ROWS_FLUID = 1, AQC_ROWS_SENSOR = 2, AQC_ROWS_BOUNDARY = 4, AQC_ROWS_ANY = 7 };
+int aqc_kernel_write_rows(int kernel_id);
+int aqc_fused_read_rows(int fused_id);
+int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs);
+
 /* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI
  * rank/size queries and wrappers (AuxiliarMethods.cpp:388-516) and the MPISync
  * tool (MPISync.cpp:183-232; kernels MPISync.cl.in:31-80), whose host-staged

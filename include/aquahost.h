@@ -53,6 +53,7 @@ int aqh_step(aqh_sim* sim, int n);
 int aqh_run(aqh_sim* sim);
 int aqh_sync(aqh_sim* sim);
 uint64_t aqh_launch_count(aqh_sim* sim); /* CUDA kernels launched so far */
+unsigned aqh_fused_groups(aqh_sim* sim); /* sweep groups the planner fused (0 with AQUA_NO_FUSION) */
 void* aqh_cuda_ctx(aqh_sim* sim);         /* the aqc_ctx* underneath */
 
 /* Variables + Tokenizer without a device (Variable.cpp:1321-1435): register the

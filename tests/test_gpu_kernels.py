@@ -27,3 +27,36 @@ def test_sweeps_match_oracle(oracle, dims, n, hfac):
     # the case must actually exercise the kernels
     assert np.abs(ref["grad_p"]).max() > 0 and np.abs(ref["grad_w_bi"]).max() > 0
     assert np.abs(ref["lap_p"]).max() > 0 and (ref["n_neighs"] > 0).any()
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(3, 14, 2.0), (2, 60, 3.0)])
+def test_fused_fluid_sweep_equals_its_members(oracle, dims, n, hfac):
+    """aqc_launch_fused: Shepard + Interactions + deltaSPH full + lapp in one pass must give
+    exactly what the four sweeps give one after the other."""
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    sets = [
+        [("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry"), ("cfd/deltaSPH.cl", "full"),
+         ("cfd/deltaSPH.cl", "lapp")],
+        [("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry")],
+        [("cfd/Interactions.cl", "entry"), ("cfd/deltaSPH.cl", "full"), ("cfd/deltaSPH.cl", "lapp")],
+    ]
+    outs = ("shepard", "grad_p", "lap_u", "div_u", "lap_p_corr", "lap_p")
+    for members in sets:
+        a = pipeline.CudaState(ctx, s)
+        b = pipeline.CudaState(ctx, s)
+        for st in (a, b):
+            st.run("basic/EOS.cl")
+            for k in outs:          # sentinel: rows the kernels do not write must stay untouched
+                st.ctx.fill(st.v[k], np.full(st.v[k].elem_bytes // 4, 7.5, np.float32).tobytes())
+        for sc, en in members:
+            a.run(sc, en)
+        ctx.launch_fused(members, b.v)
+        for k in outs:
+            assert np.array_equal(a.get(k), b.get(k)), (members, k)
+    L = _lib.lib()
+    import ctypes as C
+    ids = (C.c_int * 2)(ctx.lookup("cfd/Rates.cl", "entry"), ctx.lookup("cfd/Interactions.cl", "entry"))
+    assert L.aqc_fused_lookup(ids, 2, dims) < 0
+    ctx.close()

@@ -27,9 +27,11 @@ def _oracle(case, overrides, nset):
     return I
 
 
-@pytest.mark.parametrize("n,maxiter", [(6000, 30), (12000, 3)])
-def test_dam_break_3d_steps(oracle, n, maxiter):
+@pytest.mark.parametrize("n,maxiter,fusion", [(6000, 30, True), (12000, 3, True), (6000, 3, False)])
+def test_dam_break_3d_steps(oracle, n, maxiter, fusion, monkeypatch):
     host.set_log_level(3)
+    if not fusion:
+        monkeypatch.setenv("AQUA_NO_FUSION", "1")
     ov = {"iter_midpoint_max": maxiter}
     case = cases.spheric2_dam_break(n, 3.0, seed=7)
     nset = (case["N"] - 8, 8)
@@ -37,6 +39,8 @@ def test_dam_break_3d_steps(oracle, n, maxiter):
     sim = casegen.load("spheric2_dambreak_3d", case, nset, ov)
     assert [t for t in sim.tools() if not t[1].startswith("report")] == \
         [(t["name"], t["type"]) for t in I.tools if not t["type"].startswith("report")]
+    # the four fluid-fluid sweeps of the inner loop run as one fused launch (or not at all)
+    assert sim.fused_groups() == (1 if fusion else 0)
     for step in range(3):
         I.step()
         sim.step(1)
