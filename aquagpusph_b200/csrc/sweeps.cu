@@ -1026,8 +1026,8 @@ struct PElasticBounce : PBase {
 // kernel factors (SURVEY 2.4 "fusion targets").  Here one pass filters the
 // candidates once and evaluates every member's pair term from the shared
 // geometry.  Each member's arithmetic is exactly that of its stand-alone policy
-// (same expressions, same order), so the outputs are bit-identical to running the
-// members one after the other.  The host asks for a fusion with
+// (same expressions, same pairs, same order), so the outputs equal those of running the
+// members one after the other up to the compiler's FMA contraction (a few ulp).  The host asks for a fusion with
 // aqc_fused_lookup(); members: Interactions always, Shepard / full / lapp optional.
 template <int D, bool SHEP, bool FULL, bool LAPP>
 struct PFusedFluid : PBase {

@@ -156,8 +156,8 @@ int aqc_launch(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nar
  * geometry.  kernel_ids: n kernel ids in pipeline order.  Returns a fused id, or
  * AQC_ERR_NOKERNEL when this set is not fused (the caller then launches the
  * members one by one).  The arguments of aqc_launch_fused are the members'
- * argument lists concatenated in the same order; the results are bit-identical
- * to launching the members one after the other.  It is the CALLER's business to
+ * argument lists concatenated in the same order; the results equal those of launching
+ * the members one after the other up to FMA contraction (a few ulp).  It is the CALLER's business to
  * check that nothing between the members' positions in its pipeline reads the
  * outputs or writes the inputs (the C++ host does, calcserver.cpp). */
 int aqc_fused_lookup(const int* kernel_ids, int n, int dims);

@@ -32,7 +32,9 @@ def test_sweeps_match_oracle(oracle, dims, n, hfac):
 @pytest.mark.parametrize("dims,n,hfac", [(3, 14, 2.0), (2, 60, 3.0)])
 def test_fused_fluid_sweep_equals_its_members(oracle, dims, n, hfac):
     """aqc_launch_fused: Shepard + Interactions + deltaSPH full + lapp in one pass must give
-    exactly what the four sweeps give one after the other."""
+    what the four sweeps give one after the other: same pairs, same order, same expressions;
+    only the compiler's FMA contraction may differ between the two kernels (a few ulp of the
+    largest term), rows no member writes stay untouched."""
     case = cases.dam_break(dims, n, hfac)
     s = pipeline.oracle_linklist_and_sort(case)
     ctx = _lib.Context(0, dims=dims, h=case["h"])
@@ -54,7 +56,9 @@ def test_fused_fluid_sweep_equals_its_members(oracle, dims, n, hfac):
             a.run(sc, en)
         ctx.launch_fused(members, b.v)
         for k in outs:
-            assert np.array_equal(a.get(k), b.get(k)), (members, k)
+            x, y = a.get(k).astype(np.float64), b.get(k).astype(np.float64)
+            assert np.array_equal(x == 7.5, y == 7.5), (members, k)
+            assert np.abs(x - y).max() <= 2e-6 * np.abs(x).max(), (members, k)
     L = _lib.lib()
     import ctypes as C
     ids = (C.c_int * 2)(ctx.lookup("cfd/Rates.cl", "entry"), ctx.lookup("cfd/Interactions.cl", "entry"))

@@ -37,7 +37,7 @@ def main():
                                       "u", "dudt", "drhodt", "refd", "visc_dyn", "delta")}
     for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m", "u", "dudt", "drhodt"):
         v[k + "_in"] = ctx.empty(c[k].shape, c[k].dtype)
-    for k in ("binormal", "grad_p", "lap_u", "lap_p_corr", "grad_w_bi", "r_bak"):
+    for k in ("binormal", "grad_p", "lap_u", "lap_p_corr", "grad_w_bi", "r_bak", "r_in2"):
         v[k] = ctx.zeros((N, V), np.float32)
     for k in ("p", "div_u", "shepard", "lap_p", "div_u_bi", "dt_var", "residual_midpoint"):
         v[k] = ctx.zeros(N, np.float32)
@@ -90,9 +90,13 @@ def main():
         ("lapp", K("cfd/deltaSPH.cl", "lapp"), 40 * N),
         ("full", K("cfd/deltaSPH.cl", "full"), 52 * N),
         ("lapp_corr", K("cfd/deltaSPH.cl", "lapp_corr"), 60 * N),
+        ("fused_fluid", lambda: ctx.launch_fused([("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry"),
+                                                  ("cfd/deltaSPH.cl", "full"), ("cfd/deltaSPH.cl", "lapp")], v), 112 * N),
         ("mls", K("basic/MLS.cl"), 92 * N),
         ("bie_interactions", K("cfd/Boundary/BIe/Interactions.cl"), 76 * N),
         ("bie_p_boundary", K("cfd/Boundary/BIe/Interactions.cl", "p_boundary"), 36 * N),
+        ("bie_elastic_bounce", K("cfd/Boundary/BIe/ElasticBounce.cl"), 68 * N),
+        ("bie_pst", K("cfd/Boundary/BIe/PST.cl"), 60 * N),
         ("rates", K("cfd/Rates.cl"), 64 * N),
         ("corrector", K("basic/time_scheme/midpoint.cl", "corrector"), 96 * N),
         ("timestep", K("cfd/TimeStep.cl"), 24 * N),
