@@ -187,6 +187,16 @@ __device__ __forceinline__ uint32_t test_tile(const float4* __restrict__ T, unsi
     return hits << (32 - 2 * NPAIR);
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t a) // a: shared-window address
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(a)
+                 : "memory");
+    return v;
+}
+
 constexpr float AQC_NEVER = 1.0e30f; // |r_j|^2 of a padding / excluded candidate
 
 template <class P>
@@ -286,14 +296,322 @@ sweep2_kernel(const P p, const LLParams ll)
         p.store_i(st, i);
 }
 
+// ---------------------------------------------------------------------------
+// v3 engine (SPHERE policies): CTA-shared neighbour tiles, deferred pair bodies.
+//
+// v2 runs the pair bodies of a tile right after its filter, so a tile costs
+// max-over-lanes(hits) body iterations: a lane's hit count in one neighbour cell
+// depends on where its particle sits in its own cell, and the measured lane
+// efficiency of the body loop is 0.40 (profiles/r1_ncu_shepard_v2a*); and every warp
+// stages its own copy of every neighbour tile.  Here
+//   * a CTA of 8 warps takes 256 consecutive (cell-ordered) particles; the particles
+//     whose cells lie within S3_SPAN cells of the first one in its x row form a group
+//     that is served by ONE walk over the union of the members' neighbourhoods: the
+//     3 (2-D) or 9 (3-D) x rows [c0 - 1, c0 + span + 1] + offset, cut in parts of two
+//     cells.  Tiles of 32 candidates are taken round-robin over the parts, so that the
+//     tiles in flight always mix all directions; each warp stages one tile per round
+//     (j rows + the packed test layout) into a shared ring of K rounds;
+//   * a warp filters the tiles that hold cells adjacent to its lanes' cells and only
+//     RECORDS the hit masks (per-warp mask ring); a lane keeps the candidates of ITS
+//     OWN 3^D neighbourhood only (a tile holds at most two adjacent cells, the first
+//     n1 candidates belong to the lower one), so the pair set is exactly the
+//     reference's whatever the other lanes of the group need;
+//   * every lane walks its masks with a FIFO cursor (seq, cur); a body iteration is
+//     issued only while EVERY participating lane of the warp has a pending hit, or
+//     when the oldest ring round has to be recycled.  Replaying this on the dam-break
+//     state gives 0.80 (window of 8 tiles) to 0.92 (16+) lane efficiency.
+// Per particle the hits are consumed in the order of a fixed traversal, so sums are
+// deterministic (run-to-run bit-identical); the order is not the reference's x-outer
+// one any more: results differ from v2 by fp32 rounding of the sums only.
+// Order-dependent kernels stay on sweep_kernel.
+constexpr int S3_WARPS = 8;
+constexpr int S3_THREADS = S3_WARPS * 32;
+constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
+constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
+
+// first j in [b, N) whose cell (relative to lo) is beyond wid; icell is sorted
+__device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icell, uint32_t b,
+                                               uint32_t N, uint32_t lo, uint32_t wid)
+{
+    uint32_t step = 32, good = b; // icell[good] is inside
+    while (good + step < N && __ldg(icell + good + step) - lo <= wid) {
+        good += step;
+        step *= 2;
+    }
+    uint32_t bad = min(good + step, N); // first known outside (or N)
+    while (bad - good > 1) {
+        const uint32_t mid = good + (bad - good) / 2;
+        if (__ldg(icell + mid) - lo <= wid)
+            good = mid;
+        else
+            bad = mid;
+    }
+    return bad;
+}
+
+template <class P>
+__global__ void __launch_bounds__(S3_THREADS, (P::NJ4 <= 2) ? 4 : 3)
+sweep3_kernel(const P p, const LLParams ll, const int K)
+{
+    extern __shared__ float4 smem3[];
+    constexpr int W = S3_WARPS;
+    constexpr int SLOT4 = P::NJ4 * 32;
+    const uint32_t NS = (uint32_t)K * W; // ring slots
+    float4* const sT = smem3;            // [W][32]   packed test layout of the round's tiles
+    float4* const sJ = sT + W * 32;      // [NS][SLOT4] j rows
+    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NS][32] hit masks
+    __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
+    __shared__ uint32_t t_cnt[W], t_rel[W], t_n1[W];
+    __shared__ uint32_t s_ball[W], s_c0, s_span, s_last, s_maxk;
+    __shared__ float s_o[6];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t i = blockIdx.x * (uint32_t)S3_THREADS + tid;
+    const bool valid = i < ll.N;
+    const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
+    const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    typename P::IState st;
+    st.x = st.y = st.z = 0.f;
+    if (active)
+        p.load_i(st, i);
+    const int tslot = (lane >> 1) * 8 + (lane & 1);
+    constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
+    const float cut2f = p.cut2 * 1.0001f;
+    uint32_t* const Mw = sM + (size_t)warp * NS * 32 + lane;
+    const uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ);
+    float* const tst = reinterpret_cast<float*>(sT + warp * 32);
+
+    bool pending = active;
+    for (;;) {
+        // ---- the group of this pass: first pending particle and its x-row neighbours
+        const uint32_t pb = __ballot_sync(0xffffffffu, pending);
+        if (lane == 0)
+            s_ball[warp] = pb;
+        if (tid == 0) {
+            s_span = 0;
+            s_last = 0;
+            s_maxk = 0;
+        }
+        __syncthreads();
+        int first = -1;
+#pragma unroll
+        for (int w = W - 1; w >= 0; w--)
+            if (s_ball[w])
+                first = w * 32 + __ffs(s_ball[w]) - 1;
+        if (first < 0)
+            break;
+        if (tid == first) {
+            s_c0 = c_i;
+            s_o[0] = st.x; s_o[1] = st.y; s_o[2] = st.z;
+        }
+        __syncthreads();
+        const uint32_t c0 = s_c0;
+        const uint32_t a_i = c_i - c0;
+        const bool mine = pending && (a_i <= (uint32_t)S3_SPAN);
+        const uint32_t mine_w = __ballot_sync(0xffffffffu, mine);
+        if (mine_w) {
+            const uint32_t sp = __reduce_max_sync(0xffffffffu, mine ? a_i : 0u);
+            if (lane == 0) {
+                atomicMax(&s_span, sp);
+                atomicMax(&s_last, (uint32_t)(warp * 32 + 31 - __clz(mine_w)));
+            }
+        }
+        pending = pending && !mine;
+        __syncthreads();
+        if (tid == (int)s_last) {
+            s_o[3] = st.x; s_o[4] = st.y; s_o[5] = st.z;
+        }
+        const uint32_t len = s_span + 3u, nparts = (len + 1u) / 2u;
+        const uint32_t NE = NROWS * nparts;
+        if ((uint32_t)tid < NE) {
+            const uint32_t row = tid / nparts, part = tid - row * nparts;
+            const int cy = (int)(row % 3u) - 1, cz = (P::DIMS == 3) ? (int)(row / 3u) - 1 : 0;
+            const uint32_t base = c0 + (uint32_t)cy * ll.nx + (uint32_t)cz * ll.nx * ll.ny - 1u;
+            const uint32_t lo = base + 2u * part;
+            const uint32_t wid = (2u * part + 1u < len) ? 1u : 0u;
+            uint32_t b = __ldg(ll.ihoc + lo);
+            if (wid)
+                b = min(b, __ldg(ll.ihoc + lo + 1u));
+            uint32_t en = b;
+            if (b < ll.N)
+                en = s3_run_end(ll.icell, b, ll.N, lo, wid);
+            else
+                b = en = ll.N;
+            e_begin[tid] = b;
+            e_end[tid] = en;
+            e_lo[tid] = lo;
+            e_rel[tid] = 2u * part; // x offset of cell lo relative to c0, plus one
+            if (en > b)
+                atomicMax(&s_maxk, (en - b + 31u) / 32u);
+        }
+        __syncthreads();
+        const uint32_t maxk = s_maxk;
+        // origin of the relative coordinates: between the first and the last member
+        const float ox = 0.5f * (s_o[0] + s_o[3]), oy = 0.5f * (s_o[1] + s_o[4]);
+        const float oz = (P::DIMS == 3) ? 0.5f * (s_o[2] + s_o[5]) : 0.f;
+        const float xi = st.x - ox, yi = st.y - oy, zi = (P::DIMS == 3) ? st.z - oz : 0.f;
+        const unsigned long long X2 = pack2(-2.f * xi, -2.f * xi);
+        const unsigned long long Y2 = pack2(-2.f * yi, -2.f * yi);
+        const unsigned long long Z2 = pack2(-2.f * zi, -2.f * zi);
+        const float ci = fmaf(zi, zi, fmaf(yi, yi, xi * xi)) - cut2f;
+        const unsigned long long C2 = pack2(ci, ci);
+
+        // Per-lane FIFO over the tiles in the ring.  Bit b of nz: this lane has hits in the
+        // tile at ring position `oldest + b` (bits 0..W-1 = the oldest round); cur = the
+        // unconsumed hits of the tile it is working on (candidate k at bit 31 - k), curb that
+        // tile's bit, crow the shared-window address of its last row slot.
+        uint32_t nz = 0, cur = 0, curb = 0, crow = 0;
+        uint32_t oldest = 0; // ring slot of bit 0
+
+        auto pick = [&]() { // cur == 0 && nz != 0: take the next tile with hits
+            curb = __ffs(nz) - 1;
+            nz &= nz - 1;
+            uint32_t s = oldest + curb;
+            s = (s >= NS) ? s - NS : s;
+            cur = Mw[s * 32];
+            crow = sJ_a + s * (SLOT4 * 16) + 31 * 16;
+        };
+        auto consume = [&]() {
+            if (cur) {
+                const uint32_t f = 31 - __clz(cur);
+                cur &= (1u << f) - 1u;
+                const uint32_t a = crow - (f << 4);
+                float4 v[P::NJ4];
+#pragma unroll
+                for (int q = 0; q < P::NJ4; q++)
+                    v[q] = lds128(a + q * 512);
+                if (p.test(st, v[0]))
+                    p.body(st, v, 1);
+                if (!cur && nz)
+                    pick();
+            }
+        };
+
+        const uint32_t nrounds = (maxk * NE + W - 1) / W;
+        uint32_t rk = 0; // ring round that receives round r (r % K)
+        for (uint32_t r = 0; r < nrounds; r++) {
+            uint32_t nb = r * W; // bit of the round's first tile
+            if (r >= (uint32_t)K) {
+                // the ring round about to be overwritten is the oldest one: finish its hits
+                while (__any_sync(0xffffffffu, (cur != 0 && curb < W) || (nz & ((1u << W) - 1u))))
+                    consume();
+                nz >>= W;
+                curb -= W;
+                oldest = (oldest + W == NS) ? 0u : oldest + W;
+                nb = (K - 1) * W;
+            }
+            __syncthreads();
+            // ---- stage: warp w brings tile r * W + w = (part e, its k-th tile)
+            {
+                const uint32_t tn = r * W + warp;
+                const uint32_t k = tn / NE, e = tn - k * NE;
+                uint32_t cnt = 0;
+                if (k < maxk) {
+                    const uint32_t b = e_begin[e] + 32u * k, en = e_end[e];
+                    if (b < en) {
+                        cnt = min(32u, en - b);
+                        const bool in = (uint32_t)lane < cnt;
+                        const uint32_t jj = b + lane;
+                        const uint32_t cj = in ? __ldg(ll.icell + jj) - e_lo[e] : 0xFFFFFFFFu;
+                        const uint32_t cj0 = __shfl_sync(0xffffffffu, cj, 0);
+                        const int n1 = __popc(__ballot_sync(0xffffffffu, cj == cj0));
+                        float4* const slot = sJ + (size_t)(rk * W + warp) * SLOT4;
+                        float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
+                        if (in) {
+                            float4 o[P::NJ4];
+                            p.stage_j(jj, o);
+#pragma unroll
+                            for (int q = 0; q < P::NJ4; q++)
+                                slot[q * 32 + lane] = o[q];
+                            if (o[0].x != AQC_FAR) {
+                                tx = o[0].x - ox;
+                                ty = o[0].y - oy;
+                                tz = (P::DIMS == 3) ? o[0].z - oz : 0.f;
+                                tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+                            }
+                        }
+                        tst[tslot] = tx;
+                        tst[tslot + 2] = ty;
+                        tst[tslot + 4] = tz;
+                        tst[tslot + 6] = tn2;
+                        if (lane == 0) {
+                            t_rel[warp] = e_rel[e] + cj0;
+                            t_n1[warp] = (uint32_t)n1;
+                        }
+                    }
+                }
+                if (lane == 0)
+                    t_cnt[warp] = cnt;
+            }
+            __syncthreads();
+            // ---- filter: record the hit masks of the round's tiles
+            if (mine) {
+#pragma unroll 1
+                for (int w2 = 0; w2 < W; w2++) {
+                    const uint32_t cnt = t_cnt[w2];
+                    if (!cnt)
+                        continue;
+                    const uint32_t rel = t_rel[w2] - a_i; // (x offset of the lower cell - a_i) + 1
+                    const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[w2]);
+                    const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
+                    if (!okm)
+                        continue;
+                    const float4* T = sT + w2 * 32;
+                    uint32_t m;
+                    if (cnt > 16)
+                        m = test_tile<16>(T, X2, Y2, Z2, C2);
+                    else if (cnt > 8)
+                        m = test_tile<8>(T, X2, Y2, Z2, C2);
+                    else
+                        m = test_tile<4>(T, X2, Y2, Z2, C2);
+                    m &= okm;
+                    if (m) {
+                        Mw[(rk * W + w2) * 32] = m;
+                        nz |= 1u << (nb + w2);
+                    }
+                }
+                if (!cur && nz)
+                    pick();
+            }
+            rk = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
+            // ---- bodies, while every member lane of the warp has one pending
+            if (mine_w)
+                while (__ballot_sync(0xffffffffu, cur != 0) == mine_w)
+                    consume();
+        }
+        while (__any_sync(0xffffffffu, cur != 0))
+            consume();
+        __syncthreads();
+    }
+    if (active)
+        p.store_i(st, i);
+}
+
+int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
+int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
+
 template <class P>
 static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll)
 {
-    const unsigned grid = aqc_blocks(ll.N, SWEEP_THREADS);
-    if constexpr (P::SPHERE)
-        sweep2_kernel<P><<<grid, SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
-    else
-        sweep_kernel<P, true><<<grid, SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
+    if constexpr (P::SPHERE) {
+        if (aqc_sweep_engine() == 3) {
+            const int K = aqc_sweep_ring(P::NJ4);
+            const size_t NS = (size_t)K * S3_WARPS;
+            const size_t smem = (S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
+                                S3_WARPS * NS * 32 * sizeof(uint32_t);
+            static size_t configured = 0; // per instantiation
+            if (smem > configured) {
+                AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            sweep3_kernel<P><<<aqc_blocks(ll.N, S3_THREADS), S3_THREADS, smem, ctx->stream>>>(p, ll, K);
+        } else {
+            sweep2_kernel<P><<<aqc_blocks(ll.N, SWEEP_THREADS), SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
+        }
+    } else {
+        sweep_kernel<P, true><<<aqc_blocks(ll.N, SWEEP_THREADS), SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
+    }
     AQC_LAUNCH_CHECK(ctx);
     return AQC_OK;
 }

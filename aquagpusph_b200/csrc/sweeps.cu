@@ -13,6 +13,32 @@
 //    exactly zero for r_ij = 0 (all kernels below that exclude it).
 #include "sweep.cuh"
 
+#include <stdlib.h>
+
+// Engine selection for the SPHERE policies (A/B measurements; both engines are
+// CUDA): AQC_SWEEP_ENGINE=2 keeps the immediate-body engine, default 3 = deferred.
+int aqc_sweep_engine()
+{
+    static const int e = [] {
+        const char* s = getenv("AQC_SWEEP_ENGINE");
+        return (s && atoi(s) == 2) ? 2 : 3;
+    }();
+    return e;
+}
+// Ring rounds of the v3 engine (8 tiles each): shared memory per CTA =
+// 4 KB + K * 8 * (NJ4 * 512 + 1024) bytes
+int aqc_sweep_ring(int nj4)
+{
+    static const int forced = [] {
+        const char* s = getenv("AQC_SWEEP_RING");
+        const int r = s ? atoi(s) : 0;
+        return (r >= 1 && r <= 8) ? r : 0;
+    }();
+    if (forced)
+        return forced;
+    return nj4 <= 2 ? 3 : 2;
+}
+
 namespace {
 
 constexpr float iM_PI = 0.318309886f; // KernelFunctions/Wendland3D.hcl:34-39
