@@ -97,29 +97,38 @@ sweep_kernel(const P p, const LLParams ll)
                         const int cnt = __popc(__ballot_sync(0xffffffffu, in));
                         if (!cnt)
                             break;
+                        bool live = false;
                         if (in) {
                             float4 o[P::NJ4];
                             p.stage_j(jj, o);
+                            live = P::j_live(o[0]);
 #pragma unroll
                             for (int k = 0; k < P::NJ4; k++)
                                 tile[k][lane] = o[k];
                         }
+                        // only the candidates that can interact at all are tested (a tile of
+                        // fluid particles costs a boundary kernel one ballot)
+                        const uint32_t lm = __ballot_sync(0xffffffffu, live);
                         __syncwarp();
-                        if (mine) {
+                        if (mine && lm) {
                             if constexpr (COMPACT) {
                                 uint32_t hits = 0;
-                                for (int k = 0; k < cnt; k++)
+                                for (uint32_t mm = lm; mm; mm &= mm - 1) {
+                                    const int k = __ffs(mm) - 1;
                                     if (p.test(st, tile[0][k]))
                                         hits |= 1u << k;
+                                }
                                 while (hits) {
                                     const int k = __ffs(hits) - 1;
                                     hits &= hits - 1;
                                     p.body(st, &tile[0][k], 32);
                                 }
                             } else {
-                                for (int k = 0; k < cnt; k++)
+                                for (uint32_t mm = lm; mm; mm &= mm - 1) {
+                                    const int k = __ffs(mm) - 1;
                                     if (p.test(st, tile[0][k]))
                                         p.body(st, &tile[0][k], 32);
+                                }
                             }
                         }
                         __syncwarp();
@@ -357,11 +366,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     constexpr int W = S3_WARPS;
     constexpr int SLOT4 = P::NJ4 * 32;
     const uint32_t NS = (uint32_t)K * W; // ring slots
-    float4* const sT = smem3;            // [W][32]   packed test layout of the round's tiles
-    float4* const sJ = sT + W * 32;      // [NS][SLOT4] j rows
-    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NS][32] hit masks
+    float4* const sT = smem3;            // [2][W][32] packed test layout of the tiles of two rounds
+    float4* const sJ = sT + 2 * W * 32;  // [NS][SLOT4] j rows
+    const uint32_t NM = NS - W;          // mask slots: the round being staged has none yet
+    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NM][32] hit masks
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
-    __shared__ uint32_t t_cnt[W], t_rel[W], t_n1[W];
+    __shared__ uint32_t t_cnt[2][W], t_rel[2][W], t_n1[2][W];
     __shared__ uint32_t s_ball[W], s_c0, s_span, s_last, s_maxk;
     __shared__ float s_o[6];
 
@@ -374,12 +384,10 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     st.x = st.y = st.z = 0.f;
     if (active)
         p.load_i(st, i);
-    const int tslot = (lane >> 1) * 8 + (lane & 1);
     constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
     const float cut2f = p.cut2 * 1.0001f;
-    uint32_t* const Mw = sM + (size_t)warp * NS * 32 + lane;
+    uint32_t* const Mw = sM + (size_t)warp * NM * 32 + lane;
     const uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ);
-    float* const tst = reinterpret_cast<float*>(sT + warp * 32);
 
     bool pending = active;
     for (;;) {
@@ -446,117 +454,145 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         }
         __syncthreads();
         const uint32_t maxk = s_maxk;
-        // origin of the relative coordinates: between the first and the last member
-        const float ox = 0.5f * (s_o[0] + s_o[3]), oy = 0.5f * (s_o[1] + s_o[4]);
-        const float oz = (P::DIMS == 3) ? 0.5f * (s_o[2] + s_o[5]) : 0.f;
-        const float xi = st.x - ox, yi = st.y - oy, zi = (P::DIMS == 3) ? st.z - oz : 0.f;
-        const unsigned long long X2 = pack2(-2.f * xi, -2.f * xi);
-        const unsigned long long Y2 = pack2(-2.f * yi, -2.f * yi);
-        const unsigned long long Z2 = pack2(-2.f * zi, -2.f * zi);
-        const float ci = fmaf(zi, zi, fmaf(yi, yi, xi * xi)) - cut2f;
-        const unsigned long long C2 = pack2(ci, ci);
+        // origin of the relative coordinates: between the first and the last member (kept in
+        // shared memory: only the staging needs it)
+        if (tid == 0) {
+            s_o[0] = 0.5f * (s_o[0] + s_o[3]);
+            s_o[1] = 0.5f * (s_o[1] + s_o[4]);
+            s_o[2] = (P::DIMS == 3) ? 0.5f * (s_o[2] + s_o[5]) : 0.f;
+        }
+        __syncthreads();
+        // filter constants of this lane: -2 r_i and |r_i|^2 - cut^2, relative to the origin
+        const float fx = -2.f * (st.x - s_o[0]), fy = -2.f * (st.y - s_o[1]);
+        const float fz = (P::DIMS == 3) ? -2.f * (st.z - s_o[2]) : 0.f;
+        const float fc = 0.25f * fmaf(fz, fz, fmaf(fy, fy, fx * fx)) - cut2f;
 
         // Per-lane FIFO over the tiles in the ring.  Bit b of nz: this lane has hits in the
         // tile at ring position `oldest + b` (bits 0..W-1 = the oldest round); cur = the
         // unconsumed hits of the tile it is working on (candidate k at bit 31 - k), curb that
         // tile's bit, crow the shared-window address of its last row slot.
         uint32_t nz = 0, cur = 0, curb = 0, crow = 0;
-        uint32_t oldest = 0; // ring slot of bit 0
+        uint32_t oldest = 0, oldestm = 0; // ring slot / mask slot of bit 0
 
         auto pick = [&]() { // cur == 0 && nz != 0: take the next tile with hits
             curb = __ffs(nz) - 1;
             nz &= nz - 1;
-            uint32_t s = oldest + curb;
+            uint32_t s = oldest + curb, sm = oldestm + curb;
             s = (s >= NS) ? s - NS : s;
-            cur = Mw[s * 32];
+            sm = (sm >= NM) ? sm - NM : sm;
+            cur = Mw[sm * 32];
             crow = sJ_a + s * (SLOT4 * 16) + 31 * 16;
         };
-        auto consume = [&]() {
-            if (cur) {
-                const uint32_t f = 31 - __clz(cur);
-                cur &= (1u << f) - 1u;
-                const uint32_t a = crow - (f << 4);
-                float4 v[P::NJ4];
+        auto body1 = [&]() { // cur != 0: the next hit of this lane
+            uint32_t f;
+            asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(cur));
+            cur ^= 1u << f;
+            const uint32_t a = crow - (f << 4);
+            float4 v[P::NJ4];
 #pragma unroll
-                for (int q = 0; q < P::NJ4; q++)
-                    v[q] = lds128(a + q * 512);
-                if (p.test(st, v[0]))
-                    p.body(st, v, 1);
-                if (!cur && nz)
-                    pick();
+            for (int q = 0; q < P::NJ4; q++)
+                v[q] = lds128(a + q * 512);
+            if (p.test(st, v[0]))
+                p.body(st, v, 1);
+            if (!cur && nz)
+                pick();
+        };
+        auto consume = [&]() {
+            if (cur)
+                body1();
+        };
+        // stage: warp w brings tile r * W + w = (part e, its k-th tile) of round r
+        auto stage = [&](uint32_t r, uint32_t ring_round) {
+            const uint32_t tn = r * W + warp;
+            const uint32_t k = tn / NE, e = tn - k * NE;
+            const uint32_t par = r & 1u;
+            uint32_t cnt = 0;
+            if (k < maxk) {
+                const uint32_t b = e_begin[e] + 32u * k, en = e_end[e];
+                if (b < en) {
+                    cnt = min(32u, en - b);
+                    const bool in = (uint32_t)lane < cnt;
+                    const uint32_t jj = b + lane;
+                    float4* const slot = sJ + (size_t)(ring_round * W + warp) * SLOT4;
+                    float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
+                    uint32_t cj = 0xFFFFFFFFu;
+                    bool live = false;
+                    if (in) {
+                        cj = __ldg(ll.icell + jj) - e_lo[e];
+                        float4 o[P::NJ4];
+                        p.stage_j(jj, o);
+#pragma unroll
+                        for (int q = 0; q < P::NJ4; q++)
+                            slot[q * 32 + lane] = o[q];
+                        live = P::j_live(o[0]);
+                        if (live) {
+                            tx = o[0].x - s_o[0];
+                            ty = o[0].y - s_o[1];
+                            tz = (P::DIMS == 3) ? o[0].z - s_o[2] : 0.f;
+                            tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+                        }
+                    }
+                    float* const tst = reinterpret_cast<float*>(sT + (par * W + warp) * 32) +
+                                       (lane >> 1) * 8 + (lane & 1);
+                    tst[0] = tx;
+                    tst[2] = ty;
+                    tst[4] = tz;
+                    tst[6] = tn2;
+                    // a tile without a candidate that can interact at all is dropped (a tile of
+                    // fluid particles costs a boundary kernel its staging only)
+                    if (!__any_sync(0xffffffffu, live))
+                        cnt = 0;
+                    const uint32_t cj0 = __shfl_sync(0xffffffffu, cj, 0);
+                    const int n1 = __popc(__ballot_sync(0xffffffffu, cj == cj0));
+                    if (lane == 0) {
+                        t_rel[par][warp] = e_rel[e] + cj0;
+                        t_n1[par][warp] = (uint32_t)n1;
+                    }
+                }
             }
+            if (lane == 0)
+                t_cnt[par][warp] = cnt;
         };
 
+        // One barrier per round: at barrier r every warp has staged its tile of round r and
+        // has consumed its hits of round r + 1 - K, whose ring round receives round r + 1
+        // while round r is filtered -- a warp's staging loads overlap the other warps' work.
         const uint32_t nrounds = (maxk * NE + W - 1) / W;
-        uint32_t rk = 0; // ring round that receives round r (r % K)
+        if (nrounds)
+            stage(0, 0);
+        uint32_t rk = 0;  // ring round that holds round r (r % K)
+        uint32_t rkm = 0; // mask round of round r (r % (K - 1))
         for (uint32_t r = 0; r < nrounds; r++) {
             uint32_t nb = r * W; // bit of the round's first tile
-            if (r >= (uint32_t)K) {
-                // the ring round about to be overwritten is the oldest one: finish its hits
+            if (r + 1 >= (uint32_t)K) {
                 while (__any_sync(0xffffffffu, (cur != 0 && curb < W) || (nz & ((1u << W) - 1u))))
                     consume();
                 nz >>= W;
                 curb -= W;
                 oldest = (oldest + W == NS) ? 0u : oldest + W;
-                nb = (K - 1) * W;
+                oldestm = (oldestm + W == NM) ? 0u : oldestm + W;
+                nb = (K - 2) * W;
             }
             __syncthreads();
-            // ---- stage: warp w brings tile r * W + w = (part e, its k-th tile)
-            {
-                const uint32_t tn = r * W + warp;
-                const uint32_t k = tn / NE, e = tn - k * NE;
-                uint32_t cnt = 0;
-                if (k < maxk) {
-                    const uint32_t b = e_begin[e] + 32u * k, en = e_end[e];
-                    if (b < en) {
-                        cnt = min(32u, en - b);
-                        const bool in = (uint32_t)lane < cnt;
-                        const uint32_t jj = b + lane;
-                        const uint32_t cj = in ? __ldg(ll.icell + jj) - e_lo[e] : 0xFFFFFFFFu;
-                        const uint32_t cj0 = __shfl_sync(0xffffffffu, cj, 0);
-                        const int n1 = __popc(__ballot_sync(0xffffffffu, cj == cj0));
-                        float4* const slot = sJ + (size_t)(rk * W + warp) * SLOT4;
-                        float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
-                        if (in) {
-                            float4 o[P::NJ4];
-                            p.stage_j(jj, o);
-#pragma unroll
-                            for (int q = 0; q < P::NJ4; q++)
-                                slot[q * 32 + lane] = o[q];
-                            if (o[0].x != AQC_FAR) {
-                                tx = o[0].x - ox;
-                                ty = o[0].y - oy;
-                                tz = (P::DIMS == 3) ? o[0].z - oz : 0.f;
-                                tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-                            }
-                        }
-                        tst[tslot] = tx;
-                        tst[tslot + 2] = ty;
-                        tst[tslot + 4] = tz;
-                        tst[tslot + 6] = tn2;
-                        if (lane == 0) {
-                            t_rel[warp] = e_rel[e] + cj0;
-                            t_n1[warp] = (uint32_t)n1;
-                        }
-                    }
-                }
-                if (lane == 0)
-                    t_cnt[warp] = cnt;
-            }
-            __syncthreads();
+            const uint32_t rk1 = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
+            if (r + 1 < nrounds)
+                stage(r + 1, rk1);
             // ---- filter: record the hit masks of the round's tiles
             if (mine) {
+                const uint32_t par = r & 1u;
+                const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
+                                         C2 = pack2(fc, fc);
 #pragma unroll 1
                 for (int w2 = 0; w2 < W; w2++) {
-                    const uint32_t cnt = t_cnt[w2];
+                    const uint32_t cnt = t_cnt[par][w2];
                     if (!cnt)
                         continue;
-                    const uint32_t rel = t_rel[w2] - a_i; // (x offset of the lower cell - a_i) + 1
-                    const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[w2]);
+                    const uint32_t rel = t_rel[par][w2] - a_i; // (x offset of the lower cell - a_i) + 1
+                    const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[par][w2]);
                     const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
                     if (!okm)
                         continue;
-                    const float4* T = sT + w2 * 32;
+                    const float4* T = sT + (par * W + w2) * 32;
                     uint32_t m;
                     if (cnt > 16)
                         m = test_tile<16>(T, X2, Y2, Z2, C2);
@@ -566,18 +602,18 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                         m = test_tile<4>(T, X2, Y2, Z2, C2);
                     m &= okm;
                     if (m) {
-                        Mw[(rk * W + w2) * 32] = m;
+                        Mw[(rkm * W + w2) * 32] = m;
                         nz |= 1u << (nb + w2);
                     }
                 }
                 if (!cur && nz)
                     pick();
+                // ---- bodies, while every member lane of the warp has one pending
+                while (__ballot_sync(mine_w, cur != 0) == mine_w)
+                    body1();
             }
-            rk = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
-            // ---- bodies, while every member lane of the warp has one pending
-            if (mine_w)
-                while (__ballot_sync(0xffffffffu, cur != 0) == mine_w)
-                    consume();
+            rk = rk1;
+            rkm = (rkm + 2 == (uint32_t)K) ? 0u : rkm + 1;
         }
         while (__any_sync(0xffffffffu, cur != 0))
             consume();
@@ -594,11 +630,11 @@ template <class P>
 static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll)
 {
     if constexpr (P::SPHERE) {
-        if (aqc_sweep_engine() == 3) {
+        if (aqc_sweep_engine() == 3 && !P::SPARSE_I) {
             const int K = aqc_sweep_ring(P::NJ4);
             const size_t NS = (size_t)K * S3_WARPS;
-            const size_t smem = (S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
-                                S3_WARPS * NS * 32 * sizeof(uint32_t);
+            const size_t smem = (2 * S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
+                                S3_WARPS * (NS - S3_WARPS) * 32 * sizeof(uint32_t);
             static size_t configured = 0; // per instantiation
             if (smem > configured) {
                 AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P>,

@@ -26,17 +26,18 @@ int aqc_sweep_engine()
     return e;
 }
 // Ring rounds of the v3 engine (8 tiles each): shared memory per CTA =
-// 4 KB + K * 8 * (NJ4 * 512 + 1024) bytes
+// 8 KB + K * 8 * NJ4 * 512 + (K - 1) * 8 * 1024 bytes; the deferral window is (K - 1) * 8 tiles
 int aqc_sweep_ring(int nj4)
 {
     static const int forced = [] {
         const char* s = getenv("AQC_SWEEP_RING");
         const int r = s ? atoi(s) : 0;
-        return (r >= 1 && r <= 8) ? r : 0;
+        return (r >= 2 && r <= 4) ? r : 0; // K * 8 tiles must fit the 32-bit lane bitmap
     }();
     if (forced)
         return forced;
-    return nj4 <= 2 ? 3 : 2;
+    (void)nj4;
+    return 3;
 }
 
 namespace {
@@ -115,6 +116,11 @@ __device__ __forceinline__ float q_of(float d2, float invH)
 struct PBase {
     const int* __restrict__ imove;
     float invH, cut2;
+    // staged row 0 of a j that can interact at all (tiles without one are skipped)
+    __device__ static bool j_live(const float4& o0) { return o0.x != AQC_FAR; }
+    // kernels whose i particles are few and scattered (sensors, boundary elements) keep
+    // the per-warp engine: a CTA-wide walk for a handful of lanes does not pay
+    static constexpr bool SPARSE_I = false;
 };
 
 // ------------------------------------------------------------------------
@@ -371,6 +377,7 @@ struct PMLS : PBase {
 template <int D>
 struct PSensors : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true;
     static constexpr int DIMS = D, NJ4 = 3;
     const void* r;
     const float* m;
@@ -470,6 +477,7 @@ struct PBIeInteractions : PBase {
 template <int D>
 struct PBIePBoundary : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *m, *rho;
@@ -535,6 +543,7 @@ struct PBIeElasticBounce : PBase {
         o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
         o[1] = make_float4(n.x, n.y, n.z, dr);
     }
+    __device__ static bool j_live(const float4& o0) { return o0.w >= 0.f; }
     __device__ bool test(const IState& s, const float4& A) const
     {
         // cheap necessary condition: |rt|^2 < R^2 implies |r_ij|^2 - rn^2 < R^2; the
@@ -607,6 +616,7 @@ struct PBIePST : PBase {
         o[0] = make_float4(a.x, a.y, a.z, ok ? R * R : -1.f);
         o[1] = make_float4(n.x, n.y, n.z, 0.f);
     }
+    __device__ static bool j_live(const float4& o0) { return o0.w >= 0.f; }
     __device__ bool test(const IState&, const float4& A) const { return A.w >= 0.f; }
     __device__ void body(IState& s, const float4* row, int stride) const
     {
@@ -1003,6 +1013,7 @@ struct PElasticBounce : PBase {
         o[2] = make_float4(b.x, b.y, b.z, 0.f);
         o[3] = make_float4(c.x, c.y, c.z, 0.f);
     }
+    __device__ static bool j_live(const float4& o0) { return o0.w >= 0.f; }
     __device__ bool test(const IState&, const float4& A) const { return A.w >= 0.f; }
     __device__ void body(IState& s, const float4* row, int stride) const
     {
