@@ -497,9 +497,47 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             if (!cur && nz)
                 pick();
         };
+        // Two hits per iteration (P::PAIR2): both rows are loaded first and both bodies run
+        // as straight-line code, so the two dependency chains (LDS -> sqrt -> Wendland
+        // factors -> accumulators) overlap.  A hit that fails the exact test, or the
+        // missing second hit of a lane with a single one left, gets its weights zeroed
+        // (P::kill) instead of a branch: its terms are exactly +-0.
+        auto body2 = [&]() { // cur != 0
+            uint32_t f;
+            asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(cur));
+            cur ^= 1u << f;
+            const uint32_t a1 = crow - (f << 4);
+            if (!cur && nz)
+                pick();
+            const bool two = cur != 0;
+            uint32_t a2 = a1;
+            if (two) {
+                asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(cur));
+                cur ^= 1u << f;
+                a2 = crow - (f << 4);
+            }
+            float4 v1[P::NJ4], v2[P::NJ4];
+#pragma unroll
+            for (int q = 0; q < P::NJ4; q++) {
+                v1[q] = lds128(a1 + q * 512);
+                v2[q] = lds128(a2 + q * 512);
+            }
+            if (!p.test(st, v1[0]))
+                P::kill(v1);
+            if (!two || !p.test(st, v2[0]))
+                P::kill(v2);
+            p.body(st, v1, 1);
+            p.body(st, v2, 1);
+            if (!cur && nz)
+                pick();
+        };
         auto consume = [&]() {
-            if (cur)
-                body1();
+            if (cur) {
+                if constexpr (P::PAIR2)
+                    body2();
+                else
+                    body1();
+            }
         };
         // stage: warp w brings tile r * W + w = (part e, its k-th tile) of round r
         auto stage = [&](uint32_t r, uint32_t ring_round) {
@@ -609,8 +647,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 if (!cur && nz)
                     pick();
                 // ---- bodies, while every member lane of the warp has one pending
-                while (__ballot_sync(mine_w, cur != 0) == mine_w)
-                    body1();
+                while (__ballot_sync(mine_w, cur != 0) == mine_w) {
+                    if constexpr (P::PAIR2)
+                        body2();
+                    else
+                        body1();
+                }
             }
             rk = rk1;
             rkm = (rkm + 2 == (uint32_t)K) ? 0u : rkm + 1;

@@ -121,6 +121,10 @@ struct PBase {
     // kernels whose i particles are few and scattered (sensors, boundary elements) keep
     // the per-warp engine: a CTA-wide walk for a handful of lanes does not pay
     static constexpr bool SPARSE_I = false;
+    // v3 engine: two hits per body iteration.  Needs kill() to zero every weight of a
+    // staged row so that body() adds exactly +-0 for it.
+    static constexpr bool PAIR2 = false;
+    __device__ static void kill(float4* v) { v[0].w = 0.f; }
 };
 
 // ------------------------------------------------------------------------
@@ -128,6 +132,7 @@ struct PBase {
 template <int D>
 struct PInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u;
     const float *rho, *m, *p;
@@ -189,6 +194,7 @@ struct PInteractions : PBase {
 template <int D, int MODE>
 struct PShepard : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *rho, *m;
@@ -227,6 +233,7 @@ struct PShepard : PBase {
 template <int D, bool VECOUT>
 struct PDeltaGrad : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
     const float *rho, *m, *p;
@@ -277,6 +284,7 @@ struct PDeltaGrad : PBase {
 template <int D>
 struct PLappCorr : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
     const float *rho, *m;
@@ -320,6 +328,7 @@ struct PLappCorr : PBase {
 template <int D>
 struct PMLS : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
     const float *rho, *m;
@@ -429,6 +438,7 @@ struct PSensors : PBase {
 template <int D>
 struct PBIeInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *normal, *u;
     const float* m;
@@ -1069,6 +1079,13 @@ struct PElasticBounce : PBase {
 template <int D, bool SHEP, bool FULL, bool LAPP>
 struct PFusedFluid : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool PAIR2 = true;
+    __device__ static void kill(float4* v)
+    {
+        v[0].w = 0.f;
+        if constexpr (SHEP)
+            v[2].x = 0.f;
+    }
     static constexpr int DIMS = D, NJ4 = SHEP ? 3 : 2;
     const void *r, *u;
     const float *rho, *m, *p;
