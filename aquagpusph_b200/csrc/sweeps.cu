@@ -1224,24 +1224,22 @@ neighs_kernel(const int* __restrict__ imove, uint32_t* __restrict__ n_neighs, ui
         n_neighs[i] = 0;
         return;
     }
+    // The three cells c-1, c, c+1 of an x row hold one contiguous run of the sorted list:
+    // its length comes from two searches instead of a walk over every candidate.
     const uint32_t c = __ldg(ll.icell + i);
     constexpr int KZ = (D == 3) ? 1 : 0;
     uint32_t n = 0;
-    for (int ci = -1; ci <= 1; ci++)
-        for (int cj = -1; cj <= 1; cj++)
-            for (int ck = -KZ; ck <= KZ; ck++) {
-                const uint32_t cell =
-                    c + (uint32_t)ci + (uint32_t)cj * ll.nx + (uint32_t)ck * ll.nx * ll.ny;
-                uint32_t j = __ldg(ll.ihoc + cell);
-                while (j < ll.N && __ldg(ll.icell + j) == cell) {
-                    n++;
-                    if (n >= limit) {
-                        n_neighs[i] = n;
-                        return;
-                    }
-                    j++;
-                }
-            }
+    for (int cj = -1; cj <= 1; cj++)
+        for (int ck = -KZ; ck <= KZ; ck++) {
+            const uint32_t lo = c - 1u + (uint32_t)cj * ll.nx + (uint32_t)ck * ll.nx * ll.ny;
+            const uint32_t b = min(min(__ldg(ll.ihoc + lo), __ldg(ll.ihoc + lo + 1u)),
+                                   __ldg(ll.ihoc + lo + 2u));
+            if (b < ll.N)
+                n += s3_run_end(ll.icell, b, ll.N, lo, 2u) - b;
+        }
+    // the reference counts one by one and stops as soon as the count reaches the limit
+    if (n >= limit && n)
+        n = max(limit, 1u);
     n_neighs[i] = n;
 }
 

@@ -223,8 +223,8 @@ def run_ours(a, rank, world, local_rank):
             sim.download(k, hout[k].dtype, out=hout[k])
         dt_now = float(sim.scalar("dt"))
         for k in outs:
-            if k in hin:
-                hin[k][...] = hout[k]   # next step starts from this step's result
+            if k in hin:   # next step starts from this step's result: swap the pinned buffers
+                hin[k], hout[k] = hout[k], hin[k]
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     e2e = N_all * a.steps / (e2e_ms * 1e-3)
