@@ -176,6 +176,10 @@ class Simulation:
         _chk(lib().aqh_array_info(self.h, name.encode(), C.byref(n), C.byref(eb)))
         return int(n.value), int(eb.value)
 
+    def has_array(self, name):
+        n, eb = C.c_size_t(), C.c_size_t()
+        return lib().aqh_array_info(self.h, name.encode(), C.byref(n), C.byref(eb)) == 0
+
     def download(self, name, dtype=np.float32, unsorted=False, out=None):
         n, eb = self.array_info(name)
         dt = np.dtype(dtype)

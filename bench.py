@@ -127,7 +127,9 @@ def run_ours(a, rank, world, local_rank):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     host.set_log_level(3)
     ov = {"iter_midpoint_max": a.maxiter} if a.maxiter > 0 else None
     if world > 1 or a.slab_pipeline:
@@ -230,18 +232,26 @@ def run_ours(a, rank, world, local_rank):
     e2e = N_all * a.steps / (e2e_ms * 1e-3)
     clocks.stop_flag = True
 
+    if dist is not None:
+        dist.barrier()   # last collective: what follows is rank 0's own post-processing
     if rank != 0:
         if dist is not None:
-            dist.barrier()
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (cfd/Interactions.cl::entry), timed alone
+    # ---- roofline of the dominant kernel, timed alone on the state the K steps left: the
+    # fused fluid sweep (cfd/Shepard.cl + cfd/Interactions.cl + cfd/deltaSPH.cl full/lapp in
+    # one pass -- the launch the pipeline's planner makes 3x per step), CUDA events on the
+    # context's stream
     pk, pk_kind = peaks()
     V = {}
+    delta_sph = sim.has_array("lap_p") and sim.has_array("lap_p_corr")
     for k, dt_ in (("imove", np.int32), ("r", np.float32), ("u", np.float32), ("rho", np.float32),
                    ("m", np.float32), ("p", np.float32), ("grad_p", np.float32),
-                   ("lap_u", np.float32), ("div_u", np.float32), ("icell", np.uint32),
+                   ("lap_u", np.float32), ("div_u", np.float32), ("shepard", np.float32),
+                   ("lap_p", np.float32), ("lap_p_corr", np.float32), ("icell", np.uint32),
                    ("ihoc", np.uint32)):
+        if k in ("lap_p", "lap_p_corr") and not delta_sph:
+            continue
         n_, eb = sim.array_info(k)
         V[k] = actx.wrap(lib_ptr(sim, k), (n_, eb // 4) if eb > 4 else (n_,), dt_)
     V["N"] = NA
@@ -253,32 +263,46 @@ def run_ours(a, rank, world, local_rank):
     V["n_pairs"] = n_pairs
     actx.launch("aqua/diag.cl", "count_pairs", V)
     pairs = int(n_pairs.get().astype(np.uint64).sum())
+    members = [("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry")]
+    if delta_sph:
+        members += [("cfd/deltaSPH.cl", "full"), ("cfd/deltaSPH.cl", "lapp")]
+    assert sim.fused_groups() >= 1, "the pipeline did not fuse the fluid sweeps"
     for _ in range(2):
-        actx.launch("cfd/Interactions.cl", "entry", V)
+        actx.launch_fused(members, V)
     k0, k1 = actx.event(), actx.event()
     reps = 5
     actx.record(k0)
     for _ in range(reps):
-        actx.launch("cfd/Interactions.cl", "entry", V)
+        actx.launch_fused(members, V)
     actx.record(k1)
     kms = actx.elapsed_ms(k0, k1) / reps
-    alg_bytes = 88.0 * NA         # Interactions 88 B/particle (3-D, 32-bit idx)
-    alg_flops = 52.0 * pairs      # 52 flop per true neighbour pair
+    # distinct arrays of the fused pass, 3-D, 32-bit indices: reads imove 4, r 16,
+    # u 16, rho 4, m 4, p 4, icell 4; writes grad_p 16, lap_u 16, div_u 4, shepard 4, lap_p 4,
+    # lap_p_corr 16 = 112 B/particle (the four stand-alone sweeps: 88 + 36 + 52 + 40 = 216)
+    alg_bytes = (112.0 if delta_sph else 92.0) * NA
+    # SURVEY 8(d) per true pair: Interactions 52 flop; with the shared |r_ij|, q and F(q) the
+    # Shepard, full and lapp members add 6 + 6 + 2
+    alg_flops = (66.0 if delta_sph else 58.0) * pairs
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "interactions_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "fused_traffic.json")
     if os.path.exists(tp):
         rec = json.load(open(tp))
         if rec.get("n_particles") == NA:   # ncu capture of this very workload
             traffic = rec.get("dram_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "sweep_kernel<PInteractions<3>> (cfd/Interactions.cl::entry)",
+    roof = {"bound": "hbm",
+            "kernel": "sweep3_kernel<PFusedFluid<3,...>> (" + " + ".join(m[0] + "::" + m[1] for m in members) + ")",
             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": traffic,
             "ms_per_launch": kms, "algorithmic_bytes": alg_bytes,
+            "launches_per_step": inner / a.steps,
             "fp32": {"algorithmic_flops": alg_flops, "pairs": pairs,
                      "achieved_tflops": alg_flops / (kms * 1e-3) / 1e12,
                      "nominal_peak_tflops_at_max_clock": 148 * 128 * 2 * 1.965e-3,
-                     "note": "the sweep is FP32-issue bound (530 flop/B vs ridge ~11.5), SURVEY 8(d)"}}
+                     "note": "neighbour sweeps are FP32-issue bound, not HBM bound (>500 flop/B "
+                             "against a ridge of ~11.5, SURVEY 8(d)): the HBM fraction is "
+                             "structurally a fraction of a per cent; fp32 is the figure that moves "
+                             "with kernel quality"}}
     del d, hh
     # ---- CPU baseline (oracle port), bounded sample
     threads = os.cpu_count() or 1
@@ -308,7 +332,6 @@ def run_ours(a, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     _ = dt_now
     if dist is not None:
-        dist.barrier()
         dist.destroy_process_group()
 
 

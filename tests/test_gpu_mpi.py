@@ -238,8 +238,11 @@ def test_dam_break_slabs_two_gpus_match_one_gpu():
     example pipeline on 2 GPUs (y slabs, halo + migration over NCCL, global dt, halo
     refreshed every midpoint sub-iteration: casegen.multi_device_fixes) against the same
     pipeline on 1 GPU, two steps of two sub-iterations.  Particles farther than the kernel
-    support from the cut never see a remote term: they must be bit-identical; next to the
-    cut the remote terms are added after the local ones (fp32 summation order)."""
+    support from the cut never see a remote term: with the order-preserving sweep engine
+    (AQC_SWEEP_ENGINE=2) they are bit-identical; the default engine sums a particle's pairs
+    in an order that depends on which particles share its CTA, so far from the cut the two
+    runs agree to fp32 rounding of the sums (a tenth of the tolerance next to the cut, where
+    the remote terms are added after the local ones)."""
     if not _two_gpus():
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     n_total, steps = 40000, 2
@@ -257,4 +260,9 @@ def test_dam_break_slabs_two_gpus_match_one_gpu():
             b = two[r][k].astype(np.float64)
             err = np.abs(a - b).max() / max(np.abs(a).max(), 1e-30)
             assert err <= tol, "rank %d field %s: rel err %.3e" % (r, k, err)
-            assert np.array_equal(one[k][rows][far], two[r][k][far]), "rank %d field %s far from the cut" % (r, k)
+            if os.environ.get("AQC_SWEEP_ENGINE") == "2":
+                assert np.array_equal(one[k][rows][far], two[r][k][far]), \
+                    "rank %d field %s far from the cut" % (r, k)
+            else:
+                errf = np.abs(a[far] - b[far]).max() / max(np.abs(a).max(), 1e-30)
+                assert errf <= 0.1 * tol, "rank %d field %s far from the cut: rel err %.3e" % (r, k, errf)
