@@ -1080,18 +1080,12 @@ template <int D, bool SHEP, bool FULL, bool LAPP>
 struct PFusedFluid : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool PAIR2 = true;
-    __device__ static void kill(float4* v)
-    {
-        v[0].w = 0.f;
-        if constexpr (SHEP)
-            v[2].x = 0.f;
-    }
-    static constexpr int DIMS = D, NJ4 = SHEP ? 3 : 2;
+    static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u;
     const float *rho, *m, *p;
     void *grad_p, *lap_u, *lap_p_corr;
     float *div_u, *shepard, *lap_p;
-    float cF, cW, eps2;
+    float cF, cW, cWF, eps2; // cWF = cW / cF
     struct IState {
         float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du, sh, cx, cy, cz, lp;
         bool fluid;
@@ -1121,8 +1115,6 @@ struct PFusedFluid : PBase {
         const float mj = __ldg(m + j), rj = __ldg(rho + j);
         o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * mj / rj);
         o[1] = make_float4(b.x, b.y, b.z, __ldg(p + j));
-        if constexpr (SHEP)
-            o[2] = make_float4(cW * mj / rj, 0.f, 0.f, 0.f);
     }
     __device__ bool test(const IState& s, const float4& A) const
     {
@@ -1137,7 +1129,7 @@ struct PFusedFluid : PBase {
         const float t = 2.f - q;
         if constexpr (SHEP) {
             const float t2 = t * t;
-            s.sh += (1.f + 2.f * q) * (t2 * t2) * row[2 * stride].x;
+            s.sh += (1.f + 2.f * q) * (t2 * t2) * (A.w * cWF); // cW m_j/rho_j from the staged cF m_j/rho_j
             if (!s.fluid)
                 return;
         }
@@ -1541,6 +1533,7 @@ template <int D, bool SHEP, bool FULL, bool LAPP> int run_fused_fluid(aqc_ctx* c
     }
     p.cF = Wend<D>::F * ctx->defs.CONF;
     p.cW = Wend<D>::W * ctx->defs.CONW;
+    p.cWF = p.cW / p.cF;
     p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
     return launch_sweep(ctx, p, ll);
 }
