@@ -66,6 +66,7 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     }
     cudaFree(ctx->sort_hist);
     cudaFree(ctx->minmax_dev);
+    cudaFree(ctx->cell_cls);
     cudaFreeHost(ctx->minmax_host);
     cudaFree(ctx->red_dev);
     cudaFreeHost(ctx->red_host);

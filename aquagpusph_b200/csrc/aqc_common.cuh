@@ -32,6 +32,10 @@ struct aqc_ctx {
     uint32_t* sort_hist = nullptr; // [256][nblocks] + [256] totals
     size_t sort_hist_cap = 0;
     uint32_t* minmax_dev = nullptr; // 8 ordered-uint keys
+    // per-cell mask of the particle classes present (sweep.cuh: aqc_cls_bit), rebuilt by the
+    // sweeps whose j set is a small class (boundary elements): cells without one are skipped
+    uint8_t* cell_cls = nullptr;
+    size_t cell_cls_cap = 0;
     float* minmax_host = nullptr;   // pinned, 8 floats
     // reduction scratch
     void* red_dev = nullptr; // partials

@@ -35,7 +35,33 @@ struct LLParams {
     const uint32_t* __restrict__ ihoc;
     uint32_t nx, ny, nz, nw; // n_cells (svec4)
     uint32_t N;
+    // optional: classes of the particles of every cell (bits of aqc_cls_bit) and the classes
+    // the kernel's j set is made of; a cell without any of them is not visited
+    const uint8_t* __restrict__ cls = nullptr;
+    uint32_t jmask = 0xFFu;
 };
+
+__host__ __device__ inline uint32_t aqc_cls_bit(int mv)
+{
+    return mv == 1 ? 1u : mv == 0 ? 2u : mv == -1 ? 4u : mv == -2 ? 8u : mv == -3 ? 16u : 32u;
+}
+
+// cls[c] |= class bit of every particle of cell c (cls zeroed before; bytes or-ed through
+// their 32-bit word, one atomic per run of equal (cell, class) inside a warp)
+static __global__ void cell_class_kernel(const int* __restrict__ imove, const uint32_t* __restrict__ icell,
+                                         uint32_t N, uint32_t nw, uint8_t* __restrict__ cls)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const uint32_t c = __ldg(icell + i);
+    if (c >= nw)
+        return;
+    const uint32_t bit = aqc_cls_bit(__ldg(imove + i));
+    if (i > 0 && (threadIdx.x & 31) && __ldg(icell + i - 1) == c && aqc_cls_bit(__ldg(imove + i - 1)) == bit)
+        return; // the previous lane does it
+    atomicOr(reinterpret_cast<uint32_t*>(cls) + (c >> 2), bit << (8u * (c & 3u)));
+}
 
 constexpr float AQC_FAR = 3.0e38f; // staged position of an excluded j
 
@@ -90,6 +116,8 @@ sweep_kernel(const P p, const LLParams ll)
                 for (int ck = -KZ; ck <= KZ; ck++) {
                     const uint32_t cell = c + (uint32_t)ci + (uint32_t)cj * ll.nx +
                                           (uint32_t)ck * ll.nx * ll.ny;
+                    if (ll.cls && !(ll.cls[cell] & ll.jmask))
+                        continue;
                     uint32_t j0 = __ldg(ll.ihoc + cell);
                     while (j0 < ll.N) {
                         const uint32_t jj = j0 + lane;
@@ -253,6 +281,8 @@ sweep2_kernel(const P p, const LLParams ll)
                 for (int cz = -KZ; cz <= KZ; cz++) {
                     const uint32_t cell = c + (uint32_t)cx + (uint32_t)cy * ll.nx +
                                           (uint32_t)cz * ll.nx * ll.ny;
+                    if (ll.cls && !(ll.cls[cell] & ll.jmask))
+                        continue;
                     uint32_t j0 = __ldg(ll.ihoc + cell);
                     while (j0 < ll.N) {
                         const uint32_t jj = j0 + lane;
@@ -435,11 +465,24 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             const uint32_t row = tid / nparts, part = tid - row * nparts;
             const int cy = (int)(row % 3u) - 1, cz = (P::DIMS == 3) ? (int)(row / 3u) - 1 : 0;
             const uint32_t base = c0 + (uint32_t)cy * ll.nx + (uint32_t)cz * ll.nx * ll.ny - 1u;
-            const uint32_t lo = base + 2u * part;
-            const uint32_t wid = (2u * part + 1u < len) ? 1u : 0u;
-            uint32_t b = __ldg(ll.ihoc + lo);
-            if (wid)
+            uint32_t lo = base + 2u * part;
+            uint32_t wid = (2u * part + 1u < len) ? 1u : 0u;
+            bool has0 = true, has1 = wid != 0;
+            if (ll.cls) { // cells without any particle of the kernel's j classes are left out
+                has0 = (ll.cls[lo] & ll.jmask) != 0;
+                has1 = has1 && (ll.cls[lo + 1u] & ll.jmask) != 0;
+            }
+            uint32_t b = ll.N;
+            if (has0)
+                b = __ldg(ll.ihoc + lo);
+            if (has1)
                 b = min(b, __ldg(ll.ihoc + lo + 1u));
+            if (!has0) {
+                lo += 1u;
+                wid = 0u;
+            } else if (!has1) {
+                wid = 0u;
+            }
             uint32_t en = b;
             if (b < ll.N)
                 en = s3_run_end(ll.icell, b, ll.N, lo, wid);
@@ -448,7 +491,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             e_begin[tid] = b;
             e_end[tid] = en;
             e_lo[tid] = lo;
-            e_rel[tid] = 2u * part; // x offset of cell lo relative to c0, plus one
+            e_rel[tid] = lo - base; // x offset of cell lo relative to c0, plus one
             if (en > b)
                 atomicMax(&s_maxk, (en - b + 31u) / 32u);
         }
@@ -669,8 +712,28 @@ int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
 
 template <class P>
-static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll)
+static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
 {
+    LLParams ll = ll_in;
+    if constexpr (P::JCLS != 0) {
+        // the j set is a small class (boundary elements): rebuild the per-cell class mask
+        // (imove may have changed since the last launch) and skip the cells without one
+        const size_t need = ((size_t)ll.nw + 3) & ~(size_t)3;
+        if (need > ctx->cell_cls_cap) {
+            if (ctx->cell_cls)
+                cudaFree(ctx->cell_cls);
+            ctx->cell_cls = nullptr;
+            ctx->cell_cls_cap = 0;
+            AQC_CUDA(ctx, cudaMalloc(&ctx->cell_cls, need + need / 4));
+            ctx->cell_cls_cap = need + need / 4;
+        }
+        AQC_CUDA(ctx, cudaMemsetAsync(ctx->cell_cls, 0, need, ctx->stream));
+        cell_class_kernel<<<aqc_blocks(ll.N, 256), 256, 0, ctx->stream>>>(p.imove, ll.icell, ll.N, ll.nw,
+                                                                         ctx->cell_cls);
+        AQC_LAUNCH_CHECK(ctx);
+        ll.cls = ctx->cell_cls;
+        ll.jmask = P::JCLS;
+    }
     if constexpr (P::SPHERE) {
         if (aqc_sweep_engine() == 3 && !P::SPARSE_I) {
             const int K = aqc_sweep_ring(P::NJ4);

@@ -121,6 +121,9 @@ struct PBase {
     // kernels whose i particles are few and scattered (sensors, boundary elements) keep
     // the per-warp engine: a CTA-wide walk for a handful of lanes does not pay
     static constexpr bool SPARSE_I = false;
+    // classes (aqc_cls_bit) the j particles belong to when they are a small minority (boundary
+    // elements): the launcher then builds a per-cell class mask and cells without one are skipped
+    static constexpr uint32_t JCLS = 0;
     // v3 engine: two hits per body iteration.  Needs kill() to zero every weight of a
     // staged row so that body() adds exactly +-0 for it.
     static constexpr bool PAIR2 = false;
@@ -438,6 +441,7 @@ struct PSensors : PBase {
 template <int D>
 struct PBIeInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr uint32_t JCLS = 16u;
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *normal, *u;
@@ -526,6 +530,7 @@ struct PBIePBoundary : PBase {
 template <int D>
 struct PBIeElasticBounce : PBase {
     static constexpr bool SPHERE = false;
+    static constexpr uint32_t JCLS = 16u;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r_in, *normal, *u_in;
     const float* m;
@@ -601,6 +606,7 @@ struct PBIeElasticBounce : PBase {
 template <int D>
 struct PBIePST : PBase {
     static constexpr bool SPHERE = false;
+    static constexpr uint32_t JCLS = 16u;
     static constexpr int DIMS = D, NJ4 = 2;
     void* r;
     const void* normal;
@@ -659,6 +665,7 @@ struct PBIePST : PBase {
 template <int D>
 struct PMpiGamma : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
     static constexpr int DIMS = D, NJ4 = 1;
     const void *r, *mpi_r;
     const float *mpi_rho, *mpi_m;
@@ -693,6 +700,7 @@ struct PMpiGamma : PBase {
 template <int D>
 struct PMpiInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;
     const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
@@ -790,6 +798,7 @@ template <> __device__ __forceinline__ float kernelS_D<3>(float d, float t, floa
 template <int D>
 struct PBIShepard : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr uint32_t JCLS = 16u;
     static constexpr int DIMS = D, NJ4 = 4;
     const void *r, *normal, *tangent, *binormal;
     const float* m;
@@ -946,6 +955,7 @@ struct PBIInterpolation : PBase {
 template <int D>
 struct PBIInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr uint32_t JCLS = 16u;
     static constexpr int DIMS = D, NJ4 = 3;
     const void *r, *normal, *u;
     const float *rho, *m, *p;
@@ -1000,6 +1010,7 @@ struct PBIInteractions : PBase {
 template <int D>
 struct PElasticBounce : PBase {
     static constexpr bool SPHERE = false;
+    static constexpr uint32_t JCLS = 8u | 16u;
     static constexpr int DIMS = D, NJ4 = 4;
     const void *r, *normal;
     void *u, *dudt;

@@ -25,8 +25,15 @@ void Tool::execute()
 {
     if (_once && _n_iters > 0)
         return;
+    // AQUA_PROFILE_SYNC=1: per-tool device + host time (the stream is drained around every
+    // tool, like the reference's per-tool Profile samples; Tool.cpp:296-310) -- diagnostics only
+    static const bool prof_sync = getenv("AQUA_PROFILE_SYNC") != nullptr;
+    if (prof_sync)
+        aqc_sync(_C->ctx());
     const auto t0 = std::chrono::steady_clock::now();
     _execute();
+    if (prof_sync)
+        aqc_sync(_C->ctx());
     _elapsed_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     _n_iters++;
 }
