@@ -398,8 +398,9 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     const uint32_t NS = (uint32_t)K * W; // ring slots
     float4* const sT = smem3;            // [2][W][32] packed test layout of the tiles of two rounds
     float4* const sJ = sT + 2 * W * 32;  // [NS][SLOT4] j rows
-    const uint32_t NM = NS - W;          // mask slots: the round being staged has none yet
-    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NM][32] hit masks
+    const uint32_t NM = NS - W;          // FIFO entries per lane: the round being staged has no masks yet
+    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NM][32] masks, then
+                                                                               // [W][NM][32] slot bytes
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
     __shared__ uint32_t t_cnt[2][W], t_rel[2][W], t_n1[2][W];
     __shared__ uint32_t s_ball[W], s_c0, s_span, s_last, s_maxk;
@@ -417,6 +418,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
     const float cut2f = p.cut2 * 1.0001f;
     uint32_t* const Mw = sM + (size_t)warp * NM * 32 + lane;
+    uint8_t* const Sw = reinterpret_cast<uint8_t*>(sM + (size_t)W * NM * 32) + (size_t)warp * NM * 32 + lane;
     const uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ);
 
     bool pending = active;
@@ -510,21 +512,18 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         const float fz = (P::DIMS == 3) ? -2.f * (st.z - s_o[2]) : 0.f;
         const float fc = 0.25f * fmaf(fz, fz, fmaf(fy, fy, fx * fx)) - cut2f;
 
-        // Per-lane FIFO over the tiles in the ring.  Bit b of nz: this lane has hits in the
-        // tile at ring position `oldest + b` (bits 0..W-1 = the oldest round); cur = the
-        // unconsumed hits of the tile it is working on (candidate k at bit 31 - k), curb that
-        // tile's bit, crow the shared-window address of its last row slot.
-        uint32_t nz = 0, cur = 0, curb = 0, crow = 0;
-        uint32_t oldest = 0, oldestm = 0; // ring slot / mask slot of bit 0
+        // Per-lane FIFO of (hit mask, ring slot) entries, one per tile in which the lane has
+        // hits, appended by the filter: at most NM are alive (the tiles of K - 1 rounds), so
+        // qr == qw means empty.  cur = the unconsumed hits of the tile the lane is working on
+        // (candidate k at bit 31 - k), cslot its ring slot, crow the shared-window address of
+        // its last row slot.
+        uint32_t qr = 0, qw = 0, cur = 0, cslot = 0, crow = 0;
 
-        auto pick = [&]() { // cur == 0 && nz != 0: take the next tile with hits
-            curb = __ffs(nz) - 1;
-            nz &= nz - 1;
-            uint32_t s = oldest + curb, sm = oldestm + curb;
-            s = (s >= NS) ? s - NS : s;
-            sm = (sm >= NM) ? sm - NM : sm;
-            cur = Mw[sm * 32];
-            crow = sJ_a + s * (SLOT4 * 16) + 31 * 16;
+        auto pick = [&]() { // cur == 0 && qr != qw: take the next tile with hits
+            cur = Mw[qr * 32];
+            cslot = Sw[qr * 32];
+            qr = (qr + 1 == NM) ? 0u : qr + 1;
+            crow = sJ_a + cslot * (SLOT4 * 16) + 31 * 16;
         };
         auto body1 = [&]() { // cur != 0: the next hit of this lane
             uint32_t f;
@@ -537,7 +536,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 v[q] = lds128(a + q * 512);
             if (p.test(st, v[0]))
                 p.body(st, v, 1);
-            if (!cur && nz)
+            if (!cur && qr != qw)
                 pick();
         };
         // Two hits per iteration (P::PAIR2): both rows are loaded first and both bodies run
@@ -550,7 +549,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(cur));
             cur ^= 1u << f;
             const uint32_t a1 = crow - (f << 4);
-            if (!cur && nz)
+            if (!cur && qr != qw)
                 pick();
             const bool two = cur != 0;
             uint32_t a2 = a1;
@@ -571,7 +570,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 P::kill(v2);
             p.body(st, v1, 1);
             p.body(st, v2, 1);
-            if (!cur && nz)
+            if (!cur && qr != qw)
                 pick();
         };
         auto consume = [&]() {
@@ -642,20 +641,15 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         if (nrounds)
             stage(0, 0);
         uint32_t rk = 0;  // ring round that holds round r (r % K)
-        uint32_t rkm = 0; // mask round of round r (r % (K - 1))
         for (uint32_t r = 0; r < nrounds; r++) {
-            uint32_t nb = r * W; // bit of the round's first tile
+            const uint32_t rk1 = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
             if (r + 1 >= (uint32_t)K) {
-                while (__any_sync(0xffffffffu, (cur != 0 && curb < W) || (nz & ((1u << W) - 1u))))
+                // ring round rk1 (it holds round r + 1 - K) is recycled next: its hits are the
+                // oldest of every FIFO, a lane is done with them when its tile is a newer one
+                while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rk1))
                     consume();
-                nz >>= W;
-                curb -= W;
-                oldest = (oldest + W == NS) ? 0u : oldest + W;
-                oldestm = (oldestm + W == NM) ? 0u : oldestm + W;
-                nb = (K - 2) * W;
             }
             __syncthreads();
-            const uint32_t rk1 = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
             if (r + 1 < nrounds)
                 stage(r + 1, rk1);
             // ---- filter: record the hit masks of the round's tiles
@@ -683,11 +677,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                         m = test_tile<4>(T, X2, Y2, Z2, C2);
                     m &= okm;
                     if (m) {
-                        Mw[(rkm * W + w2) * 32] = m;
-                        nz |= 1u << (nb + w2);
+                        Mw[qw * 32] = m;
+                        Sw[qw * 32] = (uint8_t)(rk * W + w2);
+                        qw = (qw + 1 == NM) ? 0u : qw + 1;
                     }
                 }
-                if (!cur && nz)
+                if (!cur && qr != qw)
                     pick();
                 // ---- bodies, while every member lane of the warp has one pending
                 while (__ballot_sync(mine_w, cur != 0) == mine_w) {
@@ -698,7 +693,6 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 }
             }
             rk = rk1;
-            rkm = (rkm + 2 == (uint32_t)K) ? 0u : rkm + 1;
         }
         while (__any_sync(0xffffffffu, cur != 0))
             consume();
@@ -739,7 +733,7 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
             const int K = aqc_sweep_ring(P::NJ4);
             const size_t NS = (size_t)K * S3_WARPS;
             const size_t smem = (2 * S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
-                                S3_WARPS * (NS - S3_WARPS) * 32 * sizeof(uint32_t);
+                                S3_WARPS * (NS - S3_WARPS) * 32 * (sizeof(uint32_t) + 1);
             static size_t configured = 0; // per instantiation
             if (smem > configured) {
                 AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P>,
