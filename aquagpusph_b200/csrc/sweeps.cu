@@ -755,6 +755,81 @@ struct PMpiInteractions : PBase {
     }
 };
 
+// cfd/MPI.cl interactions + gamma in one pass over the remote (halo) list: the two kernels
+// share i set (gamma's is the wider one), candidates and geometry.  Same expressions as the
+// members; the Shepard weight cW m_j/rho_j is derived from the staged cF m_j/rho_j.
+template <int D>
+struct PMpiFused : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *u, *mpi_r, *mpi_u;
+    const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
+    void *grad_p, *lap_u;
+    float *div_u, *shepard;
+    float cF, cWF, eps2;
+    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du, sh; bool fluid; };
+    __device__ bool i_active(int mv) const { return !((mv < -3) || ((mv > 0) && (mv != 1))); }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+        s.fluid = __ldg(imove + i) == 1;
+        s.ux = s.uy = s.uz = s.p = 0.f;
+        if (s.fluid) {
+            const float4 b = ldvec<D>(u, i);
+            s.ux = b.x; s.uy = b.y; s.uz = b.z;
+            s.p = __ldg(p + i);
+        }
+        s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = s.sh = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j), b = ldvec<D>(mpi_u, j);
+        o[0] = make_float4(a.x, a.y, a.z, cF * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(mpi_p + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float q = q_of(d2, invH);
+        const float t = 2.f - q, t2 = t * t;
+        s.sh += (1.f + 2.f * q) * (t2 * t2) * (A.w * cWF);
+        if (!s.fluid)
+            return;
+        const float4 B = row[stride];
+        const float fr = t2 * (t * A.w);
+        float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
+        if constexpr (D == 3)
+            udr += (B.z - s.uz) * dz;
+        const float a = (s.p + B.w) * fr;
+        const float b0 = udr * fr;
+        const float b = b0 * rcp_fast(d2 + eps2);
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+        s.du += b0;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        shepard[i] += s.sh;
+        if (!s.fluid)
+            return;
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float cl = Wend<D>::CLEARY * ir;
+        const float4 g0 = ldvec_rw<D>(grad_p, i), l0 = ldvec_rw<D>(lap_u, i);
+        stvec_xyz<D>(grad_p, i, g0.x + s.gx * ir, g0.y + s.gy * ir, g0.z + s.gz * ir);
+        stvec_xyz<D>(lap_u, i, l0.x + s.lx * cl, l0.y + s.ly * cl, l0.z + s.lz * cl);
+        div_u[i] += s.du * rho_i;
+    }
+};
+
 // ------------------------------------------------------------------------
 // Boundary integrals, cfd/Boundary/BI/*.cl (2-D dam break, BASELINE config 1)
 
@@ -1553,6 +1628,27 @@ template <bool SHEP, bool FULL, bool LAPP> int l_fused_fluid(aqc_ctx* c, void* c
     return c->defs.dims == 3 ? run_fused_fluid<3, SHEP, FULL, LAPP>(c, a)
                              : run_fused_fluid<2, SHEP, FULL, LAPP>(c, a);
 }
+template <int D> int run_mpi_fused(aqc_ctx* ctx, void* const* a)
+{
+    // interactions: imove r u rho p mpi_r mpi_u mpi_rho mpi_p mpi_m grad_p lap_u div_u N
+    //               icell mpi_icell mpi_ihoc n_cells (18); gamma: imove r rho m mpi_r mpi_rho
+    //               mpi_m shepard N icell mpi_icell mpi_ihoc n_cells (13)
+    void* const* g = a + 18;
+    PMpiFused<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.p = (const float*)a[4];
+    p.mpi_r = a[5]; p.mpi_u = a[6]; p.mpi_rho = (const float*)a[7]; p.mpi_p = (const float*)a[8];
+    p.mpi_m = (const float*)a[9]; p.grad_p = a[10]; p.lap_u = a[11]; p.div_u = (float*)a[12];
+    p.shepard = (float*)g[7];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.cWF = (Wend<D>::W * ctx->defs.CONW) / p.cF;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, make_ll_remote(a, 14, aqc_scalar<uint32_t>(a, 13)));
+}
+int l_mpi_fused(aqc_ctx* c, void* const* a)
+{
+    return c->defs.dims == 3 ? run_mpi_fused<3>(c, a) : run_mpi_fused<2>(c, a);
+}
 #define K_SHEP "cfd/Shepard.cl::entry"
 #define K_INTER "cfd/Interactions.cl::entry"
 #define K_FULL "cfd/deltaSPH.cl::full"
@@ -1563,6 +1659,7 @@ const std::vector<FusedEntry>& fused_table()
         { { K_SHEP, K_INTER, K_FULL, K_LAPP }, l_fused_fluid<true, true, true> },
         { { K_SHEP, K_INTER }, l_fused_fluid<true, false, false> },
         { { K_INTER, K_FULL, K_LAPP }, l_fused_fluid<false, true, true> },
+        { { "cfd/MPI.cl::interactions", "cfd/MPI.cl::gamma" }, l_mpi_fused },
     };
     return t;
 }

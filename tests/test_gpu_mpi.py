@@ -104,8 +104,19 @@ def test_mpi_kernels_match_reference_scripts(oracle, dims):
     dev.update(mpi_icell=icell, mpi_ihoc=ihoc, mpi_id_sorted=invp)
     both("cfd/MPI.cl", "sort", outs=("mpi_iset", "mpi_r", "mpi_u", "mpi_rho", "mpi_m"))
     both("cfd/MPI.cl", "eos", outs=("mpi_p",))
+    pre = {k: dev[k].get() for k in ("shepard", "grad_p", "lap_u", "div_u")}
     both("cfd/MPI.cl", "gamma", n=N, exact=False, outs=("shepard",))
     both("cfd/MPI.cl", "interactions", n=N, exact=False, outs=("grad_p", "lap_u", "div_u"))
+    # the fused remote sweep (interactions + gamma in one pass, what the pipeline launches)
+    # must add the same terms as its members
+    sep = {k: dev[k].get() for k in pre}
+    for k, v in pre.items():
+        dev[k].set(v)
+    ctx.launch_fused([("cfd/MPI.cl", "interactions"), ("cfd/MPI.cl", "gamma")], dev)
+    for k in pre:
+        a, b = sep[k].astype(np.float64), dev[k].get().astype(np.float64)
+        assert np.abs(a - pre[k]).max() > 0, k
+        assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), ("fused remote sweep", k)
     ctx.close()
 
 
