@@ -26,7 +26,7 @@ SYMBOLS = [
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
-    "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows",
+    "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2

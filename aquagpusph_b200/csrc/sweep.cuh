@@ -709,6 +709,8 @@ template <class P>
 static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
 {
     LLParams ll = ll_in;
+    if (ll.N == 0)
+        return AQC_OK; // nothing to do (a zero-sized grid is a launch error)
     if constexpr (P::JCLS != 0) {
         // the j set is a small class (boundary elements): rebuild the per-cell class mask
         // (imove may have changed since the last launch) and skip the cells without one

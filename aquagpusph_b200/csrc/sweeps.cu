@@ -17,13 +17,20 @@
 
 // Engine selection for the SPHERE policies (A/B measurements; both engines are
 // CUDA): AQC_SWEEP_ENGINE=2 keeps the immediate-body engine, default 3 = deferred.
+static int g_sweep_engine = 0;
 int aqc_sweep_engine()
 {
-    static const int e = [] {
+    if (!g_sweep_engine) {
         const char* s = getenv("AQC_SWEEP_ENGINE");
-        return (s && atoi(s) == 2) ? 2 : 3;
-    }();
-    return e;
+        g_sweep_engine = (s && atoi(s) == 2) ? 2 : 3;
+    }
+    return g_sweep_engine;
+}
+extern "C" int aqc_sweep_engine_select(int engine)
+{
+    if (engine == 2 || engine == 3)
+        g_sweep_engine = engine;
+    return aqc_sweep_engine();
 }
 // Ring rounds of the v3 engine (8 tiles each): shared memory per CTA =
 // 8 KB + K * 8 * NJ4 * 512 + (K - 1) * 8 * 1024 bytes; the deferral window is (K - 1) * 8 tiles

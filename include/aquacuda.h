@@ -170,6 +170,11 @@ enum { AQC_ROWS_FLUID = 1, AQC_ROWS_SENSOR = 2, AQC_ROWS_BOUNDARY = 4, AQC_ROWS_
 int aqc_kernel_write_rows(int kernel_id);
 int aqc_fused_read_rows(int fused_id);
 int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs);
+/* Neighbour-sweep engine of the kernel-support sweeps (both are CUDA):
+ * 3 = CTA-shared tiles with deferred pair bodies (default), 2 = per-warp tiles, bodies in the
+ * reference's visiting order.  Initial value from AQC_SWEEP_ENGINE.  Returns the engine in
+ * use after the call; engine = 0 only queries.  For A/B measurements and order-sensitive tests. */
+int aqc_sweep_engine_select(int engine);
 
 /* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI
  * rank/size queries and wrappers (AuxiliarMethods.cpp:388-516) and the MPISync

@@ -29,6 +29,44 @@ def test_sweeps_match_oracle(oracle, dims, n, hfac):
     assert np.abs(ref["lap_p"]).max() > 0 and (ref["n_neighs"] > 0).any()
 
 
+@pytest.mark.parametrize("dims,n,hfac,scale", [(3, 10, 3.0, 3.5), (3, 12, 2.0, 0.45), (2, 50, 3.0, 4.0),
+                                               (2, 60, 4.0, 0.3)])
+def test_sweeps_sparse_and_dense_cells(oracle, dims, n, hfac, scale):
+    """The same kernels on stretched positions (0-2 particles per cell: every warp spans many
+    cells and several group passes) and on compressed ones (thousands of candidates per cell:
+    long runs, many ring rounds): the CTA-shared walk must still visit exactly the
+    reference's pairs."""
+    case = cases.dam_break(dims, n, hfac)
+    for k in ("r",):
+        case[k] = (case[k] * np.float32(scale)).astype(np.float32)
+    case["domain_min"] = (np.asarray(case["domain_min"]) * np.float32(scale) - 1).astype(np.float32)
+    case["domain_max"] = (np.asarray(case["domain_max"]) * np.float32(scale) + 1).astype(np.float32)
+    s = pipeline.oracle_linklist_and_sort(case)
+    ref = pipeline.oracle_sweeps(s)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    got = pipeline.cuda_sweeps(ctx, s)
+    ctx.close()
+    # sums of thousands of terms in another order: twice the usual absolute band
+    bad = [r for r in pipeline.compare(ref, got) if not r[3] and r[1] > 5e-6 * r[2]]
+    assert not bad, "\n".join("%s: max err %.3e (scale %.3e)" % r[:3] for r in bad)
+    # the pair SET itself, exactly: fluid neighbours within the support counted by the
+    # default engine and by the order-preserving per-warp engine
+    L = _lib.lib()
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    st = pipeline.CudaState(ctx, s)
+    counts = []
+    try:
+        for eng in (3, 2):
+            assert L.aqc_sweep_engine_select(eng) == eng
+            st.v["n_pairs"] = ctx.zeros(st.v["N"], np.uint32)
+            st.run("aqua/diag.cl", "count_pairs")
+            counts.append(st.v["n_pairs"].get())
+    finally:
+        L.aqc_sweep_engine_select(3)
+    ctx.close()
+    assert counts[0].sum() > 0 and np.array_equal(counts[0], counts[1])
+
+
 @pytest.mark.parametrize("dims,n,hfac", [(3, 14, 2.0), (2, 60, 3.0)])
 def test_fused_fluid_sweep_equals_its_members(oracle, dims, n, hfac):
     """aqc_launch_fused: Shepard + Interactions + deltaSPH full + lapp in one pass must give
