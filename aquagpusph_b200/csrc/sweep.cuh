@@ -417,9 +417,14 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         p.load_i(st, i);
     constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
     const float cut2f = p.cut2 * 1.0001f;
-    uint32_t* const Mw = sM + (size_t)warp * NM * 32 + lane;
-    uint8_t* const Sw = reinterpret_cast<uint8_t*>(sM + (size_t)W * NM * 32) + (size_t)warp * NM * 32 + lane;
-    const uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ);
+    // shared-window addresses of this lane's FIFO (masks, slot bytes) and of the last row
+    // slot of ring tile 0, kept opaque so that they stay in registers instead of being
+    // recomputed from tid at every use
+    uint32_t Mw_a = (uint32_t)__cvta_generic_to_shared(sM + (size_t)warp * NM * 32 + lane);
+    uint32_t Sw_a = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint8_t*>(sM + (size_t)W * NM * 32) +
+                                                       (size_t)warp * NM * 32 + lane);
+    uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ) + 31 * 16;
+    asm volatile("" : "+r"(Mw_a), "+r"(Sw_a), "+r"(sJ_a));
 
     bool pending = active;
     for (;;) {
@@ -520,10 +525,10 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         uint32_t qr = 0, qw = 0, cur = 0, cslot = 0, crow = 0;
 
         auto pick = [&]() { // cur == 0 && qr != qw: take the next tile with hits
-            cur = Mw[qr * 32];
-            cslot = Sw[qr * 32];
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(Mw_a + qr * 128) : "memory");
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cslot) : "r"(Sw_a + qr * 32) : "memory");
             qr = (qr + 1 == NM) ? 0u : qr + 1;
-            crow = sJ_a + cslot * (SLOT4 * 16) + 31 * 16;
+            crow = sJ_a + cslot * (SLOT4 * 16);
         };
         auto body1 = [&]() { // cur != 0: the next hit of this lane
             uint32_t f;
@@ -677,8 +682,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                         m = test_tile<4>(T, X2, Y2, Z2, C2);
                     m &= okm;
                     if (m) {
-                        Mw[qw * 32] = m;
-                        Sw[qw * 32] = (uint8_t)(rk * W + w2);
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(Mw_a + qw * 128), "r"(m) : "memory");
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(Sw_a + qw * 32), "r"(rk * W + w2) : "memory");
                         qw = (qw + 1 == NM) ? 0u : qw + 1;
                     }
                 }
