@@ -398,7 +398,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     const uint32_t NS = (uint32_t)K * W; // ring slots
     float4* const sT = smem3;            // [2][W][32] packed test layout of the tiles of two rounds
     float4* const sJ = sT + 2 * W * 32;  // [NS][SLOT4] j rows
-    const uint32_t NM = NS - W;          // FIFO entries per lane: the round being staged has no masks yet
+    uint32_t NM = NS - W;                // FIFO entries per lane: the round being staged has no masks yet
+    asm volatile("" : "+r"(NM));         // (opaque: kept in a register, not recomputed from K)
     uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NM][32] masks, then
                                                                                // [W][NM][32] slot bytes
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
