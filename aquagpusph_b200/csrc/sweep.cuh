@@ -709,6 +709,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
 }
 
 int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
+bool aqc_sweep_engine_forced(); // chosen explicitly (environment or aqc_sweep_engine_select)
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
 
 template <class P>
@@ -737,7 +738,11 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         ll.jmask = P::JCLS;
     }
     if constexpr (P::SPHERE) {
-        if (aqc_sweep_engine() == 3 && !P::SPARSE_I) {
+        // 2-D sweeps have ~20x less work per particle: below ~1 M particles the CTA-wide
+        // set-up of v3 does not pay (measured: 2-D dam break, 0.38 M particles, 1.44 vs 1.20 ms
+        // per step; 7.4 M: 12.8 vs 15.3)
+        const bool small2d = (P::DIMS == 2) && ll.N < (1u << 20) && !aqc_sweep_engine_forced();
+        if (aqc_sweep_engine() == 3 && !P::SPARSE_I && !small2d) {
             const int K = aqc_sweep_ring(P::NJ4);
             const size_t NS = (size_t)K * S3_WARPS;
             const size_t smem = (2 * S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +

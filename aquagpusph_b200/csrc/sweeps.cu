@@ -18,18 +18,30 @@
 // Engine selection for the SPHERE policies (A/B measurements; both engines are
 // CUDA): AQC_SWEEP_ENGINE=2 keeps the immediate-body engine, default 3 = deferred.
 static int g_sweep_engine = 0;
+static bool g_sweep_forced = false;
 int aqc_sweep_engine()
 {
     if (!g_sweep_engine) {
         const char* s = getenv("AQC_SWEEP_ENGINE");
+        g_sweep_forced = s && (atoi(s) == 2 || atoi(s) == 3);
         g_sweep_engine = (s && atoi(s) == 2) ? 2 : 3;
     }
     return g_sweep_engine;
 }
+bool aqc_sweep_engine_forced()
+{
+    aqc_sweep_engine();
+    return g_sweep_forced;
+}
 extern "C" int aqc_sweep_engine_select(int engine)
 {
-    if (engine == 2 || engine == 3)
+    if (engine == 2 || engine == 3) {
         g_sweep_engine = engine;
+        g_sweep_forced = true;
+    } else if (engine < 0) { // back to the automatic choice (environment, then size heuristics)
+        g_sweep_engine = 0;
+        g_sweep_forced = false;
+    }
     return aqc_sweep_engine();
 }
 // Ring rounds of the v3 engine (8 tiles each): shared memory per CTA =

@@ -173,7 +173,9 @@ int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs);
 /* Neighbour-sweep engine of the kernel-support sweeps (both are CUDA):
  * 3 = CTA-shared tiles with deferred pair bodies (default), 2 = per-warp tiles, bodies in the
  * reference's visiting order.  Initial value from AQC_SWEEP_ENGINE.  Returns the engine in
- * use after the call; engine = 0 only queries.  For A/B measurements and order-sensitive tests. */
+ * use after the call; engine = 0 only queries, engine < 0 returns to the automatic choice (the
+ * environment, else v3 except for 2-D problems below ~1 M particles, where the per-warp engine
+ * is faster).  For A/B measurements and order-sensitive tests. */
 int aqc_sweep_engine_select(int engine);
 
 /* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI

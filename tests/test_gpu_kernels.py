@@ -13,13 +13,20 @@ from aquagpusph_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("engine", [3, 2])
 @pytest.mark.parametrize("dims,n,hfac", [(3, 14, 2.0), (2, 60, 3.0), (3, 10, 3.0), (2, 40, 4.0)])
-def test_sweeps_match_oracle(oracle, dims, n, hfac):
+def test_sweeps_match_oracle(oracle, dims, n, hfac, engine):
+    """engine 3 = CTA-shared tiles with deferred bodies (the default above ~1 M particles in
+    2-D, always in 3-D), engine 2 = per-warp tiles in the reference's visiting order."""
     case = cases.dam_break(dims, n, hfac)
     s = pipeline.oracle_linklist_and_sort(case)
     ref = pipeline.oracle_sweeps(s)
     ctx = _lib.Context(0, dims=dims, h=case["h"])
-    got = pipeline.cuda_sweeps(ctx, s)
+    try:
+        assert _lib.lib().aqc_sweep_engine_select(engine) == engine
+        got = pipeline.cuda_sweeps(ctx, s)
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
     ctx.close()
     rep = pipeline.compare(ref, got)
     bad = [r for r in rep if not r[3]]
@@ -44,7 +51,11 @@ def test_sweeps_sparse_and_dense_cells(oracle, dims, n, hfac, scale):
     s = pipeline.oracle_linklist_and_sort(case)
     ref = pipeline.oracle_sweeps(s)
     ctx = _lib.Context(0, dims=dims, h=case["h"])
-    got = pipeline.cuda_sweeps(ctx, s)
+    try:
+        _lib.lib().aqc_sweep_engine_select(3)
+        got = pipeline.cuda_sweeps(ctx, s)
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
     ctx.close()
     # sums of thousands of terms in another order: twice the usual absolute band
     bad = [r for r in pipeline.compare(ref, got) if not r[3] and r[1] > 5e-6 * r[2]]
@@ -62,7 +73,7 @@ def test_sweeps_sparse_and_dense_cells(oracle, dims, n, hfac, scale):
             st.run("aqua/diag.cl", "count_pairs")
             counts.append(st.v["n_pairs"].get())
     finally:
-        L.aqc_sweep_engine_select(3)
+        L.aqc_sweep_engine_select(-1)
     ctx.close()
     assert counts[0].sum() > 0 and np.array_equal(counts[0], counts[1])
 
