@@ -368,6 +368,38 @@ constexpr int S3_THREADS = S3_WARPS * 32;
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 
+// mbarrier (shared-memory arrive/wait barrier) used as the round barrier of the v3 engine: a
+// warp that has arrived keeps consuming its pending hits while it polls, instead of idling
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity) // may suspend the thread
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
 // first j in [b, N) whose cell (relative to lo) is beyond wid; icell is sorted
 __device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icell, uint32_t b,
                                                uint32_t N, uint32_t lo, uint32_t wid)
@@ -406,8 +438,14 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     __shared__ uint32_t t_cnt[2][W], t_rel[2][W], t_n1[2][W];
     __shared__ uint32_t s_ball[W], s_c0, s_span, s_last, s_maxk;
     __shared__ float s_o[6];
+    __shared__ unsigned long long s_bar;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0)
+        mbar_init(bar_a, W); // one arrival per warp
+    uint32_t bar_phase = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * (uint32_t)S3_THREADS + tid;
     const bool valid = i < ll.N;
     const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
@@ -655,7 +693,23 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rk1))
                     consume();
             }
-            __syncthreads();
+            // round barrier: arrive, then keep consuming pending hits (of the other ring
+            // rounds) until every warp has arrived
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(bar_a);
+            for (;;) {
+                if (__all_sync(0xffffffffu, mbar_test(bar_a, bar_phase)))
+                    break;
+                if (__popc(__ballot_sync(0xffffffffu, cur != 0)) >= 20) {
+                    consume(); // most lanes still have hits: use the wait
+                } else {
+                    while (!__all_sync(0xffffffffu, mbar_wait(bar_a, bar_phase))) // suspends the warp
+                        ;
+                    break;
+                }
+            }
+            bar_phase ^= 1u;
             if (r + 1 < nrounds)
                 stage(r + 1, rk1);
             // ---- filter: record the hit masks of the round's tiles
