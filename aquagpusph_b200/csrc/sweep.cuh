@@ -363,8 +363,12 @@ sweep2_kernel(const P p, const LLParams ll)
 // deterministic (run-to-run bit-identical); the order is not the reference's x-outer
 // one any more: results differ from v2 by fp32 rounding of the sums only.
 // Order-dependent kernels stay on sweep_kernel.
-constexpr int S3_WARPS = 8;
+constexpr int S3_WARPS = 8;                  // warp 0 stages tiles, warps 1..7 own 32 particles each
 constexpr int S3_THREADS = S3_WARPS * 32;
+constexpr int S3_CWARPS = S3_WARPS - 1;       // consumer warps
+constexpr int S3_PARTICLES = S3_CWARPS * 32;  // particles of a CTA
+constexpr int S3_TILES = 8;                   // tiles of a round
+constexpr int S3_MAXK = 4;                    // ring rounds
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 
@@ -373,6 +377,10 @@ constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint32_t a)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a)
 {
@@ -425,29 +433,29 @@ __global__ void __launch_bounds__(S3_THREADS, (P::NJ4 <= 2) ? 4 : 3)
 sweep3_kernel(const P p, const LLParams ll, const int K)
 {
     extern __shared__ float4 smem3[];
-    constexpr int W = S3_WARPS;
+    constexpr int W = S3_TILES;
     constexpr int SLOT4 = P::NJ4 * 32;
     const uint32_t NS = (uint32_t)K * W; // ring slots
-    float4* const sT = smem3;            // [2][W][32] packed test layout of the tiles of two rounds
-    float4* const sJ = sT + 2 * W * 32;  // [NS][SLOT4] j rows
+    float4* const sT = smem3;            // [K][W][32] packed test layout of the ring's tiles
+    float4* const sJ = sT + NS * 32;     // [NS][SLOT4] j rows
     uint32_t NM = NS - W;                // FIFO entries per lane: the round being staged has no masks yet
     asm volatile("" : "+r"(NM));         // (opaque: kept in a register, not recomputed from K)
-    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [W][NM][32] masks, then
-                                                                               // [W][NM][32] slot bytes
+    uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [CW][NM][32] masks, then
+                                                                               // [CW][NM][32] slot bytes
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
-    __shared__ uint32_t t_cnt[2][W], t_rel[2][W], t_n1[2][W];
-    __shared__ uint32_t s_ball[W], s_c0, s_span, s_last, s_maxk;
+    __shared__ uint32_t t_cnt[S3_MAXK][W], t_rel[S3_MAXK][W], t_n1[S3_MAXK][W];
+    __shared__ uint32_t s_ball[S3_WARPS], s_c0, s_span, s_last, s_maxk;
     __shared__ float s_o[6];
-    __shared__ unsigned long long s_bar;
+    // full[k]: the producer has staged ring round k; empty[k]: a consumer warp is done with it
+    __shared__ unsigned long long s_full[S3_MAXK], s_empty[S3_MAXK];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&s_bar);
-    if (tid == 0)
-        mbar_init(bar_a, W); // one arrival per warp
-    uint32_t bar_phase = 0;
-    __syncthreads();
-    const uint32_t i = blockIdx.x * (uint32_t)S3_THREADS + tid;
-    const bool valid = i < ll.N;
+    const bool producer = warp == 0;
+    const int cw = warp - 1; // consumer index
+    const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(s_full);
+    const uint32_t empty_a = (uint32_t)__cvta_generic_to_shared(s_empty);
+    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + (uint32_t)(tid - 32);
+    const bool valid = !producer && i < ll.N;
     const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
     const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
     typename P::IState st;
@@ -459,14 +467,14 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     // shared-window addresses of this lane's FIFO (masks, slot bytes) and of the last row
     // slot of ring tile 0, kept opaque so that they stay in registers instead of being
     // recomputed from tid at every use
-    uint32_t Mw_a = (uint32_t)__cvta_generic_to_shared(sM + (size_t)warp * NM * 32 + lane);
-    uint32_t Sw_a = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint8_t*>(sM + (size_t)W * NM * 32) +
-                                                       (size_t)warp * NM * 32 + lane);
+    uint32_t Mw_a = (uint32_t)__cvta_generic_to_shared(sM + (size_t)(producer ? 0 : cw) * NM * 32 + lane);
+    uint32_t Sw_a = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint8_t*>(sM + (size_t)S3_CWARPS * NM * 32) +
+                                                       (size_t)(producer ? 0 : cw) * NM * 32 + lane);
     uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ) + 31 * 16;
     asm volatile("" : "+r"(Mw_a), "+r"(Sw_a), "+r"(sJ_a));
 
     bool pending = active;
-    for (;;) {
+    for (uint32_t npass = 0;; npass++) {
         // ---- the group of this pass: first pending particle and its x-row neighbours
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);
         if (lane == 0)
@@ -475,11 +483,19 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             s_span = 0;
             s_last = 0;
             s_maxk = 0;
+            for (int k = 0; k < K; k++) { // nobody is inside a round loop here
+                if (npass) {
+                    mbar_inval(full_a + 8 * k);
+                    mbar_inval(empty_a + 8 * k);
+                }
+                mbar_init(full_a + 8 * k, 1);
+                mbar_init(empty_a + 8 * k, S3_CWARPS);
+            }
         }
         __syncthreads();
         int first = -1;
 #pragma unroll
-        for (int w = W - 1; w >= 0; w--)
+        for (int w = S3_WARPS - 1; w >= 0; w--)
             if (s_ball[w])
                 first = w * 32 + __ffs(s_ball[w]) - 1;
         if (first < 0)
@@ -625,11 +641,11 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     body1();
             }
         };
-        // stage: warp w brings tile r * W + w = (part e, its k-th tile) of round r
-        auto stage = [&](uint32_t r, uint32_t ring_round) {
-            const uint32_t tn = r * W + warp;
+        // stage (producer warp): tile r * W + w2 = (part e, its k-th tile) of round r
+        auto stage = [&](uint32_t r, uint32_t ring_round, uint32_t w2) {
+            const uint32_t tn = r * W + w2;
             const uint32_t k = tn / NE, e = tn - k * NE;
-            const uint32_t par = r & 1u;
+            const uint32_t par = ring_round;
             uint32_t cnt = 0;
             if (k < maxk) {
                 const uint32_t b = e_begin[e] + 32u * k, en = e_end[e];
@@ -637,7 +653,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     cnt = min(32u, en - b);
                     const bool in = (uint32_t)lane < cnt;
                     const uint32_t jj = b + lane;
-                    float4* const slot = sJ + (size_t)(ring_round * W + warp) * SLOT4;
+                    float4* const slot = sJ + (size_t)(ring_round * W + w2) * SLOT4;
                     float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
                     uint32_t cj = 0xFFFFFFFFu;
                     bool live = false;
@@ -656,7 +672,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                             tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
                         }
                     }
-                    float* const tst = reinterpret_cast<float*>(sT + (par * W + warp) * 32) +
+                    float* const tst = reinterpret_cast<float*>(sT + (par * W + w2) * 32) +
                                        (lane >> 1) * 8 + (lane & 1);
                     tst[0] = tx;
                     tst[2] = ty;
@@ -669,90 +685,106 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     const uint32_t cj0 = __shfl_sync(0xffffffffu, cj, 0);
                     const int n1 = __popc(__ballot_sync(0xffffffffu, cj == cj0));
                     if (lane == 0) {
-                        t_rel[par][warp] = e_rel[e] + cj0;
-                        t_n1[par][warp] = (uint32_t)n1;
+                        t_rel[par][w2] = e_rel[e] + cj0;
+                        t_n1[par][w2] = (uint32_t)n1;
                     }
                 }
             }
             if (lane == 0)
-                t_cnt[par][warp] = cnt;
+                t_cnt[par][w2] = cnt;
         };
 
-        // One barrier per round: at barrier r every warp has staged its tile of round r and
-        // has consumed its hits of round r + 1 - K, whose ring round receives round r + 1
-        // while round r is filtered -- a warp's staging loads overlap the other warps' work.
+        // Producer / consumers over a ring of K rounds of W tiles.  The producer warp stages
+        // round r into ring round r % K as soon as every consumer warp has released the round
+        // that lived there (r - K); a consumer warp filters round r when it is full, runs its
+        // balanced bodies, and releases round r + 2 - K after consuming the hits it still had
+        // in it.  A consumer never waits for another consumer: only the ring couples them, so
+        // warps may drift apart by K - 1 rounds before anybody stalls.
         const uint32_t nrounds = (maxk * NE + W - 1) / W;
-        if (nrounds)
-            stage(0, 0);
-        uint32_t rk = 0;  // ring round that holds round r (r % K)
-        for (uint32_t r = 0; r < nrounds; r++) {
-            const uint32_t rk1 = (rk + 1 == (uint32_t)K) ? 0u : rk + 1;
-            if (r + 1 >= (uint32_t)K) {
-                // ring round rk1 (it holds round r + 1 - K) is recycled next: its hits are the
-                // oldest of every FIFO, a lane is done with them when its tile is a newer one
-                while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rk1))
-                    consume();
-            }
-            // round barrier: arrive, then keep consuming pending hits (of the other ring
-            // rounds) until every warp has arrived
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(bar_a);
-            for (;;) {
-                if (__all_sync(0xffffffffu, mbar_test(bar_a, bar_phase)))
-                    break;
-                if (__popc(__ballot_sync(0xffffffffu, cur != 0)) >= 20) {
-                    consume(); // most lanes still have hits: use the wait
-                } else {
-                    while (!__all_sync(0xffffffffu, mbar_wait(bar_a, bar_phase))) // suspends the warp
-                        ;
-                    break;
+        if (producer) {
+            uint32_t rk = 0, use = 0; // ring round r % K, r / K
+            for (uint32_t r = 0; r < nrounds; r++) {
+                if (use) { // ring round rk holds round r - K
+                    uint32_t spins = 0;
+                    while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u)))
+                        if (++spins > (1u << 26))
+                            __trap();
+                }
+#pragma unroll 1
+                for (uint32_t w2 = 0; w2 < (uint32_t)W; w2++)
+                    stage(r, rk, w2);
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(full_a + 8 * rk);
+                if (++rk == (uint32_t)K) {
+                    rk = 0;
+                    use++;
                 }
             }
-            bar_phase ^= 1u;
-            if (r + 1 < nrounds)
-                stage(r + 1, rk1);
-            // ---- filter: record the hit masks of the round's tiles
-            if (mine) {
-                const uint32_t par = r & 1u;
-                const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
-                                         C2 = pack2(fc, fc);
+        } else {
+            uint32_t rk = 0, use = 0;  // ring round of round r, r / K
+            uint32_t rq = 0;           // ring round of round r + 2 - K, the next one to release
+            const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
+                                     C2 = pack2(fc, fc);
+            for (uint32_t r = 0; r < nrounds; r++) {
+                {
+                    uint32_t spins = 0;
+                    while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u)))
+                        if (++spins > (1u << 26))
+                            __trap();
+                }
+                // ---- filter: record the hit masks of the round's tiles
+                if (mine) {
 #pragma unroll 1
-                for (int w2 = 0; w2 < W; w2++) {
-                    const uint32_t cnt = t_cnt[par][w2];
-                    if (!cnt)
-                        continue;
-                    const uint32_t rel = t_rel[par][w2] - a_i; // (x offset of the lower cell - a_i) + 1
-                    const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[par][w2]);
-                    const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
-                    if (!okm)
-                        continue;
-                    const float4* T = sT + (par * W + w2) * 32;
-                    uint32_t m;
-                    if (cnt > 16)
-                        m = test_tile<16>(T, X2, Y2, Z2, C2);
-                    else if (cnt > 8)
-                        m = test_tile<8>(T, X2, Y2, Z2, C2);
-                    else
-                        m = test_tile<4>(T, X2, Y2, Z2, C2);
-                    m &= okm;
-                    if (m) {
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(Mw_a + qw * 128), "r"(m) : "memory");
-                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(Sw_a + qw * 32), "r"(rk * W + w2) : "memory");
-                        qw = (qw + 1 == NM) ? 0u : qw + 1;
+                    for (int w2 = 0; w2 < W; w2++) {
+                        const uint32_t cnt = t_cnt[rk][w2];
+                        if (!cnt)
+                            continue;
+                        const uint32_t rel = t_rel[rk][w2] - a_i; // (x offset of the lower cell - a_i) + 1
+                        const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[rk][w2]);
+                        const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
+                        if (!okm)
+                            continue;
+                        const float4* T = sT + (rk * W + w2) * 32;
+                        uint32_t m;
+                        if (cnt > 16)
+                            m = test_tile<16>(T, X2, Y2, Z2, C2);
+                        else if (cnt > 8)
+                            m = test_tile<8>(T, X2, Y2, Z2, C2);
+                        else
+                            m = test_tile<4>(T, X2, Y2, Z2, C2);
+                        m &= okm;
+                        if (m) {
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(Mw_a + qw * 128), "r"(m) : "memory");
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(Sw_a + qw * 32), "r"(rk * W + w2) : "memory");
+                            qw = (qw + 1 == NM) ? 0u : qw + 1;
+                        }
+                    }
+                    if (!cur && qr != qw)
+                        pick();
+                    // ---- bodies, while every member lane of the warp has one pending
+                    while (__ballot_sync(mine_w, cur != 0) == mine_w) {
+                        if constexpr (P::PAIR2)
+                            body2();
+                        else
+                            body1();
                     }
                 }
-                if (!cur && qr != qw)
-                    pick();
-                // ---- bodies, while every member lane of the warp has one pending
-                while (__ballot_sync(mine_w, cur != 0) == mine_w) {
-                    if constexpr (P::PAIR2)
-                        body2();
-                    else
-                        body1();
+                // ---- release round r + 2 - K: its hits are the oldest of every FIFO, a lane is
+                // done with them when the tile it works on is a newer one
+                if (r + 2 >= (uint32_t)K) {
+                    while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rq))
+                        consume();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(empty_a + 8 * rq);
+                    rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
+                }
+                if (++rk == (uint32_t)K) {
+                    rk = 0;
+                    use++;
                 }
             }
-            rk = rk1;
         }
         while (__any_sync(0xffffffffu, cur != 0))
             consume();
@@ -798,16 +830,16 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         const bool small2d = (P::DIMS == 2) && ll.N < (1u << 20) && !aqc_sweep_engine_forced();
         if (aqc_sweep_engine() == 3 && !P::SPARSE_I && !small2d) {
             const int K = aqc_sweep_ring(P::NJ4);
-            const size_t NS = (size_t)K * S3_WARPS;
-            const size_t smem = (2 * S3_WARPS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
-                                S3_WARPS * (NS - S3_WARPS) * 32 * (sizeof(uint32_t) + 1);
+            const size_t NS = (size_t)K * S3_TILES;
+            const size_t smem = (NS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
+                                S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
             static size_t configured = 0; // per instantiation
             if (smem > configured) {
                 AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = smem;
             }
-            sweep3_kernel<P><<<aqc_blocks(ll.N, S3_THREADS), S3_THREADS, smem, ctx->stream>>>(p, ll, K);
+            sweep3_kernel<P><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K);
         } else {
             sweep2_kernel<P><<<aqc_blocks(ll.N, SWEEP_THREADS), SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
         }
