@@ -707,7 +707,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 if (use) { // ring round rk holds round r - K
                     uint32_t spins = 0;
                     while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u)))
-                        if (++spins > (1u << 26))
+                        if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
                 }
 #pragma unroll 1
@@ -730,7 +730,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 {
                     uint32_t spins = 0;
                     while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u)))
-                        if (++spins > (1u << 26))
+                        if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
                 }
                 // ---- filter: record the hit masks of the round's tiles
