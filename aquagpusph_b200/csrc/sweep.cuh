@@ -367,8 +367,11 @@ constexpr int S3_WARPS = 8;                  // warp 0 stages tiles, warps 1..7 
 constexpr int S3_THREADS = S3_WARPS * 32;
 constexpr int S3_CWARPS = S3_WARPS - 1;       // consumer warps
 constexpr int S3_PARTICLES = S3_CWARPS * 32;  // particles of a CTA
-constexpr int S3_TILES = 8;                   // tiles of a round
-constexpr int S3_MAXK = 4;                    // ring rounds
+#ifndef S3_TILES_N
+#define S3_TILES_N 8
+#endif
+constexpr int S3_TILES = S3_TILES_N;           // tiles of a round
+constexpr int S3_MAXK = 8;                    // ring rounds (at most)
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 

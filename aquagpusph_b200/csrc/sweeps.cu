@@ -51,7 +51,7 @@ int aqc_sweep_ring(int nj4)
     static const int forced = [] {
         const char* s = getenv("AQC_SWEEP_RING");
         const int r = s ? atoi(s) : 0;
-        return (r >= 2 && r <= 4) ? r : 0; // K * 8 tiles must fit the 32-bit lane bitmap
+        return (r >= 2 && r <= 8) ? r : 0;
     }();
     if (forced)
         return forced;

@@ -199,6 +199,11 @@ def run_ours(a, rank, world, local_rank):
     ms = max_over_ranks(actx.elapsed_ms(e0, e1))
     launches = sim.launch_count() - l0
     value = N_all * a.steps / (ms * 1e-3)
+    # the clock samples belong to the device-timed region; nvidia-smi polling perturbs the
+    # host-timed end-to-end loop below (driver locks), so it stops here
+    clocks.stop_flag = True
+    if rank == 0:
+        clocks.join(timeout=10)
 
     # ---- end to end: host buffers in, host buffers out, every step
     fields = ["r", "u", "dudt", "rho", "drhodt", "m", "imove"]
