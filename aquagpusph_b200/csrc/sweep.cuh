@@ -371,6 +371,36 @@ constexpr int S3_PARTICLES = S3_CWARPS * 32;  // particles of a CTA
 #define S3_TILES_N 8
 #endif
 constexpr int S3_TILES = S3_TILES_N;           // tiles of a round
+#ifndef S3_BATCH
+#define S3_BATCH 1 // tiles whose global loads the producer keeps in flight together (divides S3_TILES)
+#endif
+#ifndef S3_WAIT_CONSUME
+#define S3_WAIT_CONSUME 0 // a consumer warp waiting for the ring runs its pending pair bodies
+#endif
+#ifndef S3_INTERLEAVE
+#define S3_INTERLEAVE 0 // particles dealt to the consumer warps round-robin instead of in blocks of 32
+#endif
+#ifndef S3_ALTERNATE
+#define S3_ALTERNATE 0 // every other part of an x row is walked backwards (balance between the warps)
+#endif
+#ifndef S3_PROFILE
+#define S3_PROFILE 0 // debug builds only (tools/build_variant.py): per-phase clock64 totals
+#endif
+#if S3_PROFILE
+static __device__ unsigned long long g_s3prof[32];
+#define S3P_START long long s3p_t = clock64();
+#define S3P_ACC(k)                                                                                 \
+    {                                                                                              \
+        const long long s3p_n = clock64();                                                         \
+        if (lane == 0)                                                                             \
+            atomicAdd(&g_s3prof[(k)], (unsigned long long)(s3p_n - s3p_t));                        \
+        s3p_t = s3p_n;                                                                             \
+    }
+#else
+#define S3P_START
+#define S3P_ACC(k)
+#endif
+static_assert(S3_TILES_N % S3_BATCH == 0, "S3_BATCH must divide S3_TILES");
 constexpr int S3_MAXK = 8;                    // ring rounds (at most)
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
@@ -446,6 +476,9 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [CW][NM][32] masks, then
                                                                                // [CW][NM][32] slot bytes
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
+#if S3_ALTERNATE
+    __shared__ uint32_t e_rev[S3_MAXE]; // tiles of a part that is walked backwards (0: forwards)
+#endif
     __shared__ uint32_t t_cnt[S3_MAXK][W], t_rel[S3_MAXK][W], t_n1[S3_MAXK][W];
     __shared__ uint32_t s_ball[S3_WARPS], s_c0, s_span, s_last, s_maxk;
     __shared__ float s_o[6];
@@ -457,7 +490,15 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     const int cw = warp - 1; // consumer index
     const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(s_full);
     const uint32_t empty_a = (uint32_t)__cvta_generic_to_shared(s_empty);
-    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + (uint32_t)(tid - 32);
+#if S3_INTERLEAVE
+    // particle k of the CTA goes to consumer warp k % 7, lane k / 7: every warp holds an even
+    // sample of the CTA's (cell-ordered, spatially coherent) particles, so the warps have the same
+    // amount of work in every round of tiles
+    const uint32_t pidx = producer ? 0u : (uint32_t)(lane * S3_CWARPS + cw);
+#else
+    const uint32_t pidx = (uint32_t)(tid - 32);
+#endif
+    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + pidx;
     const bool valid = !producer && i < ll.N;
     const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
     const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
@@ -497,10 +538,25 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         }
         __syncthreads();
         int first = -1;
+#if S3_INTERLEAVE
+        {
+            int best = 1 << 30;
+#pragma unroll
+            for (int w = 1; w < S3_WARPS; w++)
+                if (s_ball[w]) {
+                    const int l = __ffs(s_ball[w]) - 1, k = l * S3_CWARPS + (w - 1);
+                    if (k < best) {
+                        best = k;
+                        first = w * 32 + l;
+                    }
+                }
+        }
+#else
 #pragma unroll
         for (int w = S3_WARPS - 1; w >= 0; w--)
             if (s_ball[w])
                 first = w * 32 + __ffs(s_ball[w]) - 1;
+#endif
         if (first < 0)
             break;
         if (tid == first) {
@@ -516,12 +572,20 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             const uint32_t sp = __reduce_max_sync(0xffffffffu, mine ? a_i : 0u);
             if (lane == 0) {
                 atomicMax(&s_span, sp);
+#if S3_INTERLEAVE
+                atomicMax(&s_last, (uint32_t)((31 - __clz(mine_w)) * S3_CWARPS + cw));
+#else
                 atomicMax(&s_last, (uint32_t)(warp * 32 + 31 - __clz(mine_w)));
+#endif
             }
         }
         pending = pending && !mine;
         __syncthreads();
+#if S3_INTERLEAVE
+        if (!producer && pidx == s_last) {
+#else
         if (tid == (int)s_last) {
+#endif
             s_o[3] = st.x; s_o[4] = st.y; s_o[5] = st.z;
         }
         const uint32_t len = s_span + 3u, nparts = (len + 1u) / 2u;
@@ -557,6 +621,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             e_end[tid] = en;
             e_lo[tid] = lo;
             e_rel[tid] = lo - base; // x offset of cell lo relative to c0, plus one
+#if S3_ALTERNATE
+            // odd parts are walked from their last tile to their first one: while the warps of
+            // the group's first cells work on the lower cell of part 0 (which the others do not
+            // need), the warps of the next cells work on the upper cell of part 1
+            e_rev[tid] = (part & 1u) ? (en - b + 31u) / 32u : 0u;
+#endif
             if (en > b)
                 atomicMax(&s_maxk, (en - b + 31u) / 32u);
         }
@@ -644,34 +714,54 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     body1();
             }
         };
-        // stage (producer warp): tile r * W + w2 = (part e, its k-th tile) of round r
-        auto stage = [&](uint32_t r, uint32_t ring_round, uint32_t w2) {
-            const uint32_t tn = r * W + w2;
-            const uint32_t k = tn / NE, e = tn - k * NE;
+        // stage (producer warp): S3_BATCH consecutive tiles of a round at a time; tile number tn =
+        // (part e = tn % NE, its k-th tile, k = tn / NE), carried in (tk, te).  The global loads
+        // of the whole batch are issued before any of them is used, so a round costs
+        // W / S3_BATCH memory latencies instead of W (branch-free: a lane without a candidate
+        // loads particle 0 and drops it).
+        uint32_t tk = 0, te = 0;
+        auto stage_batch = [&](uint32_t ring_round, uint32_t w0) {
             const uint32_t par = ring_round;
-            uint32_t cnt = 0;
-            if (k < maxk) {
-                const uint32_t b = e_begin[e] + 32u * k, en = e_end[e];
-                if (b < en) {
-                    cnt = min(32u, en - b);
-                    const bool in = (uint32_t)lane < cnt;
-                    const uint32_t jj = b + lane;
+            uint32_t cnt[S3_BATCH], cj[S3_BATCH], eb[S3_BATCH];
+            float4 o[S3_BATCH][P::NJ4];
+#pragma unroll
+            for (int b = 0; b < S3_BATCH; b++) {
+                const uint32_t e = te, k = tk;
+                if (++te == NE) {
+                    te = 0;
+                    tk++;
+                }
+                eb[b] = e;
+#if S3_ALTERNATE
+                const uint32_t nrev = e_rev[e];
+                const uint32_t kk = nrev ? nrev - 1u - k : k; // k >= nrev wraps: bg >= en below
+                const uint32_t bg = (nrev && k >= nrev) ? ll.N : e_begin[e] + 32u * kk, en = e_end[e];
+#else
+                const uint32_t bg = e_begin[e] + 32u * k, en = e_end[e];
+#endif
+                cnt[b] = (k < maxk && bg < en) ? min(32u, en - bg) : 0u;
+                const uint32_t jj = ((uint32_t)lane < cnt[b]) ? bg + lane : 0u;
+                cj[b] = __ldg(ll.icell + jj) - e_lo[e];
+                p.stage_j(jj, o[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < S3_BATCH; b++) {
+                const uint32_t w2 = w0 + b;
+                uint32_t c = cnt[b];
+                if (c) {
+                    const bool in = (uint32_t)lane < c;
                     float4* const slot = sJ + (size_t)(ring_round * W + w2) * SLOT4;
                     float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
-                    uint32_t cj = 0xFFFFFFFFu;
                     bool live = false;
                     if (in) {
-                        cj = __ldg(ll.icell + jj) - e_lo[e];
-                        float4 o[P::NJ4];
-                        p.stage_j(jj, o);
 #pragma unroll
                         for (int q = 0; q < P::NJ4; q++)
-                            slot[q * 32 + lane] = o[q];
-                        live = P::j_live(o[0]);
+                            slot[q * 32 + lane] = o[b][q];
+                        live = P::j_live(o[b][0]);
                         if (live) {
-                            tx = o[0].x - s_o[0];
-                            ty = o[0].y - s_o[1];
-                            tz = (P::DIMS == 3) ? o[0].z - s_o[2] : 0.f;
+                            tx = o[b][0].x - s_o[0];
+                            ty = o[b][0].y - s_o[1];
+                            tz = (P::DIMS == 3) ? o[b][0].z - s_o[2] : 0.f;
                             tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
                         }
                     }
@@ -684,17 +774,18 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     // a tile without a candidate that can interact at all is dropped (a tile of
                     // fluid particles costs a boundary kernel its staging only)
                     if (!__any_sync(0xffffffffu, live))
-                        cnt = 0;
-                    const uint32_t cj0 = __shfl_sync(0xffffffffu, cj, 0);
-                    const int n1 = __popc(__ballot_sync(0xffffffffu, cj == cj0));
+                        c = 0;
+                    const uint32_t cjv = in ? cj[b] : 0xFFFFFFFFu;
+                    const uint32_t cj0 = __shfl_sync(0xffffffffu, cjv, 0);
+                    const int n1 = __popc(__ballot_sync(0xffffffffu, cjv == cj0));
                     if (lane == 0) {
-                        t_rel[par][w2] = e_rel[e] + cj0;
+                        t_rel[par][w2] = e_rel[eb[b]] + cj0;
                         t_n1[par][w2] = (uint32_t)n1;
                     }
                 }
+                if (lane == 0)
+                    t_cnt[par][w2] = c;
             }
-            if (lane == 0)
-                t_cnt[par][w2] = cnt;
         };
 
         // Producer / consumers over a ring of K rounds of W tiles.  The producer warp stages
@@ -706,16 +797,20 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         const uint32_t nrounds = (maxk * NE + W - 1) / W;
         if (producer) {
             uint32_t rk = 0, use = 0; // ring round r % K, r / K
+            S3P_START
             for (uint32_t r = 0; r < nrounds; r++) {
+                S3P_ACC(20)
                 if (use) { // ring round rk holds round r - K
                     uint32_t spins = 0;
                     while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u)))
                         if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
                 }
+                S3P_ACC(16)
 #pragma unroll 1
-                for (uint32_t w2 = 0; w2 < (uint32_t)W; w2++)
-                    stage(r, rk, w2);
+                for (uint32_t w0 = 0; w0 < (uint32_t)W; w0 += S3_BATCH)
+                    stage_batch(rk, w0);
+                S3P_ACC(17)
                 __syncwarp();
                 if (lane == 0)
                     mbar_arrive(full_a + 8 * rk);
@@ -729,13 +824,35 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             uint32_t rq = 0;           // ring round of round r + 2 - K, the next one to release
             const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
                                      C2 = pack2(fc, fc);
+#if S3_PROFILE
+            const int s3p_c = mine_w ? 0 : 8; // warps without a member of the group: second bank
+#endif
+            S3P_START
             for (uint32_t r = 0; r < nrounds; r++) {
+                S3P_ACC(s3p_c + 5)
                 {
                     uint32_t spins = 0;
+#if S3_WAIT_CONSUME
+                    // not full yet: the time is spent on pending pair bodies (whatever the lane
+                    // balance) instead of polling; a warp without any suspends in try_wait
+                    for (;;) {
+                        const bool has = __any_sync(0xffffffffu, cur != 0);
+                        const bool ok = has ? mbar_test(full_a + 8 * rk, use & 1u)
+                                            : mbar_wait(full_a + 8 * rk, use & 1u);
+                        if (__all_sync(0xffffffffu, ok))
+                            break;
+                        if (has)
+                            consume();
+                        else if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
+                            __trap();
+                    }
+#else
                     while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u)))
                         if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
+#endif
                 }
+                S3P_ACC(s3p_c + 0)
                 // ---- filter: record the hit masks of the round's tiles
                 if (mine) {
 #pragma unroll 1
@@ -765,6 +882,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     }
                     if (!cur && qr != qw)
                         pick();
+                    S3P_ACC(s3p_c + 1)
                     // ---- bodies, while every member lane of the warp has one pending
                     while (__ballot_sync(mine_w, cur != 0) == mine_w) {
                         if constexpr (P::PAIR2)
@@ -773,6 +891,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                             body1();
                     }
                 }
+                __syncwarp();
+                S3P_ACC(s3p_c + 2)
                 // ---- release round r + 2 - K: its hits are the oldest of every FIFO, a lane is
                 // done with them when the tile it works on is a newer one
                 if (r + 2 >= (uint32_t)K) {
@@ -783,15 +903,28 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                         mbar_arrive(empty_a + 8 * rq);
                     rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
                 }
+                S3P_ACC(s3p_c + 3)
                 if (++rk == (uint32_t)K) {
                     rk = 0;
                     use++;
                 }
             }
         }
+#if S3_PROFILE
+        long long s3p_t = clock64();
+        const int s3p_c2 = producer ? 24 : (mine_w ? 0 : 8);
+#endif
         while (__any_sync(0xffffffffu, cur != 0))
             consume();
+        S3P_ACC(s3p_c2 + 4)
         __syncthreads();
+        S3P_ACC(s3p_c2 + 6)
+#if S3_PROFILE
+        if (tid == 0) {
+            atomicAdd(&g_s3prof[30], (unsigned long long)nrounds);
+            atomicAdd(&g_s3prof[31], 1ull);
+        }
+#endif
     }
     if (active)
         p.store_i(st, i);

@@ -44,6 +44,20 @@ extern "C" int aqc_sweep_engine_select(int engine)
     }
     return aqc_sweep_engine();
 }
+#if S3_PROFILE
+// debug builds only: per-phase clock totals of sweep3_kernel (see S3P_ACC in sweep.cuh)
+extern "C" int aqc_debug_s3prof(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    if (out)
+        cudaMemcpyFromSymbol(out, g_s3prof, sizeof(g_s3prof));
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(g_s3prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 // Ring rounds of the v3 engine (8 tiles each): shared memory per CTA =
 // 8 KB + K * 8 * NJ4 * 512 + (K - 1) * 8 * 1024 bytes; the deferral window is (K - 1) * 8 tiles
 int aqc_sweep_ring(int nj4)

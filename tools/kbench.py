@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--hfac", type=float, default=3.0)
     ap.add_argument("--case", default="spheric2")
+    ap.add_argument("--suborder", type=int, default=0,
+                    help="input pre-ordered by S x S x S sub-cells inside every link-list cell (-1: random order)")
     a = ap.parse_args()
     t0 = time.time()
     if a.case == "spheric2":
@@ -31,6 +33,19 @@ def main():
     else:
         c = cases.lattice(int(round(a.n ** (1 / 3))), a.hfac)
     N, dims = c["N"], c["dims"]
+    if a.suborder:
+        # the link-list sort is stable: the order inside a cell is the input order
+        r = c["r"][:, :dims].astype(np.float64)
+        t = (r - r.min(0)) / (2.0 * c["h"])
+        if a.suborder > 0:
+            sub = np.minimum((np.modf(t)[0] * a.suborder).astype(np.int64), a.suborder - 1)
+            key = sub[:, 0] + a.suborder * sub[:, 1] + (a.suborder ** 2 * sub[:, 2] if dims == 3 else 0)
+            order = np.argsort(key, kind="stable")
+        else:
+            order = np.random.default_rng(7).permutation(N)
+        for k, x in list(c.items()):
+            if isinstance(x, np.ndarray) and x.ndim >= 1 and x.shape[0] == N and k not in ("refd", "visc_dyn", "delta"):
+                c[k] = np.ascontiguousarray(x[order])
     ctx = _lib.Context(0, dims=dims, h=c["h"])
     V, M = (4 if dims == 3 else 2), (16 if dims == 3 else 4)
     v = {k: ctx.array(c[k]) for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m",
@@ -109,6 +124,9 @@ def main():
             ctx.copy(v["r_bak"], v["r"])
         for _ in range(a.warm):
             fn()
+        prof = getattr(_lib.lib(), "aqc_debug_s3prof", None) if hasattr(_lib.lib(), "aqc_debug_s3prof") else None
+        if prof is not None:
+            prof(None, 1)
         e0, e1 = ctx.event(), ctx.event()
         l0 = ctx.launch_count()
         ctx.record(e0)
@@ -118,6 +136,22 @@ def main():
         ms = ctx.elapsed_ms(e0, e1) / a.reps
         if name == "corrector":
             ctx.copy(v["r"], v["r_bak"])
+        if prof is not None:
+            import ctypes
+            buf = (ctypes.c_ulonglong * 32)()
+            prof(buf, 1)
+            if buf[31]:
+                names = ["wait_full", "filter", "balanced", "release", "tail", "loop", "endsync", "-"]
+                tot = float(sum(buf[0:7])) or 1.0
+                toti = float(sum(buf[8:15])) or 1.0
+                print(json.dumps(dict(s3prof=name,
+                    working={n: round(buf[k] / tot, 3) for k, n in enumerate(names[:7])},
+                    working_Mcycles=round(tot / 1e6 / a.reps, 1),
+                    idle_warps={n: round(buf[8 + k] / toti, 3) for k, n in enumerate(names[:7])},
+                    idle_Mcycles=round(toti / 1e6 / a.reps, 1),
+                    producer=dict(wait_empty=buf[16], stage=buf[17], loop=buf[20], tail=buf[28], endsync=buf[30 - 0] * 0 + buf[30 - 0] * 0),
+                    producer_Mcycles=round((buf[16] + buf[17] + buf[20]) / 1e6 / a.reps, 1),
+                    rounds_per_pass=round(buf[30] / buf[31], 1), passes=buf[31] // a.reps)), flush=True)
         print(json.dumps(dict(kernel=name, ms=round(ms, 4), launches=(ctx.launch_count() - l0) // a.reps,
                               alg_GBs=round(nbytes / ms / 1e6, 1),
                               Mparticles_s=round(N / ms / 1e3, 1))), flush=True)
