@@ -27,11 +27,12 @@ SYMBOLS = [
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
+    "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
 T_F32, T_U32, T_I32, T_VEC2, T_VEC4 = 0, 1, 2, 3, 4
-ARG_ARRAY_IN, ARG_ARRAY_OUT, ARG_SCALAR = 0, 1, 2
+ARG_ARRAY_IN, ARG_ARRAY_OUT, ARG_SCALAR, ARG_ARRAY_RO = 0, 1, 2, 3
 
 
 class Defs(C.Structure):
@@ -72,6 +73,10 @@ def lib():
     L.aqc_kernel_lookup.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.aqc_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.aqc_ctx_destroy.argtypes = [C.c_void_p]
+    L.aqc_pairs_cache_enable.argtypes = [C.c_void_p, C.c_int]
+    L.aqc_pairs_cache_invalidate.argtypes = [C.c_void_p]
+    L.aqc_pairs_cache_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]
     L.aqc_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.aqc_free.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -277,6 +282,18 @@ class Context:
 
     def launch_count(self):
         return int(lib().aqc_launch_count(self.h))
+
+    # -- pair-mask cache of the neighbour sweeps (include/aquacuda.h)
+    def pairs_cache(self, on=True):
+        self._chk(lib().aqc_pairs_cache_enable(self.h, 1 if on else 0))
+
+    def pairs_cache_invalidate(self):
+        self._chk(lib().aqc_pairs_cache_invalidate(self.h))
+
+    def pairs_cache_stats(self):
+        b, h, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._chk(lib().aqc_pairs_cache_stats(self.h, C.byref(b), C.byref(h), C.byref(n)))
+        return dict(builds=b.value, hits=h.value, bytes=n.value)
 
     def sm_count(self):
         return int(lib().aqc_device_sm_count(self.h))

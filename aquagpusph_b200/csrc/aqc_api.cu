@@ -67,6 +67,10 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFree(ctx->sort_hist);
     cudaFree(ctx->minmax_dev);
     cudaFree(ctx->cell_cls);
+    cudaFree(ctx->pc.masks);
+    cudaFree(ctx->pc.pass_tab);
+    cudaFree(ctx->pc.ctl);
+    cudaFreeHost(ctx->pc.ctl_host);
     cudaFreeHost(ctx->minmax_host);
     cudaFree(ctx->red_dev);
     cudaFreeHost(ctx->red_host);
@@ -177,6 +181,7 @@ extern "C" int aqc_free(aqc_ctx* ctx, void* dptr)
     if (!ctx)
         return AQC_ERR_ARG;
     if (dptr) {
+        aqc_pc_touch(ctx, dptr, 1);
         AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         AQC_CUDA(ctx, cudaFree(dptr));
     }
@@ -204,6 +209,7 @@ extern "C" int aqc_memcpy_h2d(aqc_ctx* ctx, void* dst, const void* src, size_t b
 {
     if (!ctx)
         return AQC_ERR_ARG;
+    aqc_pc_touch(ctx, dst, bytes);
     AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (blocking)
         AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -224,6 +230,7 @@ extern "C" int aqc_memcpy_d2d(aqc_ctx* ctx, void* dst, const void* src, size_t b
 {
     if (!ctx)
         return AQC_ERR_ARG;
+    aqc_pc_touch(ctx, dst, bytes);
     AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return AQC_OK;
 }
@@ -267,6 +274,7 @@ extern "C" int aqc_fill(aqc_ctx* ctx, void* dptr, size_t n, size_t elem_bytes, c
         return AQC_ERR_ARG;
     if (!n)
         return AQC_OK;
+    aqc_pc_touch(ctx, dptr, n * elem_bytes);
     switch (elem_bytes) {
         case 4: return fill_launch<uint32_t>(ctx, dptr, n, value);
         case 8: return fill_launch<uint2>(ctx, dptr, n, value);
@@ -408,5 +416,39 @@ extern "C" int aqc_launch(aqc_ctx* ctx, int id, size_t n, void* const* args, int
                             reg[id].script, reg[id].entry, k, reg[id].args[k].name);
     if (!n)
         return AQC_OK;
+    for (int k = 0; k < nargs; k++) // what the kernel may write: one element per work-item
+        if (reg[id].args[k].kind == AQC_ARG_ARRAY_OUT)
+            aqc_pc_touch(ctx, args[k], n * aqc_type_bytes(reg[id].args[k].type, ctx->defs.dims));
     return reg[id].fn(ctx, n, args);
+}
+
+// ---- pair-mask cache of the neighbour sweeps (sweep.cuh, S3Cache) ------------------------
+extern "C" int aqc_pairs_cache_enable(aqc_ctx* ctx, int on)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    ctx->pc.enabled = on != 0;
+    ctx->pc.valid = false;
+    return AQC_OK;
+}
+
+extern "C" int aqc_pairs_cache_invalidate(aqc_ctx* ctx)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    aqc_pc_invalidate(ctx);
+    return AQC_OK;
+}
+
+extern "C" int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    if (builds)
+        *builds = ctx->pc.builds;
+    if (hits)
+        *hits = ctx->pc.hits;
+    if (bytes)
+        *bytes = (uint64_t)ctx->pc.cap_rounds * 7168u; // S3_TILES * S3_CWARPS * 32 lanes * 4 B per round
+    return AQC_OK;
 }

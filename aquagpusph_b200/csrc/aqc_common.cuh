@@ -9,7 +9,31 @@
 
 #include "aquacuda.h"
 
+// Pair-mask cache of the v3 sweep engine (sweep.cuh, S3Cache): hit masks of the candidate filter,
+// built once per geometry (positions + link-list + particle classes) and read by every sweep
+// until one of those arrays is written through the library (aqc_pc_touch) or the caller says so
+// (aqc_pairs_cache_invalidate).
+struct aqc_pair_cache {
+    bool enabled = false;  // aqc_pairs_cache_enable
+    bool valid = false;    // the masks belong to the key below
+    bool unusable = false; // a CTA needed more passes than the pass table holds: sweeps filter
+    const void *r = nullptr, *imove = nullptr, *icell = nullptr, *ihoc = nullptr; // key
+    uint32_t N = 0, nx = 0, ny = 0, nz = 0, nw = 0;
+    int dims = 0;
+    float cut2 = 0.f;
+    uint32_t icls = 0, jcls = 0;           // particle classes (aqc_cls_bit) the masks were built for
+    uint32_t icls_want = 0, jcls_want = 0; // union of the classes asked for so far
+    uint32_t* masks = nullptr;
+    size_t cap_rounds = 0;
+    uint32_t* pass_tab = nullptr;
+    size_t pass_cap = 0;
+    unsigned long long* ctl = nullptr;      // device [2]
+    unsigned long long* ctl_host = nullptr; // pinned [2]
+    uint64_t builds = 0, hits = 0;
+};
+
 struct aqc_ctx {
+    aqc_pair_cache pc;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -53,6 +77,39 @@ struct aqc_ctx {
 };
 
 int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
+
+// [ptr, ptr + bytes) is about to be written: the pair-mask cache dies if it was built from it
+static inline void aqc_pc_touch(aqc_ctx* ctx, const void* ptr, size_t bytes)
+{
+    aqc_pair_cache& c = ctx->pc;
+    if (!c.valid || !ptr)
+        return;
+    const char* a = (const char*)ptr;
+    const char* b = a + (bytes ? bytes : 1);
+    auto hit = [&](const void* base, size_t n) {
+        const char* x = (const char*)base;
+        return base && a < x + n && x < b;
+    };
+    if (hit(c.r, (size_t)c.N * (c.dims == 3 ? 16 : 8)) || hit(c.imove, (size_t)c.N * 4) ||
+        hit(c.icell, (size_t)c.N * 4) || hit(c.ihoc, (size_t)c.nw * 4))
+        c.valid = false;
+}
+static inline void aqc_pc_invalidate(aqc_ctx* ctx) { ctx->pc.valid = false; }
+// bytes of one element of an array argument, from its reference type string ("vec*", "float*", ...)
+static inline size_t aqc_type_bytes(const char* type, int dims)
+{
+    if (!strncmp(type, "matrix", 6))
+        return dims == 3 ? 64 : 16;
+    if (!strncmp(type, "vec4", 4) || !strncmp(type, "ivec4", 5) || !strncmp(type, "uivec4", 6) ||
+        !strncmp(type, "svec4", 5))
+        return 16;
+    if (!strncmp(type, "vec2", 4) || !strncmp(type, "ivec2", 5) || !strncmp(type, "uivec2", 6))
+        return 8;
+    if (!strncmp(type, "vec", 3) || !strncmp(type, "ivec", 4) || !strncmp(type, "uivec", 5) ||
+        !strncmp(type, "svec", 4))
+        return dims == 3 ? 16 : 8;
+    return 4; // float, int, uint, usize (32-bit indices)
+}
 
 int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...);
 

@@ -952,6 +952,7 @@ int l_h_sensor(aqc_ctx* c, size_t, void* const* a)
 
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
+#define RO(n, t) { n, t, AQC_ARG_ARRAY_RO }
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
 
 #define MPI_FIELDS_OUT                                                            \
@@ -1066,7 +1067,7 @@ aqc_registrar r_sort2("basic/Sort.cl", "stage2", 0,
       IN("drhodt", "float*"), OUT("drhodt_in", "float*"), IN("id_sorted", "usize*"),
       SC("N", "usize") }, l_sort_stage2);
 aqc_registrar r_eos("basic/EOS.cl", "entry", 0,
-    { OUT("iset", "unsigned int*"), OUT("imove", "int*"), OUT("rho", "float*"), OUT("p", "float*"),
+    { RO("iset", "unsigned int*"), RO("imove", "int*"), RO("rho", "float*"), OUT("p", "float*"),
       IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"), SC("p0", "float") }, l_eos);
 aqc_registrar r_binormal("basic/Binormal.cl", "entry", 0,
     { IN("normal", "vec*"), OUT("tangent", "vec*"), OUT("binormal", "vec*"), SC("N", "usize") },

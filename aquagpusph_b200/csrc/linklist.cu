@@ -439,6 +439,9 @@ extern "C" int aqc_radix_sort(aqc_ctx* ctx, aqc_usize* keys, aqc_usize n, aqc_us
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_radix_sort: NULL keys");
     if (!n)
         return AQC_OK;
+    aqc_pc_touch(ctx, keys, (size_t)n * sizeof(uint32_t));
+    aqc_pc_touch(ctx, perm, (size_t)n * sizeof(uint32_t));
+    aqc_pc_touch(ctx, inv_perm, (size_t)n * sizeof(uint32_t));
     int rc = ensure_sort_scratch(ctx, n);
     if (rc)
         return rc;
@@ -467,6 +470,7 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
     const float cell_length = support * h;
     if (!cell_length)
         return aqc_fail(ctx, AQC_ERR_ARG, "Zero cell length detected (Invalid number of cells)");
+    aqc_pc_invalidate(ctx); // icell, ihoc and the permutations are rewritten
 
     const int vs = (dims == 3) ? 4 : 2;
     if (recompute_grid) {
@@ -580,6 +584,7 @@ extern "C" int aqc_scatter_fields(aqc_ctx* ctx, const aqc_usize* idx, aqc_usize 
                 return aqc_fail(ctx, AQC_ERR_ARG, "aqc_scatter_fields: in-place field %d", f0 + f);
             P.src[f] = src[f0 + f];
             P.dst[f] = dst[f0 + f];
+            aqc_pc_touch(ctx, dst[f0 + f], (size_t)N * b);
             P.bytes[f] = (int)b;
         }
         scatter_fields_kernel<<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>(idx, N, P);

@@ -219,6 +219,7 @@ extern "C" int aqc_mpi_sync(aqc_ctx* ctx, aqc_usize* mask, aqc_usize n, int nfie
     // MPISync.cpp:186-187: nobody to talk to => nothing happens (the mask is left alone)
     if (ctx->nranks <= 1 || !ctx->comm || !n)
         return AQC_OK;
+    aqc_pc_invalidate(ctx); // the mask and every field are rewritten
     const int P = ctx->nranks, me = ctx->rank;
     std::vector<char> peer(P, procs ? 0 : 1);
     if (procs)
@@ -332,6 +333,7 @@ extern "C" int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, si
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_allreduce: NULL argument");
     if (ctx->nranks <= 1 || !ctx->comm || !count)
         return AQC_OK;
+    aqc_pc_touch(ctx, dev_inout, count * (type == AQC_T_VEC4 ? 16 : type == AQC_T_VEC2 ? 8 : 4));
     int nt, ncomp = 1;
     switch (type) {
         case AQC_T_F32: nt = NCCL_FLOAT32; break;

@@ -133,6 +133,7 @@ extern "C" int aqc_reduce(aqc_ctx* ctx, int op, int type, const void* in, size_t
 {
     if (!ctx || (!in && n))
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_reduce: NULL input");
+    aqc_pc_touch(ctx, out_dev, type == AQC_T_VEC4 ? 16 : type == AQC_T_VEC2 ? 8 : 4);
     switch (type) {
         case AQC_T_F32: return run_op<float, 1>(ctx, op, in, n, out_dev, out_host);
         case AQC_T_U32: return run_op<uint32_t, 1>(ctx, op, in, n, out_dev, out_host);

@@ -374,15 +374,6 @@ constexpr int S3_TILES = S3_TILES_N;           // tiles of a round
 #ifndef S3_BATCH
 #define S3_BATCH 1 // tiles whose global loads the producer keeps in flight together (divides S3_TILES)
 #endif
-#ifndef S3_WAIT_CONSUME
-#define S3_WAIT_CONSUME 0 // a consumer warp waiting for the ring runs its pending pair bodies
-#endif
-#ifndef S3_INTERLEAVE
-#define S3_INTERLEAVE 0 // particles dealt to the consumer warps round-robin instead of in blocks of 32
-#endif
-#ifndef S3_ALTERNATE
-#define S3_ALTERNATE 0 // every other part of an x row is walked backwards (balance between the warps)
-#endif
 #ifndef S3_PROFILE
 #define S3_PROFILE 0 // debug builds only (tools/build_variant.py): per-phase clock64 totals
 #endif
@@ -461,9 +452,31 @@ __device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icel
     return bad;
 }
 
-template <class P>
+// Pair-mask cache of the v3 engine.  The hit masks of the candidate filter depend on the
+// geometry only (positions, link-list, the classes of the particles): every sweep between two
+// changes of those walks the same tiles and finds the same masks.  The reference's midpoint
+// scheme keeps r fixed over the sub-iterations of a step (basic/time_scheme/midpoint.cl:93-111
+// advances u and rho only), so MLS, the fluid pass and lapp_corr of all sub-iterations -- 7
+// sweeps of the 3-D dam-break pipeline -- share one set.  MODE 1 (PMaskBuild) runs the filter
+// alone and stores the masks, MODE 2 reads them instead of filtering; the exact test of every
+// selected pair stays in the pair bodies, so the pair set and the summation order are those of
+// MODE 0 (results bit-identical, tests/test_gpu_kernels.py).
+//   masks    [round][S3_TILES][S3_CWARPS][32]   rounds allocated per (CTA, pass) by the builder
+//   pass_tab [CTA][S3_MAXPASS]                   first round of the pass
+//   ctl      [0] rounds allocated (keeps counting past the capacity: the host grows the buffer
+//            and builds again), [1] bit 0: a CTA needed more than S3_MAXPASS passes
+struct S3Cache {
+    uint32_t* masks = nullptr;
+    uint32_t* pass_tab = nullptr;
+    unsigned long long* ctl = nullptr;
+    uint32_t cap_rounds = 0;
+};
+constexpr int S3_MAXPASS = 32;
+constexpr uint32_t S3_NOPASS = 0xFFFFFFFFu;
+
+template <class P, int MODE>
 __global__ void __launch_bounds__(S3_THREADS, (P::NJ4 <= 2) ? 4 : 3)
-sweep3_kernel(const P p, const LLParams ll, const int K)
+sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 {
     extern __shared__ float4 smem3[];
     constexpr int W = S3_TILES;
@@ -476,11 +489,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [CW][NM][32] masks, then
                                                                                // [CW][NM][32] slot bytes
     __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE], e_lo[S3_MAXE], e_rel[S3_MAXE];
-#if S3_ALTERNATE
-    __shared__ uint32_t e_rev[S3_MAXE]; // tiles of a part that is walked backwards (0: forwards)
-#endif
     __shared__ uint32_t t_cnt[S3_MAXK][W], t_rel[S3_MAXK][W], t_n1[S3_MAXK][W];
-    __shared__ uint32_t s_ball[S3_WARPS], s_c0, s_span, s_last, s_maxk;
+    __shared__ uint32_t s_ball[S3_WARPS], s_c0, s_span, s_firstw, s_lastw, s_maxk, s_base;
     __shared__ float s_o[6];
     // full[k]: the producer has staged ring round k; empty[k]: a consumer warp is done with it
     __shared__ unsigned long long s_full[S3_MAXK], s_empty[S3_MAXK];
@@ -490,18 +500,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     const int cw = warp - 1; // consumer index
     const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(s_full);
     const uint32_t empty_a = (uint32_t)__cvta_generic_to_shared(s_empty);
-#if S3_INTERLEAVE
-    // particle k of the CTA goes to consumer warp k % 7, lane k / 7: every warp holds an even
-    // sample of the CTA's (cell-ordered, spatially coherent) particles, so the warps have the same
-    // amount of work in every round of tiles
-    const uint32_t pidx = producer ? 0u : (uint32_t)(lane * S3_CWARPS + cw);
-#else
-    const uint32_t pidx = (uint32_t)(tid - 32);
-#endif
-    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + pidx;
+    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + (uint32_t)(tid - 32);
     const bool valid = !producer && i < ll.N;
     const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
-    const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    // the passes of a CTA are made of ALL its particles, whatever the kernel's i set: the
+    // tiles of a pass are then the same for every kernel (the mask cache relies on it)
+    const uint32_t c_i = valid ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
     typename P::IState st;
     st.x = st.y = st.z = 0.f;
     if (active)
@@ -517,7 +521,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
     uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ) + 31 * 16;
     asm volatile("" : "+r"(Mw_a), "+r"(Sw_a), "+r"(sJ_a));
 
-    bool pending = active;
+    bool pending = valid && c_i < ll.nw;
     for (uint32_t npass = 0;; npass++) {
         // ---- the group of this pass: first pending particle and its x-row neighbours
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);
@@ -525,7 +529,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             s_ball[warp] = pb;
         if (tid == 0) {
             s_span = 0;
-            s_last = 0;
+            s_firstw = 0xFFFFFFFFu;
+            s_lastw = 0;
             s_maxk = 0;
             for (int k = 0; k < K; k++) { // nobody is inside a round loop here
                 if (npass) {
@@ -538,54 +543,38 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         }
         __syncthreads();
         int first = -1;
-#if S3_INTERLEAVE
-        {
-            int best = 1 << 30;
-#pragma unroll
-            for (int w = 1; w < S3_WARPS; w++)
-                if (s_ball[w]) {
-                    const int l = __ffs(s_ball[w]) - 1, k = l * S3_CWARPS + (w - 1);
-                    if (k < best) {
-                        best = k;
-                        first = w * 32 + l;
-                    }
-                }
-        }
-#else
 #pragma unroll
         for (int w = S3_WARPS - 1; w >= 0; w--)
             if (s_ball[w])
                 first = w * 32 + __ffs(s_ball[w]) - 1;
-#endif
         if (first < 0)
             break;
-        if (tid == first) {
+        if (tid == first)
             s_c0 = c_i;
-            s_o[0] = st.x; s_o[1] = st.y; s_o[2] = st.z;
-        }
         __syncthreads();
         const uint32_t c0 = s_c0;
         const uint32_t a_i = c_i - c0;
         const bool mine = pending && (a_i <= (uint32_t)S3_SPAN);
+        const bool work = mine && active; // the lanes that take part in the pair work
         const uint32_t mine_w = __ballot_sync(0xffffffffu, mine);
+        const uint32_t work_w = __ballot_sync(0xffffffffu, work);
         if (mine_w) {
             const uint32_t sp = __reduce_max_sync(0xffffffffu, mine ? a_i : 0u);
-            if (lane == 0) {
+            if (lane == 0)
                 atomicMax(&s_span, sp);
-#if S3_INTERLEAVE
-                atomicMax(&s_last, (uint32_t)((31 - __clz(mine_w)) * S3_CWARPS + cw));
-#else
-                atomicMax(&s_last, (uint32_t)(warp * 32 + 31 - __clz(mine_w)));
-#endif
-            }
+        }
+        if (work_w && lane == 0) {
+            atomicMin(&s_firstw, (uint32_t)(warp * 32 + __ffs(work_w) - 1));
+            atomicMax(&s_lastw, (uint32_t)(warp * 32 + 31 - __clz(work_w)));
         }
         pending = pending && !mine;
         __syncthreads();
-#if S3_INTERLEAVE
-        if (!producer && pidx == s_last) {
-#else
-        if (tid == (int)s_last) {
-#endif
+        if (s_firstw == 0xFFFFFFFFu)
+            continue; // no particle of the group belongs to the kernel's i set
+        if (tid == (int)s_firstw) {
+            s_o[0] = st.x; s_o[1] = st.y; s_o[2] = st.z;
+        }
+        if (tid == (int)s_lastw) {
             s_o[3] = st.x; s_o[4] = st.y; s_o[5] = st.z;
         }
         const uint32_t len = s_span + 3u, nparts = (len + 1u) / 2u;
@@ -621,23 +610,37 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             e_end[tid] = en;
             e_lo[tid] = lo;
             e_rel[tid] = lo - base; // x offset of cell lo relative to c0, plus one
-#if S3_ALTERNATE
-            // odd parts are walked from their last tile to their first one: while the warps of
-            // the group's first cells work on the lower cell of part 0 (which the others do not
-            // need), the warps of the next cells work on the upper cell of part 1
-            e_rev[tid] = (part & 1u) ? (en - b + 31u) / 32u : 0u;
-#endif
             if (en > b)
                 atomicMax(&s_maxk, (en - b + 31u) / 32u);
         }
         __syncthreads();
         const uint32_t maxk = s_maxk;
-        // origin of the relative coordinates: between the first and the last member (kept in
-        // shared memory: only the staging needs it)
+        const uint32_t nrounds = (maxk * NE + W - 1) / W;
         if (tid == 0) {
+            // origin of the relative coordinates: between the first and the last working
+            // member (kept in shared memory: only the staging needs it)
             s_o[0] = 0.5f * (s_o[0] + s_o[3]);
             s_o[1] = 0.5f * (s_o[1] + s_o[4]);
             s_o[2] = (P::DIMS == 3) ? 0.5f * (s_o[2] + s_o[5]) : 0.f;
+            if constexpr (MODE == 1) { // rounds of this pass in the mask array
+                uint32_t base = S3_NOPASS;
+                if (npass < (uint32_t)S3_MAXPASS) {
+                    const unsigned long long b = atomicAdd(pc.ctl, (unsigned long long)nrounds);
+                    if (b + nrounds <= (unsigned long long)pc.cap_rounds)
+                        base = (uint32_t)b;
+                    pc.pass_tab[(size_t)blockIdx.x * S3_MAXPASS + npass] = base;
+                } else {
+                    atomicOr(pc.ctl + 1, 1ull);
+                }
+                s_base = base;
+            } else if constexpr (MODE == 2) {
+                const uint32_t base = (npass < (uint32_t)S3_MAXPASS)
+                                          ? pc.pass_tab[(size_t)blockIdx.x * S3_MAXPASS + npass]
+                                          : S3_NOPASS;
+                if (base == S3_NOPASS && nrounds) // the host never hands over an incomplete cache
+                    __trap();
+                s_base = base;
+            }
         }
         __syncthreads();
         // filter constants of this lane: -2 r_i and |r_i|^2 - cut^2, relative to the origin
@@ -657,6 +660,11 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cslot) : "r"(Sw_a + qr * 32) : "memory");
             qr = (qr + 1 == NM) ? 0u : qr + 1;
             crow = sJ_a + cslot * (SLOT4 * 16);
+        };
+        auto push = [&](uint32_t m, uint32_t slot) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(Mw_a + qw * 128), "r"(m) : "memory");
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(Sw_a + qw * 32), "r"(slot) : "memory");
+            qw = (qw + 1 == NM) ? 0u : qw + 1;
         };
         auto body1 = [&]() { // cur != 0: the next hit of this lane
             uint32_t f;
@@ -716,9 +724,9 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         };
         // stage (producer warp): S3_BATCH consecutive tiles of a round at a time; tile number tn =
         // (part e = tn % NE, its k-th tile, k = tn / NE), carried in (tk, te).  The global loads
-        // of the whole batch are issued before any of them is used, so a round costs
-        // W / S3_BATCH memory latencies instead of W (branch-free: a lane without a candidate
-        // loads particle 0 and drops it).
+        // of a batch are issued before any of them is used (branch-free: a lane without a
+        // candidate loads particle 0 and drops it).  MODE 1 stages the test layout only, MODE 2
+        // the j rows only.
         uint32_t tk = 0, te = 0;
         auto stage_batch = [&](uint32_t ring_round, uint32_t w0) {
             const uint32_t par = ring_round;
@@ -732,16 +740,11 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                     tk++;
                 }
                 eb[b] = e;
-#if S3_ALTERNATE
-                const uint32_t nrev = e_rev[e];
-                const uint32_t kk = nrev ? nrev - 1u - k : k; // k >= nrev wraps: bg >= en below
-                const uint32_t bg = (nrev && k >= nrev) ? ll.N : e_begin[e] + 32u * kk, en = e_end[e];
-#else
                 const uint32_t bg = e_begin[e] + 32u * k, en = e_end[e];
-#endif
                 cnt[b] = (k < maxk && bg < en) ? min(32u, en - bg) : 0u;
                 const uint32_t jj = ((uint32_t)lane < cnt[b]) ? bg + lane : 0u;
-                cj[b] = __ldg(ll.icell + jj) - e_lo[e];
+                if constexpr (MODE != 2)
+                    cj[b] = __ldg(ll.icell + jj) - e_lo[e];
                 p.stage_j(jj, o[b]);
             }
 #pragma unroll
@@ -750,41 +753,46 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
                 uint32_t c = cnt[b];
                 if (c) {
                     const bool in = (uint32_t)lane < c;
-                    float4* const slot = sJ + (size_t)(ring_round * W + w2) * SLOT4;
-                    float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
-                    bool live = false;
-                    if (in) {
+                    if constexpr (MODE != 1) {
+                        float4* const slot = sJ + (size_t)(ring_round * W + w2) * SLOT4;
+                        if (in) {
 #pragma unroll
-                        for (int q = 0; q < P::NJ4; q++)
-                            slot[q * 32 + lane] = o[b][q];
-                        live = P::j_live(o[b][0]);
+                            for (int q = 0; q < P::NJ4; q++)
+                                slot[q * 32 + lane] = o[b][q];
+                        }
+                    }
+                    if constexpr (MODE != 2) {
+                        float tx = 0.f, ty = 0.f, tz = 0.f, tn2 = AQC_NEVER;
+                        const bool live = in && P::j_live(o[b][0]);
                         if (live) {
                             tx = o[b][0].x - s_o[0];
                             ty = o[b][0].y - s_o[1];
                             tz = (P::DIMS == 3) ? o[b][0].z - s_o[2] : 0.f;
                             tn2 = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
                         }
-                    }
-                    float* const tst = reinterpret_cast<float*>(sT + (par * W + w2) * 32) +
-                                       (lane >> 1) * 8 + (lane & 1);
-                    tst[0] = tx;
-                    tst[2] = ty;
-                    tst[4] = tz;
-                    tst[6] = tn2;
-                    // a tile without a candidate that can interact at all is dropped (a tile of
-                    // fluid particles costs a boundary kernel its staging only)
-                    if (!__any_sync(0xffffffffu, live))
-                        c = 0;
-                    const uint32_t cjv = in ? cj[b] : 0xFFFFFFFFu;
-                    const uint32_t cj0 = __shfl_sync(0xffffffffu, cjv, 0);
-                    const int n1 = __popc(__ballot_sync(0xffffffffu, cjv == cj0));
-                    if (lane == 0) {
-                        t_rel[par][w2] = e_rel[eb[b]] + cj0;
-                        t_n1[par][w2] = (uint32_t)n1;
+                        float* const tst = reinterpret_cast<float*>(sT + (par * W + w2) * 32) +
+                                           (lane >> 1) * 8 + (lane & 1);
+                        tst[0] = tx;
+                        tst[2] = ty;
+                        tst[4] = tz;
+                        tst[6] = tn2;
+                        // a tile without a candidate that can interact at all is dropped (a tile
+                        // of fluid particles costs a boundary kernel its staging only)
+                        if (!__any_sync(0xffffffffu, live))
+                            c = 0;
+                        const uint32_t cjv = in ? cj[b] : 0xFFFFFFFFu;
+                        const uint32_t cj0 = __shfl_sync(0xffffffffu, cjv, 0);
+                        const int n1 = __popc(__ballot_sync(0xffffffffu, cjv == cj0));
+                        if (lane == 0) {
+                            t_rel[par][w2] = e_rel[eb[b]] + cj0;
+                            t_n1[par][w2] = (uint32_t)n1;
+                        }
                     }
                 }
-                if (lane == 0)
-                    t_cnt[par][w2] = c;
+                if constexpr (MODE != 2) {
+                    if (lane == 0)
+                        t_cnt[par][w2] = c;
+                }
             }
         };
 
@@ -794,7 +802,6 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         // balanced bodies, and releases round r + 2 - K after consuming the hits it still had
         // in it.  A consumer never waits for another consumer: only the ring couples them, so
         // warps may drift apart by K - 1 rounds before anybody stalls.
-        const uint32_t nrounds = (maxk * NE + W - 1) / W;
         if (producer) {
             uint32_t rk = 0, use = 0; // ring round r % K, r / K
             S3P_START
@@ -824,84 +831,113 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
             uint32_t rq = 0;           // ring round of round r + 2 - K, the next one to release
             const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
                                      C2 = pack2(fc, fc);
+            const uint32_t mbase = s_base;
 #if S3_PROFILE
-            const int s3p_c = mine_w ? 0 : 8; // warps without a member of the group: second bank
+            const int s3p_c = work_w ? 0 : 8; // warps without a working lane: second bank
 #endif
             S3P_START
             for (uint32_t r = 0; r < nrounds; r++) {
                 S3P_ACC(s3p_c + 5)
+                // MODE 2: the masks of the round are requested before its rows are waited for
+                uint32_t mk[W];
+                if constexpr (MODE == 2) {
+                    const uint32_t* src = pc.masks + ((size_t)(mbase + r) * W * S3_CWARPS + cw) * 32 + lane;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; w2++)
+                        mk[w2] = work ? __ldg(src + w2 * (S3_CWARPS * 32)) : 0u;
+                }
                 {
                     uint32_t spins = 0;
-#if S3_WAIT_CONSUME
-                    // not full yet: the time is spent on pending pair bodies (whatever the lane
-                    // balance) instead of polling; a warp without any suspends in try_wait
-                    for (;;) {
-                        const bool has = __any_sync(0xffffffffu, cur != 0);
-                        const bool ok = has ? mbar_test(full_a + 8 * rk, use & 1u)
-                                            : mbar_wait(full_a + 8 * rk, use & 1u);
-                        if (__all_sync(0xffffffffu, ok))
-                            break;
-                        if (has)
-                            consume();
-                        else if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
-                            __trap();
-                    }
-#else
                     while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u)))
                         if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
-#endif
                 }
                 S3P_ACC(s3p_c + 0)
-                // ---- filter: record the hit masks of the round's tiles
-                if (mine) {
+                if constexpr (MODE == 1) {
+                    // ---- filter only: the masks go to the cache (zero for the lanes that do
+                    // not work and for the tiles that are not theirs)
+                    uint32_t* dst = pc.masks + ((size_t)(mbase + r) * W * S3_CWARPS + cw) * 32 + lane;
 #pragma unroll 1
                     for (int w2 = 0; w2 < W; w2++) {
+                        uint32_t m = 0;
                         const uint32_t cnt = t_cnt[rk][w2];
-                        if (!cnt)
-                            continue;
-                        const uint32_t rel = t_rel[rk][w2] - a_i; // (x offset of the lower cell - a_i) + 1
-                        const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[rk][w2]);
-                        const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
-                        if (!okm)
-                            continue;
-                        const float4* T = sT + (rk * W + w2) * 32;
-                        uint32_t m;
-                        if (cnt > 16)
-                            m = test_tile<16>(T, X2, Y2, Z2, C2);
-                        else if (cnt > 8)
-                            m = test_tile<8>(T, X2, Y2, Z2, C2);
-                        else
-                            m = test_tile<4>(T, X2, Y2, Z2, C2);
-                        m &= okm;
-                        if (m) {
-                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(Mw_a + qw * 128), "r"(m) : "memory");
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(Sw_a + qw * 32), "r"(rk * W + w2) : "memory");
-                            qw = (qw + 1 == NM) ? 0u : qw + 1;
+                        if (work && cnt) {
+                            const uint32_t rel = t_rel[rk][w2] - a_i;
+                            const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[rk][w2]);
+                            const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
+                            if (okm) {
+                                const float4* T = sT + (rk * W + w2) * 32;
+                                if (cnt > 16)
+                                    m = test_tile<16>(T, X2, Y2, Z2, C2);
+                                else if (cnt > 8)
+                                    m = test_tile<8>(T, X2, Y2, Z2, C2);
+                                else
+                                    m = test_tile<4>(T, X2, Y2, Z2, C2);
+                                m &= okm;
+                            }
                         }
+                        __syncwarp();
+                        if (mbase != S3_NOPASS)
+                            dst[w2 * (S3_CWARPS * 32)] = m;
                     }
-                    if (!cur && qr != qw)
-                        pick();
-                    S3P_ACC(s3p_c + 1)
-                    // ---- bodies, while every member lane of the warp has one pending
-                    while (__ballot_sync(mine_w, cur != 0) == mine_w) {
-                        if constexpr (P::PAIR2)
-                            body2();
-                        else
-                            body1();
-                    }
-                }
-                __syncwarp();
-                S3P_ACC(s3p_c + 2)
-                // ---- release round r + 2 - K: its hits are the oldest of every FIFO, a lane is
-                // done with them when the tile it works on is a newer one
-                if (r + 2 >= (uint32_t)K) {
-                    while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rq))
-                        consume();
                     __syncwarp();
                     if (lane == 0)
-                        mbar_arrive(empty_a + 8 * rq);
-                    rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
+                        mbar_arrive(empty_a + 8 * rk);
+                } else {
+                    if (work) {
+                        if constexpr (MODE == 2) {
+#pragma unroll
+                            for (int w2 = 0; w2 < W; w2++)
+                                if (mk[w2])
+                                    push(mk[w2], rk * W + w2);
+                        } else {
+                            // ---- filter: record the hit masks of the round's tiles
+#pragma unroll 1
+                            for (int w2 = 0; w2 < W; w2++) {
+                                const uint32_t cnt = t_cnt[rk][w2];
+                                if (!cnt)
+                                    continue;
+                                const uint32_t rel = t_rel[rk][w2] - a_i; // (x offset of the lower cell - a_i) + 1
+                                const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[rk][w2]);
+                                const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
+                                if (!okm)
+                                    continue;
+                                const float4* T = sT + (rk * W + w2) * 32;
+                                uint32_t m;
+                                if (cnt > 16)
+                                    m = test_tile<16>(T, X2, Y2, Z2, C2);
+                                else if (cnt > 8)
+                                    m = test_tile<8>(T, X2, Y2, Z2, C2);
+                                else
+                                    m = test_tile<4>(T, X2, Y2, Z2, C2);
+                                m &= okm;
+                                if (m)
+                                    push(m, rk * W + w2);
+                            }
+                        }
+                        if (!cur && qr != qw)
+                            pick();
+                        S3P_ACC(s3p_c + 1)
+                        // ---- bodies, while every working lane of the warp has one pending
+                        while (__ballot_sync(work_w, cur != 0) == work_w) {
+                            if constexpr (P::PAIR2)
+                                body2();
+                            else
+                                body1();
+                        }
+                    }
+                    __syncwarp();
+                    S3P_ACC(s3p_c + 2)
+                    // ---- release round r + 2 - K: its hits are the oldest of every FIFO, a lane
+                    // is done with them when the tile it works on is a newer one
+                    if (r + 2 >= (uint32_t)K) {
+                        while (__any_sync(0xffffffffu, cur != 0 && cslot / W == rq))
+                            consume();
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(empty_a + 8 * rq);
+                        rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
+                    }
                 }
                 S3P_ACC(s3p_c + 3)
                 if (++rk == (uint32_t)K) {
@@ -912,7 +948,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         }
 #if S3_PROFILE
         long long s3p_t = clock64();
-        const int s3p_c2 = producer ? 24 : (mine_w ? 0 : 8);
+        const int s3p_c2 = producer ? 24 : (work_w ? 0 : 8);
 #endif
         while (__any_sync(0xffffffffu, cur != 0))
             consume();
@@ -921,7 +957,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
         S3P_ACC(s3p_c2 + 6)
 #if S3_PROFILE
         if (tid == 0) {
-            atomicAdd(&g_s3prof[30], (unsigned long long)nrounds);
+            atomicAdd(&g_s3prof[29], (unsigned long long)nrounds);
             atomicAdd(&g_s3prof[31], 1ull);
         }
 #endif
@@ -933,6 +969,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K)
 int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
 bool aqc_sweep_engine_forced(); // chosen explicitly (environment or aqc_sweep_engine_select)
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
+int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2, const LLParams& ll,
+                   uint32_t icls, uint32_t jcls, int K, S3Cache* out); // sweeps.cu
 
 template <class P>
 static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
@@ -969,13 +1007,30 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
             const size_t NS = (size_t)K * S3_TILES;
             const size_t smem = (NS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
                                 S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
+            S3Cache pc;
+            int cached = 0;
+            if constexpr (P::CACHE) {
+                cached = aqc_pc_prepare(ctx, p.imove, p.r, P::DIMS, p.cut2, ll, p.icls(), p.jcls(), K, &pc);
+                if (cached < 0)
+                    return cached;
+            }
             static size_t configured = 0; // per instantiation
             if (smem > configured) {
-                AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P>,
+                AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 0>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if constexpr (P::CACHE)
+                    AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = smem;
             }
-            sweep3_kernel<P><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K);
+            if constexpr (P::CACHE) {
+                if (cached)
+                    sweep3_kernel<P, 2><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+                else
+                    sweep3_kernel<P, 0><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+            } else {
+                sweep3_kernel<P, 0><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+            }
         } else {
             sweep2_kernel<P><<<aqc_blocks(ll.N, SWEEP_THREADS), SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
         }

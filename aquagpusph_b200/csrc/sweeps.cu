@@ -161,6 +161,12 @@ struct PBase {
     // staged row so that body() adds exactly +-0 for it.
     static constexpr bool PAIR2 = false;
     __device__ static void kill(float4* v) { v[0].w = 0.f; }
+    // v3 engine: the kernel may read the pair-mask cache (sweep.cuh, S3Cache).  icls() / jcls()
+    // = classes (aqc_cls_bit) its i and j particles can belong to; they must cover i_active()
+    // and the candidates stage_j() leaves alive.
+    static constexpr bool CACHE = false;
+    uint32_t icls() const { return 0xFFu; }
+    uint32_t jcls() const { return 0xFFu; }
 };
 
 // ------------------------------------------------------------------------
@@ -168,6 +174,9 @@ struct PBase {
 template <int D>
 struct PInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = true;
+    uint32_t icls() const { return 1u; }
+    uint32_t jcls() const { return 1u; }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u;
@@ -230,6 +239,9 @@ struct PInteractions : PBase {
 template <int D, int MODE>
 struct PShepard : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = MODE == 1; // (MODE 0 also serves imove == 2)
+    uint32_t icls() const { return 31u; }
+    uint32_t jcls() const { return 1u; }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
@@ -269,6 +281,9 @@ struct PShepard : PBase {
 template <int D, bool VECOUT>
 struct PDeltaGrad : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = true;
+    uint32_t icls() const { return 1u; }
+    uint32_t jcls() const { return 1u; }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
@@ -320,6 +335,9 @@ struct PDeltaGrad : PBase {
 template <int D>
 struct PLappCorr : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = true;
+    uint32_t icls() const { return 1u; }
+    uint32_t jcls() const { return 1u; }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void* r;
@@ -364,6 +382,9 @@ struct PLappCorr : PBase {
 template <int D>
 struct PMLS : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = true;
+    uint32_t icls() const { return aqc_cls_bit((int)mls_imove); }
+    uint32_t jcls() const { return aqc_cls_bit((int)mls_imove); }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 1;
     const void* r;
@@ -1198,6 +1219,9 @@ struct PElasticBounce : PBase {
 template <int D, bool SHEP, bool FULL, bool LAPP>
 struct PFusedFluid : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool CACHE = true;
+    uint32_t icls() const { return SHEP ? 31u : 1u; }
+    uint32_t jcls() const { return 1u; }
     static constexpr bool PAIR2 = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u;
@@ -1319,6 +1343,140 @@ struct PCountPairs : PBase {
     __device__ void body(IState& s, const float4*, int) const { s.n++; }
     __device__ void store_i(const IState& s, uint32_t i) const { n_pairs[i] = s.n; }
 };
+
+// ------------------------------------------------------------------------
+// Builder of the pair-mask cache (sweep3_kernel MODE 1): the candidate filter alone, for the i
+// particles of the classes icl against the j particles of the classes jcl.
+template <int D>
+struct PMaskBuild : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void* r;
+    uint32_t icl, jcl;
+    struct IState { float x, y, z; };
+    __device__ bool i_active(int mv) const { return (aqc_cls_bit(mv) & icl) != 0; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        o[0] = make_float4((aqc_cls_bit(__ldg(imove + j)) & jcl) ? a.x : AQC_FAR, a.y, a.z, 0.f);
+    }
+    __device__ bool test(const IState&, const float4&) const { return false; }
+    __device__ void body(IState&, const float4*, int) const {}
+    __device__ void store_i(const IState&, uint32_t) const {}
+};
+
+template <int D>
+int pc_build(aqc_ctx* ctx, const LLParams& ll, int K)
+{
+    aqc_pair_cache& c = ctx->pc;
+    PMaskBuild<D> p;
+    p.imove = (const int*)c.imove;
+    p.invH = 0.f;
+    p.cut2 = c.cut2;
+    p.r = c.r;
+    p.icl = c.icls_want;
+    p.jcl = c.jcls_want;
+    S3Cache pc;
+    pc.masks = c.masks;
+    pc.pass_tab = c.pass_tab;
+    pc.ctl = c.ctl;
+    pc.cap_rounds = (uint32_t)c.cap_rounds;
+    const size_t NS = (size_t)K * S3_TILES;
+    const size_t smem = (NS * 32 + NS * 32) * sizeof(float4) + S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
+    static size_t configured = 0;
+    if (smem > configured) {
+        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    sweep3_kernel<PMaskBuild<D>, 1><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    AQC_LAUNCH_CHECK(ctx);
+    return AQC_OK;
+}
+
+} // namespace
+
+// 1: *out describes masks that are valid for this sweep; 0: the sweep has to filter; < 0: error
+int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2,
+                   const LLParams& ll, uint32_t icls, uint32_t jcls, int K, S3Cache* out)
+{
+    aqc_pair_cache& c = ctx->pc;
+    if (!c.enabled || ((icls | jcls) & ~31u) || ll.icell_i != ll.icell || ll.cls)
+        return 0;
+    const bool same = c.valid && c.r == r && c.imove == imove && c.icell == ll.icell && c.ihoc == ll.ihoc &&
+                      c.N == ll.N && c.nx == ll.nx && c.ny == ll.ny && c.nz == ll.nz && c.nw == ll.nw &&
+                      c.dims == dims && c.cut2 == cut2 && !(icls & ~c.icls) && !(jcls & ~c.jcls);
+    if (!same) {
+        c.valid = false;
+        c.icls_want |= icls;
+        c.jcls_want |= jcls;
+        c.r = r; c.imove = imove; c.icell = ll.icell; c.ihoc = ll.ihoc;
+        c.N = ll.N; c.nx = ll.nx; c.ny = ll.ny; c.nz = ll.nz; c.nw = ll.nw;
+        c.dims = dims; c.cut2 = cut2;
+        const size_t nblk = aqc_blocks(ll.N, S3_PARTICLES);
+        if (!c.ctl) {
+            AQC_CUDA(ctx, cudaMalloc(&c.ctl, 2 * sizeof(unsigned long long)));
+            AQC_CUDA(ctx, cudaMallocHost(&c.ctl_host, 2 * sizeof(unsigned long long)));
+        }
+        if (nblk * S3_MAXPASS > c.pass_cap) {
+            if (c.pass_tab)
+                AQC_CUDA(ctx, cudaFree(c.pass_tab));
+            c.pass_tab = nullptr;
+            c.pass_cap = 0;
+            AQC_CUDA(ctx, cudaMalloc(&c.pass_tab, nblk * S3_MAXPASS * sizeof(uint32_t)));
+            c.pass_cap = nblk * S3_MAXPASS;
+        }
+        size_t want = c.cap_rounds ? c.cap_rounds : nblk * (dims == 3 ? 40 : 12);
+        for (int attempt = 0;; attempt++) {
+            if (want > c.cap_rounds) {
+                if (c.masks) {
+                    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    AQC_CUDA(ctx, cudaFree(c.masks));
+                }
+                c.masks = nullptr;
+                c.cap_rounds = 0;
+                if (want >= 0xFFFFFFF0ull)
+                    return 0; // beyond the 32-bit round index: no cache
+                AQC_CUDA(ctx, cudaMalloc(&c.masks, want * (size_t)(S3_TILES * S3_CWARPS * 32) * sizeof(uint32_t)));
+                c.cap_rounds = want;
+            }
+            AQC_CUDA(ctx, cudaMemsetAsync(c.ctl, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            AQC_CUDA(ctx, cudaMemsetAsync(c.pass_tab, 0xFF, nblk * S3_MAXPASS * sizeof(uint32_t), ctx->stream));
+            const int rc = (dims == 3) ? pc_build<3>(ctx, ll, K) : pc_build<2>(ctx, ll, K);
+            if (rc)
+                return rc;
+            AQC_CUDA(ctx, cudaMemcpyAsync(c.ctl_host, c.ctl, 2 * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (c.ctl_host[0] <= c.cap_rounds)
+                break;
+            if (attempt)
+                return aqc_fail(ctx, AQC_ERR_CUDA, "pair-mask cache: %llu rounds do not fit %zu after growing",
+                                c.ctl_host[0], c.cap_rounds);
+            want = (size_t)(c.ctl_host[0] + c.ctl_host[0] / 8 + 64);
+        }
+        c.unusable = (c.ctl_host[1] & 1ull) != 0;
+        c.icls = c.icls_want;
+        c.jcls = c.jcls_want;
+        c.valid = true;
+        c.builds++;
+    }
+    if (c.unusable)
+        return 0;
+    c.hits++;
+    out->masks = c.masks;
+    out->pass_tab = c.pass_tab;
+    out->ctl = c.ctl;
+    out->cap_rounds = (uint32_t)c.cap_rounds;
+    return 1;
+}
+
+namespace {
 
 // ------------------------------------------------------------------------
 // basic/neighs.cl:52-91: candidates are counted without any distance test, so
@@ -1866,6 +2024,20 @@ extern "C" int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, i
     for (int k = 0; k < nargs; k++)
         if (!args[k])
             return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: argument %d is NULL", k);
+    {
+        int k0 = 0; // the members' output arrays
+        for (auto nm : tab[fused_id].members) {
+            const char* sep = strstr(nm, "::");
+            const std::string script(nm, sep - nm);
+            const int id = aqc_kernel_lookup(script.c_str(), sep + 2, ctx->defs.dims);
+            const aqc_arg_info* ai = aqc_kernel_args(id);
+            const int na = aqc_kernel_nargs(id);
+            for (int k = 0; k < na; k++)
+                if (ai[k].kind == AQC_ARG_ARRAY_OUT)
+                    aqc_pc_touch(ctx, args[k0 + k], (size_t)ctx->pc.N * aqc_type_bytes(ai[k].type, ctx->defs.dims));
+            k0 += na;
+        }
+    }
     return tab[fused_id].fn(ctx, args);
 }
 

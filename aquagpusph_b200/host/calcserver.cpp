@@ -770,6 +770,12 @@ CalcServer::CalcServer(ProblemSetup& sd, int device, int mpi_rank, int mpi_size)
     }
     if (aqc_ctx_create(device, &_ctx))
         throw std::runtime_error(std::string("Cannot create the CUDA context: ") + aqc_last_error(nullptr));
+    {
+        // every array is written through libaquacuda here, so the pair-mask cache of the neighbour
+        // sweeps is safe (aquacuda.h); AQC_PAIR_CACHE=0 turns it off for A/B measurements
+        const char* e = getenv("AQC_PAIR_CACHE");
+        aqc_pairs_cache_enable(_ctx, (e && atoi(e) == 0) ? 0 : 1);
+    }
     _vars = std::make_unique<Variables>(sd.dims, _ctx);
 
     size_t N = 0;

@@ -189,6 +189,7 @@ def run_ours(a, rank, world, local_rank):
         return sum(n for name, n, _ in sim.tool_times() if name == "cfd interactions")
 
     inner = -sweeps_done()
+    pc0 = actx.pairs_cache_stats()
     barrier()
     actx.record(e0)
     for _ in range(a.steps):
@@ -196,6 +197,7 @@ def run_ours(a, rank, world, local_rank):
     actx.record(e1)
     barrier()
     inner += sweeps_done()
+    pc1 = actx.pairs_cache_stats()
     ms = max_over_ranks(actx.elapsed_ms(e0, e1))
     launches = sim.launch_count() - l0
     value = N_all * a.steps / (ms * 1e-3)
@@ -353,7 +355,12 @@ def run_ours(a, rank, world, local_rank):
                    "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
                    "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv, dt and residual "
                                  "all-reduced") if world > 1 else "single GPU",
-                   "one_gpu_same_pipeline": same1},
+                   "one_gpu_same_pipeline": same1,
+                   # neighbour sweeps that read the hit masks of one builder pass instead of
+                   # filtering their candidates again (include/aquacuda.h, aqc_pairs_cache_*)
+                   "pair_mask_cache": {"builds_per_step": (pc1["builds"] - pc0["builds"]) / a.steps,
+                                       "sweeps_served_per_step": (pc1["hits"] - pc0["hits"]) / a.steps,
+                                       "device_bytes": pc1["bytes"]}},
         "e2e": {"value": e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": launches,

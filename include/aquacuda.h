@@ -132,7 +132,9 @@ int aqc_reduce(aqc_ctx* ctx, int op, int type, const void* in, size_t n,
  * the hot-path scripts are pre-built CUDA kernels kept in a registry keyed by
  * the script path (as written in the presets, e.g. "cfd/Interactions.cl" --
  * any leading directories up to "Scripts/" are ignored) and entry point. ----- */
-enum { AQC_ARG_ARRAY_IN = 0, AQC_ARG_ARRAY_OUT = 1, AQC_ARG_SCALAR = 2 };
+/* ARRAY_RO: declared without const in the reference's script but never written by the kernel
+ * (e.g. iset, imove, rho of basic/EOS.cl:57-73): a read for every dependency purpose */
+enum { AQC_ARG_ARRAY_IN = 0, AQC_ARG_ARRAY_OUT = 1, AQC_ARG_SCALAR = 2, AQC_ARG_ARRAY_RO = 3 };
 typedef struct {
     const char* name; /* Variable name to bind (Kernel.cpp:497-556) */
     const char* type; /* reference type string: "vec*", "float", "usize", "svec4", ... */
@@ -177,6 +179,22 @@ int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs);
  * environment, else v3 except for 2-D problems below ~1 M particles, where the per-warp engine
  * is faster).  For A/B measurements and order-sensitive tests. */
 int aqc_sweep_engine_select(int engine);
+
+/* ---- pair-mask cache of the neighbour sweeps.  Every BEGIN_NEIGHS/END_NEIGHS kernel of the
+ * reference re-walks the 27 (9) cells and re-tests every candidate (types/3D.h:197-219), although
+ * between two link-list builds most sweeps see the same positions: the midpoint scheme keeps r
+ * fixed over its sub-iterations (basic/time_scheme/midpoint.cl:93-111), so MLS and the three
+ * fluid / lapp_corr passes of a step find the same neighbours.  With the cache enabled the
+ * first such sweep after a change builds the hit masks of the candidate filter (device memory:
+ * ~1 KB per particle in 3-D) and the following ones read them instead of filtering; every pair
+ * is still re-tested exactly, so the results are bit-identical with and without the cache.
+ * The cache is dropped whenever r, imove, icell or ihoc is written THROUGH THIS LIBRARY (copies,
+ * fills, kernel outputs, link-list, sort, scatter, mpi-sync); a caller that writes them by other
+ * means (its own kernels) must call aqc_pairs_cache_invalidate.  Off by default. ------------- */
+int aqc_pairs_cache_enable(aqc_ctx* ctx, int on);
+int aqc_pairs_cache_invalidate(aqc_ctx* ctx);
+/* builds / sweeps served so far, bytes of device memory held (any pointer may be NULL) */
+int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes);
 
 /* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI
  * rank/size queries and wrappers (AuxiliarMethods.cpp:388-516) and the MPISync

@@ -113,3 +113,81 @@ def test_fused_fluid_sweep_equals_its_members(oracle, dims, n, hfac):
     ids = (C.c_int * 2)(ctx.lookup("cfd/Rates.cl", "entry"), ctx.lookup("cfd/Interactions.cl", "entry"))
     assert L.aqc_fused_lookup(ids, 2, dims) < 0
     ctx.close()
+
+
+@pytest.mark.parametrize("dims,n,hfac,scale", [(3, 14, 2.0, 1.0), (3, 10, 3.0, 1.0), (2, 60, 3.0, 1.0),
+                                               (3, 10, 3.0, 3.5), (3, 12, 2.0, 0.45)])
+def test_pair_mask_cache_is_bit_identical(oracle, dims, n, hfac, scale):
+    """aqc_pairs_cache_enable: MLS, Shepard, Interactions, delta-SPH full / lapp / lapp_corr read the
+    hit masks one builder pass stored instead of filtering.  Every selected pair is still tested
+    exactly and the hits are consumed in the same order, so every output must be BIT-identical
+    with and without the cache -- also on stretched positions (a CTA spans dozens of cells: more
+    passes than the pass table holds, the sweeps fall back to filtering) and compressed ones."""
+    case = cases.dam_break(dims, n, hfac)
+    if scale != 1.0:
+        case["r"] = (case["r"] * np.float32(scale)).astype(np.float32)
+        case["domain_min"] = (np.asarray(case["domain_min"]) * np.float32(scale) - 1).astype(np.float32)
+        case["domain_max"] = (np.asarray(case["domain_max"]) * np.float32(scale) + 1).astype(np.float32)
+    s = pipeline.oracle_linklist_and_sort(case)
+    L = _lib.lib()
+    out, stats = [], None
+    try:
+        assert L.aqc_sweep_engine_select(3) == 3
+        for cache in (False, True):
+            ctx = _lib.Context(0, dims=dims, h=case["h"])
+            ctx.pairs_cache(cache)
+            out.append(pipeline.cuda_sweeps(ctx, s))
+            if cache:
+                stats = ctx.pairs_cache_stats()
+            ctx.close()
+    finally:
+        L.aqc_sweep_engine_select(-1)
+    for k in out[0]:
+        a, b = np.asarray(out[0][k]), np.asarray(out[1][k])
+        assert a.tobytes() == b.tobytes(), k
+    # one build serves the sweeps up to the first kernel that writes r (PST, at the end)
+    assert stats["builds"] >= 1 and (scale == 3.5 or stats["hits"] >= 5), stats
+
+
+def test_pair_mask_cache_is_dropped_when_its_inputs_change(oracle):
+    """Writing r, imove or the link-list through the library must invalidate the masks: the
+    sweep after the write sees the new positions (bit-identical to a context without cache)."""
+    dims = 3
+    case = cases.dam_break(dims, 12, 2.0)
+    s = pipeline.oracle_linklist_and_sort(case)
+    rng = np.random.default_rng(5)
+    r2 = s["r"].copy()
+    r2[:, :dims] += (rng.random((s["N"], dims), dtype=np.float32) - 0.5) * np.float32(0.8 * case["h"])
+    mv2 = s["imove"].copy()
+    fl = np.flatnonzero(mv2 == 1)
+    mv2[fl[::7]] = -1  # some fluid particles leave the i and j sets
+    L = _lib.lib()
+    res = []
+    try:
+        assert L.aqc_sweep_engine_select(3) == 3
+        for cache in (False, True):
+            ctx = _lib.Context(0, dims=dims, h=case["h"])
+            ctx.pairs_cache(cache)
+            st = pipeline.CudaState(ctx, s)
+            st.run("basic/EOS.cl")
+            got = []
+            for step in range(4):
+                if step == 1:
+                    st.set("r", r2)                     # aqc_memcpy_h2d
+                elif step == 2:
+                    st.set("imove", mv2)
+                elif step == 3:
+                    st.run("cfd/Boundary/BIe/PST.cl")  # a kernel with r among its outputs
+                st.run("cfd/Interactions.cl")
+                st.run("cfd/Shepard.cl")
+                got += [st.get("grad_p"), st.get("div_u"), st.get("shepard"), st.get("r")]
+            res.append(got)
+            if cache:
+                stats = ctx.pairs_cache_stats()
+            ctx.close()
+    finally:
+        L.aqc_sweep_engine_select(-1)
+    for a, b in zip(*res):
+        assert a.tobytes() == b.tobytes()
+    assert not np.array_equal(res[0][0], res[0][4]) and not np.array_equal(res[0][4], res[0][8])
+    assert stats["builds"] == 5 and stats["hits"] == 8, stats  # step 0 builds twice (Shepard adds i classes)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--hfac", type=float, default=3.0)
     ap.add_argument("--case", default="spheric2")
+    ap.add_argument("--cache", type=int, default=0, help="1: pair-mask cache on (sweeps read the masks)")
     ap.add_argument("--suborder", type=int, default=0,
                     help="input pre-ordered by S x S x S sub-cells inside every link-list cell (-1: random order)")
     a = ap.parse_args()
@@ -47,6 +48,8 @@ def main():
             if isinstance(x, np.ndarray) and x.ndim >= 1 and x.shape[0] == N and k not in ("refd", "visc_dyn", "delta"):
                 c[k] = np.ascontiguousarray(x[order])
     ctx = _lib.Context(0, dims=dims, h=c["h"])
+    if a.cache:
+        ctx.pairs_cache(True)
     V, M = (4 if dims == 3 else 2), (16 if dims == 3 else 4)
     v = {k: ctx.array(c[k]) for k in ("id", "iset", "imove", "r", "normal", "tangent", "rho", "m",
                                       "u", "dudt", "drhodt", "refd", "visc_dyn", "delta")}
@@ -108,6 +111,8 @@ def main():
         ("fused_fluid", lambda: ctx.launch_fused([("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry"),
                                                   ("cfd/deltaSPH.cl", "full"), ("cfd/deltaSPH.cl", "lapp")], v), 112 * N),
         ("mls", K("basic/MLS.cl"), 92 * N),
+        # cache only: the masks are dropped before every launch (time = builder + reading sweep)
+        ("build+shepard", lambda: (ctx.pairs_cache_invalidate(), K("cfd/Shepard.cl")()), 36 * N),
         ("bie_interactions", K("cfd/Boundary/BIe/Interactions.cl"), 76 * N),
         ("bie_p_boundary", K("cfd/Boundary/BIe/Interactions.cl", "p_boundary"), 36 * N),
         ("bie_elastic_bounce", K("cfd/Boundary/BIe/ElasticBounce.cl"), 68 * N),
@@ -151,10 +156,12 @@ def main():
                     idle_Mcycles=round(toti / 1e6 / a.reps, 1),
                     producer=dict(wait_empty=buf[16], stage=buf[17], loop=buf[20], tail=buf[28], endsync=buf[30 - 0] * 0 + buf[30 - 0] * 0),
                     producer_Mcycles=round((buf[16] + buf[17] + buf[20]) / 1e6 / a.reps, 1),
-                    rounds_per_pass=round(buf[30] / buf[31], 1), passes=buf[31] // a.reps)), flush=True)
+                    rounds_per_pass=round(buf[29] / buf[31], 1), passes=buf[31] // a.reps)), flush=True)
         print(json.dumps(dict(kernel=name, ms=round(ms, 4), launches=(ctx.launch_count() - l0) // a.reps,
                               alg_GBs=round(nbytes / ms / 1e6, 1),
                               Mparticles_s=round(N / ms / 1e3, 1))), flush=True)
+    if a.cache:
+        print(json.dumps(dict(pairs_cache=ctx.pairs_cache_stats())), flush=True)
     ctx.close()
 
 
