@@ -67,6 +67,7 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFree(ctx->sort_hist);
     cudaFree(ctx->minmax_dev);
     cudaFree(ctx->cell_cls);
+    cudaFree(ctx->pack_rows);
     cudaFree(ctx->pc.masks);
     cudaFree(ctx->pc.pass_tab);
     cudaFree(ctx->pc.ctl);

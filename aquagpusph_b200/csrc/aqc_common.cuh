@@ -60,6 +60,9 @@ struct aqc_ctx {
     // sweeps whose j set is a small class (boundary elements): cells without one are skipped
     uint8_t* cell_cls = nullptr;
     size_t cell_cls_cap = 0;
+    // packed j rows of the sweep being launched (sweep.cuh, s3_pack_kernel)
+    void* pack_rows = nullptr;
+    size_t pack_cap = 0;
     float* minmax_host = nullptr;   // pinned, 8 floats
     // reduction scratch
     void* red_dev = nullptr; // partials

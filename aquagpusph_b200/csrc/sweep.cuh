@@ -392,7 +392,14 @@ static __device__ unsigned long long g_s3prof[32];
 #define S3P_ACC(k)
 #endif
 static_assert(S3_TILES_N % S3_BATCH == 0, "S3_BATCH must divide S3_TILES");
-constexpr int S3_MAXK = 8;                    // ring rounds (at most)
+constexpr int S3_MAXK = 16;                   // ring rounds (at most)
+#ifndef S3_RTILES
+#define S3_RTILES 8 // tiles of a round of the mask-reading sweeps (MODE 2; divides S3_TILES)
+#endif
+#ifndef S3_RRING
+#define S3_RRING 3 // their ring rounds (AQC_SWEEP_RING2)
+#endif
+static_assert(S3_TILES_N % S3_RTILES == 0, "S3_RTILES must divide S3_TILES");
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 
@@ -421,15 +428,46 @@ __device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity)
     return ok != 0;
 }
 
-__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity) // may suspend the thread
+// try_wait comes back after a short system-dependent time whatever the hint (measured: a third
+// of the executed instructions were polls): a warp that finds its barrier closed sleeps
+#ifndef S3_SLEEP_P
+#define S3_SLEEP_P 400 // ns, producer warp (waits for ring space most of the time)
+#endif
+#ifndef S3_SLEEP_C
+#define S3_SLEEP_C 100 // ns, consumer warps
+#endif
+#ifndef S3_WAIT_NS
+#define S3_WAIT_NS 20000 // suspend-time hint of a waiting warp: it leaves the issue slots to the others
+#endif
+__device__ __forceinline__ bool mbar_wait(uint32_t a, uint32_t parity) // suspends the thread
 {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
-                 : "r"(a), "r"(parity)
+                 : "r"(a), "r"(parity), "r"((uint32_t)S3_WAIT_NS)
                  : "memory");
     return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(a),
+                 "r"(bytes)
+                 : "memory");
+}
+// mbarrier.init must be visible to the async proxy (bulk copies complete on the barrier)
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// TMA 1-D bulk copy global -> shared (SASS UBLKCP): bytes % 16 == 0, both addresses 16-byte
+// aligned; completes bytes of transaction count on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
 // first j in [b, N) whose cell (relative to lo) is beyond wid; icell is sorted
@@ -466,6 +504,7 @@ __device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icel
 //   ctl      [0] rounds allocated (keeps counting past the capacity: the host grows the buffer
 //            and builds again), [1] bit 0: a CTA needed more than S3_MAXPASS passes
 struct S3Cache {
+    const float4* rows = nullptr; // MODE 2: the j rows of every particle, packed by s3_pack_kernel
     uint32_t* masks = nullptr;
     uint32_t* pass_tab = nullptr;
     unsigned long long* ctl = nullptr;
@@ -474,16 +513,31 @@ struct S3Cache {
 constexpr int S3_MAXPASS = 32;
 constexpr uint32_t S3_NOPASS = 0xFFFFFFFFu;
 
-template <class P, int MODE>
+// MODE 2 pre-pass: the staged rows of EVERY particle (stage_j: position, hoisted per-j weights,
+// exclusion) as NJ4 arrays of float4, so that the rows of a tile are NJ4 contiguous runs which
+// the producer of sweep3_kernel moves with bulk copies instead of loading, converting and storing
+template <class P>
+__global__ void __launch_bounds__(256) s3_pack_kernel(const P p, const uint32_t N, float4* __restrict__ rows)
+{
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= N)
+        return;
+    float4 o[P::NJ4];
+    p.stage_j(j, o);
+#pragma unroll
+    for (int q = 0; q < P::NJ4; q++)
+        rows[(size_t)q * N + j] = o[q];
+}
+
+template <class P, int MODE, int W>
 __global__ void __launch_bounds__(S3_THREADS, (P::NJ4 <= 2) ? 4 : 3)
 sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 {
     extern __shared__ float4 smem3[];
-    constexpr int W = S3_TILES;
     constexpr int SLOT4 = P::NJ4 * 32;
     const uint32_t NS = (uint32_t)K * W; // ring slots
-    float4* const sT = smem3;            // [K][W][32] packed test layout of the ring's tiles
-    float4* const sJ = sT + NS * 32;     // [NS][SLOT4] j rows
+    float4* const sT = smem3;            // [K][W][32] packed test layout of the ring's tiles (not in MODE 2)
+    float4* const sJ = sT + (MODE == 2 ? 0u : NS * 32); // [NS][SLOT4] j rows
     uint32_t NM = NS - W;                // FIFO entries per lane: the round being staged has no masks yet
     asm volatile("" : "+r"(NM));         // (opaque: kept in a register, not recomputed from K)
     uint32_t* const sM = reinterpret_cast<uint32_t*>(sJ + (size_t)NS * SLOT4); // [CW][NM][32] masks, then
@@ -521,7 +575,10 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
     uint32_t sJ_a = (uint32_t)__cvta_generic_to_shared(sJ) + 31 * 16;
     asm volatile("" : "+r"(Mw_a), "+r"(Sw_a), "+r"(sJ_a));
 
-    bool pending = valid && c_i < ll.nw;
+    // (kernels that never read the cache group their own i particles only: a boundary kernel
+    // does not walk the neighbourhood of a CTA's fluid particles)
+    constexpr bool ALLPASS = P::CACHE || MODE == 1;
+    bool pending = (ALLPASS ? valid : active) && c_i < ll.nw;
     for (uint32_t npass = 0;; npass++) {
         // ---- the group of this pass: first pending particle and its x-row neighbours
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);
@@ -540,6 +597,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                 mbar_init(full_a + 8 * k, 1);
                 mbar_init(empty_a + 8 * k, S3_CWARPS);
             }
+            mbar_fence_init();
         }
         __syncthreads();
         int first = -1;
@@ -809,18 +867,49 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                 S3P_ACC(20)
                 if (use) { // ring round rk holds round r - K
                     uint32_t spins = 0;
-                    while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u)))
+                    while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u))) {
                         if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
+                        if (S3_SLEEP_P)
+                            __nanosleep(S3_SLEEP_P);
+                    }
                 }
                 S3P_ACC(16)
+                if constexpr (MODE == 2) {
+                    // lane w2 moves tile w2 of the round: NJ4 bulk copies from the packed rows
+                    // straight into the ring slot; the barrier completes with their bytes
+                    uint32_t bytes = 0;
+                    if (lane < W) {
+                        const uint32_t tn = r * W + (uint32_t)lane;
+                        const uint32_t k = tn / NE, e = tn - k * NE;
+                        if (k < maxk) {
+                            const uint32_t bg = e_begin[e] + 32u * k, en = e_end[e];
+                            if (bg < en) {
+                                bytes = min(32u, en - bg) * 16u;
+                                const uint32_t dst = sJ_a - 31 * 16 + (rk * W + (uint32_t)lane) * (SLOT4 * 16);
+#pragma unroll
+                                for (int q = 0; q < P::NJ4; q++)
+                                    bulk_g2s(dst + q * 512, pc.rows + (size_t)q * ll.N + bg, bytes, full_a + 8 * rk);
+                                bytes *= P::NJ4;
+                            }
+                        }
+                    }
+                    bytes = __reduce_add_sync(0xffffffffu, bytes);
+                    if (lane == 0) {
+                        if (bytes)
+                            mbar_arrive_expect_tx(full_a + 8 * rk, bytes);
+                        else
+                            mbar_arrive(full_a + 8 * rk);
+                    }
+                } else {
 #pragma unroll 1
-                for (uint32_t w0 = 0; w0 < (uint32_t)W; w0 += S3_BATCH)
-                    stage_batch(rk, w0);
+                    for (uint32_t w0 = 0; w0 < (uint32_t)W; w0 += S3_BATCH)
+                        stage_batch(rk, w0);
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(full_a + 8 * rk);
+                }
                 S3P_ACC(17)
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(full_a + 8 * rk);
                 if (++rk == (uint32_t)K) {
                     rk = 0;
                     use++;
@@ -835,22 +924,26 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 #if S3_PROFILE
             const int s3p_c = work_w ? 0 : 8; // warps without a working lane: second bank
 #endif
+            // MODE 2: the masks of round r + 1 are requested as soon as those of round r have
+            // gone to the FIFO, so their latency is covered by the pair bodies of round r
+            uint32_t mk[W];
+            const uint32_t* msrc = pc.masks + ((size_t)mbase * S3_TILES * S3_CWARPS + cw) * 32 + lane;
+            if constexpr (MODE == 2) {
+#pragma unroll
+                for (int w2 = 0; w2 < W; w2++)
+                    mk[w2] = (work && nrounds) ? __ldg(msrc + w2 * (S3_CWARPS * 32)) : 0u;
+            }
             S3P_START
             for (uint32_t r = 0; r < nrounds; r++) {
                 S3P_ACC(s3p_c + 5)
-                // MODE 2: the masks of the round are requested before its rows are waited for
-                uint32_t mk[W];
-                if constexpr (MODE == 2) {
-                    const uint32_t* src = pc.masks + ((size_t)(mbase + r) * W * S3_CWARPS + cw) * 32 + lane;
-#pragma unroll
-                    for (int w2 = 0; w2 < W; w2++)
-                        mk[w2] = work ? __ldg(src + w2 * (S3_CWARPS * 32)) : 0u;
-                }
                 {
                     uint32_t spins = 0;
-                    while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u)))
+                    while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u))) {
                         if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
+                        if (S3_SLEEP_C)
+                            __nanosleep(S3_SLEEP_C);
+                    }
                 }
                 S3P_ACC(s3p_c + 0)
                 if constexpr (MODE == 1) {
@@ -890,6 +983,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                             for (int w2 = 0; w2 < W; w2++)
                                 if (mk[w2])
                                     push(mk[w2], rk * W + w2);
+                            if (r + 1 < nrounds) {
+                                msrc += W * S3_CWARPS * 32;
+#pragma unroll
+                                for (int w2 = 0; w2 < W; w2++)
+                                    mk[w2] = __ldg(msrc + w2 * (S3_CWARPS * 32));
+                            }
                         } else {
                             // ---- filter: record the hit masks of the round's tiles
 #pragma unroll 1
@@ -969,6 +1068,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
 bool aqc_sweep_engine_forced(); // chosen explicitly (environment or aqc_sweep_engine_select)
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
+int aqc_sweep_ring2();       // ring rounds of the mask-reading sweeps (AQC_SWEEP_RING2)
 int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2, const LLParams& ll,
                    uint32_t icls, uint32_t jcls, int K, S3Cache* out); // sweeps.cu
 
@@ -1003,10 +1103,7 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         // per step; 7.4 M: 12.8 vs 15.3)
         const bool small2d = (P::DIMS == 2) && ll.N < (1u << 20) && !aqc_sweep_engine_forced();
         if (aqc_sweep_engine() == 3 && !P::SPARSE_I && !small2d) {
-            const int K = aqc_sweep_ring(P::NJ4);
-            const size_t NS = (size_t)K * S3_TILES;
-            const size_t smem = (NS * 32 + NS * P::NJ4 * 32) * sizeof(float4) +
-                                S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
+            int K = aqc_sweep_ring(P::NJ4);
             S3Cache pc;
             int cached = 0;
             if constexpr (P::CACHE) {
@@ -1014,23 +1111,50 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
                 if (cached < 0)
                     return cached;
             }
+            // shared memory: test layouts (not when the masks are read), j rows, per-lane FIFOs
+            auto smem_of = [](int k, int w, bool test) {
+                const size_t NS = (size_t)k * w;
+                return ((test ? NS * 32 : 0) + NS * P::NJ4 * 32) * sizeof(float4) +
+                       S3_CWARPS * (NS - w) * 32 * (sizeof(uint32_t) + 1);
+            };
+            if constexpr (P::CACHE) {
+                if (cached) {
+                    K = aqc_sweep_ring2();
+                    const size_t smem = smem_of(K, S3_RTILES, false);
+                    static size_t configured2 = 0; // per instantiation
+                    if (smem > configured2) {
+                        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2, S3_RTILES>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        configured2 = smem;
+                    }
+                    const size_t need = (size_t)ll.N * P::NJ4 * sizeof(float4);
+                    if (need > ctx->pack_cap) {
+                        if (ctx->pack_rows) {
+                            AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                            AQC_CUDA(ctx, cudaFree(ctx->pack_rows));
+                        }
+                        ctx->pack_rows = nullptr;
+                        ctx->pack_cap = 0;
+                        AQC_CUDA(ctx, cudaMalloc(&ctx->pack_rows, need + need / 8));
+                        ctx->pack_cap = need + need / 8;
+                    }
+                    s3_pack_kernel<P><<<aqc_blocks(ll.N, 256), 256, 0, ctx->stream>>>(p, ll.N, (float4*)ctx->pack_rows);
+                    AQC_LAUNCH_CHECK(ctx);
+                    pc.rows = (const float4*)ctx->pack_rows;
+                    sweep3_kernel<P, 2, S3_RTILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(
+                        p, ll, K, pc);
+                    AQC_LAUNCH_CHECK(ctx);
+                    return AQC_OK;
+                }
+            }
+            const size_t smem = smem_of(K, S3_TILES, true);
             static size_t configured = 0; // per instantiation
             if (smem > configured) {
-                AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 0>,
+                AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 0, S3_TILES>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                if constexpr (P::CACHE)
-                    AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2>,
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured = smem;
             }
-            if constexpr (P::CACHE) {
-                if (cached)
-                    sweep3_kernel<P, 2><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
-                else
-                    sweep3_kernel<P, 0><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
-            } else {
-                sweep3_kernel<P, 0><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
-            }
+            sweep3_kernel<P, 0, S3_TILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
         } else {
             sweep2_kernel<P><<<aqc_blocks(ll.N, SWEEP_THREADS), SWEEP_THREADS, 0, ctx->stream>>>(p, ll);
         }

@@ -73,6 +73,16 @@ int aqc_sweep_ring(int nj4)
     return 3;
 }
 
+int aqc_sweep_ring2()
+{
+    static const int forced = [] {
+        const char* s = getenv("AQC_SWEEP_RING2");
+        const int r = s ? atoi(s) : 0;
+        return (r >= 2 && r <= S3_MAXK) ? r : 0;
+    }();
+    return forced ? forced : S3_RRING;
+}
+
 namespace {
 
 constexpr float iM_PI = 0.318309886f; // KernelFunctions/Wendland3D.hcl:34-39
@@ -1390,11 +1400,11 @@ int pc_build(aqc_ctx* ctx, const LLParams& ll, int K)
     const size_t smem = (NS * 32 + NS * 32) * sizeof(float4) + S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
     static size_t configured = 0;
     if (smem > configured) {
-        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 1>,
+        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 1, S3_TILES>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    sweep3_kernel<PMaskBuild<D>, 1><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    sweep3_kernel<PMaskBuild<D>, 1, S3_TILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
     AQC_LAUNCH_CHECK(ctx);
     return AQC_OK;
 }

@@ -8,7 +8,7 @@ for vr in $VARS; do
   v=${vr%%:*}; ring=""; [[ "$vr" == *:* ]] && ring=${vr##*:}
   cp build/variants/$v/libaquacuda.so aquagpusph_b200/libaquacuda.so
   echo "== variant $v ring ${ring:-default}" | tee -a gpurun_out/kbench_$TAG.log
-  AQC_SWEEP_RING=$ring timeout 600 python tools/kbench.py --n 1000000 --reps 5 --only $ONLY 2>&1 | grep -v '"case"' | cut -c1-${CUT:-60} | tee -a gpurun_out/kbench_$TAG.log
+  AQC_SWEEP_RING=$ring timeout 600 python tools/kbench.py --n 1000000 --reps 5 $KB_ARGS --only $ONLY 2>&1 | grep -v '"case"' | cut -c1-${CUT:-60} | tee -a gpurun_out/kbench_$TAG.log
 done
 if [ -n "$TESTV" ]; then
   cp build/variants/$TESTV/libaquacuda.so aquagpusph_b200/libaquacuda.so
