@@ -392,7 +392,7 @@ static __device__ unsigned long long g_s3prof[32];
 #define S3P_ACC(k)
 #endif
 static_assert(S3_TILES_N % S3_BATCH == 0, "S3_BATCH must divide S3_TILES");
-constexpr int S3_MAXK = 16;                   // ring rounds (at most)
+constexpr int S3_MAXK = 8;                    // ring rounds (at most; static shared memory grows with it)
 #ifndef S3_RTILES
 #define S3_RTILES 8 // tiles of a round of the mask-reading sweeps (MODE 2; divides S3_TILES)
 #endif
