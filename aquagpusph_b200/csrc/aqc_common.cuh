@@ -30,6 +30,9 @@ struct aqc_pair_cache {
     unsigned long long* ctl = nullptr;      // device [2]
     unsigned long long* ctl_host = nullptr; // pinned [2]
     uint64_t builds = 0, hits = 0;
+    // a build costs about half a sweep: pipelines whose geometry changes before a second sweep
+    // reads the masks (served < 2, three times in a row) go without for a while
+    uint32_t served = 0, poor_streak = 0, cooldown = 0;
 };
 
 struct aqc_ctx {

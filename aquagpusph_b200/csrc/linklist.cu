@@ -470,7 +470,11 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
     const float cell_length = support * h;
     if (!cell_length)
         return aqc_fail(ctx, AQC_ERR_ARG, "Zero cell length detected (Invalid number of cells)");
-    aqc_pc_invalidate(ctx); // icell, ihoc and the permutations are rewritten
+    // icell, ihoc and the permutations are rewritten (ihoc may also be replaced by a larger one)
+    aqc_pc_touch(ctx, icell, (size_t)N * sizeof(aqc_usize));
+    aqc_pc_touch(ctx, perm, (size_t)N * sizeof(aqc_usize));
+    aqc_pc_touch(ctx, inv_perm, (size_t)N * sizeof(aqc_usize));
+    aqc_pc_touch(ctx, *ihoc, (*ihoc_capacity ? *ihoc_capacity : 1) * sizeof(aqc_usize));
 
     const int vs = (dims == 3) ? 4 : 2;
     if (recompute_grid) {

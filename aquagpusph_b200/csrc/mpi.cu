@@ -219,7 +219,9 @@ extern "C" int aqc_mpi_sync(aqc_ctx* ctx, aqc_usize* mask, aqc_usize n, int nfie
     // MPISync.cpp:186-187: nobody to talk to => nothing happens (the mask is left alone)
     if (ctx->nranks <= 1 || !ctx->comm || !n)
         return AQC_OK;
-    aqc_pc_invalidate(ctx); // the mask and every field are rewritten
+    aqc_pc_touch(ctx, mask, (size_t)n * sizeof(aqc_usize)); // the mask and every field are rewritten
+    for (int f = 0; f < nfields; f++)
+        aqc_pc_touch(ctx, fields[f], (size_t)n * elem_bytes[f]);
     const int P = ctx->nranks, me = ctx->rank;
     std::vector<char> peer(P, procs ? 0 : 1);
     if (procs)

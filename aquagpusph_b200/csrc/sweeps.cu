@@ -1422,6 +1422,21 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
                       c.N == ll.N && c.nx == ll.nx && c.ny == ll.ny && c.nz == ll.nz && c.nw == ll.nw &&
                       c.dims == dims && c.cut2 == cut2 && !(icls & ~c.icls) && !(jcls & ~c.jcls);
     if (!same) {
+        if (c.cooldown) { // recent builds did not pay
+            c.cooldown--;
+            c.valid = false;
+            return 0;
+        }
+        if (c.builds) {
+            c.poor_streak = (c.served < 2) ? c.poor_streak + 1 : 0;
+            if (c.poor_streak >= 3) {
+                c.poor_streak = 0;
+                c.cooldown = 64;
+                c.valid = false;
+                return 0;
+            }
+        }
+        c.served = 0;
         c.valid = false;
         c.icls_want |= icls;
         c.jcls_want |= jcls;
@@ -1479,6 +1494,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
     if (c.unusable)
         return 0;
     c.hits++;
+    c.served++;
     out->masks = c.masks;
     out->pass_tab = c.pass_tab;
     out->ctl = c.ctl;
