@@ -450,6 +450,6 @@ extern "C" int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint6
     if (hits)
         *hits = ctx->pc.hits;
     if (bytes)
-        *bytes = (uint64_t)ctx->pc.cap_rounds * 7168u; // S3_TILES * S3_CWARPS * 32 lanes * 4 B per round
+        *bytes = (uint64_t)ctx->pc.cap_rounds * AQC_PC_ROUND_BYTES;
     return AQC_OK;
 }

@@ -13,6 +13,7 @@
 // built once per geometry (positions + link-list + particle classes) and read by every sweep
 // until one of those arrays is written through the library (aqc_pc_touch) or the caller says so
 // (aqc_pairs_cache_invalidate).
+constexpr size_t AQC_PC_ROUND_BYTES = 8 * 7 * 32 * 4; // one round of masks: tiles x consumer warps x lanes x 4 B
 struct aqc_pair_cache {
     bool enabled = false;  // aqc_pairs_cache_enable
     bool valid = false;    // the masks belong to the key below

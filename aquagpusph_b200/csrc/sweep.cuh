@@ -363,6 +363,8 @@ sweep2_kernel(const P p, const LLParams ll)
 // deterministic (run-to-run bit-identical); the order is not the reference's x-outer
 // one any more: results differ from v2 by fp32 rounding of the sums only.
 // Order-dependent kernels stay on sweep_kernel.
+// (a CTA of 9 warps -- 8 consumers at 56 registers -- is not faster: the mask-reading sweeps are
+// bound by the issue slots and the shared-memory pipe of the SM, not by the number of warps)
 constexpr int S3_WARPS = 8;                  // warp 0 stages tiles, warps 1..7 own 32 particles each
 constexpr int S3_THREADS = S3_WARPS * 32;
 constexpr int S3_CWARPS = S3_WARPS - 1;       // consumer warps
@@ -400,6 +402,7 @@ constexpr int S3_MAXK = 8;                    // ring rounds (at most; static sh
 #define S3_RRING 3 // their ring rounds (AQC_SWEEP_RING2)
 #endif
 static_assert(S3_TILES_N % S3_RTILES == 0, "S3_RTILES must divide S3_TILES");
+static_assert(AQC_PC_ROUND_BYTES == (size_t)S3_TILES_N * (S3_WARPS - 1) * 32 * 4, "aqc_pairs_cache_stats");
 constexpr int S3_SPAN = 7; // cells of one x row a group may span beyond the first
 constexpr int S3_MAXE = 9 * ((S3_SPAN + 3 + 1) / 2);
 
