@@ -1467,7 +1467,14 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
                 c.cap_rounds = 0;
                 if (want >= 0xFFFFFFF0ull)
                     return 0; // beyond the 32-bit round index: no cache
-                AQC_CUDA(ctx, cudaMalloc(&c.masks, want * (size_t)(S3_TILES * S3_CWARPS * 32) * sizeof(uint32_t)));
+                if (cudaMalloc(&c.masks, want * (size_t)(S3_TILES * S3_CWARPS * 32) * sizeof(uint32_t)) !=
+                    cudaSuccess) {
+                    // no room for the masks next to the problem: the sweeps keep filtering
+                    (void)cudaGetLastError();
+                    c.masks = nullptr;
+                    c.cooldown = 0xFFFFFFFFu;
+                    return 0;
+                }
                 c.cap_rounds = want;
             }
             AQC_CUDA(ctx, cudaMemsetAsync(c.ctl, 0, 2 * sizeof(unsigned long long), ctx->stream));
