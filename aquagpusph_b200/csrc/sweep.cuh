@@ -506,6 +506,18 @@ __device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icel
 //   pass_tab [CTA][S3_MAXPASS]                   first round of the pass
 //   ctl      [0] rounds allocated (keeps counting past the capacity: the host grows the buffer
 //            and builds again), [1] bit 0: a CTA needed more than S3_MAXPASS passes
+// the masks are written once and read once per sweep (1.2 KB per particle): streaming accesses
+// (evict-first) keep them from pushing the packed rows and the particle arrays out of L2
+#ifndef S3_MASK_CS
+#define S3_MASK_CS 1
+#endif
+#if S3_MASK_CS
+#define S3_MASK_LD(p) __ldcs(p)
+#define S3_MASK_ST(p, v) __stcs(p, v)
+#else
+#define S3_MASK_LD(p) __ldg(p)
+#define S3_MASK_ST(p, v) (*(p) = (v))
+#endif
 struct S3Cache {
     const float4* rows = nullptr; // MODE 2: the j rows of every particle, packed by s3_pack_kernel
     uint32_t* masks = nullptr;
@@ -934,7 +946,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
             if constexpr (MODE == 2) {
 #pragma unroll
                 for (int w2 = 0; w2 < W; w2++)
-                    mk[w2] = (work && nrounds) ? __ldg(msrc + w2 * (S3_CWARPS * 32)) : 0u;
+                    mk[w2] = (work && nrounds) ? S3_MASK_LD(msrc + w2 * (S3_CWARPS * 32)) : 0u;
             }
             S3P_START
             for (uint32_t r = 0; r < nrounds; r++) {
@@ -974,7 +986,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                         }
                         __syncwarp();
                         if (mbase != S3_NOPASS)
-                            dst[w2 * (S3_CWARPS * 32)] = m;
+                            S3_MASK_ST(dst + w2 * (S3_CWARPS * 32), m);
                     }
                     __syncwarp();
                     if (lane == 0)
@@ -990,7 +1002,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                                 msrc += W * S3_CWARPS * 32;
 #pragma unroll
                                 for (int w2 = 0; w2 < W; w2++)
-                                    mk[w2] = __ldg(msrc + w2 * (S3_CWARPS * 32));
+                                    mk[w2] = S3_MASK_LD(msrc + w2 * (S3_CWARPS * 32));
                             }
                         } else {
                             // ---- filter: record the hit masks of the round's tiles
