@@ -1018,7 +1018,11 @@ aqc_registrar r_h_sensor("h_sensor.cl", "entry", 3,
       IN("drhodt", "float*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"),            \
       OUT("dudt_in", "vec*"), OUT("rho_in", "float*"), OUT("drhodt_in", "float*"), \
       SC("N", "usize") }
-aqc_registrar r_eu_p("basic/time_scheme/euler.cl", "predictor", 0, STATE_COPY_ARGS, l_copy_state);
+// (euler.cl:65-75 declares the state it only reads without const)
+aqc_registrar r_eu_p("basic/time_scheme/euler.cl", "predictor", 0,
+    { RO("r", "vec*"), RO("u", "vec*"), RO("dudt", "vec*"), RO("rho", "float*"), RO("drhodt", "float*"),
+      OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"), OUT("rho_in", "float*"),
+      OUT("drhodt_in", "float*"), SC("N", "usize") }, l_copy_state);
 aqc_registrar r_mp_p("basic/time_scheme/midpoint.cl", "predictor", 0, STATE_COPY_ARGS, l_copy_state);
 aqc_registrar r_eu_c("basic/time_scheme/euler.cl", "corrector", 0,
     { OUT("imove", "int*"), OUT("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"),

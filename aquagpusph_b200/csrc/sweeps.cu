@@ -1890,6 +1890,7 @@ const std::vector<FusedEntry>& fused_table()
 
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
+#define RO(n, t) { n, t, AQC_ARG_ARRAY_RO } // non-const in the reference's script, never written
 #define SC(n, t) { n, t, AQC_ARG_SCALAR }
 #define LL_ARGS IN("icell", "usize*"), IN("ihoc", "usize*"), SC("n_cells", "svec4")
 
@@ -1947,8 +1948,8 @@ aqc_registrar r_bi_interp("cfd/Boundary/BI/Interpolation.cl", "entry", 0,
 aqc_registrar r_bi_inter("cfd/Boundary/BI/Interactions.cl", "entry", 0,
     { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"),
       IN("u", "vec*"), IN("rho", "float*"), IN("m", "float*"), IN("p", "float*"),
-      IN("refd", "float*"), OUT("grad_p", "vec*"), OUT("div_u", "float*"), OUT("icell", "uint*"),
-      OUT("ihoc", "uint*"), SC("N", "usize"), SC("n_cells", "uivec4"), SC("g", "vec") },
+      IN("refd", "float*"), OUT("grad_p", "vec*"), OUT("div_u", "float*"), RO("icell", "uint*"),
+      RO("ihoc", "uint*"), SC("N", "usize"), SC("n_cells", "uivec4"), SC("g", "vec") },
     l_bi_inter);
 aqc_registrar r_elastic("cfd/Boundary/ElasticBounce.cl", "entry", 0,
     { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), OUT("u", "vec*"),

@@ -238,3 +238,34 @@ def test_tool_placement_semantics():
     assert names == ["t1", "t2", "t3", "t4", "gated in"]
     with pytest.raises(host.HostError):
         _parse(xml.replace('before="t3"', 'before="nowhere"'), 2)
+
+
+def test_whole_kernel_registry_against_the_reference_scripts():
+    """Every registered kernel against the signature the reference's Kernel tool would reflect from
+    its .cl script with clGetKernelArgInfo (Kernel.cpp:497-556; fixture: tests/golden/
+    kernel_signatures.json, made by make_kernel_signatures.py from /root/reference): same argument
+    names in the same order, pointers where the script has pointers, AQC_ARG_ARRAY_IN exactly for the
+    `const` / `__constant` ones and ARRAY_OUT / ARRAY_RO for the others."""
+    import json
+    sig = json.load(open(os.path.join(ROOT, "tests", "golden", "kernel_signatures.json")))
+    L = _lib.lib()
+    checked, own = 0, []
+    for kid in range(L.aqc_kernel_count()):
+        name = L.aqc_kernel_name(kid).decode()
+        script, entry = name.split("::")
+        key = script if script in sig else "examples:" + script
+        if key not in sig or entry not in sig[key]:
+            own.append(name)
+            continue
+        ref = sig[key][entry]
+        args = L.aqc_kernel_args(kid)
+        got = [(args[k].name.decode(), args[k].kind) for k in range(L.aqc_kernel_nargs(kid))]
+        assert [g[0] for g in got] == [r[0] for r in ref], name
+        for (gname, kind), (_, ptr, const) in zip(got, ref):
+            assert (kind != _lib.ARG_SCALAR) == ptr, (name, gname)
+            if ptr:
+                assert (kind == _lib.ARG_ARRAY_IN) == const, (name, gname, kind)
+        checked += 1
+    assert checked >= 55
+    # the only kernels without a reference script are this library's own diagnostics
+    assert own == ["aqua/diag.cl::count_pairs"], own
