@@ -430,6 +430,7 @@ extern "C" int aqc_pairs_cache_enable(aqc_ctx* ctx, int on)
         return AQC_ERR_ARG;
     ctx->pc.enabled = on != 0;
     ctx->pc.valid = false;
+    ctx->pc.served = ctx->pc.poor_streak = ctx->pc.cooldown = 0; // (and the pay-off history)
     return AQC_OK;
 }
 
