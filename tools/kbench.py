@@ -113,7 +113,7 @@ def main():
         ("mls", K("basic/MLS.cl"), 92 * N),
         # cache only: the masks are dropped before every launch (time = builder + reading sweep)
         # (enable() also clears the pay-off history, which would otherwise suspend these builds)
-        ("build+shepard", lambda: (ctx.pairs_cache(True), K("cfd/Shepard.cl")()), 36 * N),
+        ("build+shepard", lambda: (ctx.pairs_cache(True) if a.cache else None, K("cfd/Shepard.cl")()), 36 * N),
         ("bie_interactions", K("cfd/Boundary/BIe/Interactions.cl"), 76 * N),
         ("bie_p_boundary", K("cfd/Boundary/BIe/Interactions.cl", "p_boundary"), 36 * N),
         ("bie_elastic_bounce", K("cfd/Boundary/BIe/ElasticBounce.cl"), 68 * N),
