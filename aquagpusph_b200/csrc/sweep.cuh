@@ -1,4 +1,4 @@
-// sweep.cuh -- the neighbour sweep: one engine for every kernel the reference
+// sweep.cuh -- the neighbour sweep: the engines behind every kernel the reference
 // writes with BEGIN_NEIGHS/END_NEIGHS (resources/Scripts/types/3D.h:197-219,
 // 2D.h:174-193).
 //
@@ -7,23 +7,21 @@
 // candidate, and recomputing per-j factors (m_j/rho_j, kernel constants) for
 // every pair.
 //
-// B200 shape (this file):
-//   * particles are cell-ordered (the link-list sort), so one warp takes 32
-//     consecutive particles; lanes are grouped by cell and each group walks its
-//     neighbour cells ONCE for the whole group (warp-uniform loop);
-//   * the j particles of a cell are contiguous: a tile of 32 of them is loaded
-//     with coalesced 16-byte loads, reduced to the few floats a pair needs
-//     (position + a per-j weight such as wcon*CONF*m_j/rho_j; excluded j get a
-//     far-away position) and staged in per-warp shared memory as float4 SoA;
-//   * every lane tests the 32 staged candidates with broadcast LDS.128 reads
-//     and records its hits in a 32-bit mask; the pair bodies then run over the
-//     lane's own hits only (COMPACT), instead of the whole warp executing the
-//     body whenever any lane hits;
-//   * hits are visited in ascending j inside ascending cell order (x-outer, y,
-//     z-inner), i.e. the reference's summation order is preserved per particle
-//     (needed by the order-dependent ElasticBounce / PST kernels).
-//   * no __syncthreads: warps are independent, a warp with no active particle
-//     leaves immediately (sensor / boundary-only kernels).
+// Here particles are cell-ordered (the link-list sort), so the particles of a
+// cell are contiguous and a policy struct per script kernel (sweeps.cu) says what
+// a pair needs: load_i, stage_j (position + hoisted per-j weights; excluded j get
+// a far-away position), the exact test, the pair body, store_i.  Three engines:
+//   * sweep_kernel   -- one warp per 32 particles, lanes grouped by cell, tiles of
+//     32 candidates staged per warp, hits visited in the reference's order (cells
+//     x-outer, ascending j): the order-dependent ElasticBounce / PST kernels;
+//   * sweep2_kernel  -- the same walk with the packed-fp32 candidate filter:
+//     kernels whose i particles are few and scattered (sensors, boundary elements,
+//     halo sweeps) and small 2-D problems;
+//   * sweep3_kernel  -- CTA-shared tiles in a shared-memory ring fed by a producer
+//     warp, per-lane FIFOs of hit masks and deferred, lane-balanced pair bodies
+//     (MODE 0); MODE 1 stores the hit masks of the filter (the pair-mask cache),
+//     MODE 2 reads them instead of filtering, with its j rows packed by a pre-pass
+//     and moved into the ring by TMA bulk copies.  DESIGN.md section 4 / 4.1.
 #pragma once
 #include "aqc_common.cuh"
 
