@@ -286,6 +286,140 @@ int l_domain(aqc_ctx* c, size_t, void* const* a)
              aqc_vec_scalar(a, 6, d), aqc_vec_scalar(a, 7, d));
 }
 
+// ---- cfd/Motions/{Transform,UnTransform,Velocity,Acceleration}.cl (preset cfd/motion.xml:55-72) --
+// Rigid motion of the non-fluid particles of one set, Euler-XYZ angles.  The scripts evaluate
+// cos / sin of the three (uniform) angles in every work-item; here the launcher does it once on
+// the host and passes the six values, so the rotations are the same fp32 products and sums.
+struct MotionTrig { float cphi, sphi, cth, sth, cpsi, spsi; };
+static MotionTrig motion_trig(const aqc_f4& a, float sgn)
+{
+    return MotionTrig{ cosf(a.x), sgn * sinf(a.x), cosf(a.y), sgn * sinf(a.y), cosf(a.z), sgn * sinf(a.z) };
+}
+__device__ inline void rot_x(float& y, float& z, float c, float s)
+{
+    const float y0 = y, z0 = z;
+    y = c * y0 - s * z0;
+    z = s * y0 + c * z0;
+}
+__device__ inline void rot_y(float& x, float& z, float c, float s)
+{
+    const float x0 = x, z0 = z;
+    x = c * x0 + s * z0;
+    z = -s * x0 + c * z0;
+}
+__device__ inline void rot_z(float& x, float& y, float c, float s)
+{
+    const float x0 = x, y0 = y;
+    x = c * x0 - s * y0;
+    y = s * x0 + c * y0;
+}
+template <int D> __device__ inline void rotate_fwd(V<D>& a, const MotionTrig& t)
+{
+    if constexpr (D == 3) {
+        rot_x(a.v.y, a.v.z, t.cphi, t.sphi);
+        rot_y(a.v.x, a.v.z, t.cth, t.sth);
+    }
+    rot_z(a.v.x, a.v.y, t.cpsi, t.spsi);
+}
+template <int D> __device__ inline void rotate_back(V<D>& a, const MotionTrig& t) // t holds -sin
+{
+    rot_z(a.v.x, a.v.y, t.cpsi, t.spsi);
+    if constexpr (D == 3) {
+        rot_y(a.v.x, a.v.z, t.cth, t.sth);
+        rot_x(a.v.y, a.v.z, t.cphi, t.sphi);
+    }
+}
+// Transform.cl:68-134
+template <int D>
+__global__ void __launch_bounds__(256)
+k_motion_transform(const uint32_t* iset, const int* imove, void* r, void* normal, void* tangent, uint32_t N,
+                   uint32_t motion_iset, aqc_f4 motion_r, MotionTrig t)
+{
+    GID;
+    if (iset[i] != motion_iset || imove[i] == 1)
+        return;
+    V<D> r_i = V<D>::ld(r, i), n_i = V<D>::ld(normal, i), t_i = V<D>::ld(tangent, i);
+    rotate_fwd<D>(r_i, t);
+    rotate_fwd<D>(n_i, t);
+    rotate_fwd<D>(t_i, t);
+    (r_i + from_f4<D>(motion_r)).st(r, i);
+    (n_i / sqrtf(n_i.dot(n_i))).st(normal, i);   // normalize() over the whole vec
+    (t_i / sqrtf(t_i.dot(t_i))).st(tangent, i);
+}
+int l_motion_transform(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    aqc_f4 ang;
+    memcpy(&ang, a[8], sizeof(ang));
+    DISPATCH(c, k_motion_transform, N, (const uint32_t*)a[0], (const int*)a[1], a[2], a[3], a[4], N,
+             aqc_scalar<uint32_t>(a, 6), aqc_vec_scalar(a, 7, c->defs.dims), motion_trig(ang, 1.f));
+}
+// UnTransform.cl:54-119
+template <int D>
+__global__ void __launch_bounds__(256)
+k_motion_untransform(const uint32_t* iset, const int* imove, void* r, void* normal, void* tangent, uint32_t N,
+                     uint32_t motion_iset, aqc_f4 motion_r_in, MotionTrig t)
+{
+    GID;
+    if (iset[i] != motion_iset || imove[i] == 1)
+        return;
+    V<D> r_i = V<D>::ld(r, i) - from_f4<D>(motion_r_in), n_i = V<D>::ld(normal, i), t_i = V<D>::ld(tangent, i);
+    rotate_back<D>(r_i, t);
+    rotate_back<D>(n_i, t);
+    rotate_back<D>(t_i, t);
+    r_i.st(r, i);
+    n_i.st(normal, i);
+    t_i.st(tangent, i);
+}
+int l_motion_untransform(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    aqc_f4 ang;
+    memcpy(&ang, a[8], sizeof(ang));
+    DISPATCH(c, k_motion_untransform, N, (const uint32_t*)a[0], (const int*)a[1], a[2], a[3], a[4], N,
+             aqc_scalar<uint32_t>(a, 6), aqc_vec_scalar(a, 7, c->defs.dims), motion_trig(ang, -1.f));
+}
+// Velocity.cl:74-121 and Acceleration.cl: omega x r in the local frame, rotated, plus the linear part
+template <int D>
+__global__ void __launch_bounds__(256)
+k_motion_rate(const uint32_t* iset, const int* imove, const void* r, void* out, uint32_t N,
+              uint32_t motion_iset, aqc_f4 lin, aqc_f4 w, MotionTrig t)
+{
+    GID;
+    if (iset[i] != motion_iset || imove[i] == 1)
+        return;
+    const V<D> p = V<D>::ld(r, i);
+    V<D> v = V<D>::splat(0.f);
+    if constexpr (D == 2) {
+        v.v.x = -w.z * p.v.y;
+        v.v.y = w.z * p.v.x;
+    } else { // cross(float4, float4): w = 0
+        v.v.x = w.y * p.v.z - w.z * p.v.y;
+        v.v.y = w.z * p.v.x - w.x * p.v.z;
+        v.v.z = w.x * p.v.y - w.y * p.v.x;
+    }
+    rotate_fwd<D>(v, t);
+    (v + from_f4<D>(lin)).st(out, i);
+}
+int l_motion_velocity(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    aqc_f4 ang, w;
+    memcpy(&ang, a[7], sizeof(ang));
+    memcpy(&w, a[8], sizeof(w));
+    DISPATCH(c, k_motion_rate, N, (const uint32_t*)a[0], (const int*)a[1], a[2], a[3], N,
+             aqc_scalar<uint32_t>(a, 5), aqc_vec_scalar(a, 6, c->defs.dims), w, motion_trig(ang, 1.f));
+}
+int l_motion_acceleration(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    aqc_f4 ang, w;
+    memcpy(&ang, a[8], sizeof(ang));
+    memcpy(&w, a[9], sizeof(w));
+    DISPATCH(c, k_motion_rate, N, (const uint32_t*)a[0], (const int*)a[1], a[2], a[3], N,
+             aqc_scalar<uint32_t>(a, 5), aqc_vec_scalar(a, 7, c->defs.dims), w, motion_trig(ang, 1.f));
+}
+
 // ---- basic/Sort.cl:57-78 (stage1) and :102-124 (stage2) ----------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -1056,6 +1190,23 @@ aqc_registrar r_mp_c("basic/time_scheme/midpoint.cl", "corrector", 0,
     { IN("imove", "int*"), IN("r_in", "vec*"), OUT("r", "vec*"), IN("u_in", "vec*"),
       OUT("u", "vec*"), IN("dudt", "vec*"), IN("rho_in", "float*"), OUT("rho", "float*"),
       IN("drhodt", "float*"), SC("N", "usize"), SC("dt", "float") }, l_mp_corrector);
+// (r of Velocity / Acceleration is declared without const and only read)
+aqc_registrar r_mo_t("cfd/Motions/Transform.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), OUT("r", "vec*"), OUT("normal", "vec*"), OUT("tangent", "vec*"),
+      SC("N", "usize"), SC("motion_iset", "unsigned int"), SC("motion_r", "vec"), SC("motion_a", "vec4") },
+    l_motion_transform);
+aqc_registrar r_mo_u("cfd/Motions/UnTransform.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), OUT("r", "vec*"), OUT("normal", "vec*"), OUT("tangent", "vec*"),
+      SC("N", "usize"), SC("motion_iset", "unsigned int"), SC("motion_r_in", "vec"), SC("motion_a_in", "vec4") },
+    l_motion_untransform);
+aqc_registrar r_mo_v("cfd/Motions/Velocity.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), RO("r", "vec*"), OUT("u", "vec*"), SC("N", "usize"),
+      SC("motion_iset", "unsigned int"), SC("motion_drdt", "vec"), SC("motion_a", "vec4"),
+      SC("motion_dadt", "vec4") }, l_motion_velocity);
+aqc_registrar r_mo_a("cfd/Motions/Acceleration.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), RO("r", "vec*"), OUT("dudt", "vec*"), SC("N", "usize"),
+      SC("motion_iset", "unsigned int"), SC("motion_r", "vec"), SC("motion_ddrddt", "vec"),
+      SC("motion_a", "vec4"), SC("motion_ddaddt", "vec4") }, l_motion_acceleration);
 aqc_registrar r_domain("basic/Domain.cl", "entry", 0,
     { OUT("imove", "int*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"),
       OUT("m", "float*"), SC("N", "usize"), SC("domain_min", "vec"), SC("domain_max", "vec") },

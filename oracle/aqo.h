@@ -212,6 +212,20 @@ void aqo_reduce_sum_vec_tree(const float* v, aqo_usize N, int ncomp,
 float aqo_reduce_max(const float* v, aqo_usize N);
 aqo_usize aqo_reduce_max_u32(const aqo_usize* v, aqo_usize N);
 
+/* cfd/Motions/{Transform,UnTransform,Velocity,Acceleration}.cl (preset cfd/motion.xml) */
+void aqo_motion_transform(const unsigned* iset, const int* imove, float* r, float* normal,
+                          float* tangent, aqo_usize N, unsigned motion_iset,
+                          const float* motion_r, const float* motion_a, int dims);
+void aqo_motion_untransform(const unsigned* iset, const int* imove, float* r, float* normal,
+                            float* tangent, aqo_usize N, unsigned motion_iset,
+                            const float* motion_r_in, const float* motion_a_in, int dims);
+void aqo_motion_velocity(const unsigned* iset, const int* imove, const float* r, float* u,
+                         aqo_usize N, unsigned motion_iset, const float* motion_drdt,
+                         const float* motion_a, const float* motion_dadt, int dims);
+void aqo_motion_acceleration(const unsigned* iset, const int* imove, const float* r, float* dudt,
+                             aqo_usize N, unsigned motion_iset, const float* motion_ddrddt,
+                             const float* motion_a, const float* motion_ddaddt, int dims);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1071,3 +1071,138 @@ void aqo_bie_pst(const aqo_ll* L, const int* imove, float* r,
         NEIGHS_END
     }
 }
+
+/* ============================ prescribed motions ========================== *
+ * cfd/Motions/{Transform,UnTransform,Velocity,Acceleration}.cl (preset
+ * resources/Presets/src/cfd/motion.xml:55-72): rigid motion of the non-fluid
+ * particles of one set, Euler-XYZ angles (phi, theta, psi) = motion_a.xyz.
+ * vec scalars (motion_r, ...) are arrays of VS(dims) floats, vec4 ones of 4. */
+
+/* rotate (x, y, z) of up to three vectors in place: along x, then y (3-D only), then z;
+ * (s_phi, s_theta, s_psi) are passed signed so that UnTransform can reuse the stages */
+static inline void rot_x(float* v, float c, float s)
+{
+    const float y = v[1], z = v[2];
+    v[1] = c * y - s * z;
+    v[2] = s * y + c * z;
+}
+static inline void rot_y(float* v, float c, float s)
+{
+    const float x = v[0], z = v[2];
+    v[0] = c * x + s * z;
+    v[2] = -s * x + c * z;
+}
+static inline void rot_z(float* v, float c, float s)
+{
+    const float x = v[0], y = v[1];
+    v[0] = c * x - s * y;
+    v[1] = s * x + c * y;
+}
+/* OpenCL normalize over the whole vec (w = 0 in 3-D): v / length(v), products summed left to right */
+static inline void normalize_vec(float* v, int vs)
+{
+    float d = v[0] * v[0];
+    for (int k = 1; k < vs; k++)
+        d = d + v[k] * v[k];
+    const float l = sqrtf(d);
+    for (int k = 0; k < vs; k++)
+        v[k] = v[k] / l;
+}
+
+/* cfd/Motions/Transform.cl:68-134 */
+void aqo_motion_transform(const unsigned* iset, const int* imove, float* r, float* normal,
+                          float* tangent, aqo_usize N, unsigned motion_iset,
+                          const float* motion_r, const float* motion_a, int dims)
+{
+    const int vs = VS(dims);
+    const float cphi = cosf(motion_a[0]), sphi = sinf(motion_a[0]);
+    const float cth = cosf(motion_a[1]), sth = sinf(motion_a[1]);
+    const float cpsi = cosf(motion_a[2]), spsi = sinf(motion_a[2]);
+    AQO_FOR_I(N) {
+        if (iset[i] != motion_iset || imove[i] == 1)
+            continue;
+        float* v[3] = { r + (size_t)i * vs, normal + (size_t)i * vs, tangent + (size_t)i * vs };
+        for (int a = 0; a < 3; a++) {
+            if (dims == 3) {
+                rot_x(v[a], cphi, sphi);
+                rot_y(v[a], cth, sth);
+            }
+            rot_z(v[a], cpsi, spsi);
+        }
+        for (int k = 0; k < vs; k++)
+            v[0][k] = v[0][k] + motion_r[k];
+        normalize_vec(v[1], vs);
+        normalize_vec(v[2], vs);
+    }
+}
+
+/* cfd/Motions/UnTransform.cl:54-119: the inverse rotations in the inverse order */
+void aqo_motion_untransform(const unsigned* iset, const int* imove, float* r, float* normal,
+                            float* tangent, aqo_usize N, unsigned motion_iset,
+                            const float* motion_r_in, const float* motion_a_in, int dims)
+{
+    const int vs = VS(dims);
+    const float cphi = cosf(motion_a_in[0]), sphi = -sinf(motion_a_in[0]);
+    const float cth = cosf(motion_a_in[1]), sth = -sinf(motion_a_in[1]);
+    const float cpsi = cosf(motion_a_in[2]), spsi = -sinf(motion_a_in[2]);
+    AQO_FOR_I(N) {
+        if (iset[i] != motion_iset || imove[i] == 1)
+            continue;
+        float* v[3] = { r + (size_t)i * vs, normal + (size_t)i * vs, tangent + (size_t)i * vs };
+        for (int k = 0; k < vs; k++)
+            v[0][k] = v[0][k] - motion_r_in[k];
+        for (int a = 0; a < 3; a++) {
+            rot_z(v[a], cpsi, spsi);
+            if (dims == 3) {
+                rot_y(v[a], cth, sth);
+                rot_x(v[a], cphi, sphi);
+            }
+        }
+    }
+}
+
+/* cfd/Motions/Velocity.cl:74-121 and Acceleration.cl (same shape): omega x r in the local
+ * frame (r is still untransformed there), rotated, plus the linear part */
+static void motion_rate(const unsigned* iset, const int* imove, const float* r, float* out,
+                        aqo_usize N, unsigned motion_iset, const float* lin,
+                        const float* motion_a, const float* w, int dims)
+{
+    const int vs = VS(dims);
+    const float cphi = cosf(motion_a[0]), sphi = sinf(motion_a[0]);
+    const float cth = cosf(motion_a[1]), sth = sinf(motion_a[1]);
+    const float cpsi = cosf(motion_a[2]), spsi = sinf(motion_a[2]);
+    AQO_FOR_I(N) {
+        if (iset[i] != motion_iset || imove[i] == 1)
+            continue;
+        const float* p = r + (size_t)i * vs;
+        float v[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (dims == 2) {
+            v[0] = -w[2] * p[1];
+            v[1] = w[2] * p[0];
+        } else { /* cross(float4, float4): w = 0 */
+            v[0] = w[1] * p[2] - w[2] * p[1];
+            v[1] = w[2] * p[0] - w[0] * p[2];
+            v[2] = w[0] * p[1] - w[1] * p[0];
+            rot_x(v, cphi, sphi);
+            rot_y(v, cth, sth);
+        }
+        rot_z(v, cpsi, spsi);
+        for (int k = 0; k < vs; k++)
+            out[(size_t)i * vs + k] = v[k] + lin[k];
+    }
+}
+
+void aqo_motion_velocity(const unsigned* iset, const int* imove, const float* r, float* u,
+                         aqo_usize N, unsigned motion_iset, const float* motion_drdt,
+                         const float* motion_a, const float* motion_dadt, int dims)
+{
+    motion_rate(iset, imove, r, u, N, motion_iset, motion_drdt, motion_a, motion_dadt, dims);
+}
+
+/* Acceleration.cl declares motion_r too and does not use it */
+void aqo_motion_acceleration(const unsigned* iset, const int* imove, const float* r, float* dudt,
+                             aqo_usize N, unsigned motion_iset, const float* motion_ddrddt,
+                             const float* motion_a, const float* motion_ddaddt, int dims)
+{
+    motion_rate(iset, imove, r, dudt, N, motion_iset, motion_ddrddt, motion_a, motion_ddaddt, dims);
+}

@@ -36,6 +36,8 @@ SCRIPTS = [
     "cfd/Boundary/BI/LapU.cl", "cfd/Boundary/BI/GradP.cl", "cfd/Boundary/BI/Interpolation.cl",
     "cfd/Boundary/BI/InterpolationShepard.cl", "cfd/Boundary/BI/Interactions.cl",
     "cfd/Boundary/BI/Shepard.cl", "cfd/Boundary/ElasticBounce.cl",
+    "cfd/Motions/Transform.cl", "cfd/Motions/UnTransform.cl", "cfd/Motions/Velocity.cl",
+    "cfd/Motions/Acceleration.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

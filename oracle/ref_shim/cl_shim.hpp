@@ -239,6 +239,15 @@ inline float fabs(float x) { return fabsf(x); }
 inline float sqrt(float x) { return sqrtf(x); }
 inline float pow(float x, float y) { return powf(x, y); }
 inline float atan(float x) { return atanf(x); }
+inline float cos(float x) { return cosf(x); }
+inline float sin(float x) { return sinf(x); }
+// OpenCL normalize: a vector of the same direction and length 1 (here: v / length(v))
+inline float2 normalize(const float2& a) { const float l = length(a); return float2(a.x / l, a.y / l); }
+inline float4 normalize(const float4& a)
+{
+    const float l = length(a);
+    return float4(a.x / l, a.y / l, a.z / l, a.w / l);
+}
 inline float acospi(float x) { return acosf(x) * 0.318309886183790671538f; }
 inline float min(float a, float b) { return b < a ? b : a; }   // OpenCL: y if y < x, else x
 inline float max(float a, float b) { return a < b ? b : a; }   // OpenCL: y if x < y, else x

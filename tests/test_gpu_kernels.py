@@ -191,3 +191,63 @@ def test_pair_mask_cache_is_dropped_when_its_inputs_change(oracle):
         assert a.tobytes() == b.tobytes()
     assert not np.array_equal(res[0][0], res[0][4]) and not np.array_equal(res[0][4], res[0][8])
     assert stats["builds"] == 5 and stats["hits"] == 8, stats  # step 0 builds twice (Shepard adds i classes)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_motion_kernels(oracle, dims):
+    """cfd/Motions/{Velocity,Acceleration,Transform,UnTransform}.cl (moving walls, preset
+    cfd/motion.xml) through the Kernel-tool C-ABI vs the oracle (itself bit-identical to the
+    reference's scripts, tests/test_oracle_vs_reference.py).  The launcher evaluates cos / sin of
+    the three angles on the host, the kernels are built without FMA contraction: fp32 rounding of a
+    handful of products is all that may differ (tolerance 2e-6 of the largest value; in practice the
+    arrays are bit-identical)."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(11)
+    h = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r")}
+    h["iset"] = (np.arange(N) % 2).astype(np.uint32)
+    h["normal"] = rng.normal(size=(N, V)).astype(np.float32)
+    h["tangent"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        h["normal"][:, 3] = 0
+        h["tangent"][:, 3] = 0
+    h["u"] = np.zeros((N, V), np.float32)
+    h["dudt"] = np.zeros((N, V), np.float32)
+    sc = dict(N=N, motion_iset=1,
+              motion_r=np.array([0.3, -0.2, 0.1, 0.0], np.float32)[:V].copy(),
+              motion_a=np.array([0.21, -0.13, 0.37, 0.0], np.float32),
+              motion_drdt=np.array([0.5, 0.25, -0.125, 0.0], np.float32)[:V].copy(),
+              motion_dadt=np.array([0.7, -0.4, 1.1, 0.0], np.float32),
+              motion_ddrddt=np.array([-1.5, 0.75, 2.0, 0.0], np.float32)[:V].copy(),
+              motion_ddaddt=np.array([0.9, 0.3, -0.6, 0.0], np.float32))
+    sc["motion_r_in"], sc["motion_a_in"] = sc["motion_r"], sc["motion_a"]
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(v) for k, v in h.items()}
+    d.update(sc)
+    o = {k: v.copy() for k, v in h.items()}
+
+    def check(keys, what):
+        for k in keys:
+            a, b = o[k].astype(np.float64), d[k].get().astype(np.float64)
+            assert np.abs(a - b).max() <= 2e-6 * max(np.abs(a).max(), 1.0), (what, k)
+
+    ctx.launch("cfd/Motions/Velocity.cl", "entry", d)
+    oracle.call("motion_velocity", o["iset"], o["imove"], o["r"], o["u"], N, 1, sc["motion_drdt"],
+                sc["motion_a"], sc["motion_dadt"], dims)
+    ctx.launch("cfd/Motions/Acceleration.cl", "entry", d)
+    oracle.call("motion_acceleration", o["iset"], o["imove"], o["r"], o["dudt"], N, 1, sc["motion_ddrddt"],
+                sc["motion_a"], sc["motion_ddaddt"], dims)
+    check(("u", "dudt"), "rates")
+    ctx.launch("cfd/Motions/Transform.cl", "entry", d)
+    oracle.call("motion_transform", o["iset"], o["imove"], o["r"], o["normal"], o["tangent"], N, 1,
+                sc["motion_r"], sc["motion_a"], dims)
+    check(("r", "normal", "tangent"), "transform")
+    moved = (h["iset"] == 1) & (h["imove"] != 1)
+    assert np.abs(d["r"].get()[moved] - h["r"][moved]).max() > 0.05
+    assert np.array_equal(d["r"].get()[~moved], h["r"][~moved])
+    ctx.launch("cfd/Motions/UnTransform.cl", "entry", d)
+    oracle.call("motion_untransform", o["iset"], o["imove"], o["r"], o["normal"], o["tangent"], N, 1,
+                sc["motion_r_in"], sc["motion_a_in"], dims)
+    check(("r", "normal", "tangent"), "untransform")
+    assert np.abs(d["r"].get() - h["r"]).max() < 2e-6 * np.abs(h["r"]).max() + 1e-6   # round trip
+    ctx.close()

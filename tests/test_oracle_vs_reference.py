@@ -103,3 +103,63 @@ def test_time_schemes_and_permutation_match_reference_scripts(oracle, dims):
         assert np.array_equal(v[k], oracle.scatter(base[k], ll["inv_perm"])), k
     assert np.array_equal(v["dudt_in"], oracle.scatter(base["dudt"], ll["inv_perm"]))   # Sort.cl:119-123
     assert np.array_equal(v["drhodt_in"], oracle.scatter(base["drhodt"], ll["inv_perm"]))
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_motion_kernels_match_reference_scripts(oracle, dims):
+    """cfd/Motions/{Transform,UnTransform,Velocity,Acceleration}.cl (the moving-wall preset,
+    cfd/motion.xml): the restatement is bit-identical to the reference's scripts, and Transform
+    followed by UnTransform gives the positions back."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    R = ref.Ref(dims, case["h"])
+    rng = np.random.default_rng(11)
+    base = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r", "normal", "tangent")}
+    base["iset"] = (np.arange(N) % 2).astype(np.uint32)           # two sets: only set 1 moves
+    base["normal"] = rng.normal(size=(N, V)).astype(np.float32)
+    base["tangent"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        base["normal"][:, 3] = 0
+        base["tangent"][:, 3] = 0
+    sc = dict(N=N, motion_iset=1,
+              motion_r=np.array([0.3, -0.2, 0.1, 0.0], np.float32)[:V].copy(),
+              motion_a=np.array([0.21, -0.13, 0.37, 0.0], np.float32),
+              motion_drdt=np.array([0.5, 0.25, -0.125, 0.0], np.float32)[:V].copy(),
+              motion_dadt=np.array([0.7, -0.4, 1.1, 0.0], np.float32),
+              motion_ddrddt=np.array([-1.5, 0.75, 2.0, 0.0], np.float32)[:V].copy(),
+              motion_ddaddt=np.array([0.9, 0.3, -0.6, 0.0], np.float32))
+    sc["motion_r_in"], sc["motion_a_in"] = sc["motion_r"], sc["motion_a"]
+
+    def fresh():
+        v = {k: a.copy() for k, a in base.items()}
+        v["u"] = np.zeros((N, V), np.float32)
+        v["dudt"] = np.zeros((N, V), np.float32)
+        v.update(sc)
+        return v
+
+    a, b = fresh(), fresh()
+    moved = (base["iset"] == 1) & (base["imove"] != 1)
+    assert moved.any() and (~moved).any()
+    # velocity / acceleration are evaluated on the untransformed (local) positions
+    R.run("cfd/Motions/Velocity.cl", "entry", N, a)
+    oracle.call("motion_velocity", b["iset"], b["imove"], b["r"], b["u"], N, 1, sc["motion_drdt"],
+                sc["motion_a"], sc["motion_dadt"], dims)
+    R.run("cfd/Motions/Acceleration.cl", "entry", N, a)
+    oracle.call("motion_acceleration", b["iset"], b["imove"], b["r"], b["dudt"], N, 1, sc["motion_ddrddt"],
+                sc["motion_a"], sc["motion_ddaddt"], dims)
+    R.run("cfd/Motions/Transform.cl", "entry", N, a)
+    oracle.call("motion_transform", b["iset"], b["imove"], b["r"], b["normal"], b["tangent"], N, 1,
+                sc["motion_r"], sc["motion_a"], dims)
+    for k in ("u", "dudt", "r", "normal", "tangent"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["r"][~moved], base["r"][~moved]) and np.abs(a["u"][moved]).max() > 0
+    assert np.abs(a["r"][moved] - base["r"][moved]).max() > 0.05
+    assert np.allclose(np.linalg.norm(a["normal"][moved], axis=1), 1.0, atol=1e-6)
+    unit_n = a["normal"].copy()
+    R.run("cfd/Motions/UnTransform.cl", "entry", N, a)
+    oracle.call("motion_untransform", b["iset"], b["imove"], b["r"], b["normal"], b["tangent"], N, 1,
+                sc["motion_r_in"], sc["motion_a_in"], dims)
+    for k in ("r", "normal", "tangent"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.abs(a["r"] - base["r"]).max() < 2e-6 * np.abs(base["r"]).max() + 1e-6   # round trip
+    del unit_n
