@@ -420,6 +420,58 @@ int l_motion_acceleration(aqc_ctx* c, size_t, void* const* a)
              aqc_scalar<uint32_t>(a, 5), aqc_vec_scalar(a, 7, c->defs.dims), w, motion_trig(ang, 1.f));
 }
 
+// ---- cfd/Energy/Energy.cl::power (:59-87) and ::energy (:114-145), preset cfd/energy.xml ---------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_energy_power(float* dekdt, float* depdt, float* decdt, const int* imove, const void* u, const float* rho,
+               const float* m, const float* p, const void* dudt, const float* drhodt, uint32_t N, aqc_f4 g)
+{
+    GID;
+    if (imove[i] != 1) {
+        dekdt[i] = 0.f;
+        depdt[i] = 0.f;
+        decdt[i] = 0.f;
+        return;
+    }
+    const V<D> u_i = V<D>::ld(u, i);
+    depdt[i] = -m[i] * from_f4<D>(g).dot(u_i);
+    dekdt[i] = m[i] * u_i.dot(V<D>::ld(dudt, i));
+    decdt[i] = m[i] * p[i] / (rho[i] * rho[i]) * drhodt[i];
+}
+int l_energy_power(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 10);
+    DISPATCH(c, k_energy_power, N, (float*)a[0], (float*)a[1], (float*)a[2], (const int*)a[3], a[4],
+             (const float*)a[5], (const float*)a[6], (const float*)a[7], a[8], (const float*)a[9], N,
+             aqc_vec_scalar(a, 11, c->defs.dims));
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_energy_energy(float* ek, float* ep, float* ec, const uint32_t* iset, const int* imove, const void* r,
+                const void* u, const float* rho, const float* m, const float* refd, uint32_t N, aqc_f4 g,
+                float cs)
+{
+    GID;
+    if (imove[i] != 1) {
+        ek[i] = 0.f;
+        ep[i] = 0.f;
+        ec[i] = 0.f;
+        return;
+    }
+    const V<D> u_i = V<D>::ld(u, i);
+    ek[i] = 0.5f * m[i] * u_i.dot(u_i);
+    ep[i] = -m[i] * from_f4<D>(g).dot(V<D>::ld(r, i));
+    const float rho0 = refd[iset[i]];
+    ec[i] = m[i] * cs * cs * (rho0 / rho[i] + logf(rho[i] / rho0) - 1.f);
+}
+int l_energy_energy(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 10);
+    DISPATCH(c, k_energy_energy, N, (float*)a[0], (float*)a[1], (float*)a[2], (const uint32_t*)a[3],
+             (const int*)a[4], a[5], a[6], (const float*)a[7], (const float*)a[8], (const float*)a[9], N,
+             aqc_vec_scalar(a, 11, c->defs.dims), aqc_scalar<float>(a, 12));
+}
+
 // ---- basic/Sort.cl:57-78 (stage1) and :102-124 (stage2) ----------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -1207,6 +1259,15 @@ aqc_registrar r_mo_a("cfd/Motions/Acceleration.cl", "entry", 0,
     { IN("iset", "uint*"), IN("imove", "int*"), RO("r", "vec*"), OUT("dudt", "vec*"), SC("N", "usize"),
       SC("motion_iset", "unsigned int"), SC("motion_r", "vec"), SC("motion_ddrddt", "vec"),
       SC("motion_a", "vec4"), SC("motion_ddaddt", "vec4") }, l_motion_acceleration);
+aqc_registrar r_en_p("cfd/Energy/Energy.cl", "power", 0,
+    { OUT("energy_dekdt", "float*"), OUT("energy_depdt", "float*"), OUT("energy_decdt", "float*"),
+      IN("imove", "int*"), IN("u", "vec*"), IN("rho", "float*"), IN("m", "float*"), IN("p", "float*"),
+      IN("dudt", "vec*"), IN("drhodt", "float*"), SC("N", "usize"), SC("g", "vec") }, l_energy_power);
+aqc_registrar r_en_e("cfd/Energy/Energy.cl", "energy", 0,
+    { OUT("energy_ek", "float*"), OUT("energy_ep", "float*"), OUT("energy_ec", "float*"),
+      IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
+      IN("m", "float*"), IN("refd", "float*"), SC("N", "usize"), SC("g", "vec"), SC("cs", "float") },
+    l_energy_energy);
 aqc_registrar r_domain("basic/Domain.cl", "entry", 0,
     { OUT("imove", "int*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"),
       OUT("m", "float*"), SC("N", "usize"), SC("domain_min", "vec"), SC("domain_max", "vec") },

@@ -226,6 +226,15 @@ void aqo_motion_acceleration(const unsigned* iset, const int* imove, const float
                              aqo_usize N, unsigned motion_iset, const float* motion_ddrddt,
                              const float* motion_a, const float* motion_ddaddt, int dims);
 
+/* cfd/Energy/Energy.cl::power, ::energy (preset cfd/energy.xml) */
+void aqo_energy_power(float* energy_dekdt, float* energy_depdt, float* energy_decdt, const int* imove,
+                      const float* u, const float* rho, const float* m, const float* p,
+                      const float* dudt, const float* drhodt, aqo_usize N, const float* g, int dims);
+void aqo_energy_energy(float* energy_ek, float* energy_ep, float* energy_ec, const unsigned* iset,
+                       const int* imove, const float* r, const float* u, const float* rho,
+                       const float* m, const float* refd, aqo_usize N, const float* g, float cs,
+                       int dims);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1206,3 +1206,56 @@ void aqo_motion_acceleration(const unsigned* iset, const int* imove, const float
 {
     motion_rate(iset, imove, r, dudt, N, motion_iset, motion_ddrddt, motion_a, motion_ddaddt, dims);
 }
+
+/* ============================== energy report ============================= *
+ * cfd/Energy/Energy.cl (preset resources/Presets/src/cfd/energy.xml): per-particle
+ * power and energy terms, summed afterwards by reduction tools. */
+static inline float dot_vec(const float* a, const float* b, int vs)
+{
+    float d = a[0] * b[0];
+    for (int k = 1; k < vs; k++)
+        d = d + a[k] * b[k];
+    return d;
+}
+
+/* Energy.cl:59-87 */
+void aqo_energy_power(float* energy_dekdt, float* energy_depdt, float* energy_decdt, const int* imove,
+                      const float* u, const float* rho, const float* m, const float* p,
+                      const float* dudt, const float* drhodt, aqo_usize N, const float* g, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1) {
+            energy_dekdt[i] = 0.f;
+            energy_depdt[i] = 0.f;
+            energy_decdt[i] = 0.f;
+            continue;
+        }
+        const float* ui = u + (size_t)i * vs;
+        energy_depdt[i] = -m[i] * dot_vec(g, ui, vs);
+        energy_dekdt[i] = m[i] * dot_vec(ui, dudt + (size_t)i * vs, vs);
+        energy_decdt[i] = m[i] * p[i] / (rho[i] * rho[i]) * drhodt[i];
+    }
+}
+
+/* Energy.cl:114-145 */
+void aqo_energy_energy(float* energy_ek, float* energy_ep, float* energy_ec, const unsigned* iset,
+                       const int* imove, const float* r, const float* u, const float* rho,
+                       const float* m, const float* refd, aqo_usize N, const float* g, float cs,
+                       int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1) {
+            energy_ek[i] = 0.f;
+            energy_ep[i] = 0.f;
+            energy_ec[i] = 0.f;
+            continue;
+        }
+        const float* ui = u + (size_t)i * vs;
+        energy_ek[i] = 0.5f * m[i] * dot_vec(ui, ui, vs);
+        energy_ep[i] = -m[i] * dot_vec(g, r + (size_t)i * vs, vs);
+        const float rho0 = refd[iset[i]];
+        energy_ec[i] = m[i] * cs * cs * (rho0 / rho[i] + logf(rho[i] / rho0) - 1.f);
+    }
+}

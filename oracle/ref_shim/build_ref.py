@@ -37,7 +37,7 @@ SCRIPTS = [
     "cfd/Boundary/BI/InterpolationShepard.cl", "cfd/Boundary/BI/Interactions.cl",
     "cfd/Boundary/BI/Shepard.cl", "cfd/Boundary/ElasticBounce.cl",
     "cfd/Motions/Transform.cl", "cfd/Motions/UnTransform.cl", "cfd/Motions/Velocity.cl",
-    "cfd/Motions/Acceleration.cl",
+    "cfd/Motions/Acceleration.cl", "cfd/Energy/Energy.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

@@ -239,6 +239,7 @@ inline float fabs(float x) { return fabsf(x); }
 inline float sqrt(float x) { return sqrtf(x); }
 inline float pow(float x, float y) { return powf(x, y); }
 inline float atan(float x) { return atanf(x); }
+inline float log(float x) { return logf(x); }
 inline float cos(float x) { return cosf(x); }
 inline float sin(float x) { return sinf(x); }
 // OpenCL normalize: a vector of the same direction and length 1 (here: v / length(v))

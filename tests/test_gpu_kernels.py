@@ -251,3 +251,44 @@ def test_motion_kernels(oracle, dims):
     check(("r", "normal", "tangent"), "untransform")
     assert np.abs(d["r"].get() - h["r"]).max() < 2e-6 * np.abs(h["r"]).max() + 1e-6   # round trip
     ctx.close()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_energy_kernels(oracle, dims):
+    """cfd/Energy/Energy.cl::power / ::energy (preset cfd/energy.xml) through the C-ABI vs the oracle:
+    products and sums without contraction are bit-exact; energy_ec goes through the device's logf
+    (tolerance 1e-6 of the largest value: the bracket rho0/rho + log(rho/rho0) - 1 cancels to ~1e-4)."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(3)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r", "rho", "m", "refd")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        v["u"][:, 3] = 0
+        v["dudt"][:, 3] = 0
+    v["p"] = rng.normal(size=N).astype(np.float32) * 1e3
+    v["drhodt"] = rng.normal(size=N).astype(np.float32)
+    v["rho"] = (v["rho"] * (1 + 0.01 * rng.normal(size=N))).astype(np.float32)
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    names = ("energy_dekdt", "energy_depdt", "energy_decdt", "energy_ek", "energy_ep", "energy_ec")
+    b = {k: np.full(N, 7.0, np.float32) for k in names}
+    oracle.call("energy_power", b["energy_dekdt"], b["energy_depdt"], b["energy_decdt"], v["imove"], v["u"],
+                v["rho"], v["m"], v["p"], v["dudt"], v["drhodt"], N, g, dims)
+    oracle.call("energy_energy", b["energy_ek"], b["energy_ep"], b["energy_ec"], v["iset"], v["imove"], v["r"],
+                v["u"], v["rho"], v["m"], v["refd"], N, g, float(case["cs"]), dims)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(x) for k, x in v.items()}
+    for k in names:
+        d[k] = ctx.array(np.full(N, 7.0, np.float32))
+    d.update(N=N, g=g, cs=float(case["cs"]))
+    ctx.launch("cfd/Energy/Energy.cl", "power", d)
+    ctx.launch("cfd/Energy/Energy.cl", "energy", d)
+    for k in names:
+        got = d[k].get()
+        if k == "energy_ec":
+            assert np.abs(got.astype(np.float64) - b[k]).max() <= 1e-6 * np.abs(b[k]).max() + \
+                2e-7 * float(case["cs"]) ** 2 * np.abs(v["m"]).max(), k
+        else:
+            assert np.array_equal(got, b[k]), k
+    ctx.close()

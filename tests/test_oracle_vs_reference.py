@@ -163,3 +163,34 @@ def test_motion_kernels_match_reference_scripts(oracle, dims):
         assert np.array_equal(a[k], b[k]), k
     assert np.abs(a["r"] - base["r"]).max() < 2e-6 * np.abs(base["r"]).max() + 1e-6   # round trip
     del unit_n
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_energy_kernels_match_reference_scripts(oracle, dims):
+    """cfd/Energy/Energy.cl::power and ::energy (preset cfd/energy.xml), bit-identical."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    R = ref.Ref(dims, case["h"])
+    rng = np.random.default_rng(3)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r", "rho", "m", "refd")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        v["u"][:, 3] = 0
+        v["dudt"][:, 3] = 0
+    v["p"] = rng.normal(size=N).astype(np.float32) * 1e3
+    v["drhodt"] = rng.normal(size=N).astype(np.float32)
+    v["rho"] = (v["rho"] * (1 + 0.01 * rng.normal(size=N))).astype(np.float32)
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    names = ("energy_dekdt", "energy_depdt", "energy_decdt", "energy_ek", "energy_ep", "energy_ec")
+    a = dict(v, N=N, g=g, cs=float(case["cs"]), **{k: np.full(N, 7.0, np.float32) for k in names})
+    b = {k: np.full(N, 7.0, np.float32) for k in names}
+    R.run("cfd/Energy/Energy.cl", "power", N, a)
+    R.run("cfd/Energy/Energy.cl", "energy", N, a)
+    oracle.call("energy_power", b["energy_dekdt"], b["energy_depdt"], b["energy_decdt"], v["imove"], v["u"],
+                v["rho"], v["m"], v["p"], v["dudt"], v["drhodt"], N, g, dims)
+    oracle.call("energy_energy", b["energy_ek"], b["energy_ep"], b["energy_ec"], v["iset"], v["imove"], v["r"],
+                v["u"], v["rho"], v["m"], v["refd"], N, g, float(case["cs"]), dims)
+    for k in names:
+        assert np.array_equal(a[k], b[k]), k
+        assert np.abs(a[k]).max() > 0 and (a[k][v["imove"] != 1] == 0).all(), k
