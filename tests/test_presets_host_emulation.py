@@ -1,0 +1,189 @@
+"""CPU check of the LOGIC of the CUDA kernels behind cfd/motion.xml and cfd/energy.xml: the kernel
+bodies of aquagpusph_b200/csrc/elementwise.cu (k_motion_*, k_energy_*, with the V<D> helpers they
+use) are lifted out of the .cu file as text, compiled for the host by g++ behind a two-screen shim
+(float2/float4, __global__ = nothing, the thread index as a loop variable) without FMA contraction,
+and compared with the oracle on the inputs of tests/test_gpu_presets.py.
+
+What this pins: index and sign conventions, operation order, the host-side cos/sin hoisting.  What
+it cannot pin: the device's own arithmetic (IEEE for + - * / sqrt, so identical; logf is not) and
+the launchers' argument slots -- tests/test_gpu_presets.py does that on a B200.  Nothing here is a
+product path: the shim exists only in this test's temporary directory."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CU = os.path.join(ROOT, "aquagpusph_b200", "csrc", "elementwise.cu")
+
+SHIM = r"""
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
+struct aqc_f4 { float x, y, z, w; };
+#define __device__
+#define __global__
+#define __launch_bounds__(n)
+static size_t g_i;
+#define GID const size_t i = g_i; if (i >= N) return;
+"""
+
+WRAP = r"""
+static aqc_f4 f4(const float* p, int n) { aqc_f4 v{ 0.f, 0.f, 0.f, 0.f }; memcpy(&v, p, 4 * n); return v; }
+#define FOR_ALL(CALL3, CALL2) for (g_i = 0; g_i < N; g_i++) { if (dims == 3) { CALL3; } else { CALL2; } }
+extern "C" {
+void emu_transform(int dims, const uint32_t* iset, const int* imove, void* r, void* n, void* t, uint32_t N,
+                   uint32_t set, const float* mr, const float* ang)
+{
+    aqc_f4 a = f4(ang, 4), lin = f4(mr, dims == 3 ? 4 : 2);
+    FOR_ALL(k_motion_transform<3>(iset, imove, r, n, t, N, set, lin, motion_trig(a, 1.f)),
+            k_motion_transform<2>(iset, imove, r, n, t, N, set, lin, motion_trig(a, 1.f)))
+}
+void emu_untransform(int dims, const uint32_t* iset, const int* imove, void* r, void* n, void* t, uint32_t N,
+                     uint32_t set, const float* mr, const float* ang)
+{
+    aqc_f4 a = f4(ang, 4), lin = f4(mr, dims == 3 ? 4 : 2);
+    FOR_ALL(k_motion_untransform<3>(iset, imove, r, n, t, N, set, lin, motion_trig(a, -1.f)),
+            k_motion_untransform<2>(iset, imove, r, n, t, N, set, lin, motion_trig(a, -1.f)))
+}
+void emu_rate(int dims, const uint32_t* iset, const int* imove, const void* r, void* out, uint32_t N,
+              uint32_t set, const float* lin_, const float* ang, const float* w_)
+{
+    aqc_f4 a = f4(ang, 4), w = f4(w_, 4), lin = f4(lin_, dims == 3 ? 4 : 2);
+    FOR_ALL(k_motion_rate<3>(iset, imove, r, out, N, set, lin, w, motion_trig(a, 1.f)),
+            k_motion_rate<2>(iset, imove, r, out, N, set, lin, w, motion_trig(a, 1.f)))
+}
+void emu_power(int dims, float* dek, float* dep, float* dec, const int* imove, const void* u, const float* rho,
+               const float* m, const float* p, const void* dudt, const float* drhodt, uint32_t N, const float* g_)
+{
+    aqc_f4 g = f4(g_, dims == 3 ? 4 : 2);
+    FOR_ALL(k_energy_power<3>(dek, dep, dec, imove, u, rho, m, p, dudt, drhodt, N, g),
+            k_energy_power<2>(dek, dep, dec, imove, u, rho, m, p, dudt, drhodt, N, g))
+}
+void emu_energy(int dims, float* ek, float* ep, float* ec, const uint32_t* iset, const int* imove, const void* r,
+                const void* u, const float* rho, const float* m, const float* refd, uint32_t N, const float* g_,
+                float cs)
+{
+    aqc_f4 g = f4(g_, dims == 3 ? 4 : 2);
+    FOR_ALL(k_energy_energy<3>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs),
+            k_energy_energy<2>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs))
+}
+}
+"""
+
+
+def _lift():
+    """The V<D> helpers and the motion / energy kernels of elementwise.cu, launchers removed."""
+    src = open(CU).read()
+    a = src.index("template <int D> struct V;")
+    b = src.index("#define GID")
+    helpers = src[a:b]
+    a = src.index("// ---- cfd/Motions/")
+    b = src.index("// ---- basic/Sort.cl")
+    body = src[a:b]
+    # launchers: 'int l_xxx(aqc_ctx* c, ...)\n{ ... \n}\n' at column 0
+    body = re.sub(r"^int l_\w+\(aqc_ctx\*[^\n]*\n\{\n.*?^\}\n", "", body, flags=re.S | re.M)
+    assert "DISPATCH" not in body and "k_energy_energy" in body and "k_motion_rate" in body
+    return helpers + body
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emu")
+    cpp, so = str(d / "emu.cpp"), str(d / "libemu.so")
+    open(cpp, "w").write(SHIM + _lift() + WRAP)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-fno-fast-math", "-o", so, cpp])
+    return C.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_motion_kernel_bodies_match_the_oracle(oracle, emu, dims):
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(11)
+    h = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r")}
+    h["iset"] = (np.arange(N) % 2).astype(np.uint32)
+    h["normal"] = rng.normal(size=(N, V)).astype(np.float32)
+    h["tangent"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        h["normal"][:, 3] = 0
+        h["tangent"][:, 3] = 0
+    h["u"] = np.zeros((N, V), np.float32)
+    h["dudt"] = np.zeros((N, V), np.float32)
+    mr = np.array([0.3, -0.2, 0.1, 0.0], np.float32)[:V].copy()
+    ma = np.array([0.21, -0.13, 0.37, 0.0], np.float32)
+    drdt = np.array([0.5, 0.25, -0.125, 0.0], np.float32)[:V].copy()
+    dadt = np.array([0.7, -0.4, 1.1, 0.0], np.float32)
+    ddr = np.array([-1.5, 0.75, 2.0, 0.0], np.float32)[:V].copy()
+    dda = np.array([0.9, 0.3, -0.6, 0.0], np.float32)
+    e = {k: v.copy() for k, v in h.items()}
+    o = {k: v.copy() for k, v in h.items()}
+
+    def same(keys):
+        for k in keys:
+            assert e[k].tobytes() == o[k].tobytes(), k
+
+    emu.emu_rate(dims, _p(e["iset"]), _p(e["imove"]), _p(e["r"]), _p(e["u"]), N, 1, _p(drdt), _p(ma), _p(dadt))
+    oracle.call("motion_velocity", o["iset"], o["imove"], o["r"], o["u"], N, 1, drdt, ma, dadt, dims)
+    emu.emu_rate(dims, _p(e["iset"]), _p(e["imove"]), _p(e["r"]), _p(e["dudt"]), N, 1, _p(ddr), _p(ma), _p(dda))
+    oracle.call("motion_acceleration", o["iset"], o["imove"], o["r"], o["dudt"], N, 1, ddr, ma, dda, dims)
+    same(("u", "dudt"))
+    assert np.abs(o["u"]).max() > 0.1 and np.abs(o["dudt"]).max() > 0.1
+    emu.emu_transform(dims, _p(e["iset"]), _p(e["imove"]), _p(e["r"]), _p(e["normal"]), _p(e["tangent"]), N, 1,
+                      _p(mr), _p(ma))
+    oracle.call("motion_transform", o["iset"], o["imove"], o["r"], o["normal"], o["tangent"], N, 1, mr, ma, dims)
+    same(("r", "normal", "tangent"))
+    moved = (h["iset"] == 1) & (h["imove"] != 1)
+    assert moved.any() and np.abs(o["r"][moved] - h["r"][moved]).max() > 0.05
+    emu.emu_untransform(dims, _p(e["iset"]), _p(e["imove"]), _p(e["r"]), _p(e["normal"]), _p(e["tangent"]), N, 1,
+                        _p(mr), _p(ma))
+    oracle.call("motion_untransform", o["iset"], o["imove"], o["r"], o["normal"], o["tangent"], N, 1, mr, ma, dims)
+    same(("r", "normal", "tangent"))
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_energy_kernel_bodies_match_the_oracle(oracle, emu, dims):
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(3)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "iset", "r", "rho", "m", "refd")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        v["u"][:, 3] = 0
+        v["dudt"][:, 3] = 0
+    v["p"] = rng.normal(size=N).astype(np.float32) * 1e3
+    v["drhodt"] = rng.normal(size=N).astype(np.float32)
+    v["rho"] = (v["rho"] * (1 + 0.01 * rng.normal(size=N))).astype(np.float32)
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    cs = float(case["cs"])
+    names = ("energy_dekdt", "energy_depdt", "energy_decdt", "energy_ek", "energy_ep", "energy_ec")
+    o = {k: np.full(N, 7.0, np.float32) for k in names}
+    e = {k: np.full(N, 7.0, np.float32) for k in names}
+    oracle.call("energy_power", o["energy_dekdt"], o["energy_depdt"], o["energy_decdt"], v["imove"], v["u"],
+                v["rho"], v["m"], v["p"], v["dudt"], v["drhodt"], N, g, dims)
+    oracle.call("energy_energy", o["energy_ek"], o["energy_ep"], o["energy_ec"], v["iset"], v["imove"], v["r"],
+                v["u"], v["rho"], v["m"], v["refd"], N, g, cs, dims)
+    emu.emu_power(dims, _p(e["energy_dekdt"]), _p(e["energy_depdt"]), _p(e["energy_decdt"]), _p(v["imove"]),
+                  _p(v["u"]), _p(v["rho"]), _p(v["m"]), _p(v["p"]), _p(v["dudt"]), _p(v["drhodt"]), N, _p(g))
+    emu.emu_energy(dims, _p(e["energy_ek"]), _p(e["energy_ep"]), _p(e["energy_ec"]), _p(v["iset"]),
+                   _p(v["imove"]), _p(v["r"]), _p(v["u"]), _p(v["rho"]), _p(v["m"]), _p(v["refd"]), N, _p(g),
+                   C.c_float(cs))
+    for k in names:
+        assert e[k].tobytes() == o[k].tobytes(), k   # the same libm logf on both sides here
+        assert np.abs(o[k]).max() > 0
