@@ -36,6 +36,7 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
         "DELTA": repr(float(case["delta"][0])), "G": repr(float(-case["g"][case["dims"] - 1])),
         "N": str(int(set_sizes[0])),
         "N_SENSORS": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
+        "NBC": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
         "CLTYPE": "GPU", "CLDEVICE": "0", "CLPLATFORM": "0",
     }
     for k, v in rep.items():
@@ -206,6 +207,68 @@ def spheric2_slab(n_total, rank, size, hfac=3.0, overrides=None, device=0, uniqu
     c = cases.spheric2_dam_break_slab(n_total, hfac, rank, size)
     sim = load("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), overrides, device,
                mpi_rank=rank, mpi_size=size, unique_id=unique_id, transform=multi_device_fixes, **kw)
+    return sim, c
+
+
+def prescribed_roll(theta0=0.0698, period=1.94):
+    """Transform for the tuned-liquid-damper template: the two `python` tools of cfd/motion.xml
+    become `set_scalar` tools.
+
+    `cfd motion data` (examples/2D/spheric_testcase9_tld/src/templates/Motion.py:154-185) integrates a
+    mechanical model driven by the recorded mass position `T_1-94_A100mm_water.dat`, which the
+    reference tree does not ship: it is replaced by the prescribed roll
+    theta(t) = theta0 sin(2 pi t / period) with its two derivatives, evaluated at the same `t` the
+    script reads.  `cfd motion state` (resources/Scripts/cfd/Motions/State.py:30-57) is reproduced
+    exactly, including its first call, which hands the NEW state to UnTransform as the one to undo."""
+    w = "(2 * pi / motion_period)"
+    ph = "(2 * pi * t / motion_period)"
+    variables = (
+        '        <Variable name="motion_theta0" type="float" value="%r" />\n'
+        '        <Variable name="motion_period" type="float" value="%r" />\n'
+        '        <Variable name="motion_first" type="unsigned int" value="1" />\n'
+        '        <Variable name="motion_r_bak" type="vec" value="0.0, 0.0, 0.0, 0.0" />\n'
+        '        <Variable name="motion_a_bak" type="vec4" value="0.0, 0.0, 0.0, 0.0" />\n' % (theta0, period))
+
+    def tool(name, var, value):
+        return ('        <Tool action="add" name="%s" type="set_scalar" once="false" in="%s" value="%s" />\n'
+                % (name, var, value.replace("<", "&lt;")))
+
+    def keep(var, comps):
+        return ", ".join("motion_first ? %s_%s : %s_bak_%s" % (var, c, var, c) for c in comps)
+
+    data = (tool("cfd motion data", "motion_a", "0, 0, motion_theta0 * sin%s, 0" % ph) +
+            tool("cfd motion data dadt", "motion_dadt", "0, 0, motion_theta0 * %s * cos%s, 0" % (w, ph)) +
+            tool("cfd motion data ddaddt", "motion_ddaddt",
+                 "0, 0, 0 - motion_theta0 * %s * %s * sin%s, 0" % (w, w, ph)))
+
+    def state(dims):
+        rc = "xy" if dims == 2 else "xyzw"
+        return (tool("cfd motion state", "motion_r_bak", keep("motion_r", rc)) +
+                tool("cfd motion state a", "motion_a_bak", keep("motion_a", "xyzw")) +
+                tool("cfd motion state started", "motion_first", "0") +
+                tool("cfd motion state r_in", "motion_r_in", ", ".join("motion_r_bak_" + c for c in rc)) +
+                tool("cfd motion state a_in", "motion_a_in", ", ".join("motion_a_bak_" + c for c in "xyzw")) +
+                tool("cfd motion state backup r", "motion_r_bak", ", ".join("motion_r_" + c for c in rc)) +
+                tool("cfd motion state backup a", "motion_a_bak", ", ".join("motion_a_" + c for c in "xyzw")))
+
+    def transform(txt, dims=2):
+        for name, new in (("cfd motion data", data), ("cfd motion state", state(dims))):
+            pat = r'[ \t]*<Tool [^>]*name="%s" type="python"[^>]*/>\n' % name
+            if not re.search(pat, txt):
+                raise KeyError("python tool '%s' not found" % name)
+            txt = re.sub(pat, lambda m: new, txt, 1)
+        return txt.replace("    </Variables>", variables + "    </Variables>", 1)
+
+    return transform
+
+
+def spheric9_tld(n=10000, hfac=4.0, overrides=None, device=0, seed=None, theta0=0.0698, period=1.94, **kw):
+    """BASELINE config 4 (2-D SPHERIC test 9, tuned liquid damper) through the 104-tool pipeline of
+    examples/2D/spheric_testcase9_tld with the prescribed roll of `prescribed_roll`."""
+    from . import cases
+    c = cases.spheric9_tld_2d(n, hfac, seed=seed)
+    sim = load("spheric9_tld_2d", c, (c["n_set0"], c["n_set1"]), overrides, device,
+               transform=prescribed_roll(theta0, period), **kw)
     return sim, c
 
 

@@ -303,6 +303,63 @@ def spheric5_dam_break_2d(n=50000, hfac=3.0, seed=None):
     )
 
 
+def spheric9_tld_2d(n=10000, hfac=4.0, seed=None):
+    """BASELINE config 4: the 2-D tuned liquid damper (SPHERIC test 9), geometry and field
+    initialisation of examples/2D/spheric_testcase9_tld/src/Create.py:41-235: a tank L x H =
+    0.9 x 0.508 m filled to h = 0.092 m (set 0: nx x ny fluid particles, hydrostatic density), closed
+    by bottom, roof, left and right walls of boundary-integral elements (set 1: imove = -3, m = dr,
+    outward normals), which the motion preset rotates around motion_r = (0, 0.47)."""
+    g, cs, courant, refd = 9.81, 50.0, 0.1, 998.0
+    delta, visc_dyn = 0.1, 0.000894
+    H, L, hw = 0.508, 0.9, 0.092
+    dr = (L * hw / n) ** 0.5
+    nx, ny = int(round(L / dr)), int(round(hw / dr))
+    nf = nx * ny
+    h_fluid = ny * dr
+    Nx, Ny = nx, int(round(H / dr)) + 1
+    L, H = Nx * dr, Ny * dr
+    k = np.arange(nf)
+    fluid = np.stack([(k % nx) * dr - 0.5 * (L - dr), (k // nx) * dr + 0.5 * dr], 1)
+    jx, jy = np.arange(Nx) + 0.5, np.arange(Ny) + 0.5
+    bnd = np.concatenate([
+        np.stack([jx * dr - 0.5 * L, np.zeros(Nx)], 1),            # bottom
+        np.stack([jx * dr - 0.5 * L, np.full(Nx, Ny * dr)], 1),    # roof
+        np.stack([np.full(Ny, -0.5 * L), jy * dr], 1),             # left
+        np.stack([np.full(Ny, Nx * dr - 0.5 * L), jy * dr], 1)])   # right
+    nrm = np.concatenate([np.tile([0.0, -1.0], (Nx, 1)), np.tile([0.0, 1.0], (Nx, 1)),
+                          np.tile([-1.0, 0.0], (Ny, 1)), np.tile([1.0, 0.0], (Ny, 1))])
+    nb = len(bnd)
+    N = nf + nb
+    y = np.concatenate([fluid, bnd])[:, 1]
+    press = np.where(y <= h_fluid, refd * g * (h_fluid - y), 0.0)
+    rho = (refd + press / cs ** 2).astype(np.float32)
+    m = (rho.astype(np.float64) * dr ** 2).astype(np.float32)
+    m[nf:] = dr
+    imove = np.ones(N, np.int32)
+    imove[nf:] = -3
+    iset = np.zeros(N, np.uint32)
+    iset[nf:] = 1
+    normal = np.zeros((N, 2), np.float32)
+    normal[nf:] = nrm
+    u = np.zeros((N, 2), np.float32)
+    if seed is not None:
+        rng = np.random.default_rng(seed)
+        u[:nf] = 0.05 * rng.uniform(-1, 1, (nf, 2))
+    radius = (0.25 * L * L + H * H) ** 0.5
+    hh = float(np.float32(np.float32(hfac) * np.float32(dr)))
+    return dict(
+        dims=2, N=N, n_fluid=nf, n_set0=nf, n_set1=nb, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs,
+        p0=0.0, support=2.0, refd=np.array([refd, refd], np.float32),
+        visc_dyn=np.array([visc_dyn, visc_dyn], np.float32), delta=np.array([delta, delta], np.float32),
+        g=np.array([0, -g], np.float32), domain_min=np.array([-1.1 * radius, -0.5 * L], np.float32),
+        domain_max=np.array([1.1 * radius, 1.1 * radius], np.float32), courant=courant, dt_Ma=0.1,
+        dt_min=float(np.float32(0.05 * courant * hh / cs)), id=np.arange(N, dtype=np.uint32),
+        r=np.concatenate([fluid, bnd]).astype(np.float32), imove=imove, iset=iset, normal=normal,
+        tangent=np.zeros((N, 2), np.float32), rho=rho, m=m, u=u, dudt=np.zeros((N, 2), np.float32),
+        drhodt=np.zeros(N, np.float32), motion_r=(0.0, 0.47),
+    )
+
+
 def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None):
     """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way
     examples/3D/spheric_testcase2_dambreak_mpi/src/Create.py:140-200 does it: rank k

@@ -620,6 +620,24 @@ class Interpreter:
         elif key == ("basic/time_scheme/midpoint.cl", "corrector"):
             c("mp_corrector", V["imove"], V["r_in"], V["r"], V["u_in"], V["u"], V["dudt"], V["rho_in"],
               V["rho"], V["drhodt"], N, f32("dt"), d)
+        elif key == ("cfd/Motions/Transform.cl", "entry"):
+            c("motion_transform", V["iset"], V["imove"], V["r"], V["normal"], V["tangent"], N,
+              int(V["motion_iset"]), V["motion_r"], V["motion_a"], d)
+        elif key == ("cfd/Motions/UnTransform.cl", "entry"):
+            c("motion_untransform", V["iset"], V["imove"], V["r"], V["normal"], V["tangent"], N,
+              int(V["motion_iset"]), V["motion_r_in"], V["motion_a_in"], d)
+        elif key == ("cfd/Motions/Velocity.cl", "entry"):
+            c("motion_velocity", V["iset"], V["imove"], V["r"], V["u"], N, int(V["motion_iset"]),
+              V["motion_drdt"], V["motion_a"], V["motion_dadt"], d)
+        elif key == ("cfd/Motions/Acceleration.cl", "entry"):
+            c("motion_acceleration", V["iset"], V["imove"], V["r"], V["dudt"], N, int(V["motion_iset"]),
+              V["motion_ddrddt"], V["motion_a"], V["motion_ddaddt"], d)
+        elif key == ("cfd/Energy/Energy.cl", "power"):
+            c("energy_power", V["energy_dekdt"], V["energy_depdt"], V["energy_decdt"], V["imove"], V["u"],
+              V["rho"], V["m"], V["p"], V["dudt"], V["drhodt"], N, V["g"], d)
+        elif key == ("cfd/Energy/Energy.cl", "energy"):
+            c("energy_energy", V["energy_ek"], V["energy_ep"], V["energy_ec"], V["iset"], V["imove"],
+              V["r"], V["u"], V["rho"], V["m"], V["refd"], N, V["g"], f32("cs"), d)
         elif rel.endswith("h_sensor.cl"):
             # examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60
             r, dr = V["r"], np.float32(V["dr"])

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import cases
-from aquagpusph_b200 import _lib
+from aquagpusph_b200 import _lib, casegen, host
+from aquagpusph_b200 import cases as product_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -113,3 +114,66 @@ def test_energy_kernels(oracle, dims):
         else:
             assert np.array_equal(got, b[k]), k
     ctx.close()
+
+
+TLD_FIELDS = {"r": 1e-6, "u": 2e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}
+
+
+def test_tuned_liquid_damper_pipeline(oracle):
+    """BASELINE config 4: the pipeline of examples/2D/spheric_testcase9_tld (midpoint, BIe boundaries
+    with force / moment reports, energy report, delta-SPH full, moving tank; 104 tools, the two
+    `python` tools replaced by the prescribed roll of casegen.prescribed_roll) on the GPU against the
+    oracle interpreter, three steps of five midpoint sub-iterations each (the residual threshold is
+    set to 0 so that a residual next to it cannot make the two sides stop on different
+    sub-iterations): neighbour structures bit-exact on the first, fluid fields within the fp32 tolerances of the other pipeline tests, the tank's
+    elements (moved by cfd/Motions/*.cl) within 2e-6 of the tank size, the reported force, moment and
+    energies within 5e-4 (sums of N terms in a different order)."""
+    from oracle import interp
+    host.set_log_level(3)
+    case = product_cases.spheric9_tld_2d(3000, 4.0, seed=5)
+    nset = (case["n_set0"], case["n_set1"])
+    tr = casegen.prescribed_roll(0.05, 0.2)   # wall speed ~0.7 m/s: visible in three steps, not violent
+    ov = {"Residual_midpoint_max": "0.0"}
+    I = interp.Interpreter(tr(casegen.instantiate("spheric9_tld_2d", case, nset, ov)), 2)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = case[k]
+    sim = casegen.load("spheric9_tld_2d", case, nset, ov, transform=tr)
+    assert sim.tools() == [(t["name"], t["type"]) for t in I.tools]
+    for step in range(3):
+        I.step()
+        sim.step(1)
+        assert int(sim.scalar("iter_midpoint", np.uint32)) == int(I.V["iter_midpoint"]) == 5
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"])
+        assert abs(float(sim.scalar("t")) - float(I.V["t"])) <= 1e-7 * float(I.V["t"])
+        for k in ("motion_a", "motion_a_in", "motion_dadt", "motion_ddaddt"):   # the same expressions
+            a, b = np.asarray(I.V[k], np.float64), sim.scalar(k, np.float32, 4).astype(np.float64)
+            assert np.abs(a - b).max() <= 1e-6 * max(np.abs(a).max(), 1e-3), (step, k, a, b)
+        if step == 0:
+            for k in ("icell", "id_sorted", "id_unsorted"):
+                assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+            ncw = int(I.V["n_cells"][3])
+            assert np.array_equal(sim.download("ihoc", np.uint32)[:ncw], I.V["ihoc"][:ncw])
+        fl = I.unsorted("imove") == 1
+        for k, tol in TLD_FIELDS.items():
+            a = I.unsorted(k).astype(np.float64)
+            b = sim.download(k, unsorted=True).astype(np.float64)
+            scale = np.abs(a[fl]).max()
+            err = np.abs(a[fl] - b[fl]).max()
+            assert err <= tol * scale, "step %d field %s: err %.3e scale %.3e" % (step, k, err, scale)
+        for k in ("r", "u", "dudt", "normal"):
+            a = I.unsorted(k)[~fl].astype(np.float64)
+            b = sim.download(k, unsorted=True)[~fl].astype(np.float64)
+            assert np.abs(a - b).max() <= 2e-6 * max(np.abs(a).max(), 1.0), "step %d walls %s" % (step, k)
+        if step == 2:   # the tank did move
+            moved = np.abs(sim.download("r", unsorted=True)[~fl] - case["r"][~fl]).max()
+            assert moved > 20 * 2e-6, moved
+        for k, n in (("Force_p", 2), ("Moment_p", 4), ("Force_elastic", 2)):
+            a = np.asarray(I.V[k], np.float64)
+            b = sim.scalar(k, np.float32, n).astype(np.float64)
+            assert np.abs(a - b).max() <= 5e-4 * max(np.abs(I.V["Force_p"]).max(), 1.0), (step, k, a, b)
+        for k in ("energy_Ek_ref", "energy_Ep_ref", "energy_Ec_ref", "energy_dEkdt", "energy_dEpdt"):
+            a, b = float(I.V[k]), float(sim.scalar(k))
+            assert abs(a - b) <= 5e-4 * max(abs(float(I.V["energy_Ep_ref"])), abs(a), 1.0), (step, k, a, b)
+    assert sim.launch_count() > 0
+    sim.close()

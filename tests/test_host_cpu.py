@@ -178,6 +178,7 @@ def test_resolved_dam_break_3d_pipeline():
 @pytest.mark.parametrize("name,src,dims", [
     ("spheric2_dambreak_3d", "examples/3D/spheric_testcase2_dambreak/src/templates", 3),
     ("spheric5_dambreak_2d", "examples/2D/spheric_testcase5_dambreak/src/templates", 2),
+    ("spheric9_tld_2d", "examples/2D/spheric_testcase9_tld/src/templates", 2),
 ])
 def test_committed_templates_match_the_reference_examples(name, src, dims):
     """The committed resolved templates are what our front-end makes of the
