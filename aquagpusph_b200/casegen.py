@@ -33,7 +33,7 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
         "CS": repr(case["cs"]), "COURANT": repr(case["courant"]),
         "DOMAIN_MIN": _vec(case["domain_min"]), "DOMAIN_MAX": _vec(case["domain_max"]),
         "REFD": repr(float(case["refd"][0])), "VISC_DYN": repr(float(case["visc_dyn"][0])),
-        "DELTA": repr(float(case["delta"][0])), "G": repr(float(-case["g"][case["dims"] - 1])),
+        "DELTA": repr(float(case["delta"][0])), "G": repr(float(-case["g"][case["dims"] - 1]) + 0.0),
         "N": str(int(set_sizes[0])),
         "N_SENSORS": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
         "NBC": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
@@ -269,6 +269,18 @@ def spheric9_tld(n=10000, hfac=4.0, overrides=None, device=0, seed=None, theta0=
     c = cases.spheric9_tld_2d(n, hfac, seed=seed)
     sim = load("spheric9_tld_2d", c, (c["n_set0"], c["n_set1"]), overrides, device,
                transform=prescribed_roll(theta0, period), **kw)
+    return sim, c
+
+
+def lattice(n_side=100, hfac=2.0, overrides=None, device=0, **kw):
+    """BASELINE config 5 (uniform 3-D lattice, all fluid, g = 0) through the 36-tool pipeline of
+    cases_xml/src/lattice_3d/Main.xml: the reference's presets basic + improved Euler + cfd +
+    variableTimeStep, i.e. predictor, link-list, sort, EOS, Shepard + Interactions, Rates, corrector,
+    per-particle time step + min reduction."""
+    from . import cases
+    c = cases.lattice(n_side, hfac)
+    c["courant"] = 0.25
+    sim = load("lattice_3d", c, (c["N"],), overrides, device, **kw)
     return sim, c
 
 

@@ -177,3 +177,35 @@ def test_tuned_liquid_damper_pipeline(oracle):
             assert abs(a - b) <= 5e-4 * max(abs(float(I.V["energy_Ep_ref"])), abs(a), 1.0), (step, k, a, b)
     assert sim.launch_count() > 0
     sim.close()
+
+
+@pytest.mark.parametrize("n_side,hfac", [(20, 2.0), (16, 3.0)])
+def test_lattice_pipeline(oracle, n_side, hfac):
+    """BASELINE config 5: the 36-tool lattice pipeline (improved Euler, Shepard + Interactions, Rates,
+    per-particle time step + min reduction; cases_xml/src/lattice_3d) on the GPU against the oracle
+    interpreter, three steps: neighbour structures and dt bit-exact, fields within the fp32
+    tolerances of the dam-break pipeline tests."""
+    from oracle import interp
+    host.set_log_level(3)
+    case = product_cases.lattice(n_side, hfac)
+    I = interp.Interpreter(casegen.instantiate("lattice_3d", case, (case["N"],)), 3)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = case[k]
+    sim = casegen.load("lattice_3d", case, (case["N"],))
+    assert sim.tools() == [(t["name"], t["type"]) for t in I.tools]
+    for step in range(3):
+        I.step()
+        sim.step(1)
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"]), "dt must be bit-exact"
+        if step == 0:
+            for k in ("icell", "id_sorted", "id_unsorted"):
+                assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+            ncw = int(I.V["n_cells"][3])
+            assert np.array_equal(sim.download("ihoc", np.uint32)[:ncw], I.V["ihoc"][:ncw])
+        for k, tol in {"r": 1e-6, "u": 1e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 2e-4}.items():
+            a = I.unsorted(k).astype(np.float64)
+            b = sim.download(k, unsorted=True).astype(np.float64)
+            assert np.abs(a - b).max() <= tol * np.abs(a).max(), "step %d field %s" % (step, k)
+    assert sim.launch_count() > 0
+    sim.close()

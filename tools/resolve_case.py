@@ -31,6 +31,8 @@ CASES = {
     # the reference's own multi-device parity test (tests/2D/MPI_plane)
     "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
     "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
+    # BASELINE config 5: our own Main.xml (cases_xml/src/lattice_3d) over the reference's presets
+    "lattice_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_3d", 3),
 }
 
 
@@ -47,7 +49,7 @@ def resolve(name, src, dims, main="Main.xml"):
     with tempfile.TemporaryDirectory() as tmp:
         root = installed_root(tmp)
         case = os.path.join(tmp, "case")
-        shutil.copytree(os.path.join(REF, src), case)
+        shutil.copytree(os.path.join(ROOT, src[5:]) if src.startswith("repo:") else os.path.join(REF, src), case)
         keys = {}
         for fn in os.listdir(case):
             if not fn.endswith(".xml"):
