@@ -193,9 +193,10 @@ def multi_device_fixes(txt):
     txt = add_tool_after(txt, "cfd minimum time step",
                          '<Tool action="add" name="mpi global dt" type="mpi-allreduce" once="false" '
                          'in="dt" operation="min" />')
-    txt = add_tool_after(txt, "midpoint residual",
-                         '<Tool action="add" name="mpi global residual" type="mpi-allreduce" '
-                         'once="false" in="Residual_midpoint" operation="sum" />')
+    if "midpoint residual" in order:
+        txt = add_tool_after(txt, "midpoint residual",
+                             '<Tool action="add" name="mpi global residual" type="mpi-allreduce" '
+                             'once="false" in="Residual_midpoint" operation="sum" />')
     return txt
 
 
@@ -281,6 +282,22 @@ def lattice(n_side=100, hfac=2.0, overrides=None, device=0, **kw):
     c = cases.lattice(n_side, hfac)
     c["courant"] = 0.25
     sim = load("lattice_3d", c, (c["N"],), overrides, device, **kw)
+    return sim, c
+
+
+def lattice_slab(n_side, rank, size, hfac=2.0, overrides=None, device=0, unique_id=None, nz_local=0, **kw):
+    """BASELINE config 5 on `size` devices: z slabs of the lattice through the 76-tool pipeline of
+    cases_xml/src/lattice_mpi_3d (the lattice pipeline + the reference's cfd/MPI.xml migration and
+    halo presets), with the multi-device additions of `multi_device_fixes`.  nz_local = 0: the
+    n_side^3 lattice cut in `size` slabs (strong scaling, the parity tests); nz_local > 0: every rank
+    generates its own n_side x n_side x nz_local block (weak scaling, the bench)."""
+    from . import cases
+    if nz_local:
+        c = cases.lattice_slab_local(n_side, nz_local, hfac, rank, size)
+    else:
+        c = cases.lattice_slab(n_side, hfac, rank, size)
+    sim = load("lattice_mpi_3d", c, (c["N"],), overrides, device, mpi_rank=rank, mpi_size=size,
+               unique_id=unique_id, transform=multi_device_fixes, **kw)
     return sim, c
 
 

@@ -413,6 +413,76 @@ def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary
     return out
 
 
+def lattice_slab(n_side, hfac, rank, size, buffer_frac=0.1, **kw):
+    """This rank's share of `lattice(n_side, hfac)` for a run on `size` devices: the particles with
+    z in (z0, z1], z slabs of equal thickness between domain_min_z = -2 and domain_max_z = n_side + 2
+    (the planes of cases_xml/src/lattice_mpi_3d/Slabs.xml), followed by buffer particles
+    (imove = -255 parked at domain_max, basic/setBuffer.xml:35-49) that give arrivals room.
+    own = indices of the rows in the one-device lattice."""
+    c = lattice(n_side, hfac, **kw)
+    dmin, dmax = c["domain_min"].copy(), c["domain_max"].copy()
+    dmin[2], dmax[2] = -2.0, n_side + 2.0
+    dmin[3] = dmax[3] = 0.0
+    dz = (float(dmax[2]) - float(dmin[2])) / size
+    z0, z1 = float(dmin[2]) + rank * dz, float(dmin[2]) + (rank + 1) * dz
+    z = c["r"][:, 2]
+    own = np.flatnonzero((z > z0) & (z <= z1))
+    nbuf = max(256, int(buffer_frac * len(own)))
+    N = len(own) + nbuf
+    out = dict(c)
+    for k in ("r", "normal", "tangent", "u", "dudt"):
+        a = np.zeros((N, 4), np.float32)
+        a[:len(own)] = c[k][own]
+        if k == "r":
+            a[len(own):] = dmax
+        out[k] = a
+    for k, fill in (("rho", c["refd"][0]), ("drhodt", 0.0), ("m", c["m"][0])):
+        a = np.full(N, fill, np.float32)
+        a[:len(own)] = c[k][own]
+        out[k] = a
+    im = np.full(N, -255, np.int32)
+    im[:len(own)] = 1
+    out.update(imove=im, iset=np.zeros(N, np.uint32), id=np.arange(N, dtype=np.uint32), N=N, n_fluid=len(own),
+               n_fluid_global=c["N"], n_buffer=nbuf, own=own, domain_min=dmin, domain_max=dmax, slab=(z0, z1))
+    return out
+
+
+def lattice_slab_local(n_xy, nz_local, hfac, rank, size, buffer_frac=0.05, seed=1234, cs=40.0):
+    """Weak-scaled config 5 (8e6 particles per device): this rank's n_xy x n_xy x nz_local block of a
+    lattice that is size * nz_local cells tall, generated locally (nothing of the other ranks'
+    blocks is ever held: 6.4e7 particles on 8 devices), velocities from a generator seeded per rank.
+    domain z = [0, size * nz_local] puts the planes of Slabs.xml exactly between the blocks."""
+    rng = np.random.default_rng(seed + 7919 * rank)
+    ax = [np.arange(n_xy, dtype=np.float32), np.arange(n_xy, dtype=np.float32),
+          np.arange(nz_local, dtype=np.float32) + np.float32(rank * nz_local)]
+    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    n = g.shape[0]
+    nbuf = max(256, int(buffer_frac * n))
+    N = n + nbuf
+    dmin = np.array([-10.0, -10.0, 0.0, 0.0], np.float32)
+    dmax = np.array([n_xy + 10.0, n_xy + 10.0, float(size * nz_local), 0.0], np.float32)
+    r = np.zeros((N, 4), np.float32)
+    r[:n, :3] = g + 0.5
+    r[n:] = dmax
+    u = np.zeros((N, 4), np.float32)
+    u[:n, :3] = (0.01 * cs * rng.uniform(-1, 1, (n, 3))).astype(np.float32)
+    refd = np.float32(1000.0)
+    rho = np.full(N, refd, np.float32)
+    rho[:n] = (refd * (1.0 + 1e-3 * rng.uniform(-1, 1, n))).astype(np.float32)
+    imove = np.full(N, -255, np.int32)
+    imove[:n] = 1
+    z4 = np.zeros((N, 4), np.float32)
+    return dict(
+        dims=3, N=N, n_fluid=n, n_buffer=nbuf, h=float(hfac), dr=1.0, cs=float(cs), p0=0.0, support=2.0,
+        refd=np.array([refd], np.float32), visc_dyn=np.array([1e-3], np.float32),
+        delta=np.array([0.1], np.float32), g=np.zeros(4, np.float32), domain_min=dmin, domain_max=dmax,
+        courant=0.25, dt_Ma=0.1, dt_min=1e-7, id=np.arange(N, dtype=np.uint32), r=r, imove=imove,
+        iset=np.zeros(N, np.uint32), normal=z4, tangent=z4.copy(), rho=rho, m=np.full(N, refd, np.float32),
+        u=u, dudt=z4.copy(), drhodt=np.zeros(N, np.float32),
+        slab=(float(rank * nz_local), float((rank + 1) * nz_local)),
+    )
+
+
 MPI_PLANE_FIELDS = ("r", "u", "dudt", "rho", "drhodt", "m", "imove")
 
 

@@ -265,7 +265,8 @@ class Interpreter:
         for k, (n, scalars) in enumerate(self.sets):
             for name, val in scalars:
                 self.V[name][k] = np.float32(self.eval(val))
-        self.tools = [dict(t.attrib, operation=(t.text or "").strip()) for t in self.root.iter("Tool")]
+        self.tools = [dict(t.attrib, operation=((t.text or "").strip() or t.attrib.get("operation", "")))
+                      for t in self.root.iter("Tool")]
         self.once_done = set()
         self.if_state = {}
         self.steps = 0

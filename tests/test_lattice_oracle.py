@@ -65,3 +65,68 @@ def test_steps_in_the_oracle(oracle):
     mom = (I.V["m"][:, None].astype(np.float64) * I.V["u"]).sum(0)
     scale = (np.abs(c["m"][:, None].astype(np.float64) * c["u"])).sum()
     assert np.abs(mom - mom0)[:3].max() < 1e-5 * scale
+
+
+F_SLAB = ("r", "u", "rho", "dudt", "drhodt")
+
+
+def _serial(n, hfac, steps):
+    from oracle import interp
+    c = cases.lattice(n, hfac)
+    I = interp.Interpreter(casegen.instantiate("lattice_3d", c, (c["N"],)), 3)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = c[k]
+    for _ in range(steps):
+        I.step()
+    return {k: I.unsorted(k) for k in F_SLAB}, float(I.V["dt"])
+
+
+def _two_ranks(n, hfac, steps, size=2):
+    import threading
+    from oracle import interp
+    tr = interp.LocalTransport(size)
+    out, errs = {}, []
+
+    def work(rank):
+        try:
+            c = cases.lattice_slab(n, hfac, rank, size)
+            txt = casegen.multi_device_fixes(casegen.instantiate("lattice_mpi_3d", c, (c["N"],)))
+            I = interp.Interpreter(txt, 3, rank=rank, size=size, transport=tr)
+            for k in casegen.STATE_FIELDS:
+                I.V[k][...] = c[k]
+            for _ in range(steps):
+                I.step()
+            res = {k: I.unsorted(k) for k in F_SLAB}
+            res.update(own=c["own"], imove=I.unsorted("imove"), dt=float(I.V["dt"]), tools=len(I.tools))
+            out[rank] = res
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+            tr._barrier.abort()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(size)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return out
+
+
+def test_z_slabs_on_two_ranks_reproduce_the_serial_run(oracle):
+    """BASELINE config 5 on two devices (CPU oracle, two threads): the lattice split into z slabs,
+    run through cases_xml/lattice_mpi_3d (lattice pipeline + the reference's cfd/MPI.xml and
+    cfd/MPI/planes.xml presets, with casegen.multi_device_fixes), reproduces the one-device run of
+    lattice_3d: the same dt on both ranks, fields to fp32 summation order (the remote pair terms
+    are added after the local ones)."""
+    serial, dt = _serial(12, 2.0, 2)
+    ranks = _two_ranks(12, 2.0, 2)
+    cover = np.concatenate([ranks[r]["own"] for r in range(2)])
+    assert np.array_equal(np.sort(cover), np.arange(12 ** 3))       # the slabs partition the lattice
+    for r in range(2):
+        own = ranks[r]["own"]
+        n = len(own)
+        assert n == 12 ** 3 // 2 and ranks[r]["tools"] == 77           # 76 + the global-dt all-reduce
+        assert ranks[r]["dt"] == dt
+        assert (ranks[r]["imove"][:n] == 1).all() and (ranks[r]["imove"][n:] == -255).all()
+        for k, tol in (("r", 0.0), ("u", 2e-6), ("rho", 5e-7), ("dudt", 1e-4), ("drhodt", 5e-6)):
+            a = serial[k][own].astype(np.float64)
+            b = ranks[r][k][:n].astype(np.float64)
+            assert np.abs(a - b).max() <= tol * np.abs(a).max(), (r, k, np.abs(a - b).max() / np.abs(a).max())
