@@ -472,6 +472,87 @@ int l_energy_energy(aqc_ctx* c, size_t, void* const* a)
              aqc_vec_scalar(a, 11, c->defs.dims), aqc_scalar<float>(a, 12));
 }
 
+// ---- small presets next to the hot path -----------------------------------------------------------
+// cfd/Energy/EnergyKin.cl:38-54 (preset cfd/energy_kin.xml)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_energy_kin(float* energy_kin, const int* imove, const void* u, const float* m, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1) {
+        energy_kin[i] = 0.f;
+        return;
+    }
+    const V<D> u_i = V<D>::ld(u, i);
+    energy_kin[i] = 0.5f * m[i] * u_i.dot(u_i);
+}
+int l_energy_kin(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    DISPATCH(c, k_energy_kin, N, (float*)a[0], (const int*)a[1], a[2], (const float*)a[3], N);
+}
+// cfd/Forces/Forces.cl:50-84 (preset cfd/forces.xml): force and moment of every fluid particle
+template <int D>
+__global__ void __launch_bounds__(256)
+k_forces(void* forces_f, float4* forces_m, const int* imove, const void* r, const void* dudt, const float* m,
+         uint32_t N, aqc_f4 g, aqc_f4 forces_r)
+{
+    GID;
+    if (imove[i] != 1) {
+        V<D>::splat(0.f).st(forces_f, i);
+        forces_m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const V<D> arm = V<D>::ld(r, i) - from_f4<D>(forces_r);
+    const V<D> acc = from_f4<D>(g) - V<D>::ld(dudt, i);
+    const float mass = m[i];
+    (mass * acc).st(forces_f, i);
+    float4 mo = make_float4(0.f, 0.f, mass * (arm.v.x * acc.v.y - arm.v.y * acc.v.x), 0.f);
+    if constexpr (D == 3) {
+        mo.x = mass * (arm.v.y * acc.v.z - arm.v.z * acc.v.y);
+        mo.y = mass * (arm.v.z * acc.v.x - arm.v.x * acc.v.z);
+    }
+    forces_m[i] = mo;
+}
+int l_forces(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_forces, N, a[0], (float4*)a[1], (const int*)a[2], a[3], a[4], (const float*)a[5], N,
+             aqc_vec_scalar(a, 7, d), aqc_vec_scalar(a, 8, d));
+}
+// basic/DensityClamp.cl:41-52 (preset basic/densityClamp.xml)
+__global__ void __launch_bounds__(256)
+k_density_clamp(float* rho_in, uint32_t N, float rho_min, float rho_max)
+{
+    GID;
+    float v = rho_in[i];
+    if (v < rho_min)
+        v = rho_min;
+    if (v > rho_max)
+        v = rho_max;
+    rho_in[i] = v;
+}
+int l_density_clamp(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 1);
+    LAUNCH(c, k_density_clamp, N, (float*)a[0], N, aqc_scalar<float>(a, 2), aqc_scalar<float>(a, 3));
+    return AQC_OK;
+}
+// basic/IdInverse.cl:33-42 (preset basic/id_inverse.xml)
+__global__ void __launch_bounds__(256)
+k_id_inverse(const uint32_t* id, uint32_t* id_inverse, uint32_t N)
+{
+    GID;
+    id_inverse[id[i]] = (uint32_t)i;
+}
+int l_id_inverse(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    LAUNCH(c, k_id_inverse, N, (const uint32_t*)a[0], (uint32_t*)a[1], N);
+    return AQC_OK;
+}
+
 // ---- basic/Sort.cl:57-78 (stage1) and :102-124 (stage2) ----------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -1268,6 +1349,18 @@ aqc_registrar r_en_e("cfd/Energy/Energy.cl", "energy", 0,
       IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
       IN("m", "float*"), IN("refd", "float*"), SC("N", "usize"), SC("g", "vec"), SC("cs", "float") },
     l_energy_energy);
+aqc_registrar r_en_k("cfd/Energy/EnergyKin.cl", "entry", 0,
+    { OUT("energy_kin", "float*"), IN("imove", "int*"), IN("u", "vec*"), IN("m", "float*"), SC("N", "usize") },
+    l_energy_kin);
+// (imove, r, dudt, m of Forces.cl and id of IdInverse.cl are declared without const and only read)
+aqc_registrar r_forces("cfd/Forces/Forces.cl", "entry", 0,
+    { OUT("forces_f", "vec*"), OUT("forces_m", "vec4*"), RO("imove", "int*"), RO("r", "vec*"), RO("dudt", "vec*"),
+      RO("m", "float*"), SC("N", "usize"), SC("g", "vec"), SC("forces_r", "vec") }, l_forces);
+aqc_registrar r_rho_clamp("basic/DensityClamp.cl", "entry", 0,
+    { OUT("rho_in", "float*"), SC("N", "usize"), SC("rho_min", "float"), SC("rho_max", "float") },
+    l_density_clamp);
+aqc_registrar r_id_inv("basic/IdInverse.cl", "entry", 0,
+    { RO("id", "usize*"), OUT("id_inverse", "usize*"), SC("N", "usize") }, l_id_inverse);
 aqc_registrar r_domain("basic/Domain.cl", "entry", 0,
     { OUT("imove", "int*"), OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"),
       OUT("m", "float*"), SC("N", "usize"), SC("domain_min", "vec"), SC("domain_max", "vec") },

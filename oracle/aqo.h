@@ -235,6 +235,16 @@ void aqo_energy_energy(float* energy_ek, float* energy_ep, float* energy_ec, con
                        const float* m, const float* refd, aqo_usize N, const float* g, float cs,
                        int dims);
 
+/* cfd/Energy/EnergyKin.cl:38-54 (preset cfd/energy_kin.xml) */
+void aqo_energy_kin(float* energy_kin, const int* imove, const float* u, const float* m, aqo_usize N, int dims);
+/* cfd/Forces/Forces.cl:50-84 (preset cfd/forces.xml); forces_m is vec4 in 2-D and 3-D */
+void aqo_forces(float* forces_f, float* forces_m, const int* imove, const float* r, const float* dudt,
+                const float* m, aqo_usize N, const float* g, const float* forces_r, int dims);
+/* basic/DensityClamp.cl:41-52 (preset basic/densityClamp.xml) */
+void aqo_density_clamp(float* rho_in, aqo_usize N, float rho_min, float rho_max);
+/* basic/IdInverse.cl:33-42 (preset basic/id_inverse.xml) */
+void aqo_id_inverse(const aqo_usize* id, aqo_usize* id_inverse, aqo_usize N);
+
 #ifdef __cplusplus
 }
 #endif

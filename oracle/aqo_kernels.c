@@ -1259,3 +1259,70 @@ void aqo_energy_energy(float* energy_ek, float* energy_ep, float* energy_ec, con
         energy_ec[i] = m[i] * cs * cs * (rho0 / rho[i] + logf(rho[i] / rho0) - 1.f);
     }
 }
+
+/* ===================== small presets next to the hot path ================== */
+/* cfd/Energy/EnergyKin.cl:38-54 */
+void aqo_energy_kin(float* energy_kin, const int* imove, const float* u, const float* m, aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1) {
+            energy_kin[i] = 0.f;
+            continue;
+        }
+        const float* ui = u + (size_t)i * vs;
+        energy_kin[i] = 0.5f * m[i] * dot_vec(ui, ui, vs);
+    }
+}
+
+/* cfd/Forces/Forces.cl:50-84 */
+void aqo_forces(float* forces_f, float* forces_m, const int* imove, const float* r, const float* dudt,
+                const float* m, aqo_usize N, const float* g, const float* forces_r, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        float* f = forces_f + (size_t)i * vs;
+        float* mo = forces_m + (size_t)i * 4;
+        if (imove[i] != 1) {
+            for (int k = 0; k < vs; k++)
+                f[k] = 0.f;
+            mo[0] = mo[1] = mo[2] = mo[3] = 0.f;
+            continue;
+        }
+        float arm[4] = { 0.f, 0.f, 0.f, 0.f }, acc[4] = { 0.f, 0.f, 0.f, 0.f };
+        for (int k = 0; k < vs; k++) {
+            arm[k] = r[(size_t)i * vs + k] - forces_r[k];
+            acc[k] = g[k] - dudt[(size_t)i * vs + k];
+        }
+        const float mass = m[i];
+        for (int k = 0; k < vs; k++)
+            f[k] = mass * acc[k];
+        mo[2] = mass * (arm[0] * acc[1] - arm[1] * acc[0]);
+        mo[3] = 0.f;
+        if (dims == 3) {
+            mo[0] = mass * (arm[1] * acc[2] - arm[2] * acc[1]);
+            mo[1] = mass * (arm[2] * acc[0] - arm[0] * acc[2]);
+        } else {
+            mo[0] = 0.f;
+            mo[1] = 0.f;
+        }
+    }
+}
+
+/* basic/DensityClamp.cl:41-52 */
+void aqo_density_clamp(float* rho_in, aqo_usize N, float rho_min, float rho_max)
+{
+    AQO_FOR_I(N) {
+        if (rho_in[i] < rho_min)
+            rho_in[i] = rho_min;
+        if (rho_in[i] > rho_max)
+            rho_in[i] = rho_max;
+    }
+}
+
+/* basic/IdInverse.cl:33-42 */
+void aqo_id_inverse(const aqo_usize* id, aqo_usize* id_inverse, aqo_usize N)
+{
+    AQO_FOR_I(N)
+        id_inverse[id[i]] = i;
+}

@@ -278,3 +278,38 @@ def test_lattice_z_slabs_two_gpus_match_one_gpu():
             b = two[r][k].astype(np.float64)
             err = np.abs(a - b).max() / max(np.abs(a).max(), 1e-30)
             assert err <= tol, "rank %d field %s: rel err %.3e" % (r, k, err)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_small_preset_kernels(oracle, dims):
+    """cfd/Energy/EnergyKin.cl, cfd/Forces/Forces.cl, basic/DensityClamp.cl, basic/IdInverse.cl through the
+    Kernel-tool C-ABI vs the oracle: products and differences without contraction, a clamp and a scatter
+    -- bit-exact."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(8)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "r", "m", "rho")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    fr = np.array([0.3, -0.1, 0.2, 0.0], np.float32)[:V].copy()
+    perm = rng.permutation(N).astype(np.uint32)
+    lo, hi = float(np.percentile(v["rho"], 20)), float(np.percentile(v["rho"], 80))
+    o = dict(rho_in=v["rho"].copy(), energy_kin=np.full(N, 7.0, np.float32),
+             forces_f=np.full((N, V), 7.0, np.float32), forces_m=np.full((N, 4), 7.0, np.float32),
+             id_inverse=np.zeros(N, np.uint32))
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(a) for k, a in list(v.items()) + list(o.items())}
+    d["id"] = ctx.array(perm)
+    d.update(N=N, g=g, forces_r=fr, rho_min=lo, rho_max=hi)
+    oracle.call("energy_kin", o["energy_kin"], v["imove"], v["u"], v["m"], N, dims)
+    oracle.call("forces", o["forces_f"], o["forces_m"], v["imove"], v["r"], v["dudt"], v["m"], N, g, fr, dims)
+    oracle.call("density_clamp", o["rho_in"], N, lo, hi)
+    oracle.call("id_inverse", perm, o["id_inverse"], N)
+    ctx.launch("cfd/Energy/EnergyKin.cl", "entry", d)
+    ctx.launch("cfd/Forces/Forces.cl", "entry", d)
+    ctx.launch("basic/DensityClamp.cl", "entry", d)
+    ctx.launch("basic/IdInverse.cl", "entry", d)
+    for k in o:
+        assert np.array_equal(d[k].get(), o[k]), k
+    ctx.close()

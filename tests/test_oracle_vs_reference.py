@@ -194,3 +194,40 @@ def test_energy_kernels_match_reference_scripts(oracle, dims):
     for k in names:
         assert np.array_equal(a[k], b[k]), k
         assert np.abs(a[k]).max() > 0 and (a[k][v["imove"] != 1] == 0).all(), k
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_small_preset_kernels_match_reference_scripts(oracle, dims):
+    """cfd/Energy/EnergyKin.cl (cfd/energy_kin.xml), cfd/Forces/Forces.cl (cfd/forces.xml),
+    basic/DensityClamp.cl (basic/densityClamp.xml), basic/IdInverse.cl (basic/id_inverse.xml):
+    the C restatements are bit-identical to the reference's scripts."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    R = ref.Ref(dims, case["h"])
+    rng = np.random.default_rng(8)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "r", "m", "rho")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    if dims == 3:
+        v["u"][:, 3] = 0
+        v["dudt"][:, 3] = 0
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    fr = np.array([0.3, -0.1, 0.2, 0.0], np.float32)[:V].copy()
+    perm = rng.permutation(N).astype(np.uint32)
+    lo, hi = float(np.percentile(v["rho"], 20)), float(np.percentile(v["rho"], 80))
+    a = dict(v, N=N, g=g, forces_r=fr, id=perm, rho_min=lo, rho_max=hi, rho_in=v["rho"].copy(),
+             energy_kin=np.full(N, 7.0, np.float32), forces_f=np.full((N, V), 7.0, np.float32),
+             forces_m=np.full((N, 4), 7.0, np.float32), id_inverse=np.zeros(N, np.uint32))
+    b = {k: a[k].copy() for k in ("rho_in", "energy_kin", "forces_f", "forces_m", "id_inverse")}
+    R.run("cfd/Energy/EnergyKin.cl", "entry", N, a)
+    R.run("cfd/Forces/Forces.cl", "entry", N, a)
+    R.run("basic/DensityClamp.cl", "entry", N, a)
+    R.run("basic/IdInverse.cl", "entry", N, a)
+    oracle.call("energy_kin", b["energy_kin"], v["imove"], v["u"], v["m"], N, dims)
+    oracle.call("forces", b["forces_f"], b["forces_m"], v["imove"], v["r"], v["dudt"], v["m"], N, g, fr, dims)
+    oracle.call("density_clamp", b["rho_in"], N, lo, hi)
+    oracle.call("id_inverse", perm, b["id_inverse"], N)
+    for k in b:
+        assert a[k].tobytes() == b[k].tobytes(), k
+    assert np.array_equal(b["id_inverse"][perm], np.arange(N)) and b["rho_in"].min() == np.float32(lo)
+    assert np.abs(b["forces_m"][:, 2]).max() > 0 and (b["forces_f"][v["imove"] != 1] == 0).all()

@@ -1,6 +1,6 @@
-"""CPU check of the LOGIC of the CUDA kernels behind cfd/motion.xml and cfd/energy.xml: the kernel
-bodies of aquagpusph_b200/csrc/elementwise.cu (k_motion_*, k_energy_*, with the V<D> helpers they
-use) are lifted out of the .cu file as text, compiled for the host by g++ behind a two-screen shim
+"""CPU check of the LOGIC of the CUDA kernels behind cfd/motion.xml, cfd/energy.xml and the small
+presets next to them: the kernel bodies of aquagpusph_b200/csrc/elementwise.cu (k_motion_*,
+k_energy_*, k_forces, k_density_clamp, k_id_inverse, with the V<D> helpers they use) are lifted out of the .cu file as text, compiled for the host by g++ behind a two-screen shim
 (float2/float4, __global__ = nothing, the thread index as a loop variable) without FMA contraction,
 and compared with the oracle on the inputs of tests/test_gpu_presets.py.
 
@@ -78,6 +78,18 @@ void emu_energy(int dims, float* ek, float* ep, float* ec, const uint32_t* iset,
     FOR_ALL(k_energy_energy<3>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs),
             k_energy_energy<2>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs))
 }
+void emu_small(int dims, float* ekin, void* ff, float4* fm, float* rho_in, const uint32_t* id, uint32_t* inv,
+               const int* imove, const void* r, const void* u, const void* dudt, const float* m, uint32_t N,
+               const float* g_, const float* fr_, float lo, float hi)
+{
+    aqc_f4 g = f4(g_, dims == 3 ? 4 : 2), fr = f4(fr_, dims == 3 ? 4 : 2);
+    FOR_ALL(k_energy_kin<3>(ekin, imove, u, m, N), k_energy_kin<2>(ekin, imove, u, m, N))
+    FOR_ALL(k_forces<3>(ff, fm, imove, r, dudt, m, N, g, fr), k_forces<2>(ff, fm, imove, r, dudt, m, N, g, fr))
+    for (g_i = 0; g_i < N; g_i++) {
+        k_density_clamp(rho_in, N, lo, hi);
+        k_id_inverse(id, inv, N);
+    }
+}
 }
 """
 
@@ -93,7 +105,8 @@ def _lift():
     body = src[a:b]
     # launchers: 'int l_xxx(aqc_ctx* c, ...)\n{ ... \n}\n' at column 0
     body = re.sub(r"^int l_\w+\(aqc_ctx\*[^\n]*\n\{\n.*?^\}\n", "", body, flags=re.S | re.M)
-    assert "DISPATCH" not in body and "k_energy_energy" in body and "k_motion_rate" in body
+    assert "DISPATCH" not in body and "LAUNCH(" not in body
+    assert all(k in body for k in ("k_energy_energy", "k_motion_rate", "k_forces", "k_id_inverse"))
     return helpers + body
 
 
@@ -187,3 +200,33 @@ def test_energy_kernel_bodies_match_the_oracle(oracle, emu, dims):
     for k in names:
         assert e[k].tobytes() == o[k].tobytes(), k   # the same libm logf on both sides here
         assert np.abs(o[k]).max() > 0
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_small_preset_kernel_bodies_match_the_oracle(oracle, emu, dims):
+    """k_energy_kin, k_forces, k_density_clamp, k_id_inverse (cfd/energy_kin.xml, cfd/forces.xml,
+    basic/densityClamp.xml, basic/id_inverse.xml)."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(8)
+    v = {k: np.ascontiguousarray(case[k]).copy() for k in ("imove", "r", "m", "rho")}
+    v["u"] = rng.normal(size=(N, V)).astype(np.float32)
+    v["dudt"] = rng.normal(size=(N, V)).astype(np.float32)
+    g = np.asarray(case["g"], np.float32).ravel()[:V].copy()
+    fr = np.array([0.3, -0.1, 0.2, 0.0], np.float32)[:V].copy()
+    perm = rng.permutation(N).astype(np.uint32)
+    lo, hi = float(np.percentile(v["rho"], 20)), float(np.percentile(v["rho"], 80))
+    o = dict(rho_in=v["rho"].copy(), energy_kin=np.full(N, 7.0, np.float32),
+             forces_f=np.full((N, V), 7.0, np.float32), forces_m=np.full((N, 4), 7.0, np.float32),
+             id_inverse=np.zeros(N, np.uint32))
+    e = {k: a.copy() for k, a in o.items()}
+    oracle.call("energy_kin", o["energy_kin"], v["imove"], v["u"], v["m"], N, dims)
+    oracle.call("forces", o["forces_f"], o["forces_m"], v["imove"], v["r"], v["dudt"], v["m"], N, g, fr, dims)
+    oracle.call("density_clamp", o["rho_in"], N, lo, hi)
+    oracle.call("id_inverse", perm, o["id_inverse"], N)
+    emu.emu_small(dims, _p(e["energy_kin"]), _p(e["forces_f"]), _p(e["forces_m"]), _p(e["rho_in"]), _p(perm),
+                  _p(e["id_inverse"]), _p(v["imove"]), _p(v["r"]), _p(v["u"]), _p(v["dudt"]), _p(v["m"]), N,
+                  _p(g), _p(fr), C.c_float(lo), C.c_float(hi))
+    for k in o:
+        assert e[k].tobytes() == o[k].tobytes(), k
+    assert np.abs(o["forces_m"][:, 2]).max() > 0 and np.abs(o["energy_kin"]).max() > 0
