@@ -153,6 +153,7 @@ extern "C" int aqc_set_define(aqc_ctx* ctx, const char* name, const char* value)
     else if (n == "__DR_FACTOR__") { ctx->dr_factor = parse_define_float(value); ctx->has_dr_factor = true; }
     else if (n == "__MIN_BOUND_DIST__") { ctx->min_bound_dist = parse_define_float(value); ctx->has_min_bound_dist = true; }
     else if (n == "__ELASTIC_FACTOR__") ctx->elastic_factor = parse_define_float(value);
+    else if (n == "TSCHEME_ADAMS_BASHFORTH_STEPS") ctx->ab_steps = (unsigned)strtoul(v.c_str(), nullptr, 10); // "5u"
     else if (n == "KERNEL_NAME") {
         if (v != "Wendland")
             return aqc_fail(ctx, AQC_ERR_ARG, "KERNEL_NAME=%s: only the Wendland kernel is built",

@@ -51,6 +51,8 @@ struct aqc_ctx {
     float min_bound_dist = 0.f;
     float elastic_factor = 0.f;
     bool has_dr_factor = false, has_min_bound_dist = false;
+    // TSCHEME_ADAMS_BASHFORTH_STEPS (adam_bashforth.cl:66-68: 5u unless the problem defines it)
+    unsigned ab_steps = 5u;
     char err[512] = { 0 };
 
     // link-list scratch (grown on demand, never shrunk)

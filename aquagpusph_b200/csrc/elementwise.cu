@@ -472,6 +472,118 @@ int l_energy_energy(aqc_ctx* c, size_t, void* const* a)
              aqc_vec_scalar(a, 11, c->defs.dims), aqc_scalar<float>(a, 12));
 }
 
+// ---- basic/time_scheme/adam_bashforth.cl (preset basic/time_scheme/adams_bashforth.xml) -----------
+// ::predictor (:93-113) is k_copy_state.  The four history levels as1..as4 travel as small structs.
+struct AB4 { void* du[4]; float* dr[4]; };
+struct AB4c { const void* du[4]; const float* dr[4]; };
+// ::sort :122-146
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ab_sort(AB4c in, AB4 out, const uint32_t* id_sorted, uint32_t N)
+{
+    GID;
+    const size_t o = id_sorted[i];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        V<D>::ld(in.du[l], i).st(out.du[l], o);
+        out.dr[l][o] = in.dr[l][i];
+    }
+}
+int l_ab_sort(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 17);
+    AB4c in;
+    AB4 out;
+    for (int l = 0; l < 4; l++) {
+        in.du[l] = a[2 * l];
+        out.du[l] = a[2 * l + 1];
+        in.dr[l] = (const float*)a[8 + 2 * l];
+        out.dr[l] = (float*)a[9 + 2 * l];
+    }
+    DISPATCH(c, k_ab_sort, N, in, out, (const uint32_t*)a[16], N);
+}
+// DYDT_1..DYDT_5 (:148-159): the same fp32 products and sums, left to right
+__device__ inline float ab_rate(unsigned local_iter, float d0, float d1, float d2, float d3, float d4)
+{
+    if (local_iter < 1)
+        return d0;
+    if (local_iter < 2)
+        return 1.5f * d0 - 0.5f * d1;
+    if (local_iter < 3)
+        return 23.f / 12.f * d0 - 4.f / 3.f * d1 + 5.f / 12.f * d2;
+    if (local_iter < 4)
+        return 55.f / 24.f * d0 - 59.f / 24.f * d1 + 37.f / 24.f * d2 - 3.f / 8.f * d3;
+    return 1901.f / 720.f * d0 - 1387.f / 360.f * d1 + 109.f / 30.f * d2 - 637.f / 360.f * d3 +
+           251.f / 720.f * d4;
+}
+// ::corrector :207-255
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ab_corrector(const int* imove, void* r, void* u, const void* dudt, float* rho, const float* drhodt, AB4c as,
+               uint32_t N, float dt, unsigned local_iter)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    constexpr int VS = D == 3 ? 4 : 2;
+    float* rr = reinterpret_cast<float*>(r) + VS * i;
+    float* uu = reinterpret_cast<float*>(u) + VS * i;
+    const float* d0 = reinterpret_cast<const float*>(dudt) + VS * i;
+#pragma unroll
+    for (int k = 0; k < VS; k++) {
+        const float a = ab_rate(local_iter, d0[k], reinterpret_cast<const float*>(as.du[0])[VS * i + k],
+                                reinterpret_cast<const float*>(as.du[1])[VS * i + k],
+                                reinterpret_cast<const float*>(as.du[2])[VS * i + k],
+                                reinterpret_cast<const float*>(as.du[3])[VS * i + k]);
+        rr[k] += dt * uu[k] + 0.5f * dt * dt * a;
+        uu[k] += dt * a;
+    }
+    rho[i] += dt * ab_rate(local_iter, drhodt[i], as.dr[0][i], as.dr[1][i], as.dr[2][i], as.dr[3][i]);
+}
+int l_ab_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 15);
+    const unsigned iter = aqc_scalar<uint32_t>(a, 17);
+    AB4c as;
+    for (int l = 0; l < 4; l++) {
+        as.du[l] = a[7 + 2 * l];
+        as.dr[l] = (const float*)a[8 + 2 * l];
+    }
+    DISPATCH(c, k_ab_corrector, N, (const int*)a[0], a[2], a[3], a[4], (float*)a[5], (const float*)a[6], as, N,
+             aqc_scalar<float>(a, 16), iter < c->ab_steps ? iter : c->ab_steps);
+}
+// ::postcorrector :281-309
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ab_postcorrector(AB4c as, const void* dudt, const float* drhodt, AB4 in, uint32_t N)
+{
+    GID;
+    V<D>::ld(dudt, i).st(in.du[0], i);
+    in.dr[0][i] = drhodt[i];
+#pragma unroll
+    for (int l = 1; l < 4; l++) {
+        V<D>::ld(as.du[l - 1], i).st(in.du[l], i);
+        in.dr[l][i] = as.dr[l - 1][i];
+    }
+}
+int l_ab_postcorrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 16);
+    AB4c as;
+    AB4 in;
+    for (int l = 0; l < 3; l++) {
+        as.du[l] = a[2 * l];
+        as.dr[l] = (const float*)a[2 * l + 1];
+    }
+    as.du[3] = nullptr;
+    as.dr[3] = nullptr;
+    for (int l = 0; l < 4; l++) {
+        in.du[l] = a[8 + 2 * l];
+        in.dr[l] = (float*)a[9 + 2 * l];
+    }
+    DISPATCH(c, k_ab_postcorrector, N, as, a[6], (const float*)a[7], in, N);
+}
+
 // ---- small presets next to the hot path -----------------------------------------------------------
 // cfd/Energy/EnergyKin.cl:38-54 (preset cfd/energy_kin.xml)
 template <int D>
@@ -1349,6 +1461,31 @@ aqc_registrar r_en_e("cfd/Energy/Energy.cl", "energy", 0,
       IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
       IN("m", "float*"), IN("refd", "float*"), SC("N", "usize"), SC("g", "vec"), SC("cs", "float") },
     l_energy_energy);
+// basic/time_scheme/adam_bashforth.cl: ::predictor declares the state it only reads without const, ::corrector
+// everything; the history levels are read-only there
+aqc_registrar r_ab_p("basic/time_scheme/adam_bashforth.cl", "predictor", 0,
+    { RO("r", "vec*"), RO("u", "vec*"), RO("dudt", "vec*"), RO("rho", "float*"), RO("drhodt", "float*"),
+      OUT("r_in", "vec*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"), OUT("rho_in", "float*"),
+      OUT("drhodt_in", "float*"), SC("N", "usize") }, l_copy_state);
+aqc_registrar r_ab_s("basic/time_scheme/adam_bashforth.cl", "sort", 0,
+    { IN("dudt_as1_in", "vec*"), OUT("dudt_as1", "vec*"), IN("dudt_as2_in", "vec*"), OUT("dudt_as2", "vec*"),
+      IN("dudt_as3_in", "vec*"), OUT("dudt_as3", "vec*"), IN("dudt_as4_in", "vec*"), OUT("dudt_as4", "vec*"),
+      IN("drhodt_as1_in", "float*"), OUT("drhodt_as1", "float*"), IN("drhodt_as2_in", "float*"),
+      OUT("drhodt_as2", "float*"), IN("drhodt_as3_in", "float*"), OUT("drhodt_as3", "float*"),
+      IN("drhodt_as4_in", "float*"), OUT("drhodt_as4", "float*"), IN("id_sorted", "usize*"), SC("N", "usize") },
+    l_ab_sort);
+aqc_registrar r_ab_c("basic/time_scheme/adam_bashforth.cl", "corrector", 0,
+    { RO("imove", "int*"), RO("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"), RO("dudt", "vec*"),
+      OUT("rho", "float*"), RO("drhodt", "float*"), RO("dudt_as1", "vec*"), RO("drhodt_as1", "float*"),
+      RO("dudt_as2", "vec*"), RO("drhodt_as2", "float*"), RO("dudt_as3", "vec*"), RO("drhodt_as3", "float*"),
+      RO("dudt_as4", "vec*"), RO("drhodt_as4", "float*"), SC("N", "usize"), SC("dt", "float"),
+      SC("iter", "unsigned int") }, l_ab_corrector);
+aqc_registrar r_ab_pc("basic/time_scheme/adam_bashforth.cl", "postcorrector", 0,
+    { IN("dudt_as1", "vec*"), IN("drhodt_as1", "float*"), IN("dudt_as2", "vec*"), IN("drhodt_as2", "float*"),
+      IN("dudt_as3", "vec*"), IN("drhodt_as3", "float*"), IN("dudt", "vec*"), IN("drhodt", "float*"),
+      OUT("dudt_as1_in", "vec*"), OUT("drhodt_as1_in", "float*"), OUT("dudt_as2_in", "vec*"),
+      OUT("drhodt_as2_in", "float*"), OUT("dudt_as3_in", "vec*"), OUT("drhodt_as3_in", "float*"),
+      OUT("dudt_as4_in", "vec*"), OUT("drhodt_as4_in", "float*"), SC("N", "usize") }, l_ab_postcorrector);
 aqc_registrar r_en_k("cfd/Energy/EnergyKin.cl", "entry", 0,
     { OUT("energy_kin", "float*"), IN("imove", "int*"), IN("u", "vec*"), IN("m", "float*"), SC("N", "usize") },
     l_energy_kin);

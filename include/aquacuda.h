@@ -70,7 +70,8 @@ float aqc_define_round6(float value); /* CalcServer.cpp:245-257 "%#G" + "f" */
 int aqc_set_defs(aqc_ctx* ctx, const aqc_defs* defs);
 /* Any other "-Dname=value" of the problem (CalcServer.cpp:240-265), as text.  The
  * ones the CUDA kernels honour: __DR_FACTOR__, __MIN_BOUND_DIST__ (BIe/ElasticBounce.cl:
- * 31-36, PST.cl:31-33), plus DIMS/H/CONW/CONF/SUPPORT (same as aqc_set_defs).  Returns 0
+ * 31-36, PST.cl:31-33), TSCHEME_ADAMS_BASHFORTH_STEPS (basic/time_scheme/adam_bashforth.cl:66-68),
+ * plus DIMS/H/CONW/CONF/SUPPORT (same as aqc_set_defs).  Returns 0
  * when the definition was consumed, 1 when it is not used by any CUDA kernel, and <0
  * when it selects something this build does not provide (KERNEL_NAME other than
  * Wendland, __LAP_FORMULATION__ other than __LAP_MONAGHAN__ = 1). */

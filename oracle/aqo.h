@@ -245,6 +245,18 @@ void aqo_density_clamp(float* rho_in, aqo_usize N, float rho_min, float rho_max)
 /* basic/IdInverse.cl:33-42 (preset basic/id_inverse.xml) */
 void aqo_id_inverse(const aqo_usize* id, aqo_usize* id_inverse, aqo_usize N);
 
+/* basic/time_scheme/adam_bashforth.cl (preset basic/time_scheme/adams_bashforth.xml): ::sort :122-146,
+ * ::corrector :207-255, ::postcorrector :281-309; ::predictor :93-113 is aqo_mp_predictor's body.
+ * steps = TSCHEME_ADAMS_BASHFORTH_STEPS (5 when undefined, :66-68) */
+void aqo_ab_sort(const float* const* dudt_as_in, float* const* dudt_as, const float* const* drhodt_as_in,
+                 float* const* drhodt_as, const aqo_usize* id_sorted, aqo_usize N, int dims);
+void aqo_ab_corrector(const int* imove, float* r, float* u, const float* dudt, float* rho, const float* drhodt,
+                      const float* const* dudt_as, const float* const* drhodt_as, aqo_usize N, float dt,
+                      unsigned iter, unsigned steps, int dims);
+void aqo_ab_postcorrector(const float* const* dudt_as, const float* const* drhodt_as, const float* dudt,
+                          const float* drhodt, float* const* dudt_as_in, float* const* drhodt_as_in,
+                          aqo_usize N, int dims);
+
 #ifdef __cplusplus
 }
 #endif

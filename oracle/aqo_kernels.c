@@ -1326,3 +1326,78 @@ void aqo_id_inverse(const aqo_usize* id, aqo_usize* id_inverse, aqo_usize N)
     AQO_FOR_I(N)
         id_inverse[id[i]] = i;
 }
+
+/* ================= basic/time_scheme/adam_bashforth.cl ===================== *
+ * The four history levels travel as arrays of 4 pointers (as1..as4). */
+/* :122-146 */
+void aqo_ab_sort(const float* const* dudt_as_in, float* const* dudt_as, const float* const* drhodt_as_in,
+                 float* const* drhodt_as, const aqo_usize* id_sorted, aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        const size_t o = id_sorted[i];
+        for (int l = 0; l < 4; l++) {
+            for (int k = 0; k < vs; k++)
+                dudt_as[l][o * vs + k] = dudt_as_in[l][(size_t)i * vs + k];
+            drhodt_as[l][o] = drhodt_as_in[l][i];
+        }
+    }
+}
+
+/* the extrapolated rate, DYDT_1..DYDT_5 (:148-159): products and sums left to right in fp32 */
+static inline float ab_rate(unsigned local_iter, float d0, float d1, float d2, float d3, float d4)
+{
+    if (local_iter < 1)
+        return d0;
+    if (local_iter < 2)
+        return 1.5f * d0 - 0.5f * d1;
+    if (local_iter < 3)
+        return 23.f / 12.f * d0 - 4.f / 3.f * d1 + 5.f / 12.f * d2;
+    if (local_iter < 4)
+        return 55.f / 24.f * d0 - 59.f / 24.f * d1 + 37.f / 24.f * d2 - 3.f / 8.f * d3;
+    return 1901.f / 720.f * d0 - 1387.f / 360.f * d1 + 109.f / 30.f * d2 - 637.f / 360.f * d3 +
+           251.f / 720.f * d4;
+}
+
+/* :207-255 */
+void aqo_ab_corrector(const int* imove, float* r, float* u, const float* dudt, float* rho, const float* drhodt,
+                      const float* const* dudt_as, const float* const* drhodt_as, aqo_usize N, float dt,
+                      unsigned iter, unsigned steps, int dims)
+{
+    const int vs = VS(dims);
+    const unsigned local_iter = iter < steps ? iter : steps;
+    AQO_FOR_I(N) {
+        if (imove[i] <= 0)
+            continue;
+        for (int k = 0; k < vs; k++) {
+            const size_t j = (size_t)i * vs + k;
+            const float a = ab_rate(local_iter, dudt[j], dudt_as[0][j], dudt_as[1][j], dudt_as[2][j],
+                                    dudt_as[3][j]);
+            r[j] += dt * u[j] + 0.5f * dt * dt * a;
+            u[j] += dt * a;
+        }
+        rho[i] += dt * ab_rate(local_iter, drhodt[i], drhodt_as[0][i], drhodt_as[1][i], drhodt_as[2][i],
+                               drhodt_as[3][i]);
+    }
+}
+
+/* :281-309 */
+void aqo_ab_postcorrector(const float* const* dudt_as, const float* const* drhodt_as, const float* dudt,
+                          const float* drhodt, float* const* dudt_as_in, float* const* drhodt_as_in,
+                          aqo_usize N, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        for (int k = 0; k < vs; k++) {
+            const size_t j = (size_t)i * vs + k;
+            dudt_as_in[0][j] = dudt[j];
+            dudt_as_in[1][j] = dudt_as[0][j];
+            dudt_as_in[2][j] = dudt_as[1][j];
+            dudt_as_in[3][j] = dudt_as[2][j];
+        }
+        drhodt_as_in[0][i] = drhodt[i];
+        drhodt_as_in[1][i] = drhodt_as[0][i];
+        drhodt_as_in[2][i] = drhodt_as[1][i];
+        drhodt_as_in[3][i] = drhodt_as[2][i];
+    }
+}

@@ -639,6 +639,25 @@ class Interpreter:
         elif key == ("cfd/Energy/Energy.cl", "energy"):
             c("energy_energy", V["energy_ek"], V["energy_ep"], V["energy_ec"], V["iset"], V["imove"],
               V["r"], V["u"], V["rho"], V["m"], V["refd"], N, V["g"], f32("cs"), d)
+        elif key == ("basic/time_scheme/adam_bashforth.cl", "predictor"):
+            c("mp_predictor", V["r"], V["u"], V["dudt"], V["rho"], V["drhodt"], V["r_in"], V["u_in"],
+              V["dudt_in"], V["rho_in"], V["drhodt_in"], N, d)
+        elif key == ("basic/time_scheme/adam_bashforth.cl", "sort"):
+            lv = range(1, 5)
+            O.call("ab_sort", O.ptrs(V["dudt_as%d_in" % l] for l in lv), O.ptrs(V["dudt_as%d" % l] for l in lv),
+                   O.ptrs(V["drhodt_as%d_in" % l] for l in lv), O.ptrs(V["drhodt_as%d" % l] for l in lv),
+                   V["id_sorted"], N, d)
+        elif key == ("basic/time_scheme/adam_bashforth.cl", "corrector"):
+            lv = range(1, 5)
+            steps = int(str(self.defs.get("TSCHEME_ADAMS_BASHFORTH_STEPS", "5u")).rstrip("uU"))
+            O.call("ab_corrector", V["imove"], V["r"], V["u"], V["dudt"], V["rho"], V["drhodt"],
+                   O.ptrs(V["dudt_as%d" % l] for l in lv), O.ptrs(V["drhodt_as%d" % l] for l in lv), N,
+                   f32("dt"), int(V["iter"]), steps, d)
+        elif key == ("basic/time_scheme/adam_bashforth.cl", "postcorrector"):
+            lv = range(1, 5)
+            O.call("ab_postcorrector", O.ptrs(V["dudt_as%d" % l] for l in lv),
+                   O.ptrs(V["drhodt_as%d" % l] for l in lv), V["dudt"], V["drhodt"],
+                   O.ptrs(V["dudt_as%d_in" % l] for l in lv), O.ptrs(V["drhodt_as%d_in" % l] for l in lv), N, d)
         elif rel.endswith("h_sensor.cl"):
             # examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60
             r, dr = V["r"], np.float32(V["dr"])

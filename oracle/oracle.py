@@ -59,6 +59,15 @@ def _arg(a):
     return a
 
 
+def ptrs(arrays):
+    """An array of pointers (float* const*) to the given contiguous numpy arrays."""
+    arrays = list(arrays)
+    assert all(isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"] for a in arrays)
+    p = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    p._keep = arrays
+    return p
+
+
 def call(name, *args):
     """Call aqo_<name> converting numpy arrays / python scalars."""
     return getattr(lib(), "aqo_" + name)(*[_arg(a) for a in args])

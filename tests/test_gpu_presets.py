@@ -183,21 +183,23 @@ def test_tuned_liquid_damper_pipeline(oracle):
     sim.close()
 
 
-@pytest.mark.parametrize("n_side,hfac", [(20, 2.0), (16, 3.0)])
-def test_lattice_pipeline(oracle, n_side, hfac):
+@pytest.mark.parametrize("template,n_side,hfac", [("lattice_3d", 20, 2.0), ("lattice_3d", 16, 3.0),
+                                                  ("lattice_ab_3d", 20, 2.0)])
+def test_lattice_pipeline(oracle, template, n_side, hfac):
     """BASELINE config 5: the 36-tool lattice pipeline (improved Euler, Shepard + Interactions, Rates,
     per-particle time step + min reduction; cases_xml/src/lattice_3d) on the GPU against the oracle
     interpreter, three steps: neighbour structures and dt bit-exact, fields within the fp32
-    tolerances of the dam-break pipeline tests."""
+    tolerances of the dam-break pipeline tests.  lattice_ab_3d = the same with the Adams-Bashforth scheme
+    (basic/time_scheme/adams_bashforth.xml, 38 tools), six steps so that every order up to DYDT_5 runs."""
     from oracle import interp
     host.set_log_level(3)
     case = product_cases.lattice(n_side, hfac)
-    I = interp.Interpreter(casegen.instantiate("lattice_3d", case, (case["N"],)), 3)
+    I = interp.Interpreter(casegen.instantiate(template, case, (case["N"],)), 3)
     for k in casegen.STATE_FIELDS:
         I.V[k][...] = case[k]
-    sim = casegen.load("lattice_3d", case, (case["N"],))
+    sim = casegen.load(template, case, (case["N"],))
     assert sim.tools() == [(t["name"], t["type"]) for t in I.tools]
-    for step in range(3):
+    for step in range(6 if template == "lattice_ab_3d" else 3):
         I.step()
         sim.step(1)
         assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
@@ -312,4 +314,28 @@ def test_small_preset_kernels(oracle, dims):
     ctx.launch("basic/IdInverse.cl", "entry", d)
     for k in o:
         assert np.array_equal(d[k].get(), o[k]), k
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_adams_bashforth_kernels(oracle, dims):
+    """basic/time_scheme/adam_bashforth.cl::sort / ::corrector / ::postcorrector through the Kernel-tool
+    C-ABI vs the oracle for iter = 0 .. 6 (every order): copies, and products / sums without
+    contraction -- bit-exact."""
+    from test_oracle_vs_reference import _ab_state, ab_oracle_step
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N = case["N"]
+    o = _ab_state(case, dims, 21)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(x) for k, x in o.items()}
+    for it in range(7):
+        ab_oracle_step(oracle, o, N, dims, 1.25e-3, it)
+        d.update(N=N, dt=1.25e-3, iter=it)
+        ctx.launch("basic/time_scheme/adam_bashforth.cl", "sort", d)
+        ctx.launch("basic/time_scheme/adam_bashforth.cl", "corrector", d)
+        ctx.launch("basic/time_scheme/adam_bashforth.cl", "postcorrector", d)
+        for k in o:
+            assert np.array_equal(d[k].get(), o[k]), (it, k)
+        o["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
+        d["dudt"] = ctx.array(o["dudt"])
     ctx.close()

@@ -130,3 +130,30 @@ def test_z_slabs_on_two_ranks_reproduce_the_serial_run(oracle):
             a = serial[k][own].astype(np.float64)
             b = ranks[r][k][:n].astype(np.float64)
             assert np.abs(a - b).max() <= tol * np.abs(a).max(), (r, k, np.abs(a - b).max() / np.abs(a).max())
+
+
+def test_adams_bashforth_variant(oracle, tmp_path):
+    """lattice_ab_3d: the lattice pipeline with basic/time_scheme/adams_bashforth.xml (38 tools).  Host
+    front-end and interpreter agree on it; its first step (order 1) equals the improved-Euler pipeline's,
+    later steps differ by the scheme, not by orders of magnitude."""
+    from oracle import interp
+    c = cases.lattice(12, 2.0)
+    txt = casegen.instantiate("lattice_ab_3d", c, (c["N"],))
+    p = tmp_path / "ab.xml"
+    p.write_text(txt)
+    tools = host.Simulation(str(p), dims=3, parse_only=True).tools()
+    I = interp.Interpreter(txt, 3)
+    assert tools == [(t["name"], t["type"]) for t in I.tools] and len(tools) == 38
+    names = [n for n, _ in tools]
+    assert names.index("sort adams-bashforth") < names.index("Sort") < names.index("corrector") < \
+        names.index("backup adams-bashforth") < names.index("Corrector")
+    assert I.defs.get("TSCHEME_ADAMS_BASHFORTH_STEPS") == "5u"
+    J = interp.Interpreter(casegen.instantiate("lattice_3d", c, (c["N"],)), 3)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = c[k]
+        J.V[k][...] = c[k]
+    for step in range(6):
+        I.step()
+        J.step()
+        diff = np.abs(I.unsorted("u") - J.unsorted("u")).max()
+        assert (diff == 0) if step == 0 else (0 < diff < 0.05 * np.abs(J.unsorted("u")).max()), (step, diff)

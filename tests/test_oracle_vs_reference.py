@@ -231,3 +231,63 @@ def test_small_preset_kernels_match_reference_scripts(oracle, dims):
         assert a[k].tobytes() == b[k].tobytes(), k
     assert np.array_equal(b["id_inverse"][perm], np.arange(N)) and b["rho_in"].min() == np.float32(lo)
     assert np.abs(b["forces_m"][:, 2]).max() > 0 and (b["forces_f"][v["imove"] != 1] == 0).all()
+
+
+def _ab_state(case, dims, seed):
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(seed)
+
+    def vec():
+        a = rng.normal(size=(N, V)).astype(np.float32)
+        if dims == 3:
+            a[:, 3] = 0
+        return a
+    v = {"imove": np.ascontiguousarray(case["imove"]).copy(), "iset": np.zeros(N, np.uint32),
+         "r": np.ascontiguousarray(case["r"]).copy(), "u": vec(), "dudt": vec(),
+         "rho": np.ascontiguousarray(case["rho"]).copy(), "drhodt": rng.normal(size=N).astype(np.float32),
+         "id_sorted": rng.permutation(N).astype(np.uint32)}
+    for l in range(1, 5):
+        v["dudt_as%d" % l], v["dudt_as%d_in" % l] = vec(), vec()
+        v["drhodt_as%d" % l] = rng.normal(size=N).astype(np.float32)
+        v["drhodt_as%d_in" % l] = rng.normal(size=N).astype(np.float32)
+    return v
+
+
+def ab_oracle_step(oracle, v, N, dims, dt, it, steps=5):
+    """sort -> corrector -> postcorrector of adam_bashforth.cl on the dict v through the C restatement."""
+    lv = range(1, 5)
+    P = oracle.ptrs
+    oracle.call("ab_sort", P(v["dudt_as%d_in" % l] for l in lv), P(v["dudt_as%d" % l] for l in lv),
+                P(v["drhodt_as%d_in" % l] for l in lv), P(v["drhodt_as%d" % l] for l in lv), v["id_sorted"], N, dims)
+    oracle.call("ab_corrector", v["imove"], v["r"], v["u"], v["dudt"], v["rho"], v["drhodt"],
+                P(v["dudt_as%d" % l] for l in lv), P(v["drhodt_as%d" % l] for l in lv), N, float(dt), int(it),
+                int(steps), dims)
+    oracle.call("ab_postcorrector", P(v["dudt_as%d" % l] for l in lv), P(v["drhodt_as%d" % l] for l in lv),
+                v["dudt"], v["drhodt"], P(v["dudt_as%d_in" % l] for l in lv),
+                P(v["drhodt_as%d_in" % l] for l in lv), N, dims)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_adams_bashforth_kernels_match_reference_scripts(oracle, dims):
+    """basic/time_scheme/adam_bashforth.cl::sort / ::corrector / ::postcorrector (preset
+    basic/time_scheme/adams_bashforth.xml) for iter = 0 .. 6, i.e. every order DYDT_1 .. DYDT_5 of the
+    default TSCHEME_ADAMS_BASHFORTH_STEPS = 5: bit-identical.  (::predictor has the body of the midpoint
+    predictor, checked in test_time_schemes_and_permutation_match_reference_scripts.)"""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N = case["N"]
+    R = ref.Ref(dims, case["h"])
+    a = _ab_state(case, dims, 21)
+    b = {k: x.copy() for k, x in a.items()}
+    dt = 1.25e-3
+    for it in range(7):
+        A = dict(a, N=N, dt=dt, iter=it)
+        R.run("basic/time_scheme/adam_bashforth.cl", "sort", N, A)
+        R.run("basic/time_scheme/adam_bashforth.cl", "corrector", N, A)
+        R.run("basic/time_scheme/adam_bashforth.cl", "postcorrector", N, A)
+        ab_oracle_step(oracle, b, N, dims, dt, it)
+        for k in a:
+            assert a[k].tobytes() == b[k].tobytes(), (it, k)
+        # new rates for the next round
+        a["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
+        b["dudt"][...] = a["dudt"]
+    assert not np.array_equal(a["r"], case["r"])

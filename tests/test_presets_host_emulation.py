@@ -1,6 +1,6 @@
 """CPU check of the LOGIC of the CUDA kernels behind cfd/motion.xml, cfd/energy.xml and the small
 presets next to them: the kernel bodies of aquagpusph_b200/csrc/elementwise.cu (k_motion_*,
-k_energy_*, k_forces, k_density_clamp, k_id_inverse, with the V<D> helpers they use) are lifted out of the .cu file as text, compiled for the host by g++ behind a two-screen shim
+k_energy_*, k_ab_*, k_forces, k_density_clamp, k_id_inverse, with the V<D> helpers they use) are lifted out of the .cu file as text, compiled for the host by g++ behind a two-screen shim
 (float2/float4, __global__ = nothing, the thread index as a loop variable) without FMA contraction,
 and compared with the oracle on the inputs of tests/test_gpu_presets.py.
 
@@ -78,6 +78,22 @@ void emu_energy(int dims, float* ek, float* ep, float* ec, const uint32_t* iset,
     FOR_ALL(k_energy_energy<3>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs),
             k_energy_energy<2>(ek, ep, ec, iset, imove, r, u, rho, m, refd, N, g, cs))
 }
+void emu_ab_step(int dims, void* const* du, void* const* du_in, float* const* dr, float* const* dr_in,
+                 const uint32_t* id_sorted, const int* imove, void* r, void* u, const void* dudt, float* rho,
+                 const float* drhodt, uint32_t N, float dt, unsigned iter, unsigned steps)
+{
+    AB4 lv, in;
+    AB4c lvc, inc;
+    for (int l = 0; l < 4; l++) {
+        lv.du[l] = du[l]; lv.dr[l] = dr[l]; lvc.du[l] = du[l]; lvc.dr[l] = dr[l];
+        in.du[l] = du_in[l]; in.dr[l] = dr_in[l]; inc.du[l] = du_in[l]; inc.dr[l] = dr_in[l];
+    }
+    const unsigned local_iter = iter < steps ? iter : steps;   // l_ab_corrector
+    FOR_ALL(k_ab_sort<3>(inc, lv, id_sorted, N), k_ab_sort<2>(inc, lv, id_sorted, N))
+    FOR_ALL(k_ab_corrector<3>(imove, r, u, dudt, rho, drhodt, lvc, N, dt, local_iter),
+            k_ab_corrector<2>(imove, r, u, dudt, rho, drhodt, lvc, N, dt, local_iter))
+    FOR_ALL(k_ab_postcorrector<3>(lvc, dudt, drhodt, in, N), k_ab_postcorrector<2>(lvc, dudt, drhodt, in, N))
+}
 void emu_small(int dims, float* ekin, void* ff, float4* fm, float* rho_in, const uint32_t* id, uint32_t* inv,
                const int* imove, const void* r, const void* u, const void* dudt, const float* m, uint32_t N,
                const float* g_, const float* fr_, float lo, float hi)
@@ -106,7 +122,7 @@ def _lift():
     # launchers: 'int l_xxx(aqc_ctx* c, ...)\n{ ... \n}\n' at column 0
     body = re.sub(r"^int l_\w+\(aqc_ctx\*[^\n]*\n\{\n.*?^\}\n", "", body, flags=re.S | re.M)
     assert "DISPATCH" not in body and "LAUNCH(" not in body
-    assert all(k in body for k in ("k_energy_energy", "k_motion_rate", "k_forces", "k_id_inverse"))
+    assert all(k in body for k in ("k_energy_energy", "k_motion_rate", "k_forces", "k_id_inverse", "k_ab_corrector"))
     return helpers + body
 
 
@@ -230,3 +246,27 @@ def test_small_preset_kernel_bodies_match_the_oracle(oracle, emu, dims):
     for k in o:
         assert e[k].tobytes() == o[k].tobytes(), k
     assert np.abs(o["forces_m"][:, 2]).max() > 0 and np.abs(o["energy_kin"]).max() > 0
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("steps", [5, 2])
+def test_adams_bashforth_kernel_bodies_match_the_oracle(oracle, emu, dims, steps):
+    """k_ab_sort / k_ab_corrector / k_ab_postcorrector over seven steps (every order), also with
+    TSCHEME_ADAMS_BASHFORTH_STEPS = 2 capping the order."""
+    from test_oracle_vs_reference import _ab_state, ab_oracle_step
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N = case["N"]
+    o = _ab_state(case, dims, 21)
+    e = {k: x.copy() for k, x in o.items()}
+    PP = lambda keys: (C.c_void_p * 4)(*[e[k].ctypes.data for k in keys])   # noqa: E731
+    lv = range(1, 5)
+    for it in range(7):
+        ab_oracle_step(oracle, o, N, dims, 1.25e-3, it, steps)
+        emu.emu_ab_step(dims, PP("dudt_as%d" % l for l in lv), PP("dudt_as%d_in" % l for l in lv),
+                        PP("drhodt_as%d" % l for l in lv), PP("drhodt_as%d_in" % l for l in lv),
+                        _p(e["id_sorted"]), _p(e["imove"]), _p(e["r"]), _p(e["u"]), _p(e["dudt"]), _p(e["rho"]),
+                        _p(e["drhodt"]), N, C.c_float(1.25e-3), it, steps)
+        for k in o:
+            assert e[k].tobytes() == o[k].tobytes(), (it, k)
+        o["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
+        e["dudt"][...] = o["dudt"]

@@ -34,6 +34,7 @@ CASES = {
     # BASELINE config 5: our own Main.xml (cases_xml/src/lattice_3d) over the reference's presets
     "lattice_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_3d", 3),
     "lattice_mpi_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_mpi_3d", 3),
+    "lattice_ab_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_ab_3d", 3),
 }
 
 
