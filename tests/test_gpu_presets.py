@@ -1,10 +1,15 @@
-"""GPU parity of the element-wise kernels of the presets next to the hot path (SURVEY 8(f) row 2:
-cfd/motion.xml and cfd/energy.xml, the moving-tank case) through the Kernel-tool C-ABI vs the
-oracle, which tests/test_oracle_vs_reference.py pins bit-for-bit to the reference's own scripts.
+"""GPU parity of what was built next to the hot path after round 1's GPU budget was spent, all against
+the oracle (which tests/test_oracle_vs_reference.py pins bit-for-bit to the reference's own scripts):
+  * element-wise preset kernels through the Kernel-tool C-ABI: cfd/Motions/*.cl, cfd/Energy/Energy.cl,
+    EnergyKin.cl, cfd/Forces/Forces.cl, basic/DensityClamp.cl, basic/IdInverse.cl,
+    basic/time_scheme/adam_bashforth.cl;
+  * whole pipelines through the C++ host: BASELINE config 4 (2-D tuned liquid damper, 104 tools) and
+    config 5 (lattice, 36 tools; its Adams-Bashforth variant; z slabs on two GPUs).
 
-Kept in a file of its own that sorts after the hot-path suites: these kernels were written after
-the round's GPU budget was spent, so the first run on a B200 is the driver's; the hot-path parity
-tests must not hide behind them under -x."""
+Kept in a file of its own that sorts after the hot-path suites: the first run of these on a B200 is
+the driver's, and the hot-path parity tests must not hide behind them under -x.  Their CPU halves
+(kernel bodies compiled for the host, pipelines in the oracle interpreter, host front-end) are
+tests/test_presets_host_emulation.py, tests/test_tld_oracle.py and tests/test_lattice_oracle.py."""
 import os
 import socket
 import sys
