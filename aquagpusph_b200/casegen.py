@@ -263,6 +263,28 @@ def prescribed_roll(theta0=0.0698, period=1.94):
     return transform
 
 
+SCRIPTS = os.path.join(TEMPLATES, "scripts")
+
+
+def python_roll(theta0=0.0698, period=1.94):
+    """Transform for the tuned-liquid-damper template that KEEPS the two `python` tools of
+    cfd/motion.xml and points them at this repository's scripts (cases_xml/scripts/PrescribedRoll.py,
+    MotionState.py) -- the same prescribed roll as `prescribed_roll`, through the python-tool route
+    (host: aqh_set_script_runner + aquagpusph_b200/pytool.py)."""
+    variables = ('        <Variable name="motion_theta0" type="float" value="%r" />\n'
+                 '        <Variable name="motion_period" type="float" value="%r" />\n' % (theta0, period))
+
+    def transform(txt, dims=2):
+        for name, script in (("cfd motion data", "PrescribedRoll.py"), ("cfd motion state", "MotionState.py")):
+            pat = r'(<Tool [^>]*name="%s" type="python"[^>]*path=")[^"]*(")' % name
+            if not re.search(pat, txt):
+                raise KeyError("python tool '%s' not found" % name)
+            txt = re.sub(pat, lambda m: m.group(1) + os.path.join(SCRIPTS, script) + m.group(2), txt, 1)
+        return txt.replace("    </Variables>", variables + "    </Variables>", 1)
+
+    return transform
+
+
 def spheric9_tld(n=10000, hfac=4.0, overrides=None, device=0, seed=None, theta0=0.0698, period=1.94, **kw):
     """BASELINE config 4 (2-D SPHERIC test 9, tuned liquid damper) through the 104-tool pipeline of
     examples/2D/spheric_testcase9_tld with the prescribed roll of `prescribed_roll`."""

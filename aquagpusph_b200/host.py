@@ -20,12 +20,56 @@ SYMBOLS = [
     "aqh_tool_used_times", "aqh_step", "aqh_run", "aqh_sync", "aqh_launch_count", "aqh_cuda_ctx",
     "aqh_fused_groups",
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
-    "aqh_array_upload", "aqh_array_devptr",
+    "aqh_array_upload", "aqh_array_devptr", "aqh_set_script_runner", "aqh_variable_type",
 ]
 
 
 class HostError(RuntimeError):
     pass
+
+
+_SCRIPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_char_p)
+_ACTIVE = []            # Simulations inside step() / run(), innermost last
+_SCRIPT_ERROR = [None]  # the exception a script raised, re-raised by step() / run()
+
+
+def _script_dispatch(user, tool, path):
+    try:
+        if not _ACTIVE:
+            raise HostError("python tool \"%s\" ran outside Simulation.step()/run()" % tool.decode())
+        _ACTIVE[-1]._run_script(path.decode())
+        return 0
+    except BaseException as e:   # noqa: BLE001 -- nothing may propagate into the C++ caller
+        _SCRIPT_ERROR[0] = e
+        return 1
+
+
+_SCRIPT_CB = _SCRIPT_FN(_script_dispatch)
+
+
+def type_info(type_name, dims):
+    """(numpy dtype, components) of a reference type string; 32-bit indices (State.cpp:499-502)."""
+    import re
+    t = type_name.replace("*", "").strip()
+    if t == "vec":
+        return np.float32, 4 if dims == 3 else 2
+    if t == "ivec":
+        return np.int32, 4 if dims == 3 else 2
+    if t in ("uivec", "svec"):
+        return np.uint32, 4 if dims == 3 else 2
+    if t == "matrix":
+        return np.float32, 16 if dims == 3 else 4
+    m = re.match(r"^(uivec|svec|ivec|vec)(\d+)$", t)
+    if m:
+        return {"uivec": np.uint32, "svec": np.uint32, "ivec": np.int32, "vec": np.float32}[m.group(1)], \
+            int(m.group(2))
+    if t in ("unsigned int", "uint", "size_t", "usize", "unsigned long", "ulong"):
+        return np.uint32, 1
+    if t in ("int", "long", "ssize_t"):
+        return np.int32, 1
+    if t == "float":
+        return np.float32, 1
+    raise HostError("unsupported variable type \"%s\"" % type_name)
 
 
 def lib():
@@ -72,6 +116,13 @@ def lib():
     L.aqh_array_upload.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     L.aqh_array_devptr.argtypes = [C.c_void_p, C.c_char_p]
     L.aqh_array_devptr.restype = C.c_void_p
+    L.aqh_variable_type.argtypes = [C.c_void_p, C.c_char_p]
+    L.aqh_variable_type.restype = C.c_char_p
+    # type="python" tools: the host calls back into this process (include/aquahost.h); registered
+    # once, before any aqh_load, and dispatched to the Simulation that is stepping
+    L.aqh_set_script_runner.argtypes = [_SCRIPT_FN, C.c_void_p]
+    L.aqh_set_script_runner.restype = None
+    L.aqh_set_script_runner(_SCRIPT_CB, None)
     _lib = L
     return L
 
@@ -104,9 +155,14 @@ class Simulation:
     """FileManager::load + CalcServer (parse_only=True: XML front-end only, no GPU)."""
 
     def __init__(self, xml_path, dims=3, device=-1, root=None, mpi_rank=0, mpi_size=1,
-                 parse_only=False):
+                 parse_only=False, script_dir=None, script_roots=()):
         self.h = C.c_void_p()
         self.dims = dims
+        # type="python" tools: relative script paths and the scripts' data files live next to the
+        # XML unless script_dir says otherwise; script_roots = folders that hold the presets' Scripts/
+        self.script_dir = script_dir or os.path.dirname(os.path.abspath(xml_path))
+        self.script_roots = tuple(script_roots) + ((root,) if root else ())
+        self._scripts = None
         r = root.encode() if root else None
         if parse_only:
             _chk(lib().aqh_parse(xml_path.encode(), dims, r, C.byref(self.h)))
@@ -144,11 +200,64 @@ class Simulation:
     def write_resolved(self, path):
         _chk(lib().aqh_write_resolved(self.h, path.encode()))
 
+    def _stepping(self, fn, *args):
+        _ACTIVE.append(self)
+        _SCRIPT_ERROR[0] = None
+        try:
+            rc = fn(self.h, *args)
+        finally:
+            _ACTIVE.pop()
+        if rc and _SCRIPT_ERROR[0] is not None:
+            e, _SCRIPT_ERROR[0] = _SCRIPT_ERROR[0], None
+            raise HostError("%s (%s: %s)" % (lib().aqh_last_error().decode(), type(e).__name__, e)) from e
+        _chk(rc)
+
     def step(self, n=1):
-        _chk(lib().aqh_step(self.h, int(n)))
+        self._stepping(lib().aqh_step, int(n))
 
     def run(self):
-        _chk(lib().aqh_run(self.h))
+        self._stepping(lib().aqh_run)
+
+    # type="python" tools (aquagpusph_b200/pytool.py): get / set of the `aquagpusph` module
+    def _run_script(self, path):
+        if self._scripts is None:
+            from . import pytool
+            self._scripts = pytool.ScriptRunner(self, self.script_dir, self.script_roots)
+        self._scripts.run(path)
+
+    def variable_type(self, name):
+        t = lib().aqh_variable_type(self.h, name.encode())
+        return t.decode() if t else None
+
+    def py_get(self, name, offset=0, n=0):
+        t = self.variable_type(name)
+        if t is None:
+            raise ValueError('Variable "%s" has not been declared' % name)
+        dt, nc = type_info(t, self.dims)
+        if "*" in t:
+            a = self.download(name, dt)
+            return a[offset:offset + n] if n else a[offset:]
+        v = self.scalar(name, dt, nc)
+        if nc > 1:
+            return v
+        return float(v) if dt == np.float32 else int(v)
+
+    def py_set(self, name, value, offset=0, n=0):
+        from . import pytool
+        t = self.variable_type(name)
+        if t is None:
+            raise ValueError('Variable "%s" has not been declared' % name)
+        dt, nc = type_info(t, self.dims)
+        if "*" in t:
+            a = np.ascontiguousarray(value, dt)
+            full = self.download(name, dt) if (offset or a.shape[0] != self.array_info(name)[0]) else a
+            if full is not a:
+                full[offset:offset + a.shape[0]] = a
+            self.upload(name, full)
+            return
+        v = np.atleast_1d(pytool.narrow(value, dt, nc))
+        # exact: repr of the float32 value read as a double narrows back to the same float32
+        self.set_scalar(name, ", ".join(repr(float(x)) if dt == np.float32 else str(int(x)) for x in v))
 
     def sync(self):
         _chk(lib().aqh_sync(self.h))

@@ -582,6 +582,36 @@ void MPISync::_execute()
                        _procs.empty() ? nullptr : _procs.data(), nullptr));
 }
 
+// --------------------------------------------------------------- PythonTool --
+namespace {
+ScriptRunnerFn g_script_runner = nullptr;
+void* g_script_user = nullptr;
+}
+void setScriptRunner(ScriptRunnerFn fn, void* user)
+{
+    g_script_runner = fn;
+    g_script_user = user;
+}
+
+void PythonTool::setup()
+{
+    if (_path.empty())
+        throw std::runtime_error("The tool \"" + name() + "\" names no script");
+    if (!g_script_runner)
+        throw std::runtime_error("The tool \"" + name() + "\" (type python, script \"" + _path +
+                                 "\") needs a script runner: this host does not embed an interpreter, "
+                                 "the driving process registers one with aqh_set_script_runner");
+}
+
+void PythonTool::_execute()
+{
+    // the script reads variables through aqh_scalar_get / aqh_array_download: everything enqueued so
+    // far must have landed (the reference's getters wait for the variable's event the same way)
+    check(aqc_sync(_C->ctx()));
+    if (g_script_runner(g_script_user, name().c_str(), _path.c_str()))
+        throw std::runtime_error("Python execution error in the tool \"" + name() + "\"");
+}
+
 // ------------------------------------------------------------- MPIAllReduce --
 void MPIAllReduce::setup()
 {
@@ -938,6 +968,8 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
         return new MPISync(this, name, t.get("mask"), t.get("fields"), t.get("processes"), once);
     if (type == "mpi-allreduce")
         return new MPIAllReduce(this, name, t.get("in"), t.get("operation"), once);
+    if (type == "python")
+        return new PythonTool(this, name, t.get("path"), once);
     if (type == "dummy")
         return new Tool(this, name, once);
     if (startswith(type, "report_"))

@@ -298,6 +298,23 @@ class MPIAllReduce : public Tool {
     size_t _count = 1;
 };
 
+/// type="python" (Python.cpp:295-325).  The reference embeds CPython; this host hands the script to
+/// the process that drives it through the runner registered with aqh_set_script_runner
+/// (include/aquahost.h), which imports it and calls its main() with the `aquagpusph` module bound
+/// to this simulation (aquagpusph_b200/pytool.py).  Without a runner the tool refuses to set up.
+typedef int (*ScriptRunnerFn)(void* user, const char* tool_name, const char* script_path);
+void setScriptRunner(ScriptRunnerFn fn, void* user);
+class PythonTool : public Tool {
+  public:
+    PythonTool(CalcServer* C, const std::string& name, const std::string& path, bool once)
+      : Tool(C, name, once), _path(path) {}
+    void setup() override;
+  protected:
+    void _execute() override;
+  private:
+    std::string _path;
+};
+
 /// report_screen / report_file / report_dump / report_performance, and <Reports>
 class Report : public Tool {
   public:

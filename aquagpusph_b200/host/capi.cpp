@@ -206,6 +206,23 @@ extern "C" int aqh_eval(int dims, const char* decls, const char* type, const cha
     AQH_CATCH
 }
 
+extern "C" void aqh_set_script_runner(aqh_script_fn fn, void* user)
+{
+    Aqua::CalcServer::setScriptRunner(fn, user);
+}
+
+extern "C" const char* aqh_variable_type(aqh_sim* sim, const char* name)
+{
+    if (!sim || !sim->C || !name)
+        return nullptr;
+    auto* v = sim->C->variables()->get(name);
+    if (!v)
+        return nullptr;
+    static thread_local std::string type;
+    type = v->type();
+    return type.c_str();
+}
+
 extern "C" int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes)
 {
     AQH_TRY

@@ -63,7 +63,20 @@ void* aqh_cuda_ctx(aqh_sim* sim);         /* the aqc_ctx* underneath */
 int aqh_eval(int dims, const char* decls, const char* type, const char* expr, void* out,
              size_t bytes);
 
+/* type="python" tools (aquagpusph/CalcServer/Python.cpp:295-325).  The reference embeds CPython in
+ * its host; this host calls `fn(user, tool name, script path)` instead, once per execution of the
+ * tool and after a device sync, and the driving process runs the script's main() with get / set
+ * bound to aqh_scalar_get / aqh_scalar_set / aqh_array_download / aqh_array_upload
+ * (aquagpusph_b200/pytool.py).  Non-zero = "Python execution error" (or main() returned False):
+ * the step fails like Python.cpp:304-318.  Process-wide; register before aqh_load -- a problem
+ * with a python tool and no runner fails at set-up. */
+typedef int (*aqh_script_fn)(void* user, const char* tool_name, const char* script_path);
+void aqh_set_script_runner(aqh_script_fn fn, void* user);
+
 /* variables */
+/* the reference type string of a variable ("float", "vec", "unsigned int*", ...), NULL when it is
+ * not declared; valid until the next call on this thread */
+const char* aqh_variable_type(aqh_sim* sim, const char* name);
 int aqh_scalar_get(aqh_sim* sim, const char* name, void* out, size_t bytes);
 int aqh_scalar_set(aqh_sim* sim, const char* name, const char* expression);
 int aqh_array_info(aqh_sim* sim, const char* name, size_t* length, size_t* elem_bytes);

@@ -411,6 +411,8 @@ class Interpreter:
             self.mpi_sync(t)
         elif typ == "mpi-allreduce":
             self.mpi_allreduce(t)
+        elif typ == "python":
+            self.python(t)
         else:
             raise NotImplementedError("oracle interpreter: tool type %s" % typ)
         return i + 1
@@ -508,6 +510,40 @@ class Interpreter:
                 V[f][off:off + n] = a
             mask[off:off + n] = p
             off += n
+
+    # -- type="python" (Python.cpp:295-325): the script's main() against this interpreter's variables
+    script_dir = None       # where relative script paths and the scripts' data files live
+    script_roots = ()       # where the presets' "Scripts/..." paths are looked for
+
+    def python(self, t):
+        if self.script_dir is None:
+            raise NotImplementedError("oracle interpreter: tool type python needs script_dir")
+        if getattr(self, "_scripts", None) is None:
+            from aquagpusph_b200 import pytool
+            self._scripts = pytool.ScriptRunner(self, self.script_dir, self.script_roots)
+        self._scripts.run(t["path"])
+
+    def py_get(self, name, offset=0, n=0):
+        if name not in self.V:
+            raise ValueError('Variable "%s" has not been declared' % name)
+        v = self.V[name]
+        if "*" in self.types[name]:
+            return np.array(v[offset:offset + n] if n else v[offset:])
+        if np.ndim(v) == 0:
+            return float(v) if isinstance(v, np.floating) else int(v)
+        return np.array(v)
+
+    def py_set(self, name, value, offset=0, n=0):
+        if name not in self.V:
+            raise ValueError('Variable "%s" has not been declared' % name)
+        if "*" in self.types[name]:
+            a = np.asarray(value)
+            self.V[name][offset:offset + a.shape[0]] = a
+            return
+        from aquagpusph_b200 import pytool
+        dt, nc = self._base(self.types[name])
+        self.V[name] = pytool.narrow(value, dt, nc)
+        self.publish(name)
 
     def mpi_allreduce(self, t):
         if self.size <= 1:

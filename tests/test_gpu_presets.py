@@ -344,3 +344,42 @@ def test_adams_bashforth_kernels(oracle, dims):
         o["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
         d["dudt"] = ctx.array(o["dudt"])
     ctx.close()
+
+
+def test_tld_python_tools(oracle, tmp_path):
+    """type="python" tools through the C++ host: the tuned-liquid-damper pipeline with its two python
+    tools kept (cases_xml/scripts/PrescribedRoll.py, MotionState.py, run by the script runner the
+    binding registers with aqh_set_script_runner) against the same pipeline with casegen.prescribed_roll's
+    set_scalar tools, both on the GPU, three steps: the motion scalars are bit-identical (same
+    arithmetic), so are the tank's elements; fluid fields agree to 1e-6.  A script whose main() returns
+    False stops the run with an error (Python.cpp:313-316)."""
+    host.set_log_level(3)
+    case = product_cases.spheric9_tld_2d(3000, 4.0, seed=5)
+    nset = (case["n_set0"], case["n_set1"])
+    ov = {"Residual_midpoint_max": "0.0"}
+    A = casegen.load("spheric9_tld_2d", case, nset, ov, transform=casegen.python_roll(0.05, 0.2))
+    B = casegen.load("spheric9_tld_2d", case, nset, ov, transform=casegen.prescribed_roll(0.05, 0.2))
+    assert sum(t == "python" for _, t in A.tools()) == 2
+    for step in range(3):
+        A.step(1)
+        B.step(1)
+        for k in ("motion_a", "motion_dadt", "motion_ddaddt", "motion_a_in"):
+            assert np.array_equal(A.scalar(k, np.float32, 4), B.scalar(k, np.float32, 4)), (step, k)
+        wall = B.download("imove", np.int32, unsorted=True) == -3
+        for k in ("r", "u", "normal"):
+            a, b = A.download(k, unsorted=True), B.download(k, unsorted=True)
+            assert np.array_equal(a[wall], b[wall]), (step, k)
+            assert np.abs(a - b).max() <= 1e-6 * max(np.abs(b).max(), 1.0), (step, k)
+    assert float(A.scalar("motion_a", np.float32, 4)[2]) != 0
+    A.close()
+    B.close()
+    stop = tmp_path / "Stop.py"
+    stop.write_text("def main():\n    return False\n")
+
+    def stopping(txt):
+        txt = casegen.python_roll()(txt)
+        return txt.replace(os.path.join(casegen.SCRIPTS, "PrescribedRoll.py"), str(stop))
+    S = casegen.load("spheric9_tld_2d", case, nset, ov, transform=stopping)
+    with pytest.raises(host.HostError, match="simulation stop"):
+        S.step(1)
+    S.close()
