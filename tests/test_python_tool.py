@@ -119,3 +119,19 @@ def test_type_info():
     assert host.type_info("matrix*", 2) == (np.float32, 4) and host.type_info("svec4", 3) == (np.uint32, 4)
     with pytest.raises(host.HostError):
         host.type_info("double", 3)
+
+
+def test_python_command_line(tmp_path, capsys):
+    """python -m aquagpusph_b200: the CLI's flags through the binding (so python tools have a runner).
+    --resolve needs no device; a run without one fails loudly, never on a CPU path."""
+    from aquagpusph_b200 import __main__ as cli
+    c = cases.spheric9_tld_2d(1500)
+    xml = tmp_path / "Main.xml"
+    xml.write_text(casegen.python_roll()(casegen.instantiate("spheric9_tld_2d", c, (c["n_set0"], c["n_set1"]))))
+    out = tmp_path / "flat.xml"
+    assert cli.main(["-i", str(xml), "-d", "2", "--resolve", str(out), "-l", "3"]) == 0
+    assert out.read_text().count('type="python"') == 2
+    import torch
+    if not torch.cuda.is_available():
+        assert cli.main(["-i", str(xml), "-d", "2", "--steps", "1", "-l", "3"]) == 1
+        assert "no CPU fallback" in capsys.readouterr().err
