@@ -162,10 +162,13 @@ def test_adams_bashforth_variant(oracle, tmp_path):
 def test_z_slabs_on_four_ranks_reproduce_the_serial_run(oracle):
     """Interior ranks have a neighbour on both faces (the low_ and high_ instances of
     cfd/MPI/planes.xml both active), as on the 8-GPU runs of config 5: four ranks of 4, 6, 6 and 4 layers
-    (planes every (n + 4) / 4 = 6 from z = -2; halo width 2h = 4 layers) against the one-device run."""
+    (planes every (n + 4) / 4 = 6 from z = -2) against the one-device run.  hfac = 1, i.e. a halo of
+    2h = 2 layers: the reference's masks hold ONE destination per particle (cfd/MPI/planes.cl:41-99), so
+    a slab must be thicker than the two halos it feeds -- with hfac = 2 the middle layers of a 6-layer
+    slab would be wanted by both neighbours and reach only one of them."""
     n = 20
-    serial, dt = _serial(n, 2.0, 2)
-    ranks = _two_ranks(n, 2.0, 2, size=4)
+    serial, dt = _serial(n, 1.0, 2)
+    ranks = _two_ranks(n, 1.0, 2, size=4)
     assert np.array_equal(np.sort(np.concatenate([ranks[r]["own"] for r in range(4)])), np.arange(n ** 3))
     for r in range(4):
         own = ranks[r]["own"]
