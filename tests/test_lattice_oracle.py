@@ -4,6 +4,7 @@ tool list SURVEY 8(d) names, parses identically in the C++ host and the oracle i
 only registered kernels, and steps in the oracle.  GPU side: tests/test_gpu_presets.py."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -179,3 +180,45 @@ def test_z_slabs_on_four_ranks_reproduce_the_serial_run(oracle):
             a = serial[k][own].astype(np.float64)
             b = ranks[r][k][:m].astype(np.float64)
             assert np.abs(a - b).max() <= tol * np.abs(a).max(), (r, k, np.abs(a - b).max() / np.abs(a).max())
+
+
+def _gloo_rank(rank, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=2)
+    from aquagpusph_b200 import casegen as cg, cases as cs
+    from oracle import interp as ip, oracle as O
+    O.build()
+    c = cs.lattice_slab(12, 2.0, rank, 2)
+    txt = cg.multi_device_fixes(cg.instantiate("lattice_mpi_3d", c, (c["N"],)))
+    I = ip.Interpreter(txt, 3, rank=rank, size=2, transport=ip.TorchTransport())
+    for k in cg.STATE_FIELDS:
+        I.V[k][...] = c[k]
+    for _ in range(2):
+        I.step()
+    q.put((rank, {k: np.asarray(I.unsorted(k)) for k in F_SLAB}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_z_slabs_two_processes_gloo(oracle):
+    """world_size = 2 over torch.distributed / gloo (one interpreter rank per process, the arrangement
+    of the GPU runs): bit-identical to the two threaded ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_rank, args=(r, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    want = _two_ranks(12, 2.0, 2)
+    for r in range(2):
+        for k in F_SLAB:
+            assert np.array_equal(got[r][k], want[r][k]), (r, k)
