@@ -1145,6 +1145,69 @@ struct PBIInteractions : PBase {
     }
 };
 
+// BI/NoSlip.cl:52-130 (preset cfd/BINoSlip.xml): fluid i against the boundary elements of the set
+// noslip_iset; adds to the lap_u the fluid-fluid sweep left (__LAP_MONAGHAN__: the Cleary term along
+// n_j plus the tangential velocity difference over the wall distance, never closer than dr)
+template <int D>
+struct PBINoSlip : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr uint32_t JCLS = 16u;
+    static constexpr int DIMS = D, NJ4 = 3;
+    const uint32_t* iset;
+    const void *r, *normal, *u;
+    const float *rho, *m;
+    void* lap_u;
+    uint32_t noslip_iset;
+    float cW, H2, dr;
+    struct IState { float x, y, z, ux, uy, uz, irho, lx, ly, lz; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.irho = 1.f / __ldg(rho + i);
+        s.lx = s.ly = s.lz = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), n = ldvec<D>(normal, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == -3 && __ldg(iset + j) == noslip_iset;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j));
+        o[1] = make_float4(n.x, n.y, n.z, 0.f);
+        o[2] = make_float4(b.x, b.y, b.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], Nn = row[stride], U = row[2 * stride];
+        const float rx = A.x - s.x, ry = A.y - s.y, rz = D == 3 ? A.z - s.z : 0.f;
+        const float q = q_of(dist2<D>(rx, ry, rz), invH);
+        const float t = 2.f - q, t2 = t * t;
+        const float w = (1.f + 2.f * q) * (t2 * t2) * A.w * s.irho; // kernelW*CONW*area_j / rho_i
+        const float dux = U.x - s.ux, duy = U.y - s.uy, duz = D == 3 ? U.z - s.uz : 0.f;
+        float dudr = dux * rx + duy * ry, rn = rx * Nn.x + ry * Nn.y, dun = dux * Nn.x + duy * Nn.y;
+        if constexpr (D == 3) {
+            dudr += duz * rz;
+            rn += rz * Nn.z;
+            dun += duz * Nn.z;
+        }
+        const float c1 = (D == 3 ? 10.f : 8.f) * w * dudr / ((q * q + 0.01f) * H2);
+        const float c2 = 2.f * w / fmaxf(fabsf(rn), dr);
+        s.lx += c1 * Nn.x + c2 * (dux - dun * Nn.x);
+        s.ly += c1 * Nn.y + c2 * (duy - dun * Nn.y);
+        if constexpr (D == 3)
+            s.lz += c1 * Nn.z + c2 * (duz - dun * Nn.z);
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float4 l0 = ldvec_rw<D>(lap_u, i);
+        stvec_xyz<D>(lap_u, i, l0.x + s.lx, l0.y + s.ly, l0.z + s.lz);
+    }
+};
+
 // cfd/Boundary/ElasticBounce.cl:77-148 -- order dependent (u_i, dudt_i change inside the loop)
 template <int D>
 struct PElasticBounce : PBase {
@@ -1757,6 +1820,21 @@ template <int D> int run_bi_inter(aqc_ctx* ctx, void* const* a)
     return launch_sweep(ctx, p, ll);
 }
 int l_bi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_inter, c, a); }
+template <int D> int run_bi_noslip(aqc_ctx* ctx, void* const* a)
+{
+    // (iset, imove, r, normal, u, rho, m, lap_u, N, noslip_iset, dr, icell, ihoc, n_cells)
+    PBINoSlip<D> p;
+    set_base(p, ctx, a[1]);
+    p.iset = (const uint32_t*)a[0];
+    p.r = a[2]; p.normal = a[3]; p.u = a[4]; p.rho = (const float*)a[5]; p.m = (const float*)a[6];
+    p.lap_u = a[7];
+    p.noslip_iset = aqc_scalar<uint32_t>(a, 9);
+    p.dr = aqc_scalar<float>(a, 10);
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    p.H2 = ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, make_ll(a, 11, aqc_scalar<uint32_t>(a, 8)));
+}
+int l_bi_noslip(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_noslip, c, a); }
 template <int D> int run_elastic_bounce(aqc_ctx* ctx, void* const* a)
 {
     PElasticBounce<D> p;
@@ -1951,6 +2029,10 @@ aqc_registrar r_bi_inter("cfd/Boundary/BI/Interactions.cl", "entry", 0,
       IN("refd", "float*"), OUT("grad_p", "vec*"), OUT("div_u", "float*"), RO("icell", "uint*"),
       RO("ihoc", "uint*"), SC("N", "usize"), SC("n_cells", "uivec4"), SC("g", "vec") },
     l_bi_inter);
+aqc_registrar r_bi_noslip("cfd/Boundary/BI/NoSlip.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), IN("u", "vec*"),
+      IN("rho", "float*"), IN("m", "float*"), OUT("lap_u", "vec*"), SC("N", "usize"),
+      SC("noslip_iset", "uint"), SC("dr", "float"), LL_ARGS }, l_bi_noslip);
 aqc_registrar r_elastic("cfd/Boundary/ElasticBounce.cl", "entry", 0,
     { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), OUT("u", "vec*"),
       OUT("dudt", "vec*"), SC("N", "usize"), SC("dr", "float"), SC("dt", "float"), LL_ARGS },

@@ -257,6 +257,11 @@ void aqo_ab_postcorrector(const float* const* dudt_as, const float* const* drhod
                           const float* drhodt, float* const* dudt_as_in, float* const* drhodt_as_in,
                           aqo_usize N, int dims);
 
+/* cfd/Boundary/BI/NoSlip.cl:52-130 (preset cfd/BINoSlip.xml), __LAP_MONAGHAN__ */
+void aqo_bi_noslip(const aqo_defs* D, const aqo_ll* L, const unsigned* iset, const int* imove, const float* r,
+                   const float* normal, const float* u, const float* rho, const float* m, float* lap_u,
+                   unsigned noslip_iset, float dr);
+
 #ifdef __cplusplus
 }
 #endif

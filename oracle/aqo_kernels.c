@@ -1401,3 +1401,44 @@ void aqo_ab_postcorrector(const float* const* dudt_as, const float* const* drhod
         drhodt_as_in[3][i] = drhodt_as[2][i];
     }
 }
+
+/* cfd/Boundary/BI/NoSlip.cl:52-130: fluid i against the elements of the set noslip_iset, added to lap_u */
+void aqo_bi_noslip(const aqo_defs* D, const aqo_ll* L, const unsigned* iset, const int* imove, const float* r,
+                   const float* normal, const float* u, const float* rho, const float* m, float* lap_u,
+                   unsigned noslip_iset, float dr)
+{
+    const int dims = D->dims, vs = VS(dims);
+    const float cleary = dims == 3 ? 10.f : 8.f; /* :41-47 */
+    AQO_FOR_I(L->N) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* u_i = u + (size_t)i * vs;
+        const float rho_i = rho[i];
+        float* lap = lap_u + (size_t)i * vs;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((imove[j] != -3) || (iset[j] != noslip_iset))
+                continue;
+            float r_ij[3] = { 0.f, 0.f, 0.f }, q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float* n_j = normal + (size_t)j * vs;
+            const float area_j = m[j];
+            const float w_ij = kernelW(q, dims) * D->CONW * area_j;
+            float du[3] = { 0.f, 0.f, 0.f };
+            for (int d = 0; d < dims; d++)
+                du[d] = u[(size_t)j * vs + d] - u_i[d];
+            const float r2 = (q * q + 0.01f) * D->H * D->H;
+            const float c1 = cleary * w_ij * dotv(du, r_ij, dims) / (r2 * rho_i);
+            for (int d = 0; d < dims; d++)
+                lap[d] += c1 * n_j[d];
+            const float dr_n = fmaxf(fabsf(dotv(r_ij, n_j, dims)), dr);
+            const float dun = dotv(du, n_j, dims);
+            const float c2 = 2.f * w_ij / (rho_i * dr_n);
+            for (int d = 0; d < dims; d++)
+                lap[d] += c2 * (du[d] - dun * n_j[d]);
+        }
+        NEIGHS_END
+    }
+}

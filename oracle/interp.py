@@ -694,6 +694,9 @@ class Interpreter:
             O.call("ab_postcorrector", O.ptrs(V["dudt_as%d" % l] for l in lv),
                    O.ptrs(V["drhodt_as%d" % l] for l in lv), V["dudt"], V["drhodt"],
                    O.ptrs(V["dudt_as%d_in" % l] for l in lv), O.ptrs(V["drhodt_as%d_in" % l] for l in lv), N, d)
+        elif key == ("cfd/Boundary/BI/NoSlip.cl", "entry"):
+            c("bi_noslip", D, self.ll(), V["iset"], V["imove"], V["r"], V["normal"], V["u"], V["rho"], V["m"],
+              V["lap_u"], int(V["noslip_iset"]), f32("dr"))
         elif rel.endswith("h_sensor.cl"):
             # examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60
             r, dr = V["r"], np.float32(V["dr"])

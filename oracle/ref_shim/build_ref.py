@@ -39,7 +39,7 @@ SCRIPTS = [
     "cfd/Motions/Transform.cl", "cfd/Motions/UnTransform.cl", "cfd/Motions/Velocity.cl",
     "cfd/Motions/Acceleration.cl", "cfd/Energy/Energy.cl",
     "cfd/Energy/EnergyKin.cl", "cfd/Forces/Forces.cl", "basic/DensityClamp.cl", "basic/IdInverse.cl",
-    "basic/time_scheme/adam_bashforth.cl",
+    "basic/time_scheme/adam_bashforth.cl", "cfd/Boundary/BI/NoSlip.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

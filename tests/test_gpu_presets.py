@@ -383,3 +383,35 @@ def test_tld_python_tools(oracle, tmp_path):
     with pytest.raises(host.HostError, match="simulation stop"):
         S.step(1)
     S.close()
+
+
+@pytest.mark.parametrize("engine", [3, 2])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 60, 4.0)])
+def test_bi_noslip_sweep(oracle, dims, n, hfac, engine):
+    """cfd/Boundary/BI/NoSlip.cl::entry (cfd/BINoSlip.xml: the lid-driven cavity, SPHERIC test 3) through
+    the Kernel-tool C-ABI on both sweep engines vs the oracle, which is bit-identical to the reference's
+    script.  Tolerance of the sweep tests: |gpu - oracle| <= 2e-6 max|oracle| + 2e-5 |oracle|."""
+    import pipeline
+    from test_oracle_vs_reference import noslip_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    lap, u, iset = noslip_inputs(case, s)
+    want = lap.copy()
+    oracle.call("bi_noslip", oracle.make_defs(dims, s["h"]), pipeline._ll(s), iset, s["imove"], s["r"],
+                s["normal"], u, s["rho"], s["m"], want, 1, float(case["dr"]))
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    c = pipeline.CudaState(ctx, s)
+    c.set("lap_u", lap)
+    c.set("u", u)
+    c.set("iset", iset)
+    try:
+        assert _lib.lib().aqc_sweep_engine_select(engine) == engine
+        c.run("cfd/Boundary/BI/NoSlip.cl", noslip_iset=1, dr=float(case["dr"]))
+        got = c.get("lap_u")
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
+    ctx.close()
+    a, b = want.astype(np.float64), got.astype(np.float64)
+    assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
+    fl = s["imove"] == 1
+    assert np.abs(want - lap)[fl].max() > 0 and np.array_equal(got[~fl], lap[~fl])

@@ -291,3 +291,37 @@ def test_adams_bashforth_kernels_match_reference_scripts(oracle, dims):
         a["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
         b["dudt"][...] = a["dudt"]
     assert not np.array_equal(a["r"], case["r"])
+
+
+def noslip_inputs(case, s, seed=4):
+    """lap_u as a fluid-fluid sweep would leave it (random here), velocities on fluid and walls."""
+    rng = np.random.default_rng(seed)
+    N, dims = s["N"], s["dims"]
+    V = 4 if dims == 3 else 2
+    lap = np.zeros((N, V), np.float32)
+    lap[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+    u = np.zeros((N, V), np.float32)
+    u[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+    iset = (np.arange(N) % 2).astype(np.uint32)     # only half of the elements belong to the no-slip set
+    return lap, u, iset
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0)])
+def test_bi_noslip_matches_reference_script(oracle, dims, n, hfac):
+    """cfd/Boundary/BI/NoSlip.cl::entry (preset cfd/BINoSlip.xml, the lid-driven cavity of
+    examples/2D/spheric_testcase3_liddriven): the C restatement is bit-identical to the script."""
+    import pipeline
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    lap, u, iset = noslip_inputs(case, s)
+    c = pipeline.RefState(ref.Ref(dims, case["h"]), s)
+    c.set("lap_u", lap)
+    c.set("u", u)
+    c.set("iset", iset)
+    c.run("cfd/Boundary/BI/NoSlip.cl", noslip_iset=1, dr=float(case["dr"]))
+    got = lap.copy()
+    oracle.call("bi_noslip", oracle.make_defs(dims, s["h"]), pipeline._ll(s), iset, s["imove"], s["r"],
+                s["normal"], u, s["rho"], s["m"], got, 1, float(case["dr"]))
+    assert c.get("lap_u").tobytes() == got.tobytes()
+    fl = s["imove"] == 1
+    assert np.abs(got - lap)[fl].max() > 0 and np.array_equal(got[~fl], lap[~fl])

@@ -1,0 +1,120 @@
+"""CPU check of the LOGIC of a sweep policy written without a GPU at hand (PBINoSlip, sweeps.cu): the
+policy struct and the helpers it uses (ldvec / stvec_xyz / dist2 / q_of / Wend / PBase) are lifted out
+of sweeps.cu and sweep.cuh as text, compiled for the host by g++ behind a shim (__ldg = a plain load,
+the two MUFU approximations = sqrtf and 1/x), and driven by a brute-force loop with the engines'
+contract (sweep.cuh: load_i; for every j: stage_j, skip dead rows, test, body; store_i) instead of the
+cell walk.  The engines themselves are verified on the GPU through the other policies; what this pins
+is the policy: which pairs count, the formula, what is stored.  Compared with the oracle (bit-identical
+to the reference's script) at the sweep tests' tolerance; tests/test_gpu_presets.py::test_bi_noslip_sweep
+is the run on a B200."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import pipeline
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "aquagpusph_b200", "csrc")
+
+SHIM = r"""
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+template <class T> static inline T __ldg(const T* p) { return *p; }
+"""
+
+DRIVER = r"""
+template <int D> static void run(const uint32_t* iset, const int* imove, const void* r, const void* normal,
+                                 const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
+                                 uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
+{
+    PBINoSlip<D> p;
+    p.imove = imove; p.invH = 1.f / H; p.cut2 = (SUPPORT * H) * (SUPPORT * H);      // set_base
+    p.iset = iset; p.r = r; p.normal = normal; p.u = u; p.rho = rho; p.m = m; p.lap_u = lap_u;
+    p.noslip_iset = noslip_iset; p.dr = dr; p.cW = Wend<D>::W * CONW; p.H2 = H * H;   // run_bi_noslip
+    for (uint32_t i = 0; i < N; i++) {
+        if (!p.i_active(imove[i]))
+            continue;
+        typename PBINoSlip<D>::IState s;
+        p.load_i(s, i);
+        for (uint32_t j = 0; j < N; j++) {
+            float4 row[PBINoSlip<D>::NJ4];
+            p.stage_j(j, row);
+            if (!PBase::j_live(row[0]) || !p.test(s, row[0]))
+                continue;
+            p.body(s, row, 1);
+        }
+        p.store_i(s, i);
+    }
+}
+extern "C" void emu_noslip(int dims, const uint32_t* iset, const int* imove, const void* r, const void* normal,
+                           const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
+                           uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
+{
+    if (dims == 3)
+        run<3>(iset, imove, r, normal, u, rho, m, lap_u, N, noslip_iset, dr, H, CONW, SUPPORT);
+    else
+        run<2>(iset, imove, r, normal, u, rho, m, lap_u, N, noslip_iset, dr, H, CONW, SUPPORT);
+}
+"""
+
+
+def _between(src, a, b):
+    i = src.index(a)
+    return src[i:src.index(b, i)]
+
+
+def _lift():
+    cuh = open(os.path.join(CSRC, "sweep.cuh")).read()
+    cu = open(os.path.join(CSRC, "sweeps.cu")).read()
+    far = re.search(r"constexpr float AQC_FAR = [^;]*;", cuh).group(0)
+    dist2 = _between(cuh, "template <int DIMS>\n__device__ __forceinline__ float dist2", "// Policy concept")
+    helpers = _between(cu, "constexpr float iM_PI", "// ------------------------------------------------------------------------\n// cfd/Interactions.cl")
+    # the two MUFU approximations (1 ulp) become their exact counterparts on the host
+    helpers = re.sub(r'asm\("sqrt\.approx\.ftz\.f32[^\n]*\n', "r = sqrtf(x);\n", helpers)
+    helpers = re.sub(r'asm\("rcp\.approx\.ftz\.f32[^\n]*\n', "r = 1.f / x;\n", helpers)
+    assert "asm(" not in helpers and "struct PBase" in helpers
+    policy = _between(cu, "template <int D>\nstruct PBINoSlip : PBase {", "// cfd/Boundary/ElasticBounce.cl:77-148")
+    return far + "\n" + dist2 + helpers + policy
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emu_sweep")
+    cpp, so = str(d / "emu.cpp"), str(d / "libemu.so")
+    open(cpp, "w").write(SHIM + _lift() + DRIVER)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-fno-fast-math", "-o", so, cpp])
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 40, 4.0)])
+def test_noslip_policy_matches_the_oracle(oracle, emu, dims, n, hfac):
+    from test_oracle_vs_reference import noslip_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    lap, u, iset = noslip_inputs(case, s)
+    D = oracle.make_defs(dims, s["h"])
+    want = lap.copy()
+    oracle.call("bi_noslip", D, pipeline._ll(s), iset, s["imove"], s["r"], s["normal"], u, s["rho"], s["m"], want,
+                1, float(case["dr"]))
+    got = lap.copy()
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)   # noqa: E731
+    arr = {k: np.ascontiguousarray(s[k]) for k in ("imove", "r", "normal", "rho", "m")}
+    emu.emu_noslip(dims, P(iset), P(arr["imove"]), P(arr["r"]), P(arr["normal"]), P(u), P(arr["rho"]), P(arr["m"]),
+                   P(got), s["N"], 1, C.c_float(case["dr"]), C.c_float(D.H), C.c_float(D.CONW), C.c_float(D.SUPPORT))
+    a, b = want.astype(np.float64), got.astype(np.float64)
+    assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
+    fl = s["imove"] == 1
+    assert np.abs(want - lap)[fl].max() > 1e-3 and np.array_equal(got[~fl], lap[~fl])
