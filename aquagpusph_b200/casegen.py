@@ -37,6 +37,8 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
         "N": str(int(set_sizes[0])),
         "N_SENSORS": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
         "NBC": str(int(set_sizes[1]) if len(set_sizes) > 1 else 0),
+        "NFLUID": str(int(set_sizes[0])), "P0": repr(float(case.get("p0", 0.0))),
+        "TEND": repr(float(case.get("t_end", 1.0))),
         "CLTYPE": "GPU", "CLDEVICE": "0", "CLPLATFORM": "0",
     }
     for k, v in rep.items():
@@ -320,6 +322,15 @@ def lattice_slab(n_side, rank, size, hfac=2.0, overrides=None, device=0, unique_
         c = cases.lattice_slab(n_side, hfac, rank, size)
     sim = load("lattice_mpi_3d", c, (c["N"],), overrides, device, mpi_rank=rank, mpi_size=size,
                unique_id=unique_id, transform=multi_device_fixes, **kw)
+    return sim, c
+
+
+def spheric3_lid_driven(nx=200, hfac=4.0, overrides=None, device=0, **kw):
+    """The lid-driven cavity (SPHERIC test 3) through the unchanged 55-tool pipeline of
+    examples/2D/spheric_testcase3_liddriven (improved Euler, delta-SPH full, BI boundaries, BINoSlip)."""
+    from . import cases
+    c = cases.spheric3_lid_driven_2d(nx, hfac)
+    sim = load("spheric3_liddriven_2d", c, (c["n_set0"], c["n_set1"]), overrides, device, **kw)
     return sim, c
 
 

@@ -360,6 +360,52 @@ def spheric9_tld_2d(n=10000, hfac=4.0, seed=None):
     )
 
 
+def spheric3_lid_driven_2d(nx=200, hfac=4.0, Re=1000.0):
+    """The lid-driven cavity (SPHERIC test 3), geometry and fields of
+    examples/2D/spheric_testcase3_liddriven/src/Create.py:41-230: a unit square of nx x nx fluid
+    particles at rest (set 0, rho = refd = 1, background pressure p0 = 3 refd U^2), closed by four walls
+    of nx boundary-integral elements each (set 1: imove = -3, m = dr, outward normals), the top one
+    moving with u = (U, 0); no gravity; the no-slip set is noslip_iset = 1 (BINoSlip.xml)."""
+    cs, courant, refd, L, U = 50.0, 0.1, 1.0, 1.0, 1.0
+    dr = L / nx
+    visc_dyn = refd * U * L / Re
+    alpha = 8.0 * visc_dyn / (refd * hfac * dr * cs)
+    delta = 1.0 if alpha < 0.03 else 0.0
+    k = np.arange(nx)
+    c = -0.5 * (L - dr) + k * dr
+    X, Y = np.meshgrid(c, c, indexing="ij")                      # x outer, y inner
+    fluid = np.stack([X.ravel(), Y.ravel()], 1)
+    half = np.full(nx, 0.5 * L)
+    bnd = np.concatenate([np.stack([c, half], 1), np.stack([c, -half], 1),       # top, bottom
+                          np.stack([-half, c], 1), np.stack([half, c], 1)])      # left, right
+    nrm = np.concatenate([np.tile([0.0, 1.0], (nx, 1)), np.tile([0.0, -1.0], (nx, 1)),
+                          np.tile([-1.0, 0.0], (nx, 1)), np.tile([1.0, 0.0], (nx, 1))])
+    nf, nb = len(fluid), len(bnd)
+    N = nf + nb
+    u = np.zeros((N, 2), np.float32)
+    u[nf:nf + nx, 0] = U                                         # the lid
+    m = np.full(N, refd * dr ** 2, np.float32)
+    m[nf:] = dr
+    imove = np.ones(N, np.int32)
+    imove[nf:] = -3
+    iset = np.zeros(N, np.uint32)
+    iset[nf:] = 1
+    normal = np.zeros((N, 2), np.float32)
+    normal[nf:] = nrm
+    hh = float(np.float32(np.float32(hfac) * np.float32(dr)))
+    return dict(
+        dims=2, N=N, n_fluid=nf, n_set0=nf, n_set1=nb, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs,
+        p0=3.0 * refd * U ** 2, support=2.0, refd=np.array([refd, refd], np.float32),
+        visc_dyn=np.array([visc_dyn, visc_dyn], np.float32), delta=np.array([delta, delta], np.float32),
+        g=np.array([0, 0], np.float32), domain_min=np.array([-L, -L], np.float32),
+        domain_max=np.array([L, L], np.float32), courant=courant, dt_Ma=0.1,
+        dt_min=float(np.float32(0.05 * courant * hh / cs)), id=np.arange(N, dtype=np.uint32),
+        r=np.concatenate([fluid, bnd]).astype(np.float32), imove=imove, iset=iset, normal=normal,
+        tangent=np.zeros((N, 2), np.float32), rho=np.full(N, refd, np.float32), m=m, u=u,
+        dudt=np.zeros((N, 2), np.float32), drhodt=np.zeros(N, np.float32),
+    )
+
+
 def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None):
     """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way
     examples/3D/spheric_testcase2_dambreak_mpi/src/Create.py:140-200 does it: rank k

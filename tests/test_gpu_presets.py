@@ -415,3 +415,34 @@ def test_bi_noslip_sweep(oracle, dims, n, hfac, engine):
     assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
     fl = s["imove"] == 1
     assert np.abs(want - lap)[fl].max() > 0 and np.array_equal(got[~fl], lap[~fl])
+
+
+def test_lid_driven_cavity_pipeline(oracle):
+    """SPHERIC test 3: the unchanged 55-tool pipeline of examples/2D/spheric_testcase3_liddriven (improved
+    Euler, delta-SPH full, BI boundaries, BINoSlip) on the GPU against the oracle interpreter, three steps:
+    neighbour structures and dt bit-exact, fields within the tolerances of the 2-D dam-break pipeline."""
+    from oracle import interp
+    host.set_log_level(3)
+    case = product_cases.spheric3_lid_driven_2d(50)
+    nset = (case["n_set0"], case["n_set1"])
+    I = interp.Interpreter(casegen.instantiate("spheric3_liddriven_2d", case, nset), 2)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = case[k]
+    sim = casegen.load("spheric3_liddriven_2d", case, nset)
+    assert sim.tools() == [(t["name"], t["type"]) for t in I.tools]
+    for step in range(3):
+        I.step()
+        sim.step(1)
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"])
+        if step == 0:
+            for k in ("icell", "id_sorted", "id_unsorted"):
+                assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+        fl = I.unsorted("imove") == 1
+        for k, tol in {"r": 1e-6, "u": 2e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}.items():
+            a = I.unsorted(k).astype(np.float64)
+            b = sim.download(k, unsorted=True).astype(np.float64)
+            scale = max(np.abs(a[fl]).max(), 1e-30)
+            assert np.abs(a[fl] - b[fl]).max() <= tol * scale, "step %d field %s" % (step, k)
+    assert np.abs(sim.download("u", unsorted=True)[fl]).max() > 0      # the lid drags the fluid
+    sim.close()

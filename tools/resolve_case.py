@@ -28,6 +28,8 @@ CASES = {
     # BASELINE config 4: tuned liquid damper, BIe + forces + energy + motion presets (the two
     # `python` tools of cfd/motion.xml stay in the template; casegen.prescribed_roll replaces them)
     "spheric9_tld_2d": ("examples/2D/spheric_testcase9_tld/src/templates", 2),
+    # lid-driven cavity (SPHERIC test 3): improved Euler, delta-SPH full, BI boundaries + BINoSlip
+    "spheric3_liddriven_2d": ("examples/2D/spheric_testcase3_liddriven/src/templates", 2),
     # the reference's own multi-device parity test (tests/2D/MPI_plane)
     "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
     "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
@@ -64,7 +66,7 @@ def resolve(name, src, dims, main="Main.xml"):
             txt = txt.replace("@RESOURCES_DIR@", os.path.join(root, "resources"))
             for k in set(re.findall(r"\{\{(\w+)\}\}", txt)):
                 if k not in keys:
-                    keys[k] = "9%06d" % (len(keys) + 1) if k in ("N", "N_SENSORS", "NBC") \
+                    keys[k] = "9%06d" % (len(keys) + 1) if k in ("N", "N_SENSORS", "NBC", "NFLUID") \
                         else "0.9%05d1" % (len(keys) + 1)
                 txt = txt.replace("{{%s}}" % k, keys[k])
             open(p, "w").write(txt)
