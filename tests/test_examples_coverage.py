@@ -1,0 +1,70 @@
+"""Build-container check (needs /root/reference): which of the reference's shipped examples this build
+covers (tools/example_coverage.py), and for every covered one that each kernel tool of
+its resolved pipeline would bind -- every argument the CUDA registry lists is a declared variable of the
+right kind (array / scalar) and type, the check Kernel::setup makes on the device side
+(aquagpusph_b200/host/calcserver.cpp, after Kernel.cpp:497-556)."""
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/examples"),
+                                reason="needs the reference tree (build container only)")
+
+COVERED = {"2D/lobovsky_etal_2014", "2D/normal_impact", "2D/spheric_testcase10_waveimpact",
+           "2D/spheric_testcase3_liddriven", "2D/spheric_testcase5_dambreak", "2D/spheric_testcase9_tld",
+           "3D/spheric_testcase10_waveimpact", "3D/spheric_testcase2_dambreak",
+           "3D/spheric_testcase2_dambreak_mpi", "3D/spheric_testcase9_tld"}
+
+# variables the host registers itself (CalcServer.cpp:139-236, Variables defaults)
+BUILTIN = dict(N="usize", n_sets="uint", n_radix="usize", t="float", dt="float", iter="uint", frame="uint",
+               end_t="float", id="usize*", r="vec*", iset="uint*", id_sorted="usize*", id_unsorted="usize*",
+               icell="usize*", ihoc="usize*", n_cells="svec4", mpi_rank="uint", mpi_size="uint")
+
+
+def _norm(t, dims):
+    t = t.strip()
+    arr = t.endswith("*")
+    t = t.rstrip("*").strip()
+    t = {"unsigned int": "uint", "usize": "uint", "size_t": "uint", "svec4": "uivec4", "unsigned long": "uint",
+         "svec": "uivec"}.get(t, t)
+    if dims == 3 and t in ("vec", "vec4"):
+        t = "vec4"
+    if dims == 3 and t in ("uivec", "uivec4"):
+        t = "uivec4"
+    return t, arr
+
+
+def test_covered_examples_and_their_bindings():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import example_coverage as ec
+    from aquagpusph_b200 import _lib
+    L = _lib.lib()
+    rows = ec.scan()
+    assert len(rows) == 20
+    full = {"%s/%s" % (r[0], r[1]) for r in rows if r[2] and not r[4] and not r[5]}
+    assert full == COVERED
+    # apollo_capsule lacks only the `installable` plugin type
+    apollo = [r for r in rows if r[1] == "apollo_capsule"][0]
+    assert not apollo[4] and apollo[5] == ["installable"]
+    bad = []
+    for D, ex in sorted(x.split("/") for x in full):
+        dims = int(D[0])
+        txt = open(os.path.join(ec.R.OUT, "%s_%s.xml" % (ex, D))).read()
+        declared = dict(BUILTIN)
+        declared.update({m[0]: m[1] for m in re.findall(r'<Variable name="([^"]*)" type="([^"]*)"', txt)})
+        for path, entry in set(re.findall(r'type="kernel"[^>]*path="[^"]*?((?:Scripts/)?[^"/][^"]*\.cl)" entry_point="([^"]*)"', txt)):
+            kid = L.aqc_kernel_lookup(path.encode(), entry.encode(), dims)
+            if kid < 0:
+                kid = L.aqc_kernel_lookup(("Scripts/" + path).encode(), entry.encode(), dims)
+            assert kid >= 0, (ex, path, entry)
+            info = L.aqc_kernel_args(kid)
+            for k in range(L.aqc_kernel_nargs(kid)):
+                name, kt = info[k].name.decode(), info[k].type.decode()
+                if name not in declared:
+                    bad.append((ex, path, entry, name, "undeclared"))
+                elif _norm(kt, dims) != _norm(declared[name], dims):
+                    bad.append((ex, path, entry, name, kt, declared[name]))
+    assert not bad, bad
