@@ -299,7 +299,7 @@ def spheric9_tld(n=10000, hfac=4.0, overrides=None, device=0, seed=None, theta0=
 
 def lattice(n_side=100, hfac=2.0, overrides=None, device=0, **kw):
     """BASELINE config 5 (uniform 3-D lattice, all fluid, g = 0) through the 36-tool pipeline of
-    cases_xml/src/lattice_3d/Main.xml: the reference's presets basic + improved Euler + cfd +
+    cases_xml/src/lattice_3d/Lattice.xml: the reference's presets basic + improved Euler + cfd +
     variableTimeStep, i.e. predictor, link-list, sort, EOS, Shepard + Interactions, Rates, corrector,
     per-particle time step + min reduction."""
     from . import cases

@@ -1,4 +1,4 @@
-"""BASELINE config 5 on the CPU: the 36-tool lattice pipeline (cases_xml/src/lattice_3d/Main.xml over
+"""BASELINE config 5 on the CPU: the 36-tool lattice pipeline (cases_xml/src/lattice_3d/Lattice.xml over
 the reference's unchanged presets basic + improved_euler + cfd + variableTimeStep) resolves to the
 tool list SURVEY 8(d) names, parses identically in the C++ host and the oracle interpreter, names
 only registered kernels, and steps in the oracle.  GPU side: tests/test_gpu_presets.py."""

@@ -34,9 +34,9 @@ CASES = {
     "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
     "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
     # BASELINE config 5: our own Main.xml (cases_xml/src/lattice_3d) over the reference's presets
-    "lattice_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_3d", 3),
-    "lattice_mpi_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_mpi_3d", 3),
-    "lattice_ab_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_ab_3d", 3),
+    "lattice_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_3d", 3, "Lattice.xml"),
+    "lattice_mpi_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_mpi_3d", 3, "Lattice.xml"),
+    "lattice_ab_3d": ("repo:aquagpusph_b200/cases_xml/src/lattice_ab_3d", 3, "Lattice.xml"),
 }
 
 
