@@ -4,7 +4,9 @@
     python tools/bench2d.py [n] [steps] tld        SPHERIC test 9 tuned liquid damper (BIe + forces + energy +
                                                    motion presets, hfac 4, BASELINE config 4; n = fluid
                                                    particles, 2000000 in BASELINE.json; prescribed roll of
-                                                   casegen.prescribed_roll instead of the python tools)"""
+                                                   casegen.prescribed_roll instead of the python tools)
+    python tools/bench2d.py [n] [steps] cavity     SPHERIC test 3 lid-driven cavity (BI + BINoSlip, hfac 4;
+                                                   n = fluid particles, 40000 as shipped)"""
 import os, sys, json, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,6 +18,9 @@ which = sys.argv[3] if len(sys.argv) > 3 else "dambreak"
 if which == "tld":
     name = "spheric9_tld_2d"
     sim, case = casegen.spheric9_tld(n, 4.0)
+elif which == "cavity":
+    name = "spheric3_liddriven_2d"
+    sim, case = casegen.spheric3_lid_driven(int(round(n ** 0.5)), 4.0)
 else:
     name = "spheric5_dambreak_2d"
     case = cases.spheric5_dam_break_2d(n, 3.0)

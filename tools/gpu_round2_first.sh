@@ -12,3 +12,4 @@ timeout 300 python tools/bench2d.py 50000 50 > gpurun_out/bench2d_dambreak_50k_$
 for HF in 1.3 2 3; do
   timeout 600 python tools/bench_lattice.py 200 $HF 5 > gpurun_out/bench_lattice_8M_hfac${HF}_$TAG.log 2>&1; tail -2 gpurun_out/bench_lattice_8M_hfac${HF}_$TAG.log
 done
+timeout 300 python tools/bench2d.py 1000000 10 cavity > gpurun_out/bench2d_cavity_1M_$TAG.log 2>&1; tail -2 gpurun_out/bench2d_cavity_1M_$TAG.log
