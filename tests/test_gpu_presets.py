@@ -420,7 +420,8 @@ def test_bi_noslip_sweep(oracle, dims, n, hfac, engine):
 def test_lid_driven_cavity_pipeline(oracle):
     """SPHERIC test 3: the unchanged 55-tool pipeline of examples/2D/spheric_testcase3_liddriven (improved
     Euler, delta-SPH full, BI boundaries, BINoSlip) on the GPU against the oracle interpreter, three steps:
-    neighbour structures and dt bit-exact, fields within the tolerances of the 2-D dam-break pipeline."""
+    neighbour structures and dt bit-exact, fields within the tolerances of the 2-D dam-break pipeline
+    (u within dudt's: the fluid starts at rest)."""
     from oracle import interp
     host.set_log_level(3)
     case = product_cases.spheric3_lid_driven_2d(50)
@@ -439,7 +440,8 @@ def test_lid_driven_cavity_pipeline(oracle):
             for k in ("icell", "id_sorted", "id_unsorted"):
                 assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
         fl = I.unsorted("imove") == 1
-        for k, tol in {"r": 1e-6, "u": 2e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}.items():
+        # the fluid starts at rest: u is dt * dudt during these steps and carries dudt's tolerance
+        for k, tol in {"r": 1e-6, "u": 2e-4, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}.items():
             a = I.unsorted(k).astype(np.float64)
             b = sim.download(k, unsorted=True).astype(np.float64)
             scale = max(np.abs(a[fl]).max(), 1e-30)
