@@ -125,7 +125,11 @@ def test_energy_kernels(oracle, dims):
     ctx.close()
 
 
-TLD_FIELDS = {"r": 1e-6, "u": 2e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}
+# Tolerances of the pipeline tests below = about twice what a 1-ulp perturbation of the fluid's u and rho does to the
+# ORACLE's own result over the same steps (a conservative stand-in for the summation-order differences of the sweeps,
+# measured here without a GPU: tld dudt 1.1e-3 on the first step, cavity u / dudt 1e-3 and drhodt 1e-2 because the
+# fluid starts at rest under a background pressure, lattice u 8e-6).  To be tightened after the first run on a B200.
+TLD_FIELDS = {"r": 1e-6, "u": 5e-5, "rho": 1e-6, "p": 4e-4, "dudt": 2e-3, "drhodt": 5e-4}
 
 
 def test_tuned_liquid_damper_pipeline(oracle):
@@ -214,7 +218,7 @@ def test_lattice_pipeline(oracle, template, n_side, hfac):
                 assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
             ncw = int(I.V["n_cells"][3])
             assert np.array_equal(sim.download("ihoc", np.uint32)[:ncw], I.V["ihoc"][:ncw])
-        for k, tol in {"r": 1e-6, "u": 1e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 2e-4}.items():
+        for k, tol in {"r": 1e-6, "u": 3e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 2e-4}.items():
             a = I.unsorted(k).astype(np.float64)
             b = sim.download(k, unsorted=True).astype(np.float64)
             assert np.abs(a - b).max() <= tol * np.abs(a).max(), "step %d field %s" % (step, k)
@@ -441,7 +445,7 @@ def test_lid_driven_cavity_pipeline(oracle):
                 assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
         fl = I.unsorted("imove") == 1
         # the fluid starts at rest: u is dt * dudt during these steps and carries dudt's tolerance
-        for k, tol in {"r": 1e-6, "u": 2e-4, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 5e-4}.items():
+        for k, tol in {"r": 1e-6, "u": 2e-3, "rho": 1e-6, "p": 4e-4, "dudt": 2e-3, "drhodt": 2e-2}.items():
             a = I.unsorted(k).astype(np.float64)
             b = sim.download(k, unsorted=True).astype(np.float64)
             scale = max(np.abs(a[fl]).max(), 1e-30)
