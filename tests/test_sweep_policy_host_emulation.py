@@ -59,6 +59,44 @@ template <int D> static void run(const uint32_t* iset, const int* imove, const v
         p.store_i(s, i);
     }
 }
+template <class P, class Set> static void sweep_all(P& p, const int* imove, uint32_t N, float H, float SUPPORT, Set set)
+{
+    p.imove = imove; p.invH = 1.f / H; p.cut2 = (SUPPORT * H) * (SUPPORT * H);      // set_base
+    set(p);
+    for (uint32_t i = 0; i < N; i++) {
+        if (!p.i_active(imove[i]))
+            continue;
+        typename P::IState s;
+        p.load_i(s, i);
+        for (uint32_t j = 0; j < N; j++) {
+            float4 row[P::NJ4];
+            p.stage_j(j, row);
+            if (!PBase::j_live(row[0]) || !p.test(s, row[0]))
+                continue;
+            p.body(s, row, 1);
+        }
+        p.store_i(s, i);
+    }
+}
+template <int D> static void run_inter(const int* imove, const void* r, const void* normal, const void* u,
+                                       const float* rho, const float* m, const float* pp, void* grad_p,
+                                       float* div_u, uint32_t N, float H, float CONW, float SUPPORT)
+{
+    PBIInteractions<D> p;
+    sweep_all(p, imove, N, H, SUPPORT, [&](PBIInteractions<D>& q) {      // run_bi_inter
+        q.r = r; q.normal = normal; q.u = u; q.rho = rho; q.m = m; q.p = pp; q.grad_p = grad_p; q.div_u = div_u;
+        q.cW = Wend<D>::W * CONW;
+    });
+}
+extern "C" void emu_bi_inter(int dims, const int* imove, const void* r, const void* normal, const void* u,
+                             const float* rho, const float* m, const float* pp, void* grad_p, float* div_u,
+                             uint32_t N, float H, float CONW, float SUPPORT)
+{
+    if (dims == 3)
+        run_inter<3>(imove, r, normal, u, rho, m, pp, grad_p, div_u, N, H, CONW, SUPPORT);
+    else
+        run_inter<2>(imove, r, normal, u, rho, m, pp, grad_p, div_u, N, H, CONW, SUPPORT);
+}
 extern "C" void emu_noslip(int dims, const uint32_t* iset, const int* imove, const void* r, const void* normal,
                            const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
                            uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
@@ -87,7 +125,9 @@ def _lift():
     helpers = re.sub(r'asm\("rcp\.approx\.ftz\.f32[^\n]*\n', "r = 1.f / x;\n", helpers)
     assert "asm(" not in helpers and "struct PBase" in helpers
     policy = _between(cu, "template <int D>\nstruct PBINoSlip : PBase {", "// cfd/Boundary/ElasticBounce.cl:77-148")
-    return far + "\n" + dist2 + helpers + policy
+    # a policy that IS verified on the GPU (tests/test_gpu_bi.py), to validate this harness itself
+    known = _between(cu, "template <int D>\nstruct PBIInteractions : PBase {", "// BI/NoSlip.cl:52-130")
+    return far + "\n" + dist2 + helpers + known + policy
 
 
 @pytest.fixture(scope="module")
@@ -118,3 +158,37 @@ def test_noslip_policy_matches_the_oracle(oracle, emu, dims, n, hfac):
     assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
     fl = s["imove"] == 1
     assert np.abs(want - lap)[fl].max() > 1e-3 and np.array_equal(got[~fl], lap[~fl])
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0)])
+def test_harness_reproduces_a_gpu_verified_policy(oracle, emu, dims, n, hfac):
+    """The harness itself: PBIInteractions (cfd/Boundary/BI/Interactions.cl), whose GPU parity is established
+    (tests/test_gpu_bi.py), lifted and driven the same way, equals the reference's own script (behind the
+    shim) at that test's tolerance."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    rng = np.random.default_rng(9)
+    N, V = s["N"], (4 if dims == 3 else 2)
+    c = pipeline.RefState(ref.Ref(dims, case["h"]), s)
+    c.run("basic/EOS.cl")
+    gp = np.zeros((N, V), np.float32)
+    gp[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+    du = rng.normal(size=N).astype(np.float32)
+    c.set("grad_p", gp)
+    c.set("div_u", du)
+    p_arr, rho = c.get("p"), c.get("rho")
+    c.run("cfd/Boundary/BI/Interactions.cl")
+    want_g, want_d = c.get("grad_p"), c.get("div_u")
+    got_g, got_d = gp.copy(), du.copy()
+    D = oracle.make_defs(dims, s["h"])
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)   # noqa: E731
+    arr = {k: np.ascontiguousarray(s[k]) for k in ("imove", "r", "normal", "u", "m")}
+    emu.emu_bi_inter(dims, P(arr["imove"]), P(arr["r"]), P(arr["normal"]), P(arr["u"]), P(rho), P(arr["m"]), P(p_arr),
+                     P(got_g), P(got_d), N, C.c_float(D.H), C.c_float(D.CONW), C.c_float(D.SUPPORT))
+    for a, b in ((want_g, got_g), (want_d, got_d)):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        assert np.all(np.abs(a - b) <= 5e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
+    assert np.abs(want_g - gp).max() > 0
