@@ -25,7 +25,7 @@ SYMBOLS = [
     "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
-    "aqc_mpi_sync", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
+    "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
     "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats",
 ]
@@ -114,6 +114,11 @@ def lib():
     L.aqc_comm_size.argtypes = [C.c_void_p]
     L.aqc_mpi_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p),
                                C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint32)]
+    L.aqc_mpi_sync_plan.argtypes = [C.c_void_p]
+    L.aqc_mpi_sync_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint32),
+                                  C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.aqc_mpi_sync_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -297,6 +302,42 @@ class Context:
 
     def sm_count(self):
         return int(lib().aqc_device_sm_count(self.h))
+
+    # -- multi-device (include/aquacuda.h): one process per GPU, NCCL
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        if lib().aqc_comm_unique_id(buf):
+            raise AquaError("aqc_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, rank, size, unique_id):
+        self._chk(lib().aqc_comm_init(self.h, int(rank), int(size), unique_id))
+
+    def mpi_sync_plan(self):
+        return int(lib().aqc_mpi_sync_plan(self.h))
+
+    def mpi_sync(self, mask, fields, procs=None, plan=-1, deps=()):
+        """MPISync::_execute on DevArrays; returns the number of elements received."""
+        nf = len(fields)
+        ptrs = (C.c_void_p * max(nf, 1))(*[f.ptr for f in fields])
+        eb = (C.c_size_t * max(nf, 1))(*[f.elem_bytes for f in fields])
+        pr = (C.c_uint * max(len(procs or ()), 1))(*(procs or ()))
+        dp = (C.c_void_p * max(len(deps), 1))(*[d.ptr for d in deps])
+        db = (C.c_size_t * max(len(deps), 1))(*[d.nbytes for d in deps])
+        nrecv = C.c_uint32(0)
+        self._chk(lib().aqc_mpi_sync_ex(self.h, int(plan), mask.ptr, mask.shape[0], nf, ptrs, eb,
+                                        len(procs or ()), pr if procs else None, C.byref(nrecv),
+                                        len(deps), dp, db))
+        return int(nrecv.value)
+
+    def mpi_sync_stats(self, plan):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._chk(lib().aqc_mpi_sync_stats(self.h, int(plan), C.byref(a), C.byref(b)))
+        return dict(full=a.value, reused=b.value)
+
+    def allreduce(self, op, typ, arr, count):
+        self._chk(lib().aqc_allreduce(self.h, op, typ, arr.ptr, count))
 
     # -- tools
     def linklist(self, r, support, h, icell, ihoc, perm, inv_perm, rmin=None, rmax=None,

@@ -192,6 +192,11 @@ def multi_device_fixes(txt):
         for nm in chain:
             txt = move_tool(txt, nm, anchor)
             anchor = nm
+        # r and imove are fixed inside the loop (midpoint.cl:93-111 advances u and rho), and the
+        # plane masks are functions of them alone (cfd/MPI/planes.cl:41-99): every sub-iteration
+        # after the first reuses the first one's sort and counts (MPISync `depends`, ours)
+        txt = re.sub(r'(<Tool [^>]*name="mpi neighs sync" [^>]*?)(\s*/>)',
+                     lambda m: m.group(1) + ' depends="r,imove"' + m.group(2), txt, 1)
     txt = add_tool_after(txt, "cfd minimum time step",
                          '<Tool action="add" name="mpi global dt" type="mpi-allreduce" once="false" '
                          'in="dt" operation="min" />')
@@ -202,12 +207,13 @@ def multi_device_fixes(txt):
     return txt
 
 
-def spheric2_slab(n_total, rank, size, hfac=3.0, overrides=None, device=0, unique_id=None, **kw):
+def spheric2_slab(n_total, rank, size, hfac=3.0, overrides=None, device=0, unique_id=None, seed=None,
+                  jitter=0.0, uscale=0.1, **kw):
     """BASELINE config 3: the 3-D dam break on `size` devices (y slabs) through the
     pipeline of examples/3D/spheric_testcase2_dambreak_mpi (131 tools: midpoint, BIe
     boundaries, variable time step, cfd/MPI.xml migration + halo)."""
     from . import cases
-    c = cases.spheric2_dam_break_slab(n_total, hfac, rank, size)
+    c = cases.spheric2_dam_break_slab(n_total, hfac, rank, size, seed=seed, jitter=jitter, uscale=uscale)
     sim = load("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), overrides, device,
                mpi_rank=rank, mpi_size=size, unique_id=unique_id, transform=multi_device_fixes, **kw)
     return sim, c

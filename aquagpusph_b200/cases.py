@@ -118,7 +118,7 @@ def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0):
     )
 
 
-def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
+def spheric2_dam_break(n=1000000, hfac=3.0, seed=None, jitter=0.0, uscale=0.1):
     """BASELINE config 2: the 3-D SPHERIC test 2 dam break with obstacle, same
     geometry and field initialisation as the reference's case generator
     (examples/3D/spheric_testcase2_dambreak/src/Create.py:39-462): fluid block
@@ -216,7 +216,9 @@ def spheric2_dam_break(n=1000000, hfac=3.0, seed=None):
     u = np.zeros((N, 4), np.float32)
     if seed is not None:  # optional perturbation so that every term is exercised
         rng = np.random.default_rng(seed)
-        u[:nfluid, :3] = 0.1 * rng.uniform(-1, 1, (nfluid, 3))
+        u[:nfluid, :3] = uscale * rng.uniform(-1, 1, (nfluid, 3))
+        if jitter:  # off-lattice positions: halo / migration counts of a slab cut are arbitrary
+            r[:nfluid, :3] += (jitter * dr * rng.uniform(-1, 1, (nfluid, 3))).astype(np.float32)
     return dict(
         dims=3, N=N, n_fluid=nfluid, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs, p0=0.0,
         support=2.0, refd=np.array([refd, refd], np.float32),
@@ -406,7 +408,8 @@ def spheric3_lid_driven_2d(nx=200, hfac=4.0, Re=1000.0):
     )
 
 
-def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None):
+def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None, seed=None,
+                            jitter=0.0, uscale=0.1):
     """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way
     examples/3D/spheric_testcase2_dambreak_mpi/src/Create.py:140-200 does it: rank k
     owns the fluid with y in (y_min + k dy, y_min + (k+1) dy), dy = (domain_max_y -
@@ -417,8 +420,9 @@ def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary
     (imove = -255 parked at domain_max, Create.py:170-190) that receive migrating
     particles.  The y limits of the domain hug the tank (2 dr of slack) so that the
     slabs hold the same amount of fluid.  Returns the case dict of this rank with
-    n_set0 (fluid + boundary + buffer) and the global particle count."""
-    c = spheric2_dam_break(n_total, hfac)
+    n_set0 (fluid + boundary + buffer) and the global particle count.  `seed`: the perturbed
+    state of spheric2_dam_break (the same on every rank: it is cut afterwards)."""
+    c = spheric2_dam_break(n_total, hfac, seed=seed, jitter=jitter, uscale=uscale)
     dr, h = c["dr"], c["h"]
     dmin, dmax = c["domain_min"].copy(), c["domain_max"].copy()
     dmin[1], dmax[1] = -0.5 - 2.0 * dr, 0.5 + 2.0 * dr

@@ -12,6 +12,10 @@ int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...)
         va_start(ap, fmt);
         vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
         va_end(ap);
+        // a rank that hit a device fault cannot keep step with its peers: give the communicator
+        // up now, so that this process can leave and the peers' bounded waits end (mpi.cu)
+        if (code == AQC_ERR_CUDA && ctx->comm)
+            aqc_comm_abort(ctx);
     }
     return code;
 }
@@ -58,8 +62,8 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
+    aqc_comm_destroy(ctx); // (drains the stream with a deadline while a communicator is live)
     cudaStreamSynchronize(ctx->stream);
-    aqc_comm_destroy(ctx);
     for (int k = 0; k < 2; k++) {
         cudaFree(ctx->sort_keys[k]);
         cudaFree(ctx->sort_vals[k]);
@@ -89,7 +93,7 @@ extern "C" int aqc_set_stream(aqc_ctx* ctx, void* s)
 {
     if (!ctx)
         return AQC_ERR_ARG;
-    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AQC_SYNC(ctx);
     if (ctx->own_stream) {
         cudaStreamDestroy(ctx->stream);
         ctx->own_stream = false;
@@ -109,7 +113,7 @@ extern "C" int aqc_sync(aqc_ctx* ctx)
 {
     if (!ctx)
         return AQC_ERR_ARG;
-    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AQC_SYNC(ctx);
     return AQC_OK;
 }
 
@@ -184,7 +188,7 @@ extern "C" int aqc_free(aqc_ctx* ctx, void* dptr)
         return AQC_ERR_ARG;
     if (dptr) {
         aqc_pc_touch(ctx, dptr, 1);
-        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_SYNC(ctx);
         AQC_CUDA(ctx, cudaFree(dptr));
     }
     return AQC_OK;
@@ -214,7 +218,7 @@ extern "C" int aqc_memcpy_h2d(aqc_ctx* ctx, void* dst, const void* src, size_t b
     aqc_pc_touch(ctx, dst, bytes);
     AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (blocking)
-        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_SYNC(ctx);
     return AQC_OK;
 }
 
@@ -224,7 +228,7 @@ extern "C" int aqc_memcpy_d2h(aqc_ctx* ctx, void* dst, const void* src, size_t b
         return AQC_ERR_ARG;
     AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (blocking)
-        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_SYNC(ctx);
     return AQC_OK;
 }
 
@@ -325,6 +329,8 @@ extern "C" int aqc_event_sync(aqc_ctx* ctx, void* ev)
 {
     if (!ctx)
         return AQC_ERR_ARG;
+    if (ctx->comm)
+        return aqc_comm_wait(ctx, (cudaEvent_t)ev);
     AQC_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)ev));
     return AQC_OK;
 }

@@ -5,9 +5,13 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "aquacuda.h"
+
+struct aqc_ctx;
+int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...);
 
 // Pair-mask cache of the v3 sweep engine (sweep.cuh, S3Cache): hit masks of the candidate filter,
 // built once per geometry (positions + link-list + particle classes) and read by every sweep
@@ -34,6 +38,24 @@ struct aqc_pair_cache {
     // a build costs about half a sweep: pipelines whose geometry changes before a second sweep
     // reads the masks (served < 2, three times in a row) go without for a while
     uint32_t served = 0, poor_streak = 0, cooldown = 0;
+};
+
+// One slot per mpi-sync tool (aqc_mpi_sync_plan): what a call leaves behind so that the next call on
+// a mask with the same content only gathers and exchanges (mpi.cu)
+struct aqc_sync_plan {
+    bool valid = false;
+    const void* mask = nullptr;
+    uint32_t n = 0;
+    std::vector<const void*> fields;
+    std::vector<size_t> elem_bytes;
+    std::vector<char> peer;
+    std::vector<uint32_t> soff, scnt, rcnt, roff; // per process
+    uint32_t* perm = nullptr; // device: sort permutation of the mask
+    size_t perm_cap = 0;
+    uint32_t* mask_copy = nullptr; // device: the mask the plan was made from (AQC_MPI_VERIFY=1)
+    size_t mask_copy_cap = 0;
+    std::vector<std::pair<const char*, size_t>> deps; // ranges the mask is a function of
+    uint64_t full = 0, reused = 0;
 };
 
 struct aqc_ctx {
@@ -83,18 +105,48 @@ struct aqc_ctx {
     size_t comm_perm_cap = 0;
     void* comm_send = nullptr;         // packed outgoing fields
     size_t comm_send_cap = 0;
+    bool comm_dead = false;            // the communicator was aborted (a peer is gone, a local fault)
+    std::vector<aqc_sync_plan> plans;  // aqc_mpi_sync_plan slots
 };
 
 int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
+// Bounded wait for everything queued on the context's stream while a communicator is live: a
+// collective whose peer died never completes, so the stream is polled against a deadline
+// (AQC_COMM_TIMEOUT_S, default 60 s) together with ncclCommGetAsyncError; on expiry or error the
+// communicator is aborted and the call fails (mpi.cu).  ev != nullptr: wait for that event only.
+int aqc_comm_wait(aqc_ctx* ctx, cudaEvent_t ev);
+void aqc_comm_abort(aqc_ctx* ctx); // mpi.cu
+static inline int aqc_stream_wait(aqc_ctx* ctx)
+{
+    if (ctx->comm)
+        return aqc_comm_wait(ctx, nullptr);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess)
+        return aqc_fail(ctx, AQC_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    return AQC_OK;
+}
+#define AQC_SYNC(ctx)                                                          \
+    do {                                                                       \
+        int s__ = aqc_stream_wait(ctx);                                        \
+        if (s__)                                                               \
+            return s__;                                                        \
+    } while (0)
 
 // [ptr, ptr + bytes) is about to be written: the pair-mask cache dies if it was built from it
 static inline void aqc_pc_touch(aqc_ctx* ctx, const void* ptr, size_t bytes)
 {
     aqc_pair_cache& c = ctx->pc;
-    if (!c.valid || !ptr)
+    if (!ptr)
         return;
     const char* a = (const char*)ptr;
     const char* b = a + (bytes ? bytes : 1);
+    for (aqc_sync_plan& pl : ctx->plans) // mpi-sync plans die with the arrays their mask derives from
+        if (pl.valid)
+            for (auto& d : pl.deps)
+                if (a < d.first + d.second && d.first < b)
+                    pl.valid = false;
+    if (!c.valid)
+        return;
     auto hit = [&](const void* base, size_t n) {
         const char* x = (const char*)base;
         return base && a < x + n && x < b;
@@ -119,8 +171,6 @@ static inline size_t aqc_type_bytes(const char* type, int dims)
         return dims == 3 ? 16 : 8;
     return 4; // float, int, uint, usize (32-bit indices)
 }
-
-int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...);
 
 #define AQC_CUDA(ctx, call)                                                    \
     do {                                                                       \

@@ -495,7 +495,7 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
         AQC_CUDA(ctx, cudaMemcpyAsync(ctx->minmax_host, ctx->minmax_dev, 8 * sizeof(uint32_t),
                                       cudaMemcpyDeviceToHost, ctx->stream));
         // the reference blocks here too (LinkList.cpp:350-356)
-        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_SYNC(ctx);
         const uint32_t* k = (const uint32_t*)ctx->minmax_host;
         for (int c = 0; c < 4; c++) {
             rmin[c] = (c < vs) ? ord2f_host(k[c]) : 0.f;
@@ -527,7 +527,7 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
     // LinkList::allocate (LinkList.cpp:234-271)
     if ((size_t)ncells[3] > *ihoc_capacity || !*ihoc) {
         if (*ihoc) {
-            AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            AQC_SYNC(ctx);
             AQC_CUDA(ctx, cudaFree(*ihoc));
             *ihoc = nullptr;
             *ihoc_capacity = 0;

@@ -109,7 +109,7 @@ int run(aqc_ctx* ctx, const void* in, size_t n, void* out_dev, void* out_host)
     if (out_host) {
         AQC_CUDA(ctx, cudaMemcpyAsync(ctx->red_host, final_dev, NC * sizeof(T),
                                       cudaMemcpyDeviceToHost, ctx->stream));
-        AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AQC_SYNC(ctx);
         memcpy(out_host, ctx->red_host, NC * sizeof(T));
     }
     return AQC_OK;

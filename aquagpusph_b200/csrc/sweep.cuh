@@ -1143,7 +1143,7 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
                     const size_t need = (size_t)ll.N * P::NJ4 * sizeof(float4);
                     if (need > ctx->pack_cap) {
                         if (ctx->pack_rows) {
-                            AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                            AQC_SYNC(ctx);
                             AQC_CUDA(ctx, cudaFree(ctx->pack_rows));
                         }
                         ctx->pack_rows = nullptr;

@@ -1523,7 +1523,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
         for (int attempt = 0;; attempt++) {
             if (want > c.cap_rounds) {
                 if (c.masks) {
-                    AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    AQC_SYNC(ctx);
                     AQC_CUDA(ctx, cudaFree(c.masks));
                 }
                 c.masks = nullptr;
@@ -1547,7 +1547,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
                 return rc;
             AQC_CUDA(ctx, cudaMemcpyAsync(c.ctl_host, c.ctl, 2 * sizeof(unsigned long long),
                                           cudaMemcpyDeviceToHost, ctx->stream));
-            AQC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            AQC_SYNC(ctx);
             if (c.ctl_host[0] <= c.cap_rounds)
                 break;
             if (attempt)

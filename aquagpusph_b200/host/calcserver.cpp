@@ -565,6 +565,9 @@ void MPISync::setup()
                                      " does not exist");
         _procs.push_back(v);
     }
+    for (auto& d : split(_depends_txt))
+        if (!trimCopy(d).empty())
+            _depends.push_back(variable(trimCopy(d), true));
 }
 
 void MPISync::_execute()
@@ -577,9 +580,18 @@ void MPISync::_execute()
         ptrs.push_back(v->dptr());
         eb.push_back(v->typesize());
     }
-    check(aqc_mpi_sync(_C->ctx(), (aqc_usize*)_mask->dptr(), (aqc_usize)_mask->length(),
-                       (int)ptrs.size(), ptrs.data(), eb.data(), (int)_procs.size(),
-                       _procs.empty() ? nullptr : _procs.data(), nullptr));
+    if (_plan < 0 && !_depends.empty())
+        _plan = aqc_mpi_sync_plan(_C->ctx());
+    std::vector<const void*> dptrs;
+    std::vector<size_t> dbytes;
+    for (auto v : _depends) {
+        dptrs.push_back(v->dptr());
+        dbytes.push_back(v->length() * v->typesize());
+    }
+    check(aqc_mpi_sync_ex(_C->ctx(), _plan, (aqc_usize*)_mask->dptr(), (aqc_usize)_mask->length(),
+                          (int)ptrs.size(), ptrs.data(), eb.data(), (int)_procs.size(),
+                          _procs.empty() ? nullptr : _procs.data(), nullptr, (int)dptrs.size(),
+                          dptrs.data(), dbytes.data()));
 }
 
 // --------------------------------------------------------------- PythonTool --
@@ -965,7 +977,7 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
     if (type == "endif" || type == "end")
         return new End(this, name, once);
     if (type == "mpi-sync")
-        return new MPISync(this, name, t.get("mask"), t.get("fields"), t.get("processes"), once);
+        return new MPISync(this, name, t.get("mask"), t.get("fields"), t.get("processes"), t.get("depends"), once);
     if (type == "mpi-allreduce")
         return new MPIAllReduce(this, name, t.get("in"), t.get("operation"), once);
     if (type == "python")

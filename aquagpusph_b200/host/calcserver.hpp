@@ -263,20 +263,26 @@ class UnSort : public Tool {
 
 /// type="mpi-sync" (MPISync.cpp:183-232): particles whose `mask` names another
 /// process travel there; what arrives is packed at the front of the same arrays.
-/// The exchange runs over NCCL between device buffers (aqc_mpi_sync).
+/// The exchange runs over NCCL between device buffers (aqc_mpi_sync_ex).
+/// `depends` (not a reference attribute; empty = the reference's behaviour) names the arrays the
+/// mask content is a pure function of: while none of them is written, a later execution reuses
+/// the sort permutation and the counts of the previous one and only gathers and exchanges --
+/// the halo refresh inside the midpoint loop, where r is fixed.
 class MPISync : public Tool {
   public:
     MPISync(CalcServer* C, const std::string& name, const std::string& mask,
-            const std::string& fields, const std::string& procs, bool once)
-      : Tool(C, name, once), _mask_name(mask), _fields_txt(fields), _procs_txt(procs) {}
+            const std::string& fields, const std::string& procs, const std::string& depends, bool once)
+      : Tool(C, name, once), _mask_name(mask), _fields_txt(fields), _procs_txt(procs),
+        _depends_txt(depends) {}
     void setup() override;
   protected:
     void _execute() override;
   private:
-    std::string _mask_name, _fields_txt, _procs_txt;
+    std::string _mask_name, _fields_txt, _procs_txt, _depends_txt;
     InputOutput::Variable* _mask = nullptr;
-    std::vector<InputOutput::Variable*> _fields;
+    std::vector<InputOutput::Variable*> _fields, _depends;
     std::vector<unsigned> _procs;
+    int _plan = -1;
 };
 
 /// type="mpi-allreduce" in="var" operation="min|max|sum" -- NOT a reference tool:

@@ -231,6 +231,8 @@ void State::configureTool(ProblemSetup::Tool* tool, const Xml::Node* e, ProblemS
         toolAttr(tool, e, "mask");
         toolAttr(tool, e, "fields");
         toolAttr(tool, e, "processes", "");
+        // (ours, optional) the arrays the mask is a function of: see calcserver.hpp, MPISync
+        toolAttr(tool, e, "depends", "");
     } else if (type == "mpi-allreduce") { // not a reference tool, see calcserver.hpp
         toolAttr(tool, e, "in");
         toolAttr(tool, e, "operation", "min");

@@ -414,8 +414,17 @@ def main():
         a.warmup = 3
     if a.impl == "reference":
         run_reference(a, rank, world)
-    else:
+        return
+    try:
         run_ours(a, rank, world, local_rank)
+    except BaseException:
+        # a rank that failed must END the job: the peers' waits are bounded (aqc_comm_wait), and the
+        # launcher kills them as soon as this process is gone -- no destructors, no barriers
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

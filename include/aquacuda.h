@@ -222,6 +222,28 @@ int aqc_comm_size(const aqc_ctx* ctx);
 int aqc_mpi_sync(aqc_ctx* ctx, aqc_usize* mask, aqc_usize n, int nfields, void* const* fields,
                  const size_t* elem_bytes, int nprocs, const unsigned* procs,
                  aqc_usize* n_received);
+/* The same with a PLAN (one slot per mpi-sync tool, aqc_mpi_sync_plan): the caller names the device
+ * ranges the mask content is a pure function of (`dep_ptrs`/`dep_bytes`: e.g. r and imove for the
+ * plane masks of cfd/MPI/planes.cl).  A later call with the same plan, mask, fields and processes
+ * finds the sort permutation, the counts and the receive layout of the previous one still valid
+ * unless one of those ranges was written through this library in between, and then only gathers
+ * and exchanges: no sort, no count all-gather, no host synchronisation.  The reference sorts and
+ * exchanges counts on every call (MPISync.cpp:183-232); inside the midpoint loop r is fixed
+ * (basic/time_scheme/midpoint.cl:93-111), so the halo of every sub-iteration but the first
+ * travels on the first one's plan.  ndeps = 0 or plan < 0: every call is a full one.
+ * AQC_MPI_VERIFY=1 checks every reuse against a copy of the mask (tests).
+ * Failure behaviour of every collective entry point: while a communicator is live, waits for the
+ * device are bounded (AQC_COMM_TIMEOUT_S, default 60 s); a local device fault, an NCCL error or an
+ * expired wait aborts the communicator (ncclCommAbort) and the call fails, after which every
+ * collective call of this context fails at once -- a dead rank ends the job instead of leaving
+ * its peers inside ncclRecv. */
+int aqc_mpi_sync_plan(aqc_ctx* ctx); /* returns a new plan id >= 0 */
+int aqc_mpi_sync_ex(aqc_ctx* ctx, int plan, aqc_usize* mask, aqc_usize n, int nfields,
+                    void* const* fields, const size_t* elem_bytes, int nprocs, const unsigned* procs,
+                    aqc_usize* n_received, int ndeps, const void* const* dep_ptrs,
+                    const size_t* dep_bytes);
+/* full (sorted + counted) and reused executions of a plan so far */
+int aqc_mpi_sync_stats(const aqc_ctx* ctx, int plan, uint64_t* full, uint64_t* reused);
 /* ADDITIONS to the reference, which has no collective: element-wise
  * all-reduce (AQC_OP_*, AQC_T_*) of a device array in place / of a small host
  * value (<= 64 bytes; syncs).  aqc_linklist_build all-reduces r_min / r_max by

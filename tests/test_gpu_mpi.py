@@ -165,10 +165,7 @@ def _run_two_gpus(fixed_mask, overrides, steps=1):
     port = _free_port()
     procs = [ctx.Process(target=_gpu_rank, args=(r, port, q, fixed_mask, overrides, steps)) for r in range(2)]
     [p.start() for p in procs]
-    got = dict(q.get(timeout=600) for _ in range(2))
-    [p.join(120) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
-    return got
+    return _collect(procs, q, 2, 600)
 
 
 def _two_gpus():
@@ -203,8 +200,9 @@ def test_mpi_plane_two_gpus(golden, oracle):
             assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-30), (r, k)
 
 
-def _slab_rank(rank, size, port, q, n_total, steps):
+def _slab_rank(rank, size, port, q, n_total, steps, kw=None):
     import torch.distributed as dist
+    os.environ["AQC_MPI_VERIFY"] = "1"   # every reused mpi-sync plan is checked against its mask
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from aquagpusph_b200 import casegen, host
@@ -215,11 +213,25 @@ def _slab_rank(rank, size, port, q, n_total, steps):
         uid = [host.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
     ov = {"iter_midpoint_max": int(os.environ.get("AQ_DIAG_MAXITER", "2"))}
-    sim, c = casegen.spheric2_slab(n_total, rank, size, overrides=ov, device=rank, unique_id=uid[0])
+    kw = dict(kw or {})
+    whole = kw.pop("whole", False)
+    if "iter_midpoint_max" in kw:
+        ov["iter_midpoint_max"] = kw.pop("iter_midpoint_max")
+    sim, c = casegen.spheric2_slab(n_total, rank, size, overrides=ov, device=rank, unique_id=uid[0], **kw)
     sim.step(steps)
     nf = c["n_fluid"]
-    res = {k: sim.download(k, np.float32, unsorted=True)[:nf] for k in ("r", "u", "rho", "dudt")}
-    res["imove"] = sim.download("imove", np.int32, unsorted=True)[:nf]
+    if whole:
+        # after migration a rank's rows are no longer its initial fluid: the test takes every
+        # row of set 0 in device order and matches the live fluid ones by position
+        n0 = c["n_set0"]
+        res = {k: sim.download(k, np.float32)[:n0] for k in ("r", "u", "rho", "dudt")}
+        res["imove"] = sim.download("imove", np.int32)[:n0]
+    else:
+        res = {k: sim.download(k, np.float32, unsorted=True)[:nf] for k in ("r", "u", "rho", "dudt")}
+        res["imove"] = sim.download("imove", np.int32, unsorted=True)[:nf]
+    res["sync_tools"] = {name: n for name, n, _ in sim.tool_times() if "sync" in name}
+    res["plan0"] = _lib.Context.borrow(sim.cuda_ctx(), 3).mpi_sync_stats(0) if size > 1 else None
+    res["n_fluid0"] = nf
     res["fluid_index"] = c["fluid_index"]
     res["dt"] = float(sim.scalar("dt"))
     res["slab"] = c["slab"]
@@ -231,17 +243,37 @@ def _slab_rank(rank, size, port, q, n_total, steps):
     sim.close()
 
 
-def _run_slabs(size, n_total, steps):
+def _collect(procs, q, size, timeout=900):
+    """Results of `size` ranks; a rank that dies fails the test at once (and takes the
+    others with it) instead of leaving the parent in q.get()."""
+    import queue
+    import time
+    got, t0 = {}, time.time()
+    while len(got) < size:
+        try:
+            rank, res = q.get(timeout=1.0)
+            got[rank] = res
+        except queue.Empty:
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError("rank process(es) failed: exit codes %s after %.0f s"
+                                     % ([p.exitcode for p in procs], time.time() - t0))
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    return got
+
+
+def _run_slabs(size, n_total, steps, **kw):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_rank, args=(r, size, port, q, n_total, steps)) for r in range(size)]
+    procs = [ctx.Process(target=_slab_rank, args=(r, size, port, q, n_total, steps, kw)) for r in range(size)]
     [p.start() for p in procs]
-    got = dict(q.get(timeout=900) for _ in range(size))
-    [p.join(120) for p in procs]
-    assert all(p.exitcode == 0 for p in procs)
-    return got
+    return _collect(procs, q, size)
 
 
 def test_dam_break_slabs_two_gpus_match_one_gpu():
@@ -277,3 +309,149 @@ def test_dam_break_slabs_two_gpus_match_one_gpu():
             else:
                 errf = np.abs(a[far] - b[far]).max() / max(np.abs(a).max(), 1e-30)
                 assert errf <= 0.5 * tol, "rank %d field %s far from the cut: rel err %.3e" % (r, k, errf)
+
+
+# ---------------------------------------------------------------------------------------------
+# More than two ranks: an interior rank talks to two peers, and nothing about the counts is
+# special (round 1's states were lattices at rest whose halo counts were multiples of 4, which
+# hid a misaligned packed send buffer).
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _sync_rank(rank, size, port, q, seed):
+    """aqc_mpi_sync through the C-ABI on random masks: fields of 4, 8 and 16 bytes in that
+    order, odd element counts, every rank talks to every other one; then the plan path."""
+    import torch.distributed as dist
+    os.environ["AQC_MPI_VERIFY"] = "1"
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=size)
+    uid = [_lib.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = _lib.Context(rank, dims=3, h=1.0)
+    ctx.comm_init(rank, size, uid[0])
+    n = 4099 + 37 * rank   # (every rank's arrays must hold what it receives: ~n/size per peer)
+    rng = np.random.default_rng(seed + rank)
+    # ~1/3 of the elements travel; counts per destination are arbitrary (not multiples of 4)
+    mask_h = np.where(rng.random(n) < 0.33, rng.integers(0, size, n), rank).astype(np.uint32)
+    f4 = (np.arange(n) + 100000 * rank).astype(np.uint32)
+    f8 = rng.normal(size=(n, 2)).astype(np.float32)
+    f16 = rng.normal(size=(n, 4)).astype(np.float32)
+    out = {"mask0": mask_h.copy(), "f4_0": f4.copy(), "f8_0": f8.copy(), "f16_0": f16.copy()}
+    mask, a4, a8, a16 = ctx.array(mask_h), ctx.array(f4), ctx.array(f8), ctx.array(f16)
+    out["nrecv"] = ctx.mpi_sync(mask, [a4, a8, a16])
+    out.update(mask=mask.get(), f4=a4.get(), f8=a8.get(), f16=a16.get())
+    # ---- plan: a second call on the same mask content reuses the sort and the counts
+    dep = ctx.array(np.zeros(16, np.float32))
+    plan = ctx.mpi_sync_plan()
+    for it in range(3):
+        mask.set(mask_h)
+        a4.set(f4 + it)
+        a16.set(f16 * (it + 1))
+        if it == 2:
+            ctx.fill(dep, np.float32(1).tobytes())   # a dependency was written: full call again
+        out["nrecv_plan%d" % it] = ctx.mpi_sync(mask, [a4, a16], plan=plan, deps=[dep])
+        out["plan%d" % it] = dict(mask=mask.get(), f4=a4.get(), f16=a16.get())
+    out["stats"] = ctx.mpi_sync_stats(plan)
+    q.put((rank, out))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def _expected_sync(rank, size, masks, fields):
+    """MPISync.cpp:183-232: blocks packed at the front in process order, stable inside."""
+    parts = [[] for _ in fields]
+    m = []
+    for p in range(size):
+        if p == rank:
+            continue
+        sel = np.flatnonzero(masks[p] == rank)
+        for k, f in enumerate(fields):
+            parts[k].append(f[p][sel])
+        m += [p] * len(sel)
+    return [np.concatenate(x) for x in parts], np.array(m, np.uint32)
+
+
+@pytest.mark.parametrize("size", [2, 3, 4])
+def test_mpi_sync_random_masks(size):
+    if _n_gpus() < size:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (size, size))
+    import torch.multiprocessing as mp
+    mpx = mp.get_context("spawn")
+    q = mpx.Queue()
+    port = _free_port()
+    procs = [mpx.Process(target=_sync_rank, args=(r, size, port, q, 77)) for r in range(size)]
+    [p.start() for p in procs]
+    got = _collect(procs, q, size, 300)
+    masks = [got[r]["mask0"] for r in range(size)]
+    # block sizes that are not multiples of 4 elements (a 4-byte field followed by 16-byte ones)
+    assert any(int((masks[p] == r).sum()) % 4 for p in range(size) for r in range(size) if p != r)
+    for r in range(size):
+        g = got[r]
+        (e4, e8, e16), em = _expected_sync(r, size, masks, [[got[p][k] for p in range(size)]
+                                                             for k in ("f4_0", "f8_0", "f16_0")])
+        k = len(em)
+        assert g["nrecv"] == k, (r, k, g["nrecv"])
+        assert np.array_equal(g["mask"][:k], em) and np.all(g["mask"][k:] == r)
+        assert np.array_equal(g["f4"][:k], e4) and np.array_equal(g["f4"][k:], g["f4_0"][k:])
+        assert np.array_equal(g["f8"][:k], e8) and np.array_equal(g["f8"][k:], g["f8_0"][k:])
+        assert np.array_equal(g["f16"][:k], e16) and np.array_equal(g["f16"][k:], g["f16_0"][k:])
+        for it in range(3):
+            (p4, p16), _ = _expected_sync(r, size, masks, [[got[p]["f4_0"] + it for p in range(size)],
+                                                           [got[p]["f16_0"] * (it + 1) for p in range(size)]])
+            assert g["nrecv_plan%d" % it] == k
+            assert np.array_equal(g["plan%d" % it]["mask"][:k], em)
+            assert np.array_equal(g["plan%d" % it]["f4"][:k], p4), (r, it)
+            assert np.array_equal(g["plan%d" % it]["f16"][:k], p16), (r, it)
+        assert g["stats"] == dict(full=2, reused=1), g["stats"]
+
+
+def _match_rows(one, ranks):
+    """Rows of the 1-GPU run that correspond to every live fluid row of the N-GPU run.
+    Particles migrate, so ids are rank-local: the match goes through positions (two particles
+    are never closer than a fraction of dr; the runs differ by fp32 rounding)."""
+    from scipy.spatial import cKDTree
+    fl1 = np.flatnonzero(one["imove"] == 1)
+    tree = cKDTree(one["r"][fl1][:, :3].astype(np.float64))
+    out = []
+    for g in ranks:
+        fl = np.flatnonzero(g["imove"] == 1)
+        d, j = tree.query(g["r"][fl][:, :3].astype(np.float64))
+        out.append((fl, fl1[j], d))
+    return fl1, out
+
+
+@pytest.mark.parametrize("size", [3, 4])
+def test_dam_break_slabs_n_gpus_match_one_gpu(size):
+    """3 and 4 y-slabs of a JITTERED, moving dam break (halo and migration counts arbitrary;
+    particles cross the cuts during the run) against the same pipeline on one GPU: interior
+    ranks exchange with two peers, migrating particles land in buffer rows, every reused
+    mpi-sync plan is verified against its mask (AQC_MPI_VERIFY)."""
+    if _n_gpus() < size:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (size, size))
+    n_total, steps = 60000, 6
+    kw = dict(seed=5, jitter=0.3, uscale=2.0, whole=True, iter_midpoint_max=3)
+    one = _run_slabs(1, n_total, steps, **kw)[0]
+    many = _run_slabs(size, n_total, steps, **kw)
+    assert len({many[r]["dt"] for r in range(size)} | {one["dt"]}) == 1, "dt must be global"
+    fl1, matches = _match_rows(one, [many[r] for r in range(size)])
+    n_live = sum(len(m[0]) for m in matches)
+    assert n_live == len(fl1), "fluid particles lost or duplicated: %d vs %d" % (n_live, len(fl1))
+    assert len(np.unique(np.concatenate([m[1] for m in matches]))) == len(fl1)
+    h = one["h"]
+    # particles crossed the cuts: the ranks no longer hold the fluid they started with
+    assert any(len(matches[r][0]) != many[r]["n_fluid0"] for r in range(size)), "nothing migrated"
+    for r in range(size):
+        rows, rows1, d = matches[r]
+        assert d.max() < 1e-4 * h, "rank %d: a particle is %.3e away from its 1-GPU twin" % (r, d.max())
+        for k, tol in (("r", 2e-6), ("u", 2e-4), ("rho", 5e-5), ("dudt", 5e-4)):
+            a = one[k][rows1].astype(np.float64)
+            b = many[r][k][rows].astype(np.float64)
+            err = np.abs(a - b).max() / max(np.abs(one[k][fl1]).max(), 1e-30)
+            assert err <= tol, "rank %d field %s: rel err %.3e" % (r, k, err)
+        # the in-loop halo sync sorted and counted once per step and reused that plan afterwards
+        calls = many[r]["sync_tools"].get("mpi neighs sync", 0)
+        st = many[r]["plan0"]
+        assert st["full"] == steps and st["full"] + st["reused"] == calls and st["reused"] >= steps, (st, calls)
