@@ -172,8 +172,9 @@ def add_tool_after(txt, after, tool_xml):
 def multi_device_fixes(txt):
     """What this repository changes in the reference's MPI example pipeline so that an
     N-device run is a consistent simulation: the halo mask is taken after
-    the sort (halo_mask_after_sort) and dt / the midpoint residual are all-reduced, so
-    every rank advances with the same time step and leaves the inner loop together.
+    the sort (halo_mask_after_sort), dt / the midpoint residual are all-reduced, so
+    every rank advances with the same time step and leaves the inner loop together, and
+    `remove` sees the outgoing mask ((iii) below).
     When the halo exchange sits outside the midpoint loop (the example's include order,
     TODO at cfd/MPI.xml:21-23) it is moved inside, right after "midpoint eos": the
     reference exchanges u and rho of the halo once per step and iterates on stale
@@ -181,6 +182,19 @@ def multi_device_fixes(txt):
     to the cuts; refreshed every sub-iteration the two agree to fp32 summation order."""
     txt = halo_mask_after_sort(txt)
     order = [m.group(1) for m in re.finditer(r'<Tool [^>]*name="([^"]*)"', txt)]
+    # (iii) cfd/MPI.cl::remove (:176-199) decides by mpi_local_mask which LOCAL rows have left, but
+    # mpi-sync has rewritten that mask by then (MPISync.cpp:222-223: own rank everywhere, the
+    # sender's rank over what arrived): rows 0 .. n_received-1 are parked instead of the rows that
+    # were sent, so every migration duplicates a particle on the receiver and destroys an
+    # unrelated one on the sender.  The outgoing mask is kept and handed back for `remove`.
+    if "mpi local sync" in order and "mpi remove" in order and "mpi append" in order:
+        txt = txt.replace("    </Variables>",
+                          '        <Variable name="mpi_sent_mask" type="size_t*" length="n_radix" />\n'
+                          "    </Variables>", 1)
+        txt = add_tool_after(txt, "mpi copy", '<Tool action="add" name="mpi sent mask backup" type="copy" '
+                             'once="false" in="mpi_local_mask" out="mpi_sent_mask" />')
+        txt = add_tool_after(txt, "mpi append", '<Tool action="add" name="mpi sent mask restore" type="copy" '
+                             'once="false" in="mpi_sent_mask" out="mpi_local_mask" />')
     if "midpoint eos" in order and "mpi neighs sync" in order and \
             order.index("mpi neighs sync") < order.index("midpoint loop"):
         chain = ["mpi neighs mask reset"]

@@ -90,9 +90,10 @@ def dam_break(dims=3, n_side=12, hfac=2.0, seed=1234, jitter=0.2, n_sensors=3, n
     )
 
 
-def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0):
+def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0, uscale=0.01, jitter=0.0):
     """BASELINE config 5 shape: uniform lattice dr = 1, all fluid, rho = refd,
-    u = 0.01*cs*U(-1,1); no boundary (the ref has no periodic BC)."""
+    u = 0.01*cs*U(-1,1); no boundary (the ref has no periodic BC).  `uscale` / `jitter` (tests):
+    faster particles on off-lattice positions, so that they cross the cuts of a slab run."""
     rng = np.random.default_rng(seed)
     V = vs(dims)
     ax = [np.arange(n_side, dtype=np.float32) for _ in range(dims)]
@@ -101,7 +102,9 @@ def lattice(n_side, hfac=2.0, dims=3, seed=1234, cs=40.0):
     r = np.zeros((N, V), np.float32)
     r[:, :dims] = gpos + 0.5
     u = np.zeros((N, V), np.float32)
-    u[:, :dims] = (0.01 * cs * rng.uniform(-1, 1, (N, dims))).astype(np.float32)
+    u[:, :dims] = (uscale * cs * rng.uniform(-1, 1, (N, dims))).astype(np.float32)
+    if jitter:
+        r[:, :dims] += (jitter * np.random.default_rng(seed + 1).uniform(-1, 1, (N, dims))).astype(np.float32)
     refd = np.float32(1000.0)
     z = np.zeros(V, np.float32)
     return dict(

@@ -73,6 +73,8 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFree(ctx->cell_cls);
     cudaFree(ctx->pack_rows);
     cudaFree(ctx->pc.masks);
+    cudaFree(ctx->pc.chunks);
+    cudaFree(ctx->pc.cnt);
     cudaFree(ctx->pc.pass_tab);
     cudaFree(ctx->pc.ctl);
     cudaFreeHost(ctx->pc.ctl_host);
@@ -458,6 +460,7 @@ extern "C" int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint6
     if (hits)
         *hits = ctx->pc.hits;
     if (bytes)
-        *bytes = (uint64_t)ctx->pc.cap_rounds * AQC_PC_ROUND_BYTES;
+        *bytes = ctx->pc.lists ? (uint64_t)ctx->pc.chunks_bytes + (uint64_t)ctx->pc.cap_rounds * 7 * 32
+                               : (uint64_t)ctx->pc.cap_rounds * AQC_PC_ROUND_BYTES;
     return AQC_OK;
 }

@@ -30,10 +30,17 @@ struct aqc_pair_cache {
     uint32_t icls_want = 0, jcls_want = 0; // union of the classes asked for so far
     uint32_t* masks = nullptr;
     size_t cap_rounds = 0;
+    // neighbour lists (sweep.cuh, v4 engine): the default form of the cache; AQC_PAIR_LISTS=0 keeps
+    // the hit masks of round 1 (MODE 1 / 2)
+    bool lists = true;
+    void* chunks = nullptr;    // uint2 [CTA][consumer warp][capc][32]
+    size_t chunks_bytes = 0;
+    uint8_t* cnt = nullptr;    // [round][consumer warp][32]
+    uint32_t capc = 0;
     uint32_t* pass_tab = nullptr;
     size_t pass_cap = 0;
-    unsigned long long* ctl = nullptr;      // device [2]
-    unsigned long long* ctl_host = nullptr; // pinned [2]
+    unsigned long long* ctl = nullptr;      // device [4]
+    unsigned long long* ctl_host = nullptr; // pinned [4]
     uint64_t builds = 0, hits = 0;
     // a build costs about half a sweep: pipelines whose geometry changes before a second sweep
     // reads the masks (served < 2, three times in a row) go without for a while

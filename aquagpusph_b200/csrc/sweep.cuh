@@ -517,12 +517,22 @@ __device__ __forceinline__ uint32_t s3_run_end(const uint32_t* __restrict__ icel
 #define S3_MASK_ST(p, v) (*(p) = (v))
 #endif
 struct S3Cache {
-    const float4* rows = nullptr; // MODE 2: the j rows of every particle, packed by s3_pack_kernel
+    const float4* rows = nullptr; // MODE 2 / v4: the j rows of every particle, packed by s3_pack_kernel
     uint32_t* masks = nullptr;
     uint32_t* pass_tab = nullptr;
     unsigned long long* ctl = nullptr;
     uint32_t cap_rounds = 0;
+    // neighbour lists (MODE 3 builds them, sweep4_kernel reads them; see "v4 engine" below)
+    uint2* chunks = nullptr; // [CTA][consumer warp][capc][32 lanes]: 4 entries of 16 bits
+    uint8_t* cnt = nullptr;  // [round][consumer warp][32 lanes]: chunks of the lane in that round
+    uint32_t capc = 0;       // chunks a lane's list can hold
 };
+// An entry of a neighbour list is the byte offset of the candidate's row inside ONE row array of
+// the reader's ring (S4_K rounds of S3_TILES tiles of 32 rows of 16 bytes); S4_NULL addresses the
+// extra row behind the ring, whose weights are zero (the padding of a lane's last chunk in a round)
+constexpr int S4_K = 3;
+constexpr uint32_t S4_ROWS = S4_K * S3_TILES_N * 32;
+constexpr uint32_t S4_NULL = S4_ROWS * 16;
 constexpr int S3_MAXPASS = 32;
 constexpr uint32_t S3_NOPASS = 0xFFFFFFFFu;
 
@@ -590,7 +600,8 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 
     // (kernels that never read the cache group their own i particles only: a boundary kernel
     // does not walk the neighbourhood of a CTA's fluid particles)
-    constexpr bool ALLPASS = P::CACHE || MODE == 1;
+    uint32_t lc = 0; // MODE 3: chunks this lane has written to its list (a lane works in one pass)
+    constexpr bool ALLPASS = P::CACHE || MODE == 1 || MODE == 3;
     bool pending = (ALLPASS ? valid : active) && c_i < ll.nw;
     for (uint32_t npass = 0;; npass++) {
         // ---- the group of this pass: first pending particle and its x-row neighbours
@@ -693,7 +704,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
             s_o[0] = 0.5f * (s_o[0] + s_o[3]);
             s_o[1] = 0.5f * (s_o[1] + s_o[4]);
             s_o[2] = (P::DIMS == 3) ? 0.5f * (s_o[2] + s_o[5]) : 0.f;
-            if constexpr (MODE == 1) { // rounds of this pass in the mask array
+            if constexpr (MODE == 1 || MODE == 3) { // rounds of this pass in the mask / count array
                 uint32_t base = S3_NOPASS;
                 if (npass < (uint32_t)S3_MAXPASS) {
                     const unsigned long long b = atomicAdd(pc.ctl, (unsigned long long)nrounds);
@@ -989,6 +1000,72 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                     __syncwarp();
                     if (lane == 0)
                         mbar_arrive(empty_a + 8 * rk);
+                } else if constexpr (MODE == 3) {
+                    // ---- filter, exact test of every selected candidate, and the survivors go
+                    // to the lane's neighbour list in visiting order (tiles ascending, candidates
+                    // ascending): 4 entries per chunk, the last chunk of the round padded
+                    uint32_t acc0 = 0, acc1 = 0, nn = 0, nch = 0;
+                    uint2* const lbase = pc.chunks + ((size_t)(blockIdx.x * S3_CWARPS + cw) * pc.capc) * 32 + lane;
+                    const uint32_t ebase = (r % (uint32_t)S4_K) * (W * 512u);
+                    auto flush = [&]() {
+                        if (lc < pc.capc)
+                            __stcs(lbase + (size_t)lc * 32, make_uint2(acc0, acc1));
+                        lc++;
+                        nch++;
+                        acc0 = acc1 = nn = 0;
+                    };
+#pragma unroll 1
+                    for (int w2 = 0; w2 < W; w2++) {
+                        uint32_t m = 0;
+                        const uint32_t cnt = t_cnt[rk][w2];
+                        if (work && cnt) {
+                            const uint32_t rel = t_rel[rk][w2] - a_i;
+                            const uint32_t pm = 0xFFFFFFFFu << (32u - t_n1[rk][w2]);
+                            const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
+                            if (okm) {
+                                const float4* T = sT + (rk * W + w2) * 32;
+                                if (cnt > 16)
+                                    m = test_tile<16>(T, X2, Y2, Z2, C2);
+                                else if (cnt > 8)
+                                    m = test_tile<8>(T, X2, Y2, Z2, C2);
+                                else
+                                    m = test_tile<4>(T, X2, Y2, Z2, C2);
+                                m &= okm;
+                            }
+                        }
+                        const float4* const rowp = sJ + (size_t)(rk * W + w2) * SLOT4;
+                        while (m) {
+                            const uint32_t f = 31u - (uint32_t)__clz(m);
+                            m ^= 1u << f;
+                            const uint32_t k = 31u - f;
+                            const float4 A = rowp[k];
+                            // the readers' P::test, to the letter
+                            if (dist2<P::DIMS>(A.x - st.x, A.y - st.y, A.z - st.z) < p.cut2) {
+                                const uint32_t e = ebase + (uint32_t)w2 * 512u + k * 16u;
+                                const uint32_t sh = (nn & 1u) * 16u;
+                                if (nn & 2u)
+                                    acc1 |= e << sh;
+                                else
+                                    acc0 |= e << sh;
+                                if (++nn == 4u)
+                                    flush();
+                            }
+                        }
+                    }
+                    if (nn) {
+                        if (nn == 1u)
+                            acc0 |= S4_NULL << 16;
+                        if (nn <= 2u)
+                            acc1 = S4_NULL | (S4_NULL << 16);
+                        else
+                            acc1 |= S4_NULL << 16;
+                        flush();
+                    }
+                    if (mbase != S3_NOPASS)
+                        pc.cnt[((size_t)(mbase + r) * S3_CWARPS + cw) * 32 + lane] = (uint8_t)nch;
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(empty_a + 8 * rk);
                 } else {
                     if (work) {
                         if constexpr (MODE == 2) {
@@ -1074,6 +1151,299 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
         }
 #endif
     }
+    if constexpr (MODE == 3) {
+        // the longest list of the warp: beyond capc the host grows the lists and builds again
+        const uint32_t lmax = __reduce_max_sync(0xffffffffu, lc);
+        if (lane == 0 && !producer && lmax)
+            atomicMax(pc.ctl + 2, (unsigned long long)lmax);
+    }
+    if (active)
+        p.store_i(st, i);
+}
+
+// ---------------------------------------------------------------------------
+// v4 engine: the readers of the neighbour LISTS (pair cache, MODE 3 builder above).
+//
+// What the mask-reading sweeps (MODE 2) spent per pair besides the pair body, by their SASS
+// (profiles/r1_ncu_fused_fluid_v4_maskcache_lines.txt: 157 instructions per two hits, 93 of them
+// floating point): the exact re-test of every cached hit (7 + the kill selects), the decoding
+// of the hit masks (find-leading-one, shift, xor, address: 4), the per-lane FIFO of (mask, slot)
+// entries in shared memory (push, pick, wrap-around: ~10 issued whether they are predicated off
+// or not), and the branches around the second hit of an iteration.  None of that depends on the
+// kernel, so the builder does it once per geometry: it applies the exact test and stores, per
+// lane, the rows to visit as a list of 16-bit ring offsets in visiting order, in chunks of four
+// (the last chunk of a ring round padded with the offset of a zero-weight row), plus the number
+// of chunks per (lane, round).  A reader then runs, per chunk, 2 integer instructions to split
+// the two words, 4 x NJ4 LDS.128 at [ring + offset] (the ring is static shared memory: the base
+// is an immediate) and four pair bodies back to back -- no test, no branch, four independent
+// dependency chains.  The lane-balancing of v3 stays, at chunk granularity: a warp takes a
+// chunk only while every working lane has one from the rounds in the ring, and a lane finishes
+// the oldest round's chunks before the warp releases it.
+// Same pairs in the same order as MODE 0 / 2 (the padding rows add exactly +-0).
+#ifndef S4_MINB
+#define S4_MINB 3 // CTAs per SM the register allocation aims at
+#endif
+template <class P>
+__global__ void __launch_bounds__(S3_THREADS, S4_MINB)
+sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
+{
+    constexpr int W = S3_TILES, K = S4_K;
+    __shared__ float4 ring[P::NJ4][S4_ROWS + 1];
+    __shared__ uint32_t e_begin[S3_MAXE], e_end[S3_MAXE];
+    __shared__ uint32_t s_ball[S3_WARPS], s_c0, s_span, s_anywork, s_maxk, s_base;
+    __shared__ unsigned long long s_full[K], s_empty[K];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool producer = warp == 0;
+    const int cw = warp - 1;
+    const uint32_t full_a = (uint32_t)__cvta_generic_to_shared(s_full);
+    const uint32_t empty_a = (uint32_t)__cvta_generic_to_shared(s_empty);
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(&ring[0][0]); // (the producer's copies)
+    constexpr uint32_t QSTRIDE = (S4_ROWS + 1) * 16; // bytes between the row arrays
+    const uint32_t i = blockIdx.x * (uint32_t)S3_PARTICLES + (uint32_t)(tid - 32);
+    const bool valid = !producer && i < ll.N;
+    const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
+    const uint32_t c_i = valid ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    typename P::IState st;
+    st.x = st.y = st.z = 0.f;
+    if (active)
+        p.load_i(st, i);
+    if (tid == 32) {
+        // the padding row: a finite position next to the CTA's particles, every weight zero
+        const float4 r0 = pc.rows[min(blockIdx.x * (uint32_t)S3_PARTICLES, ll.N - 1)];
+        ring[0][S4_ROWS] = make_float4(P::j_live(r0) ? r0.x : 0.f, r0.y, r0.z, 0.f);
+#pragma unroll
+        for (int q = 1; q < P::NJ4; q++)
+            ring[q][S4_ROWS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
+    // this lane's list: chunk c at lp0[c * 32]
+    const uint2* lp = pc.chunks + ((size_t)(blockIdx.x * S3_CWARPS + (producer ? 0 : cw)) * pc.capc) * 32 + lane;
+
+    bool pending = valid && c_i < ll.nw;
+    for (uint32_t npass = 0;; npass++) {
+        // ---- the group of this pass, exactly as the builder formed it (sweep3_kernel)
+        const uint32_t pb = __ballot_sync(0xffffffffu, pending);
+        if (lane == 0)
+            s_ball[warp] = pb;
+        if (tid == 0) {
+            s_span = 0;
+            s_anywork = 0;
+            s_maxk = 0;
+            for (int k = 0; k < K; k++) {
+                if (npass) {
+                    mbar_inval(full_a + 8 * k);
+                    mbar_inval(empty_a + 8 * k);
+                }
+                mbar_init(full_a + 8 * k, 1);
+                mbar_init(empty_a + 8 * k, S3_CWARPS);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        int first = -1;
+#pragma unroll
+        for (int w = S3_WARPS - 1; w >= 0; w--)
+            if (s_ball[w])
+                first = w * 32 + __ffs(s_ball[w]) - 1;
+        if (first < 0)
+            break;
+        if (tid == first)
+            s_c0 = c_i;
+        __syncthreads();
+        const uint32_t c0 = s_c0;
+        const uint32_t a_i = c_i - c0;
+        const bool mine = pending && (a_i <= (uint32_t)S3_SPAN);
+        const bool work = mine && active;
+        const uint32_t mine_w = __ballot_sync(0xffffffffu, mine);
+        const uint32_t work_w = __ballot_sync(0xffffffffu, work);
+        if (mine_w) {
+            const uint32_t sp = __reduce_max_sync(0xffffffffu, mine ? a_i : 0u);
+            if (lane == 0)
+                atomicMax(&s_span, sp);
+        }
+        if (work_w && lane == 0)
+            s_anywork = 1u;
+        pending = pending && !mine;
+        __syncthreads();
+        if (!s_anywork)
+            continue; // (the builder's i classes include this kernel's: it may have worked here)
+        const uint32_t len = s_span + 3u, nparts = (len + 1u) / 2u;
+        const uint32_t NE = NROWS * nparts;
+        if ((uint32_t)tid < NE) {
+            const uint32_t row = tid / nparts, part = tid - row * nparts;
+            const int cy = (int)(row % 3u) - 1, cz = (P::DIMS == 3) ? (int)(row / 3u) - 1 : 0;
+            const uint32_t lo = c0 + (uint32_t)cy * ll.nx + (uint32_t)cz * ll.nx * ll.ny - 1u + 2u * part;
+            const uint32_t wid = (2u * part + 1u < len) ? 1u : 0u;
+            uint32_t b = __ldg(ll.ihoc + lo);
+            if (wid)
+                b = min(b, __ldg(ll.ihoc + lo + 1u));
+            uint32_t en = b;
+            if (b < ll.N)
+                en = s3_run_end(ll.icell, b, ll.N, lo, wid);
+            else
+                b = en = ll.N;
+            e_begin[tid] = b;
+            e_end[tid] = en;
+            if (en > b)
+                atomicMax(&s_maxk, (en - b + 31u) / 32u);
+        }
+        __syncthreads();
+        const uint32_t maxk = s_maxk;
+        const uint32_t nrounds = (maxk * NE + W - 1) / W;
+        if (tid == 0) {
+            const uint32_t base = (npass < (uint32_t)S3_MAXPASS)
+                                      ? pc.pass_tab[(size_t)blockIdx.x * S3_MAXPASS + npass]
+                                      : S3_NOPASS;
+            if (base == S3_NOPASS && nrounds) // the host never hands over incomplete lists
+                __trap();
+            s_base = base;
+        }
+        __syncthreads();
+
+        if (producer) {
+            // one elected lane per tile: NJ4 bulk copies from the packed rows into the ring slot,
+            // completing on the round's `full` barrier
+            uint32_t rk = 0, use = 0;
+            for (uint32_t r = 0; r < nrounds; r++) {
+                if (use) {
+                    uint32_t spins = 0;
+                    while (!__all_sync(0xffffffffu, mbar_wait(empty_a + 8 * rk, (use - 1) & 1u))) {
+                        if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
+                            __trap();
+                        __nanosleep(S3_SLEEP_P);
+                    }
+                }
+                uint32_t bytes = 0;
+                if (lane < W) {
+                    const uint32_t tn = r * W + (uint32_t)lane;
+                    const uint32_t k = tn / NE, e = tn - k * NE;
+                    if (k < maxk) {
+                        const uint32_t bg = e_begin[e] + 32u * k, en = e_end[e];
+                        if (bg < en) {
+                            bytes = min(32u, en - bg) * 16u;
+                            const uint32_t dst = ring_a + (rk * W + (uint32_t)lane) * 512u;
+#pragma unroll
+                            for (int q = 0; q < P::NJ4; q++)
+                                bulk_g2s(dst + q * QSTRIDE, pc.rows + (size_t)q * ll.N + bg, bytes, full_a + 8 * rk);
+                            bytes *= P::NJ4;
+                        }
+                    }
+                }
+                bytes = __reduce_add_sync(0xffffffffu, bytes);
+                if (lane == 0) {
+                    if (bytes)
+                        mbar_arrive_expect_tx(full_a + 8 * rk, bytes);
+                    else
+                        mbar_arrive(full_a + 8 * rk);
+                }
+                if (++rk == (uint32_t)K) {
+                    rk = 0;
+                    use++;
+                }
+            }
+        } else {
+            const uint8_t* cp = pc.cnt + ((size_t)s_base * S3_CWARPS + cw) * 32 + lane;
+            // chunks of the lane from the oldest round still in the ring / from the newest one
+            uint32_t a_old = 0, a_new = 0;
+            uint32_t cn = (work && nrounds) ? (uint32_t)__ldg(cp) : 0u;
+            // two chunks ahead of the one being worked on (reads past the end of a list stay
+            // inside the allocation and are never used)
+            uint2 c0v = make_uint2(0u, 0u), c1v = make_uint2(0u, 0u);
+            if (work) {
+                c0v = __ldg(lp);
+                c1v = __ldg(lp + 32);
+                lp += 64;
+            }
+            // policies whose body returns early for some i particles (the fused pass: Shepard serves
+            // boundary elements too) offer body_all(), the same terms without the branch: a warp
+            // with at least one lane that needs everything runs it for all its lanes (what the
+            // others accumulate is never stored)
+            bool whole = false;
+            if constexpr (P::HAS_BODY_ALL)
+                whole = __any_sync(0xffffffffu, work && p.needs_all(st));
+            const char* const ring_c = reinterpret_cast<const char*>(&ring[0][0]);
+            auto take = [&]() { // one chunk: four rows, four pair bodies
+                const uint2 e = c0v;
+                c0v = c1v;
+                c1v = __ldg(lp);
+                lp += 32;
+                const uint32_t o0 = e.x & 0xFFFFu, o1 = e.x >> 16, o2 = e.y & 0xFFFFu, o3 = e.y >> 16;
+                float4 v0[P::NJ4], v1[P::NJ4], v2[P::NJ4], v3[P::NJ4];
+#pragma unroll
+                for (int q = 0; q < P::NJ4; q++) {
+                    v0[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o0);
+                    v1[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o1);
+                    v2[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o2);
+                    v3[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o3);
+                }
+                if constexpr (P::HAS_BODY_ALL) {
+                    if (whole) {
+                        p.body_all(st, v0);
+                        p.body_all(st, v1);
+                        p.body_all(st, v2);
+                        p.body_all(st, v3);
+                    } else {
+                        p.body(st, v0, 1);
+                        p.body(st, v1, 1);
+                        p.body(st, v2, 1);
+                        p.body(st, v3, 1);
+                    }
+                } else {
+                    p.body(st, v0, 1);
+                    p.body(st, v1, 1);
+                    p.body(st, v2, 1);
+                    p.body(st, v3, 1);
+                }
+                if (a_old)
+                    a_old--;
+                else
+                    a_new--;
+            };
+            uint32_t rk = 0, use = 0, rq = 0;
+            for (uint32_t r = 0; r < nrounds; r++) {
+                {
+                    uint32_t spins = 0;
+                    while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u))) {
+                        if (++spins > (1u << 28))
+                            __trap();
+                        __nanosleep(S3_SLEEP_C);
+                    }
+                }
+                a_new = cn;
+                if (work && r + 1 < nrounds)
+                    cn = (uint32_t)__ldg(cp + (size_t)(r + 1) * (S3_CWARPS * 32));
+                if (work) {
+                    // ---- chunks, while every working lane of the warp has one
+                    while (__ballot_sync(work_w, (a_old | a_new) != 0u) == work_w)
+                        take();
+                }
+                __syncwarp();
+                if (r >= 1) {
+                    // ---- release round r - 1: its chunks are the oldest of every list
+                    while (__any_sync(0xffffffffu, a_old != 0u)) {
+                        if (a_old)
+                            take();
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(empty_a + 8 * rq);
+                    rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
+                }
+                a_old = a_new; // (everything older has been consumed)
+                a_new = 0;
+                if (++rk == (uint32_t)K) {
+                    rk = 0;
+                    use++;
+                }
+            }
+            while (__any_sync(0xffffffffu, a_old != 0u)) {
+                if (a_old)
+                    take();
+            }
+        }
+        __syncthreads();
+    }
     if (active)
         p.store_i(st, i);
 }
@@ -1132,14 +1502,7 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
             };
             if constexpr (P::CACHE) {
                 if (cached) {
-                    K = aqc_sweep_ring2();
-                    const size_t smem = smem_of(K, S3_RTILES, false);
-                    static size_t configured2 = 0; // per instantiation
-                    if (smem > configured2) {
-                        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2, S3_RTILES>,
-                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        configured2 = smem;
-                    }
+                    // the j rows of every particle, packed for the bulk copies of the readers
                     const size_t need = (size_t)ll.N * P::NJ4 * sizeof(float4);
                     if (need > ctx->pack_cap) {
                         if (ctx->pack_rows) {
@@ -1154,6 +1517,21 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
                     s3_pack_kernel<P><<<aqc_blocks(ll.N, 256), 256, 0, ctx->stream>>>(p, ll.N, (float4*)ctx->pack_rows);
                     AQC_LAUNCH_CHECK(ctx);
                     pc.rows = (const float4*)ctx->pack_rows;
+                }
+                if (cached == 2) {
+                    sweep4_kernel<P><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, 0, ctx->stream>>>(p, ll, pc);
+                    AQC_LAUNCH_CHECK(ctx);
+                    return AQC_OK;
+                }
+                if (cached) {
+                    K = aqc_sweep_ring2();
+                    const size_t smem = smem_of(K, S3_RTILES, false);
+                    static size_t configured2 = 0; // per instantiation
+                    if (smem > configured2) {
+                        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2, S3_RTILES>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        configured2 = smem;
+                    }
                     sweep3_kernel<P, 2, S3_RTILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(
                         p, ll, K, pc);
                     AQC_LAUNCH_CHECK(ctx);

@@ -175,6 +175,8 @@ struct PBase {
     // = classes (aqc_cls_bit) its i and j particles can belong to; they must cover i_active()
     // and the candidates stage_j() leaves alive.
     static constexpr bool CACHE = false;
+    // v4 engine: body_all() / needs_all() exist (see PFusedFluid)
+    static constexpr bool HAS_BODY_ALL = false;
     uint32_t icls() const { return 0xFFu; }
     uint32_t jcls() const { return 0xFFu; }
 };
@@ -1336,7 +1338,14 @@ struct PFusedFluid : PBase {
     {
         return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
     }
-    __device__ void body(IState& s, const float4* row, int stride) const
+    // v4 engine: every term without the early return of the non-fluid i particles (their
+    // u = p = 0 give finite terms that store_i never writes)
+    static constexpr bool HAS_BODY_ALL = SHEP;
+    __device__ bool needs_all(const IState& s) const { return s.fluid; }
+    __device__ void body_all(IState& s, const float4* row) const { body_t<false>(s, row, 1); }
+    __device__ void body(IState& s, const float4* row, int stride) const { body_t<true>(s, row, stride); }
+    template <bool EARLY>
+    __device__ __forceinline__ void body_t(IState& s, const float4* row, int stride) const
     {
         const float4 A = row[0];
         const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
@@ -1346,8 +1355,10 @@ struct PFusedFluid : PBase {
         if constexpr (SHEP) {
             const float t2 = t * t;
             s.sh += (1.f + 2.f * q) * (t2 * t2) * (A.w * cWF); // cW m_j/rho_j from the staged cF m_j/rho_j
-            if (!s.fluid)
-                return;
+            if constexpr (EARLY) {
+                if (!s.fluid)
+                    return;
+            }
         }
         const float4 B = row[stride];
         const float fr = (t * t) * (t * A.w); // kernelF(q)*CONF*m_j / rho_j
@@ -1459,27 +1470,47 @@ int pc_build(aqc_ctx* ctx, const LLParams& ll, int K)
     pc.pass_tab = c.pass_tab;
     pc.ctl = c.ctl;
     pc.cap_rounds = (uint32_t)c.cap_rounds;
+    pc.chunks = (uint2*)c.chunks;
+    pc.cnt = c.cnt;
+    pc.capc = c.capc;
     const size_t NS = (size_t)K * S3_TILES;
     const size_t smem = (NS * 32 + NS * 32) * sizeof(float4) + S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
-    static size_t configured = 0;
-    if (smem > configured) {
+    const unsigned grid = aqc_blocks(ll.N, S3_PARTICLES);
+    if (c.lists) {
+        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 3, S3_TILES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sweep3_kernel<PMaskBuild<D>, 3, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    } else {
         AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 1, S3_TILES>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        sweep3_kernel<PMaskBuild<D>, 1, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
     }
-    sweep3_kernel<PMaskBuild<D>, 1, S3_TILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
     AQC_LAUNCH_CHECK(ctx);
     return AQC_OK;
 }
 
 } // namespace
 
-// 1: *out describes masks that are valid for this sweep; 0: the sweep has to filter; < 0: error
+// 1: *out describes hit masks that are valid for this sweep, 2: neighbour lists; 0: the sweep has
+// to filter; < 0: error
 int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2,
                    const LLParams& ll, uint32_t icls, uint32_t jcls, int K, S3Cache* out)
 {
     aqc_pair_cache& c = ctx->pc;
     if (!c.enabled || ((icls | jcls) & ~31u) || ll.icell_i != ll.icell || ll.cls)
+        return 0;
+    {
+        static int lists_env = -1;
+        if (lists_env < 0) {
+            const char* e = getenv("AQC_PAIR_LISTS");
+            lists_env = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        if (!c.builds)
+            c.lists = lists_env == 1;
+    }
+    // a list holds the pairs that passed the exact test and nothing else: a reader whose j set
+    // differs from the one the lists were made for cannot use them (the masks can, by re-testing)
+    if (c.lists && c.jcls_want && jcls != c.jcls_want)
         return 0;
     const bool same = c.valid && c.r == r && c.imove == imove && c.icell == ll.icell && c.ihoc == ll.ihoc &&
                       c.N == ll.N && c.nx == ll.nx && c.ny == ll.ny && c.nz == ll.nz && c.nw == ll.nw &&
@@ -1508,8 +1539,8 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
         c.dims = dims; c.cut2 = cut2;
         const size_t nblk = aqc_blocks(ll.N, S3_PARTICLES);
         if (!c.ctl) {
-            AQC_CUDA(ctx, cudaMalloc(&c.ctl, 2 * sizeof(unsigned long long)));
-            AQC_CUDA(ctx, cudaMallocHost(&c.ctl_host, 2 * sizeof(unsigned long long)));
+            AQC_CUDA(ctx, cudaMalloc(&c.ctl, 4 * sizeof(unsigned long long)));
+            AQC_CUDA(ctx, cudaMallocHost(&c.ctl_host, 4 * sizeof(unsigned long long)));
         }
         if (nblk * S3_MAXPASS > c.pass_cap) {
             if (c.pass_tab)
@@ -1519,41 +1550,71 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
             AQC_CUDA(ctx, cudaMalloc(&c.pass_tab, nblk * S3_MAXPASS * sizeof(uint32_t)));
             c.pass_cap = nblk * S3_MAXPASS;
         }
+        // bytes of one round: hit masks of every (tile, lane), or one chunk count per lane
+        const size_t round_bytes = c.lists ? (size_t)S3_CWARPS * 32 : (size_t)(S3_TILES * S3_CWARPS * 32) * sizeof(uint32_t);
+        void** rounds_buf = c.lists ? (void**)&c.cnt : (void**)&c.masks;
+        auto no_room = [&]() { // no room next to the problem: the sweeps keep filtering
+            (void)cudaGetLastError();
+            c.cooldown = 0xFFFFFFFFu;
+            return 0;
+        };
         size_t want = c.cap_rounds ? c.cap_rounds : nblk * (dims == 3 ? 40 : 12);
+        uint32_t want_capc = c.capc ? c.capc : (dims == 3 ? 272u : 72u);
         for (int attempt = 0;; attempt++) {
             if (want > c.cap_rounds) {
-                if (c.masks) {
+                if (*rounds_buf) {
                     AQC_SYNC(ctx);
-                    AQC_CUDA(ctx, cudaFree(c.masks));
+                    AQC_CUDA(ctx, cudaFree(*rounds_buf));
                 }
-                c.masks = nullptr;
+                *rounds_buf = nullptr;
                 c.cap_rounds = 0;
                 if (want >= 0xFFFFFFF0ull)
                     return 0; // beyond the 32-bit round index: no cache
-                if (cudaMalloc(&c.masks, want * (size_t)(S3_TILES * S3_CWARPS * 32) * sizeof(uint32_t)) !=
-                    cudaSuccess) {
-                    // no room for the masks next to the problem: the sweeps keep filtering
-                    (void)cudaGetLastError();
-                    c.masks = nullptr;
-                    c.cooldown = 0xFFFFFFFFu;
-                    return 0;
+                if (cudaMalloc(rounds_buf, want * round_bytes) != cudaSuccess) {
+                    *rounds_buf = nullptr;
+                    return no_room();
                 }
                 c.cap_rounds = want;
             }
-            AQC_CUDA(ctx, cudaMemsetAsync(c.ctl, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            if (c.lists) {
+                // (two chunk rows of slack: the readers load two chunks ahead)
+                const size_t need = (nblk * S3_CWARPS * (size_t)want_capc + 2) * 32 * sizeof(uint2);
+                if (need > c.chunks_bytes || want_capc != c.capc) {
+                    if (need > c.chunks_bytes) {
+                        if (c.chunks) {
+                            AQC_SYNC(ctx);
+                            AQC_CUDA(ctx, cudaFree(c.chunks));
+                        }
+                        c.chunks = nullptr;
+                        c.chunks_bytes = 0;
+                        if (cudaMalloc(&c.chunks, need) != cudaSuccess) {
+                            c.chunks = nullptr;
+                            return no_room();
+                        }
+                        c.chunks_bytes = need;
+                    }
+                    c.capc = want_capc;
+                }
+            }
+            AQC_CUDA(ctx, cudaMemsetAsync(c.ctl, 0, 4 * sizeof(unsigned long long), ctx->stream));
             AQC_CUDA(ctx, cudaMemsetAsync(c.pass_tab, 0xFF, nblk * S3_MAXPASS * sizeof(uint32_t), ctx->stream));
             const int rc = (dims == 3) ? pc_build<3>(ctx, ll, K) : pc_build<2>(ctx, ll, K);
             if (rc)
                 return rc;
-            AQC_CUDA(ctx, cudaMemcpyAsync(c.ctl_host, c.ctl, 2 * sizeof(unsigned long long),
+            AQC_CUDA(ctx, cudaMemcpyAsync(c.ctl_host, c.ctl, 4 * sizeof(unsigned long long),
                                           cudaMemcpyDeviceToHost, ctx->stream));
             AQC_SYNC(ctx);
-            if (c.ctl_host[0] <= c.cap_rounds)
+            const bool rounds_ok = c.ctl_host[0] <= c.cap_rounds;
+            const bool lists_ok = !c.lists || c.ctl_host[2] <= c.capc;
+            if (rounds_ok && lists_ok)
                 break;
-            if (attempt)
-                return aqc_fail(ctx, AQC_ERR_CUDA, "pair-mask cache: %llu rounds do not fit %zu after growing",
-                                c.ctl_host[0], c.cap_rounds);
-            want = (size_t)(c.ctl_host[0] + c.ctl_host[0] / 8 + 64);
+            if (attempt >= 2)
+                return aqc_fail(ctx, AQC_ERR_CUDA, "pair cache: %llu rounds / %llu chunks per lane do not fit "
+                                "%zu / %u after growing", c.ctl_host[0], c.ctl_host[2], c.cap_rounds, c.capc);
+            if (!rounds_ok)
+                want = (size_t)(c.ctl_host[0] + c.ctl_host[0] / 8 + 64);
+            if (!lists_ok)
+                want_capc = (uint32_t)(c.ctl_host[2] + c.ctl_host[2] / 8 + 8);
         }
         c.unusable = (c.ctl_host[1] & 1ull) != 0;
         c.icls = c.icls_want;
@@ -1569,7 +1630,10 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
     out->pass_tab = c.pass_tab;
     out->ctl = c.ctl;
     out->cap_rounds = (uint32_t)c.cap_rounds;
-    return 1;
+    out->chunks = (uint2*)c.chunks;
+    out->cnt = c.cnt;
+    out->capc = c.capc;
+    return c.lists ? 2 : 1;
 }
 
 namespace {

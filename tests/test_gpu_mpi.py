@@ -431,11 +431,14 @@ def test_dam_break_slabs_n_gpus_match_one_gpu(size):
     mpi-sync plan is verified against its mask (AQC_MPI_VERIFY)."""
     if _n_gpus() < size:
         pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (size, size))
-    n_total, steps = 60000, 6
+    # (a slab must be thicker than the two halos it feeds: 1.07 / 4 > 2 x 2 h at this size)
+    n_total, steps = 100000, 6
     kw = dict(seed=5, jitter=0.3, uscale=2.0, whole=True, iter_midpoint_max=3)
     one = _run_slabs(1, n_total, steps, **kw)[0]
     many = _run_slabs(size, n_total, steps, **kw)
-    assert len({many[r]["dt"] for r in range(size)} | {one["dt"]}) == 1, "dt must be global"
+    assert len({many[r]["dt"] for r in range(size)}) == 1, "dt must be global"
+    # (against one GPU the velocities dt derives from differ by the rounding of the summation order)
+    assert abs(many[0]["dt"] - one["dt"]) <= 1e-6 * one["dt"]
     fl1, matches = _match_rows(one, [many[r] for r in range(size)])
     n_live = sum(len(m[0]) for m in matches)
     assert n_live == len(fl1), "fluid particles lost or duplicated: %d vs %d" % (n_live, len(fl1))
@@ -455,3 +458,57 @@ def test_dam_break_slabs_n_gpus_match_one_gpu(size):
         calls = many[r]["sync_tools"].get("mpi neighs sync", 0)
         st = many[r]["plan0"]
         assert st["full"] == steps and st["full"] + st["reused"] == calls and st["reused"] >= steps, (st, calls)
+
+
+def _dead_peer_rank(rank, size, port, q):
+    import time
+    import torch.distributed as dist
+    os.environ["AQC_COMM_TIMEOUT_S"] = "8"
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=size)
+    uid = [_lib.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = _lib.Context(rank, dims=3, h=1.0)
+    ctx.comm_init(rank, size, uid[0])
+    n = 1000
+    mask = ctx.array(np.full(n, (rank + 1) % size, np.uint32))
+    f = ctx.array(np.arange(n, dtype=np.float32))
+    assert ctx.mpi_sync(mask, [f]) == n      # the communicator works
+    dist.barrier()
+    if rank == size - 1:
+        os._exit(0)                          # this rank leaves without a word
+    mask.set(np.full(n, (rank + 1) % size, np.uint32))
+    t0 = time.time()
+    try:
+        ctx.mpi_sync(mask, [f])
+        ctx.sync()
+        q.put((rank, ("no error", time.time() - t0, "")))
+    except _lib.AquaError as e:
+        dt = time.time() - t0
+        # and the context stays failed: no later collective may hang either
+        try:
+            ctx.mpi_sync(mask, [f])
+            again = "no error"
+        except _lib.AquaError as e2:
+            again = str(e2)
+        q.put((rank, (str(e), dt, again)))
+    os._exit(0)
+
+
+def test_dead_peer_ends_the_job():
+    """A rank that disappears must not leave its peers inside ncclRecv (round 1: three ranks
+    spun for 870 s): the bounded wait aborts the communicator and the call fails."""
+    size = min(_n_gpus(), 3)
+    if size < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mpx = mp.get_context("spawn")
+    q = mpx.Queue()
+    port = _free_port()
+    procs = [mpx.Process(target=_dead_peer_rank, args=(r, size, port, q)) for r in range(size)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in range(size - 1))
+    [p.join(60) for p in procs]
+    for r, (msg, dt, again) in got.items():
+        assert msg != "no error" and dt < 40.0, (r, msg, dt)
+        assert "abort" in msg or "peer" in msg or "NCCL" in msg, msg
+        assert "aborted" in again, again

@@ -71,9 +71,9 @@ def test_steps_in_the_oracle(oracle):
 F_SLAB = ("r", "u", "rho", "dudt", "drhodt")
 
 
-def _serial(n, hfac, steps):
+def _serial(n, hfac, steps, **kw):
     from oracle import interp
-    c = cases.lattice(n, hfac)
+    c = cases.lattice(n, hfac, **kw)
     I = interp.Interpreter(casegen.instantiate("lattice_3d", c, (c["N"],)), 3)
     for k in casegen.STATE_FIELDS:
         I.V[k][...] = c[k]
@@ -82,22 +82,24 @@ def _serial(n, hfac, steps):
     return {k: I.unsorted(k) for k in F_SLAB}, float(I.V["dt"])
 
 
-def _two_ranks(n, hfac, steps, size=2):
+def _two_ranks(n, hfac, steps, size=2, fixes=None, **kw):
     import threading
+    fixes = fixes or casegen.multi_device_fixes
     from oracle import interp
     tr = interp.LocalTransport(size)
     out, errs = {}, []
 
     def work(rank):
         try:
-            c = cases.lattice_slab(n, hfac, rank, size)
-            txt = casegen.multi_device_fixes(casegen.instantiate("lattice_mpi_3d", c, (c["N"],)))
+            c = cases.lattice_slab(n, hfac, rank, size, **kw)
+            txt = fixes(casegen.instantiate("lattice_mpi_3d", c, (c["N"],)))
             I = interp.Interpreter(txt, 3, rank=rank, size=size, transport=tr)
             for k in casegen.STATE_FIELDS:
                 I.V[k][...] = c[k]
             for _ in range(steps):
                 I.step()
             res = {k: I.unsorted(k) for k in F_SLAB}
+            res.update({k + "_dev": I.V[k].copy() for k in F_SLAB + ("imove",)})
             res.update(own=c["own"], imove=I.unsorted("imove"), dt=float(I.V["dt"]), tools=len(I.tools))
             out[rank] = res
         except BaseException as e:   # noqa: BLE001
@@ -124,7 +126,7 @@ def test_z_slabs_on_two_ranks_reproduce_the_serial_run(oracle):
     for r in range(2):
         own = ranks[r]["own"]
         n = len(own)
-        assert n == 12 ** 3 // 2 and ranks[r]["tools"] == 77           # 76 + the global-dt all-reduce
+        assert n == 12 ** 3 // 2 and ranks[r]["tools"] == 79           # 76 + the global-dt all-reduce + the outgoing-mask backup / restore
         assert ranks[r]["dt"] == dt
         assert (ranks[r]["imove"][:n] == 1).all() and (ranks[r]["imove"][n:] == -255).all()
         for k, tol in (("r", 5e-7), ("u", 2e-6), ("rho", 5e-7), ("dudt", 1e-4), ("drhodt", 5e-6)):
@@ -222,3 +224,49 @@ def test_z_slabs_two_processes_gloo(oracle):
     for r in range(2):
         for k in F_SLAB:
             assert np.array_equal(got[r][k], want[r][k]), (r, k)
+
+
+def test_migrating_particles_are_neither_lost_nor_duplicated(oracle):
+    """Particles that cross a cut travel through `mpi local sync` + cfd/MPI.cl append / remove.  The
+    reference's pipeline hands `remove` the mask mpi-sync has already rewritten, so it parks the
+    wrong rows (casegen.multi_device_fixes, (iii)): with the outgoing mask restored, three ranks
+    hold exactly the serial run's particles after the crossings, field by field; without it they
+    do not.  Fast particles on off-lattice positions: about a tenth of a layer crosses each cut."""
+    kw = dict(uscale=0.2, jitter=0.45)
+    n, steps, size = 22, 4, 3      # (a slab must be thicker than the two halos it feeds: 26 / 3 > 2 x 4)
+    serial, dt = _serial(n, 2.0, steps, **kw)
+    ranks = _two_ranks(n, 2.0, steps, size=size, **kw)
+
+    def live(res):
+        rows = np.flatnonzero(res["imove_dev"] == 1)
+        return rows, res["r_dev"][rows]
+
+    from scipy.spatial import cKDTree
+    tree = cKDTree(serial["r"][:, :3].astype(np.float64))
+    seen, moved = [], 0
+    for r in range(size):
+        # one dt for all ranks (all-reduced); against the serial run the velocities it derives from
+        # carry the rounding of a different summation order by now
+        assert ranks[r]["dt"] == ranks[0]["dt"] and abs(ranks[r]["dt"] - dt) <= 1e-6 * dt
+        rows, pos = live(ranks[r])
+        d, j = tree.query(pos[:, :3].astype(np.float64))
+        assert d.max() < 1e-5, (r, d.max())
+        seen.append(j)
+        moved += len(set(j.tolist()) ^ set(ranks[r]["own"].tolist()))
+        for k, tol in (("u", 2e-6), ("rho", 2e-6), ("dudt", 2e-5), ("drhodt", 1e-5)):
+            a = serial[k][j].astype(np.float64)
+            b = ranks[r][k + "_dev"][rows].astype(np.float64)
+            assert np.abs(a - b).max() <= tol * np.abs(serial[k]).max(), (r, k)
+    seen = np.concatenate(seen)
+    assert moved > 20, "no particle crossed a cut: the test does not test"
+    assert len(seen) == n ** 3 and len(np.unique(seen)) == n ** 3, "particles lost or duplicated"
+
+    # the reference's order of things does lose / duplicate them
+    def without_iii(txt):
+        txt = casegen.multi_device_fixes(txt)
+        return re.sub(r'\s*<Tool [^>]*name="mpi sent mask (backup|restore)"[^>]*/>', "", txt)
+    bad = _two_ranks(n, 2.0, steps, size=size, fixes=without_iii, **kw)
+    n_bad = sum(int((bad[r]["imove_dev"] == 1).sum()) for r in range(size))
+    rows = [live(bad[r])[1] for r in range(size)]
+    d, j = tree.query(np.concatenate(rows)[:, :3].astype(np.float64))
+    assert n_bad != n ** 3 or len(np.unique(j[d < 1e-3])) != n ** 3
