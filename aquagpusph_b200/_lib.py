@@ -27,7 +27,7 @@ SYMBOLS = [
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
-    "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats",
+    "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_fp32_peak",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -119,6 +119,7 @@ def lib():
                                   C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint32),
                                   C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.aqc_mpi_sync_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.aqc_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -302,6 +303,12 @@ class Context:
 
     def sm_count(self):
         return int(lib().aqc_device_sm_count(self.h))
+
+    def fp32_peak(self):
+        """Measured FP32 TFLOP/s of the device: (scalar FFMA, packed FFMA2)."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._chk(lib().aqc_fp32_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- multi-device (include/aquacuda.h): one process per GPU, NCCL
     @staticmethod

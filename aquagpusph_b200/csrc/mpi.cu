@@ -182,6 +182,16 @@ double comm_timeout_s()
     return v;
 }
 
+bool plans_enabled() // AQC_MPI_PLANS=0: every mpi-sync call sorts and counts (A/B runs)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AQC_MPI_PLANS");
+        v = (e && !atoi(e)) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 bool verify_plans()
 {
     static int v = -1;
@@ -452,7 +462,7 @@ extern "C" int aqc_mpi_sync_ex(aqc_ctx* ctx, int plan, aqc_usize* mask, aqc_usiz
     aqc_sync_plan* pl = plan >= 0 ? &ctx->plans[plan] : &scratch;
     // ---- the plan of the previous call stands when the caller declared what the mask derives
     // from, none of that was written since, and the call is the same one
-    bool reuse = plan >= 0 && pl->valid && pl->mask == mask && pl->n == n && pl->peer == peer &&
+    bool reuse = plan >= 0 && plans_enabled() && pl->valid && pl->mask == mask && pl->n == n && pl->peer == peer &&
                  (int)pl->fields.size() == nfields;
     for (int f = 0; reuse && f < nfields; f++)
         reuse = pl->fields[f] == fields[f] && pl->elem_bytes[f] == elem_bytes[f];

@@ -173,8 +173,19 @@ def run_ours(a, rank, world, local_rank):
 
     N_all = int(sum_over_ranks(N))
 
-    for _ in range(a.warmup):
+    def sweeps_done():
+        # executions of the interaction sweep = inner (midpoint) iterations so far;
+        # iter_midpoint itself is overwritten by the autostop preset when it converges
+        return sum(n for name, n, _ in sim.tool_times() if name == "cfd interactions")
+
+    trace = os.environ.get("AQ_BENCH_TRACE") == "1" and rank == 0
+    for w in range(a.warmup):
+        n0 = sweeps_done()
         sim.step(1)
+        if trace:
+            print("warm-up step %d: %d inner iterations, residual %.4g, dt %.4g"
+                  % (w, sweeps_done() - n0, float(sim.scalar("Residual_midpoint")),
+                     float(sim.scalar("dt"))), file=sys.stderr, flush=True)
     barrier()
     clocks = Clocks(local_rank)
     if rank == 0:
@@ -182,11 +193,6 @@ def run_ours(a, rank, world, local_rank):
     # ---- device-resident timing: K steps between CUDA events on the stream
     e0, e1 = actx.event(), actx.event()
     l0 = sim.launch_count()
-
-    def sweeps_done():
-        # executions of the interaction sweep = inner (midpoint) iterations so far;
-        # iter_midpoint itself is overwritten by the autostop preset when it converges
-        return sum(n for name, n, _ in sim.tool_times() if name == "cfd interactions")
 
     inner = -sweeps_done()
     pc0 = actx.pairs_cache_stats()

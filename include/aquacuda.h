@@ -251,6 +251,12 @@ int aqc_mpi_sync_stats(const aqc_ctx* ctx, int plan, uint64_t* full, uint64_t* r
 int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, size_t count);
 int aqc_allreduce_host(aqc_ctx* ctx, int op, int type, void* host_inout, size_t count);
 
+/* ---- measured FP32 (non-tensor) throughput of the device: two register-to-register FMA
+ * micro-benchmarks (scalar FFMA and sm_100's packed FFMA2), TFLOP/s with fma = 2 flop.  The
+ * denominator of the "% of FP32 peak" figures of the neighbour sweeps (no
+ * such percentage without a measured peak); not a reference entry point. ---------------------- */
+int aqc_fp32_peak(aqc_ctx* ctx, double* tflops_ffma, double* tflops_ffma2);
+
 /* ---- events / profiling (Tool.cpp:296-310, Kernel.cpp:48-116) ------------ */
 int aqc_event_create(aqc_ctx* ctx, void** ev);
 int aqc_event_destroy(aqc_ctx* ctx, void* ev);

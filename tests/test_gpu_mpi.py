@@ -409,9 +409,10 @@ def test_mpi_sync_random_masks(size):
 
 
 def _match_rows(one, ranks):
-    """Rows of the 1-GPU run that correspond to every live fluid row of the N-GPU run.
-    Particles migrate, so ids are rank-local: the match goes through positions (two particles
-    are never closer than a fraction of dr; the runs differ by fp32 rounding)."""
+    """Rows of the 1-GPU run (original order: row k is particle fluid_index[k] of the whole dam
+    break) that correspond to every live fluid row of the N-GPU run.  Particles migrate, so ids
+    are rank-local: the match goes through positions (two particles are never closer than a
+    fraction of dr; the runs differ by fp32 rounding)."""
     from scipy.spatial import cKDTree
     fl1 = np.flatnonzero(one["imove"] == 1)
     tree = cKDTree(one["r"][fl1][:, :3].astype(np.float64))
@@ -433,8 +434,8 @@ def test_dam_break_slabs_n_gpus_match_one_gpu(size):
         pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (size, size))
     # (a slab must be thicker than the two halos it feeds: 1.07 / 4 > 2 x 2 h at this size)
     n_total, steps = 100000, 6
-    kw = dict(seed=5, jitter=0.3, uscale=2.0, whole=True, iter_midpoint_max=3)
-    one = _run_slabs(1, n_total, steps, **kw)[0]
+    kw = dict(seed=5, jitter=0.45, uscale=2.0, whole=True, iter_midpoint_max=3)
+    one = _run_slabs(1, n_total, steps, **dict(kw, whole=False))[0]
     many = _run_slabs(size, n_total, steps, **kw)
     assert len({many[r]["dt"] for r in range(size)}) == 1, "dt must be global"
     # (against one GPU the velocities dt derives from differ by the rounding of the summation order)
@@ -444,8 +445,10 @@ def test_dam_break_slabs_n_gpus_match_one_gpu(size):
     assert n_live == len(fl1), "fluid particles lost or duplicated: %d vs %d" % (n_live, len(fl1))
     assert len(np.unique(np.concatenate([m[1] for m in matches]))) == len(fl1)
     h = one["h"]
-    # particles crossed the cuts: the ranks no longer hold the fluid they started with
-    assert any(len(matches[r][0]) != many[r]["n_fluid0"] for r in range(size)), "nothing migrated"
+    # particles crossed the cuts: ranks hold particles that started on another rank
+    arrived = [int((~np.isin(one["fluid_index"][matches[r][1]], many[r]["fluid_index"])).sum())
+               for r in range(size)]
+    assert sum(arrived) > 20, "hardly anything migrated: %s" % arrived
     for r in range(size):
         rows, rows1, d = matches[r]
         assert d.max() < 1e-4 * h, "rank %d: a particle is %.3e away from its 1-GPU twin" % (r, d.max())

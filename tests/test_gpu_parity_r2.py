@@ -1,0 +1,191 @@
+"""GPU parity cases the first round left open ("close the parity gaps"):
+
+* one full step of the 116-tool pipeline at BASELINE config 2's size (1.2 M particles) against the
+  oracle FIELD BY FIELD (round 1 compared the full size through properties only);
+* the removal branch of basic/Domain.cl:48-90 (NaN / out of the box -> imove = -256, parked at
+  domain_max, which inflates the grid) and the sort that follows, through the whole pipeline;
+* basic/time_scheme/euler.cl (the one time scheme without a GPU test);
+* a 60-step run of a small case, so that the pair-cache invalidation, the growth of ihoc and the
+  re-sorting of moving particles are all crossed while the comparison goes on."""
+import numpy as np
+import pytest
+
+from aquagpusph_b200 import _lib, cases, casegen, host
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = {"r": 1e-6, "u": 1e-5, "rho": 1e-6, "p": 2e-4, "dudt": 2e-4, "drhodt": 2e-4}
+
+
+def _oracle(case, overrides, nset, template="spheric2_dambreak_3d"):
+    from oracle import interp
+    I = interp.Interpreter(casegen.instantiate(template, case, nset, overrides), case["dims"])
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = case[k]
+    return I
+
+
+def _compare_fields(I, sim, fields, what, mask=None):
+    fl = (I.unsorted("imove") == 1) if mask is None else mask
+    for k, tol in fields.items():
+        a = I.unsorted(k).astype(np.float64)
+        b = sim.download(k, unsorted=True).astype(np.float64)
+        scale = np.abs(a[fl]).max()
+        err = np.abs(a[fl] - b[fl]).max()
+        assert err <= tol * scale, "%s field %s: err %.3e scale %.3e" % (what, k, err, scale)
+
+
+def test_one_step_at_full_size_field_by_field(oracle):
+    """BASELINE config 2 as the bench runs it (n = 1e6 fluid particles, 1.2 M with the boundary
+    elements, hfac 3, the unchanged 116-tool pipeline, perturbed velocities so that every term is
+    alive), one step of two midpoint sub-iterations on the GPU against the oracle interpreter on
+    all host threads: neighbour structures, imove and dt bit-exact, the six fields of north_star
+    within the tolerances of the small pipeline tests."""
+    import os
+    from oracle import oracle as O
+    host.set_log_level(3)
+    O.set_threads(os.cpu_count() or 1)
+    try:
+        ov = {"iter_midpoint_max": 2}
+        case = cases.spheric2_dam_break(1000000, 3.0, seed=11)
+        nset = (case["N"] - 8, 8)
+        sim = casegen.load("spheric2_dambreak_3d", case, nset, ov)
+        sim.step(1)
+        I = _oracle(case, ov, nset)
+        I.step()
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"]), "dt must be bit-exact"
+        for k in ("icell", "id_sorted", "id_unsorted"):
+            assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+        ncw = int(I.V["n_cells"][3])
+        assert np.array_equal(sim.download("ihoc", np.uint32)[:ncw], I.V["ihoc"][:ncw])
+        assert np.array_equal(sim.download("imove", np.int32), I.V["imove"])
+        _compare_fields(I, sim, FIELDS, "1.2 M particles, step 1")
+        sim.close()
+    finally:
+        O.set_threads(1)
+
+
+def test_domain_removal_branch_through_the_pipeline(oracle):
+    """Particles that leave the box or turn NaN: basic/Domain.cl:48-90 makes them imove = -256 with
+    m = 0, u = dudt = 0 at domain_max; the link-list of the same step then hashes on a grid that
+    reaches domain_max (n_cells grows, ihoc is re-allocated, LinkList.cpp:234-271).  Four steps
+    against the oracle (two more particles leave during the third):
+    imove, n_cells, the neighbour structures and dt bit-exact, fields of the survivors in
+    tolerance."""
+    host.set_log_level(3)
+    ov = {"iter_midpoint_max": 3}
+    case = cases.spheric2_dam_break(6000, 3.0, seed=7)
+    fl = np.flatnonzero(case["imove"] == 1)
+    rng = np.random.default_rng(3)
+    out = rng.choice(fl, 8, replace=False)
+    dmin, dmax = np.asarray(case["domain_min"]), np.asarray(case["domain_max"])
+    case["r"][out[0], 0] = dmax[0] + 0.5          # beyond a face of the box, each axis
+    case["r"][out[1], 1] = dmin[1] - 0.25
+    case["r"][out[2], 2] = dmax[2] + 3.0
+    case["r"][out[3], 0] = dmin[0] - 1e-3
+    case["r"][out[4], 2] = np.nan
+    case["r"][out[5], 0] = np.inf
+    # two fast particles in empty space (no neighbours to disturb) that leave DURING the run:
+    # 0.18 per step at the dt their own speed imposes
+    case["r"][out[6], :3] = (dmax[0] - 0.25, 0.0, 1.5)
+    case["u"][out[6], 0] = 4.0e3
+    case["r"][out[7], :3] = (0.0, 0.0, dmin[2] + 0.25)
+    case["u"][out[7], 2] = -4.0e3
+    nset = (case["N"] - 8, 8)
+    I = _oracle(case, ov, nset)
+    sim = casegen.load("spheric2_dambreak_3d", case, nset, ov)
+    seen_grid = set()
+    for step in range(4):
+        I.step()
+        sim.step(1)
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"]), step
+        seen_grid.add(tuple(int(x) for x in I.V["n_cells"]))
+        for k in ("icell", "id_sorted", "id_unsorted"):
+            assert np.array_equal(sim.download(k, np.uint32), I.V[k]), (step, k)
+        ncw = int(I.V["n_cells"][3])
+        assert np.array_equal(sim.download("ihoc", np.uint32)[:ncw], I.V["ihoc"][:ncw]), step
+        mv = sim.download("imove", np.int32, unsorted=True)
+        assert np.array_equal(mv, I.unsorted("imove")), step
+        assert float(sim.scalar("dt")) == float(I.V["dt"]), "dt must be bit-exact (step %d)" % step
+        gone = mv <= -255
+        assert gone[out[:6]].all() and gone.sum() == (8 if step == 3 else 6), (step, mv[out])
+        # what Domain wrote for the removed rows is exact
+        for k in ("m", "u", "dudt"):
+            a, b = I.unsorted(k)[gone], sim.download(k, unsorted=True)[gone]
+            assert np.array_equal(a, b) and not np.any(a), (step, k)
+        assert np.array_equal(I.unsorted("r")[gone], sim.download("r", unsorted=True)[gone])
+        keep = (mv == 1)
+        _compare_fields(I, sim, {"r": 1e-6, "u": 2e-5, "rho": 2e-6, "p": 5e-4, "dudt": 5e-4, "drhodt": 5e-4},
+                        "step %d" % step, keep)
+    assert len(seen_grid) >= 1
+    sim.close()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_euler_time_scheme_kernels(oracle, dims):
+    """basic/time_scheme/euler.cl::predictor (:65-87, the state copy) and ::corrector (:105-124) through
+    the Kernel-tool C-ABI against the oracle: copies, products and sums without contraction --
+    bit-exact, fixed particles (imove <= 0) untouched."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(31)
+    st = {"imove": np.ascontiguousarray(case["imove"]).copy(), "iset": np.ascontiguousarray(case["iset"]).copy()}
+    for k in ("r", "u", "dudt"):
+        st[k] = rng.normal(size=(N, V)).astype(np.float32)
+    for k in ("rho", "drhodt"):
+        st[k] = rng.normal(size=N).astype(np.float32)
+    bak = {k + "_in": np.zeros_like(st[k]) for k in ("r", "u", "dudt", "rho", "drhodt")}
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(a) for k, a in list(st.items()) + list(bak.items())}
+    dt = 7.5e-4
+    d.update(N=N, dt=dt)
+    ctx.launch("basic/time_scheme/euler.cl", "predictor", d)
+    for k in bak:
+        assert np.array_equal(d[k].get(), st[k[:-3]]), k
+    want = {k: a.copy() for k, a in st.items()}
+    oracle.call("euler_corrector", want["imove"], want["r"], want["u"], want["dudt"], want["rho"],
+                want["drhodt"], N, dt, dims)
+    ctx.launch("basic/time_scheme/euler.cl", "corrector", d)
+    moved = 0
+    for k in ("r", "u", "rho", "dudt", "drhodt", "imove"):
+        got = d[k].get()
+        assert np.array_equal(got, want[k]), k
+        moved += int(not np.array_equal(got, st[k]))
+    assert moved >= 3      # r, u and rho advanced
+    fixed = st["imove"] <= 0
+    assert fixed.any() and np.array_equal(d["r"].get()[fixed], st["r"][fixed])
+    ctx.close()
+
+
+def test_sixty_steps_of_a_small_dam_break(oracle):
+    """60 steps of the 116-tool pipeline (n = 4000, perturbed, up to 4 sub-iterations) with the
+    comparison going on at every tenth step: the pair cache is rebuilt every step and served in
+    between, particles change cells, dt varies.  Neighbour structures cannot stay bit-exact once
+    positions differ by an ulp (a particle on a cell face hashes differently), so after the first
+    step the bar is: same n_cells, dt to 1e-5, fields within a tolerance that grows with the
+    number of steps (chaotic amplification of fp32 rounding), no particle lost."""
+    host.set_log_level(3)
+    ov = {"iter_midpoint_max": 4}
+    case = cases.spheric2_dam_break(4000, 3.0, seed=5)
+    nset = (case["N"] - 8, 8)
+    I = _oracle(case, ov, nset)
+    sim = casegen.load("spheric2_dambreak_3d", case, nset, ov)
+    ctx = _lib.Context.borrow(sim.cuda_ctx(), 3)
+    for step in range(60):
+        I.step()
+        sim.step(1)
+        if step == 0:
+            for k in ("icell", "id_sorted", "id_unsorted"):
+                assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+            assert float(sim.scalar("dt")) == float(I.V["dt"])
+        if step % 10 == 9:
+            assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"]), step
+            assert abs(float(sim.scalar("dt")) / float(I.V["dt"]) - 1.0) < 1e-5, step
+            assert np.array_equal(sim.download("imove", np.int32, unsorted=True), I.unsorted("imove"))
+            grow = 1.0 + step / 10.0
+            _compare_fields(I, sim, {"r": 2e-6 * grow, "u": 1e-4 * grow, "rho": 5e-6 * grow,
+                                     "p": 2e-3 * grow, "dudt": 2e-3 * grow}, "step %d" % step)
+    st = ctx.pairs_cache_stats()
+    assert st["builds"] >= 60 and st["hits"] >= 3 * st["builds"], st
+    sim.close()
