@@ -222,6 +222,31 @@ __device__ __forceinline__ uint32_t test_tile(const float4* __restrict__ T, unsi
     return hits << (32 - 2 * NPAIR);
 }
 
+// The same test against two radii at once: `hits` for C2, `sure` for C2 + D2 (a smaller radius)
+template <int NPAIR>
+__device__ __forceinline__ void test_tile2(const float4* __restrict__ T, unsigned long long X2,
+                                           unsigned long long Y2, unsigned long long Z2,
+                                           unsigned long long C2, unsigned long long D2, uint32_t& hits,
+                                           uint32_t& sure)
+{
+    uint32_t h = 0, s = 0;
+#pragma unroll
+    for (int q = 0; q < NPAIR; q++) {
+        const float4 a = T[2 * q], b = T[2 * q + 1];
+        unsigned long long t = ffma2(X2, pack2(a.x, a.y), C2);
+        t = ffma2(Y2, pack2(a.z, a.w), t);
+        t = ffma2(Z2, pack2(b.x, b.y), t);
+        t = fadd2(t, pack2(b.z, b.w));
+        const unsigned long long u = fadd2(t, D2);
+        h = __funnelshift_l((uint32_t)t, h, 1);
+        h = __funnelshift_l((uint32_t)(t >> 32), h, 1);
+        s = __funnelshift_l((uint32_t)u, s, 1);
+        s = __funnelshift_l((uint32_t)(u >> 32), s, 1);
+    }
+    hits = h << (32 - 2 * NPAIR);
+    sure = s << (32 - 2 * NPAIR);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t a) // a: shared-window address
 {
     float4 v;
@@ -391,7 +416,10 @@ static __device__ unsigned long long g_s3prof[32];
 #define S3P_START
 #define S3P_ACC(k)
 #endif
-static_assert(S3_TILES_N % S3_BATCH == 0, "S3_BATCH must divide S3_TILES");
+#ifndef S3_BBATCH
+#define S3_BBATCH 4 // the same for the builders of the pair cache (MODE 1 / 3)
+#endif
+static_assert(S3_TILES_N % S3_BATCH == 0 && S3_TILES_N % S3_BBATCH == 0, "S3_BATCH must divide S3_TILES");
 constexpr int S3_MAXK = 8;                    // ring rounds (at most; static shared memory grows with it)
 #ifndef S3_RTILES
 #define S3_RTILES 8 // tiles of a round of the mask-reading sweeps (MODE 2; divides S3_TILES)
@@ -530,7 +558,10 @@ struct S3Cache {
 // An entry of a neighbour list is the byte offset of the candidate's row inside ONE row array of
 // the reader's ring (S4_K rounds of S3_TILES tiles of 32 rows of 16 bytes); S4_NULL addresses the
 // extra row behind the ring, whose weights are zero (the padding of a lane's last chunk in a round)
-constexpr int S4_K = 3;
+#ifndef S4_RING
+#define S4_RING 5 // ring rounds of the list readers: how far the warps of a CTA may drift apart
+#endif
+constexpr int S4_K = S4_RING;
 constexpr uint32_t S4_ROWS = S4_K * S3_TILES_N * 32;
 constexpr uint32_t S4_NULL = S4_ROWS * 16;
 constexpr int S3_MAXPASS = 32;
@@ -809,13 +840,16 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
         // of a batch are issued before any of them is used (branch-free: a lane without a
         // candidate loads particle 0 and drops it).  MODE 1 stages the test layout only, MODE 2
         // the j rows only.
+        // (the builders are bound by their staging warp, which waits for one tile's loads at a time:
+        // they keep S3_BBATCH tiles in flight; with pair bodies to run the consumers are the bottleneck)
+        constexpr int NB = (MODE == 1 || MODE == 3) ? S3_BBATCH : S3_BATCH;
         uint32_t tk = 0, te = 0;
         auto stage_batch = [&](uint32_t ring_round, uint32_t w0) {
             const uint32_t par = ring_round;
-            uint32_t cnt[S3_BATCH], cj[S3_BATCH], eb[S3_BATCH];
-            float4 o[S3_BATCH][P::NJ4];
+            uint32_t cnt[NB], cj[NB], eb[NB];
+            float4 o[NB][P::NJ4];
 #pragma unroll
-            for (int b = 0; b < S3_BATCH; b++) {
+            for (int b = 0; b < NB; b++) {
                 const uint32_t e = te, k = tk;
                 if (++te == NE) {
                     te = 0;
@@ -830,7 +864,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                 p.stage_j(jj, o[b]);
             }
 #pragma unroll
-            for (int b = 0; b < S3_BATCH; b++) {
+            for (int b = 0; b < NB; b++) {
                 const uint32_t w2 = w0 + b;
                 uint32_t c = cnt[b];
                 if (c) {
@@ -927,7 +961,7 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                     }
                 } else {
 #pragma unroll 1
-                    for (uint32_t w0 = 0; w0 < (uint32_t)W; w0 += S3_BATCH)
+                    for (uint32_t w0 = 0; w0 < (uint32_t)W; w0 += NB)
                         stage_batch(rk, w0);
                     __syncwarp();
                     if (lane == 0)
@@ -944,6 +978,9 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
             uint32_t rq = 0;           // ring round of round r + 2 - K, the next one to release
             const unsigned long long X2 = pack2(fx, fx), Y2 = pack2(fy, fy), Z2 = pack2(fz, fz),
                                      C2 = pack2(fc, fc);
+            // MODE 3: the same test with the radius deflated by 1e-4 instead of inflated
+            const unsigned long long D2s = pack2(p.cut2 * 2.0e-4f, p.cut2 * 2.0e-4f);
+            (void)D2s;
             const uint32_t mbase = s_base;
 #if S3_PROFILE
             const int s3p_c = work_w ? 0 : 8; // warps without a working lane: second bank
@@ -1014,9 +1051,18 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                         nch++;
                         acc0 = acc1 = nn = 0;
                     };
+                    auto append = [&](uint32_t e) {
+                        const uint32_t sh = (nn & 1u) * 16u;
+                        if (nn & 2u)
+                            acc1 |= e << sh;
+                        else
+                            acc0 |= e << sh;
+                        if (++nn == 4u)
+                            flush();
+                    };
 #pragma unroll 1
                     for (int w2 = 0; w2 < W; w2++) {
-                        uint32_t m = 0;
+                        uint32_t m = 0, sure = 0;
                         const uint32_t cnt = t_cnt[rk][w2];
                         if (work && cnt) {
                             const uint32_t rel = t_rel[rk][w2] - a_i;
@@ -1024,31 +1070,42 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
                             const uint32_t okm = (rel <= 2u ? pm : 0u) | (rel + 1u <= 2u ? ~pm : 0u);
                             if (okm) {
                                 const float4* T = sT + (rk * W + w2) * 32;
+                                // the packed filter over-selects by 1e-4 of the radius; with the radius
+                                // DEFLATED by as much it only under-selects (its own error is ~1e-6):
+                                // those candidates need no exact test
                                 if (cnt > 16)
-                                    m = test_tile<16>(T, X2, Y2, Z2, C2);
+                                    test_tile2<16>(T, X2, Y2, Z2, C2, D2s, m, sure);
                                 else if (cnt > 8)
-                                    m = test_tile<8>(T, X2, Y2, Z2, C2);
+                                    test_tile2<8>(T, X2, Y2, Z2, C2, D2s, m, sure);
                                 else
-                                    m = test_tile<4>(T, X2, Y2, Z2, C2);
+                                    test_tile2<4>(T, X2, Y2, Z2, C2, D2s, m, sure);
                                 m &= okm;
+                                sure &= m;
                             }
                         }
                         const float4* const rowp = sJ + (size_t)(rk * W + w2) * SLOT4;
-                        while (m) {
+                        const uint32_t etile = ebase + (uint32_t)w2 * 512u + 31u * 16u;
+                        // the shell between the two radii: the readers' P::test, to the letter
+                        for (uint32_t mm = m & ~sure; mm; mm &= mm - 1u) {
+                            const uint32_t f = 31u - (uint32_t)__clz(mm);
+                            const float4 A = rowp[31u - f];
+                            if (!(dist2<P::DIMS>(A.x - st.x, A.y - st.y, A.z - st.z) < p.cut2))
+                                m ^= 1u << f;
+                        }
+                        auto next = [&]() { // the next candidate k = 31 - f of the tile
                             const uint32_t f = 31u - (uint32_t)__clz(m);
                             m ^= 1u << f;
-                            const uint32_t k = 31u - f;
-                            const float4 A = rowp[k];
-                            // the readers' P::test, to the letter
-                            if (dist2<P::DIMS>(A.x - st.x, A.y - st.y, A.z - st.z) < p.cut2) {
-                                const uint32_t e = ebase + (uint32_t)w2 * 512u + k * 16u;
-                                const uint32_t sh = (nn & 1u) * 16u;
-                                if (nn & 2u)
-                                    acc1 |= e << sh;
-                                else
-                                    acc0 |= e << sh;
-                                if (++nn == 4u)
-                                    flush();
+                            return etile - (f << 4);
+                        };
+                        while (m) {
+                            if (nn == 0u && __popc(m) >= 4) { // a whole chunk at once
+                                acc0 = next();
+                                acc0 |= next() << 16;
+                                acc1 = next();
+                                acc1 |= next() << 16;
+                                flush();
+                            } else {
+                                append(next());
                             }
                         }
                     }
@@ -1181,10 +1238,22 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 // the oldest round's chunks before the warp releases it.
 // Same pairs in the same order as MODE 0 / 2 (the padding rows add exactly +-0).
 #ifndef S4_MINB
-#define S4_MINB 3 // CTAs per SM the register allocation aims at
+#define S4_MINB 4 // CTAs per SM the register allocation aims at (kernels with two row arrays)
+#endif
+#ifndef S4_MINB1
+#define S4_MINB1 4 // ... (kernels with one: fewer live registers, more warps pay)
+#endif
+#ifndef S4_SPLIT
+#define S4_SPLIT 1 // 1: the rows of a chunk are fetched two at a time (fewer live registers)
+#endif
+#ifndef S4_NBUF
+#define S4_NBUF 1 // chunks held in registers ahead of the current one (1 or 3)
+#endif
+#ifndef S4_AHEAD
+#define S4_AHEAD 6 // chunks ahead of the current one whose line is prefetched into L1 (0: none)
 #endif
 template <class P>
-__global__ void __launch_bounds__(S3_THREADS, S4_MINB)
+__global__ void __launch_bounds__(S3_THREADS, (P::NJ4 == 1) ? S4_MINB1 : S4_MINB)
 sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
 {
     constexpr int W = S3_TILES, K = S4_K;
@@ -1217,7 +1286,7 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
             ring[q][S4_ROWS] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     constexpr int NROWS = (P::DIMS == 3) ? 9 : 3;
-    // this lane's list: chunk c at lp0[c * 32]
+    // this lane's list: chunk c at lp[c * 32]
     const uint2* lp = pc.chunks + ((size_t)(blockIdx.x * S3_CWARPS + (producer ? 0 : cw)) * pc.capc) * 32 + lane;
 
     bool pending = valid && c_i < ll.nw;
@@ -1344,17 +1413,29 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
             }
         } else {
             const uint8_t* cp = pc.cnt + ((size_t)s_base * S3_CWARPS + cw) * 32 + lane;
-            // chunks of the lane from the oldest round still in the ring / from the newest one
-            uint32_t a_old = 0, a_new = 0;
-            uint32_t cn = (work && nrounds) ? (uint32_t)__ldg(cp) : 0u;
-            // two chunks ahead of the one being worked on (reads past the end of a list stay
-            // inside the allocation and are never used)
-            uint2 c0v = make_uint2(0u, 0u), c1v = make_uint2(0u, 0u);
+            // chunks of this lane: consumed so far / staged in the ring so far (through the round that
+            // was last found full) / belonging to the rounds up to the one to be released next
+            uint32_t done = 0, avail = 0, relq = 0;
+            uint32_t cn = (work && nrounds) ? (uint32_t)__ldg(cp) : 0u; // of the round to come
+            uint32_t cq = cn;                                            // of the round to release next
+            // the lane's list: the next chunk is loaded while the current one is worked on, and the
+            // lines S4_AHEAD chunks further on are already on their way to L1 (reads past the end of
+            // a list stay inside the allocation and are never used)
+#if S4_NBUF == 3
+            uint2 c0v = make_uint2(0u, 0u), c1v = c0v, c2v = c0v;
             if (work) {
                 c0v = __ldg(lp);
                 c1v = __ldg(lp + 32);
-                lp += 64;
+                c2v = __ldg(lp + 64);
+                lp += 96;
             }
+#else
+            uint2 c0v = make_uint2(0u, 0u);
+            if (work) {
+                c0v = __ldg(lp);
+                lp += 32;
+            }
+#endif
             // policies whose body returns early for some i particles (the fused pass: Shepard serves
             // boundary elements too) offer body_all(), the same terms without the branch: a warp
             // with at least one lane that needs everything runs it for all its lanes (what the
@@ -1363,66 +1444,81 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
             if constexpr (P::HAS_BODY_ALL)
                 whole = __any_sync(0xffffffffu, work && p.needs_all(st));
             const char* const ring_c = reinterpret_cast<const char*>(&ring[0][0]);
+            auto bodies = [&](const float4* va, const float4* vb) {
+                if constexpr (P::HAS_BODY_ALL) {
+                    if (whole) {
+                        p.body_all(st, va);
+                        p.body_all(st, vb);
+                        return;
+                    }
+                }
+                p.body(st, va, 1);
+                p.body(st, vb, 1);
+            };
             auto take = [&]() { // one chunk: four rows, four pair bodies
                 const uint2 e = c0v;
+#if S4_NBUF == 3
                 c0v = c1v;
-                c1v = __ldg(lp);
+                c1v = c2v;
+                c2v = __ldg(lp);
+#else
+                c0v = __ldg(lp);
+#endif
+#if S4_AHEAD
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + S4_AHEAD * 32));
+#endif
                 lp += 32;
+                done++;
                 const uint32_t o0 = e.x & 0xFFFFu, o1 = e.x >> 16, o2 = e.y & 0xFFFFu, o3 = e.y >> 16;
                 float4 v0[P::NJ4], v1[P::NJ4], v2[P::NJ4], v3[P::NJ4];
 #pragma unroll
                 for (int q = 0; q < P::NJ4; q++) {
                     v0[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o0);
                     v1[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o1);
+                }
+#if S4_SPLIT
+                bodies(v0, v1);
+                asm volatile("" ::: "memory"); // (the second half's rows are fetched after the first half's bodies)
+#endif
+#pragma unroll
+                for (int q = 0; q < P::NJ4; q++) {
                     v2[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o2);
                     v3[q] = *reinterpret_cast<const float4*>(ring_c + q * QSTRIDE + o3);
                 }
-                if constexpr (P::HAS_BODY_ALL) {
-                    if (whole) {
-                        p.body_all(st, v0);
-                        p.body_all(st, v1);
-                        p.body_all(st, v2);
-                        p.body_all(st, v3);
-                    } else {
-                        p.body(st, v0, 1);
-                        p.body(st, v1, 1);
-                        p.body(st, v2, 1);
-                        p.body(st, v3, 1);
-                    }
-                } else {
-                    p.body(st, v0, 1);
-                    p.body(st, v1, 1);
-                    p.body(st, v2, 1);
-                    p.body(st, v3, 1);
-                }
-                if (a_old)
-                    a_old--;
-                else
-                    a_new--;
+#if !S4_SPLIT
+                bodies(v0, v1);
+#endif
+                bodies(v2, v3);
             };
+            // Round r is consumed from ring round r % K.  After finding it full a warp takes chunks
+            // while every working lane has one staged; then it releases round r + 2 - K, whose chunks
+            // are the oldest of every list: a lane still owing some runs them first.  Only the ring
+            // couples the warps: they may drift apart by K - 2 rounds before anybody waits.
             uint32_t rk = 0, use = 0, rq = 0;
             for (uint32_t r = 0; r < nrounds; r++) {
                 {
                     uint32_t spins = 0;
                     while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u))) {
-                        if (++spins > (1u << 28))
+                        if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
                         __nanosleep(S3_SLEEP_C);
                     }
                 }
-                a_new = cn;
+                avail += cn;
                 if (work && r + 1 < nrounds)
                     cn = (uint32_t)__ldg(cp + (size_t)(r + 1) * (S3_CWARPS * 32));
                 if (work) {
-                    // ---- chunks, while every working lane of the warp has one
-                    while (__ballot_sync(work_w, (a_old | a_new) != 0u) == work_w)
+                    while (__ballot_sync(work_w, done < avail) == work_w)
                         take();
                 }
                 __syncwarp();
-                if (r >= 1) {
-                    // ---- release round r - 1: its chunks are the oldest of every list
-                    while (__any_sync(0xffffffffu, a_old != 0u)) {
-                        if (a_old)
+                if (r + 2 >= (uint32_t)K) {
+                    const uint32_t q = r + 2 - (uint32_t)K;
+                    relq += cq;
+                    if (work)
+                        cq = (uint32_t)__ldg(cp + (size_t)(q + 1) * (S3_CWARPS * 32));
+                    while (__any_sync(0xffffffffu, done < relq)) {
+                        if (done < relq)
                             take();
                     }
                     __syncwarp();
@@ -1430,15 +1526,13 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
                         mbar_arrive(empty_a + 8 * rq);
                     rq = (rq + 1 == (uint32_t)K) ? 0u : rq + 1;
                 }
-                a_old = a_new; // (everything older has been consumed)
-                a_new = 0;
                 if (++rk == (uint32_t)K) {
                     rk = 0;
                     use++;
                 }
             }
-            while (__any_sync(0xffffffffu, a_old != 0u)) {
-                if (a_old)
+            while (__any_sync(0xffffffffu, done < avail)) {
+                if (done < avail)
                     take();
             }
         }

@@ -1559,7 +1559,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
             return 0;
         };
         size_t want = c.cap_rounds ? c.cap_rounds : nblk * (dims == 3 ? 40 : 12);
-        uint32_t want_capc = c.capc ? c.capc : (dims == 3 ? 272u : 72u);
+        uint32_t want_capc = c.capc ? c.capc : (dims == 3 ? 272u : 72u); // (even: stored in pairs)
         for (int attempt = 0;; attempt++) {
             if (want > c.cap_rounds) {
                 if (*rounds_buf) {
@@ -1577,8 +1577,8 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
                 c.cap_rounds = want;
             }
             if (c.lists) {
-                // (two chunk rows of slack: the readers load two chunks ahead)
-                const size_t need = (nblk * S3_CWARPS * (size_t)want_capc + 2) * 32 * sizeof(uint2);
+                // (slack: the readers load two chunk pairs ahead and prefetch three more)
+                const size_t need = (nblk * S3_CWARPS * (size_t)want_capc + 16) * 32 * sizeof(uint2);
                 if (need > c.chunks_bytes || want_capc != c.capc) {
                     if (need > c.chunks_bytes) {
                         if (c.chunks) {
@@ -1614,7 +1614,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
             if (!rounds_ok)
                 want = (size_t)(c.ctl_host[0] + c.ctl_host[0] / 8 + 64);
             if (!lists_ok)
-                want_capc = (uint32_t)(c.ctl_host[2] + c.ctl_host[2] / 8 + 8);
+                want_capc = ((uint32_t)(c.ctl_host[2] + c.ctl_host[2] / 8 + 8) + 1u) & ~1u;
         }
         c.unusable = (c.ctl_host[1] & 1ull) != 0;
         c.icls = c.icls_want;

@@ -110,10 +110,10 @@ def test_domain_removal_branch_through_the_pipeline(oracle):
         assert float(sim.scalar("dt")) == float(I.V["dt"]), "dt must be bit-exact (step %d)" % step
         gone = mv <= -255
         assert gone[out[:6]].all() and gone.sum() == (8 if step == 3 else 6), (step, mv[out])
-        # what Domain wrote for the removed rows is exact
+        # what Domain wrote for the removed rows is exact (they keep getting g from cfd/Rates.cl)
         for k in ("m", "u", "dudt"):
             a, b = I.unsorted(k)[gone], sim.download(k, unsorted=True)[gone]
-            assert np.array_equal(a, b) and not np.any(a), (step, k)
+            assert np.array_equal(a, b) and (k == "dudt" or not np.any(a)), (step, k)
         assert np.array_equal(I.unsorted("r")[gone], sim.download("r", unsorted=True)[gone])
         keep = (mv == 1)
         _compare_fields(I, sim, {"r": 1e-6, "u": 2e-5, "rho": 2e-6, "p": 5e-4, "dudt": 5e-4, "drhodt": 5e-4},

@@ -120,3 +120,70 @@ def test_mpi_plane_two_processes_gloo(golden, oracle):
     for r in range(2):
         for k in mpi_common.FIELDS:
             assert np.array_equal(got[r][k], ref_ranks[r][k]), (r, k)
+
+
+def _dam_break_ranks(size, n_total, steps, **kw):
+    """The 3-D dam break cut in `size` y slabs through the oracle interpreter (threads), with the
+    multi-device additions of casegen.multi_device_fixes; returns the device-order state."""
+    import threading
+    from aquagpusph_b200 import cases, casegen
+    tr = interp.LocalTransport(size)
+    out, errs = {}, []
+
+    def work(rank):
+        try:
+            c = cases.spheric2_dam_break_slab(n_total, 3.0, rank, size, **kw)
+            txt = casegen.multi_device_fixes(casegen.instantiate(
+                "spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), {"iter_midpoint_max": 3}))
+            I = interp.Interpreter(txt, 3, rank=rank, size=size, transport=tr)
+            for k in casegen.STATE_FIELDS:
+                I.V[k][...] = c[k]
+            for _ in range(steps):
+                I.step()
+            res = {k: I.V[k].copy() for k in ("r", "u", "rho", "dudt", "imove")}
+            res.update(fluid_index=c["fluid_index"], n_fluid=c["n_fluid"], dt=float(I.V["dt"]), h=c["h"],
+                       r0=I.unsorted("r")[:c["n_fluid"]], u0=I.unsorted("u")[:c["n_fluid"]])
+            out[rank] = res
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+            tr._barrier.abort()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(size)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return out
+
+
+def test_dam_break_three_slabs_with_migration(oracle):
+    """BASELINE config 3's shape with what round 1 never exercised: off-lattice particles that
+    move fast enough to cross the cuts, an interior rank with two peers.  Three ranks reproduce
+    the one-rank run particle by particle (matched by position: ids are rank-local once a
+    particle has migrated), nothing is lost or duplicated, and dozens of particles end on a
+    rank they did not start on.  The same scenario runs on GPUs in tests/test_gpu_mpi.py."""
+    from scipy.spatial import cKDTree
+    from oracle import oracle as O
+    O.set_threads(4)
+    try:
+        kw = dict(seed=5, jitter=0.45, uscale=2.0)
+        n_total, steps, size = 24000, 5, 3
+        one = _dam_break_ranks(1, n_total, steps, **kw)[0]
+        many = _dam_break_ranks(size, n_total, steps, **kw)
+    finally:
+        O.set_threads(1)
+    nf = one["n_fluid"]
+    tree = cKDTree(one["r0"][:, :3].astype(np.float64))
+    seen, arrived = [], 0
+    for r in range(size):
+        g = many[r]
+        assert g["dt"] == many[0]["dt"] and abs(g["dt"] - one["dt"]) <= 1e-6 * one["dt"]
+        fl = np.flatnonzero(g["imove"] == 1)
+        d, j = tree.query(g["r"][fl][:, :3].astype(np.float64))
+        assert d.max() < 1e-4 * g["h"], (r, d.max())
+        seen.append(j)
+        arrived += int((~np.isin(one["fluid_index"][j], g["fluid_index"])).sum())
+        a, b = one["u0"][j].astype(np.float64), g["u"][fl].astype(np.float64)
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(a).max(), r
+    seen = np.concatenate(seen)
+    assert len(seen) == nf and len(np.unique(seen)) == nf, "particles lost or duplicated"
+    assert arrived > 20, arrived
