@@ -1249,6 +1249,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
 #ifndef S4_NBUF
 #define S4_NBUF 1 // chunks held in registers ahead of the current one (1 or 3)
 #endif
+#ifndef S4_SLEEP0
+#define S4_SLEEP0 64 // ns: first sleep of a consumer warp that waits for its round, doubled up to
+#endif
+#ifndef S4_SLEEP1
+#define S4_SLEEP1 1024
+#endif
 #ifndef S4_AHEAD
 #define S4_AHEAD 6 // chunks ahead of the current one whose line is prefetched into L1 (0: none)
 #endif
@@ -1497,11 +1503,14 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
             uint32_t rk = 0, use = 0, rq = 0;
             for (uint32_t r = 0; r < nrounds; r++) {
                 {
-                    uint32_t spins = 0;
+                    // a warp that finds its round not staged yet is ahead of the slowest warp of the
+                    // CTA (or of the copies): it backs off, leaving the issue slots to the others
+                    uint32_t spins = 0, ns = S4_SLEEP0;
                     while (!__all_sync(0xffffffffu, mbar_wait(full_a + 8 * rk, use & 1u))) {
-                        if (++spins > (1u << 28)) // watchdog: a lost arrival must not hang the GPU
+                        if (++spins > (1u << 24)) // watchdog: a lost arrival must not hang the GPU
                             __trap();
-                        __nanosleep(S3_SLEEP_C);
+                        __nanosleep(ns);
+                        ns = min(2u * ns, (uint32_t)S4_SLEEP1);
                     }
                 }
                 avail += cn;

@@ -1,6 +1,8 @@
 // calcserver.cpp -- see calcserver.hpp
 #include "calcserver.hpp"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstring>
 #include <filesystem>
@@ -984,6 +986,27 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
         return new PythonTool(this, name, t.get("path"), once);
     if (type == "dummy")
         return new Tool(this, name, once);
+    if (type == "installable") {
+        // CalcServer.cpp:375-400: dlopen(path), dlsym("create_object"), Tool* create_object(const
+        // std::string name, bool once).  The plugin derives from THIS host's Tool
+        // (aquagpusph_b200/host/calcserver.hpp) and links libaquahost.so, the way the reference's
+        // tests/ExternalTool links libaquagpusphlib.so; a plugin built against the reference's
+        // OpenCL Tool cannot be loaded (there is no OpenCL here).
+        void* handle = dlopen(t.get("path").c_str(), RTLD_LAZY);
+        if (!handle)
+            throw std::runtime_error("Installable tool \"" + name + "\" failed loading \"" + t.get("path") +
+                                     "\" library: " + (dlerror() ? dlerror() : "?"));
+        typedef Tool* (*maker_t)(const std::string, bool);
+        maker_t maker = (maker_t)dlsym(handle, "create_object");
+        if (!maker)
+            throw std::runtime_error("Installable tool \"" + name +
+                                     "\" failed loading \"create_object\" symbol");
+        Tool* tool = maker(name, once);
+        if (!tool)
+            throw std::runtime_error("Installable tool \"" + name + "\": create_object returned NULL");
+        tool->attach(this);
+        return tool;
+    }
     if (startswith(type, "report_"))
         return new Report(this, name, type.substr(7), t, once);
     throw std::runtime_error("The tool \"" + name + "\" has the type \"" + type +

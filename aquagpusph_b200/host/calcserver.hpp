@@ -31,6 +31,10 @@ class Tool {
   public:
     Tool(CalcServer* C, const std::string& name, bool once = false)
       : _C(C), _name(name), _once(once) {}
+    /// The reference's constructor (Tool.hpp:180: name, once): what a type="installable" plugin's
+    /// create_object(name, once) calls; the host attaches the server right after
+    Tool(const std::string& name, bool once = false) : _C(nullptr), _name(name), _once(once) {}
+    void attach(CalcServer* C) { _C = C; }
     virtual ~Tool() {}
     const std::string& name() const { return _name; }
     virtual void setup() {}

@@ -43,6 +43,12 @@ SCRIPTS = [
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 
+# Tool-layer kernels (embedded by the reference's build into its C++ tools, with the matching
+# .hcl.in header prepended): only those without work-group cooperation can run one item at a
+# time -- LinkList.cl.in (iHoc, iCell, linkList).  RadixSort.cl.in scans through __local memory
+# between barriers and stays pinned by the reference's own property tests.
+TOOL_SCRIPTS = [("aquagpusph/CalcServer/LinkList.cl.in", "aquagpusph/CalcServer/LinkList.hcl.in")]
+
 VEC_LITERAL = re.compile(r"\(\s*(float2|float3|float4|float16|matrix|vec|vec2|vec3|vec4|vec_xyz)\s*\)\s*\(")
 MACRO_PARAMS = {
     "LINKLIST_LOCAL_PARAMS": ["icell", "ihoc", "n_cells"],
@@ -66,6 +72,14 @@ def mirror(tmp):
             dst = os.path.join(tmp, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             with open(p, encoding="utf-8", errors="replace") as f:
+                txt = f.read()
+            with open(dst, "w") as f:
+                f.write(rewrite(txt))
+    for files in TOOL_SCRIPTS:
+        for rel in files:
+            dst = os.path.join(tmp, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            with open(os.path.join(REF, rel), encoding="utf-8", errors="replace") as f:
                 txt = f.read()
             with open(dst, "w") as f:
                 f.write(rewrite(txt))
@@ -103,15 +117,21 @@ def mangle(script):
     return re.sub(r"\W", "_", script[:-3])
 
 
-def wrapper(script, dims):
-    tag = mangle(script)
-    ks = kernels_of(os.path.join(REF, "resources", "Scripts", script))
+def wrapper(script, dims, header=None):
+    """header: a tool-layer script (path relative to the reference root) and the .hcl.in the
+    reference's build prepends to it."""
+    tag = mangle(os.path.basename(script)[:-3] if header else script)
+    ks = kernels_of(os.path.join(REF, script) if header else os.path.join(REF, "resources", "Scripts", script))
     lines = ["#define HAVE_%dD 1" % dims, '#include "cl_shim.hpp"']
     for entry, _, _ in ks:
         lines.append("#define %s aqrefk_%s__%s" % (entry, tag, entry))
     # the type headers define non-inline helpers (outer, det, inv): keep them TU-local
     lines.append("namespace {")
-    lines.append('#include "resources/Scripts/%s"' % script)
+    if header:
+        lines.append('#include "%s"' % header)
+        lines.append('#include "%s"' % script)
+    else:
+        lines.append('#include "resources/Scripts/%s"' % script)
     lines.append("}")
     for entry, _, _ in ks:
         lines.append("#undef %s" % entry)
@@ -132,7 +152,7 @@ def wrapper(script, dims):
                 t = " ".join(p_.replace("const", "").split()[:-1])
                 kinds.append({"float": "float", "usize": "uint", "uint": "uint", "unsigned int": "uint",
                               "int": "int", "vec": "vec", "svec4": "svec4", "uivec4": "svec4",
-                              "vec4": "vec4"}[t])
+                              "vec4": "vec4"}[t.strip()])
         out.append((entry, names, kinds))
     return "\n".join(lines) + "\n", out
 
@@ -173,6 +193,12 @@ def build(verbose=False):
                 open(src, "w").write(txt)
                 jobs.append((src, src[:-4] + ".o"))
                 index[s] = ks
+            for s, hdr in TOOL_SCRIPTS:
+                txt, ks = wrapper(s, dims, hdr)
+                src = os.path.join(d, "tool_" + mangle(os.path.basename(s)[:-3]) + ".cpp")
+                open(src, "w").write(txt)
+                jobs.append((src, src[:-4] + ".o"))
+                index[os.path.basename(s)[:-3]] = ks
 
             def cc(job):
                 cmd = [cxx] + flags + ["-I" + tmp, "-c", job[0], "-o", job[1]]

@@ -325,3 +325,44 @@ def test_bi_noslip_matches_reference_script(oracle, dims, n, hfac):
     assert c.get("lap_u").tobytes() == got.tobytes()
     fl = s["imove"] == 1
     assert np.abs(got - lap)[fl].max() > 0 and np.array_equal(got[~fl], lap[~fl])
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_linklist_tool_kernels_match_the_reference_source(oracle, golden, dims):
+    """The tool layer: aquagpusph/CalcServer/LinkList.cl.in (iCell :54-85, iHoc :32-42, linkList
+    :92-113), compiled from the reference tree behind the shim with its LinkList.hcl.in, against
+    the restatement oracle/aqo_linklist.c -- cell index of every particle and the head-of-cell
+    table BIT for bit, on the reference's own LinkList test particles, on a dam break with buffer
+    particles far away (a grid much larger than the fluid) and on random positions.  The radix
+    sort between the two kernels keeps its property tests (RadixSort.cl.in scans through __local
+    memory between barriers: it cannot run one work-item at a time)."""
+    R = ref.Ref(dims, 0.1)
+    V = 4 if dims == 3 else 2
+    rng = np.random.default_rng(17)
+    case = cases.dam_break(dims, 12 if dims == 3 else 50, 2.0)
+    sets = [(np.ascontiguousarray(golden["linklist_%dD_r" % dims], np.float32), 0.1),
+            (case["r"], case["h"])]
+    rnd = np.zeros((5000, V), np.float32)
+    rnd[:, :dims] = rng.normal(size=(5000, dims)).astype(np.float32) * 3.0
+    sets.append((rnd, 0.37))
+    for r, h in sets:
+        r = np.ascontiguousarray(r, np.float32)
+        if r.shape[1] != V:
+            rr = np.zeros((r.shape[0], V), np.float32)
+            rr[:, :min(V, r.shape[1])] = r[:, :min(V, r.shape[1])]
+            r = rr
+        N = r.shape[0]
+        ll = oracle.linklist(r, dims, 2.0, h)
+        # iCell on the unsorted positions == the oracle's sorted cells, un-permuted
+        icell = np.zeros(N, np.uint32)
+        R.run("LinkList.cl", "iCell", N, dict(icell=icell, r=r, N=N, r_min=ll["rmin"], support=2.0, h=h,
+                                               n_cells=ll["ncells"]))
+        assert np.array_equal(icell[ll["perm"]], ll["icell"])
+        assert np.all(np.diff(ll["icell"].astype(np.int64)) >= 0)
+        # iHoc + linkList on the sorted cells
+        ncw = int(ll["ncells"][3])
+        ihoc = np.zeros(ncw, np.uint32)
+        R.run("LinkList.cl", "iHoc", ncw, dict(ihoc=ihoc, N=N, n_cells=ll["ncells"]))
+        assert np.all(ihoc == N)
+        R.run("LinkList.cl", "linkList", N, dict(icell=ll["icell"], ihoc=ihoc, N=N))
+        assert np.array_equal(ihoc, ll["ihoc"][:ncw])
