@@ -28,6 +28,7 @@ SYMBOLS = [
     "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
     "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_fp32_peak",
+    "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -120,6 +121,9 @@ def lib():
                                   C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.aqc_mpi_sync_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.aqc_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.aqc_watch_create.argtypes = [C.c_void_p]
+    L.aqc_watch_dirty.argtypes = [C.c_void_p, C.c_int]
+    L.aqc_watch_reset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]

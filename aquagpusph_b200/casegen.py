@@ -211,6 +211,10 @@ def multi_device_fixes(txt):
         # after the first reuses the first one's sort and counts (MPISync `depends`, ours)
         txt = re.sub(r'(<Tool [^>]*name="mpi neighs sync" [^>]*?)(\s*/>)',
                      lambda m: m.group(1) + ' depends="r,imove"' + m.group(2), txt, 1)
+        # ... and so does the halo link-list: the positions it hashes are the neighbours' r, fixed
+        # on every rank at once (link-list `depends`, ours)
+        txt = re.sub(r'(<Tool [^>]*name="mpi link-list" [^>]*?)(\s*/>)',
+                     lambda m: m.group(1) + ' depends="r,imove"' + m.group(2), txt, 1)
     txt = add_tool_after(txt, "cfd minimum time step",
                          '<Tool action="add" name="mpi global dt" type="mpi-allreduce" once="false" '
                          'in="dt" operation="min" />')

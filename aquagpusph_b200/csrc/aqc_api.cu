@@ -432,6 +432,35 @@ extern "C" int aqc_launch(aqc_ctx* ctx, int id, size_t n, void* const* args, int
     return reg[id].fn(ctx, n, args);
 }
 
+// ---- write watches ---------------------------------------------------------------------------
+extern "C" int aqc_watch_create(aqc_ctx* ctx)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    ctx->watches.emplace_back();
+    return (int)ctx->watches.size() - 1;
+}
+
+extern "C" int aqc_watch_dirty(const aqc_ctx* ctx, int watch)
+{
+    if (!ctx || watch < 0 || watch >= (int)ctx->watches.size())
+        return 1;
+    return ctx->watches[watch].dirty ? 1 : 0;
+}
+
+extern "C" int aqc_watch_reset(aqc_ctx* ctx, int watch, int n, const void* const* ptrs, const size_t* bytes)
+{
+    if (!ctx || watch < 0 || watch >= (int)ctx->watches.size() || (n > 0 && (!ptrs || !bytes)))
+        return AQC_ERR_ARG;
+    aqc_watch& w = ctx->watches[watch];
+    w.ranges.clear();
+    for (int k = 0; k < n; k++)
+        if (ptrs[k])
+            w.ranges.emplace_back((const char*)ptrs[k], bytes[k]);
+    w.dirty = w.ranges.empty();
+    return AQC_OK;
+}
+
 // ---- pair-mask cache of the neighbour sweeps (sweep.cuh, S3Cache) ------------------------
 extern "C" int aqc_pairs_cache_enable(aqc_ctx* ctx, int on)
 {

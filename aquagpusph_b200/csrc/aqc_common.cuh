@@ -65,6 +65,13 @@ struct aqc_sync_plan {
     uint64_t full = 0, reused = 0;
 };
 
+// Device ranges a caller wants to know about: dirty as soon as one of them is written through the
+// library (aqc_watch_*: what lets a tool skip work whose inputs have not changed)
+struct aqc_watch {
+    std::vector<std::pair<const char*, size_t>> ranges;
+    bool dirty = true;
+};
+
 struct aqc_ctx {
     aqc_pair_cache pc;
     int device = 0;
@@ -114,6 +121,7 @@ struct aqc_ctx {
     size_t comm_send_cap = 0;
     bool comm_dead = false;            // the communicator was aborted (a peer is gone, a local fault)
     std::vector<aqc_sync_plan> plans;  // aqc_mpi_sync_plan slots
+    std::vector<aqc_watch> watches;    // aqc_watch_create slots
 };
 
 int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
@@ -147,6 +155,11 @@ static inline void aqc_pc_touch(aqc_ctx* ctx, const void* ptr, size_t bytes)
         return;
     const char* a = (const char*)ptr;
     const char* b = a + (bytes ? bytes : 1);
+    for (aqc_watch& w : ctx->watches)
+        if (!w.dirty)
+            for (auto& d : w.ranges)
+                if (a < d.first + d.second && d.first < b)
+                    w.dirty = true;
     for (aqc_sync_plan& pl : ctx->plans) // mpi-sync plans die with the arrays their mask derives from
         if (pl.valid)
             for (auto& d : pl.deps)

@@ -1555,6 +1555,7 @@ int aqc_sweep_engine();      // 2 or 3 (AQC_SWEEP_ENGINE, default 3)
 bool aqc_sweep_engine_forced(); // chosen explicitly (environment or aqc_sweep_engine_select)
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
 int aqc_sweep_ring2();       // ring rounds of the mask-reading sweeps (AQC_SWEEP_RING2)
+int aqc_remote_engine();     // 2 or 3 (AQC_REMOTE_ENGINE)
 int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2, const LLParams& ll,
                    uint32_t icls, uint32_t jcls, int K, S3Cache* out); // sweeps.cu
 
@@ -1588,7 +1589,8 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         // set-up of v3 does not pay (measured: 2-D dam break, 0.38 M particles, 1.44 vs 1.20 ms
         // per step; 7.4 M: 12.8 vs 15.3)
         const bool small2d = (P::DIMS == 2) && ll.N < (1u << 20) && !aqc_sweep_engine_forced();
-        if (aqc_sweep_engine() == 3 && !P::SPARSE_I && !small2d) {
+        const bool sparse = P::SPARSE_I && !(P::REMOTE && aqc_remote_engine() == 3);
+        if (aqc_sweep_engine() == 3 && !sparse && !small2d) {
             int K = aqc_sweep_ring(P::NJ4);
             S3Cache pc;
             int cached = 0;

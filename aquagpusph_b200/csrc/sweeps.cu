@@ -73,6 +73,16 @@ int aqc_sweep_ring(int nj4)
     return 3;
 }
 
+int aqc_remote_engine() // engine of the remote (halo) sweeps: 2 (per warp, default) or 3 (CTA rings)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AQC_REMOTE_ENGINE");
+        v = (e && atoi(e) == 3) ? 3 : 2;
+    }
+    return v;
+}
+
 int aqc_sweep_ring2()
 {
     static const int forced = [] {
@@ -177,6 +187,8 @@ struct PBase {
     static constexpr bool CACHE = false;
     // v4 engine: body_all() / needs_all() exist (see PFusedFluid)
     static constexpr bool HAS_BODY_ALL = false;
+    // the j list is a remote (halo) one: SPARSE_I by default, the CTA engine with AQC_REMOTE_ENGINE=3
+    static constexpr bool REMOTE = false;
     uint32_t icls() const { return 0xFFu; }
     uint32_t jcls() const { return 0xFFu; }
 };
@@ -731,6 +743,7 @@ struct PBIePST : PBase {
 template <int D>
 struct PMpiGamma : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
     static constexpr int DIMS = D, NJ4 = 1;
     const void *r, *mpi_r;
@@ -766,6 +779,7 @@ struct PMpiGamma : PBase {
 template <int D>
 struct PMpiInteractions : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;
@@ -827,6 +841,7 @@ struct PMpiInteractions : PBase {
 template <int D>
 struct PMpiFused : PBase {
     static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true;
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;

@@ -447,6 +447,7 @@ LinkList::LinkList(CalcServer* C, const std::string& name, const ProblemSetup::T
   , _ihoc_name(t.get("ihoc")), _icell_name(t.get("icell")), _ncells_name(t.get("n_cells"))
   , _perm_name(t.get("perm")), _inv_name(t.get("inv_perm"))
   , _recompute(toLowerCopy(t.get("recompute_grid")) != "false")
+  , _depends_txt(t.get("depends"))
 {
     const std::string sorter = t.get("sorter");
     if (!sorter.empty() && sorter != "radix-sort" && sorter != "bitonic")
@@ -464,6 +465,9 @@ void LinkList::setup()
     _ncells = variable(_ncells_name, false, true);
     _perm = variable(_perm_name, true);
     _inv = variable(_inv_name, true);
+    for (auto& d : split(_depends_txt))
+        if (!trimCopy(d).empty())
+            _depends.push_back(variable(trimCopy(d), true));
     _N = variable("N", false, true);
     _support = variable("support", false, true);
     _h = variable("h", false, true);
@@ -475,6 +479,23 @@ void LinkList::setup()
 
 void LinkList::_execute()
 {
+    static const bool verify = getenv("AQC_MPI_VERIFY") && atoi(getenv("AQC_MPI_VERIFY"));
+    std::vector<uint32_t> old_icell, old_perm;
+    if (!_depends.empty()) {
+        if (_watch < 0)
+            _watch = aqc_watch_create(_C->ctx());
+        if (!aqc_watch_dirty(_C->ctx(), _watch) && _built_in == _in->dptr() && _built_n == _in->length()) {
+            if (!verify) {
+                _skipped++;
+                return;
+            }
+            // tests: build anyway and require the outputs to be what they were
+            old_icell.resize(_icell->length());
+            old_perm.resize(_perm->length());
+            check(aqc_memcpy_d2h(_C->ctx(), old_icell.data(), _icell->dptr(), _icell->size(), 1));
+            check(aqc_memcpy_d2h(_C->ctx(), old_perm.data(), _perm->dptr(), _perm->size(), 1));
+        }
+    }
     float rmin[4] = { 0, 0, 0, 0 }, rmax[4] = { 0, 0, 0, 0 };
     memcpy(rmin, _min->get(), _min->typesize());
     memcpy(rmax, _max->get(), _max->typesize());
@@ -495,6 +516,26 @@ void LinkList::_execute()
     }
     _ncells->set(nc);
     _C->variables()->populate(_ncells);
+    if (!old_icell.empty()) {
+        std::vector<uint32_t> now_icell(old_icell.size()), now_perm(old_perm.size());
+        check(aqc_memcpy_d2h(_C->ctx(), now_icell.data(), _icell->dptr(), _icell->size(), 1));
+        check(aqc_memcpy_d2h(_C->ctx(), now_perm.data(), _perm->dptr(), _perm->size(), 1));
+        if (now_icell != old_icell || now_perm != old_perm)
+            throw std::runtime_error("The tool \"" + name() + "\" would have skipped a build whose result "
+                                     "changed: its depends list is incomplete");
+        _skipped++;
+    }
+    if (!_depends.empty()) {
+        std::vector<const void*> ptrs;
+        std::vector<size_t> bytes;
+        for (auto v : _depends) {
+            ptrs.push_back(v->dptr());
+            bytes.push_back(v->length() * v->typesize());
+        }
+        check(aqc_watch_reset(_C->ctx(), _watch, (int)ptrs.size(), ptrs.data(), bytes.data()));
+        _built_in = _in->dptr();
+        _built_n = _in->length();
+    }
 }
 
 // ---------------------------------------------------------------- RadixSort --

@@ -223,7 +223,12 @@ class Reduction : public Tool {
     std::vector<char> _identity;
 };
 
-/// type="link-list" (LinkList.cpp:326-494)
+/// type="link-list" (LinkList.cpp:326-494).
+/// `depends` (not a reference attribute; empty = the reference's behaviour) names the arrays whose
+/// writes are the only way the input positions can change: while none of them is written through
+/// the library a later execution finds its outputs (icell, ihoc, permutations) still valid and
+/// does nothing -- the halo list of the slab pipelines inside the midpoint loop, whose input is
+/// re-filled with the same positions in every sub-iteration.
 class LinkList : public Tool {
   public:
     LinkList(CalcServer* C, const std::string& name, const InputOutput::ProblemSetup::Tool& t, bool once);
@@ -235,6 +240,14 @@ class LinkList : public Tool {
         _inv_name;
     bool _recompute;
     InputOutput::Variable *_in, *_min, *_max, *_ihoc, *_icell, *_ncells, *_perm, *_inv, *_N, *_support, *_h;
+    std::string _depends_txt;
+    std::vector<InputOutput::Variable*> _depends;
+    int _watch = -1;
+    const void* _built_in = nullptr;   // input pointer and length of the build the watch guards
+    size_t _built_n = 0;
+    uint64_t _skipped = 0;
+  public:
+    uint64_t skipped() const { return _skipped; }
 };
 
 /// type="radix-sort" / "sort" (RadixSort.cpp:129-303)

@@ -217,6 +217,10 @@ void State::configureTool(ProblemSetup::Tool* tool, const Xml::Node* e, ProblemS
         toolAttr(tool, e, "inv_perm", "id_sorted");
         toolAttr(tool, e, "recompute_grid", "true");
         toolAttr(tool, e, "sorter", "radix-sort");
+        // (ours, optional) arrays whose writes are the only way the input positions can change:
+        // see calcserver.hpp, LinkList
+        if (e->has("depends"))
+            toolAttr(tool, e, "depends");
     } else if (type == "radix-sort" || type == "sort") {
         for (auto a : { "in", "perm", "inv_perm" })
             toolAttr(tool, e, a);
@@ -232,7 +236,8 @@ void State::configureTool(ProblemSetup::Tool* tool, const Xml::Node* e, ProblemS
         toolAttr(tool, e, "fields");
         toolAttr(tool, e, "processes", "");
         // (ours, optional) the arrays the mask is a function of: see calcserver.hpp, MPISync
-        toolAttr(tool, e, "depends", "");
+        if (e->has("depends"))
+            toolAttr(tool, e, "depends");
     } else if (type == "mpi-allreduce") { // not a reference tool, see calcserver.hpp
         toolAttr(tool, e, "in");
         toolAttr(tool, e, "operation", "min");

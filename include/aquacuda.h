@@ -197,6 +197,14 @@ int aqc_pairs_cache_invalidate(aqc_ctx* ctx);
 /* builds / sweeps served so far, bytes of device memory held (any pointer may be NULL) */
 int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes);
 
+/* ---- write watches: a set of device ranges that turns dirty as soon as one of them is written
+ * through this library (the mechanism behind the pair cache and the mpi-sync plans, for callers).
+ * The host's link-list tool uses one to skip the re-build of a list whose positions cannot have
+ * changed (`depends`).  A new watch is dirty; aqc_watch_reset arms it. ------ */
+int aqc_watch_create(aqc_ctx* ctx); /* returns a watch id >= 0 */
+int aqc_watch_dirty(const aqc_ctx* ctx, int watch);
+int aqc_watch_reset(aqc_ctx* ctx, int watch, int n, const void* const* ptrs, const size_t* bytes);
+
 /* ---- multi-device: one process per GPU, NCCL over NVLink.  Replaces the MPI
  * rank/size queries and wrappers (AuxiliarMethods.cpp:388-516) and the MPISync
  * tool (MPISync.cpp:183-232; kernels MPISync.cl.in:31-80), whose host-staged
