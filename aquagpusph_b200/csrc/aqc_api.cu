@@ -63,7 +63,8 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
         return;
     cudaSetDevice(ctx->device);
     aqc_comm_destroy(ctx); // (drains the stream with a deadline while a communicator is live)
-    cudaStreamSynchronize(ctx->stream);
+    if (!ctx->comm_dead)   // (after an abort a kernel of this rank may never end)
+        cudaStreamSynchronize(ctx->stream);
     for (int k = 0; k < 2; k++) {
         cudaFree(ctx->sort_keys[k]);
         cudaFree(ctx->sort_vals[k]);

@@ -120,6 +120,7 @@ struct aqc_ctx {
     void* comm_send = nullptr;         // packed outgoing fields
     size_t comm_send_cap = 0;
     bool comm_dead = false;            // the communicator was aborted (a peer is gone, a local fault)
+    void* comm_watchdog = nullptr;     // backstop thread of the bounded waits (mpi.cu)
     std::vector<aqc_sync_plan> plans;  // aqc_mpi_sync_plan slots
     std::vector<aqc_watch> watches;    // aqc_watch_create slots
 };

@@ -13,6 +13,11 @@
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <time.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <memory>
+#include <thread>
 
 #include "aqc_common.cuh"
 
@@ -172,6 +177,82 @@ double now_s()
     return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
+double comm_timeout_s();
+
+// Backstop of the bounded waits.  aqc_comm_wait covers a host that waits for the device; a host
+// that is stuck INSIDE an NCCL call (the enqueue of a collective whose peer process has died can
+// block in the library), or that never comes back to a wait, is caught here: a thread per
+// communicator watches the time since collective work was queued on a stream that has not
+// drained.  After the time-out (+ a grace period that lets the in-line path report first) it
+// says why on stderr, tries ncclCommAbort and ends the process with exit code 70 -- a job with a
+// dead rank must end, not spin (round 1: three ranks held their GPUs for 870 s).
+struct Watchdog {
+    std::thread th;
+    std::atomic<bool> stop{ false };
+    std::atomic<long long> busy_since_ms{ 0 }; // 0: nothing pending
+};
+
+long long now_ms() { return (long long)(now_s() * 1e3); }
+
+void watchdog_loop(aqc_ctx* ctx, Watchdog* w)
+{
+    cudaSetDevice(ctx->device);
+    const long long limit_ms = (long long)((comm_timeout_s() + 5.0) * 1e3);
+    while (!w->stop.load()) {
+        usleep(200 * 1000);
+        const long long b = w->busy_since_ms.load();
+        if (!b || w->stop.load())
+            continue;
+        if (cudaStreamQuery(ctx->stream) == cudaSuccess) {
+            long long expect = b;
+            w->busy_since_ms.compare_exchange_strong(expect, 0);
+            continue;
+        }
+        if (now_ms() - b > limit_ms) {
+            fprintf(stderr, "aquacuda watchdog: rank %d of %d: collective work has been pending for %.0f s "
+                            "(AQC_COMM_TIMEOUT_S + 5): a peer is gone or this rank is stuck inside NCCL; "
+                            "aborting the communicator and ending the process (exit code 70)\n",
+                    ctx->rank, ctx->nranks, (now_ms() - b) * 1e-3);
+            fflush(stderr);
+            void* c = ctx->comm;
+            if (c && g_nccl.CommAbort)
+                std::thread([c]() { g_nccl.CommAbort((nccl_comm)c); }).detach(); // (may block too)
+            usleep(2000 * 1000);
+            _exit(70);
+        }
+    }
+}
+
+void comm_mark_busy(aqc_ctx* ctx)
+{
+    Watchdog* w = (Watchdog*)ctx->comm_watchdog;
+    if (!w)
+        return;
+    long long expect = 0;
+    w->busy_since_ms.compare_exchange_strong(expect, now_ms());
+}
+
+void comm_mark_idle(aqc_ctx* ctx)
+{
+    Watchdog* w = (Watchdog*)ctx->comm_watchdog;
+    if (w)
+        w->busy_since_ms.store(0);
+}
+
+void watchdog_stop(aqc_ctx* ctx)
+{
+    Watchdog* w = (Watchdog*)ctx->comm_watchdog;
+    if (!w)
+        return;
+    ctx->comm_watchdog = nullptr;
+    w->stop.store(true);
+    if (w->th.joinable() && w->th.get_id() != std::this_thread::get_id())
+        w->th.join();
+    else if (w->th.joinable())
+        w->th.detach();
+    delete w;
+}
+
 double comm_timeout_s()
 {
     static double v = -1.0;
@@ -216,7 +297,16 @@ void aqc_comm_abort(aqc_ctx* ctx)
     nccl_comm c = (nccl_comm)ctx->comm;
     ctx->comm = nullptr;
     ctx->comm_dead = true;
-    g_nccl.CommAbort(c); // also ends the kernels of this rank that wait for the peer
+    comm_mark_idle(ctx); // (the watchdog stands down: the failure is being reported in line)
+    // ncclCommAbort also ends the kernels of this rank that wait for the peer; it can block itself
+    // when the peer process is gone, so it gets five seconds on a thread of its own
+    auto done = std::make_shared<std::atomic<bool>>(false);
+    std::thread([c, done]() {
+        g_nccl.CommAbort(c);
+        done->store(true);
+    }).detach();
+    for (int k = 0; k < 500 && !done->load(); k++)
+        usleep(10 * 1000);
 }
 
 int aqc_comm_wait(aqc_ctx* ctx, cudaEvent_t ev)
@@ -225,8 +315,11 @@ int aqc_comm_wait(aqc_ctx* ctx, cudaEvent_t ev)
     unsigned polls = 0;
     for (;;) {
         const cudaError_t e = ev ? cudaEventQuery(ev) : cudaStreamQuery(ctx->stream);
-        if (e == cudaSuccess)
+        if (e == cudaSuccess) {
+            if (!ev)
+                comm_mark_idle(ctx);
             return AQC_OK;
+        }
         if (e != cudaErrorNotReady) {
             char msg[256];
             snprintf(msg, sizeof(msg), "%s", cudaGetErrorString(e));
@@ -289,6 +382,14 @@ extern "C" int aqc_comm_init(aqc_ctx* ctx, int rank, int size, const void* uniqu
     nccl_comm comm = nullptr;
     AQC_NCCL(ctx, g_nccl.CommInitRank(&comm, size, id, rank));
     ctx->comm = comm;
+    {
+        const char* e = getenv("AQC_COMM_WATCHDOG");
+        if (!(e && atoi(e) == 0)) {
+            Watchdog* w = new Watchdog();
+            ctx->comm_watchdog = w;
+            w->th = std::thread(watchdog_loop, ctx, w);
+        }
+    }
     // [2P] own counts + peer flags, then [P][2P] gathered
     AQC_CUDA(ctx, cudaMalloc(&ctx->comm_counts, (size_t)2 * size * (size + 1) * sizeof(uint32_t) + 256));
     AQC_CUDA(ctx, cudaMallocHost(&ctx->comm_counts_host, (size_t)2 * size * (size + 1) * sizeof(uint32_t)));
@@ -299,6 +400,7 @@ extern "C" int aqc_comm_destroy(aqc_ctx* ctx)
 {
     if (!ctx)
         return AQC_ERR_ARG;
+    watchdog_stop(ctx);
     if (ctx->comm) {
         // a clean shutdown drains the stream first; if that does not end (a peer left
         // without its matching call) the communicator is aborted instead of destroyed
@@ -379,6 +481,7 @@ int sync_exchange(aqc_ctx* ctx, const aqc_sync_plan& pl, const uint32_t* perm, a
             }
     // exchange, device to device.  A failure between GroupStart and GroupEnd still closes the
     // group, and any NCCL failure aborts the communicator: the peers' waits then end too.
+    comm_mark_busy(ctx);
     int nrc = g_nccl.GroupStart();
     bool opened = nrc == 0;
     for (int p = 0; p < P && nrc == 0; p++) {
@@ -525,6 +628,7 @@ extern "C" int aqc_mpi_sync_ex(aqc_ctx* ctx, int plan, aqc_usize* mask, aqc_usiz
         AQC_LAUNCH_CHECK(ctx);
     }
     {
+        comm_mark_busy(ctx);
         const int nrc = g_nccl.AllGather(d_mine, d_all, 2 * P, NCCL_UINT32, (nccl_comm)ctx->comm, ctx->stream);
         if (nrc != 0) {
             aqc_comm_abort(ctx);
@@ -603,6 +707,7 @@ extern "C" int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, si
         default: return aqc_fail(ctx, AQC_ERR_ARG, "aqc_allreduce: unknown type %d", type);
     }
     const int nop = op == AQC_OP_SUM ? NCCL_SUM : (op == AQC_OP_MIN ? NCCL_MIN : NCCL_MAX);
+    comm_mark_busy(ctx);
     const int nrc = g_nccl.AllReduce(dev_inout, dev_inout, count * ncomp, nt, nop, (nccl_comm)ctx->comm,
                                      ctx->stream);
     if (nrc != 0) {
@@ -644,6 +749,7 @@ int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys)
         return aqc_fail(ctx, AQC_ERR_NCCL, "link-list: rank %d: the communicator was aborted", ctx->rank);
     if (ctx->nranks <= 1 || !ctx->comm)
         return AQC_OK;
+    comm_mark_busy(ctx);
     int nrc = g_nccl.GroupStart();
     if (nrc == 0) {
         nrc = g_nccl.AllReduce(keys, keys, 4, NCCL_UINT32, NCCL_MIN, (nccl_comm)ctx->comm, ctx->stream);

@@ -37,6 +37,9 @@ struct LLParams {
     // the kernel's j set is made of; a cell without any of them is not visited
     const uint8_t* __restrict__ cls = nullptr;
     uint32_t jmask = 0xFFu;
+    // optional (remote lists): near[c] != 0 when one of the 3^D cells around c holds a j particle;
+    // a warp none of whose particles sits in such a cell has nothing to do
+    const uint8_t* __restrict__ near = nullptr;
 };
 
 __host__ __device__ inline uint32_t aqc_cls_bit(int mv)
@@ -59,6 +62,29 @@ static __global__ void cell_class_kernel(const int* __restrict__ imove, const ui
     if (i > 0 && (threadIdx.x & 31) && __ldg(icell + i - 1) == c && aqc_cls_bit(__ldg(imove + i - 1)) == bit)
         return; // the previous lane does it
     atomicOr(reinterpret_cast<uint32_t*>(cls) + (c >> 2), bit << (8u * (c & 3u)));
+}
+
+// near[c'] = 1 for the 3^D cells c' around every cell that heads a run of the sorted list `icell`
+// (near zeroed before).  The halo of a slab occupies a few layers of cells next to its cuts: the
+// remote sweeps of cfd/MPI.cl visit every local particle, and all but those layers find 27 empty
+// cells -- with the flags they leave after one byte load.
+static __global__ void remote_near_kernel(const uint32_t* __restrict__ icell, uint32_t n, uint32_t nx, uint32_t ny,
+                                          uint32_t nw, int dims, uint8_t* __restrict__ near)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t c = __ldg(icell + i);
+    if (c >= nw || (i > 0 && __ldg(icell + i - 1) == c))
+        return;
+    const int kz = dims == 3 ? 1 : 0;
+    for (int dz = -kz; dz <= kz; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const uint32_t cc = c + (uint32_t)dx + (uint32_t)dy * nx + (uint32_t)dz * nx * ny;
+                if (cc < nw)
+                    near[cc] = 1;
+            }
 }
 
 constexpr float AQC_FAR = 3.0e38f; // staged position of an excluded j
@@ -97,6 +123,8 @@ sweep_kernel(const P p, const LLParams ll)
     if (!remaining)
         return;
     const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    if (ll.near && !__any_sync(0xffffffffu, active && c_i < ll.nw && ll.near[c_i < ll.nw ? c_i : 0]))
+        return;
     typename P::IState st;
     if (active)
         p.load_i(st, i);
@@ -273,6 +301,8 @@ sweep2_kernel(const P p, const LLParams ll)
     if (!remaining)
         return;
     const uint32_t c_i = active ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    if (ll.near && !__any_sync(0xffffffffu, active && c_i < ll.nw && ll.near[c_i < ll.nw ? c_i : 0]))
+        return;
     typename P::IState st;
     st.x = st.y = st.z = 0.f;
     if (active)
@@ -1583,6 +1613,31 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         AQC_LAUNCH_CHECK(ctx);
         ll.cls = ctx->cell_cls;
         ll.jmask = P::JCLS;
+    }
+    if constexpr (P::REMOTE) {
+        // remote (halo) list: flag the cells that have a halo particle in their 3^D neighbourhood
+        // (AQC_REMOTE_NEAR=0: every warp walks its 27 cells, as before)
+        static const bool use_near = !(getenv("AQC_REMOTE_NEAR") && atoi(getenv("AQC_REMOTE_NEAR")) == 0);
+        if (use_near && aqc_remote_engine() != 3) {
+            const size_t need = ((size_t)ll.nw + 3) & ~(size_t)3;
+            if (need > ctx->cell_cls_cap) {
+                if (ctx->cell_cls) {
+                    AQC_SYNC(ctx);
+                    cudaFree(ctx->cell_cls);
+                }
+                ctx->cell_cls = nullptr;
+                ctx->cell_cls_cap = 0;
+                AQC_CUDA(ctx, cudaMalloc(&ctx->cell_cls, need + need / 4));
+                ctx->cell_cls_cap = need + need / 4;
+            }
+            AQC_CUDA(ctx, cudaMemsetAsync(ctx->cell_cls, 0, need, ctx->stream));
+            // (the halo rows head the sorted remote list; what follows them is the pile of
+            // unused rows parked at r_max by cfd/MPI.cl::backup_r, flagged through its first row)
+            remote_near_kernel<<<aqc_blocks(ll.N, 256), 256, 0, ctx->stream>>>(ll.icell, ll.N, ll.nx, ll.ny, ll.nw,
+                                                                              P::DIMS, ctx->cell_cls);
+            AQC_LAUNCH_CHECK(ctx);
+            ll.near = ctx->cell_cls;
+        }
     }
     if constexpr (P::SPHERE) {
         // 2-D sweeps have ~20x less work per particle: below ~1 M particles the CTA-wide

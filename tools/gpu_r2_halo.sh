@@ -3,7 +3,7 @@
 # profile of the slab pipeline
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_mpi.py tests/test_gpu_presets.py -x -q -m gpu -k "gpus or dead_peer or slabs or mpi_plane or random_masks" > gpurun_out/r2_pytest_mpi_${N}gpu_h.log 2>&1
+timeout 1200 python -m pytest tests/test_gpu_mpi.py tests/test_gpu_presets.py -x -q -m gpu -k "${KSEL:-gpus or dead_peer or slabs or mpi_plane or random_masks}" > gpurun_out/r2_pytest_mpi_${N}gpu_h.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2_pytest_mpi_${N}gpu_h.log
 tail -6 gpurun_out/r2_pytest_mpi_${N}gpu_h.log
 run() { # tag extra-env
@@ -16,9 +16,7 @@ for l in open("gpurun_out/r2_halo_${N}gpu_$1.json"):
         d=json.loads(l); print("$1", round(d["ms_per_step"],3), d["config"]["mean_inner_iterations"], d["config"]["one_gpu_same_pipeline"])
 PY
 }
-run engine2 AQC_REMOTE_ENGINE=2
-run engine3 AQC_REMOTE_ENGINE=3
-AQUA_PROFILE_SYNC=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29545 tools/prof_slabs.py 1000000 > gpurun_out/r2_prof_slabs_${N}gpu_e2.log 2>&1
-AQC_REMOTE_ENGINE=3 AQUA_PROFILE_SYNC=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29546 tools/prof_slabs.py 1000000 > gpurun_out/r2_prof_slabs_${N}gpu_e3.log 2>&1
-grep "rank 0" gpurun_out/r2_prof_slabs_${N}gpu_e2.log | head -22
-grep "rank 0" gpurun_out/r2_prof_slabs_${N}gpu_e3.log | grep "mpi\|ms/step over" | head -14
+run near1 AQC_REMOTE_NEAR=1
+run near0 AQC_REMOTE_NEAR=0
+AQUA_PROFILE_SYNC=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29545 tools/prof_slabs.py 1000000 > gpurun_out/r2_prof_slabs_${N}gpu_near.log 2>&1
+grep "^rank 0" gpurun_out/r2_prof_slabs_${N}gpu_near.log | grep "mpi\|ms/step over" | head -14

@@ -36,6 +36,6 @@ if rank in (0, world - 1):
     tot = sum(r[0] for r in rows)
     print("rank %d: %.2f ms/step over %d tools" % (rank, tot / steps, len(rows)))
     for ms, k, name in rows[:28]:
-        print("rank %d  %-40s x%-3d %8.3f ms/step" % (rank, name, k // steps, ms / steps))
+        print("rank %d  %-40s x%-3d %8.3f ms/step" % (rank, name, k // steps, ms / steps), flush=True)
 if world > 1:
     dist.destroy_process_group()
