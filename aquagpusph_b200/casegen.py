@@ -225,15 +225,107 @@ def multi_device_fixes(txt):
     return txt
 
 
+def _tool_text(txt, name):
+    m = re.search(r'\n[ \t]*(<Tool [^>]*name="%s" [^>]*?(/>|>.*?</Tool>))' % re.escape(name), txt, flags=re.S)
+    if not m:
+        raise KeyError("tool %s not found" % name)
+    return m.group(1)
+
+
+def slab_delta_sph(txt, delta=0.1):
+    """The slab pipeline of the reference's MPI example (after multi_device_fixes) with the
+    delta-SPH and MLS stages of the single-device dam break (examples/3D/spheric_testcase2_dambreak:
+    presets cfd/deltaSPH-full.xml + basic/MLS.xml): what BASELINE config 2 runs on one GPU, on N.
+
+    The reference cannot do this: its MPI preset exchanges r, u, rho, m of the halo and adds the
+    remote terms of cfd/Interactions.cl and the Shepard factor only (cfd/MPI.xml:59-87).  Here
+      * the halo is exchanged once more BEFORE the midpoint loop (the MLS matrix is computed there,
+        basic/MLS.xml), which also builds the halo link-list for the whole step: positions are
+        fixed inside the loop, so the in-loop copy of that tool goes;
+      * aqua/MPIdeltaSPH.cl::mls / ::full_lapp / ::lapp_corr (ours) add the remote terms of
+        basic/MLS.cl, deltaSPH.cl::full + ::lapp and ::lapp_corr right after their local twins;
+      * the corrected gradient lap_p_corr of the halo particles, which lapp_corr needs, travels in
+        a second mpi-sync per sub-iteration on the OUTGOING mask of the first (kept in
+        mpi_sent_neigh_mask), and is put in the order of the halo list like the other fields."""
+    src = open(os.path.join(TEMPLATES, "spheric2_dambreak_3d.xml")).read()
+    variables = (
+        '        <Variable name="delta" type="float*" length="n_sets" />\n'
+        '        <Variable name="lap_p" type="float*" length="N" />\n'
+        '        <Variable name="mls_imove" type="unsigned int" value="1" />\n'
+        '        <Variable name="mls" type="matrix*" length="N" />\n'
+        '        <Variable name="mls_fluid" type="matrix*" length="N" />\n'
+        '        <Variable name="lap_p_corr" type="vec*" length="N" />\n'
+        '        <Variable name="mpi_lap_p_corr" type="vec*" length="n_radix" />\n'
+        '        <Variable name="mpi_lap_p_corr_in" type="vec*" length="n_radix" />\n'
+        '        <Variable name="mpi_neigh_mask2" type="size_t*" length="n_radix" />\n'
+        '        <Variable name="mpi_sent_neigh_mask" type="size_t*" length="n_radix" />\n')
+    txt = txt.replace("    </Variables>", variables + "    </Variables>", 1)
+    txt = re.sub(r'(<Scalar name="visc_dyn" [^>]*/>)', lambda m: m.group(1) +
+                 '\n        <Scalar name="delta" value="%r" />' % float(delta), txt)
+
+    def tool(name, typ, attrs):
+        return '<Tool action="add" name="%s" type="%s" once="false" %s />' % (name, typ, attrs)
+
+    def kernel(name, entry, n=""):
+        return tool(name, "kernel", 'path="Scripts/aqua/MPIdeltaSPH.cl" entry_point="%s" n="%s"' % (entry, n))
+
+    order = [m.group(1) for m in re.finditer(r'<Tool [^>]*name="([^"]*)"', txt)]
+    # ---- before the loop: halo exchange, halo link-list, MLS with its remote term
+    chain = [n for n in order if order.index("midpoint eos") < order.index(n) <= order.index("mpi neighs sync")]
+    pre = [tool("cfd reinit lap_p_corr", "set", 'in="lap_p_corr" value="VEC_ZERO"'), _tool_text(src, "MLS_imove1")]
+    for nm in chain:
+        pre.append(_tool_text(txt, nm).replace('name="%s"' % nm, 'name="pre %s"' % nm).replace(' depends="r,imove"', ""))
+    for nm in ("mpi backup r", "mpi backup iset", "mpi backup u", "mpi backup rho", "mpi backup m"):
+        pre.append(_tool_text(txt, nm).replace('name="%s"' % nm, 'name="pre %s"' % nm))
+    pre.append(_tool_text(txt, "mpi link-list").replace(' depends="r,imove"', ""))
+    pre.append(_tool_text(txt, "mpi sort").replace('name="mpi sort"', 'name="pre mpi sort"'))
+    pre += [_tool_text(src, "imove1_MLS interactions"), kernel("mpi mls", "mls"), _tool_text(src, "imove1_MLS"),
+            _tool_text(src, "MLS_mls_fluid"), _tool_text(src, "cfd reinit lap_p")]
+    txt = re.sub(r'\n[ \t]*<Tool [^>]*name="mpi link-list" [^>]*?/>', "", txt, 1)   # (once per step is enough)
+    anchor = "Sort"
+    for t_xml in pre:
+        txt = add_tool_after(txt, anchor, t_xml)
+        anchor = re.search(r'name="([^"]*)"', t_xml).group(1)
+    # ---- inside the loop
+    txt = add_tool_after(txt, "mpi neighs copy", tool("mpi sent neigh mask backup", "copy",
+                                                     'in="mpi_neigh_mask" out="mpi_sent_neigh_mask"'))
+    anchor = "cfd interactions"
+    for nm in ("cfd lap p mls", "cfd lap p full", "cfd lap p"):
+        txt = add_tool_after(txt, anchor, _tool_text(src, nm))
+        anchor = nm
+    txt = add_tool_after(txt, "mpi shepard", kernel("mpi lap p", "full_lapp"))
+    anchor = "Interactions"
+    for t_xml in (_tool_text(src, "cfd lap p correction mls"),
+                  kernel("mpi g copy", "copy_g"),
+                  tool("mpi g mask", "copy", 'in="mpi_sent_neigh_mask" out="mpi_neigh_mask2"'),
+                  tool("mpi g sync", "mpi-sync", 'mask="mpi_neigh_mask2" fields="mpi_lap_p_corr" processes="" '
+                                                 'depends="r,imove"'),
+                  tool("mpi g backup", "copy", 'in="mpi_lap_p_corr" out="mpi_lap_p_corr_in"'),
+                  kernel("mpi g sort", "sort_g"),
+                  _tool_text(src, "cfd lap p apply correction"),
+                  kernel("mpi lap p apply correction", "lapp_corr"),
+                  _tool_text(src, "LapP Correction")):
+        txt = add_tool_after(txt, anchor, t_xml)
+        anchor = re.search(r'name="([^"]*)"', t_xml).group(1)
+    txt = add_tool_after(txt, "cfd rates", _tool_text(src, "cfd delta-SPH"))
+    return txt
+
+
+def slab_fixes_delta_sph(delta):
+    """Transform for casegen.load: multi_device_fixes + slab_delta_sph."""
+    return lambda txt: slab_delta_sph(multi_device_fixes(txt), delta)
+
+
 def spheric2_slab(n_total, rank, size, hfac=3.0, overrides=None, device=0, unique_id=None, seed=None,
-                  jitter=0.0, uscale=0.1, **kw):
+                  jitter=0.0, uscale=0.1, delta_sph=False, **kw):
     """BASELINE config 3: the 3-D dam break on `size` devices (y slabs) through the
     pipeline of examples/3D/spheric_testcase2_dambreak_mpi (131 tools: midpoint, BIe
     boundaries, variable time step, cfd/MPI.xml migration + halo)."""
     from . import cases
     c = cases.spheric2_dam_break_slab(n_total, hfac, rank, size, seed=seed, jitter=jitter, uscale=uscale)
     sim = load("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), overrides, device,
-               mpi_rank=rank, mpi_size=size, unique_id=unique_id, transform=multi_device_fixes, **kw)
+               mpi_rank=rank, mpi_size=size, unique_id=unique_id,
+               transform=slab_fixes_delta_sph(float(c["delta"][0])) if delta_sph else multi_device_fixes, **kw)
     return sim, c
 
 
@@ -358,10 +450,10 @@ def spheric3_lid_driven(nx=200, hfac=4.0, overrides=None, device=0, **kw):
     return sim, c
 
 
-def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, **kw):
+def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, jitter=0.0, uscale=0.1, **kw):
     """BASELINE config 2 (3-D SPHERIC test 2 dam break) through the unchanged
     116-tool pipeline of examples/3D/spheric_testcase2_dambreak."""
     from . import cases
-    c = cases.spheric2_dam_break(n, hfac, seed=seed)
+    c = cases.spheric2_dam_break(n, hfac, seed=seed, jitter=jitter, uscale=uscale)
     sim = load("spheric2_dambreak_3d", c, (c["N"] - 8, 8), overrides, device, **kw)
     return sim, c

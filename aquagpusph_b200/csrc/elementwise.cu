@@ -1208,6 +1208,33 @@ int l_mpi_eos(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// aqua/MPIdeltaSPH.cl::copy_g / ::sort_g (ours): the corrected pressure gradient of delta-SPH
+// travels like the other halo fields -- copied into its mpi_ twin, exchanged, and put in the
+// order of the halo link-list (cfd/MPI.cl:64-91 and :248-267 do this for r, u, rho, m)
+template <int D>
+__global__ void __launch_bounds__(256) k_mpi_copy_g(void* mpi_g, const void* g, uint32_t N)
+{
+    GID;
+    V<D>::ld(g, i).st(mpi_g, i);
+}
+int l_mpi_copy_g(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    DISPATCH(c, k_mpi_copy_g, N, a[0], a[1], N);
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_mpi_sort_g(const void* g_in, void* g, const uint32_t* mpi_id_sorted, uint32_t N)
+{
+    GID;
+    V<D>::ld(g_in, i).st(g, mpi_id_sorted[i]);
+}
+int l_mpi_sort_g(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    DISPATCH(c, k_mpi_sort_g, N, a[0], a[1], (const uint32_t*)a[2], N);
+}
+
 // planes.cl: HALO = false -> local_mask (d > 0), true -> neigh_mask (d >= -SUPPORT*H)
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -1367,6 +1394,11 @@ aqc_registrar r_mpi_sort("cfd/MPI.cl", "sort", 0,
 aqc_registrar r_mpi_eos("cfd/MPI.cl", "eos", 0,
     { OUT("mpi_iset", "unsigned int*"), OUT("mpi_rho", "float*"), OUT("mpi_p", "float*"),
       IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"), SC("p0", "float") }, l_mpi_eos);
+aqc_registrar r_mpi_copy_g("aqua/MPIdeltaSPH.cl", "copy_g", 0,
+    { OUT("mpi_lap_p_corr", "vec*"), IN("lap_p_corr", "vec*"), SC("N", "usize") }, l_mpi_copy_g);
+aqc_registrar r_mpi_sort_g("aqua/MPIdeltaSPH.cl", "sort_g", 0,
+    { IN("mpi_lap_p_corr_in", "vec*"), OUT("mpi_lap_p_corr", "vec*"), IN("mpi_id_sorted", "usize*"),
+      SC("N", "usize") }, l_mpi_sort_g);
 aqc_registrar r_mpi_lmask("cfd/MPI/planes.cl", "local_mask", 0,
     { IN("imove", "int*"), IN("r", "vec*"), OUT("mpi_local_mask", "usize*"),
       SC("mpi_plane_r", "vec"), SC("mpi_plane_n", "vec"), SC("mpi_plane_proc", "unsigned int"),

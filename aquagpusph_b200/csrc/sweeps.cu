@@ -912,6 +912,162 @@ struct PMpiFused : PBase {
 };
 
 // ------------------------------------------------------------------------
+// Remote (halo) terms of MLS and delta-SPH: aqua/MPIdeltaSPH.cl::mls / ::full_lapp / ::lapp_corr.
+// NOT reference kernels.  The reference's MPI preset exchanges what cfd/Interactions.cl and the
+// Shepard factor need and nothing else (resources/Presets/src/cfd/MPI.xml:59-87), so its
+// multi-process runs cannot carry delta-SPH or MLS; the slab pipelines of this repository that do
+// (casegen.slab_delta_sph) insert these next to their local twins.  Each is the j loop of the local
+// script (basic/MLS.cl:58-112, basic/deltaSPH.cl:94-145 + 191-242, 261-313) over the halo list,
+// written the way cfd/MPI.cl:328-485 writes its own: every halo particle counts, the result is
+// ADDED to what the local kernel left.
+template <int D>
+struct PMpiMLS : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void *r, *mpi_r;
+    const float *mpi_rho, *mpi_m;
+    float* mls;
+    uint32_t mls_imove;
+    float cF;
+    struct IState { float x, y, z, a[D * D]; };
+    __device__ bool i_active(int mv) const { return (uint32_t)mv == mls_imove; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+#pragma unroll
+        for (int k = 0; k < D * D; k++)
+            s.a[k] = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j);
+        o[0] = make_float4(a.x, a.y, a.z, cF * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        float d[3] = { A.x - s.x, A.y - s.y, A.z - s.z };
+        const float t = 2.f - q_of(dist2<D>(d[0], d[1], d[2]), invH);
+        const float f = (t * t) * (t * A.w);
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+            for (int b = 0; b < D; b++)
+                s.a[a * D + b] += d[a] * (f * d[b]);
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if constexpr (D == 3) {
+            float4* o = reinterpret_cast<float4*>(mls) + 4 * (size_t)i;
+            float4 m0 = o[0], m1 = o[1], m2 = o[2];
+            m0.x += s.a[0]; m0.y += s.a[1]; m0.z += s.a[2];
+            m1.x += s.a[3]; m1.y += s.a[4]; m1.z += s.a[5];
+            m2.x += s.a[6]; m2.y += s.a[7]; m2.z += s.a[8];
+            o[0] = m0; o[1] = m1; o[2] = m2;
+        } else {
+            float4 m0 = reinterpret_cast<float4*>(mls)[i];
+            m0.x += s.a[0]; m0.y += s.a[1]; m0.z += s.a[2]; m0.w += s.a[3];
+            reinterpret_cast<float4*>(mls)[i] = m0;
+        }
+    }
+};
+
+template <int D>
+struct PMpiDelta : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *mpi_r;
+    const float *p, *mpi_rho, *mpi_m, *mpi_p;
+    void* lap_p_corr;
+    float* lap_p;
+    float cF;
+    struct IState { float x, y, z, p, ax, ay, az, lp; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.p = __ldg(p + i);
+        s.ax = s.ay = s.az = s.lp = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j);
+        o[0] = make_float4(a.x, a.y, a.z, cF * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+        o[1] = make_float4(__ldg(mpi_p + j), 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0];
+        const float pj = row[stride].x;
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float t = 2.f - q_of(dist2<D>(dx, dy, dz), invH);
+        const float c = (pj - s.p) * ((t * t) * (t * A.w));
+        s.ax += c * dx; s.ay += c * dy; s.az += c * dz;
+        s.lp += c;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float4 g0 = ldvec_rw<D>(lap_p_corr, i);
+        stvec_xyz<D>(lap_p_corr, i, g0.x + s.ax, g0.y + s.ay, g0.z + s.az);
+        lap_p[i] += s.lp;
+    }
+};
+
+template <int D>
+struct PMpiLappCorr : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const void *r, *mpi_r, *lap_p_corr, *mpi_lap_p_corr;
+    const float *mpi_rho, *mpi_m;
+    float* lap_p;
+    float cF;
+    struct IState { float x, y, z, gx, gy, gz, acc; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), g = ldvec<D>(lap_p_corr, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.gx = g.x; s.gy = g.y; s.gz = g.z;
+        s.acc = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(mpi_r, j), g = ldvec<D>(mpi_lap_p_corr, j);
+        o[0] = make_float4(a.x, a.y, a.z, cF * __ldg(mpi_m + j) / __ldg(mpi_rho + j));
+        o[1] = make_float4(g.x, g.y, g.z, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], G = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float t = 2.f - q_of(dist2<D>(dx, dy, dz), invH);
+        float gr = (G.x + s.gx) * dx + (G.y + s.gy) * dy;
+        if constexpr (D == 3)
+            gr += (G.z + s.gz) * dz;
+        s.acc += gr * ((t * t) * (t * A.w));
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const { lap_p[i] -= 0.5f * s.acc; }
+};
+
+// ------------------------------------------------------------------------
 // Boundary integrals, cfd/Boundary/BI/*.cl (2-D dam break, BASELINE config 1)
 
 // KernelFunctions/Wendland{2D,3D}.hcl:107-185: analytic Shepard terms of a flat element
@@ -1964,6 +2120,43 @@ template <int D> int run_mpi_inter(aqc_ctx* ctx, void* const* a)
 }
 int l_mpi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_inter, c, a); }
 
+// aqua/MPIdeltaSPH.cl (ours): remote terms of MLS and delta-SPH
+template <int D> int run_mpi_mls(aqc_ctx* ctx, void* const* a)
+{
+    // imove r mpi_r mpi_rho mpi_m mls mls_imove N icell mpi_icell mpi_ihoc n_cells
+    PMpiMLS<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.mpi_r = a[2]; p.mpi_rho = (const float*)a[3]; p.mpi_m = (const float*)a[4];
+    p.mls = (float*)a[5];
+    p.mls_imove = aqc_scalar<uint32_t>(a, 6);
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll_remote(a, 8, aqc_scalar<uint32_t>(a, 7)));
+}
+int l_mpi_mls(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_mls, c, a); }
+template <int D> int run_mpi_delta(aqc_ctx* ctx, void* const* a)
+{
+    // imove r p mpi_r mpi_rho mpi_m mpi_p lap_p_corr lap_p N icell mpi_icell mpi_ihoc n_cells
+    PMpiDelta<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.p = (const float*)a[2]; p.mpi_r = a[3]; p.mpi_rho = (const float*)a[4];
+    p.mpi_m = (const float*)a[5]; p.mpi_p = (const float*)a[6]; p.lap_p_corr = a[7];
+    p.lap_p = (float*)a[8];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll_remote(a, 10, aqc_scalar<uint32_t>(a, 9)));
+}
+int l_mpi_delta(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_delta, c, a); }
+template <int D> int run_mpi_lapp_corr(aqc_ctx* ctx, void* const* a)
+{
+    // imove r lap_p_corr mpi_r mpi_rho mpi_m mpi_lap_p_corr lap_p N icell mpi_icell mpi_ihoc n_cells
+    PMpiLappCorr<D> p;
+    set_base(p, ctx, a[0]);
+    p.r = a[1]; p.lap_p_corr = a[2]; p.mpi_r = a[3]; p.mpi_rho = (const float*)a[4];
+    p.mpi_m = (const float*)a[5]; p.mpi_lap_p_corr = a[6]; p.lap_p = (float*)a[7];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    return launch_sweep(ctx, p, make_ll_remote(a, 9, aqc_scalar<uint32_t>(a, 8)));
+}
+int l_mpi_lapp_corr(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_lapp_corr, c, a); }
+
 // ---- fused launches -----------------------------------------------------------
 // Members are given in pipeline order; the argument list of a fused launch is the
 // concatenation of the members' own argument lists (same names, same order).
@@ -2126,6 +2319,18 @@ aqc_registrar r_mpi_inter("cfd/MPI.cl", "interactions", 0,
       IN("mpi_r", "vec*"), IN("mpi_u", "vec*"), IN("mpi_rho", "float*"), IN("mpi_p", "float*"),
       IN("mpi_m", "float*"), OUT("grad_p", "vec*"), OUT("lap_u", "vec*"), OUT("div_u", "float*"),
       SC("N", "usize"), LL_REMOTE_ARGS }, l_mpi_inter);
+aqc_registrar r_mpi_mls("aqua/MPIdeltaSPH.cl", "mls", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("mpi_r", "vec*"), IN("mpi_rho", "float*"),
+      IN("mpi_m", "float*"), OUT("mls", "matrix*"), SC("mls_imove", "unsigned int"), SC("N", "usize"),
+      LL_REMOTE_ARGS }, l_mpi_mls);
+aqc_registrar r_mpi_delta("aqua/MPIdeltaSPH.cl", "full_lapp", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("p", "float*"), IN("mpi_r", "vec*"),
+      IN("mpi_rho", "float*"), IN("mpi_m", "float*"), IN("mpi_p", "float*"), OUT("lap_p_corr", "vec*"),
+      OUT("lap_p", "float*"), SC("N", "usize"), LL_REMOTE_ARGS }, l_mpi_delta);
+aqc_registrar r_mpi_lapp_corr("aqua/MPIdeltaSPH.cl", "lapp_corr", 0,
+    { IN("imove", "int*"), IN("r", "vec*"), IN("lap_p_corr", "vec*"), IN("mpi_r", "vec*"),
+      IN("mpi_rho", "float*"), IN("mpi_m", "float*"), IN("mpi_lap_p_corr", "vec*"), OUT("lap_p", "float*"),
+      SC("N", "usize"), LL_REMOTE_ARGS }, l_mpi_lapp_corr);
 template <int D> int run_count_pairs(aqc_ctx* ctx, void* const* a)
 {
     PCountPairs<D> p;

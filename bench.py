@@ -140,10 +140,13 @@ def run_ours(a, rank, world, local_rank):
         if world > 1:
             dist.broadcast_object_list(uid, src=0)
         sim, case = casegen.spheric2_slab(a.n * world, rank, world, overrides=ov,
-                                          device=local_rank, unique_id=uid[0])
+                                          device=local_rank, unique_id=uid[0], delta_sph=not a.mpi_example)
         N = case["N"] - case["n_buffer"]      # buffer rows are not particles
-        workload = ("3D SPHERIC test 2 dam break, %d y-slabs (examples/3D/spheric_testcase2_dambreak_mpi "
-                    "pipeline: migration + halo over NCCL)" % world)
+        workload = ("3D SPHERIC test 2 dam break, %d y-slabs: " % world) + (
+            "examples/3D/spheric_testcase2_dambreak_mpi pipeline (migration + halo over NCCL; no delta-SPH / MLS)"
+            if a.mpi_example else
+            "the physics of the single-GPU pipeline (examples/3D/spheric_testcase2_dambreak: delta-SPH, MLS, "
+            "BIe) on the reference's MPI presets, remote delta-SPH / MLS terms added (casegen.slab_delta_sph)")
     else:
         sim, case = casegen.spheric2(a.n, overrides=ov, device=local_rank)
         N = case["N"]
@@ -347,16 +350,19 @@ def run_ours(a, rank, world, local_rank):
     except Exception as e:   # never lose the line over the extra measurement
         roof["stages"] = {"error": str(e)[:200]}
     del d, hh
-    # ---- N > 1 runs the reference's MPI example pipeline (131 tools: no delta-SPH / MLS, which
-    # the reference's MPI preset cannot exchange), not the 116-tool pipeline of the N = 1
-    # headline.  For an honest scaling figure rank 0 also times ONE slab of the same per-GPU
-    # size through that same pipeline on its GPU, after the other ranks have left.
+    # ---- N > 1 runs the physics of the N = 1 headline (delta-SPH, MLS, BIe) on slabs: the
+    # reference's MPI presets plus the remote delta-SPH / MLS terms its own MPI preset lacks
+    # (casegen.slab_delta_sph; --mpi-example gives the reference's lighter 131-tool example instead).
+    # On one rank that pipeline is the 116-tool one bit for bit, so value(N) / (N value(1)) of the
+    # driver is a weak-scaling efficiency; rank 0 still times ONE slab of the same per-GPU size
+    # through the very same tool list on its GPU, after the other ranks have left.
     same1 = None
     if world > 1:
         try:
             sim1, case1 = casegen.spheric2_slab(a.n, 0, 1, overrides=ov, device=local_rank,
-                                                unique_id=None)
+                                                unique_id=None, delta_sph=not a.mpi_example)
             ctx1 = _lib.Context.borrow(sim1.cuda_ctx(), 3)
+            sim1.step(a.pre_steps)
             for _ in range(a.warmup):
                 sim1.step(1)
             sim1.sync()
@@ -390,8 +396,9 @@ def run_ours(a, rank, world, local_rank):
                    "first_timed_step": a.pre_steps + a.warmup,
                    "iter_midpoint_max": a.maxiter or 30,
                    "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
-                   "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv, dt and residual "
-                                 "all-reduced") if world > 1 else "single GPU",
+                   "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv (halo of r, u, rho, m and of "
+                                 "the delta-SPH gradient every sub-iteration), dt and residual all-reduced")
+                   if world > 1 else "single GPU",
                    "one_gpu_same_pipeline": same1,
                    # neighbour sweeps that read the hit masks of one builder pass instead of
                    # filtering their candidates again (include/aquacuda.h, aqc_pairs_cache_*)
@@ -478,6 +485,9 @@ def main():
                     help="steps evolved on the GPU before the warm-up (outside the timed regions)")
     ap.add_argument("--slab-pipeline", action="store_true",
                     help="run the multi-GPU (slab) pipeline also on one GPU, for scaling studies")
+    ap.add_argument("--mpi-example", action="store_true",
+                    help="N > 1: the reference's MPI example pipeline (no delta-SPH / MLS) instead of the "
+                         "single-GPU pipeline's physics on slabs")
     ap.add_argument("--maxiter", type=int, default=0, help="pin iter_midpoint_max (0: case default 30)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -265,4 +265,17 @@ void aqo_bi_noslip(const aqo_defs* D, const aqo_ll* L, const unsigned* iset, con
 #ifdef __cplusplus
 }
 #endif
+/* Remote (halo) terms of MLS and delta-SPH (ours: see aqo_kernels.c) */
+void aqo_mpi_mls(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i, const int* imove,
+                 const float* r, const float* mpi_r, const float* mpi_rho, const float* mpi_m,
+                 float* mls, aqo_usize mls_imove);
+void aqo_mpi_dsph_full_lapp(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i,
+                            const int* imove, const float* r, const float* p, const float* mpi_r,
+                            const float* mpi_rho, const float* mpi_m, const float* mpi_p,
+                            float* lap_p_corr, float* lap_p);
+void aqo_mpi_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i,
+                            const int* imove, const float* r, const float* lap_p_corr,
+                            const float* mpi_r, const float* mpi_rho, const float* mpi_m,
+                            const float* mpi_lap_p_corr, float* lap_p);
+
 #endif

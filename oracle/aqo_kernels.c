@@ -1442,3 +1442,113 @@ void aqo_bi_noslip(const aqo_defs* D, const aqo_ll* L, const unsigned* iset, con
         NEIGHS_END
     }
 }
+
+/* ---------------------------------------------------------------------------
+ * Remote (halo) terms of MLS and delta-SPH.  NOT reference kernels: the reference's MPI preset
+ * (resources/Presets/src/cfd/MPI.xml) exchanges what cfd/Interactions.cl and the Shepard factor need
+ * and nothing else, so its multi-process runs cannot use delta-SPH or MLS.  These are the j loops of
+ * basic/MLS.cl:58-112 and basic/deltaSPH.cl:94-145, 191-242, 261-313 over the halo list, written the
+ * way cfd/MPI.cl:328-485 writes its own (every halo particle counts, the result is ADDED to what the
+ * local kernel left); cases_xml of the multi-device pipelines insert them next to their local twins.
+ * L: icell/ihoc of the HALO list (mpi_icell, mpi_ihoc) with N = number of local particles;
+ * icell_i: cells of the local particles. */
+#define REMOTE_NEIGHS_BEGIN(L, icell_i, i, dims)                               \
+    {                                                                          \
+        const aqo_usize c_i__ = (icell_i)[i];                                  \
+        const aqo_usize nx__ = (L)->ncells[0], ny__ = (L)->ncells[1];          \
+        const int kz__ = ((dims) == 3) ? 1 : 0;                                \
+        for (int ci__ = -1; ci__ <= 1; ci__++)                                 \
+            for (int cj__ = -1; cj__ <= 1; cj__++)                             \
+                for (int ck__ = -kz__; ck__ <= kz__; ck__++) {                 \
+                    const aqo_usize c_j__ =                                    \
+                        c_i__ + (aqo_usize)ci__ + (aqo_usize)cj__ * nx__ +     \
+                        (aqo_usize)ck__ * nx__ * ny__;                         \
+                    for (aqo_usize j = (L)->ihoc[c_j__];                       \
+                         (j < (L)->N) && ((L)->icell[j] == c_j__); j++) {
+
+void aqo_mpi_mls(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i, const int* imove,
+                 const float* r, const float* mpi_r, const float* mpi_rho, const float* mpi_m,
+                 float* mls, aqo_usize mls_imove)
+{
+    const int dims = D->dims, vs = VS(dims), ms = MS(dims);
+    const int rs = (dims == 3) ? 4 : 2;
+    AQO_FOR_I(L->N) {
+        if ((aqo_usize)imove[i] != mls_imove)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float M[16];
+        for (int k = 0; k < 16; k++)
+            M[k] = 0.f;
+        REMOTE_NEIGHS_BEGIN(L, icell_i, i, dims)
+        {
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, mpi_r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float f_ij = kernelF(q, dims) * D->CONF * mpi_m[j] / mpi_rho[j];
+            for (int a = 0; a < dims; a++)
+                for (int b = 0; b < dims; b++)
+                    M[a * rs + b] += r_ij[a] * (f_ij * r_ij[b]);
+        }
+        NEIGHS_END
+        for (int k = 0; k < ms; k++)
+            mls[(size_t)i * ms + k] += M[k];
+    }
+}
+
+void aqo_mpi_dsph_full_lapp(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i,
+                            const int* imove, const float* r, const float* p, const float* mpi_r,
+                            const float* mpi_rho, const float* mpi_m, const float* mpi_p,
+                            float* lap_p_corr, float* lap_p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    AQO_FOR_I(L->N) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float p_i = p[i];
+        float gp[3] = { 0.f, 0.f, 0.f }, lp = 0.f;
+        REMOTE_NEIGHS_BEGIN(L, icell_i, i, dims)
+        {
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, mpi_r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float f_ij = kernelF(q, dims) * D->CONF * mpi_m[j] / mpi_rho[j];
+            const float c = (mpi_p[j] - p_i) * f_ij;
+            for (int d = 0; d < dims; d++)
+                gp[d] += c * r_ij[d];
+            lp += c;
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            lap_p_corr[(size_t)i * vs + d] += gp[d];
+        lap_p[i] += lp;
+    }
+}
+
+void aqo_mpi_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const aqo_usize* icell_i,
+                            const int* imove, const float* r, const float* lap_p_corr,
+                            const float* mpi_r, const float* mpi_rho, const float* mpi_m,
+                            const float* mpi_lap_p_corr, float* lap_p)
+{
+    const int dims = D->dims, vs = VS(dims);
+    AQO_FOR_I(L->N) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* g_i = lap_p_corr + (size_t)i * vs;
+        float acc = 0.f;
+        REMOTE_NEIGHS_BEGIN(L, icell_i, i, dims)
+        {
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, mpi_r + (size_t)j * vs, r_ij, &q))
+                continue;
+            float g_ij[3];
+            for (int d = 0; d < dims; d++)
+                g_ij[d] = mpi_lap_p_corr[(size_t)j * vs + d] + g_i[d];
+            const float f_ij = kernelF(q, dims) * D->CONF * mpi_m[j] / mpi_rho[j];
+            acc += dotv(g_ij, r_ij, dims) * f_ij;
+        }
+        NEIGHS_END
+        lap_p[i] -= 0.5f * acc;
+    }
+}

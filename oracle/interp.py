@@ -697,6 +697,24 @@ class Interpreter:
         elif key == ("cfd/Boundary/BI/NoSlip.cl", "entry"):
             c("bi_noslip", D, self.ll(), V["iset"], V["imove"], V["r"], V["normal"], V["u"], V["rho"], V["m"],
               V["lap_u"], int(V["noslip_iset"]), f32("dr"))
+        elif rel == "aqua/MPIdeltaSPH.cl":
+            # remote (halo) terms of MLS / delta-SPH: ours, not reference scripts (aqo_kernels.c)
+            rl = O.make_ll(V["mpi_icell"], V["mpi_ihoc"], V["n_cells"], N)
+            if entry == "mls":
+                c("mpi_mls", D, rl, V["icell"], V["imove"], V["r"], V["mpi_r"], V["mpi_rho"], V["mpi_m"],
+                  V["mls"], int(V["mls_imove"]))
+            elif entry == "full_lapp":
+                c("mpi_dsph_full_lapp", D, rl, V["icell"], V["imove"], V["r"], V["p"], V["mpi_r"], V["mpi_rho"],
+                  V["mpi_m"], V["mpi_p"], V["lap_p_corr"], V["lap_p"])
+            elif entry == "lapp_corr":
+                c("mpi_dsph_lapp_corr", D, rl, V["icell"], V["imove"], V["r"], V["lap_p_corr"], V["mpi_r"],
+                  V["mpi_rho"], V["mpi_m"], V["mpi_lap_p_corr"], V["lap_p"])
+            elif entry == "copy_g":
+                V["mpi_lap_p_corr"][:N] = V["lap_p_corr"][:N]
+            elif entry == "sort_g":
+                V["mpi_lap_p_corr"][V["mpi_id_sorted"][:N]] = V["mpi_lap_p_corr_in"][:N]
+            else:
+                raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
         elif rel.endswith("h_sensor.cl"):
             # examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60
             r, dr = V["r"], np.float32(V["dr"])

@@ -538,3 +538,54 @@ def test_dead_peer_ends_the_job():
         else:            # the watchdog ended the process
             assert procs[r].exitcode == 70, (r, procs[r].exitcode)
     assert took < 90.0, took
+
+
+def _single_116_rank(q, n_total, steps, kw):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from aquagpusph_b200 import casegen, host
+    host.set_log_level(3)
+    kw = dict(kw)
+    ov = {"iter_midpoint_max": kw.pop("iter_midpoint_max", 3)}
+    sim, c = casegen.spheric2(n_total, overrides=ov, device=0, **kw)
+    sim.step(steps)
+    nf = c["n_fluid"]
+    res = {k: sim.download(k, np.float32, unsorted=True)[:nf] for k in ("r", "u", "rho", "dudt")}
+    res["imove"] = sim.download("imove", np.int32, unsorted=True)[:nf]
+    res.update(dt=float(sim.scalar("dt")), h=c["h"], fluid_index=np.arange(nf), tools=len(sim.tools()))
+    q.put((0, res))
+    sim.close()
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_delta_sph_slabs_match_the_single_gpu_pipeline(size):
+    """BASELINE config 2's physics on N GPUs: the slab pipeline with delta-SPH and MLS
+    (casegen.slab_delta_sph: remote terms aqua/MPIdeltaSPH.cl, a second halo exchange per
+    sub-iteration for the corrected pressure gradient) against the UNCHANGED 116-tool pipeline of
+    examples/3D/spheric_testcase2_dambreak on one GPU -- the pipeline bench.py runs at N = 1.
+    Jittered, moving particles (they migrate at two ranks, where the cut runs through a lattice
+    layer); every live particle within fp32 summation rounding of its single-GPU twin."""
+    if _n_gpus() < size:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (size, size))
+    import torch.multiprocessing as mp
+    n_total, steps = 50000, 4
+    kw = dict(seed=5, jitter=0.45, uscale=2.0, iter_midpoint_max=3)
+    mpx = mp.get_context("spawn")
+    q = mpx.Queue()
+    p = mpx.Process(target=_single_116_rank, args=(q, n_total, steps, kw))
+    p.start()
+    one = _collect([p], q, 1, 600)[0]
+    many = _run_slabs(size, n_total, steps, whole=True, delta_sph=True, **kw)
+    assert len({many[r]["dt"] for r in range(size)}) == 1
+    assert abs(many[0]["dt"] - one["dt"]) <= 1e-6 * one["dt"]
+    fl1, matches = _match_rows(one, [many[r] for r in range(size)])
+    assert sum(len(m[0]) for m in matches) == len(fl1)
+    assert len(np.unique(np.concatenate([m[1] for m in matches]))) == len(fl1)
+    for r in range(size):
+        rows, rows1, d = matches[r]
+        assert d.max() < 1e-4 * one["h"], (r, d.max())
+        for k, tol in (("r", 2e-6), ("u", 2e-4), ("rho", 5e-5), ("dudt", 1e-3)):
+            a = one[k][rows1].astype(np.float64)
+            b = many[r][k][rows].astype(np.float64)
+            err = np.abs(a - b).max() / max(np.abs(one[k][fl1]).max(), 1e-30)
+            assert err <= tol, "rank %d field %s: rel err %.3e" % (r, k, err)

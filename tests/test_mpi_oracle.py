@@ -122,9 +122,10 @@ def test_mpi_plane_two_processes_gloo(golden, oracle):
             assert np.array_equal(got[r][k], ref_ranks[r][k]), (r, k)
 
 
-def _dam_break_ranks(size, n_total, steps, **kw):
+def _dam_break_ranks(size, n_total, steps, delta_sph=False, **kw):
     """The 3-D dam break cut in `size` y slabs through the oracle interpreter (threads), with the
-    multi-device additions of casegen.multi_device_fixes; returns the device-order state."""
+    multi-device additions of casegen.multi_device_fixes (and the delta-SPH / MLS stages of
+    casegen.slab_delta_sph); returns the device-order state."""
     import threading
     from aquagpusph_b200 import cases, casegen
     tr = interp.LocalTransport(size)
@@ -133,8 +134,10 @@ def _dam_break_ranks(size, n_total, steps, **kw):
     def work(rank):
         try:
             c = cases.spheric2_dam_break_slab(n_total, 3.0, rank, size, **kw)
-            txt = casegen.multi_device_fixes(casegen.instantiate(
-                "spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), {"iter_midpoint_max": 3}))
+            txt = casegen.instantiate("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]),
+                                      {"iter_midpoint_max": 3})
+            txt = (casegen.slab_fixes_delta_sph(float(c["delta"][0])) if delta_sph
+                   else casegen.multi_device_fixes)(txt)
             I = interp.Interpreter(txt, 3, rank=rank, size=size, transport=tr)
             for k in casegen.STATE_FIELDS:
                 I.V[k][...] = c[k]
@@ -142,7 +145,9 @@ def _dam_break_ranks(size, n_total, steps, **kw):
                 I.step()
             res = {k: I.V[k].copy() for k in ("r", "u", "rho", "dudt", "imove")}
             res.update(fluid_index=c["fluid_index"], n_fluid=c["n_fluid"], dt=float(I.V["dt"]), h=c["h"],
-                       r0=I.unsorted("r")[:c["n_fluid"]], u0=I.unsorted("u")[:c["n_fluid"]])
+                       r0=I.unsorted("r")[:c["n_fluid"]], u0=I.unsorted("u")[:c["n_fluid"]],
+                       unsorted={k: I.unsorted(k)[:c["n_fluid"]] for k in ("r", "u", "rho", "dudt", "drhodt")},
+                       n_tools=len(I.tools))
             out[rank] = res
         except BaseException as e:   # noqa: BLE001
             errs.append(e)
@@ -187,3 +192,40 @@ def test_dam_break_three_slabs_with_migration(oracle):
     seen = np.concatenate(seen)
     assert len(seen) == nf and len(np.unique(seen)) == nf, "particles lost or duplicated"
     assert arrived > 20, arrived
+
+
+def test_slab_pipeline_with_delta_sph_is_the_single_device_pipeline(oracle):
+    """casegen.slab_delta_sph: the reference's MPI example pipeline extended with the delta-SPH and
+    MLS stages of the single-device dam break (remote terms: aqua/MPIdeltaSPH.cl, ours -- the
+    reference's MPI preset cannot exchange them).  On ONE rank it is the 116-tool pipeline of
+    examples/3D/spheric_testcase2_dambreak bit for bit; on three ranks (an interior rank, cuts off
+    the lattice layers so that nothing migrates in two steps) every particle agrees with the
+    single-device run to the rounding of a sum whose remote terms come last."""
+    from aquagpusph_b200 import cases, casegen
+    from oracle import oracle as O
+    O.set_threads(4)
+    try:
+        kw = dict(seed=5, jitter=0.0, uscale=0.1)
+        n_total, steps = 24000, 2
+        c = cases.spheric2_dam_break(n_total, 3.0, **kw)
+        I = interp.Interpreter(casegen.instantiate("spheric2_dambreak_3d", c, (c["N"] - 8, 8),
+                                                   {"iter_midpoint_max": 3}), 3)
+        for k in casegen.STATE_FIELDS:
+            I.V[k][...] = c[k]
+        for _ in range(steps):
+            I.step()
+        serial = {k: I.unsorted(k) for k in ("r", "u", "rho", "dudt", "drhodt")}
+        one = _dam_break_ranks(1, n_total, steps, delta_sph=True, **kw)[0]
+        three = _dam_break_ranks(3, n_total, steps, delta_sph=True, **kw)
+    finally:
+        O.set_threads(1)
+    assert one["dt"] == float(I.V["dt"])
+    for k in serial:
+        assert np.array_equal(one["unsorted"][k], serial[k][one["fluid_index"]]), k
+    for r in range(3):
+        g = three[r]
+        assert g["dt"] == float(I.V["dt"]) and g["n_tools"] == one["n_tools"]
+        for k, tol in (("r", 1e-7), ("u", 2e-5), ("rho", 1e-6), ("dudt", 2e-4), ("drhodt", 2e-4)):
+            a = serial[k][g["fluid_index"]].astype(np.float64)
+            b = g["unsorted"][k].astype(np.float64)
+            assert np.abs(a - b).max() <= tol * np.abs(serial[k]).max(), (r, k)
