@@ -485,6 +485,8 @@ def _dead_peer_rank(rank, size, port, q):
         ctx.mpi_sync(mask, [f])
         ctx.sync()
         q.put((rank, ("no error", time.time() - t0, "")))
+        q.close()
+        q.join_thread()
     except _lib.AquaError as e:
         dt = time.time() - t0
         # and the context stays failed: no later collective may hang either
@@ -494,6 +496,8 @@ def _dead_peer_rank(rank, size, port, q):
         except _lib.AquaError as e2:
             again = str(e2)
         q.put((rank, (str(e), dt, again)))
+        q.close()
+        q.join_thread()      # (os._exit would drop what the feeder thread has not sent yet)
     os._exit(0)
 
 

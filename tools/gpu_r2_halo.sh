@@ -16,7 +16,5 @@ for l in open("gpurun_out/r2_halo_${N}gpu_$1.json"):
         d=json.loads(l); print("$1", round(d["ms_per_step"],3), d["config"]["mean_inner_iterations"], d["config"]["one_gpu_same_pipeline"])
 PY
 }
-run near1 AQC_REMOTE_NEAR=1
-run near0 AQC_REMOTE_NEAR=0
-AQUA_PROFILE_SYNC=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29545 tools/prof_slabs.py 1000000 > gpurun_out/r2_prof_slabs_${N}gpu_near.log 2>&1
-grep "^rank 0" gpurun_out/r2_prof_slabs_${N}gpu_near.log | grep "mpi\|ms/step over" | head -14
+run dsph AQC_REMOTE_NEAR=1
+tail -c 600 gpurun_out/r2_halo_${N}gpu_dsph.err
