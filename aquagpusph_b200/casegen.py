@@ -260,6 +260,14 @@ def slab_delta_sph(txt, delta=0.1):
         '        <Variable name="mpi_neigh_mask2" type="size_t*" length="n_radix" />\n'
         '        <Variable name="mpi_sent_neigh_mask" type="size_t*" length="n_radix" />\n')
     txt = txt.replace("    </Variables>", variables + "    </Variables>", 1)
+    # the definitions the single-device example adds to the presets' (the delta-SPH switches and
+    # __DR_FACTOR__ = 0.75f, the element radius of BIe/ElasticBounce.cl and BIe/PST.cl: without it
+    # particles next to a wall bounce at another distance than on one device)
+    have = set(re.findall(r'<Define name="([^"]*)"', txt))
+    last = list(re.finditer(r'\n[ \t]*<Define [^>]*/>', txt))[-1]
+    extra = "".join(m.group(0) for m in re.finditer(r'\n[ \t]*<Define name="([^"]*)"[^>]*/>', src)
+                    if m.group(1) not in have)
+    txt = txt[:last.end()] + extra + txt[last.end():]
     txt = re.sub(r'(<Scalar name="visc_dyn" [^>]*/>)', lambda m: m.group(1) +
                  '\n        <Scalar name="delta" value="%r" />' % float(delta), txt)
 

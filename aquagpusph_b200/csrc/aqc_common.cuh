@@ -95,9 +95,11 @@ struct aqc_ctx {
     uint32_t* sort_keys[2] = { nullptr, nullptr };
     uint32_t* sort_vals[2] = { nullptr, nullptr };
     size_t sort_cap = 0;
-    uint32_t* sort_hist = nullptr; // [256][nblocks] + [256] totals
+    uint32_t* sort_hist = nullptr; // digit totals + tile tickets + tile status words (linklist.cu)
     size_t sort_hist_cap = 0;
+    bool sort_ghist_clean = false; // totals and tickets are zero (left so by the heads kernel)
     uint32_t* minmax_dev = nullptr; // 8 ordered-uint keys
+    bool minmax_clean = false;      // ... hold the identities (left so by the prepare kernel)
     // per-cell mask of the particle classes present (sweep.cuh: aqc_cls_bit), rebuilt by the
     // sweeps whose j set is a small class (boundary elements): cells without one are skipped
     uint8_t* cell_cls = nullptr;

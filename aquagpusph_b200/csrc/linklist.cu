@@ -9,13 +9,18 @@
 // B200 design: all stages are HBM-bound integer work.
 //   minmax   : one grid-stride pass, warp-shuffle + ordered-uint atomics
 //   icell    : one pass, 16 B/particle read (3-D), 4 B write
-//   sort     : LSD radix, 8 bit digits (the reference uses 4), tiles of 4096
-//              keys per CTA; ranking with __match_any_sync (stable inside a
-//              warp by lane order, across warps/CTAs by prefix order), keys and
-//              permutation staged through shared memory so global stores of a
-//              digit run are contiguous; the last pass also emits the inverse
-//              permutation (RadixSort.cl.in:313-323).
+//   prepare  : cell keys + the digit totals of every sort pass + ihoc = N, one pass
+//   sort     : LSD radix, digits of 8 - 11 bits (the reference uses 4): TWO passes
+//              for the 18 - 22 bit cell keys of the BASELINE cases, one kernel per
+//              pass (tile offsets by decoupled look-back instead of a histogram,
+//              a scan and a scatter launch); tiles of 4096 keys per CTA, ranking
+//              with __match_any_sync (stable inside a warp by lane order, across
+//              warps/CTAs by prefix order), keys and permutation staged through
+//              shared memory so global stores of a digit run are contiguous; the
+//              last pass also emits the inverse permutation
+//              (RadixSort.cl.in:313-323).
 //   heads    : one pass over the sorted keys.
+// 5 launches per build (min/max, prepare, 2 passes, heads) against 12 before.
 #include <math.h>
 
 #include "aqc_common.cuh"
@@ -26,8 +31,6 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
 
 __device__ __forceinline__ uint32_t f2ord(float f)
 {
@@ -107,13 +110,10 @@ __global__ void minmax_init_kernel(uint32_t* out)
 
 // ---- iCell (LinkList.cl.in:54-85) -------------------------------------------
 template <int VS>
-__global__ void __launch_bounds__(256)
-icell_kernel(uint32_t* __restrict__ icell, const float* __restrict__ r, uint32_t N,
-             float rminx, float rminy, float rminz, float idist, uint32_t nx, uint32_t ny)
+__device__ __forceinline__ uint32_t icell_of(const float* __restrict__ r, size_t i, float rminx,
+                                             float rminy, float rminz, float idist, uint32_t nx,
+                                             uint32_t ny)
 {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= N)
-        return;
     float x, y, z = 0.f;
     if constexpr (VS == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(r) + i);
@@ -130,31 +130,90 @@ icell_kernel(uint32_t* __restrict__ icell, const float* __restrict__ r, uint32_t
         const uint32_t cz = (uint32_t)__fmul_rn(__fsub_rn(z, rminz), idist) + 3u;
         id += (cz - 1u) * nx * ny;
     }
-    icell[i] = id;
+    return id;
 }
 
 // ---- radix sort ---------------------------------------------------------------
-// Per-CTA digit histogram of one tile; hist layout [digit][block].
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift,
-                 uint32_t* __restrict__ hist, uint32_t nblocks)
+// Stable LSD sort, ONE kernel per digit (decoupled look-back between the tiles of a pass instead of
+// a histogram + scan + scatter triple) and digits of 8 ... 11 bits chosen so that the keys of a
+// link-list (18 - 22 bits at the BASELINE sizes) need two passes.  Scratch (ctx->sort_hist):
+//   ghist[MAX_PASSES][MAX_RADIX]  digit totals of every pass, counted by the prepare kernel
+//   ticket[MAX_PASSES]            tile tickets (a tile's predecessors are always running or done)
+//   status[pass][tile][RADIX]     tile digit counts: value | AGGREGATE, later prefix | INCLUSIVE
+constexpr int MAX_PASSES = 4;
+constexpr int MAX_BITS = 11;
+constexpr int MAX_RADIX = 1 << MAX_BITS;
+constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 1u << 31, ST_VAL = ST_AGG - 1u;
+constexpr int GH_WORDS = MAX_PASSES * MAX_RADIX + 32; // ghist + tickets (padded)
+constexpr int LOOK_W = 8;                             // predecessors polled per look-back round
+
+struct SortPlan {
+    int passes;
+    int bits[MAX_PASSES];
+    int shift[MAX_PASSES];
+};
+
+// Prepare kernel: (optionally) the cell keys of the particles, the digit totals of every pass, the
+// status words zeroed, and (optionally) ihoc filled with N (LinkList.cl.in:32-42) -- everything the
+// passes and the heads kernel need that does not depend on the order of the keys.
+template <int VS> // 0: keys are given, 2 / 4: keys = icell(r)
+__global__ void __launch_bounds__(256)
+sort_prepare_kernel(uint32_t* __restrict__ keys, const float* __restrict__ r, uint32_t n,
+                    float rminx, float rminy, float rminz, float idist, uint32_t nx, uint32_t ny,
+                    SortPlan plan, uint32_t* __restrict__ ghist, uint32_t* __restrict__ status,
+                    size_t status_words, uint32_t* __restrict__ fill, uint32_t fill_n,
+                    uint32_t fill_value, uint32_t* __restrict__ minmax_reset)
 {
-    __shared__ uint32_t cnt[RADIX];
-    cnt[threadIdx.x] = 0;
+    extern __shared__ uint32_t sh[]; // sum over passes of 2^bits counters
+    int total_bins = 0;
+    for (int p = 0; p < plan.passes; p++)
+        total_bins += 1 << plan.bits[p];
+    for (int k = threadIdx.x; k < total_bins; k += blockDim.x)
+        sh[k] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * SORT_TILE;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-#pragma unroll 4
-    for (int k = 0; k < SORT_ITEMS; k++) {
-        const uint32_t idx = base + w * (32 * SORT_ITEMS) + k * 32 + l;
-        const bool valid = idx < n;
-        const uint32_t d = valid ? ((__ldg(keys + idx) >> shift) & (RADIX - 1)) : 0xFFFFFFFFu;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
-        if (valid && l == (__ffs(m) - 1))
-            atomicAdd(&cnt[d], __popc(m));
+    const int l = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    // whole warps iterate together (__match_any_sync needs every lane)
+    const size_t n_up = ((size_t)n + 31) & ~(size_t)31;
+    for (size_t i = first; i < n_up; i += stride) {
+        const bool valid = i < n;
+        uint32_t key = 0;
+        if (valid) {
+            if constexpr (VS == 0)
+                key = __ldg(keys + i);
+            else {
+                key = icell_of<VS>(r, i, rminx, rminy, rminz, idist, nx, ny);
+                keys[i] = key;
+            }
+        }
+        int off = 0;
+        for (int p = 0; p < plan.passes; p++) {
+            const uint32_t d = valid ? ((key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))
+                                     : 0xFFFFFFFFu;
+            const uint32_t m = __match_any_sync(0xffffffffu, d);
+            if (valid && l == (__ffs(m) - 1))
+                atomicAdd(&sh[off + d], __popc(m));
+            off += 1 << plan.bits[p];
+        }
     }
+    for (size_t k = first; k < status_words; k += stride)
+        status[k] = 0u;
+    for (size_t k = first; k < fill_n; k += stride)
+        fill[k] = fill_value;
+    if (minmax_reset && blockIdx.x == 0 && threadIdx.x < 8)
+        minmax_reset[threadIdx.x] = threadIdx.x < 4 ? 0xFFFFFFFFu : 0u;
     __syncthreads();
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+    int off = 0;
+    for (int p = 0; p < plan.passes; p++) {
+        const int R = 1 << plan.bits[p];
+        for (int k = threadIdx.x; k < R; k += blockDim.x) {
+            const uint32_t c = sh[off + k];
+            if (c)
+                atomicAdd(ghist + p * MAX_RADIX + k, c);
+        }
+        off += R;
+    }
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* warp_sums,
@@ -185,53 +244,82 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wa
     return pre + x - v;
 }
 
-// One CTA per digit: exclusive scan of hist[d][0..nblocks) in place, total -> tot[d]
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ tot)
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p)
 {
-    __shared__ uint32_t ws[SORT_WARPS];
-    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-    uint32_t carry = 0;
-    for (uint32_t b0 = 0; b0 < nblocks; b0 += SORT_THREADS) {
-        const uint32_t b = b0 + threadIdx.x;
-        const uint32_t v = b < nblocks ? row[b] : 0u;
-        uint32_t t;
-        const uint32_t e = block_excl_scan_256(v, ws, &t);
-        if (b < nblocks)
-            row[b] = carry + e;
-        carry += t;
-    }
-    if (threadIdx.x == 0)
-        tot[blockIdx.x] = carry;
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Stable scatter of one tile.  vals_in == nullptr => values are the global
-// indices (first pass, RadixSort.cl.in:35-52 "init").
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                    uint32_t* __restrict__ inv_out, uint32_t n, int shift,
-                    const uint32_t* __restrict__ hist, uint32_t nblocks,
-                    const uint32_t* __restrict__ tot)
+// Sum of the digit-d counts of the tiles before `tile`: every status word carries its own flag, so
+// no fence is needed; LOOK_W predecessors are polled per round (their loads overlap), which bounds
+// the walk when a whole wave of tiles starts at once.
+template <int RADIX>
+__device__ __forceinline__ uint32_t look_back(const uint32_t* __restrict__ status, int tile, int d)
 {
-    __shared__ uint32_t wcnt[SORT_WARPS][RADIX]; // 8 KB
-    __shared__ uint32_t dstart[RADIX];           // local start of every digit
-    __shared__ uint32_t goff[RADIX];             // global offset - local start
+    uint32_t excl = 0;
+    int t = tile - 1;
+    while (t >= 0) {
+        uint32_t s[LOOK_W];
+#pragma unroll
+        for (int k = 0; k < LOOK_W; k++)
+            s[k] = (t - k >= 0) ? ld_status(status + (size_t)(t - k) * RADIX + d) : ST_INC;
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < LOOK_W; k++) {
+            if (used == k) { // everything before was an aggregate
+                if (s[k] & (ST_AGG | ST_INC)) {
+                    excl += s[k] & ST_VAL;
+                    used = (s[k] & ST_INC) ? LOOK_W + 1 : k + 1;
+                }
+            }
+        }
+        if (used > LOOK_W)
+            return excl;
+        t -= used; // used < LOOK_W: the next one is not published yet, poll again from there
+    }
+    return excl;
+}
+
+// One pass over one tile.  vals_in == nullptr => values are the global indices (first pass,
+// RadixSort.cl.in:35-52 "init").
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                 uint32_t* __restrict__ inv_out, uint32_t n, int shift,
+                 const uint32_t* __restrict__ ghist, uint32_t* __restrict__ ticket,
+                 uint32_t* __restrict__ status)
+{
+    constexpr int RADIX = 1 << BITS;
+    constexpr int DPT = RADIX / SORT_THREADS; // digits per thread: d = threadIdx.x + j * 256
+    extern __shared__ uint32_t smem[];
+    uint32_t* skeys = smem;                         // SORT_TILE
+    uint32_t* svals = skeys + SORT_TILE;            // SORT_TILE
+    uint32_t* goff = svals + SORT_TILE;             // RADIX: global offset - local start
+    uint16_t* dstart = (uint16_t*)(goff + RADIX);   // RADIX: local start of every digit
+    uint16_t* wcnt = dstart + RADIX;                // SORT_WARPS x RADIX
     __shared__ uint32_t ws[SORT_WARPS];
-    __shared__ uint32_t skeys[SORT_TILE];        // 16 KB
-    __shared__ uint32_t svals[SORT_TILE];        // 16 KB
+    __shared__ uint32_t tile_s;
 
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const uint32_t base = blockIdx.x * SORT_TILE;
+    if (threadIdx.x == 0)
+        tile_s = atomicAdd(ticket, 1u);
+    for (int k = threadIdx.x; k < SORT_WARPS * RADIX / 2; k += SORT_THREADS)
+        ((uint32_t*)wcnt)[k] = 0u;
+    __syncthreads();
+    const uint32_t tile = tile_s;
+    const uint32_t base = tile * SORT_TILE;
     const uint32_t valid_count = min((uint32_t)SORT_TILE, n - base);
     const uint32_t lt_mask = (1u << l) - 1u;
+    uint16_t* myw = wcnt + w * RADIX;
 
-#pragma unroll
-    for (int k = 0; k < SORT_WARPS; k++)
-        wcnt[k][threadIdx.x] = 0;
-    __syncthreads();
-
-    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
+    uint16_t rank[SORT_ITEMS];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t idx = base + w * (32 * SORT_ITEMS) + k * 32 + l;
@@ -246,36 +334,60 @@ sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __rest
         const int leader = __ffs(m) - 1;
         uint32_t old = 0;
         if (l == leader) {
-            old = wcnt[w][d];
-            wcnt[w][d] = old + __popc(m);
+            old = myw[d];
+            myw[d] = (uint16_t)(old + __popc(m));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = old + __popc(m & lt_mask);
+        rank[k] = (uint16_t)(old + __popc(m & lt_mask));
         __syncwarp();
     }
     __syncthreads();
 
-    // thread t owns digit t: prefix over warps, then scan over digits
-    {
-        const int d = threadIdx.x;
+    // thread t owns the digits t + 256 j: prefix over the warps, publish the tile's counts, scan
+    // over the digits (local starts and global digit bases), then the look-back
+    uint32_t cnt[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = threadIdx.x + j * SORT_THREADS;
         uint32_t run = 0;
 #pragma unroll
         for (int k = 0; k < SORT_WARPS; k++) {
-            const uint32_t c = wcnt[k][d];
-            wcnt[k][d] = run;
+            const uint32_t c = wcnt[k * RADIX + d];
+            wcnt[k * RADIX + d] = (uint16_t)run;
             run += c;
         }
-        const uint32_t ls = block_excl_scan_256(run, ws, nullptr);
-        const uint32_t gb = block_excl_scan_256(__ldg(tot + d), ws, nullptr);
-        dstart[d] = ls;
-        goff[d] = gb + __ldg(hist + (size_t)d * nblocks + blockIdx.x) - ls;
+        cnt[j] = run;
+        st_status(status + (size_t)tile * RADIX + d, run | (tile == 0 ? ST_INC : ST_AGG));
+    }
+    uint32_t lcarry = 0, gcarry = 0;
+    uint32_t gbase[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = threadIdx.x + j * SORT_THREADS;
+        uint32_t lt, gt;
+        const uint32_t ls = block_excl_scan_256(cnt[j], ws, &lt);
+        const uint32_t gs = block_excl_scan_256(__ldg(ghist + d), ws, &gt);
+        dstart[d] = (uint16_t)(lcarry + ls);
+        gbase[j] = gcarry + gs - (lcarry + ls);
+        lcarry += lt;
+        gcarry += gt;
+    }
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = threadIdx.x + j * SORT_THREADS;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            excl = look_back<RADIX>(status, (int)tile, d);
+            st_status(status + (size_t)tile * RADIX + d, (excl + cnt[j]) | ST_INC);
+        }
+        goff[d] = gbase[j] + excl;
     }
     __syncthreads();
 
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
         const uint32_t d = (key[k] >> shift) & (RADIX - 1);
-        const uint32_t lp = dstart[d] + wcnt[w][d] + rank[k];
+        const uint32_t lp = (uint32_t)dstart[d] + myw[d] + rank[k];
         skeys[lp] = key[k];
         svals[lp] = val[k];
     }
@@ -297,22 +409,20 @@ sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __rest
     }
 }
 
-__global__ void iota_kernel(uint32_t* p, uint32_t n)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        p[i] = i;
-}
-
 // ---- iHoc + linkList (LinkList.cl.in:32-42, 92-113) ------------------------
+// (ihoc was filled with N by the prepare kernel; this one also leaves the digit totals and the
+// tickets of the sort at zero for the next build)
 __global__ void __launch_bounds__(256)
-heads_kernel(const uint32_t* __restrict__ icell, uint32_t* __restrict__ ihoc, uint32_t N)
+heads_kernel(const uint32_t* __restrict__ icell, uint32_t* __restrict__ ihoc, uint32_t N,
+             uint32_t* __restrict__ ghist_reset)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghist_reset && i < GH_WORDS)
+        ghist_reset[i] = 0u;
     if (i >= N)
         return;
     const uint32_t c = __ldg(icell + i);
-    if (i == 0 || __ldg(icell + i - 1) != c)
+    if (N >= 2 && (i == 0 || __ldg(icell + i - 1) != c)) // (the reference launches N - 1 work-items)
         ihoc[c] = i;
 }
 
@@ -353,7 +463,44 @@ scatter_fields_kernel(const uint32_t* __restrict__ idx, uint32_t N, ScatterParam
     }
 }
 
-int ensure_sort_scratch(aqc_ctx* ctx, size_t n)
+SortPlan make_plan(uint32_t key_max)
+{
+    // digits covering every key < key_max (0 => full 32 bit): as few passes as 11-bit digits allow,
+    // the bits spread evenly over them (never less than 8: a narrower digit is not cheaper)
+    int bits = 32;
+    if (key_max) {
+        uint32_t top = key_max - 1;
+        bits = 0;
+        while (top) {
+            bits++;
+            top >>= 1;
+        }
+        if (bits == 0)
+            bits = 1;
+    }
+    SortPlan pl{};
+    pl.passes = (bits + MAX_BITS - 1) / MAX_BITS;
+    int shift = 0;
+    for (int p = 0; p < pl.passes; p++) {
+        int b = (bits - shift + (pl.passes - p) - 1) / (pl.passes - p);
+        if (b < 8)
+            b = 8;
+        pl.bits[p] = b;
+        pl.shift[p] = shift;
+        shift += b;
+    }
+    return pl;
+}
+
+size_t status_words(const SortPlan& pl, size_t nblocks)
+{
+    size_t w = 0;
+    for (int p = 0; p < pl.passes; p++)
+        w += nblocks << pl.bits[p];
+    return w;
+}
+
+int ensure_sort_scratch(aqc_ctx* ctx, size_t n, const SortPlan& pl)
 {
     if (n > ctx->sort_cap) {
         const size_t cap = n + n / 8 + 1024;
@@ -372,60 +519,96 @@ int ensure_sort_scratch(aqc_ctx* ctx, size_t n)
         ctx->sort_cap = cap;
     }
     const size_t nblocks = (n + SORT_TILE - 1) / SORT_TILE;
-    const size_t hneed = (size_t)RADIX * nblocks + RADIX;
+    const size_t hneed = GH_WORDS + status_words(pl, nblocks);
     if (hneed > ctx->sort_hist_cap) {
         if (ctx->sort_hist)
             AQC_CUDA(ctx, cudaFree(ctx->sort_hist));
         ctx->sort_hist = nullptr;
         ctx->sort_hist_cap = 0;
+        ctx->sort_ghist_clean = false;
         AQC_CUDA(ctx, cudaMalloc(&ctx->sort_hist, (hneed + hneed / 8) * sizeof(uint32_t)));
         ctx->sort_hist_cap = hneed + hneed / 8;
     }
     return AQC_OK;
 }
 
-int key_passes(uint32_t key_max)
+constexpr size_t pass_smem(int bits)
 {
-    // number of 8-bit passes covering every key < key_max (0 => full 32 bit)
-    if (key_max == 0)
-        return 4;
-    uint32_t top = key_max - 1;
-    int bits = 0;
-    while (top) {
-        bits++;
-        top >>= 1;
-    }
-    if (bits == 0)
-        bits = 1;
-    return (bits + RADIX_BITS - 1) / RADIX_BITS;
+    return (size_t)2 * SORT_TILE * 4 + ((size_t)4 << bits) + ((size_t)2 << bits) +
+           ((size_t)2 * SORT_WARPS << bits);
 }
 
-// Sort `n` keys found in ctx->sort_keys[start] (values implicit iota): the sorted
-// keys end in keys_out and the permutation in perm_out / inv_out (user arrays;
-// perm_out / inv_out may be NULL).  Intermediate passes ping-pong in scratch.
+template <int BITS>
+int launch_pass(aqc_ctx* ctx, uint32_t nblocks, const uint32_t* kin, const uint32_t* vin,
+                uint32_t* kout, uint32_t* vout, uint32_t* inv, uint32_t n, int shift,
+                const uint32_t* ghist, uint32_t* ticket, uint32_t* status)
+{
+    constexpr size_t smem = pass_smem(BITS);
+    // (per device, and cheap: set before every launch instead of remembering it per process)
+    AQC_CUDA(ctx, cudaFuncSetAttribute(sort_pass_kernel<BITS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_pass_kernel<BITS><<<nblocks, SORT_THREADS, smem, ctx->stream>>>(
+        kin, vin, kout, vout, inv, n, shift, ghist, ticket, status);
+    AQC_LAUNCH_CHECK(ctx);
+    return AQC_OK;
+}
 
-int run_sort(aqc_ctx* ctx, uint32_t n, int passes, int start, uint32_t* keys_out,
-             uint32_t* perm_out, uint32_t* inv_out)
+// Digit totals and tickets must be zero when the prepare kernel starts.
+int clean_ghist(aqc_ctx* ctx)
+{
+    if (!ctx->sort_ghist_clean)
+        AQC_CUDA(ctx, cudaMemsetAsync(ctx->sort_hist, 0, GH_WORDS * sizeof(uint32_t), ctx->stream));
+    ctx->sort_ghist_clean = false; // the prepare kernel is about to count into them
+    return AQC_OK;
+}
+
+unsigned prepare_grid(aqc_ctx* ctx, size_t n)
+{
+    unsigned grid = aqc_blocks(n, 256 * 8);
+    const unsigned cap = (unsigned)ctx->sm_count * 8;
+    return grid > cap ? cap : (grid ? grid : 1);
+}
+size_t prepare_smem(const SortPlan& pl)
+{
+    size_t bins = 0;
+    for (int p = 0; p < pl.passes; p++)
+        bins += (size_t)1 << pl.bits[p];
+    return bins * sizeof(uint32_t);
+}
+
+// Sort `n` keys (values implicit iota).  The prepare kernel has run: first_in holds the keys,
+// digit totals counted, status words zero.  The sorted keys end in keys_out and the permutation in
+// perm_out / inv_out (user arrays; perm_out / inv_out may be NULL).  Intermediate passes ping-pong
+// in scratch, starting with sort_keys[first_out].
+int run_sort(aqc_ctx* ctx, uint32_t n, const SortPlan& pl, const uint32_t* first_in, int first_out,
+             uint32_t* keys_out, uint32_t* perm_out, uint32_t* inv_out)
 {
     const uint32_t nblocks = (n + SORT_TILE - 1) / SORT_TILE;
-    uint32_t* hist = ctx->sort_hist;
-    uint32_t* tot = ctx->sort_hist + (size_t)RADIX * nblocks;
-    int cur = start;
-    for (int p = 0; p < passes; p++) {
-        const bool last = (p == passes - 1);
-        const uint32_t* kin = ctx->sort_keys[cur];
-        const uint32_t* vin = (p == 0) ? nullptr : ctx->sort_vals[cur];
-        uint32_t* kout = last ? keys_out : ctx->sort_keys[cur ^ 1];
-        uint32_t* vout = last ? perm_out : ctx->sort_vals[cur ^ 1];
-        const int shift = p * RADIX_BITS;
-        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(kin, n, shift, hist, nblocks);
-        AQC_LAUNCH_CHECK(ctx);
-        sort_rowscan_kernel<<<RADIX, SORT_THREADS, 0, ctx->stream>>>(hist, nblocks, tot);
-        AQC_LAUNCH_CHECK(ctx);
-        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(
-            kin, vin, kout, vout, last ? inv_out : nullptr, n, shift, hist, nblocks, tot);
-        AQC_LAUNCH_CHECK(ctx);
-        cur ^= 1;
+    uint32_t* ghist = ctx->sort_hist;
+    uint32_t* tickets = ctx->sort_hist + MAX_PASSES * MAX_RADIX;
+    uint32_t* status = ctx->sort_hist + GH_WORDS;
+    const uint32_t* kin = first_in;
+    const uint32_t* vin = nullptr;
+    int out = first_out;
+    for (int p = 0; p < pl.passes; p++) {
+        const bool last = (p == pl.passes - 1);
+        uint32_t* kout = last ? keys_out : ctx->sort_keys[out];
+        uint32_t* vout = last ? perm_out : ctx->sort_vals[out];
+        uint32_t* inv = last ? inv_out : nullptr;
+        const uint32_t* gh = ghist + p * MAX_RADIX;
+        int rc;
+        switch (pl.bits[p]) {
+            case 8: rc = launch_pass<8>(ctx, nblocks, kin, vin, kout, vout, inv, n, pl.shift[p], gh, tickets + p, status); break;
+            case 9: rc = launch_pass<9>(ctx, nblocks, kin, vin, kout, vout, inv, n, pl.shift[p], gh, tickets + p, status); break;
+            case 10: rc = launch_pass<10>(ctx, nblocks, kin, vin, kout, vout, inv, n, pl.shift[p], gh, tickets + p, status); break;
+            default: rc = launch_pass<11>(ctx, nblocks, kin, vin, kout, vout, inv, n, pl.shift[p], gh, tickets + p, status); break;
+        }
+        if (rc)
+            return rc;
+        status += (size_t)nblocks << pl.bits[p];
+        kin = kout;
+        vin = vout;
+        out ^= 1;
     }
     return AQC_OK;
 }
@@ -442,15 +625,27 @@ extern "C" int aqc_radix_sort(aqc_ctx* ctx, aqc_usize* keys, aqc_usize n, aqc_us
     aqc_pc_touch(ctx, keys, (size_t)n * sizeof(uint32_t));
     aqc_pc_touch(ctx, perm, (size_t)n * sizeof(uint32_t));
     aqc_pc_touch(ctx, inv_perm, (size_t)n * sizeof(uint32_t));
-    int rc = ensure_sort_scratch(ctx, n);
+    const SortPlan pl = make_plan(key_max);
+    int rc = ensure_sort_scratch(ctx, n, pl);
     if (rc)
         return rc;
-    const int passes = key_passes(key_max);
-    // the last pass must not write the buffer it reads: stage the input in scratch
-    const int start = 0;
-    AQC_CUDA(ctx, cudaMemcpyAsync(ctx->sort_keys[start], keys, (size_t)n * sizeof(uint32_t),
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-    return run_sort(ctx, n, passes, start, keys, perm, inv_perm);
+    if ((rc = clean_ghist(ctx)))
+        return rc;
+    // no pass may write the buffer it reads, and the last one writes `keys`: with one pass the
+    // input is staged in scratch, with more the first pass reads `keys` where they lie.  Without a
+    // permutation array the values still travel between the passes (scratch).
+    const uint32_t* first_in = keys;
+    if (pl.passes == 1) {
+        AQC_CUDA(ctx, cudaMemcpyAsync(ctx->sort_keys[1], keys, (size_t)n * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        first_in = ctx->sort_keys[1];
+    }
+    const uint32_t nblocks = (n + SORT_TILE - 1) / SORT_TILE;
+    sort_prepare_kernel<0><<<prepare_grid(ctx, n), 256, prepare_smem(pl), ctx->stream>>>(
+        const_cast<uint32_t*>(first_in), nullptr, n, 0.f, 0.f, 0.f, 0.f, 0u, 0u, pl, ctx->sort_hist,
+        ctx->sort_hist + GH_WORDS, status_words(pl, nblocks), nullptr, 0u, 0u, nullptr);
+    AQC_LAUNCH_CHECK(ctx);
+    return run_sort(ctx, n, pl, first_in, 0, keys, perm, inv_perm);
 }
 
 extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int dims,
@@ -478,8 +673,11 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
 
     const int vs = (dims == 3) ? 4 : 2;
     if (recompute_grid) {
-        minmax_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->minmax_dev);
-        AQC_LAUNCH_CHECK(ctx);
+        if (!ctx->minmax_clean) {
+            minmax_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->minmax_dev);
+            AQC_LAUNCH_CHECK(ctx);
+        }
+        ctx->minmax_clean = false;
         unsigned grid = aqc_blocks(N, 256);
         const unsigned cap = (unsigned)ctx->sm_count * 8;
         if (grid > cap)
@@ -537,35 +735,37 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
         *ihoc = (aqc_usize*)p;
         *ihoc_capacity = ncells[3];
     }
-    int rc = ensure_sort_scratch(ctx, N);
+    const SortPlan pl = make_plan(ncells[3]);
+    int rc = ensure_sort_scratch(ctx, N, pl);
     if (rc)
         return rc;
-    const int passes = key_passes(ncells[3]);
-    const int start = 0;
+    if ((rc = clean_ghist(ctx)))
+        return rc;
+    // one launch: cell keys (-> scratch), digit totals of every pass, status words zeroed, every
+    // cell of ihoc = N, and the min/max slots back at their identities for the next build
     const float idist = 1.f / cell_length;
+    const uint32_t nblocks = (N + SORT_TILE - 1) / SORT_TILE;
+    uint32_t* keys0 = ctx->sort_keys[0];
     if (vs == 4)
-        icell_kernel<4><<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>(
-            ctx->sort_keys[start], (const float*)r, N, rmin[0], rmin[1], rmin[2], idist,
-            ncells[0], ncells[1]);
+        sort_prepare_kernel<4><<<prepare_grid(ctx, N), 256, prepare_smem(pl), ctx->stream>>>(
+            keys0, (const float*)r, N, rmin[0], rmin[1], rmin[2], idist, ncells[0], ncells[1], pl,
+            ctx->sort_hist, ctx->sort_hist + GH_WORDS, status_words(pl, nblocks), *ihoc, ncells[3],
+            (uint32_t)N, ctx->minmax_dev);
     else
-        icell_kernel<2><<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>(
-            ctx->sort_keys[start], (const float*)r, N, rmin[0], rmin[1], 0.f, idist, ncells[0],
-            ncells[1]);
+        sort_prepare_kernel<2><<<prepare_grid(ctx, N), 256, prepare_smem(pl), ctx->stream>>>(
+            keys0, (const float*)r, N, rmin[0], rmin[1], 0.f, idist, ncells[0], ncells[1], pl,
+            ctx->sort_hist, ctx->sort_hist + GH_WORDS, status_words(pl, nblocks), *ihoc, ncells[3],
+            (uint32_t)N, ctx->minmax_dev);
     AQC_LAUNCH_CHECK(ctx);
-    rc = run_sort(ctx, N, passes, start, icell, perm, inv_perm);
+    ctx->minmax_clean = true;
+    rc = run_sort(ctx, N, pl, keys0, 1, icell, perm, inv_perm);
     if (rc)
         return rc;
-    // iHoc: every cell = N, then the heads
-    {
-        const aqc_usize Nval = N;
-        rc = aqc_fill(ctx, *ihoc, ncells[3], sizeof(aqc_usize), &Nval);
-        if (rc)
-            return rc;
-    }
-    if (N >= 2) { // the reference launches linkList on N-1 work-items
-        heads_kernel<<<aqc_blocks(N, 256), 256, 0, ctx->stream>>>(icell, *ihoc, N);
-        AQC_LAUNCH_CHECK(ctx);
-    }
+    // iHoc: the heads (every other cell holds N since the prepare kernel)
+    heads_kernel<<<aqc_blocks(N > GH_WORDS ? N : GH_WORDS, 256), 256, 0, ctx->stream>>>(
+        icell, *ihoc, N, ctx->sort_hist);
+    AQC_LAUNCH_CHECK(ctx);
+    ctx->sort_ghist_clean = true;
     return AQC_OK;
 }
 

@@ -838,7 +838,7 @@ struct PMpiInteractions : PBase {
 // cfd/MPI.cl interactions + gamma in one pass over the remote (halo) list: the two kernels
 // share i set (gamma's is the wider one), candidates and geometry.  Same expressions as the
 // members; the Shepard weight cW m_j/rho_j is derived from the staged cF m_j/rho_j.
-template <int D>
+template <int D, bool DELTA>
 struct PMpiFused : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
@@ -846,10 +846,13 @@ struct PMpiFused : PBase {
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;
     const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
-    void *grad_p, *lap_u;
-    float *div_u, *shepard;
+    void *grad_p, *lap_u, *lap_p_corr;
+    float *div_u, *shepard, *lap_p;
     float cF, cWF, eps2;
-    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du, sh; bool fluid; };
+    struct IState {
+        float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du, sh, ax, ay, az, lp;
+        bool fluid;
+    };
     __device__ bool i_active(int mv) const { return !((mv < -3) || ((mv > 0) && (mv != 1))); }
     __device__ void load_i(IState& s, uint32_t i) const
     {
@@ -863,6 +866,7 @@ struct PMpiFused : PBase {
             s.p = __ldg(p + i);
         }
         s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = s.sh = 0.f;
+        s.ax = s.ay = s.az = s.lp = 0.f;
     }
     __device__ void stage_j(uint32_t j, float4* o) const
     {
@@ -886,6 +890,11 @@ struct PMpiFused : PBase {
             return;
         const float4 B = row[stride];
         const float fr = t2 * (t * A.w);
+        if constexpr (DELTA) { // aqua/MPIdeltaSPH.cl::full_lapp (PMpiDelta::body)
+            const float c = (B.w - s.p) * fr;
+            s.ax += c * dx; s.ay += c * dy; s.az += c * dz;
+            s.lp += c;
+        }
         float udr = (B.x - s.ux) * dx + (B.y - s.uy) * dy;
         if constexpr (D == 3)
             udr += (B.z - s.uz) * dz;
@@ -908,6 +917,11 @@ struct PMpiFused : PBase {
         stvec_xyz<D>(grad_p, i, g0.x + s.gx * ir, g0.y + s.gy * ir, g0.z + s.gz * ir);
         stvec_xyz<D>(lap_u, i, l0.x + s.lx * cl, l0.y + s.ly * cl, l0.z + s.lz * cl);
         div_u[i] += s.du * rho_i;
+        if constexpr (DELTA) {
+            const float4 c0 = ldvec_rw<D>(lap_p_corr, i);
+            stvec_xyz<D>(lap_p_corr, i, c0.x + s.ax, c0.y + s.ay, c0.z + s.az);
+            lap_p[i] += s.lp;
+        }
     }
 };
 
@@ -2202,13 +2216,17 @@ template <bool SHEP, bool FULL, bool LAPP> int l_fused_fluid(aqc_ctx* c, void* c
     return c->defs.dims == 3 ? run_fused_fluid<3, SHEP, FULL, LAPP>(c, a)
                              : run_fused_fluid<2, SHEP, FULL, LAPP>(c, a);
 }
-template <int D> int run_mpi_fused(aqc_ctx* ctx, void* const* a)
+template <int D, bool DELTA> int run_mpi_fused(aqc_ctx* ctx, void* const* a)
 {
     // interactions: imove r u rho p mpi_r mpi_u mpi_rho mpi_p mpi_m grad_p lap_u div_u N
     //               icell mpi_icell mpi_ihoc n_cells (18); gamma: imove r rho m mpi_r mpi_rho
     //               mpi_m shepard N icell mpi_icell mpi_ihoc n_cells (13)
+    //               [full_lapp: imove r p mpi_r mpi_rho mpi_m mpi_p lap_p_corr lap_p N icell
+    //               mpi_icell mpi_ihoc n_cells (14)]
     void* const* g = a + 18;
-    PMpiFused<D> p;
+    PMpiFused<D, DELTA> p;
+    p.lap_p_corr = DELTA ? g[13 + 7] : nullptr;
+    p.lap_p = DELTA ? (float*)g[13 + 8] : nullptr;
     set_base(p, ctx, a[0]);
     p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.p = (const float*)a[4];
     p.mpi_r = a[5]; p.mpi_u = a[6]; p.mpi_rho = (const float*)a[7]; p.mpi_p = (const float*)a[8];
@@ -2219,9 +2237,9 @@ template <int D> int run_mpi_fused(aqc_ctx* ctx, void* const* a)
     p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
     return launch_sweep(ctx, p, make_ll_remote(a, 14, aqc_scalar<uint32_t>(a, 13)));
 }
-int l_mpi_fused(aqc_ctx* c, void* const* a)
+template <bool DELTA> int l_mpi_fused(aqc_ctx* c, void* const* a)
 {
-    return c->defs.dims == 3 ? run_mpi_fused<3>(c, a) : run_mpi_fused<2>(c, a);
+    return c->defs.dims == 3 ? run_mpi_fused<3, DELTA>(c, a) : run_mpi_fused<2, DELTA>(c, a);
 }
 #define K_SHEP "cfd/Shepard.cl::entry"
 #define K_INTER "cfd/Interactions.cl::entry"
@@ -2233,7 +2251,9 @@ const std::vector<FusedEntry>& fused_table()
         { { K_SHEP, K_INTER, K_FULL, K_LAPP }, l_fused_fluid<true, true, true> },
         { { K_SHEP, K_INTER }, l_fused_fluid<true, false, false> },
         { { K_INTER, K_FULL, K_LAPP }, l_fused_fluid<false, true, true> },
-        { { "cfd/MPI.cl::interactions", "cfd/MPI.cl::gamma" }, l_mpi_fused },
+        { { "cfd/MPI.cl::interactions", "cfd/MPI.cl::gamma", "aqua/MPIdeltaSPH.cl::full_lapp" },
+          l_mpi_fused<true> },
+        { { "cfd/MPI.cl::interactions", "cfd/MPI.cl::gamma" }, l_mpi_fused<false> },
     };
     return t;
 }

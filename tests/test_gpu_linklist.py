@@ -98,7 +98,13 @@ def test_radix_sort_reference_inputs(golden, ctx3, d):
     assert np.array_equal(p, np.argsort(f_orig, kind="stable"))
 
 
-@pytest.mark.parametrize("n,key_max", [(1, 0), (255, 7), (4096, 256), (100003, 0), (1 << 20, 70000)])
+# key_max picks the digits (linklist.cu make_plan): 1 pass of 8 bits; 2 x 8; 2 x 9 (the dam break's
+# n_cells.w); 2 x 10; 2 x 11; 3 passes (11 + 11 + 10 for the full 32 bits, 8 + 8 + 8 for 23); sizes on
+# and around the tile of 4096 keys, and two more tiles than one wave of CTAs holds
+@pytest.mark.parametrize("n,key_max", [(1, 0), (2, 2), (33, 2), (255, 7), (4096, 256), (4097, 257),
+                                       (8192, 1 << 18), (100003, 0), (1 << 20, 70000),
+                                       (300001, 1 << 20), (123457, 1 << 22), (70001, 1 << 23),
+                                       (3 * 1000 * 1000 + 17, 150000)])
 def test_radix_sort_random(ctx3, n, key_max):
     rng = np.random.default_rng(n)
     hi = key_max if key_max else 2 ** 32
@@ -110,6 +116,13 @@ def test_radix_sort_random(ctx3, n, key_max):
     assert np.array_equal(keys.get(), k[ref])
     ip = inv.get()
     assert np.array_equal(ip[ref], np.arange(n, dtype=np.uint32))
+    # many equal keys (stability across tiles) and without the optional outputs; the context's
+    # scratch is reused from the call above (digit totals / tickets cleaned by the library)
+    k2 = (k % np.uint32(5)).astype(np.uint32) if key_max != 2 else k
+    keys.set(k2)
+    ctx3.radix_sort(keys, key_max, perm, None)
+    ref2 = np.argsort(k2, kind="stable").astype(np.uint32)
+    assert np.array_equal(perm.get(), ref2) and np.array_equal(keys.get(), k2[ref2])
 
 
 def test_scatter_fields_and_fill(ctx3, oracle):

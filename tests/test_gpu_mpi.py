@@ -117,6 +117,65 @@ def test_mpi_kernels_match_reference_scripts(oracle, dims):
         a, b = sep[k].astype(np.float64), dev[k].get().astype(np.float64)
         assert np.abs(a - pre[k]).max() > 0, k
         assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), ("fused remote sweep", k)
+    # ---- aqua/MPIdeltaSPH.cl (ours: the remote delta-SPH / MLS terms the reference's MPI preset
+    # lacks) against its plain-C statement in the oracle, on the same halo list
+    from oracle import oracle as O
+    D = O.make_defs(dims, case["h"])
+    rl = O.make_ll(hostv["mpi_icell"], hostv["mpi_ihoc"], hostv["n_cells"], N)
+    extra = {"mls": rng.normal(size=(N, V * V)).astype(np.float32),
+             "lap_p": rng.normal(size=N).astype(np.float32),
+             "lap_p_corr": rng.normal(size=(N, V)).astype(np.float32),
+             "mpi_lap_p_corr": rng.normal(size=(n_radix, V)).astype(np.float32),
+             "mpi_lap_p_corr_in": rng.normal(size=(n_radix, V)).astype(np.float32)}
+    for k, v in extra.items():
+        hostv[k] = v.copy()
+        dev[k] = ctx.array(v)
+    hostv["mls_imove"] = dev["mls_imove"] = 1
+
+    def ours(entry, call, outs, exact=False):
+        call()
+        ctx.launch("aqua/MPIdeltaSPH.cl", entry, dev, n=N)
+        for k in outs:
+            a, b = hostv[k].astype(np.float64), dev[k].get().astype(np.float64)
+            if exact:
+                assert np.array_equal(a, b), (entry, k)
+            else:
+                assert np.abs(a - extra[k]).max() > 0, (entry, k, "no remote term")
+                assert np.abs(a - b).max() <= 5e-6 * np.abs(a).max(), (entry, k)
+
+    H = hostv
+    ours("mls", lambda: O.pcall("mpi_mls", N, D, rl, H["icell"], H["imove"], H["r"], H["mpi_r"], H["mpi_rho"],
+                                H["mpi_m"], H["mls"], 1), ("mls",))
+    pre = {k: dev[k].get() for k in ("shepard", "grad_p", "lap_u", "div_u", "lap_p", "lap_p_corr")}
+    ours("full_lapp", lambda: O.pcall("mpi_dsph_full_lapp", N, D, rl, H["icell"], H["imove"], H["r"], H["p"],
+                                      H["mpi_r"], H["mpi_rho"], H["mpi_m"], H["mpi_p"], H["lap_p_corr"],
+                                      H["lap_p"]), ("lap_p_corr", "lap_p"))
+    # the pipeline launches interactions + gamma + full_lapp as ONE remote sweep
+    ctx.launch("cfd/MPI.cl", "gamma", dev, n=N)
+    ctx.launch("cfd/MPI.cl", "interactions", dev, n=N)
+    sep = {k: dev[k].get() for k in pre}
+    for k, v in pre.items():
+        dev[k].set(v)
+    ctx.launch_fused([("cfd/MPI.cl", "interactions"), ("cfd/MPI.cl", "gamma"),
+                      ("aqua/MPIdeltaSPH.cl", "full_lapp")], dev)
+    for k in pre:
+        a, b = sep[k].astype(np.float64), dev[k].get().astype(np.float64)
+        assert np.abs(a - pre[k]).max() > 0, k
+        assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), ("fused remote sweep with delta-SPH", k)
+    extra["lap_p"] = dev["lap_p"].get()
+    H["lap_p"][...] = extra["lap_p"]
+    H["lap_p_corr"][...] = dev["lap_p_corr"].get()
+    ours("lapp_corr", lambda: O.pcall("mpi_dsph_lapp_corr", N, D, rl, H["icell"], H["imove"], H["r"],
+                                      H["lap_p_corr"], H["mpi_r"], H["mpi_rho"], H["mpi_m"], H["mpi_lap_p_corr"],
+                                      H["lap_p"]), ("lap_p",))
+
+    def copy_g():
+        H["mpi_lap_p_corr"][:N] = H["lap_p_corr"][:N]
+
+    def sort_g():
+        H["mpi_lap_p_corr"][H["mpi_id_sorted"][:N]] = H["mpi_lap_p_corr_in"][:N]
+    ours("copy_g", copy_g, ("mpi_lap_p_corr",), exact=True)
+    ours("sort_g", sort_g, ("mpi_lap_p_corr",), exact=True)
     ctx.close()
 
 

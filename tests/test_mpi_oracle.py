@@ -122,7 +122,7 @@ def test_mpi_plane_two_processes_gloo(golden, oracle):
             assert np.array_equal(got[r][k], ref_ranks[r][k]), (r, k)
 
 
-def _dam_break_ranks(size, n_total, steps, delta_sph=False, **kw):
+def _dam_break_ranks(size, n_total, steps, delta_sph=False, maxiter=3, **kw):
     """The 3-D dam break cut in `size` y slabs through the oracle interpreter (threads), with the
     multi-device additions of casegen.multi_device_fixes (and the delta-SPH / MLS stages of
     casegen.slab_delta_sph); returns the device-order state."""
@@ -135,7 +135,7 @@ def _dam_break_ranks(size, n_total, steps, delta_sph=False, **kw):
         try:
             c = cases.spheric2_dam_break_slab(n_total, 3.0, rank, size, **kw)
             txt = casegen.instantiate("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]),
-                                      {"iter_midpoint_max": 3})
+                                      {"iter_midpoint_max": maxiter})
             txt = (casegen.slab_fixes_delta_sph(float(c["delta"][0])) if delta_sph
                    else casegen.multi_device_fixes)(txt)
             I = interp.Interpreter(txt, 3, rank=rank, size=size, transport=tr)
@@ -194,6 +194,24 @@ def test_dam_break_three_slabs_with_migration(oracle):
     assert arrived > 20, arrived
 
 
+def _one_rank_is_the_116_tool_pipeline_when_particles_reach_the_walls():
+    """Jittered, fast particles: some bounce off the walls within a step, so the element radius
+    (__DR_FACTOR__, which the single-device example sets and the MPI example does not) must have
+    travelled into the slab pipeline with the other definitions."""
+    from aquagpusph_b200 import cases, casegen
+    kw = dict(seed=5, jitter=0.45, uscale=2.0)
+    n_total = 12000
+    c = cases.spheric2_dam_break(n_total, 3.0, **kw)
+    I = interp.Interpreter(casegen.instantiate("spheric2_dambreak_3d", c, (c["N"] - 8, 8),
+                                               {"iter_midpoint_max": 2}), 3)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = c[k]
+    I.step()
+    one = _dam_break_ranks(1, n_total, 1, delta_sph=True, maxiter=2, **kw)[0]
+    for k in ("r", "u", "rho", "dudt", "drhodt"):
+        assert np.array_equal(one["unsorted"][k], I.unsorted(k)[one["fluid_index"]]), k
+
+
 def test_slab_pipeline_with_delta_sph_is_the_single_device_pipeline(oracle):
     """casegen.slab_delta_sph: the reference's MPI example pipeline extended with the delta-SPH and
     MLS stages of the single-device dam break (remote terms: aqua/MPIdeltaSPH.cl, ours -- the
@@ -222,6 +240,7 @@ def test_slab_pipeline_with_delta_sph_is_the_single_device_pipeline(oracle):
     assert one["dt"] == float(I.V["dt"])
     for k in serial:
         assert np.array_equal(one["unsorted"][k], serial[k][one["fluid_index"]]), k
+    _one_rank_is_the_116_tool_pipeline_when_particles_reach_the_walls()
     for r in range(3):
         g = three[r]
         assert g["dt"] == float(I.V["dt"]) and g["n_tools"] == one["n_tools"]

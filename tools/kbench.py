@@ -99,6 +99,8 @@ def main():
     vb = 16 if dims == 3 else 8
     tests = [
         ("linklist", relink, (vb + 20 + 4 + 16 * 2 + 8 + 4) * N),
+        # the link-list build alone on the cell-ordered state: SURVEY 8(d)'s 84 B + 4 n_cells.w / N per particle
+        ("linklist_only", linklist, 84 * N + 4 * int(nc[3])),
         ("sort_stage1+2", lambda: (backup(), K("basic/Sort.cl", "stage1")(), K("basic/Sort.cl", "stage2")()), 212 * N),
         ("predictor", K("basic/time_scheme/midpoint.cl", "predictor"), 112 * N),
         ("eos", K("basic/EOS.cl"), 16 * N),

@@ -15,7 +15,8 @@ if world > 1:
     uid = [host.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
 host.set_log_level(3)
-sim, case = casegen.spheric2_slab(n * world, rank, world, device=lr, unique_id=uid[0])
+dsph = len(sys.argv) > 2 and sys.argv[2] == "dsph"
+sim, case = casegen.spheric2_slab(n * world, rank, world, device=lr, unique_id=uid[0], delta_sph=dsph)
 for _ in range(3):
     sim.step(1)
 sim.sync()
@@ -34,8 +35,9 @@ if world > 1:
     dist.barrier()
 if rank in (0, world - 1):
     tot = sum(r[0] for r in rows)
-    print("rank %d: %.2f ms/step over %d tools" % (rank, tot / steps, len(rows)))
-    for ms, k, name in rows[:28]:
-        print("rank %d  %-40s x%-3d %8.3f ms/step" % (rank, name, k // steps, ms / steps), flush=True)
+    sys.stdout.write("rank %d: %.2f ms/step over %d tools\n" % (rank, tot / steps, len(rows)))
+    for ms, k, name in rows[:44]:
+        sys.stdout.write("rank %d  %-40s x%-3d %8.3f ms/step\n" % (rank, name, k // steps, ms / steps))
+    sys.stdout.flush()
 if world > 1:
     dist.destroy_process_group()
