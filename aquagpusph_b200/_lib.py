@@ -20,7 +20,7 @@ SYMBOLS = [
     "aqc_sync", "aqc_launch_count", "aqc_device_sm_count", "aqc_define_round6", "aqc_set_defs",
     "aqc_set_define",
     "aqc_alloc", "aqc_free", "aqc_host_alloc", "aqc_host_free", "aqc_memcpy_h2d",
-    "aqc_memcpy_d2h", "aqc_memcpy_d2d", "aqc_fill", "aqc_linklist_build", "aqc_radix_sort",
+    "aqc_memcpy_d2h", "aqc_memcpy_d2d", "aqc_side_fork", "aqc_memcpy_d2h_side", "aqc_side_record", "aqc_side_wait", "aqc_fill", "aqc_linklist_build", "aqc_radix_sort",
     "aqc_scatter_fields", "aqc_reduce", "aqc_kernel_lookup", "aqc_kernel_count",
     "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",

@@ -82,6 +82,11 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFreeHost(ctx->minmax_host);
     cudaFree(ctx->red_dev);
     cudaFreeHost(ctx->red_host);
+    if (ctx->side) {
+        cudaStreamSynchronize(ctx->side);
+        cudaStreamDestroy(ctx->side);
+        cudaEventDestroy(ctx->side_fork_ev);
+    }
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -118,6 +123,50 @@ extern "C" int aqc_sync(aqc_ctx* ctx)
         return AQC_ERR_ARG;
     AQC_SYNC(ctx);
     return AQC_OK;
+}
+
+// ---- side stream of the savers (Particles.cpp:243-323) ---------------------------------------
+extern "C" int aqc_side_fork(aqc_ctx* ctx)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    if (!ctx->side) {
+        AQC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        AQC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->side_fork_ev, cudaEventDisableTiming));
+    }
+    AQC_CUDA(ctx, cudaEventRecord(ctx->side_fork_ev, ctx->stream));
+    AQC_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->side_fork_ev, 0));
+    return AQC_OK;
+}
+
+extern "C" int aqc_memcpy_d2h_side(aqc_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx || !ctx->side)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_memcpy_d2h_side: aqc_side_fork first");
+    if (!bytes)
+        return AQC_OK;
+    if (!dst || !src)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_memcpy_d2h_side: NULL pointer");
+    AQC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->side));
+    return AQC_OK;
+}
+
+extern "C" int aqc_side_record(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx || !ctx->side || !ev)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_side_record: aqc_side_fork first, ev != NULL");
+    AQC_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->side));
+    return AQC_OK;
+}
+
+extern "C" int aqc_side_wait(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx || !ev)
+        return AQC_ERR_ARG;
+    // (no aqc_fail here: ctx->err belongs to the thread that drives the context)
+    if (cudaSetDevice(ctx->device) != cudaSuccess)
+        return AQC_ERR_CUDA;
+    return cudaEventSynchronize((cudaEvent_t)ev) == cudaSuccess ? AQC_OK : AQC_ERR_CUDA;
 }
 
 extern "C" uint64_t aqc_launch_count(const aqc_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -78,6 +78,8 @@ struct aqc_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;     // savers' downloads (aqc_side_*), created on first use
+    cudaEvent_t side_fork_ev = nullptr;
     uint64_t launches = 0;
     aqc_defs defs{ 3, 1.f, 1.f, 1.f, 2.f, 3.f };
     // __DR_FACTOR__ / __MIN_BOUND_DIST__ / __ELASTIC_FACTOR__: script-specific defaults

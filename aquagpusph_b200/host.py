@@ -18,7 +18,7 @@ SYMBOLS = [
     "aqh_comm_unique_id", "aqh_comm_init",
     "aqh_write_resolved", "aqh_n_tools", "aqh_tool_name", "aqh_tool_type", "aqh_tool_elapsed_ms",
     "aqh_tool_used_times", "aqh_step", "aqh_run", "aqh_sync", "aqh_launch_count", "aqh_cuda_ctx",
-    "aqh_fused_groups",
+    "aqh_fused_groups", "aqh_save", "aqh_wait_savers", "aqh_checkpoint_file", "aqh_n_savers", "aqh_saver_file",
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr", "aqh_set_script_runner", "aqh_variable_type",
 ]
@@ -101,6 +101,13 @@ def lib():
     L.aqh_step.argtypes = [C.c_void_p, C.c_int]
     L.aqh_run.argtypes = [C.c_void_p]
     L.aqh_sync.argtypes = [C.c_void_p]
+    L.aqh_save.argtypes = [C.c_void_p]
+    L.aqh_wait_savers.argtypes = [C.c_void_p]
+    L.aqh_checkpoint_file.argtypes = [C.c_void_p]
+    L.aqh_checkpoint_file.restype = C.c_char_p
+    L.aqh_n_savers.argtypes = [C.c_void_p]
+    L.aqh_saver_file.argtypes = [C.c_void_p, C.c_int]
+    L.aqh_saver_file.restype = C.c_char_p
     L.aqh_launch_count.argtypes = [C.c_void_p]
     L.aqh_launch_count.restype = C.c_uint64
     L.aqh_fused_groups.argtypes = [C.c_void_p]
@@ -217,6 +224,21 @@ class Simulation:
 
     def run(self):
         self._stepping(lib().aqh_run)
+
+    def save(self, wait=False):
+        """FileManager::save: start the <Save> files of every set (asynchronously) and rewrite the
+        AQUAgpusph.save.N.xml state file; returns its path."""
+        _chk(lib().aqh_save(self.h))
+        if wait:
+            self.wait_savers()
+        return lib().aqh_checkpoint_file(self.h).decode()
+
+    def wait_savers(self):
+        _chk(lib().aqh_wait_savers(self.h))
+
+    def saver_files(self):
+        L = lib()
+        return [L.aqh_saver_file(self.h, i).decode() for i in range(L.aqh_n_savers(self.h))]
 
     # type="python" tools (aquagpusph_b200/pytool.py): get / set of the `aquagpusph` module
     def _run_script(self, path):

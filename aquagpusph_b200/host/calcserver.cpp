@@ -919,6 +919,7 @@ CalcServer::CalcServer(ProblemSetup& sd, int device, int mpi_rank, int mpi_size)
 
 CalcServer::~CalcServer()
 {
+    _savers.clear(); // (joins the writer threads, frees their staging buffers)
     _tools.clear();
     if (_unsort_scratch)
         aqc_free(_ctx, _unsort_scratch);
@@ -1280,7 +1281,7 @@ void CalcServer::loadParticles()
         }
         if (!set.in_path.empty()) {
             const std::string fmt = toLowerCopy(set.in_format);
-            if (fmt != "fastascii" && fmt != "ascii")
+            if (fmt != "fastascii" && fmt != "ascii" && fmt != "csv")
                 throw std::runtime_error("Particles set " + std::to_string(iset) +
                                          ": unsupported input format \"" + set.in_format + "\"");
             std::vector<Variable*> fields;
@@ -1340,50 +1341,6 @@ void CalcServer::loadParticles()
                     throw std::runtime_error(aqc_last_error(_ctx));
         }
         offset += n;
-    }
-}
-
-void CalcServer::saveParticles(const std::string& suffix)
-{
-    size_t offset = 0;
-    for (size_t iset = 0; iset < _sim_data.sets.size(); iset++) {
-        auto& set = *_sim_data.sets[iset];
-        for (auto& o : set.outputs) {
-            std::vector<Variable*> fields;
-            for (auto f : split(o[2])) {
-                Variable* v = _vars->get(f);
-                if (v && v->isArray() && v->length() == _vars->get("id")->length())
-                    fields.push_back(v);
-            }
-            std::vector<std::vector<char>> host;
-            for (auto v : fields) {
-                host.emplace_back(v->size());
-                getUnsortedMem(v->name(), host.back().data());
-            }
-            const std::string path = formatPath(o[0], _mpi_rank) + suffix + ".dat";
-            FILE* f = fopen(path.c_str(), "w");
-            if (!f)
-                throw std::runtime_error("Cannot write \"" + path + "\"");
-            fprintf(f, "# AQUAgpusph particles set %zu; fields:", iset);
-            for (auto v : fields)
-                fprintf(f, " %s", v->name().c_str());
-            fprintf(f, "\n");
-            for (size_t i = offset; i < offset + set.n; i++) {
-                for (size_t k = 0; k < fields.size(); k++) {
-                    Variable* v = fields[k];
-                    const char* e = host[k].data() + i * v->typesize();
-                    for (unsigned c = 0; c < v->ncomp(); c++) {
-                        if (v->kind() == 'f') fprintf(f, "%.9g", *(const float*)(e + 4 * c));
-                        else if (v->kind() == 'u') fprintf(f, "%u", *(const uint32_t*)(e + 4 * c));
-                        else fprintf(f, "%d", *(const int32_t*)(e + 4 * c));
-                        fputc(c + 1 < v->ncomp() ? ' ' : ',', f);
-                    }
-                }
-                fputc('\n', f);
-            }
-            fclose(f);
-        }
-        offset += set.n;
     }
 }
 

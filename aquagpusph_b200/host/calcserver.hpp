@@ -11,6 +11,7 @@
 // scalar computed on the device is needed by host logic (reductions, the
 // link-list grid), which is where the reference blocks too.
 #pragma once
+#include <thread>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -371,6 +372,37 @@ class TimeManager {
     int _output_ipf = -1;
 };
 
+/// The saver of one <Save> of a particles set (InputOutput/Particles.cpp:82-120, 243-323;
+/// ASCII.cpp:240-333): device-side un-sort, download on the context's side stream into pinned
+/// memory, file written by a thread that waits for the copy event (host/savers.cpp)
+class ParticlesSaver {
+  public:
+    ParticlesSaver(CalcServer* C, size_t iset, size_t first, size_t n, const std::string& path,
+                   const std::string& format, const std::string& fields);
+    ~ParticlesSaver();
+    /// Queue the download and start the writer; returns without waiting for either
+    void save(float t);
+    /// Particles::waitForSavers: block until the last file is complete (rethrows a writer error)
+    void wait();
+    size_t set() const { return _iset; }
+    const std::string& file() const { return _file; }     ///< last file started
+    const std::string& format() const { return _format; } ///< format actually written
+    const std::string& fields() const { return _fields_txt; }
+  private:
+    struct Field;
+    std::string nextFile();
+    void print_file();
+    CalcServer* _C;
+    size_t _iset, _first, _n;
+    std::string _path, _format, _ext, _fields_txt, _file, _error;
+    char _sep = ',', _csep = ' '; // ASCII.hpp:83: print_file(',', ' ')
+    unsigned _next_index = 0;
+    float _time = 0.f;
+    std::vector<std::unique_ptr<Field>> _fields;
+    void* _event = nullptr;
+    std::thread _writer;
+};
+
 /// The simulation: variables + tools on one device (CalcServer.cpp:139-621)
 class CalcServer {
   public:
@@ -404,8 +436,13 @@ class CalcServer {
     void getUnsortedMem(const std::string& var, void* out);
     void download(const std::string& var, void* out);
     void upload(const std::string& var, const void* in);
-    /// ASCII dump of the <Save> fields of every set (ASCII.cpp:240-333 layout)
-    void saveParticles(const std::string& suffix);
+    /// FileManager::save (FileManager.cpp:146-155): every set's <Save> file (asynchronously, see
+    /// ParticlesSaver) and the AQUAgpusph.save.N.xml state file the run can be resumed from
+    void save(float t);
+    /// FileManager::waitForSavers (FileManager.cpp:157-164)
+    void waitForSavers();
+    const std::string& checkpoint_file() const { return _checkpoint_file; }
+    const std::vector<std::unique_ptr<ParticlesSaver>>& savers() const { return _savers; }
     uint64_t steps_done() const { return _steps; }
     /// Join the NCCL communicator of the run (id = 128 bytes made by rank 0 with
     /// aqc_comm_unique_id and distributed by the launcher); replaces MPI_Init
@@ -424,6 +461,9 @@ class CalcServer {
     unsigned _fused_groups = 0;
     void* _unsort_scratch = nullptr;
     size_t _unsort_cap = 0;
+    void writeCheckpoint();
+    std::vector<std::unique_ptr<ParticlesSaver>> _savers;
+    std::string _checkpoint_file;
 };
 
 } // namespace CalcServer

@@ -17,6 +17,35 @@ struct aqh_sim {
 
 static thread_local std::string g_err;
 
+// AQUA_SEGV_BACKTRACE=1: a fatal signal inside the host or a plugin prints the native frames first
+// (the driving process usually only knows its own, interpreted, ones)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void aqh_fatal_signal(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "libaquahost: fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+namespace {
+struct SegvBacktrace {
+    SegvBacktrace()
+    {
+        const char* e = getenv("AQUA_SEGV_BACKTRACE");
+        if (e && atoi(e) != 0) {
+            signal(SIGSEGV, aqh_fatal_signal);
+            signal(SIGBUS, aqh_fatal_signal);
+            signal(SIGABRT, aqh_fatal_signal);
+        }
+    }
+} g_segv_backtrace;
+} // namespace
+
 #define AQH_TRY try {
 #define AQH_CATCH                                                              \
     }                                                                          \
@@ -148,13 +177,45 @@ extern "C" int aqh_step(aqh_sim* sim, int n)
 extern "C" int aqh_run(aqh_sim* sim)
 {
     AQH_TRY
-    while (!sim->T->mustStop())
+    // main.cpp:162-181: update until an output frame is due, save it, ...; wait for the writers
+    while (!sim->T->mustStop()) {
         sim->C->update(*sim->T);
+        sim->C->save(sim->T->time());
+    }
     if (aqc_sync(sim->C->ctx()))
         throw std::runtime_error(aqc_last_error(sim->C->ctx()));
-    sim->C->saveParticles("");
+    sim->C->waitForSavers();
     return 0;
     AQH_CATCH
+}
+
+extern "C" int aqh_save(aqh_sim* sim)
+{
+    AQH_TRY
+    sim->C->save(sim->T->time());
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" int aqh_wait_savers(aqh_sim* sim)
+{
+    AQH_TRY
+    sim->C->waitForSavers();
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" const char* aqh_checkpoint_file(aqh_sim* sim)
+{
+    return (sim && sim->C) ? sim->C->checkpoint_file().c_str() : "";
+}
+
+extern "C" int aqh_n_savers(aqh_sim* sim) { return (sim && sim->C) ? (int)sim->C->savers().size() : 0; }
+extern "C" const char* aqh_saver_file(aqh_sim* sim, int i)
+{
+    if (!sim || !sim->C || i < 0 || (size_t)i >= sim->C->savers().size())
+        return "";
+    return sim->C->savers()[i]->file().c_str();
 }
 
 extern "C" int aqh_sync(aqh_sim* sim)

@@ -114,8 +114,10 @@ class State {
     void load(const std::string& input_file, ProblemSetup& sim_data);
     /// Write the fully resolved problem (one flat XML, no includes): the format of
     /// the reference's AQUAgpusph.save.NNNNN.xml checkpoints (State.cpp:1517-1908)
+    /// full_load_paths: <Load file=...> keeps its directory (a checkpoint names the file a saver
+    /// just wrote); otherwise only the file name, as the examples' templates have it
     void write(const std::string& output_file, const ProblemSetup& sim_data,
-               bool relative_script_paths = true) const;
+               bool relative_script_paths = true, bool full_load_paths = false) const;
 
   private:
     void parse(const std::string& filepath, ProblemSetup& sim_data, const std::string& prefix);

@@ -481,7 +481,7 @@ static std::string scriptRelPath(const std::string& p)
 }
 
 void State::write(const std::string& output_file, const ProblemSetup& sd,
-                  bool relative_script_paths) const
+                  bool relative_script_paths, bool full_load_paths) const
 {
     using Xml::encodeEntities;
     std::ofstream f(output_file);
@@ -560,7 +560,8 @@ void State::write(const std::string& output_file, const ProblemSetup& sd,
             f << "        <Scalar name=\"" << kv.first << "\" value=\"" << encodeEntities(kv.second) << "\" />\n";
         if (!s->in_path.empty())
             f << "        <Load format=\"" << s->in_format << "\" file=\""
-              << encodeEntities(fs::path(s->in_path).filename().string()) << "\" fields=\""
+              << encodeEntities(full_load_paths ? s->in_path : fs::path(s->in_path).filename().string())
+              << "\" fields=\""
               << s->in_fields << "\" />\n";
         for (auto& o : s->outputs)
             f << "        <Save format=\"" << o[1] << "\" file=\"" << encodeEntities(o[0])

@@ -87,6 +87,20 @@ int aqc_memcpy_h2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int b
 int aqc_memcpy_d2h(aqc_ctx* ctx, void* dst, const void* src, size_t bytes, int blocking);
 int aqc_memcpy_d2d(aqc_ctx* ctx, void* dst, const void* src, size_t bytes);
 
+/* Asynchronous device->host copy on the context's SIDE stream: the reference's savers download on
+ * a command queue of their own (Particles.cpp:243-323: C->command_queue(cmd_queue_new), events joined
+ * by a marker) so that writing files overlaps the next time steps.  aqc_side_fork makes the side
+ * stream wait for everything queued so far on the main stream; aqc_memcpy_d2h_side queues one copy
+ * there (dst: pinned memory of aqc_host_alloc); aqc_side_record records `ev` (aqc_event_create)
+ * behind the copies: aqc_side_wait(ev) from any thread then waits for the data only.  The main
+ * stream never waits for the side stream: a source buffer must not be rewritten before `ev`. */
+int aqc_side_fork(aqc_ctx* ctx);
+int aqc_memcpy_d2h_side(aqc_ctx* ctx, void* dst, const void* src, size_t bytes);
+int aqc_side_record(aqc_ctx* ctx, void* ev);
+/* Wait for `ev` from ANY host thread (the savers' writer threads): selects the context's device for
+ * the calling thread and blocks on the event alone -- no communicator polling, no context state. */
+int aqc_side_wait(aqc_ctx* ctx, void* ev);
+
 /* ---- Set tool (Set.cpp:197-226, Set.cl.in:32-47): fill n elements of
  * elem_bytes (4, 8, 16 or 64) with the value at *value ---------------------- */
 int aqc_fill(aqc_ctx* ctx, void* dptr, size_t n, size_t elem_bytes, const void* value);

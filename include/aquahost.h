@@ -49,8 +49,21 @@ unsigned aqh_tool_used_times(aqh_sim* sim, int i);
 
 /* CalcServer::update split in steps: run n passes over the pipeline */
 int aqh_step(aqh_sim* sim, int n);
-/* main.cpp:162-179: run until the end criteria; saves the <Save> sets at the end */
+/* main.cpp:162-181: run until the end criteria -- update until an output frame is due
+ * (TimeManager::mustPrintOutput), save it (aqh_save), ... -- then wait for the writers */
 int aqh_run(aqh_sim* sim);
+/* FileManager::save (FileManager.cpp:146-155, Particles.cpp:82-120, ASCII.cpp:240-333,
+ * State.cpp:195-226 + 1517-1908): every <Save> of every particles set goes to its next numbered file
+ * (un-sorted on the device, downloaded on a side stream, written by a thread: the call returns at
+ * once) and the state file AQUAgpusph.save.N.xml is rewritten: all variables with their current
+ * values, the tools, the timing options and a <Load> of the files just started -- loading it with
+ * aqh_load resumes the run.  aqh_wait_savers = FileManager::waitForSavers (blocks until the files
+ * are complete; a writer's error surfaces here). */
+int aqh_save(aqh_sim* sim);
+int aqh_wait_savers(aqh_sim* sim);
+const char* aqh_checkpoint_file(aqh_sim* sim); /* "" before the first aqh_save */
+int aqh_n_savers(aqh_sim* sim);
+const char* aqh_saver_file(aqh_sim* sim, int i); /* last file of saver i */
 int aqh_sync(aqh_sim* sim);
 uint64_t aqh_launch_count(aqh_sim* sim); /* CUDA kernels launched so far */
 unsigned aqh_fused_groups(aqh_sim* sim); /* sweep groups the planner fused (0 with AQUA_NO_FUSION) */
