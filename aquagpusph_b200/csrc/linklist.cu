@@ -109,25 +109,30 @@ __global__ void minmax_init_kernel(uint32_t* out)
 }
 
 // ---- iCell (LinkList.cl.in:54-85) -------------------------------------------
+struct Pos3 { float x, y, z; };
 template <int VS>
-__device__ __forceinline__ uint32_t icell_of(const float* __restrict__ r, size_t i, float rminx,
-                                             float rminy, float rminz, float idist, uint32_t nx,
-                                             uint32_t ny)
+__device__ __forceinline__ Pos3 load_pos(const float* __restrict__ r, size_t i)
 {
-    float x, y, z = 0.f;
+    Pos3 q;
     if constexpr (VS == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(r) + i);
-        x = t.x; y = t.y; z = t.z;
+        q.x = t.x; q.y = t.y; q.z = t.z;
     } else {
         const float2 t = __ldg(reinterpret_cast<const float2*>(r) + i);
-        x = t.x; y = t.y;
+        q.x = t.x; q.y = t.y; q.z = 0.f;
     }
+    return q;
+}
+template <int VS>
+__device__ __forceinline__ uint32_t icell_of(const Pos3 q, float rminx, float rminy, float rminz,
+                                             float idist, uint32_t nx, uint32_t ny)
+{
     // explicit _rn intrinsics: never contracted, IEEE like the reference
-    const uint32_t cx = (uint32_t)__fmul_rn(__fsub_rn(x, rminx), idist) + 3u;
-    const uint32_t cy = (uint32_t)__fmul_rn(__fsub_rn(y, rminy), idist) + 3u;
+    const uint32_t cx = (uint32_t)__fmul_rn(__fsub_rn(q.x, rminx), idist) + 3u;
+    const uint32_t cy = (uint32_t)__fmul_rn(__fsub_rn(q.y, rminy), idist) + 3u;
     uint32_t id = cx - 1u + (cy - 1u) * nx;
     if constexpr (VS == 4) {
-        const uint32_t cz = (uint32_t)__fmul_rn(__fsub_rn(z, rminz), idist) + 3u;
+        const uint32_t cz = (uint32_t)__fmul_rn(__fsub_rn(q.z, rminz), idist) + 3u;
         id += (cz - 1u) * nx * ny;
     }
     return id;
@@ -174,27 +179,47 @@ sort_prepare_kernel(uint32_t* __restrict__ keys, const float* __restrict__ r, ui
     const int l = threadIdx.x & 31;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    // whole warps iterate together (__match_any_sync needs every lane)
-    const size_t n_up = ((size_t)n + 31) & ~(size_t)31;
-    for (size_t i = first; i < n_up; i += stride) {
-        const bool valid = i < n;
-        uint32_t key = 0;
-        if (valid) {
-            if constexpr (VS == 0)
-                key = __ldg(keys + i);
-            else {
-                key = icell_of<VS>(r, i, rminx, rminy, rminz, idist, nx, ny);
-                keys[i] = key;
+    // a warp takes 4 x 32 consecutive particles per iteration: the four loads of a lane are in
+    // flight together, and whole warps iterate together (__match_any_sync needs every lane)
+    constexpr int U = 4;
+    const size_t nwarps = stride >> 5;
+    for (size_t base = (first >> 5) * (32 * U); base < n; base += nwarps * (32 * U)) {
+        uint32_t key[U];
+        bool valid[U];
+        if constexpr (VS == 0) {
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                const size_t i = base + k * 32 + l;
+                valid[k] = i < n;
+                key[k] = valid[k] ? __ldg(keys + i) : 0u;
             }
+        } else {
+            Pos3 q[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                const size_t i = base + k * 32 + l;
+                valid[k] = i < n;
+                if (valid[k])
+                    q[k] = load_pos<VS>(r, i);
+            }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                if (valid[k]) {
+                    key[k] = icell_of<VS>(q[k], rminx, rminy, rminz, idist, nx, ny);
+                    keys[base + k * 32 + l] = key[k];
+                }
         }
-        int off = 0;
-        for (int p = 0; p < plan.passes; p++) {
-            const uint32_t d = valid ? ((key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))
-                                     : 0xFFFFFFFFu;
-            const uint32_t m = __match_any_sync(0xffffffffu, d);
-            if (valid && l == (__ffs(m) - 1))
-                atomicAdd(&sh[off + d], __popc(m));
-            off += 1 << plan.bits[p];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            int off = 0;
+            for (int p = 0; p < plan.passes; p++) {
+                const uint32_t d = valid[k] ? ((key[k] >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))
+                                            : 0xFFFFFFFFu;
+                const uint32_t m = __match_any_sync(0xffffffffu, d);
+                if (valid[k] && l == (__ffs(m) - 1))
+                    atomicAdd(&sh[off + d], __popc(m));
+                off += 1 << plan.bits[p];
+            }
         }
     }
     for (size_t k = first; k < status_words; k += stride)
@@ -261,9 +286,11 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
 template <int RADIX>
 __device__ __forceinline__ uint32_t look_back(const uint32_t* __restrict__ status, int tile, int d)
 {
-    uint32_t excl = 0;
+    uint32_t excl = 0, polls = 0;
     int t = tile - 1;
     while (t >= 0) {
+        if (++polls > (1u << 24)) // watchdog: a lost status word must not hang the GPU
+            __trap();
         uint32_t s[LOOK_W];
 #pragma unroll
         for (int k = 0; k < LOOK_W; k++)
@@ -416,14 +443,32 @@ __global__ void __launch_bounds__(256)
 heads_kernel(const uint32_t* __restrict__ icell, uint32_t* __restrict__ ihoc, uint32_t N,
              uint32_t* __restrict__ ghist_reset)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ghist_reset && i < GH_WORDS)
-        ghist_reset[i] = 0u;
-    if (i >= N)
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ghist_reset && t < GH_WORDS)
+        ghist_reset[t] = 0u;
+    // four consecutive keys per thread (one 16-byte load); the key before them comes from the
+    // neighbour lane, lane 0 of a warp fetches it
+    const uint32_t i0 = t * 4u;
+    uint32_t c[4] = { 0u, 0u, 0u, 0u };
+    if (i0 + 3u < N) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(icell) + t);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+        for (uint32_t k = 0; k < 4u; k++)
+            if (i0 + k < N)
+                c[k] = __ldg(icell + i0 + k);
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, c[3], 1);
+    if ((threadIdx.x & 31) == 0 && i0 > 0 && i0 < N)
+        prev = __ldg(icell + i0 - 1u);
+    if (N < 2) // the reference launches linkList on N - 1 work-items: a single particle sets no head
         return;
-    const uint32_t c = __ldg(icell + i);
-    if (N >= 2 && (i == 0 || __ldg(icell + i - 1) != c)) // (the reference launches N - 1 work-items)
-        ihoc[c] = i;
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+        if (i0 + k < N && (i0 + k == 0 || prev != c[k]))
+            ihoc[c[k]] = i0 + k;
+        prev = c[k];
+    }
 }
 
 constexpr int MAX_FIELDS = 16;
@@ -762,8 +807,11 @@ extern "C" int aqc_linklist_build(aqc_ctx* ctx, const void* r, aqc_usize N, int 
     if (rc)
         return rc;
     // iHoc: the heads (every other cell holds N since the prepare kernel)
-    heads_kernel<<<aqc_blocks(N > GH_WORDS ? N : GH_WORDS, 256), 256, 0, ctx->stream>>>(
-        icell, *ihoc, N, ctx->sort_hist);
+    {
+        const size_t threads = ((size_t)N + 3) / 4;
+        heads_kernel<<<aqc_blocks(threads > GH_WORDS ? threads : GH_WORDS, 256), 256, 0, ctx->stream>>>(
+            icell, *ihoc, N, ctx->sort_hist);
+    }
     AQC_LAUNCH_CHECK(ctx);
     ctx->sort_ghist_clean = true;
     return AQC_OK;

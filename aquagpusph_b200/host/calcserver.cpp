@@ -1035,9 +1035,11 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
         // tests/ExternalTool links libaquagpusphlib.so; a plugin built against the reference's
         // OpenCL Tool cannot be loaded (there is no OpenCL here).
         void* handle = dlopen(t.get("path").c_str(), RTLD_LAZY);
-        if (!handle)
+        if (!handle) {
+            const char* why = dlerror(); // (a second call returns NULL: the message is consumed)
             throw std::runtime_error("Installable tool \"" + name + "\" failed loading \"" + t.get("path") +
-                                     "\" library: " + (dlerror() ? dlerror() : "?"));
+                                     "\" library: " + (why ? why : "?"));
+        }
         typedef Tool* (*maker_t)(const std::string, bool);
         maker_t maker = (maker_t)dlsym(handle, "create_object");
         if (!maker)

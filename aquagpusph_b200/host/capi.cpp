@@ -24,10 +24,10 @@ static thread_local std::string g_err;
 #include <unistd.h>
 static void aqh_fatal_signal(int sig)
 {
-    void* frames[64];
-    const int n = backtrace(frames, 64);
     const char msg[] = "libaquahost: fatal signal, native backtrace:\n";
     if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    void* frames[96];
+    const int n = backtrace(frames, 96);
     backtrace_symbols_fd(frames, n, 2);
     signal(sig, SIG_DFL);
     raise(sig);
@@ -37,11 +37,26 @@ struct SegvBacktrace {
     SegvBacktrace()
     {
         const char* e = getenv("AQUA_SEGV_BACKTRACE");
-        if (e && atoi(e) != 0) {
-            signal(SIGSEGV, aqh_fatal_signal);
-            signal(SIGBUS, aqh_fatal_signal);
-            signal(SIGABRT, aqh_fatal_signal);
-        }
+        if (!e || atoi(e) == 0)
+            return;
+        // an alternate stack (a stack overflow leaves no room for a handler on the faulting one) and
+        // one backtrace() up front (its first call loads libgcc, which a signal handler must not do)
+        static char altstack[1 << 16];
+        stack_t ss;
+        ss.ss_sp = altstack;
+        ss.ss_size = sizeof(altstack);
+        ss.ss_flags = 0;
+        sigaltstack(&ss, nullptr);
+        void* warm[4];
+        backtrace(warm, 4);
+        struct sigaction sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sa_handler = aqh_fatal_signal;
+        sa.sa_flags = SA_ONSTACK | SA_NODEFER;
+        sigemptyset(&sa.sa_mask);
+        sigaction(SIGSEGV, &sa, nullptr);
+        sigaction(SIGBUS, &sa, nullptr);
+        sigaction(SIGABRT, &sa, nullptr);
     }
 } g_segv_backtrace;
 } // namespace
