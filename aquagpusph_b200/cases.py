@@ -500,11 +500,14 @@ def lattice_slab(n_side, hfac, rank, size, buffer_frac=0.1, **kw):
     return out
 
 
-def lattice_slab_local(n_xy, nz_local, hfac, rank, size, buffer_frac=0.05, seed=1234, cs=40.0):
+def lattice_slab_local(n_xy, nz_local, hfac, rank, size, buffer_frac=0.02, seed=1234, cs=40.0):
     """Weak-scaled config 5 (8e6 particles per device): this rank's n_xy x n_xy x nz_local block of a
     lattice that is size * nz_local cells tall, generated locally (nothing of the other ranks'
     blocks is ever held: 6.4e7 particles on 8 devices), velocities from a generator seeded per rank.
-    domain z = [0, size * nz_local] puts the planes of Slabs.xml exactly between the blocks."""
+    domain z = [0, size * nz_local] puts the planes of Slabs.xml exactly between the blocks.
+    buffer_frac: rows kept free for arrivals (basic/setBuffer.xml); 2 % keeps the 200^3 block below
+    2^23 rows, so that n_radix -- a power of two, the length of every mpi_* array and of the halo
+    link-list -- is 8.4 M instead of 16.8 M (with 5 % every O(n_radix) tool of the halo path cost twice as much)."""
     rng = np.random.default_rng(seed + 7919 * rank)
     ax = [np.arange(n_xy, dtype=np.float32), np.arange(n_xy, dtype=np.float32),
           np.arange(nz_local, dtype=np.float32) + np.float32(rank * nz_local)]

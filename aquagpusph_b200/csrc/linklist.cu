@@ -150,7 +150,6 @@ constexpr int MAX_BITS = 11;
 constexpr int MAX_RADIX = 1 << MAX_BITS;
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 1u << 31, ST_VAL = ST_AGG - 1u;
 constexpr int GH_WORDS = MAX_PASSES * MAX_RADIX + 32; // ghist + tickets (padded)
-constexpr int LOOK_W = 8;                             // predecessors polled per look-back round
 
 struct SortPlan {
     int passes;
@@ -209,16 +208,25 @@ sort_prepare_kernel(uint32_t* __restrict__ keys, const float* __restrict__ r, ui
                     keys[base + k * 32 + l] = key[k];
                 }
         }
+        // (passes unrolled to the maximum: plan.* is then read at constant offsets of the parameter
+        // space instead of through a local copy)
 #pragma unroll
-        for (int k = 0; k < U; k++) {
-            int off = 0;
-            for (int p = 0; p < plan.passes; p++) {
-                const uint32_t d = valid[k] ? ((key[k] >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))
-                                            : 0xFFFFFFFFu;
-                const uint32_t m = __match_any_sync(0xffffffffu, d);
-                if (valid[k] && l == (__ffs(m) - 1))
-                    atomicAdd(&sh[off + d], __popc(m));
-                off += 1 << plan.bits[p];
+        for (int p = 0; p < MAX_PASSES; p++) {
+            if (p < plan.passes) {
+                int off = 0;
+#pragma unroll
+                for (int q = 0; q < MAX_PASSES; q++)
+                    if (q < p)
+                        off += 1 << plan.bits[q];
+                const uint32_t mask = (1u << plan.bits[p]) - 1u;
+                const int shift = plan.shift[p];
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    const uint32_t d = valid[k] ? ((key[k] >> shift) & mask) : 0xFFFFFFFFu;
+                    const uint32_t m = __match_any_sync(0xffffffffu, d);
+                    if (valid[k] && l == (__ffs(m) - 1))
+                        atomicAdd(&sh[off + d], __popc(m));
+                }
             }
         }
     }
@@ -282,7 +290,9 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
 
 // Sum of the digit-d counts of the tiles before `tile`: every status word carries its own flag, so
 // no fence is needed; LOOK_W predecessors are polled per round (their loads overlap), which bounds
-// the walk when a whole wave of tiles starts at once.
+// the walk when a whole wave of tiles starts at once.  (Walking the DPT digits of a thread together
+// was measured and dropped: more registers in the ranking loop, passes 10 % slower.)
+constexpr int LOOK_W = 8;
 template <int RADIX>
 __device__ __forceinline__ uint32_t look_back(const uint32_t* __restrict__ status, int tile, int d)
 {

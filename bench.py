@@ -362,7 +362,7 @@ def run_ours(a, rank, world, local_rank):
     # driver is a weak-scaling efficiency; rank 0 still times ONE slab of the same per-GPU size
     # through the very same tool list on its GPU, after the other ranks have left.
     same1 = None
-    if world > 1:
+    if world > 1 and not a.skip_same_pipeline:
         try:
             sim1, case1 = casegen.spheric2_slab(a.n, 0, 1, overrides=ov, device=local_rank,
                                                 unique_id=None, delta_sph=not a.mpi_example)
@@ -386,9 +386,14 @@ def run_ours(a, rank, world, local_rank):
             same1["weak_scaling_efficiency"] = value / (world * same1["value"])
         except Exception as e:   # never lose the line over the extra measurement
             same1 = {"error": str(e)[:200]}
-    # ---- CPU baseline (oracle port), bounded sample
+    # ---- CPU baseline (oracle port), bounded sample: on rank 0 of the N = 1 run only
     threads = os.cpu_count() or 1
-    cv, cN, cms = cpu_port(a.cpu_n, a.cpu_steps, 1, threads, a.maxiter)
+    cpu_baseline = None
+    if world == 1:
+        cv, cN, cms = cpu_port(a.cpu_n, a.cpu_steps, 1, threads, a.maxiter)
+        cpu_baseline = {"value": cv, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                        "sample": "same pipeline at n_fluid=%d (N=%d), %d steps after 1 warm-up, "
+                                  "%.0f ms/step" % (a.cpu_n, cN, a.cpu_steps, cms)}
     line = {
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
@@ -416,9 +421,7 @@ def run_ours(a, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roof,
-        "cpu_baseline": {"value": cv, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                         "sample": "same pipeline at n_fluid=%d (N=%d), %d steps after 1 warm-up, "
-                                   "%.0f ms/step" % (a.cpu_n, cN, a.cpu_steps, cms)},
+        "cpu_baseline": cpu_baseline,   # (timed by the N = 1 line)
     }
     print(json.dumps(line), flush=True)
     _ = dt_now
@@ -493,6 +496,8 @@ def main():
     ap.add_argument("--mpi-example", action="store_true",
                     help="N > 1: the reference's MPI example pipeline (no delta-SPH / MLS) instead of the "
                          "single-GPU pipeline's physics on slabs")
+    ap.add_argument("--skip-same-pipeline", action="store_true",
+                    help="N > 1: do not time the one-GPU run of the same slab pipeline afterwards")
     ap.add_argument("--maxiter", type=int, default=0, help="pin iter_midpoint_max (0: case default 30)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

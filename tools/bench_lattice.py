@@ -64,7 +64,7 @@ if rank == 0:
                       "particle_steps_per_s": round(n_particles / ms * 1e3),
                       "launches_per_step_rank0": (sim.launch_count() - l0) // steps, "scaling": "weak"}))
     if os.environ.get("AQUA_PROFILE_SYNC"):
-        for name, k, t in sorted(sim.tool_times(), key=lambda x: -x[2])[:8]:
+        for name, k, t in sorted(sim.tool_times(), key=lambda x: -x[2])[:40]:
             print("  %-40s x%-4d %.3f ms/step" % (name, k, t / (steps + 3)))
 if dist is not None:
     dist.barrier()
