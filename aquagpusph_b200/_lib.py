@@ -27,7 +27,7 @@ SYMBOLS = [
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
-    "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_fp32_peak",
+    "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_pairs_cache_stats_remote", "aqc_fp32_peak",
     "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
 ]
 
@@ -78,6 +78,7 @@ def lib():
     L.aqc_pairs_cache_invalidate.argtypes = [C.c_void_p]
     L.aqc_pairs_cache_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64)]
+    L.aqc_pairs_cache_stats_remote.argtypes = L.aqc_pairs_cache_stats.argtypes
     L.aqc_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.aqc_free.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -300,9 +301,10 @@ class Context:
     def pairs_cache_invalidate(self):
         self._chk(lib().aqc_pairs_cache_invalidate(self.h))
 
-    def pairs_cache_stats(self):
+    def pairs_cache_stats(self, remote=False):
         b, h, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
-        self._chk(lib().aqc_pairs_cache_stats(self.h, C.byref(b), C.byref(h), C.byref(n)))
+        fn = lib().aqc_pairs_cache_stats_remote if remote else lib().aqc_pairs_cache_stats
+        self._chk(fn(self.h, C.byref(b), C.byref(h), C.byref(n)))
         return dict(builds=b.value, hits=h.value, bytes=n.value)
 
     def sm_count(self):

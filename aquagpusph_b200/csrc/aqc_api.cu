@@ -73,12 +73,14 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFree(ctx->minmax_dev);
     cudaFree(ctx->cell_cls);
     cudaFree(ctx->pack_rows);
-    cudaFree(ctx->pc.masks);
-    cudaFree(ctx->pc.chunks);
-    cudaFree(ctx->pc.cnt);
-    cudaFree(ctx->pc.pass_tab);
-    cudaFree(ctx->pc.ctl);
-    cudaFreeHost(ctx->pc.ctl_host);
+    for (aqc_pair_cache* c : { &ctx->pc, &ctx->pcr }) {
+        cudaFree(c->masks);
+        cudaFree(c->chunks);
+        cudaFree(c->cnt);
+        cudaFree(c->pass_tab);
+        cudaFree(c->ctl);
+        cudaFreeHost(c->ctl_host);
+    }
     cudaFreeHost(ctx->minmax_host);
     cudaFree(ctx->red_dev);
     cudaFreeHost(ctx->red_host);
@@ -516,9 +518,11 @@ extern "C" int aqc_pairs_cache_enable(aqc_ctx* ctx, int on)
 {
     if (!ctx)
         return AQC_ERR_ARG;
-    ctx->pc.enabled = on != 0;
-    ctx->pc.valid = false;
-    ctx->pc.served = ctx->pc.poor_streak = ctx->pc.cooldown = 0; // (and the pay-off history)
+    for (aqc_pair_cache* c : { &ctx->pc, &ctx->pcr }) {
+        c->enabled = on != 0;
+        c->valid = false;
+        c->served = c->poor_streak = c->cooldown = 0; // (and the pay-off history)
+    }
     return AQC_OK;
 }
 
@@ -530,16 +534,22 @@ extern "C" int aqc_pairs_cache_invalidate(aqc_ctx* ctx)
     return AQC_OK;
 }
 
+static int pc_stats(const aqc_pair_cache& c, uint64_t* builds, uint64_t* hits, uint64_t* bytes)
+{
+    if (builds)
+        *builds = c.builds;
+    if (hits)
+        *hits = c.hits;
+    if (bytes)
+        *bytes = c.lists ? (uint64_t)c.chunks_bytes + (uint64_t)c.cap_rounds * 7 * 32
+                         : (uint64_t)c.cap_rounds * AQC_PC_ROUND_BYTES;
+    return AQC_OK;
+}
 extern "C" int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes)
 {
-    if (!ctx)
-        return AQC_ERR_ARG;
-    if (builds)
-        *builds = ctx->pc.builds;
-    if (hits)
-        *hits = ctx->pc.hits;
-    if (bytes)
-        *bytes = ctx->pc.lists ? (uint64_t)ctx->pc.chunks_bytes + (uint64_t)ctx->pc.cap_rounds * 7 * 32
-                               : (uint64_t)ctx->pc.cap_rounds * AQC_PC_ROUND_BYTES;
-    return AQC_OK;
+    return ctx ? pc_stats(ctx->pc, builds, hits, bytes) : AQC_ERR_ARG;
+}
+extern "C" int aqc_pairs_cache_stats_remote(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes)
+{
+    return ctx ? pc_stats(ctx->pcr, builds, hits, bytes) : AQC_ERR_ARG;
 }

@@ -23,6 +23,12 @@ struct aqc_pair_cache {
     bool valid = false;    // the masks belong to the key below
     bool unusable = false; // a CTA needed more passes than the pass table holds: sweeps filter
     const void *r = nullptr, *imove = nullptr, *icell = nullptr, *ihoc = nullptr; // key
+    // the cache of the REMOTE (halo) sweeps: i cells from the local list, j rows / cells / heads from
+    // the halo list (LINKLIST_REMOTE_PARAMS).  rj is part of the key but NOT of the write tracking:
+    // cfd/MPI.cl::sort rewrites the halo positions every sub-iteration with the values they had,
+    // and the halo list itself (icell, ihoc above) is only valid for the positions it was built from
+    bool remote = false;
+    const void *rj = nullptr, *icell_i = nullptr;
     uint32_t N = 0, nx = 0, ny = 0, nz = 0, nw = 0;
     int dims = 0;
     float cut2 = 0.f;
@@ -74,6 +80,7 @@ struct aqc_watch {
 
 struct aqc_ctx {
     aqc_pair_cache pc;
+    aqc_pair_cache pcr; // remote (halo) sweeps
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -170,17 +177,20 @@ static inline void aqc_pc_touch(aqc_ctx* ctx, const void* ptr, size_t bytes)
             for (auto& d : pl.deps)
                 if (a < d.first + d.second && d.first < b)
                     pl.valid = false;
-    if (!c.valid)
-        return;
     auto hit = [&](const void* base, size_t n) {
         const char* x = (const char*)base;
         return base && a < x + n && x < b;
     };
-    if (hit(c.r, (size_t)c.N * (c.dims == 3 ? 16 : 8)) || hit(c.imove, (size_t)c.N * 4) ||
-        hit(c.icell, (size_t)c.N * 4) || hit(c.ihoc, (size_t)c.nw * 4))
+    if (c.valid && (hit(c.r, (size_t)c.N * (c.dims == 3 ? 16 : 8)) || hit(c.imove, (size_t)c.N * 4) ||
+                    hit(c.icell, (size_t)c.N * 4) || hit(c.ihoc, (size_t)c.nw * 4)))
         c.valid = false;
+    aqc_pair_cache& q = ctx->pcr;
+    if (q.valid && (hit(q.r, (size_t)q.N * (q.dims == 3 ? 16 : 8)) || hit(q.imove, (size_t)q.N * 4) ||
+                    hit(q.icell_i, (size_t)q.N * 4) || hit(q.icell, (size_t)q.N * 4) ||
+                    hit(q.ihoc, (size_t)q.nw * 4)))
+        q.valid = false;
 }
-static inline void aqc_pc_invalidate(aqc_ctx* ctx) { ctx->pc.valid = false; }
+static inline void aqc_pc_invalidate(aqc_ctx* ctx) { ctx->pc.valid = ctx->pcr.valid = false; }
 // bytes of one element of an array argument, from its reference type string ("vec*", "float*", ...)
 static inline size_t aqc_type_bytes(const char* type, int dims)
 {

@@ -644,6 +644,12 @@ sweep3_kernel(const P p, const LLParams ll, const int K, const S3Cache pc)
     // the passes of a CTA are made of ALL its particles, whatever the kernel's i set: the
     // tiles of a pass are then the same for every kernel (the mask cache relies on it)
     const uint32_t c_i = valid ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    if constexpr (P::REMOTE) {
+        // remote (halo) list: a CTA none of whose particles has a halo particle in its 3^D cells has
+        // nothing to do -- nor has the builder of its lists (same flags, same decision)
+        if (ll.near && !__syncthreads_or(valid && c_i < ll.nw && ll.near[c_i < ll.nw ? c_i : 0]))
+            return;
+    }
     typename P::IState st;
     st.x = st.y = st.z = 0.f;
     if (active)
@@ -1309,6 +1315,10 @@ sweep4_kernel(const P p, const LLParams ll, const S3Cache pc)
     const bool valid = !producer && i < ll.N;
     const bool active = valid && p.i_active(p.imove[valid ? i : 0]);
     const uint32_t c_i = valid ? __ldg(ll.icell_i + i) : 0xFFFFFFFFu;
+    if constexpr (P::REMOTE) {
+        if (ll.near && !__syncthreads_or(valid && c_i < ll.nw && ll.near[c_i < ll.nw ? c_i : 0]))
+            return; // (the builder left this CTA at the same place)
+    }
     typename P::IState st;
     st.x = st.y = st.z = 0.f;
     if (active)
@@ -1586,8 +1596,9 @@ bool aqc_sweep_engine_forced(); // chosen explicitly (environment or aqc_sweep_e
 int aqc_sweep_ring(int nj4); // ring rounds K of the v3 engine (AQC_SWEEP_RING)
 int aqc_sweep_ring2();       // ring rounds of the mask-reading sweeps (AQC_SWEEP_RING2)
 int aqc_remote_engine();     // 2 or 3 (AQC_REMOTE_ENGINE)
-int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2, const LLParams& ll,
-                   uint32_t icls, uint32_t jcls, int K, S3Cache* out); // sweeps.cu
+bool aqc_remote_lists();     // the remote sweeps read neighbour lists of their own (AQC_REMOTE_LISTS)
+int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, const void* rj, int dims, float cut2,
+                   const LLParams& ll, uint32_t icls, uint32_t jcls, int K, S3Cache* out); // sweeps.cu
 
 template <class P>
 static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
@@ -1618,7 +1629,9 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
         // remote (halo) list: flag the cells that have a halo particle in their 3^D neighbourhood
         // (AQC_REMOTE_NEAR=0: every warp walks its 27 cells, as before)
         static const bool use_near = !(getenv("AQC_REMOTE_NEAR") && atoi(getenv("AQC_REMOTE_NEAR")) == 0);
-        if (use_near && aqc_remote_engine() != 3) {
+        const bool rlists = P::SPHERE && aqc_remote_lists() && ctx->pcr.enabled && aqc_sweep_engine() == 3 &&
+                            !((p.icls() | p.jcls()) & ~31u);
+        if ((use_near && aqc_remote_engine() != 3) || rlists) {
             const size_t need = ((size_t)ll.nw + 3) & ~(size_t)3;
             if (need > ctx->cell_cls_cap) {
                 if (ctx->cell_cls) {
@@ -1639,6 +1652,39 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
             ll.near = ctx->cell_cls;
         }
     }
+    if constexpr (P::REMOTE && P::SPHERE) {
+        // remote sweeps on neighbour lists of their own (the second pair cache, ctx->pcr): built by
+        // the first remote sweep after the halo list (or the local geometry) changed, read by every
+        // one that follows -- inside a midpoint loop the halo positions are fixed, so the seven
+        // remote sweeps of a delta-SPH step share one build
+        if (ll.near && aqc_remote_lists() && ctx->pcr.enabled && aqc_sweep_engine() == 3 &&
+            !((p.icls() | p.jcls()) & ~31u)) {
+            S3Cache pc;
+            const int cached = aqc_pc_prepare(ctx, p.imove, p.r, p.mpi_r, P::DIMS, p.cut2, ll, p.icls(), 0u,
+                                              aqc_sweep_ring(1), &pc);
+            if (cached < 0)
+                return cached;
+            if (cached == 2) {
+                const size_t need = (size_t)ll.N * P::NJ4 * sizeof(float4);
+                if (need > ctx->pack_cap) {
+                    if (ctx->pack_rows) {
+                        AQC_SYNC(ctx);
+                        AQC_CUDA(ctx, cudaFree(ctx->pack_rows));
+                    }
+                    ctx->pack_rows = nullptr;
+                    ctx->pack_cap = 0;
+                    AQC_CUDA(ctx, cudaMalloc(&ctx->pack_rows, need + need / 8));
+                    ctx->pack_cap = need + need / 8;
+                }
+                s3_pack_kernel<P><<<aqc_blocks(ll.N, 256), 256, 0, ctx->stream>>>(p, ll.N, (float4*)ctx->pack_rows);
+                AQC_LAUNCH_CHECK(ctx);
+                pc.rows = (const float4*)ctx->pack_rows;
+                sweep4_kernel<P><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, 0, ctx->stream>>>(p, ll, pc);
+                AQC_LAUNCH_CHECK(ctx);
+                return AQC_OK;
+            }
+        }
+    }
     if constexpr (P::SPHERE) {
         // 2-D sweeps have ~20x less work per particle: below ~1 M particles the CTA-wide
         // set-up of v3 does not pay (measured: 2-D dam break, 0.38 M particles, 1.44 vs 1.20 ms
@@ -1650,7 +1696,7 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
             S3Cache pc;
             int cached = 0;
             if constexpr (P::CACHE) {
-                cached = aqc_pc_prepare(ctx, p.imove, p.r, P::DIMS, p.cut2, ll, p.icls(), p.jcls(), K, &pc);
+                cached = aqc_pc_prepare(ctx, p.imove, p.r, nullptr, P::DIMS, p.cut2, ll, p.icls(), p.jcls(), K, &pc);
                 if (cached < 0)
                     return cached;
             }
@@ -1686,11 +1732,11 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
                 if (cached) {
                     K = aqc_sweep_ring2();
                     const size_t smem = smem_of(K, S3_RTILES, false);
-                    static size_t configured2 = 0; // per instantiation
-                    if (smem > configured2) {
+                    static size_t configured2[64] = { 0 }; // per instantiation AND device (the attribute is per device)
+                    if (smem > configured2[ctx->device & 63]) {
                         AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 2, S3_RTILES>,
                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        configured2 = smem;
+                        configured2[ctx->device & 63] = smem;
                     }
                     sweep3_kernel<P, 2, S3_RTILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(
                         p, ll, K, pc);
@@ -1699,11 +1745,11 @@ static int launch_sweep(aqc_ctx* ctx, const P& p, const LLParams& ll_in)
                 }
             }
             const size_t smem = smem_of(K, S3_TILES, true);
-            static size_t configured = 0; // per instantiation
-            if (smem > configured) {
+            static size_t configured[64] = { 0 }; // per instantiation AND device (the attribute is per device)
+            if (smem > configured[ctx->device & 63]) {
                 AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<P, 0, S3_TILES>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
+                configured[ctx->device & 63] = smem;
             }
             sweep3_kernel<P, 0, S3_TILES><<<aqc_blocks(ll.N, S3_PARTICLES), S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
         } else {

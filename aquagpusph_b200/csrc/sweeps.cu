@@ -83,6 +83,16 @@ int aqc_remote_engine() // engine of the remote (halo) sweeps: 2 (per warp, defa
     return v;
 }
 
+bool aqc_remote_lists() // the remote (halo) sweeps read neighbour lists of their own (AQC_REMOTE_LISTS, default on)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AQC_REMOTE_LISTS");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int aqc_sweep_ring2()
 {
     static const int forced = [] {
@@ -745,6 +755,8 @@ struct PMpiGamma : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
+    uint32_t icls() const { return 31u; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 1;
     const void *r, *mpi_r;
     const float *mpi_rho, *mpi_m;
@@ -781,6 +793,8 @@ struct PMpiInteractions : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true; // the remote list is a thin halo: most CTAs find nothing
+    uint32_t icls() const { return 1u; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;
     const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
@@ -843,6 +857,8 @@ struct PMpiFused : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true;
+    uint32_t icls() const { return 31u; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *u, *mpi_r, *mpi_u;
     const float *rho, *p, *mpi_rho, *mpi_p, *mpi_m;
@@ -939,6 +955,8 @@ struct PMpiMLS : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true;
+    uint32_t icls() const { return (mls_imove == 1u) ? 1u : 0xFFu; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 1;
     const void *r, *mpi_r;
     const float *mpi_rho, *mpi_m;
@@ -998,6 +1016,8 @@ struct PMpiDelta : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true;
+    uint32_t icls() const { return 1u; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *mpi_r;
     const float *p, *mpi_rho, *mpi_m, *mpi_p;
@@ -1045,6 +1065,8 @@ struct PMpiLappCorr : PBase {
     static constexpr bool SPHERE = true;
     static constexpr bool REMOTE = true;
     static constexpr bool SPARSE_I = true;
+    uint32_t icls() const { return 1u; } // (the remote neighbour lists, ctx->pcr)
+    uint32_t jcls() const { return 0u; }
     static constexpr int DIMS = D, NJ4 = 2;
     const void *r, *mpi_r, *lap_p_corr, *mpi_lap_p_corr;
     const float *mpi_rho, *mpi_m;
@@ -1639,17 +1661,54 @@ struct PMaskBuild : PBase {
     __device__ void store_i(const IState&, uint32_t) const {}
 };
 
+// ... of the remote (halo) sweeps: i particles of the classes icl from the local arrays, every row of
+// the halo list as j (cfd/MPI.cl:328-485 let every halo particle count)
 template <int D>
-int pc_build(aqc_ctx* ctx, const LLParams& ll, int K)
+struct PMaskBuildR : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool REMOTE = true;
+    static constexpr int DIMS = D, NJ4 = 1;
+    const void *r, *rj;
+    uint32_t icl;
+    struct IState { float x, y, z; };
+    __device__ bool i_active(int mv) const { return (aqc_cls_bit(mv) & icl) != 0; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        s.x = a.x; s.y = a.y; s.z = a.z;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(rj, j);
+        o[0] = make_float4(a.x, a.y, a.z, 0.f);
+    }
+    __device__ bool test(const IState&, const float4&) const { return false; }
+    __device__ void body(IState&, const float4*, int) const {}
+    __device__ void store_i(const IState&, uint32_t) const {}
+};
+
+template <class PB>
+int pc_build_launch(aqc_ctx* ctx, aqc_pair_cache& c, const PB& p, const LLParams& ll, int K, const S3Cache& pc)
 {
-    aqc_pair_cache& c = ctx->pc;
-    PMaskBuild<D> p;
-    p.imove = (const int*)c.imove;
-    p.invH = 0.f;
-    p.cut2 = c.cut2;
-    p.r = c.r;
-    p.icl = c.icls_want;
-    p.jcl = c.jcls_want;
+    const size_t NS = (size_t)K * S3_TILES;
+    const size_t smem = (NS * 32 + NS * 32) * sizeof(float4) + S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
+    const unsigned grid = aqc_blocks(ll.N, S3_PARTICLES);
+    if (c.lists) {
+        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PB, 3, S3_TILES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sweep3_kernel<PB, 3, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    } else {
+        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PB, 1, S3_TILES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sweep3_kernel<PB, 1, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    }
+    AQC_LAUNCH_CHECK(ctx);
+    return AQC_OK;
+}
+
+template <int D>
+int pc_build(aqc_ctx* ctx, aqc_pair_cache& c, const LLParams& ll, int K)
+{
     S3Cache pc;
     pc.masks = c.masks;
     pc.pass_tab = c.pass_tab;
@@ -1658,31 +1717,38 @@ int pc_build(aqc_ctx* ctx, const LLParams& ll, int K)
     pc.chunks = (uint2*)c.chunks;
     pc.cnt = c.cnt;
     pc.capc = c.capc;
-    const size_t NS = (size_t)K * S3_TILES;
-    const size_t smem = (NS * 32 + NS * 32) * sizeof(float4) + S3_CWARPS * (NS - S3_TILES) * 32 * (sizeof(uint32_t) + 1);
-    const unsigned grid = aqc_blocks(ll.N, S3_PARTICLES);
-    if (c.lists) {
-        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 3, S3_TILES>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sweep3_kernel<PMaskBuild<D>, 3, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
-    } else {
-        AQC_CUDA(ctx, cudaFuncSetAttribute(sweep3_kernel<PMaskBuild<D>, 1, S3_TILES>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sweep3_kernel<PMaskBuild<D>, 1, S3_TILES><<<grid, S3_THREADS, smem, ctx->stream>>>(p, ll, K, pc);
+    if (c.remote) {
+        PMaskBuildR<D> p;
+        p.imove = (const int*)c.imove;
+        p.invH = 0.f;
+        p.cut2 = c.cut2;
+        p.r = c.r;
+        p.rj = c.rj;
+        p.icl = c.icls_want;
+        return pc_build_launch(ctx, c, p, ll, K, pc);
     }
-    AQC_LAUNCH_CHECK(ctx);
-    return AQC_OK;
+    PMaskBuild<D> p;
+    p.imove = (const int*)c.imove;
+    p.invH = 0.f;
+    p.cut2 = c.cut2;
+    p.r = c.r;
+    p.icl = c.icls_want;
+    p.jcl = c.jcls_want;
+    return pc_build_launch(ctx, c, p, ll, K, pc);
 }
 
 } // namespace
 
 // 1: *out describes hit masks that are valid for this sweep, 2: neighbour lists; 0: the sweep has
 // to filter; < 0: error
-int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, float cut2,
+int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, const void* rj, int dims, float cut2,
                    const LLParams& ll, uint32_t icls, uint32_t jcls, int K, S3Cache* out)
 {
-    aqc_pair_cache& c = ctx->pc;
-    if (!c.enabled || ((icls | jcls) & ~31u) || ll.icell_i != ll.icell || ll.cls)
+    // rj != nullptr: the cache of the remote (halo) sweeps (i cells from ll.icell_i, j rows at rj)
+    const bool remote = rj != nullptr;
+    aqc_pair_cache& c = remote ? ctx->pcr : ctx->pc;
+    c.remote = remote;
+    if (!c.enabled || ((icls | jcls) & ~31u) || (!remote && ll.icell_i != ll.icell) || ll.cls)
         return 0;
     {
         static int lists_env = -1;
@@ -1697,7 +1763,8 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
     // differs from the one the lists were made for cannot use them (the masks can, by re-testing)
     if (c.lists && c.jcls_want && jcls != c.jcls_want)
         return 0;
-    const bool same = c.valid && c.r == r && c.imove == imove && c.icell == ll.icell && c.ihoc == ll.ihoc &&
+    const bool same = c.valid && c.r == r && c.rj == rj && c.icell_i == ll.icell_i && c.imove == imove &&
+                      c.icell == ll.icell && c.ihoc == ll.ihoc &&
                       c.N == ll.N && c.nx == ll.nx && c.ny == ll.ny && c.nz == ll.nz && c.nw == ll.nw &&
                       c.dims == dims && c.cut2 == cut2 && !(icls & ~c.icls) && !(jcls & ~c.jcls);
     if (!same) {
@@ -1720,6 +1787,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
         c.icls_want |= icls;
         c.jcls_want |= jcls;
         c.r = r; c.imove = imove; c.icell = ll.icell; c.ihoc = ll.ihoc;
+        c.rj = rj; c.icell_i = ll.icell_i;
         c.N = ll.N; c.nx = ll.nx; c.ny = ll.ny; c.nz = ll.nz; c.nw = ll.nw;
         c.dims = dims; c.cut2 = cut2;
         const size_t nblk = aqc_blocks(ll.N, S3_PARTICLES);
@@ -1744,7 +1812,8 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
             return 0;
         };
         size_t want = c.cap_rounds ? c.cap_rounds : nblk * (dims == 3 ? 40 : 12);
-        uint32_t want_capc = c.capc ? c.capc : (dims == 3 ? 272u : 72u); // (even: stored in pairs)
+        // (a halo list holds at most the far half of a neighbourhood: half the chunks to begin with)
+        uint32_t want_capc = c.capc ? c.capc : (dims == 3 ? (remote ? 136u : 272u) : (remote ? 36u : 72u)); // (even)
         for (int attempt = 0;; attempt++) {
             if (want > c.cap_rounds) {
                 if (*rounds_buf) {
@@ -1783,7 +1852,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, int dims, floa
             }
             AQC_CUDA(ctx, cudaMemsetAsync(c.ctl, 0, 4 * sizeof(unsigned long long), ctx->stream));
             AQC_CUDA(ctx, cudaMemsetAsync(c.pass_tab, 0xFF, nblk * S3_MAXPASS * sizeof(uint32_t), ctx->stream));
-            const int rc = (dims == 3) ? pc_build<3>(ctx, ll, K) : pc_build<2>(ctx, ll, K);
+            const int rc = (dims == 3) ? pc_build<3>(ctx, c, ll, K) : pc_build<2>(ctx, c, ll, K);
             if (rc)
                 return rc;
             AQC_CUDA(ctx, cudaMemcpyAsync(c.ctl_host, c.ctl, 4 * sizeof(unsigned long long),

@@ -210,6 +210,10 @@ int aqc_pairs_cache_enable(aqc_ctx* ctx, int on);
 int aqc_pairs_cache_invalidate(aqc_ctx* ctx);
 /* builds / sweeps served so far, bytes of device memory held (any pointer may be NULL) */
 int aqc_pairs_cache_stats(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes);
+/* ... and of the second cache, the one of the REMOTE (halo) sweeps of cfd/MPI.cl / aqua/MPIdeltaSPH.cl: their
+ * neighbour lists are built once per halo link-list and read by every remote sweep until the local
+ * geometry or the halo list changes (AQC_REMOTE_LISTS=0: the remote sweeps filter every time) */
+int aqc_pairs_cache_stats_remote(const aqc_ctx* ctx, uint64_t* builds, uint64_t* hits, uint64_t* bytes);
 
 /* ---- write watches: a set of device ranges that turns dirty as soon as one of them is written
  * through this library (the mechanism behind the pair cache and the mpi-sync plans, for callers).

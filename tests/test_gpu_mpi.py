@@ -176,6 +176,37 @@ def test_mpi_kernels_match_reference_scripts(oracle, dims):
         H["mpi_lap_p_corr"][H["mpi_id_sorted"][:N]] = H["mpi_lap_p_corr_in"][:N]
     ours("copy_g", copy_g, ("mpi_lap_p_corr",), exact=True)
     ours("sort_g", sort_g, ("mpi_lap_p_corr",), exact=True)
+    # ---- the remote sweeps on neighbour lists of their own (the second pair cache, what the host
+    # turns on): one build serves every remote sweep while the halo list and the local geometry
+    # stand; same pairs as the filtering sweeps above, summed in another order
+    outs = ("shepard", "grad_p", "lap_u", "div_u", "lap_p", "lap_p_corr", "mls")
+    start = {k: dev[k].get() for k in outs}
+
+    def remote_sweeps():
+        ctx.launch("aqua/MPIdeltaSPH.cl", "mls", dev, n=N)
+        ctx.launch_fused([("cfd/MPI.cl", "interactions"), ("cfd/MPI.cl", "gamma"),
+                          ("aqua/MPIdeltaSPH.cl", "full_lapp")], dev)
+        ctx.launch("aqua/MPIdeltaSPH.cl", "lapp_corr", dev, n=N)
+        ctx.launch("cfd/MPI.cl", "interactions", dev, n=N)
+        return {k: dev[k].get().astype(np.float64) for k in outs}
+    filtered = remote_sweeps()
+    for k, v in start.items():
+        dev[k].set(v)
+    ctx.pairs_cache(True)
+    listed = remote_sweeps()
+    st = ctx.pairs_cache_stats(remote=True)
+    if os.environ.get("AQC_REMOTE_LISTS", "1") != "0" and os.environ.get("AQC_SWEEP_ENGINE", "3") == "3":
+        assert st["builds"] in (1, 2) and st["hits"] >= 4, st   # (mls asks for the fluid only, the fused sweep widens it)
+    for k in outs:
+        assert np.abs(filtered[k] - start[k]).max() > 0, k
+        assert np.abs(filtered[k] - listed[k]).max() <= 2e-6 * np.abs(filtered[k]).max(), ("remote lists", k)
+    # a new halo list drops them (the link-list build reports the arrays it writes)
+    ctx.linklist(dev["mpi_r_in"], 2.0, case["h"], icell, ihoc, perm, invp, rmin=ll["rmin"], rmax=ll["rmax"],
+                 recompute=False)
+    ctx.launch("cfd/MPI.cl", "interactions", dev, n=N)
+    st2 = ctx.pairs_cache_stats(remote=True)
+    if st["builds"]:
+        assert st2["builds"] == st["builds"] + 1, (st, st2)
     ctx.close()
 
 
@@ -596,8 +627,10 @@ def test_dead_peer_ends_the_job():
         if r in got:     # the call failed in line
             msg, dt, again = got[r]
             assert msg != "no error" and dt < 40.0, (r, msg, dt)
-            assert "abort" in msg or "peer" in msg or "NCCL" in msg, msg
-            assert "aborted" in again, again
+            # (a vanished rank can also surface as garbage in the gathered counts: the symmetry
+            # check of the process lists then fails the call before any wait expires)
+            assert "abort" in msg or "peer" in msg or "NCCL" in msg or "symmetric" in msg, msg
+            assert "aborted" in again or "symmetric" in again or "peer" in again, again
         else:            # the watchdog ended the process
             assert procs[r].exitcode == 70, (r, procs[r].exitcode)
     assert took < 90.0, took
