@@ -2492,6 +2492,10 @@ extern "C" int aqc_kernel_write_rows(int kernel_id)
     // cfd/Sensors.cl:57-130 and SensorsRenormalization.cl:42-67 return unless imove == 0
     if (!strcmp(nm, "cfd/Sensors.cl::entry") || !strcmp(nm, "cfd/SensorsRenormalization.cl::entry"))
         return AQC_ROWS_SENSOR;
+    // cfd/Boundary/BIe/Interactions.cl:124-137 returns unless imove == -3: p of the boundary elements only
+    // (the tuned-liquid-damper presets place it between cfd interactions and the delta-SPH sweeps)
+    if (!strcmp(nm, "cfd/Boundary/BIe/Interactions.cl::p_boundary"))
+        return AQC_ROWS_BOUNDARY;
     return AQC_ROWS_ANY;
 }
 

@@ -1123,7 +1123,7 @@ void CalcServer::planFusion()
             continue;
         int best_fid = -1;
         size_t best_n = 0;
-        for (size_t j = i + 1; j < _tools.size() && j < i + 16; j++) {
+        for (size_t j = i + 1; j < _tools.size() && j < i + 32; j++) {
             Tool* t = _tools[j].get();
             if (t->scope_modifier() != 0)
                 break;

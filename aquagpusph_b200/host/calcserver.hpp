@@ -132,6 +132,14 @@ class Set : public Tool {
     Set(CalcServer* C, const std::string& name, const std::string& var, const std::string& value, bool once)
       : Tool(C, name, once), _var_name(var), _value(value) {}
     void setup() override;
+    /// writes its array, reads scalars only (Set.cpp:60-75)
+    bool dependencies(std::vector<InputOutput::Variable*>& in,
+                      std::vector<InputOutput::Variable*>& out) const override
+    {
+        (void)in;
+        out.push_back(_var);
+        return true;
+    }
   protected:
     void _execute() override;
   private:
