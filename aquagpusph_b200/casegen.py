@@ -41,6 +41,7 @@ def instantiate(template, case, set_sizes, overrides=None, keep_reports=False):
         "TEND": repr(float(case.get("t_end", 1.0))),
         "CLTYPE": "GPU", "CLDEVICE": "0", "CLPLATFORM": "0",
     }
+    rep.update(case.get("placeholders", {}))   # the case's own keys (Create.py `data` of that example)
     for k, v in rep.items():
         txt = txt.replace("{{%s}}" % k, v)
     # the MPI example's Fluids.xml leaves the size of set 0 to the particle file
@@ -455,6 +456,16 @@ def spheric3_lid_driven(nx=200, hfac=4.0, overrides=None, device=0, **kw):
     from . import cases
     c = cases.spheric3_lid_driven_2d(nx, hfac)
     sim = load("spheric3_liddriven_2d", c, (c["n_set0"], c["n_set1"]), overrides, device, **kw)
+    return sim, c
+
+
+def souto2012_standing_wave(ny=100, hfac=4.0, overrides=None, device=0, **kw):
+    """The standing wave of examples/2D/souto_etal_2012_standingwave through its unchanged 91-tool pipeline
+    (improved Euler, delta-SPH full, BI bottom, elastic bounce, TWO symmetry planes of cfd/symmetry.xml feeding
+    on buffer particles, kinetic-energy report)."""
+    from . import cases
+    c = cases.souto2012_standing_wave_2d(ny, hfac)
+    sim = load("souto2012_standingwave_2d", c, (c["N"],), overrides, device, **kw)
     return sim, c
 
 

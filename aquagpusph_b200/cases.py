@@ -7,6 +7,8 @@ a jittered fluid lattice (imove = 1) resting on boundary-integral elements
 sensors (imove = 0) and a few buffer particles (imove = -255) parked at
 domain_max, with a hydrostatic-ish density field and random velocities.
 """
+import math
+
 import numpy as np
 
 
@@ -408,6 +410,73 @@ def spheric3_lid_driven_2d(nx=200, hfac=4.0, Re=1000.0):
         r=np.concatenate([fluid, bnd]).astype(np.float32), imove=imove, iset=iset, normal=normal,
         tangent=np.zeros((N, 2), np.float32), rho=np.full(N, refd, np.float32), m=m, u=u,
         dudt=np.zeros((N, 2), np.float32), drhodt=np.zeros(N, np.float32),
+    )
+
+
+def souto2012_standing_wave_2d(ny=100, hfac=4.0, periods=8):
+    """The viscous standing wave of Souto-Iglesias et al. 2012, geometry and fields of
+    examples/2D/souto_etal_2012_standingwave/src/Create.py:40-238: a tank L x H = 2 x 1 of nx x ny =
+    2 ny x ny fluid particles (x inner, y outer) moving with the linear standing-wave velocity field,
+    hydrostatic density, a bottom of nx boundary-integral elements (imove = -3, m = dr, normal (0, -1)),
+    and n + nx buffer particles (imove = -255, m = 0) parked beyond domain_max for the two symmetry
+    planes x = 0 and x = L of templates/Symmetries.xml; one particles set."""
+    g, cs, courant, refd, alpha, delta = 1.0, 50.0, 0.1, 1.0, 0.0, 10.0
+    L = 2.0
+    H = 0.5 * L
+    k = 2.0 * math.pi / L
+    omega = math.sqrt(g * k * math.tanh(k * H))
+    eps, Re, sep = 0.1, 250.0, 2.0
+    nx = 2 * ny
+    dr = H / ny
+    h = hfac * dr
+    n = nx * ny
+    visc_dyn = max(alpha / 8.0 * refd * h * cs, refd * H * math.sqrt(g * H) / Re)
+    A = 0.5 * eps * H
+    dmin = (-0.2 * L - 6.0 * sep * h, -0.2 * (H + A) - 6.0 * sep * h)
+    dmax = (1.2 * L + 6.0 * sep * h, 1.2 * (H + A) + 6.0 * sep * h)
+    nb = nx
+    nbuf = n + nb
+    N = n + nb + nbuf
+    T = 2.0 * math.pi / omega
+    nu = H * math.sqrt(g * H) / Re
+    ekin0 = eps ** 2 * g * H ** 2 * L / 32 * 2
+    epot0 = 0.5 * g * H * (L * H * refd)
+    j = np.arange(n)
+    px = (j % nx) * dr + 0.5 * dr
+    py = (j // nx) * dr + 0.5 * dr
+    y = py - H
+    ku = eps * g * H * k / (2.0 * omega * math.cosh(k * H))
+    r = np.zeros((N, 2), np.float64)
+    u = np.zeros((N, 2), np.float64)
+    rho = np.full(N, refd, np.float64)
+    m = np.zeros(N, np.float64)
+    imove = np.full(N, -255, np.int32)
+    normal = np.zeros((N, 2), np.float32)
+    r[:n, 0], r[:n, 1] = px, py
+    u[:n, 0] = ku * np.sin(k * px) * np.cosh(k * (H + y))
+    u[:n, 1] = -ku * np.cos(k * px) * np.sinh(k * (H + y))
+    rho[:n] = refd + refd * g * (H - py) / cs ** 2
+    m[:n] = rho[:n] * dr ** 2
+    imove[:n] = 1
+    r[n:n + nb, 0] = (np.arange(nb) + 0.5) * dr
+    rho[n:n + nb] = refd + refd * g * H / cs ** 2
+    m[n:n + nb] = dr
+    imove[n:n + nb] = -3
+    normal[n:n + nb] = (0.0, -1.0)
+    r[n + nb:] = (dmax[0] + sep * h, dmax[1] + sep * h)
+    hh = float(np.float32(np.float32(hfac) * np.float32(dr)))
+    _ = nu
+    return dict(
+        dims=2, N=N, n_fluid=n, n_boundary=nb, n_buffer=nbuf, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs, p0=0.0,
+        support=2.0, refd=np.array([refd], np.float32), visc_dyn=np.array([visc_dyn], np.float32),
+        delta=np.array([delta], np.float32), g=np.array([0.0, -g], np.float32),
+        domain_min=np.array(dmin, np.float32), domain_max=np.array(dmax, np.float32), courant=courant, dt_Ma=0.1,
+        dt_min=float(np.float32(0.05 * courant * hh / cs)), t_end=periods * T,
+        placeholders={"L": repr(L), "END_TIME": repr(periods * T), "E_KIN": repr(ekin0), "E_POT": repr(epot0)},
+        id=np.arange(N, dtype=np.uint32), r=r.astype(np.float32), imove=imove, iset=np.zeros(N, np.uint32),
+        normal=normal, tangent=np.zeros((N, 2), np.float32), rho=rho.astype(np.float32), m=m.astype(np.float32),
+        u=u.astype(np.float32), dudt=np.zeros((N, 2), np.float32), drhodt=np.zeros(N, np.float32),
+        L=L, period=T,
     )
 
 

@@ -633,6 +633,167 @@ int l_forces(aqc_ctx* c, size_t, void* const* a)
     DISPATCH(c, k_forces, N, a[0], (float4*)a[1], (const int*)a[2], a[3], a[4], (const float*)a[5], N,
              aqc_vec_scalar(a, 7, d), aqc_vec_scalar(a, 8, d));
 }
+// ---- cfd/Boundary/Symmetry/Mirror.cl:37-251 (preset cfd/symmetry.xml): an infinite symmetry plane made of
+// mirrored copies of the particles within the kernel support of it, taken from the buffer rows
+template <int D> __device__ inline float sym_dot_xyz(V<D> a, V<D> b);
+template <> __device__ inline float sym_dot_xyz<3>(V<3> a, V<3> b) { return a.v.x * b.v.x + a.v.y * b.v.y + a.v.z * b.v.z; }
+template <> __device__ inline float sym_dot_xyz<2>(V<2> a, V<2> b) { return a.v.x * b.v.x + a.v.y * b.v.y; }
+// base + reflection(u, n) over the XYZ components (Mirror.cl:114-117); w of `base` is kept
+template <int D> __device__ inline V<D> sym_reflect_add(V<D> base, V<D> u, V<D> n);
+template <> __device__ inline V<3> sym_reflect_add<3>(V<3> base, V<3> u, V<3> n)
+{
+    const float f = -2.f * sym_dot_xyz<3>(u, n);
+    return V<3>(make_float4(base.v.x + f * n.v.x, base.v.y + f * n.v.y, base.v.z + f * n.v.z, base.v.w));
+}
+template <> __device__ inline V<2> sym_reflect_add<2>(V<2> base, V<2> u, V<2> n)
+{
+    const float f = -2.f * sym_dot_xyz<2>(u, n);
+    return V<2>(make_float2(base.v.x + f * n.v.x, base.v.y + f * n.v.y));
+}
+// ::drop (:37-55)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sym_drop(int* imove, void* r, uint32_t N, aqc_f4 symmetry_r, aqc_f4 symmetry_n, aqc_f4 domain_max)
+{
+    GID;
+    if (imove[i] <= -255)
+        return;
+    const float dr_n = (V<D>::ld(r, i) - from_f4<D>(symmetry_r)).dot(from_f4<D>(symmetry_n));
+    if (dr_n >= 0.f) {
+        V<D> one = V<D>::splat(1.f);
+        if constexpr (D == 3)
+            one.v.w = 0.f; // VEC_ONE (types/3D.h:38)
+        (from_f4<D>(domain_max) + one).st(r, i);
+        imove[i] = -256;
+    }
+}
+int l_sym_drop(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_sym_drop, N, (int*)a[0], a[1], N, aqc_vec_scalar(a, 3, d), aqc_vec_scalar(a, 4, d),
+             aqc_vec_scalar(a, 5, d));
+}
+// ::detect (:72-96)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sym_detect(const int* imove, const void* r_in, uint32_t* imirror, uint32_t N, aqc_f4 symmetry_r,
+             aqc_f4 symmetry_n, float support_h)
+{
+    GID;
+    if (imove[i] <= -255) {
+        imirror[i] = 0u;
+        return;
+    }
+    const float dr_n = (from_f4<D>(symmetry_r) - V<D>::ld(r_in, i)).dot(from_f4<D>(symmetry_n));
+    imirror[i] = (fabsf(dr_n) <= support_h) ? 1u : 0u;
+}
+int l_sym_detect(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_sym_detect, N, (const int*)a[0], a[1], (uint32_t*)a[2], N, aqc_vec_scalar(a, 4, d),
+             aqc_vec_scalar(a, 5, d), c->defs.SUPPORT * c->defs.H);
+}
+// ::feed (:140-186).  A row that is being fed (a buffer row) is never a row that feeds: its sorted
+// imirror entry is 0, so reading its imove before or after the copy leads to the same return.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sym_feed(int* imove, uint32_t* iset, const uint32_t* imirror, const uint32_t* imirror_invperm,
+           uint32_t* mirror_src, void* normal, void* tangent, void* r_in, uint32_t N, uint32_t nbuffer,
+           aqc_f4 symmetry_r, aqc_f4 symmetry_n)
+{
+    GID;
+    const int mv = imove[i];
+    if (mv <= -255)
+        return;
+    const uint32_t j = imirror_invperm[i];
+    if (imirror[j] != 1u)
+        return;
+    const uint32_t i0 = N - nbuffer;
+    const uint32_t ii = i0 + (N - j - 1u);
+    if (ii >= N)
+        return;
+    const V<D> n = from_f4<D>(symmetry_n);
+    mirror_src[ii] = (uint32_t)i;
+    imove[ii] = mv;
+    iset[ii] = iset[i];
+    // (only the XYZ components of the twin's rows are written: .XYZ assignments, Mirror.cl:178-185)
+    const V<D> nrm = V<D>::ld(normal, i), tng = V<D>::ld(tangent, i), pos = V<D>::ld(r_in, i);
+    V<D> o = sym_reflect_add<D>(nrm, nrm, n);
+    V<D> keep = V<D>::ld(normal, ii);
+    if constexpr (D == 3)
+        o.v.w = keep.v.w;
+    o.st(normal, ii);
+    o = sym_reflect_add<D>(tng, tng, n);
+    keep = V<D>::ld(tangent, ii);
+    if constexpr (D == 3)
+        o.v.w = keep.v.w;
+    o.st(tangent, ii);
+    o = sym_reflect_add<D>(pos, pos - from_f4<D>(symmetry_r), n);
+    keep = V<D>::ld(r_in, ii);
+    if constexpr (D == 3)
+        o.v.w = keep.v.w;
+    o.st(r_in, ii);
+}
+int l_sym_feed(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_sym_feed, N, (int*)a[0], (uint32_t*)a[1], (const uint32_t*)a[2], (const uint32_t*)a[3],
+             (uint32_t*)a[4], a[5], a[6], a[7], N, aqc_scalar<uint32_t>(a, 9), aqc_vec_scalar(a, 10, d),
+             aqc_vec_scalar(a, 11, d));
+}
+// ::set (:203-228)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sym_set(const uint32_t* mirror_src, float* m, void* u_in, void* dudt_in, void* dudt, float* rho_in,
+          float* drhodt_in, float* drhodt, uint32_t N, aqc_f4 symmetry_n)
+{
+    GID;
+    const uint32_t src = mirror_src[i];
+    if (src >= N)
+        return;
+    const V<D> n = from_f4<D>(symmetry_n);
+    m[i] = m[src];
+    rho_in[i] = rho_in[src];
+    const float dr = drhodt_in[src];
+    drhodt_in[i] = dr;
+    drhodt[i] = dr;
+    const V<D> us = V<D>::ld(u_in, src), as = V<D>::ld(dudt_in, src);
+    V<D> o = sym_reflect_add<D>(us, us, n);
+    if constexpr (D == 3)
+        o.v.w = V<D>::ld(u_in, i).v.w;
+    o.st(u_in, i);
+    o = sym_reflect_add<D>(as, as, n);
+    V<D> o2 = o;
+    if constexpr (D == 3) {
+        o.v.w = V<D>::ld(dudt_in, i).v.w;
+        o2.v.w = V<D>::ld(dudt, i).v.w;
+    }
+    o.st(dudt_in, i);
+    o2.st(dudt, i);
+}
+int l_sym_set(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_sym_set, N, (const uint32_t*)a[0], (float*)a[1], a[2], a[3], a[4], (float*)a[5], (float*)a[6],
+             (float*)a[7], N, aqc_vec_scalar(a, 10, d));
+}
+// ::sort (:239-251)
+__global__ void __launch_bounds__(256)
+k_sym_sort(const uint32_t* mirror_src_in, uint32_t* mirror_src, const uint32_t* id_sorted, uint32_t N)
+{
+    GID;
+    mirror_src[id_sorted[i]] = mirror_src_in[i];
+}
+int l_sym_sort(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    LAUNCH(c, k_sym_sort, N, (const uint32_t*)a[0], (uint32_t*)a[1], (const uint32_t*)a[2], N);
+    return AQC_OK;
+}
 // basic/DensityClamp.cl:41-52 (preset basic/densityClamp.xml)
 __global__ void __launch_bounds__(256)
 k_density_clamp(float* rho_in, uint32_t N, float rho_min, float rho_max)
@@ -1525,6 +1686,24 @@ aqc_registrar r_en_k("cfd/Energy/EnergyKin.cl", "entry", 0,
 aqc_registrar r_forces("cfd/Forces/Forces.cl", "entry", 0,
     { OUT("forces_f", "vec*"), OUT("forces_m", "vec4*"), RO("imove", "int*"), RO("r", "vec*"), RO("dudt", "vec*"),
       RO("m", "float*"), SC("N", "usize"), SC("g", "vec"), SC("forces_r", "vec") }, l_forces);
+// cfd/Boundary/Symmetry/Mirror.cl (preset cfd/symmetry.xml)
+aqc_registrar r_sym_drop("cfd/Boundary/Symmetry/Mirror.cl", "drop", 0,
+    { OUT("imove", "int*"), OUT("r", "vec*"), SC("N", "usize"), SC("symmetry_r", "vec"), SC("symmetry_n", "vec"),
+      SC("domain_max", "vec") }, l_sym_drop);
+aqc_registrar r_sym_detect("cfd/Boundary/Symmetry/Mirror.cl", "detect", 0,
+    { IN("imove", "int*"), IN("r_in", "vec*"), OUT("imirror", "uint*"), SC("N", "usize"), SC("symmetry_r", "vec"),
+      SC("symmetry_n", "vec") }, l_sym_detect);
+aqc_registrar r_sym_feed("cfd/Boundary/Symmetry/Mirror.cl", "feed", 0,
+    { OUT("imove", "int*"), OUT("iset", "uint*"), IN("imirror", "uint*"), IN("imirror_invperm", "usize*"),
+      OUT("mirror_src", "usize*"), OUT("normal", "vec*"), OUT("tangent", "vec*"), OUT("r_in", "vec*"),
+      SC("N", "usize"), SC("nbuffer", "usize"), SC("symmetry_r", "vec"), SC("symmetry_n", "vec") }, l_sym_feed);
+aqc_registrar r_sym_set("cfd/Boundary/Symmetry/Mirror.cl", "set", 0,
+    { IN("mirror_src", "usize*"), OUT("m", "float*"), OUT("u_in", "vec*"), OUT("dudt_in", "vec*"),
+      OUT("dudt", "vec*"), OUT("rho_in", "float*"), OUT("drhodt_in", "float*"), OUT("drhodt", "float*"),
+      SC("N", "usize"), SC("symmetry_r", "vec"), SC("symmetry_n", "vec") }, l_sym_set);
+aqc_registrar r_sym_sort("cfd/Boundary/Symmetry/Mirror.cl", "sort", 0,
+    { IN("mirror_src_in", "usize*"), OUT("mirror_src", "usize*"), IN("id_sorted", "usize*"), SC("N", "usize") },
+    l_sym_sort);
 aqc_registrar r_rho_clamp("basic/DensityClamp.cl", "entry", 0,
     { OUT("rho_in", "float*"), SC("N", "usize"), SC("rho_min", "float"), SC("rho_max", "float") },
     l_density_clamp);

@@ -278,4 +278,16 @@ void aqo_mpi_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const aqo_usize*
                             const float* mpi_r, const float* mpi_rho, const float* mpi_m,
                             const float* mpi_lap_p_corr, float* lap_p);
 
+/* cfd/Boundary/Symmetry/Mirror.cl:37-251 (preset cfd/symmetry.xml) */
+void aqo_sym_drop(int* imove, float* r, aqo_usize N, const float* symmetry_r, const float* symmetry_n,
+                  const float* domain_max, int dims);
+void aqo_sym_detect(const aqo_defs* D, const int* imove, const float* r_in, aqo_usize* imirror, aqo_usize N,
+                    const float* symmetry_r, const float* symmetry_n);
+void aqo_sym_feed(int* imove, int* iset, const aqo_usize* imirror, const aqo_usize* imirror_invperm,
+                  aqo_usize* mirror_src, float* normal, float* tangent, float* r_in, aqo_usize N,
+                  aqo_usize nbuffer, const float* symmetry_r, const float* symmetry_n, int dims);
+void aqo_sym_set(const aqo_usize* mirror_src, float* m, float* u_in, float* dudt_in, float* dudt, float* rho_in,
+                 float* drhodt_in, float* drhodt, aqo_usize N, const float* symmetry_n, int dims);
+void aqo_sym_sort(const aqo_usize* mirror_src_in, aqo_usize* mirror_src, const aqo_usize* id_sorted, aqo_usize N);
+
 #endif

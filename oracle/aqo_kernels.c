@@ -1552,3 +1552,116 @@ void aqo_mpi_dsph_lapp_corr(const aqo_defs* D, const aqo_ll* L, const aqo_usize*
         lap_p[i] -= 0.5f * acc;
     }
 }
+
+/* ---------------------------------------------------------------------------
+ * cfd/Boundary/Symmetry/Mirror.cl (preset cfd/symmetry.xml): an infinite symmetry plane made of
+ * mirrored copies of the particles within the kernel support of it, taken from the buffer rows. */
+static float aqo_dotv(const float* a, const float* b, int n)
+{
+    float s = a[0] * b[0];
+    for (int k = 1; k < n; k++)
+        s += a[k] * b[k];
+    return s;
+}
+
+/* Mirror.cl:37-55 */
+void aqo_sym_drop(int* imove, float* r, aqo_usize N, const float* symmetry_r, const float* symmetry_n,
+                  const float* domain_max, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] <= -255)
+            continue;
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = r[(size_t)i * vs + k] - symmetry_r[k];
+        if (aqo_dotv(d, symmetry_n, vs) >= 0.f) {
+            for (int k = 0; k < vs; k++) /* VEC_ONE: w = 0 in 3-D (types/3D.h:38) */
+                r[(size_t)i * vs + k] = domain_max[k] + ((k < dims) ? 1.f : 0.f);
+            imove[i] = -256;
+        }
+    }
+}
+
+/* Mirror.cl:72-96 */
+void aqo_sym_detect(const aqo_defs* D, const int* imove, const float* r_in, aqo_usize* imirror, aqo_usize N,
+                    const float* symmetry_r, const float* symmetry_n)
+{
+    const int vs = VS(D->dims);
+    AQO_FOR_I(N) {
+        if (imove[i] <= -255) {
+            imirror[i] = 0;
+            continue;
+        }
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = symmetry_r[k] - r_in[(size_t)i * vs + k];
+        imirror[i] = (fabsf(aqo_dotv(d, symmetry_n, vs)) <= D->SUPPORT * D->H) ? 1u : 0u;
+    }
+}
+
+/* Mirror.cl:114-117: v = -2 (u . n) n over the XYZ components; out = base + v */
+static void aqo_reflect_add(const float* base, const float* u, const float* n, int dims, float* out)
+{
+    const float f = -2.f * aqo_dotv(u, n, dims);
+    for (int k = 0; k < dims; k++)
+        out[k] = base[k] + f * n[k];
+}
+
+/* Mirror.cl:140-186 (a sequential loop: the script's only cross-row access, imove of a buffer row
+ * that another work-item is overwriting, cannot change what that row's work-item does -- its sorted
+ * imirror entry is 0 either way) */
+void aqo_sym_feed(int* imove, int* iset, const aqo_usize* imirror, const aqo_usize* imirror_invperm,
+                  aqo_usize* mirror_src, float* normal, float* tangent, float* r_in, aqo_usize N,
+                  aqo_usize nbuffer, const float* symmetry_r, const float* symmetry_n, int dims)
+{
+    const int vs = VS(dims);
+    for (aqo_usize i = 0; i < N; i++) {
+        if (imove[i] <= -255)
+            continue;
+        const aqo_usize j = imirror_invperm[i];
+        if (imirror[j] != 1)
+            continue;
+        const aqo_usize i0 = N - nbuffer;
+        const aqo_usize ii = i0 + (N - j - 1);
+        if (ii >= N)
+            continue;
+        mirror_src[ii] = i;
+        imove[ii] = imove[i];
+        iset[ii] = iset[i];
+        aqo_reflect_add(normal + (size_t)i * vs, normal + (size_t)i * vs, symmetry_n, dims, normal + (size_t)ii * vs);
+        aqo_reflect_add(tangent + (size_t)i * vs, tangent + (size_t)i * vs, symmetry_n, dims,
+                        tangent + (size_t)ii * vs);
+        float rel[3];
+        for (int k = 0; k < dims; k++)
+            rel[k] = r_in[(size_t)i * vs + k] - symmetry_r[k];
+        aqo_reflect_add(r_in + (size_t)i * vs, rel, symmetry_n, dims, r_in + (size_t)ii * vs);
+    }
+}
+
+/* Mirror.cl:203-228 */
+void aqo_sym_set(const aqo_usize* mirror_src, float* m, float* u_in, float* dudt_in, float* dudt, float* rho_in,
+                 float* drhodt_in, float* drhodt, aqo_usize N, const float* symmetry_n, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        const aqo_usize ii = i, src = mirror_src[ii];
+        if (src >= N)
+            continue;
+        m[ii] = m[src];
+        rho_in[ii] = rho_in[src];
+        drhodt[ii] = drhodt_in[ii] = drhodt_in[src];
+        aqo_reflect_add(u_in + (size_t)src * vs, u_in + (size_t)src * vs, symmetry_n, dims, u_in + (size_t)ii * vs);
+        float a[3];
+        aqo_reflect_add(dudt_in + (size_t)src * vs, dudt_in + (size_t)src * vs, symmetry_n, dims, a);
+        for (int k = 0; k < dims; k++)
+            dudt[(size_t)ii * vs + k] = dudt_in[(size_t)ii * vs + k] = a[k];
+    }
+}
+
+/* Mirror.cl:239-251 */
+void aqo_sym_sort(const aqo_usize* mirror_src_in, aqo_usize* mirror_src, const aqo_usize* id_sorted, aqo_usize N)
+{
+    AQO_FOR_I(N)
+        mirror_src[id_sorted[i]] = mirror_src_in[i];
+}

@@ -405,6 +405,16 @@ class Interpreter:
             return self.jump_back[i]
         elif typ == "reduction":
             self.reduction(t)
+        elif typ == "radix-sort":
+            # RadixSort.cpp:129-303: keys sorted in place (ascending, stable); perm[sorted] = original
+            # index, inv_perm[original] = sorted index (RadixSort.cl.in:313-323)
+            keys = V[t["in"]]
+            perm = np.argsort(keys, kind="stable").astype(np.uint32)
+            keys[...] = keys[perm]
+            if t.get("perm"):
+                V[t["perm"]][...] = perm
+            if t.get("inv_perm"):
+                V[t["inv_perm"]][perm] = np.arange(len(perm), dtype=np.uint32)
         elif typ == "link-list":
             self.linklist(t)
         elif typ == "mpi-sync":
@@ -697,6 +707,23 @@ class Interpreter:
         elif key == ("cfd/Boundary/BI/NoSlip.cl", "entry"):
             c("bi_noslip", D, self.ll(), V["iset"], V["imove"], V["r"], V["normal"], V["u"], V["rho"], V["m"],
               V["lap_u"], int(V["noslip_iset"]), f32("dr"))
+        elif rel == "cfd/Boundary/Symmetry/Mirror.cl":
+            # preset cfd/symmetry.xml: detect / feed / set / sort / drop (aqo_kernels.c, bit-identical to the script)
+            if entry == "detect":
+                c("sym_detect", D, V["imove"], V["r_in"], V["imirror"], N, V["symmetry_r"], V["symmetry_n"])
+            elif entry == "feed":
+                O.call("sym_feed", V["imove"], V["iset"].view(np.int32), V["imirror"], V["imirror_invperm"],
+                       V["mirror_src"], V["normal"], V["tangent"], V["r_in"], N, int(V["nbuffer"]), V["symmetry_r"],
+                       V["symmetry_n"], d)
+            elif entry == "set":
+                c("sym_set", V["mirror_src"], V["m"], V["u_in"], V["dudt_in"], V["dudt"], V["rho_in"], V["drhodt_in"],
+                  V["drhodt"], N, V["symmetry_n"], d)
+            elif entry == "sort":
+                c("sym_sort", V["mirror_src_in"], V["mirror_src"], V["id_sorted"], N)
+            elif entry == "drop":
+                c("sym_drop", V["imove"], V["r"], N, V["symmetry_r"], V["symmetry_n"], V["domain_max"], d)
+            else:
+                raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
         elif rel == "aqua/MPIdeltaSPH.cl":
             # remote (halo) terms of MLS / delta-SPH: ours, not reference scripts (aqo_kernels.c)
             rl = O.make_ll(V["mpi_icell"], V["mpi_ihoc"], V["n_cells"], N)

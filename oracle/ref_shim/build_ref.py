@@ -40,6 +40,7 @@ SCRIPTS = [
     "cfd/Motions/Acceleration.cl", "cfd/Energy/Energy.cl",
     "cfd/Energy/EnergyKin.cl", "cfd/Forces/Forces.cl", "basic/DensityClamp.cl", "basic/IdInverse.cl",
     "basic/time_scheme/adam_bashforth.cl", "cfd/Boundary/BI/NoSlip.cl",
+    "cfd/Boundary/Symmetry/Mirror.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

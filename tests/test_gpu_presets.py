@@ -327,6 +327,56 @@ def test_small_preset_kernels(oracle, dims):
 
 
 @pytest.mark.parametrize("dims", [2, 3])
+def test_symmetry_mirror_kernels(oracle, dims):
+    """cfd/Boundary/Symmetry/Mirror.cl::detect / feed / set / sort / drop (preset cfd/symmetry.xml, SURVEY 8(f)
+    row 4) through the Kernel-tool C-ABI, with the preset's radix-sort of imirror in between
+    (aqc_radix_sort), against the oracle -- which is bit-identical to the reference's script
+    (tests/test_oracle_vs_reference.py): copies, products and sums without contraction, bit-exact."""
+    from test_oracle_vs_reference import _symmetry_state
+    case, v, N, nbuf, sr, sn, dmax = _symmetry_state(dims)
+    V = 4 if dims == 3 else 2
+    D = oracle.make_defs(dims, case["h"])
+    o = dict(imove=v["imove"].copy(), iset=v["iset"].astype(np.uint32), r_in=v["r"].copy(), r=v["r"].copy(),
+             normal=v["normal"].copy(), tangent=v["tangent"].copy(), m=v["m"].copy(), u_in=v["u"].copy(),
+             dudt_in=v["dudt"].copy(), dudt=np.zeros((N, V), np.float32), rho_in=v["rho"].copy(),
+             drhodt_in=v["drhodt"].copy(), drhodt=np.zeros(N, np.float32), imirror=np.full(N, 7, np.uint32),
+             mirror_src=np.full(N, N, np.uint32), mirror_src_in=np.zeros(N, np.uint32))
+    ids = np.random.default_rng(4).permutation(N).astype(np.uint32)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    d = {k: ctx.array(a) for k, a in o.items()}
+    d.update(N=N, nbuffer=nbuf, symmetry_r=sr, symmetry_n=sn, domain_max=dmax, id_sorted=ctx.array(ids),
+             imirror_perm=ctx.empty(N, np.uint32), imirror_invperm=ctx.empty(N, np.uint32))
+    S = "cfd/Boundary/Symmetry/Mirror.cl"
+    ctx.launch(S, "detect", d)
+    oracle.call("sym_detect", D, o["imove"], o["r_in"], o["imirror"], N, sr, sn)
+    assert np.array_equal(d["imirror"].get(), o["imirror"]) and o["imirror"].sum() > 0
+    ctx.radix_sort(d["imirror"], 2, d["imirror_perm"], d["imirror_invperm"])
+    perm = np.argsort(o["imirror"], kind="stable").astype(np.uint32)
+    inv = np.empty(N, np.uint32)
+    inv[perm] = np.arange(N, dtype=np.uint32)
+    o["imirror"] = o["imirror"][perm].copy()
+    assert np.array_equal(d["imirror_invperm"].get(), inv) and np.array_equal(d["imirror"].get(), o["imirror"])
+    ctx.launch(S, "feed", d)
+    ctx.launch(S, "set", d)
+    ctx.copy(d["mirror_src_in"], d["mirror_src"])
+    ctx.launch(S, "sort", d)
+    ctx.copy(d["r"], d["r_in"])
+    ctx.launch(S, "drop", d)
+    oracle.call("sym_feed", o["imove"], o["iset"].view(np.int32), o["imirror"], inv, o["mirror_src"], o["normal"],
+                o["tangent"], o["r_in"], N, nbuf, sr, sn, dims)
+    oracle.call("sym_set", o["mirror_src"], o["m"], o["u_in"], o["dudt_in"], o["dudt"], o["rho_in"], o["drhodt_in"],
+                o["drhodt"], N, sn, dims)
+    o["mirror_src_in"] = o["mirror_src"].copy()
+    oracle.call("sym_sort", o["mirror_src_in"], o["mirror_src"], ids, N)
+    o["r"] = o["r_in"].copy()
+    oracle.call("sym_drop", o["imove"], o["r"], N, sr, sn, dmax, dims)
+    for k in o:
+        assert d[k].get().tobytes() == o[k].tobytes(), k
+    assert (o["mirror_src_in"] < N).sum() == int(o["imirror"].sum()) and (o["imove"] == -256).sum() > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
 def test_adams_bashforth_kernels(oracle, dims):
     """basic/time_scheme/adam_bashforth.cl::sort / ::corrector / ::postcorrector through the Kernel-tool
     C-ABI vs the oracle for iter = 0 .. 6 (every order): copies, and products / sums without
@@ -451,4 +501,40 @@ def test_lid_driven_cavity_pipeline(oracle):
             scale = max(np.abs(a[fl]).max(), 1e-30)
             assert np.abs(a[fl] - b[fl]).max() <= tol * scale, "step %d field %s" % (step, k)
     assert np.abs(sim.download("u", unsorted=True)[fl]).max() > 0      # the lid drags the fluid
+    sim.close()
+
+
+def test_standing_wave_with_symmetry_planes_pipeline(oracle):
+    """examples/2D/souto_etal_2012_standingwave: the unchanged 91-tool pipeline (improved Euler, delta-SPH full,
+    BI bottom, elastic bounce, kinetic energy, and TWO symmetry planes of cfd/symmetry.xml: detect, the radix-sort
+    tool on imirror, buffer bookkeeping, feed, set, sort, drop -- cfd/Boundary/Symmetry/Mirror.cl) on the GPU
+    against the oracle interpreter, four steps: who is mirrored into which buffer row, imove and the neighbour
+    structures bit-exact, dt bit-exact, fields within the tolerances of the other 2-D pipelines."""
+    from oracle import interp
+    host.set_log_level(3)
+    case = product_cases.souto2012_standing_wave_2d(24)
+    nset = (case["N"],)
+    I = interp.Interpreter(casegen.instantiate("souto2012_standingwave_2d", case, nset), 2)
+    for k in casegen.STATE_FIELDS:
+        I.V[k][...] = case[k]
+    sim = casegen.load("souto2012_standingwave_2d", case, nset)
+    assert sim.tools() == [(t["name"], t["type"]) for t in I.tools] and len(I.tools) == 91
+    N = case["N"]
+    for step in range(4):
+        I.step()
+        sim.step(1)
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"])
+        assert int(sim.scalar("nbuffer", np.uint32)) == int(I.V["nbuffer"])
+        for k, dt_ in (("imove", np.int32), ("mirror_src", np.uint32), ("icell", np.uint32), ("id_sorted", np.uint32)):
+            assert np.array_equal(sim.download(k, dt_), I.V[k]), (step, k)
+        fl = I.unsorted("imove") == 1
+        for k, tol in {"r": 1e-6, "u": 1e-5, "rho": 1e-6, "p": 4e-4, "dudt": 1e-3, "drhodt": 2e-2}.items():
+            a = I.unsorted(k).astype(np.float64)
+            b = sim.download(k, unsorted=True).astype(np.float64)
+            scale = max(np.abs(a[fl]).max(), 1e-30)
+            assert np.abs(a[fl] - b[fl]).max() <= tol * scale, "step %d field %s: %.3e" % (
+                step, k, np.abs(a[fl] - b[fl]).max() / scale)
+    # both planes mirrored something, and what they mirrored was dropped again
+    assert (I.V["imove"] == -256).sum() > 0 and (I.V["mirror_src"] < N).sum() > 0
     sim.close()

@@ -366,3 +366,92 @@ def test_linklist_tool_kernels_match_the_reference_source(oracle, golden, dims):
         assert np.all(ihoc == N)
         R.run("LinkList.cl", "linkList", N, dict(icell=ll["icell"], ihoc=ihoc, N=N))
         assert np.array_equal(ihoc, ll["ihoc"][:ncw])
+
+
+def _symmetry_state(dims, seed=21):
+    """A dam break with buffer rows at the end and a symmetry plane through the fluid."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    n, V = case["N"], (4 if dims == 3 else 2)
+    nbuf = n            # (room for every particle next to the plane)
+    N = n + nbuf
+    rng = np.random.default_rng(seed)
+
+    def grow(a, fill):
+        out = np.empty((N,) + a.shape[1:], a.dtype)
+        out[:n] = a
+        out[n:] = fill
+        return out
+    dmax = np.asarray(case["domain_max"], np.float32).ravel()[:V].copy()
+    v = {"imove": grow(np.ascontiguousarray(case["imove"]), -255), "iset": grow(np.ascontiguousarray(case["iset"]).astype(np.int32), 0),
+         "r": grow(np.ascontiguousarray(case["r"]), dmax), "m": grow(np.ascontiguousarray(case["m"]), 0),
+         "rho": grow(np.ascontiguousarray(case["rho"]), 1000.0)}
+    for k in ("normal", "tangent", "u", "dudt"):
+        a = rng.normal(size=(N, V)).astype(np.float32)
+        if dims == 3:
+            a[:, 3] = 0
+        v[k] = a
+    v["drhodt"] = rng.normal(size=N).astype(np.float32)
+    fl = v["imove"] == 1
+    x0 = float(np.median(v["r"][fl][:, 0]))
+    sr = np.zeros(V, np.float32)
+    sr[0] = x0
+    sn = np.zeros(V, np.float32)
+    sn[0], sn[1] = 0.8, 0.6            # normalised, not axis aligned
+    return case, v, N, nbuf, sr, sn, dmax
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_symmetry_mirror_kernels_match_reference_script(oracle, dims):
+    """cfd/Boundary/Symmetry/Mirror.cl::detect / feed / set / sort / drop (preset cfd/symmetry.xml, SURVEY
+    8(f) row 4) in the order the preset runs them: the C restatement is bit-identical to the
+    reference's script, particles next to the plane get a mirrored twin in a buffer row, and drop
+    removes what lies beyond the plane."""
+    case, v, N, nbuf, sr, sn, dmax = _symmetry_state(dims)
+    V = 4 if dims == 3 else 2
+    R = ref.Ref(dims, case["h"])
+    D = oracle.make_defs(dims, case["h"])
+    a = dict(imove=v["imove"].copy(), iset=v["iset"].copy(), r_in=v["r"].copy(), r=v["r"].copy(),
+             normal=v["normal"].copy(), tangent=v["tangent"].copy(), m=v["m"].copy(), u_in=v["u"].copy(),
+             dudt_in=v["dudt"].copy(), dudt=np.zeros((N, V), np.float32), rho_in=v["rho"].copy(),
+             drhodt_in=v["drhodt"].copy(), drhodt=np.zeros(N, np.float32),
+             imirror=np.full(N, 7, np.uint32), mirror_src=np.full(N, N, np.uint32),
+             mirror_src_in=np.zeros(N, np.uint32), N=N, nbuffer=nbuf, symmetry_r=sr, symmetry_n=sn,
+             domain_max=dmax)
+    b = {k: (x.copy() if isinstance(x, np.ndarray) else x) for k, x in a.items()}
+    # detect
+    R.run("cfd/Boundary/Symmetry/Mirror.cl", "detect", N, a)
+    oracle.call("sym_detect", D, b["imove"], b["r_in"], b["imirror"], N, sr, sn)
+    assert np.array_equal(a["imirror"], b["imirror"]) and 0 < a["imirror"].sum() < (v["imove"] > -255).sum()
+    # the radix-sort tool of the preset: keys sorted in place, inverse permutation kept
+    perm = np.argsort(a["imirror"], kind="stable").astype(np.uint32)
+    inv = np.empty(N, np.uint32)
+    inv[perm] = np.arange(N, dtype=np.uint32)
+    for d in (a, b):
+        d["imirror"] = d["imirror"][perm].copy()
+        d["imirror_invperm"] = inv
+    R.run("cfd/Boundary/Symmetry/Mirror.cl", "feed", N, a)
+    oracle.call("sym_feed", b["imove"], b["iset"], b["imirror"], inv, b["mirror_src"], b["normal"], b["tangent"],
+                b["r_in"], N, nbuf, sr, sn, dims)
+    R.run("cfd/Boundary/Symmetry/Mirror.cl", "set", N, a)
+    oracle.call("sym_set", b["mirror_src"], b["m"], b["u_in"], b["dudt_in"], b["dudt"], b["rho_in"], b["drhodt_in"],
+                b["drhodt"], N, sn, dims)
+    ids = np.random.default_rng(4).permutation(N).astype(np.uint32)
+    for d in (a, b):
+        d["mirror_src_in"] = d["mirror_src"].copy()
+        d["id_sorted"] = ids
+    R.run("cfd/Boundary/Symmetry/Mirror.cl", "sort", N, a)
+    oracle.call("sym_sort", b["mirror_src_in"], b["mirror_src"], ids, N)
+    for d in (a, b):
+        d["r"] = d["r_in"].copy()
+    R.run("cfd/Boundary/Symmetry/Mirror.cl", "drop", N, a)
+    oracle.call("sym_drop", b["imove"], b["r"], N, sr, sn, dmax, dims)
+    for k in ("imove", "iset", "mirror_src", "normal", "tangent", "r_in", "m", "u_in", "dudt_in", "dudt", "rho_in",
+              "drhodt_in", "drhodt", "r"):
+        assert a[k].tobytes() == b[k].tobytes(), k
+    # every detected particle has a twin at its mirror image, the twins lie beyond the plane and are dropped
+    src = b["mirror_src_in"]
+    twins = np.flatnonzero(src < N)
+    assert len(twins) == int(a["imirror"].sum())
+    dn = ((b["r_in"][twins] - sr) * sn).sum(1) + ((b["r_in"][src[twins]] - sr) * sn).sum(1)
+    assert np.abs(dn).max() < 1e-5
+    assert (b["imove"][twins][((b["r_in"][twins] - sr) * sn).sum(1) > 1e-6] == -256).all()

@@ -106,6 +106,31 @@ void emu_small(int dims, float* ekin, void* ff, float4* fm, float* rho_in, const
         k_id_inverse(id, inv, N);
     }
 }
+/* cfd/Boundary/Symmetry/Mirror.cl: detect, (the preset's radix sort happens outside), feed, set, sort, drop */
+void emu_sym_detect(int dims, const int* imove, const void* r_in, uint32_t* imirror, uint32_t N, const float* sr_,
+                    const float* sn_, float support_h)
+{
+    aqc_f4 sr = f4(sr_, dims == 3 ? 4 : 2), sn = f4(sn_, dims == 3 ? 4 : 2);
+    FOR_ALL(k_sym_detect<3>(imove, r_in, imirror, N, sr, sn, support_h),
+            k_sym_detect<2>(imove, r_in, imirror, N, sr, sn, support_h))
+}
+void emu_sym_rest(int dims, int* imove, uint32_t* iset, const uint32_t* imirror, const uint32_t* invperm,
+                  uint32_t* mirror_src, uint32_t* mirror_src_in, const uint32_t* id_sorted, void* normal, void* tangent,
+                  void* r_in, void* r, float* m, void* u_in, void* dudt_in, void* dudt, float* rho_in, float* drhodt_in,
+                  float* drhodt, uint32_t N, uint32_t nbuffer, const float* sr_, const float* sn_, const float* dmax_)
+{
+    const int n = dims == 3 ? 4 : 2;
+    aqc_f4 sr = f4(sr_, n), sn = f4(sn_, n), dmax = f4(dmax_, n);
+    FOR_ALL(k_sym_feed<3>(imove, iset, imirror, invperm, mirror_src, normal, tangent, r_in, N, nbuffer, sr, sn),
+            k_sym_feed<2>(imove, iset, imirror, invperm, mirror_src, normal, tangent, r_in, N, nbuffer, sr, sn))
+    FOR_ALL(k_sym_set<3>(mirror_src, m, u_in, dudt_in, dudt, rho_in, drhodt_in, drhodt, N, sn),
+            k_sym_set<2>(mirror_src, m, u_in, dudt_in, dudt, rho_in, drhodt_in, drhodt, N, sn))
+    memcpy(mirror_src_in, mirror_src, 4 * (size_t)N);
+    for (g_i = 0; g_i < N; g_i++)
+        k_sym_sort(mirror_src_in, mirror_src, id_sorted, N);
+    memcpy(r, r_in, 4 * (size_t)n * N);
+    FOR_ALL(k_sym_drop<3>(imove, r, N, sr, sn, dmax), k_sym_drop<2>(imove, r, N, sr, sn, dmax))
+}
 }
 """
 
@@ -270,3 +295,48 @@ def test_adams_bashforth_kernel_bodies_match_the_oracle(oracle, emu, dims, steps
             assert e[k].tobytes() == o[k].tobytes(), (it, k)
         o["dudt"][:, :dims] = np.random.default_rng(100 + it).normal(size=(N, dims)).astype(np.float32)
         e["dudt"][...] = o["dudt"]
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_symmetry_mirror_kernel_bodies_match_the_oracle(oracle, emu, dims):
+    """k_sym_detect / feed / set / sort / drop (cfd/Boundary/Symmetry/Mirror.cl, preset cfd/symmetry.xml) in
+    the preset's order, on the state of tests/test_oracle_vs_reference.py's symmetry test."""
+    import test_oracle_vs_reference as T
+    case, v, N, nbuf, sr, sn, dmax = T._symmetry_state(dims)
+    V = 4 if dims == 3 else 2
+    D = oracle.make_defs(dims, case["h"])
+
+    def state():
+        return dict(imove=v["imove"].copy(), iset=v["iset"].astype(np.uint32), r_in=v["r"].copy(), r=v["r"].copy(),
+                    normal=v["normal"].copy(), tangent=v["tangent"].copy(), m=v["m"].copy(), u_in=v["u"].copy(),
+                    dudt_in=v["dudt"].copy(), dudt=np.zeros((N, V), np.float32), rho_in=v["rho"].copy(),
+                    drhodt_in=v["drhodt"].copy(), drhodt=np.zeros(N, np.float32),
+                    imirror=np.full(N, 7, np.uint32), mirror_src=np.full(N, N, np.uint32),
+                    mirror_src_in=np.zeros(N, np.uint32))
+    e, o = state(), state()
+    emu.emu_sym_detect(dims, _p(e["imove"]), _p(e["r_in"]), _p(e["imirror"]), N, _p(sr), _p(sn),
+                       C.c_float(float(np.float32(D.SUPPORT) * np.float32(D.H))))
+    oracle.call("sym_detect", D, o["imove"], o["r_in"], o["imirror"], N, sr, sn)
+    assert np.array_equal(e["imirror"], o["imirror"]) and e["imirror"].sum() > 0
+    perm = np.argsort(o["imirror"], kind="stable").astype(np.uint32)
+    inv = np.empty(N, np.uint32)
+    inv[perm] = np.arange(N, dtype=np.uint32)
+    ids = np.random.default_rng(4).permutation(N).astype(np.uint32)
+    for d in (e, o):
+        d["imirror"] = d["imirror"][perm].copy()
+    emu.emu_sym_rest(dims, _p(e["imove"]), _p(e["iset"]), _p(e["imirror"]), _p(inv), _p(e["mirror_src"]),
+                     _p(e["mirror_src_in"]), _p(ids), _p(e["normal"]), _p(e["tangent"]), _p(e["r_in"]), _p(e["r"]),
+                     _p(e["m"]), _p(e["u_in"]), _p(e["dudt_in"]), _p(e["dudt"]), _p(e["rho_in"]), _p(e["drhodt_in"]),
+                     _p(e["drhodt"]), N, nbuf, _p(sr), _p(sn), _p(dmax))
+    oi = o["iset"].view(np.int32)
+    oracle.call("sym_feed", o["imove"], oi, o["imirror"], inv, o["mirror_src"], o["normal"], o["tangent"], o["r_in"],
+                N, nbuf, sr, sn, dims)
+    oracle.call("sym_set", o["mirror_src"], o["m"], o["u_in"], o["dudt_in"], o["dudt"], o["rho_in"], o["drhodt_in"],
+                o["drhodt"], N, sn, dims)
+    o["mirror_src_in"] = o["mirror_src"].copy()
+    oracle.call("sym_sort", o["mirror_src_in"], o["mirror_src"], ids, N)
+    o["r"] = o["r_in"].copy()
+    oracle.call("sym_drop", o["imove"], o["r"], N, sr, sn, dmax, dims)
+    for k in e:
+        assert e[k].tobytes() == o[k].tobytes(), k
+    assert (o["mirror_src_in"] < N).sum() == int(o["imirror"].sum()) > 0 and (o["imove"] == -256).sum() > 0

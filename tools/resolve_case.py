@@ -30,6 +30,9 @@ CASES = {
     "spheric9_tld_2d": ("examples/2D/spheric_testcase9_tld/src/templates", 2),
     # lid-driven cavity (SPHERIC test 3): improved Euler, delta-SPH full, BI boundaries + BINoSlip
     "spheric3_liddriven_2d": ("examples/2D/spheric_testcase3_liddriven/src/templates", 2),
+    # standing wave of Souto-Iglesias et al. 2012: improved Euler, delta-SPH full, BI bottom, two symmetry
+    # planes (cfd/symmetry.xml twice: Symmetry/Mirror.cl) feeding on buffer particles, kinetic-energy report
+    "souto2012_standingwave_2d": ("examples/2D/souto_etal_2012_standingwave/src/templates", 2),
     # the reference's own multi-device parity test (tests/2D/MPI_plane)
     "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
     "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
