@@ -22,7 +22,7 @@ SYMBOLS = [
     "aqc_alloc", "aqc_free", "aqc_host_alloc", "aqc_host_free", "aqc_memcpy_h2d",
     "aqc_memcpy_d2h", "aqc_memcpy_d2d", "aqc_side_fork", "aqc_memcpy_d2h_side", "aqc_side_record", "aqc_side_wait", "aqc_fill", "aqc_linklist_build", "aqc_radix_sort",
     "aqc_scatter_fields", "aqc_reduce", "aqc_kernel_lookup", "aqc_kernel_count",
-    "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_event_create",
+    "aqc_kernel_name", "aqc_kernel_nargs", "aqc_kernel_args", "aqc_launch", "aqc_script_compile", "aqc_script_check", "aqc_event_create",
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
@@ -79,6 +79,8 @@ def lib():
     L.aqc_pairs_cache_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64)]
     L.aqc_pairs_cache_stats_remote.argtypes = L.aqc_pairs_cache_stats.argtypes
+    L.aqc_script_compile.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_char_p),
+                                     C.c_int]
     L.aqc_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.aqc_free.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -207,6 +209,20 @@ def _scalar_bytes(value, typ, dims):
     if t == "vec4":
         return np.asarray(value, np.float32).reshape(4).tobytes()
     raise AquaError("unsupported scalar type '%s'" % typ)
+
+
+def script_check(path, entry="entry", dims=3, base_path="", defines=()):
+    """aqc_script_check: compile a run-time script up to the cubin WITHOUT a device; returns its argument
+    list as text, raises AquaError with the compiler's message."""
+    L = lib()
+    L.aqc_script_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
+                                   C.c_char_p, C.c_size_t]
+    arr = (C.c_char_p * max(len(defines), 1))(*[d.encode() for d in defines])
+    log = C.create_string_buffer(4096)
+    rc = L.aqc_script_check(path.encode(), entry.encode(), int(dims), base_path.encode(), arr, len(defines), log, 4096)
+    if rc < 0:
+        raise AquaError(log.value.decode())
+    return log.value.decode()
 
 
 class Context:
@@ -413,11 +429,22 @@ class Context:
             raise AquaError("kernel %s::%s is not in the registry" % (script, entry))
         return kid
 
-    def launch(self, script, entry, variables, n=None):
+    def script_compile(self, path, entry="entry", base_path="", defines=()):
+        """A script that is not in the registry, compiled at run time (aqc_script_compile): the kernel
+        id, usable with launch(kid=...)."""
+        arr = (C.c_char_p * max(len(defines), 1))(*[d.encode() for d in defines])
+        kid = lib().aqc_script_compile(self.h, path.encode(), entry.encode(), self.dims, base_path.encode(), arr,
+                                       len(defines))
+        if kid < 0:
+            raise AquaError(lib().aqc_last_error(self.h).decode())
+        return kid
+
+    def launch(self, script, entry, variables, n=None, kid=None):
         """Kernel tool: bind arguments by NAME from `variables` (dict name ->
         DevArray | python scalar), like Kernel.cpp:497-556."""
         L = lib()
-        kid = self.lookup(script, entry)
+        if kid is None:
+            kid = self.lookup(script, entry)
         na = L.aqc_kernel_nargs(kid)
         info = L.aqc_kernel_args(kid)
         argv = (C.c_void_p * na)()

@@ -420,15 +420,17 @@ extern "C" int aqc_kernel_lookup(const char* script_path, const char* entry, int
     const char* rel = strip_script_path(script_path);
     const char* ent = (entry && *entry) ? entry : "entry"; // State.cpp:1058-1059
     auto& reg = aqc_registry();
+    // (run-time scripts are compiled per problem -- its definitions are baked in -- and are only
+    // handed out by aqc_script_compile)
     for (size_t k = 0; k < reg.size(); k++)
-        if (!strcmp(reg[k].script, rel) && !strcmp(reg[k].entry, ent) &&
+        if (!reg[k].jit && !strcmp(reg[k].script, rel) && !strcmp(reg[k].entry, ent) &&
             (reg[k].dims == 0 || reg[k].dims == dims))
             return (int)k;
     // case-local scripts (outside resources/Scripts) are registered by file name
     const char* base = strrchr(rel, '/');
     base = base ? base + 1 : rel;
     for (size_t k = 0; k < reg.size(); k++)
-        if (!strchr(reg[k].script, '/') && !strcmp(reg[k].script, base) &&
+        if (!reg[k].jit && !strchr(reg[k].script, '/') && !strcmp(reg[k].script, base) &&
             !strcmp(reg[k].entry, ent) && (reg[k].dims == 0 || reg[k].dims == dims))
             return (int)k;
     return AQC_ERR_NOKERNEL;
@@ -481,6 +483,8 @@ extern "C" int aqc_launch(aqc_ctx* ctx, int id, size_t n, void* const* args, int
     for (int k = 0; k < nargs; k++) // what the kernel may write: one element per work-item
         if (reg[id].args[k].kind == AQC_ARG_ARRAY_OUT)
             aqc_pc_touch(ctx, args[k], n * aqc_type_bytes(reg[id].args[k].type, ctx->defs.dims));
+    if (reg[id].jit)
+        return aqc_script_launch(ctx, reg[id], n, args);
     return reg[id].fn(ctx, n, args);
 }
 

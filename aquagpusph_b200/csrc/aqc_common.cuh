@@ -239,7 +239,9 @@ struct aqc_kernel_entry {
     int dims; // 0 = both, 2, 3
     std::vector<aqc_arg_info> args;
     aqc_launcher fn;
+    void* jit = nullptr; // run-time script (clc.cu): launched through aqc_script_launch, fn == nullptr
 };
+int aqc_script_launch(aqc_ctx* ctx, const aqc_kernel_entry& e, size_t n, void* const* args); // clc.cu
 std::vector<aqc_kernel_entry>& aqc_registry();
 struct aqc_registrar {
     aqc_registrar(const char* script, const char* entry, int dims,

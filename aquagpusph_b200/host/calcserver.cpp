@@ -65,11 +65,24 @@ Kernel::Kernel(CalcServer* C, const std::string& name, const std::string& path,
 void Kernel::setup()
 {
     _kid = aqc_kernel_lookup(_path.c_str(), _entry.c_str(), _C->dims());
-    if (_kid < 0)
-        throw std::runtime_error(
-            "The tool \"" + name() + "\" asks for the script \"" + _path + "\" entry point \"" +
-            _entry + "\", which is not in the CUDA kernel registry (there is no run-time OpenCL "
-            "compiler in this build)");
+    if (_kid < 0) {
+        // not a hand-written kernel: the script itself, compiled at run time like the reference compiles
+        // every script (Kernel.cpp:354-420) -- here by NVRTC for sm_100a (csrc/clc.cu)
+        std::vector<std::string> defs;
+        for (auto& d : _C->definitions())
+            defs.push_back("-D" + d.first + (d.second.empty() ? "" : "=" + d.second));
+        std::vector<const char*> dp;
+        for (auto& d : defs)
+            dp.push_back(d.c_str());
+        _kid = aqc_script_compile(_C->ctx(), _path.c_str(), _entry.c_str(), _C->dims(),
+                                  _C->sim_data().settings.base_path.c_str(), dp.data(), (int)dp.size());
+        if (_kid < 0)
+            throw std::runtime_error("The tool \"" + name() + "\" asks for the script \"" + _path +
+                                     "\" entry point \"" + _entry + "\", which is not in the CUDA kernel "
+                                     "registry and could not be compiled at run time: " + aqc_last_error(_C->ctx()));
+        log(L_INFO, "The tool \"" + name() + "\" runs the script \"" + _path + "\"::" + _entry +
+                        " compiled at run time (NVRTC)\n");
+    }
     const int na = aqc_kernel_nargs(_kid);
     const aqc_arg_info* info = aqc_kernel_args(_kid);
     Variables* vars = _C->variables();

@@ -166,6 +166,21 @@ const aqc_arg_info* aqc_kernel_args(int kernel_id);
  * (float, uint, vec = 2/4 floats, svec4 = 4 uints) for scalar arguments, in
  * registry order.  n = global work size (Kernel.cpp:558-594). */
 int aqc_launch(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nargs);
+/* A script that is NOT in the registry (case-local *.cl, families without hand-written kernels): what
+ * Kernel::make does with every script in the reference (Kernel.cpp:354-420: read the source, "-I<script
+ * folder> -I<base path>", the problem's -D definitions, clBuildProgram; :497-556 argument names and
+ * qualifiers from clGetKernelArgInfo).  The script and the headers it includes are read where they lie,
+ * compiled for sm_100a by NVRTC behind a dialect header, and entered in the registry: the returned id works
+ * with aqc_kernel_nargs / aqc_kernel_args / aqc_launch.  defines: "-DNAME=VALUE" strings of
+ * CalcServer.cpp:240-265.  Neighbour loops (BEGIN_NEIGHS) run as the script wrote them, one particle
+ * per thread; registry kernels are never replaced by this path.  < 0: error (libnvrtc missing, compile error:
+ * aqc_last_error holds the log). */
+int aqc_script_compile(aqc_ctx* ctx, const char* path, const char* entry, int dims, const char* base_path,
+                       const char* const* defines, int ndefines);
+/* the same up to the cubin, without a device and without registering anything: returns the number of
+ * arguments (their "type name;" list goes to `log`), or < 0 with the compiler's message in `log` */
+int aqc_script_check(const char* path, const char* entry, int dims, const char* base_path,
+                     const char* const* defines, int ndefines, char* log, size_t log_bytes);
 
 /* ---- fusion of neighbour sweeps.  The reference launches one sweep per script
  * kernel (9 per midpoint sub-iteration in the 3-D dam break); sweeps

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/examples"),
 COVERED = {"2D/lobovsky_etal_2014", "2D/normal_impact", "2D/souto_etal_2012_standingwave",
            "2D/spheric_testcase10_waveimpact",
            "2D/spheric_testcase3_liddriven", "2D/spheric_testcase5_dambreak", "2D/spheric_testcase9_tld",
-           "3D/spheric_testcase10_waveimpact", "3D/spheric_testcase2_dambreak",
+           "3D/apollo_capsule", "3D/spheric_testcase10_waveimpact", "3D/spheric_testcase2_dambreak",
            "3D/spheric_testcase2_dambreak_mpi", "3D/spheric_testcase9_tld"}
 
 # variables the host registers itself (CalcServer.cpp:139-236, Variables defaults)
@@ -47,10 +47,13 @@ def test_covered_examples_and_their_bindings():
     assert len(rows) == 20
     full = {"%s/%s" % (r[0], r[1]) for r in rows if r[2] and not r[4] and not r[5]}
     assert full == COVERED
-    # apollo_capsule: every script is registered; its `installable` tool needs the example's own plugin,
-    # which is built against the reference's OpenCL Tool class (the tool type itself loads, test_installable.py)
-    apollo = [r for r in rows if r[1] == "apollo_capsule"][0]
-    assert not apollo[4] and apollo[5] == ["installable"]
+    # apollo_capsule: every script is registered and its `installable` tool type loads (test_installable.py);
+    # the example's own plugin is built against the reference's OpenCL Tool class and cannot be loaded here
+    # ... and with the run-time script path (csrc/clc.cu) every script of 18 examples has a kernel: the two
+    # left are the moving square (its Main.xml includes a file only its generator writes) and the cylinder in
+    # a channel (cfd/Forces/BI/ViscousForces.cl needs a definition this scan does not supply)
+    runs = {"%s/%s" % (r[0], r[1]) for r in rows if r[2] and not r[7] and not r[5]}
+    assert len(runs) >= 18 and COVERED <= runs, sorted(runs)
     bad = []
     for D, ex in sorted(x.split("/") for x in full):
         dims = int(D[0])
