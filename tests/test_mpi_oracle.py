@@ -248,3 +248,50 @@ def test_slab_pipeline_with_delta_sph_is_the_single_device_pipeline(oracle):
             a = serial[k][g["fluid_index"]].astype(np.float64)
             b = g["unsorted"][k].astype(np.float64)
             assert np.abs(a - b).max() <= tol * np.abs(serial[k]).max(), (r, k)
+
+
+def _gloo_dsph_worker(rank, port, q, n_total, steps, kw):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=2)
+    from aquagpusph_b200 import cases as cs, casegen as cg
+    from oracle import interp as ip, oracle as O
+    O.build()
+    c = cs.spheric2_dam_break_slab(n_total, 3.0, rank, 2, **kw)
+    txt = cg.instantiate("spheric2_dambreak_mpi_3d", c, (c["n_set0"], c["N"] - c["n_set0"]), {"iter_midpoint_max": 2})
+    txt = cg.slab_fixes_delta_sph(float(c["delta"][0]))(txt)
+    I = ip.Interpreter(txt, 3, rank=rank, size=2, transport=ip.TorchTransport())
+    for k in cg.STATE_FIELDS:
+        I.V[k][...] = c[k]
+    for _ in range(steps):
+        I.step()
+    q.put((rank, {k: I.V[k].copy() for k in ("r", "u", "rho", "dudt", "imove")}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_delta_sph_slabs_two_processes_gloo(oracle):
+    """The delta-SPH slab pipeline (casegen.slab_delta_sph: two halo exchanges per sub-iteration, the pre-loop
+    one, migration, both all-reduces) on world_size = 2 over torch.distributed / gloo: bit-identical to the
+    same two ranks run as threads of one process -- the transport does not matter, only the protocol."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    kw = dict(seed=5, jitter=0.45, uscale=2.0)
+    n_total, steps = 6000, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_dsph_worker, args=(r, port, q, n_total, steps, kw)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=600) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    want = _dam_break_ranks(2, n_total, steps, delta_sph=True, maxiter=2, **kw)
+    for r in range(2):
+        for k in ("r", "u", "rho", "dudt", "imove"):
+            assert np.array_equal(got[r][k], want[r][k]), (r, k)
+        assert np.abs(got[r]["dudt"]).max() > 0
