@@ -29,6 +29,9 @@ SYMBOLS = [
     "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
     "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_pairs_cache_stats_remote", "aqc_fp32_peak",
     "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
+    "aqc_loop_create", "aqc_loop_destroy", "aqc_loop_table", "aqc_loop_begin", "aqc_loop_svm",
+    "aqc_loop_end", "aqc_loop_abort", "aqc_loop_run", "aqc_loop_stats", "aqc_kernel_dev_scalars",
+    "aqc_launch_ex",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -47,6 +50,33 @@ class ArgInfo(C.Structure):
 
 class AquaError(RuntimeError):
     pass
+
+
+# ---- device-side loops (include/aquasvm.h): the scalar programs of a recorded `while`
+class AqsOp(C.Structure):
+    _fields_ = [("code", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32),
+                ("imm", C.c_double)]
+
+
+class AqsHeader(C.Structure):
+    _fields_ = [("iters", C.c_uint32), ("snaps", C.c_uint32), ("error", C.c_uint32),
+                ("cond", C.c_uint32)]
+
+
+(AQS_IMM, AQS_LOAD, AQS_STORE, AQS_ADD, AQS_SUB, AQS_MUL, AQS_DIV, AQS_MOD, AQS_POW, AQS_NEG, AQS_NOT,
+ AQS_LT, AQS_GT, AQS_LE, AQS_GE, AQS_EQ, AQS_NE, AQS_AND, AQS_OR, AQS_SELECT, AQS_CALL, AQS_FOLD,
+ AQS_SNAP, AQS_ASSERT, AQS_SETCOND) = range(25)
+
+
+def aqs_program(ops):
+    """[(code, a, b, c, imm), ...] (missing fields = 0; kinds as 'f' / 'u' / 'i') -> AqsOp array."""
+    arr = (AqsOp * len(ops))()
+    for k, op in enumerate(ops):
+        op = tuple(op) + (0,) * (5 - len(op))
+        arr[k].code, arr[k].a = op[0], op[1]
+        arr[k].b = ord(op[2]) if isinstance(op[2], str) else op[2]
+        arr[k].c, arr[k].imm = op[3], float(op[4])
+    return arr
 
 
 def lib():
@@ -130,6 +160,22 @@ def lib():
     L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aqc_loop_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.aqc_loop_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_loop_table.argtypes = [C.c_void_p]
+    L.aqc_loop_table.restype = C.c_void_p
+    L.aqc_loop_begin.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(AqsOp), C.c_int]
+    L.aqc_loop_svm.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(AqsOp), C.c_int]
+    L.aqc_loop_end.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_loop_abort.argtypes = [C.c_void_p, C.c_void_p]
+    L.aqc_loop_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(AqsHeader),
+                               C.c_void_p, C.c_void_p]
+    L.aqc_loop_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double)]
+    L.aqc_kernel_dev_scalars.argtypes = [C.c_int]
+    L.aqc_kernel_dev_scalars.restype = C.c_uint64
+    L.aqc_launch_ex.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_int,
+                                C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -439,9 +485,10 @@ class Context:
             raise AquaError(lib().aqc_last_error(self.h).decode())
         return kid
 
-    def launch(self, script, entry, variables, n=None, kid=None):
+    def launch(self, script, entry, variables, n=None, kid=None, dev_scalars=None):
         """Kernel tool: bind arguments by NAME from `variables` (dict name ->
-        DevArray | python scalar), like Kernel.cpp:497-556."""
+        DevArray | python scalar), like Kernel.cpp:497-556.  dev_scalars: {name: device address}
+        of scalars the kernel reads when it runs (aqc_launch_ex)."""
         L = lib()
         if kid is None:
             kid = self.lookup(script, entry)
@@ -462,7 +509,16 @@ class Context:
                 argv[k] = v.ptr
         if n is None:
             n = int(variables["N"])
+        if dev_scalars:
+            dv = (C.c_void_p * na)()
+            for k in range(na):
+                dv[k] = dev_scalars.get(info[k].name.decode())
+            self._chk(L.aqc_launch_ex(self.h, kid, int(n), argv, na, dv))
+            return
         self._chk(L.aqc_launch(self.h, kid, int(n), argv, na))
+
+    def loop(self, table_bytes, hist_rows=0, max_ops=1024):
+        return DeviceLoop(self, table_bytes, hist_rows, max_ops)
 
     def launch_fused(self, members, variables):
         """Fused launch of [(script, entry), ...] (pipeline order), arguments by name."""
@@ -501,3 +557,54 @@ class Context:
         ms = C.c_float()
         self._chk(lib().aqc_event_elapsed_ms(self.h, a, b, C.byref(ms)))
         return float(ms.value)
+
+
+class DeviceLoop:
+    """aqc_loop_*: a loop body recorded as a CUDA graph WHILE node (include/aquacuda.h)."""
+
+    def __init__(self, ctx, table_bytes, hist_rows=0, max_ops=1024):
+        self.ctx, self.table_bytes, self.hist_rows = ctx, table_bytes, hist_rows
+        self.h = C.c_void_p()
+        ctx._chk(lib().aqc_loop_create(ctx.h, table_bytes, hist_rows, max_ops, C.byref(self.h)))
+
+    def table(self):
+        return lib().aqc_loop_table(self.h)
+
+    def begin(self, entry):
+        p = aqs_program(entry)
+        self.ctx._chk(lib().aqc_loop_begin(self.ctx.h, self.h, p, len(p)))
+
+    def svm(self, ops):
+        p = aqs_program(ops)
+        self.ctx._chk(lib().aqc_loop_svm(self.ctx.h, self.h, p, len(p)))
+
+    def end(self):
+        self.ctx._chk(lib().aqc_loop_end(self.ctx.h, self.h))
+
+    def abort(self):
+        self.ctx._chk(lib().aqc_loop_abort(self.ctx.h, self.h))
+
+    def run(self, table, max_iters=1000):
+        """-> (header, table bytes as uint8 array, history rows [(tool id, table bytes), ...])."""
+        tab = np.ascontiguousarray(np.frombuffer(bytes(table), np.uint8)).copy()
+        assert tab.nbytes == self.table_bytes
+        hdr = AqsHeader()
+        out = np.zeros(self.table_bytes, np.uint8)
+        hist = np.zeros(max(1, self.hist_rows) * (16 + self.table_bytes), np.uint8)
+        self.ctx._chk(lib().aqc_loop_run(self.ctx.h, self.h, tab.ctypes.data, max_iters, C.byref(hdr),
+                                         out.ctypes.data, hist.ctypes.data if self.hist_rows else None))
+        rows = []
+        for k in range(min(hdr.snaps, self.hist_rows)):
+            row = hist[k * (16 + self.table_bytes):(k + 1) * (16 + self.table_bytes)]
+            rows.append((int(row[:4].view(np.int32)[0]), row[16:].copy()))
+        return hdr, out, rows
+
+    def stats(self):
+        n, a, b = C.c_int(0), C.c_double(0), C.c_double(0)
+        lib().aqc_loop_stats(self.h, C.byref(n), C.byref(a), C.byref(b))
+        return n.value, a.value, b.value
+
+    def close(self):
+        if self.h:
+            lib().aqc_loop_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()

@@ -49,6 +49,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "aquacuda.h"))
+    headers.append(os.path.join(ROOT, "include", "aquasvm.h"))
     headers.append(os.path.abspath(__file__))
     jobs = []
     objs = []
@@ -86,7 +87,7 @@ def build_host(force=False, verbose=False):
     flags = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-I" + os.path.join(ROOT, "include"),
              "-I" + HOST]
     hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
-    hdrs += [os.path.join(ROOT, "include", f) for f in ("aquacuda.h", "aquahost.h")]
+    hdrs += [os.path.join(ROOT, "include", f) for f in ("aquacuda.h", "aquahost.h", "aquasvm.h")]
     hdrs.append(os.path.abspath(__file__))
     srcs = sorted(f for f in os.listdir(HOST) if f.endswith(".cpp") and f != "main.cpp")
     jobs, objs = [], []

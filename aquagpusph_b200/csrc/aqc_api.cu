@@ -14,7 +14,7 @@ int aqc_fail(aqc_ctx* ctx, int code, const char* fmt, ...)
         va_end(ap);
         // a rank that hit a device fault cannot keep step with its peers: give the communicator
         // up now, so that this process can leave and the peers' bounded waits end (mpi.cu)
-        if (code == AQC_ERR_CUDA && ctx->comm)
+        if (code == AQC_ERR_CUDA && ctx->comm && !ctx->recording) // (a failed recording ran nothing)
             aqc_comm_abort(ctx);
     }
     return code;
@@ -462,6 +462,32 @@ extern "C" const aqc_arg_info* aqc_kernel_args(int id)
     if (id < 0 || id >= (int)reg.size())
         return nullptr;
     return reg[id].args.data();
+}
+
+extern "C" uint64_t aqc_kernel_dev_scalars(int id)
+{
+    auto& reg = aqc_registry();
+    return (id < 0 || id >= (int)reg.size()) ? 0 : reg[id].dev_mask;
+}
+
+extern "C" int aqc_launch_ex(aqc_ctx* ctx, int id, size_t n, void* const* args, int nargs,
+                             const void* const* dev_scalars)
+{
+    if (!ctx)
+        return AQC_ERR_ARG;
+    auto& reg = aqc_registry();
+    if (id < 0 || id >= (int)reg.size())
+        return aqc_fail(ctx, AQC_ERR_NOKERNEL, "aqc_launch_ex: bad kernel id %d", id);
+    if (dev_scalars)
+        for (int k = 0; k < nargs && k < (int)reg[id].args.size(); k++)
+            if (dev_scalars[k] && (k >= 64 || !((reg[id].dev_mask >> k) & 1)))
+                return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_ex(%s::%s): argument %d (%s) cannot be "
+                                "read from device memory", reg[id].script, reg[id].entry, k,
+                                reg[id].args[k].name);
+    ctx->dev_scalars = dev_scalars;
+    const int rc = aqc_launch(ctx, id, n, args, nargs);
+    ctx->dev_scalars = nullptr;
+    return rc;
 }
 
 extern "C" int aqc_launch(aqc_ctx* ctx, int id, size_t n, void* const* args, int nargs)

@@ -134,6 +134,10 @@ struct aqc_ctx {
     void* comm_watchdog = nullptr;     // backstop thread of the bounded waits (mpi.cu)
     std::vector<aqc_sync_plan> plans;  // aqc_mpi_sync_plan slots
     std::vector<aqc_watch> watches;    // aqc_watch_create slots
+    // device-side loops (devloop.cu): the loop whose body is being recorded on `stream`, and the
+    // device addresses of the scalar arguments of the launch in flight (aqc_launch_ex)
+    struct aqc_loop* recording = nullptr;
+    const void* const* dev_scalars = nullptr;
 };
 
 int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
@@ -145,6 +149,11 @@ int aqc_comm_wait(aqc_ctx* ctx, cudaEvent_t ev);
 void aqc_comm_abort(aqc_ctx* ctx); // mpi.cu
 static inline int aqc_stream_wait(aqc_ctx* ctx)
 {
+    // a loop body is being recorded (devloop.cu): nothing runs, so there is nothing to wait for,
+    // and whatever the caller wanted to read back is not there -- the recording fails cleanly
+    if (ctx->recording)
+        return aqc_fail(ctx, AQC_ERR_STATE, "this call synchronises with the device, which a recorded "
+                                            "loop body cannot do");
     if (ctx->comm)
         return aqc_comm_wait(ctx, nullptr);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -240,14 +249,15 @@ struct aqc_kernel_entry {
     std::vector<aqc_arg_info> args;
     aqc_launcher fn;
     void* jit = nullptr; // run-time script (clc.cu): launched through aqc_script_launch, fn == nullptr
+    uint64_t dev_mask = 0; // scalar arguments the launcher can bind to a device address (aqc_launch_ex)
 };
 int aqc_script_launch(aqc_ctx* ctx, const aqc_kernel_entry& e, size_t n, void* const* args); // clc.cu
 std::vector<aqc_kernel_entry>& aqc_registry();
 struct aqc_registrar {
     aqc_registrar(const char* script, const char* entry, int dims,
-                  std::vector<aqc_arg_info> args, aqc_launcher fn)
+                  std::vector<aqc_arg_info> args, aqc_launcher fn, uint64_t dev_mask = 0)
     {
-        aqc_registry().push_back({ script, entry, dims, std::move(args), fn });
+        aqc_registry().push_back({ script, entry, dims, std::move(args), fn, nullptr, dev_mask });
     }
 };
 
@@ -258,6 +268,22 @@ static inline T aqc_scalar(void* const* args, int k)
     T v;
     memcpy(&v, args[k], sizeof(T));
     return v;
+}
+// ... or, under aqc_launch_ex, a device address the kernel reads when it runs (p != nullptr)
+template <typename T> struct aqc_sv {
+    const T* p;
+    T v;
+#if defined(__CUDACC__)
+    __device__ __forceinline__ T get() const { return p ? *p : v; }
+#endif
+};
+template <typename T>
+static inline aqc_sv<T> aqc_scalar_sv(const aqc_ctx* ctx, void* const* args, int k)
+{
+    aqc_sv<T> s;
+    s.p = ctx->dev_scalars ? (const T*)ctx->dev_scalars[k] : nullptr;
+    s.v = aqc_scalar<T>(args, k);
+    return s;
 }
 struct aqc_u4 { uint32_t x, y, z, w; };
 struct aqc_f4 { float x, y, z, w; };

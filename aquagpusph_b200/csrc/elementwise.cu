@@ -195,11 +195,12 @@ int l_mp_midpoint_r(aqc_ctx* c, size_t, void* const* a)
 template <int D>
 __global__ void __launch_bounds__(256)
 k_mp_relax(const int* imove, const void* dudt_in, void* dudt, const float* drhodt_in,
-           float* drhodt, uint32_t N, float f)
+           float* drhodt, uint32_t N, aqc_sv<float> relax)
 {
     GID;
     if (imove[i] <= 0)
         return;
+    const float f = relax.get(); // inside a recorded loop: the value the loop's scalar program left
     (f * V<D>::ld(dudt_in, i) + (1.f - f) * V<D>::ld(dudt, i)).st(dudt, i);
     drhodt[i] = f * drhodt_in[i] + (1.f - f) * drhodt[i];
 }
@@ -207,7 +208,7 @@ int l_mp_relax(aqc_ctx* c, size_t, void* const* a)
 {
     const uint32_t N = aqc_scalar<uint32_t>(a, 5);
     DISPATCH(c, k_mp_relax, N, (const int*)a[0], a[1], a[2], (const float*)a[3], (float*)a[4], N,
-             aqc_scalar<float>(a, 6));
+             aqc_scalar_sv<float>(c, a, 6));
 }
 
 // ---- basic/time_scheme/midpoint.cl:159-184 ---------------------------------------
@@ -1618,7 +1619,7 @@ aqc_registrar r_mp_mr("basic/time_scheme/midpoint.cl", "midpoint_r", 0,
       SC("dt", "float") }, l_mp_midpoint_r);
 aqc_registrar r_mp_rx("basic/time_scheme/midpoint.cl", "relax", 0,
     { IN("imove", "int*"), OUT("dudt_in", "vec*"), OUT("dudt", "vec*"), OUT("drhodt_in", "float*"),
-      OUT("drhodt", "float*"), SC("N", "usize"), SC("relax_midpoint", "float") }, l_mp_relax);
+      OUT("drhodt", "float*"), SC("N", "usize"), SC("relax_midpoint", "float") }, l_mp_relax, 1ull << 6);
 aqc_registrar r_mp_rs("basic/time_scheme/midpoint.cl", "residuals", 0,
     { IN("imove", "int*"), IN("m", "float*"), IN("u", "vec*"), IN("dudt_in", "vec*"),
       IN("dudt", "vec*"), IN("rho", "float*"), IN("p", "float*"), IN("drhodt_in", "float*"),

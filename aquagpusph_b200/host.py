@@ -21,6 +21,7 @@ SYMBOLS = [
     "aqh_fused_groups", "aqh_save", "aqh_wait_savers", "aqh_checkpoint_file", "aqh_n_savers", "aqh_saver_file",
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr", "aqh_set_script_runner", "aqh_variable_type",
+    "aqh_eval_svm", "aqh_device_loops", "aqh_device_loop_stats", "aqh_loop_host_reason",
 ]
 
 
@@ -115,6 +116,12 @@ def lib():
     L.aqh_cuda_ctx.argtypes = [C.c_void_p]
     L.aqh_cuda_ctx.restype = C.c_void_p
     L.aqh_eval.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.aqh_eval_svm.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.aqh_device_loops.argtypes = [C.c_void_p]
+    L.aqh_device_loops.restype = C.c_uint
+    L.aqh_device_loop_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.aqh_loop_host_reason.argtypes = [C.c_void_p, C.c_int]
+    L.aqh_loop_host_reason.restype = C.c_char_p
     L.aqh_scalar_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
     L.aqh_scalar_set.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     L.aqh_array_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t),
@@ -148,6 +155,15 @@ def evaluate(expr, type="float", decls="", dims=3, dtype=np.float32, n=1):
     out = np.zeros(n, dtype)
     _chk(lib().aqh_eval(dims, decls.encode(), type.encode(), expr.encode(), out.ctypes.data,
                         out.nbytes))
+    return out[0] if n == 1 else out
+
+
+def evaluate_svm(expr, type="float", decls="", dims=3, dtype=np.float32, n=1):
+    """The same value through the stack programs a recorded `while` runs on the device
+    (SvmCompiler + aqs_run of include/aquasvm.h, here on the host)."""
+    out = np.zeros(n, dtype)
+    _chk(lib().aqh_eval_svm(dims, decls.encode(), type.encode(), expr.encode(), out.ctypes.data,
+                            out.nbytes))
     return out[0] if n == 1 else out
 
 
@@ -292,6 +308,21 @@ class Simulation:
 
     def cuda_ctx(self):
         return lib().aqh_cuda_ctx(self.h)
+
+    def device_loops(self):
+        """`while` loops that run as a CUDA graph from their second pass on."""
+        return int(lib().aqh_device_loops(self.h))
+
+    def device_loop_stats(self):
+        """(times a loop ran on the device, passes made there)."""
+        runs, iters = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().aqh_device_loop_stats(self.h, C.byref(runs), C.byref(iters)))
+        return int(runs.value), int(iters.value)
+
+    def loop_host_reason(self, i):
+        """Why the `while` at tool index i stays on the host ('' when it runs on the device)."""
+        r = lib().aqh_loop_host_reason(self.h, int(i))
+        return None if r is None else r.decode()
 
     # variables
     def scalar(self, name, dtype=np.float32, n=1):

@@ -1,5 +1,6 @@
 // calcserver.cpp -- see calcserver.hpp
 #include "calcserver.hpp"
+#include "devloop.hpp"
 
 #include <dlfcn.h>
 
@@ -127,17 +128,7 @@ void Kernel::_execute()
         check(aqc_launch_fused(_C->ctx(), _fused_id, args.data(), (int)args.size()));
         return;
     }
-    // global size: n="" -> longest array argument (Kernel.cpp:558-594)
-    size_t N = 0;
-    if (_n.empty()) {
-        for (auto v : _vars)
-            if (v->isArray() && v->length() > N)
-                N = v->length();
-    } else {
-        uint64_t n = 0;
-        _C->variables()->solve("unsigned long", _n, &n);
-        N = (size_t)n;
-    }
+    const size_t N = globalSize();
     std::vector<void*> args(_vars.size());
     for (size_t k = 0; k < _vars.size(); k++)
         args[k] = _vars[k]->isArray() ? _vars[k]->dptr() : _vars[k]->get();
@@ -1040,7 +1031,7 @@ Tool* CalcServer::makeTool(const ProblemSetup::Tool& t)
     if (type == "python")
         return new PythonTool(this, name, t.get("path"), once);
     if (type == "dummy")
-        return new Tool(this, name, once);
+        return new Dummy(this, name, once);
     if (type == "installable") {
         // CalcServer.cpp:375-400: dlopen(path), dlsym("create_object"), Tool* create_object(const
         // std::string name, bool once).  The plugin derives from THIS host's Tool
@@ -1100,6 +1091,7 @@ void CalcServer::setup()
     for (auto& t : _tools)
         t->setup();
     planFusion();
+    planDeviceLoops();
 }
 
 // Sweep fusion planner.  A group {M0 < M1 < ...} of kernel tools is executed by ONE fused

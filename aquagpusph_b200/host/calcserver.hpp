@@ -26,6 +26,7 @@ namespace Aqua {
 namespace CalcServer {
 
 class CalcServer;
+class DeviceLoop;
 
 /// Base class of every tool (Tool.hpp:173-567)
 class Tool {
@@ -58,6 +59,21 @@ class Tool {
         (void)in; (void)out;
         return false;
     }
+    // ---- device-side loops (host/devloop.hpp).  recordable: one pass of the tool inside the loop
+    // L only enqueues device work or is scalar arithmetic a program can do (no read-back, no host
+    // decision); scalarOutputs: the scalar variables it writes (they move into the loop's device
+    // table); record: enqueue / emit that pass while the loop's body is being recorded.
+    virtual bool recordable(const DeviceLoop& L, std::string& why) const
+    {
+        (void)L;
+        why = "its tool type runs on the host";
+        return false;
+    }
+    virtual void scalarOutputs(std::vector<InputOutput::Variable*>& out) const { (void)out; }
+    virtual void record(DeviceLoop& L) { (void)L; }
+    bool once() const { return _once; }
+    /// passes that ran inside a device-side loop
+    void account(unsigned n) { _n_iters += n; }
 
   protected:
     virtual void _execute() {}
@@ -93,9 +109,12 @@ class Kernel : public Tool {
     void fuse_lead(int fused_id, const std::vector<Kernel*>& group) { _fused_id = fused_id; _group = group; }
     void fuse_follow(Kernel* leader) { _leader = leader; }
     bool fused() const { return _fused_id >= 0 || _leader; }
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
   private:
+    size_t globalSize() const;
     int _fused_id = -1;
     std::vector<Kernel*> _group;
     Kernel* _leader = nullptr;
@@ -119,11 +138,20 @@ class Copy : public Tool {
         out.push_back(_out);
         return true;
     }
+    bool recordable(const DeviceLoop&, std::string&) const override { return true; }
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
   private:
     std::string _in_name, _out_name;
     InputOutput::Variable *_in = nullptr, *_out = nullptr;
+};
+
+/// type="dummy": a named position in the pipeline (presets hang their tools before / after it)
+class Dummy : public Tool {
+  public:
+    using Tool::Tool;
+    bool recordable(const DeviceLoop&, std::string&) const override { return true; }
 };
 
 /// type="set" (Set.cpp:197-226, Set.cl.in:32-47)
@@ -140,6 +168,8 @@ class Set : public Tool {
         out.push_back(_var);
         return true;
     }
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
   private:
@@ -168,6 +198,9 @@ class SetScalar : public ScalarExpression {
     SetScalar(CalcServer* C, const std::string& name, const std::string& var, const std::string& value, bool once)
       : ScalarExpression(C, name, value, "float", once), _var_name(var) {}
     void setup() override;
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void scalarOutputs(std::vector<InputOutput::Variable*>& out) const override { out.push_back(_var); }
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
   private:
@@ -180,6 +213,8 @@ class Assert : public ScalarExpression {
   public:
     Assert(CalcServer* C, const std::string& name, const std::string& cond, bool once)
       : ScalarExpression(C, name, cond, "int", once) {}
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
 };
@@ -197,9 +232,24 @@ class Conditional : public ScalarExpression {
     bool _result = true;
     Tool* _ending_tool = nullptr;
 };
+/// `while`: the first pass runs tool by tool; when the body can be recorded (DeviceLoop::plan) the
+/// rest of the loop runs as one CUDA graph from the first `end` on
 class While : public Conditional {
   public:
     using Conditional::Conditional;
+    ~While() override;
+    /// called once every tool is set up and the sweeps are fused
+    void planDeviceLoop();
+    /// the matching `end` hands control back (End::next_tool)
+    void reentry() { _reentry = true; }
+    const DeviceLoop* deviceLoop() const { return _dev; }
+    const std::string& hostReason() const { return _why; }
+  protected:
+    void _execute() override;
+  private:
+    DeviceLoop* _dev = nullptr;
+    bool _reentry = false;
+    std::string _why;
 };
 class If : public Conditional {
   public:
@@ -213,6 +263,8 @@ class End : public Tool {
   public:
     End(CalcServer* C, const std::string& name, bool once) : Tool(C, name, once) {}
     void setup() override;
+    using Tool::next_tool;
+    Tool* next_tool() override;
     int scope_modifier() const override { return -1; }
 };
 
@@ -223,6 +275,9 @@ class Reduction : public Tool {
               const std::string& operation, const std::string& null_val, bool once)
       : Tool(C, name, once), _in_name(in), _out_name(out), _operation(operation), _null(null_val) {}
     void setup() override;
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void scalarOutputs(std::vector<InputOutput::Variable*>& out) const override { out.push_back(_out); }
+    void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
   private:
@@ -354,6 +409,9 @@ class Report : public Tool {
            const InputOutput::ProblemSetup::Tool& t, bool once);
     void setup() override;
     ~Report() override;
+    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    void record(DeviceLoop& L) override;
+    const std::vector<InputOutput::Variable*>& fields() const { return _vars; }
   protected:
     void _execute() override;
   private:
@@ -425,6 +483,9 @@ class CalcServer {
     /// between them in the pipeline reads their outputs or writes their inputs
     void planFusion();
     unsigned fused_groups() const { return _fused_groups; }
+    /// `while` loops whose body runs as a CUDA graph (AQUA_DEVICE_LOOPS=0: none)
+    void planDeviceLoops();
+    unsigned device_loops() const { return _device_loops; }
     /// Run time steps until an output frame is due or the end criteria is met
     void update(TimeManager& t);
     /// Run exactly one pass over the pipeline (one time step)
@@ -467,6 +528,7 @@ class CalcServer {
     int _mpi_rank, _mpi_size;
     uint64_t _steps = 0;
     unsigned _fused_groups = 0;
+    unsigned _device_loops = 0;
     void* _unsort_scratch = nullptr;
     size_t _unsort_cap = 0;
     void writeCheckpoint();

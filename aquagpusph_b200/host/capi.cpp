@@ -5,6 +5,7 @@
 
 #include "aquahost.h"
 #include "calcserver.hpp"
+#include "devloop.hpp"
 
 using namespace Aqua;
 
@@ -246,13 +247,8 @@ extern "C" uint64_t aqh_launch_count(aqh_sim* sim) { return aqc_launch_count(sim
 extern "C" void* aqh_cuda_ctx(aqh_sim* sim) { return sim->C->ctx(); }
 extern "C" unsigned aqh_fused_groups(aqh_sim* sim) { return sim->C ? sim->C->fused_groups() : 0; }
 
-extern "C" int aqh_eval(int dims, const char* decls, const char* type, const char* expr,
-                        void* out, size_t bytes)
+static void declareScalars(InputOutput::Variables& vars, const char* decls, const char* who)
 {
-    AQH_TRY
-    if (!type || !expr || !out)
-        throw std::runtime_error("aqh_eval: NULL argument");
-    InputOutput::Variables vars(dims, nullptr);
     std::string d(decls ? decls : "");
     size_t pos = 0;
     while (pos < d.size()) {
@@ -265,14 +261,24 @@ extern "C" int aqh_eval(int dims, const char* decls, const char* type, const cha
             continue;
         const size_t eq = item.find('=');
         if (eq == std::string::npos)
-            throw std::runtime_error("aqh_eval: \"" + item + "\" is not \"type name=value\"");
+            throw std::runtime_error(std::string(who) + ": \"" + item + "\" is not \"type name=value\"");
         const std::string lhs = trimCopy(item.substr(0, eq));
         const size_t sp = lhs.find_last_of(" \t");
         if (sp == std::string::npos)
-            throw std::runtime_error("aqh_eval: \"" + item + "\" is not \"type name=value\"");
+            throw std::runtime_error(std::string(who) + ": \"" + item + "\" is not \"type name=value\"");
         vars.registerVariable(trimCopy(lhs.substr(sp + 1)), trimCopy(lhs.substr(0, sp)), "",
                               trimCopy(item.substr(eq + 1)));
     }
+}
+
+extern "C" int aqh_eval(int dims, const char* decls, const char* type, const char* expr,
+                        void* out, size_t bytes)
+{
+    AQH_TRY
+    if (!type || !expr || !out)
+        throw std::runtime_error("aqh_eval: NULL argument");
+    InputOutput::Variables vars(dims, nullptr);
+    declareScalars(vars, decls, "aqh_eval");
     vars.exprVariables(expr); // unknown names are an error (Variable.cpp:1230-1237)
     const size_t ts = vars.typeToBytes(type);
     if (!ts || ts > bytes)
@@ -280,6 +286,132 @@ extern "C" int aqh_eval(int dims, const char* decls, const char* type, const cha
     vars.solve(type, expr, out);
     return 0;
     AQH_CATCH
+}
+
+// The same value through the device evaluator's code path, on the host: every declared 32-bit
+// scalar lives in a table (as the loop scalars of a recorded `while` do), `expr` is compiled by
+// SvmCompiler and run by aqs_run (include/aquasvm.h, the source the one-thread kernel of
+// csrc/devloop.cu is built from)
+namespace {
+struct SvmTable {
+    InputOutput::Variables* vars;
+    std::map<const InputOutput::Variable*, int> slots;
+    static bool resolve(void* user, const std::string& id, CalcServer::SvmCompiler::Slot& out)
+    {
+        SvmTable* T = (SvmTable*)user;
+        InputOutput::Variable* v = T->vars->get(id);
+        unsigned comp = 0;
+        if (!v) {
+            static const char* suf[] = { "_x", "_y", "_z", "_w" };
+            for (unsigned c = 0; c < 4 && !v; c++)
+                if (endswith(id, suf[c])) {
+                    InputOutput::Variable* b = T->vars->get(id.substr(0, id.size() - 2));
+                    if (b && b->ncomp() > c) {
+                        v = b;
+                        comp = c;
+                    }
+                }
+            if (!v)
+                return false;
+        } else if (v->ncomp() != 1)
+            return false;
+        auto it = T->slots.find(v);
+        if (it == T->slots.end())
+            return false;
+        out.offset = it->second + 4 * (int)comp;
+        out.kind = v->kind();
+        return true;
+    }
+};
+} // namespace
+
+extern "C" int aqh_eval_svm(int dims, const char* decls, const char* type, const char* expr,
+                            void* out, size_t bytes)
+{
+    AQH_TRY
+    if (!type || !expr || !out)
+        throw std::runtime_error("aqh_eval_svm: NULL argument");
+    InputOutput::Variables vars(dims, nullptr);
+    declareScalars(vars, decls, "aqh_eval_svm");
+    vars.exprVariables(expr);
+    const size_t ts = vars.typeToBytes(type);
+    if (!ts || ts > bytes || ts > 64)
+        throw std::runtime_error(std::string("aqh_eval_svm: bad type or buffer for \"") + type + "\"");
+    // the result type as the host describes it
+    vars.registerVariable("__aqh_result__", type, "", "");
+    InputOutput::Variable* res = vars.get("__aqh_result__");
+    if (res->kind() != 'f' && res->kind() != 'u' && res->kind() != 'i')
+        throw std::runtime_error("aqh_eval_svm: only 32-bit component types live on the device");
+    SvmTable T{ &vars, {} };
+    int table_bytes = 0;
+    for (auto& v : vars.all())
+        if (!v->isArray() && (v->kind() == 'f' || v->kind() == 'u' || v->kind() == 'i') &&
+            v->typesize() <= 64) {
+            T.slots[v.get()] = table_bytes;
+            table_bytes += 64;
+        }
+    std::vector<char> table(table_bytes, 0);
+    for (auto& kv : T.slots)
+        memcpy(table.data() + kv.second, kv.first->get(), kv.first->typesize());
+    CalcServer::SvmCompiler comp(&vars.tokenizer(), &SvmTable::resolve, &T);
+    const auto parts = split_formulae(expr);
+    const unsigned n = res->ncomp();
+    if (parts.size() < n)
+        throw std::runtime_error("Invalid number of fields in \"" + std::string(expr) + "\"");
+    std::vector<aqs_op> prog;
+    for (unsigned c = 0; c < n; c++)
+        comp.compile(parts[c], prog);
+    const int off = T.slots[res];
+    for (unsigned c = n; c-- > 0;) {
+        aqs_op o;
+        o.code = AQS_STORE;
+        o.a = off + 4 * (int)c;
+        o.b = res->kind();
+        o.c = 0;
+        o.imm = 0.0;
+        prog.push_back(o);
+    }
+    aqs_header hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    aqs_run(prog.data(), (int)prog.size(), table.data(), table_bytes, &hdr, nullptr, 0, 1u);
+    if (hdr.error)
+        throw std::out_of_range("aqh_eval_svm: error " + std::to_string(hdr.error) +
+                                " (the value overflows the variable type)");
+    memcpy(out, table.data() + off, ts);
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" unsigned aqh_device_loops(aqh_sim* sim) { return sim && sim->C ? sim->C->device_loops() : 0; }
+
+extern "C" int aqh_device_loop_stats(aqh_sim* sim, uint64_t* runs, uint64_t* iterations)
+{
+    AQH_TRY
+    uint64_t r = 0, it = 0;
+    for (auto& t : sim->C->tools())
+        if (auto* w = dynamic_cast<CalcServer::While*>(t.get()))
+            if (w->deviceLoop()) {
+                r += w->deviceLoop()->runs();
+                it += w->deviceLoop()->iterations();
+            }
+    if (runs)
+        *runs = r;
+    if (iterations)
+        *iterations = it;
+    return 0;
+    AQH_CATCH
+}
+
+extern "C" const char* aqh_loop_host_reason(aqh_sim* sim, int i)
+{
+    if (!sim || !sim->C || i < 0 || i >= (int)sim->C->tools().size())
+        return nullptr;
+    auto* w = dynamic_cast<CalcServer::While*>(sim->C->tools()[i].get());
+    if (!w)
+        return nullptr;
+    static thread_local std::string why;
+    why = w->deviceLoop() ? "" : w->hostReason();
+    return why.c_str();
 }
 
 extern "C" void aqh_set_script_runner(aqh_script_fn fn, void* user)

@@ -405,6 +405,11 @@ def run_ours(a, rank, world, local_rank):
                    "mean_inner_iterations": inner / a.steps,
                    "first_timed_step": a.pre_steps + a.warmup,
                    "iter_midpoint_max": a.maxiter or 30,
+                   # `while` loops run as a CUDA graph WHILE node from their second pass on
+                   # (host/devloop.hpp; AQUA_DEVICE_LOOPS=0 keeps them on the host), and the passes
+                   # made there since the set-up
+                   "device_loops": {"loops": sim.device_loops(),
+                                    "runs_and_passes": list(sim.device_loop_stats())},
                    "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
                    "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv (halo of r, u, rho, m and of "
                                  "the delta-SPH gradient every sub-iteration), dt and residual all-reduced")

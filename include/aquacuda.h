@@ -292,6 +292,55 @@ int aqc_mpi_sync_stats(const aqc_ctx* ctx, int plan, uint64_t* full, uint64_t* r
 int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, size_t count);
 int aqc_allreduce_host(aqc_ctx* ctx, int op, int type, void* host_inout, size_t count);
 
+/* ---- device-side loops.  The reference evaluates `while` conditions and
+ * set_scalar expressions on the host behind the events of the variables they read
+ * (Conditional.cpp:85-96, SetScalar.cpp:146-195) and reads every reduction back before the host
+ * can decide what to enqueue next (Reduction.cpp:205-258).  A loop object records ONE pass over a
+ * loop body -- every call made on the context between aqc_loop_begin and aqc_loop_end is
+ * captured instead of executed -- as the body of a CUDA graph WHILE node; the scalar tools of the
+ * body are small stack programs (include/aquasvm.h) over a table of typed scalars in device
+ * memory, run by a one-thread kernel, and the program holding AQS_SETCOND sets the node's
+ * condition.  aqc_loop_run uploads the table, launches the graph (entry program -> while (cond)
+ * { body }), downloads header, table and report history, and syncs ONCE, however many
+ * iterations ran.  Only calls that neither synchronise nor read back may be made while a loop
+ * records (kernel launches, fills, device copies, aqc_reduce with out_host == NULL): anything
+ * else fails the recording -- aqc_loop_end then returns an error, nothing has been executed, the
+ * pair caches and watches are invalidated, and the caller runs the loop its old way. ---------- */
+typedef struct aqc_loop aqc_loop;
+struct aqs_op;     /* aquasvm.h */
+struct aqs_header; /* aquasvm.h */
+/* table_bytes: size of the scalar table (multiple of 16); hist_rows: report snapshots kept per run;
+ * max_ops: capacity of the program arena */
+int aqc_loop_create(aqc_ctx* ctx, int table_bytes, int hist_rows, int max_ops, aqc_loop** out);
+int aqc_loop_destroy(aqc_ctx* ctx, aqc_loop* loop);
+/* device address of the table: what aqc_reduce writes to (out_dev) and aqc_launch_ex reads from */
+void* aqc_loop_table(aqc_loop* loop);
+/* starts recording the body; `entry` (n_entry ops, must hold one AQS_SETCOND) is the program run
+ * once before the loop: the `while` tool's condition */
+int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* loop, const struct aqs_op* entry, int n_entry);
+/* queues a scalar program at this point of the body */
+int aqc_loop_svm(aqc_ctx* ctx, aqc_loop* loop, const struct aqs_op* prog, int n);
+/* ends the recording and instantiates the graph.  The body must have queued a program with
+ * AQS_SETCOND (a loop that cannot end is refused). */
+int aqc_loop_end(aqc_ctx* ctx, aqc_loop* loop);
+/* gives a recording up (also what aqc_loop_end does on failure) */
+int aqc_loop_abort(aqc_ctx* ctx, aqc_loop* loop);
+/* table_in: table_bytes of initial values (host).  max_iters bounds the loop (error 0x30000 in
+ * the header when reached).  hdr_out, table_out (table_bytes), hist_out (hist_rows rows of
+ * 16 + table_bytes: tool id, padding, snapshot) are host buffers, any may be NULL.  Syncs once. */
+int aqc_loop_run(aqc_ctx* ctx, aqc_loop* loop, const void* table_in, uint32_t max_iters,
+                 struct aqs_header* hdr_out, void* table_out, void* hist_out);
+/* kernel nodes of the recorded body, and host milliseconds the last recording / instantiation took */
+int aqc_loop_stats(const aqc_loop* loop, int* body_nodes, double* record_ms, double* instantiate_ms);
+/* aqc_launch with scalars that live on the device: dev_scalars[k] != NULL makes the kernel read
+ * scalar argument k from that device address when it RUNS instead of taking the value at args[k]
+ * now (which is then only a fallback value and may be stale) -- what lets a recorded body read a
+ * scalar that the loop itself updates (relax_midpoint of basic/time_scheme/midpoint.cl:141-157).
+ * Only arguments flagged in aqc_kernel_dev_scalars(kernel_id) (bit k) may be bound that way. */
+uint64_t aqc_kernel_dev_scalars(int kernel_id);
+int aqc_launch_ex(aqc_ctx* ctx, int kernel_id, size_t n, void* const* args, int nargs,
+                  const void* const* dev_scalars);
+
 /* ---- measured FP32 (non-tensor) throughput of the device: two register-to-register FMA
  * micro-benchmarks (scalar FFMA and sm_100's packed FFMA2), TFLOP/s with fma = 2 flop.  The
  * denominator of the "% of FP32 peak" figures of the neighbour sweeps (no

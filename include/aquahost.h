@@ -76,6 +76,20 @@ void* aqh_cuda_ctx(aqh_sim* sim);         /* the aqc_ctx* underneath */
 int aqh_eval(int dims, const char* decls, const char* type, const char* expr, void* out,
              size_t bytes);
 
+/* The same value computed the way a recorded loop computes it: `expr` is compiled
+ * into a stack program of include/aquasvm.h over a table holding every declared 32-bit scalar and
+ * run by the interpreter the device kernel is built from -- on the host.  The CPU tests pin it to
+ * aqh_eval bit for bit. */
+int aqh_eval_svm(int dims, const char* decls, const char* type, const char* expr, void* out,
+                 size_t bytes);
+/* `while` loops of the pipeline that run as a CUDA graph from their second pass on
+ * (host/devloop.hpp; AQUA_DEVICE_LOOPS=0: none), how many times they ran on the device and the
+ * passes they made there; why the `while` at tool index i stays on the host ("" when it does not,
+ * NULL when tool i is not a `while`) */
+unsigned aqh_device_loops(aqh_sim* sim);
+int aqh_device_loop_stats(aqh_sim* sim, uint64_t* runs, uint64_t* iterations);
+const char* aqh_loop_host_reason(aqh_sim* sim, int i);
+
 /* type="python" tools (aquagpusph/CalcServer/Python.cpp:295-325).  The reference embeds CPython in
  * its host; this host calls `fn(user, tool name, script path)` instead, once per execution of the
  * tool and after a device sync, and the driving process runs the script's main() with get / set

@@ -275,3 +275,72 @@ def test_whole_kernel_registry_against_the_reference_scripts():
     assert sorted(own) == ["aqua/MPIdeltaSPH.cl::copy_g", "aqua/MPIdeltaSPH.cl::full_lapp",
                            "aqua/MPIdeltaSPH.cl::lapp_corr", "aqua/MPIdeltaSPH.cl::mls",
                            "aqua/MPIdeltaSPH.cl::sort_g", "aqua/diag.cl::count_pairs"], own
+
+
+# ---- device-side loops: the scalar programs (include/aquasvm.h, host/devloop.cpp) ----------------
+def _loop_expressions():
+    """Every set_scalar value, while / if / assert condition of the committed pipelines."""
+    import glob
+    import xml.etree.ElementTree as ET
+    out = set()
+    for f in glob.glob(os.path.join(ROOT, "aquagpusph_b200", "cases_xml", "*.xml")):
+        for t in ET.parse(f).getroot().iter("Tool"):
+            if t.get("type") == "set_scalar":
+                out.add(t.get("value"))
+            elif t.get("type") in ("while", "if", "assert"):
+                out.add(t.get("condition"))
+    return sorted(out)
+
+
+def test_svm_programs_equal_the_host_evaluator():
+    """SvmCompiler + aqs_run (what a recorded `while` runs on the device) give
+    the bits of Variables::solve (SetScalar.cpp:146-195 through Tokenizer::solve): same grammar,
+    double arithmetic one operation at a time, one narrowing per store."""
+    ev, sv = host.evaluate, host.evaluate_svm
+    d = ("float a=3;float b=2;float h=0.0123;float cs=45.5;int i=-7;unsigned int u=4000000000;"
+         "vec v=3.0, 4.0, 5.0, 6.0;float relax=0.75;float r0=1.25e-3;float r1=3.5e-3;float z=0")
+    exprs = ["1/3", "2^3^2", "-2^2", "a < b ? a : b", "(a > 1) && !(b > 5) || 0",
+             "sqrt(16) + abs(-1) + max(1,2,3) + min(4,2)", "2.f * 0.5f", "pi", "7 % 4", "e^a",
+             "0.25*h/cs", "i*h", "u/3", "v_x*v_y - v_z/v_w", "a - b - 1", "a / b / 3", "a - -b",
+             "!a", "!z + !(a != 3)", "a <= 3 == 1", "r1 / r0 > 0.9 ? 0.5 + (1.0 - 0.5) * relax : relax",
+             "i == 0 ? 1.0 : relax", "r1 < 1e-2 ? 30 : i", "pow(a, b) + log(a) + ln(a) + log2(a) + log10(a)",
+             "floor(-1.5) + ceil(1.2) + round(2.5) + rint(3.5) + sign(-a) + sign(z)",
+             "sin(a) + cos(b) + tan(h) + asin(0.5) + acos(0.5) + atan(a) + atan2(a, b)",
+             "sinh(h) + cosh(h) + tanh(a) + exp(-b)", "avg(a, b, 4) + sum(a, b)", "a > b > 0",
+             "a*b+h*cs", "h*cs+a*b", "(a+b)*(a-b)/(h+cs)", "1.e-8 + 2.E+3f", "+a", "-(-a)", "a != b != 0"]
+    for x in exprs + _loop_expressions():
+        names = set(re.findall(r"[A-Za-z_]\w*", x))
+        dd = d
+        for n in sorted(names - set("a b h cs i u v relax r0 r1 z pi e".split())):
+            if re.search(r"\b%s\s*\(" % n, x) or n[:-2] == "v" or n in ("f", "E"):
+                continue
+            dd += ";float %s=%r" % (n, 0.3 + 0.001 * (sum(map(ord, n)) % 977))
+        for ty, dt in (("float", np.float32), ("int", np.int32)):
+            try:
+                want = ev(x, ty, dd, dtype=dt)
+            except host.HostError:
+                with pytest.raises(host.HostError):
+                    sv(x, ty, dd, dtype=dt)
+                continue
+            got = sv(x, ty, dd, dtype=dt)
+            assert want.tobytes() == got.tobytes() or (np.isnan(want) and np.isnan(got)), (x, ty, want, got)
+    # vector values: every component sees the OLD variable (Variables::solve stores at the end)
+    for x in ("v_y,v_x,v_z,v_w", "v_x * h,v_y / h,v_z,v_w"):
+        assert ev(x, "vec", d, n=4).tobytes() == sv(x, "vec", d, n=4).tobytes()
+    assert sv("1,2", "vec", dims=2, n=2).tolist() == [1.0, 2.0]
+    assert sv("7.9", "unsigned int", dtype=np.uint32) == 7
+    nc = sv("n_x*n_y, 2, 3, n_w", "uivec4", "uivec4 n=4,5,6,120", dtype=np.uint32, n=4)
+    assert list(nc) == [20, 2, 3, 120]
+    # the same errors
+    with pytest.raises(host.HostError, match="Invalid number of fields"):
+        sv("1,2", "vec", dims=3, n=4)
+    with pytest.raises(host.HostError, match="cannot be found"):
+        sv("2*nope")
+    with pytest.raises(host.HostError):
+        sv("2*(3")
+    with pytest.raises(host.HostError, match="overflows"):
+        sv("-1", "unsigned int", dtype=np.uint32)
+    with pytest.raises(host.HostError, match="overflows"):
+        sv("3e9", "int", dtype=np.int32)
+    with pytest.raises(host.HostError, match="expects 2 arguments"):
+        sv("atan2(1)")
