@@ -30,7 +30,7 @@ SYMBOLS = [
     "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_pairs_cache_stats_remote", "aqc_fp32_peak",
     "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
     "aqc_loop_create", "aqc_loop_destroy", "aqc_loop_table", "aqc_loop_begin", "aqc_loop_svm",
-    "aqc_loop_end", "aqc_loop_abort", "aqc_loop_run", "aqc_loop_stats", "aqc_kernel_dev_scalars",
+    "aqc_loop_end", "aqc_loop_abort", "aqc_loop_run", "aqc_loop_start", "aqc_loop_stats", "aqc_kernel_dev_scalars",
     "aqc_launch_ex",
 ]
 
@@ -65,7 +65,7 @@ class AqsHeader(C.Structure):
 
 (AQS_IMM, AQS_LOAD, AQS_STORE, AQS_ADD, AQS_SUB, AQS_MUL, AQS_DIV, AQS_MOD, AQS_POW, AQS_NEG, AQS_NOT,
  AQS_LT, AQS_GT, AQS_LE, AQS_GE, AQS_EQ, AQS_NE, AQS_AND, AQS_OR, AQS_SELECT, AQS_CALL, AQS_FOLD,
- AQS_SNAP, AQS_ASSERT, AQS_SETCOND) = range(25)
+ AQS_SNAP, AQS_ASSERT, AQS_SETCOND, AQS_RECOND) = range(26)
 
 
 def aqs_program(ops):
@@ -170,6 +170,7 @@ def lib():
     L.aqc_loop_abort.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_loop_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(AqsHeader),
                                C.c_void_p, C.c_void_p]
+    L.aqc_loop_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     L.aqc_loop_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double)]
     L.aqc_kernel_dev_scalars.argtypes = [C.c_int]
@@ -584,14 +585,25 @@ class DeviceLoop:
     def abort(self):
         self.ctx._chk(lib().aqc_loop_abort(self.ctx.h, self.h))
 
-    def run(self, table, max_iters=1000):
-        """-> (header, table bytes as uint8 array, history rows [(tool id, table bytes), ...])."""
-        tab = np.ascontiguousarray(np.frombuffer(bytes(table), np.uint8)).copy()
+    def start(self, table, max_iters=1000):
+        """Upload the table: programs queued with svm() before begin() now run at once."""
+        tab = np.frombuffer(bytes(table), np.uint8).copy()
         assert tab.nbytes == self.table_bytes
+        self.ctx._chk(lib().aqc_loop_start(self.ctx.h, self.h, tab.ctypes.data, max_iters))
+
+    def run(self, table=None, max_iters=1000):
+        """-> (header, table bytes as uint8 array, history rows [(tool id, table bytes), ...]).
+        table=None: the table start() uploaded, as the programs run since left it."""
+        if table is None:
+            tab = None
+        else:
+            tab = np.frombuffer(bytes(table), np.uint8).copy()
+            assert tab.nbytes == self.table_bytes
         hdr = AqsHeader()
         out = np.zeros(self.table_bytes, np.uint8)
         hist = np.zeros(max(1, self.hist_rows) * (16 + self.table_bytes), np.uint8)
-        self.ctx._chk(lib().aqc_loop_run(self.ctx.h, self.h, tab.ctypes.data, max_iters, C.byref(hdr),
+        self.ctx._chk(lib().aqc_loop_run(self.ctx.h, self.h, tab.ctypes.data if tab is not None else None,
+                                         max_iters, C.byref(hdr),
                                          out.ctypes.data, hist.ctypes.data if self.hist_rows else None))
         rows = []
         for k in range(min(hdr.snaps, self.hist_rows)):

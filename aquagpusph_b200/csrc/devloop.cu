@@ -33,7 +33,9 @@ struct aqc_loop {
     cudaGraph_t body = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaGraphConditionalHandle handle = 0;
+    int arena_graph_from = 0;     // first op of the recorded programs (direct ones sit in front)
     bool recording = false, ready = false, body_has_cond = false;
+    bool started = false;         // aqc_loop_start uploaded the table: aqc_loop_run(table_in = NULL) may follow
     uint64_t launches_at_begin = 0, body_launches = 0;
     int body_nodes = 0;
     double record_ms = 0.0, instantiate_ms = 0.0;
@@ -60,7 +62,7 @@ svm_kernel(const aqs_op* __restrict__ prog, int n, char* __restrict__ base, int 
 bool has_setcond(const aqs_op* prog, int n)
 {
     for (int k = 0; k < n; k++)
-        if (prog[k].code == AQS_SETCOND)
+        if (prog[k].code == AQS_SETCOND || prog[k].code == AQS_RECOND)
             return true;
     return false;
 }
@@ -143,21 +145,24 @@ extern "C" int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* L, const aqs_op* entry, in
         return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_begin: a loop is already being recorded");
     if (!has_setcond(entry, n_entry))
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_begin: the entry program holds no AQS_SETCOND");
-    if (n_entry > L->max_ops)
+    if (!L->started)
+        L->arena_used = 0; // (programs run directly since aqc_loop_start stay where they are)
+    if (L->arena_used + n_entry > L->max_ops)
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_begin: program arena too small");
     L->t_begin = std::chrono::steady_clock::now();
     // the previous graph may still be referenced by nothing: aqc_loop_run synchronises
     drop_graph(L);
-    L->arena_used = 0;
     L->body_has_cond = false;
-    memcpy(L->arena_host, entry, (size_t)n_entry * sizeof(aqs_op));
-    L->arena_used = n_entry;
+    const int entry_at = L->arena_used;
+    memcpy(L->arena_host + entry_at, entry, (size_t)n_entry * sizeof(aqs_op));
+    L->arena_used += n_entry;
+    L->arena_graph_from = entry_at;
 
     AQC_CUDA(ctx, cudaGraphCreate(&L->graph, 0));
     // the default value only matters if the entry program did not run: never
     AQC_CUDA(ctx, cudaGraphConditionalHandleCreate(&L->handle, L->graph, 0, cudaGraphCondAssignDefault));
     // entry program node
-    const aqs_op* prog = L->arena_dev;
+    const aqs_op* prog = L->arena_dev + entry_at;
     int n = n_entry, tb = L->table_bytes, hr = L->hist_rows, hc = 1;
     char* base = L->dev;
     const uint32_t* mi = L->max_iters_dev;
@@ -191,11 +196,21 @@ extern "C" int aqc_loop_svm(aqc_ctx* ctx, aqc_loop* L, const aqs_op* prog, int n
 {
     if (!ctx || !L || !prog || n <= 0)
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_svm: bad argument");
-    if (!L->recording)
-        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_svm: the loop is not being recorded");
+    if (ctx->recording && ctx->recording != L)
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_svm: another loop is being recorded");
     if (L->arena_used + n > L->max_ops)
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_svm: program arena full (%d ops)", L->max_ops);
     memcpy(L->arena_host + L->arena_used, prog, (size_t)n * sizeof(aqs_op));
+    if (!L->recording) {
+        // direct: the program runs now (no graph, so no condition to set)
+        AQC_CUDA(ctx, cudaMemcpyAsync(L->arena_dev + L->arena_used, L->arena_host + L->arena_used,
+                                      (size_t)n * sizeof(aqs_op), cudaMemcpyHostToDevice, ctx->stream));
+        svm_kernel<<<1, 32, 0, ctx->stream>>>(L->arena_dev + L->arena_used, n, L->dev, L->table_bytes,
+                                              L->hist_rows, 0, 0, L->max_iters_dev);
+        L->arena_used += n;
+        AQC_LAUNCH_CHECK(ctx);
+        return AQC_OK;
+    }
     const int hc = has_setcond(prog, n) ? 1 : 0;
     svm_kernel<<<1, 32, 0, ctx->stream>>>(L->arena_dev + L->arena_used, n, L->dev, L->table_bytes,
                                           L->hist_rows, L->handle, hc, L->max_iters_dev);
@@ -261,19 +276,19 @@ extern "C" int aqc_loop_end(aqc_ctx* ctx, aqc_loop* L)
     L->instantiate_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     // the programs travel behind whatever is queued, in front of the launch
-    AQC_CUDA(ctx, cudaMemcpyAsync(L->arena_dev, L->arena_host, (size_t)L->arena_used * sizeof(aqs_op),
+    AQC_CUDA(ctx, cudaMemcpyAsync(L->arena_dev + L->arena_graph_from, L->arena_host + L->arena_graph_from,
+                                  (size_t)(L->arena_used - L->arena_graph_from) * sizeof(aqs_op),
                                   cudaMemcpyHostToDevice, ctx->stream));
     L->ready = true;
     return AQC_OK;
 }
 
-extern "C" int aqc_loop_run(aqc_ctx* ctx, aqc_loop* L, const void* table_in, uint32_t max_iters,
-                            aqs_header* hdr_out, void* table_out, void* hist_out)
+extern "C" int aqc_loop_start(aqc_ctx* ctx, aqc_loop* L, const void* table_in, uint32_t max_iters)
 {
     if (!ctx || !L || !table_in)
-        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_run: bad argument");
-    if (!L->ready)
-        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_run: no recorded body");
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_start: bad argument");
+    if (ctx->recording)
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_start: a loop is being recorded");
     const size_t head = sizeof(aqs_header) + (size_t)L->table_bytes;
     // (the pinned mirror is free: the previous run synchronised)
     memset(L->host, 0, sizeof(aqs_header));
@@ -282,11 +297,41 @@ extern "C" int aqc_loop_run(aqc_ctx* ctx, aqc_loop* L, const void* table_in, uin
     *mi_host = max_iters;
     AQC_CUDA(ctx, cudaMemcpyAsync(L->max_iters_dev, mi_host, 4, cudaMemcpyHostToDevice, ctx->stream));
     AQC_CUDA(ctx, cudaMemcpyAsync(L->dev, L->host, head, cudaMemcpyHostToDevice, ctx->stream));
-    AQC_CUDA(ctx, cudaGraphLaunch(L->exec, ctx->stream));
+    L->arena_used = 0;
+    L->started = true;
+    L->ready = false; // a body recorded for other values is not the one to launch
+    return AQC_OK;
+}
+
+extern "C" int aqc_loop_run(aqc_ctx* ctx, aqc_loop* L, const void* table_in, uint32_t max_iters,
+                            aqs_header* hdr_out, void* table_out, void* hist_out)
+{
+    if (!ctx || !L)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_run: bad argument");
+    if (ctx->recording)
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_run: a loop is being recorded");
+    if (table_in) {
+        if (!L->ready)
+            return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_run: no recorded body");
+        const bool ready = L->ready;
+        const int used = L->arena_used;
+        const int rc = aqc_loop_start(ctx, L, table_in, max_iters);
+        L->ready = ready;      // the same recording, other initial values
+        L->arena_used = used;
+        if (rc)
+            return rc;
+    } else if (!L->started) {
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_run: neither a table nor aqc_loop_start");
+    }
+    const size_t head = sizeof(aqs_header) + (size_t)L->table_bytes;
+    if (L->ready)
+        AQC_CUDA(ctx, cudaGraphLaunch(L->exec, ctx->stream));
     AQC_CUDA(ctx, cudaMemcpyAsync(L->host, L->dev, L->dev_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     AQC_SYNC(ctx);
+    L->started = false;
     const aqs_header* h = (const aqs_header*)L->host;
-    ctx->launches += 1 + (uint64_t)h->iters * L->body_launches;
+    if (L->ready) // the entry program + the passes the graph made: one per condition that came out true
+        ctx->launches += 1 + (uint64_t)h->iters * L->body_launches; // (a first pass run directly counted itself)
     if (hdr_out)
         *hdr_out = *h;
     if (table_out)

@@ -402,6 +402,31 @@ extern "C" int aqh_device_loop_stats(aqh_sim* sim, uint64_t* runs, uint64_t* ite
     AQH_CATCH
 }
 
+extern "C" int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* record_ms, double* instantiate_ms)
+{
+    AQH_TRY
+    int n = 0;
+    double r = 0.0, i = 0.0;
+    for (auto& t : sim->C->tools())
+        if (auto* w = dynamic_cast<CalcServer::While*>(t.get()))
+            if (w->deviceLoop()) {
+                int n1;
+                double r1, i1;
+                w->deviceLoop()->timing(n1, r1, i1);
+                n += n1;
+                r += r1;
+                i += i1;
+            }
+    if (body_nodes)
+        *body_nodes = n;
+    if (record_ms)
+        *record_ms = r;
+    if (instantiate_ms)
+        *instantiate_ms = i;
+    return 0;
+    AQH_CATCH
+}
+
 extern "C" const char* aqh_loop_host_reason(aqh_sim* sim, int i)
 {
     if (!sim || !sim->C || i < 0 || i >= (int)sim->C->tools().size())

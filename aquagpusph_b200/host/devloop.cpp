@@ -462,20 +462,29 @@ void DeviceLoop::flush()
     _pending.clear();
 }
 
-void DeviceLoop::record()
+void DeviceLoop::pass()
 {
+    // one pass over the body through the tools' record(): queued while the loop records, run at
+    // once (in stream order, nothing read back) otherwise
     auto& tools = _C->tools();
     std::vector<aqs_op> cond;
     compile(_condition, cond);
     cond.push_back(mk(AQS_SETCOND));
-    if (aqc_loop_begin(_C->ctx(), _loop, cond.data(), (int)cond.size()))
+    _pending.clear();
+    for (size_t i = _first; i < _last; i++)
+        tools[i]->record(*this);
+    emit(cond);
+    flush();
+}
+
+void DeviceLoop::record()
+{
+    // the graph starts from the condition the pass before it left in the header
+    const aqs_op entry = mk(AQS_RECOND);
+    if (aqc_loop_begin(_C->ctx(), _loop, &entry, 1))
         throw std::runtime_error(aqc_last_error(_C->ctx()));
     try {
-        _pending.clear();
-        for (size_t i = _first; i < _last; i++)
-            tools[i]->record(*this);
-        emit(cond);
-        flush();
+        pass();
     } catch (...) {
         aqc_loop_abort(_C->ctx(), _loop);
         throw;
@@ -490,32 +499,41 @@ bool DeviceLoop::run()
         return false;
     auto& tools = _C->tools();
     Variables* vars = _C->variables();
+    std::vector<char> table(_initial);
+    for (auto v : _order)
+        memcpy(table.data() + _slots[v], v->get(), v->typesize());
+    if (aqc_loop_start(_C->ctx(), _loop, table.data(), _max_iters))
+        throw std::runtime_error(aqc_last_error(_C->ctx()));
+    // the first pass, tool by tool: it builds the neighbour lists and sizes every scratch buffer.
+    // Its reductions and scalar tools already work on the device table, so nothing is read back
+    // and the device is still busy with it while the body is recorded and instantiated below
+    pass();
+    bool recorded = true;
     try {
         record();
     } catch (std::exception& e) {
-        // nothing ran; the caches the recording touched were invalidated by the library
+        // nothing of the recording ran; the caches it touched were invalidated by the library
+        recorded = false;
         _failures++;
         log(_failures == 1 ? L_WARNING : L_DEBUG,
             "The loop \"" + _opener->name() + "\" could not be recorded (" + e.what() +
-                "): this pass runs on the host\n");
+                "): it goes on tool by tool\n");
         if (_failures >= 3) {
             log(L_WARNING, "The loop \"" + _opener->name() + "\" stays on the host from now on\n");
             _usable = false;
         }
-        return false;
     }
-    _failures = 0;
-    std::vector<char> table(_initial);
-    for (auto v : _order)
-        memcpy(table.data() + _slots[v], v->get(), v->typesize());
+    if (recorded)
+        _failures = 0;
     aqs_header hdr;
     std::vector<char> hist((size_t)_hist_rows * (16 + (size_t)_table_bytes));
-    if (aqc_loop_run(_C->ctx(), _loop, table.data(), _max_iters, &hdr, table.data(),
+    if (aqc_loop_run(_C->ctx(), _loop, nullptr, _max_iters, &hdr, table.data(),
                      hist.empty() ? nullptr : hist.data()))
         throw std::runtime_error("Failure running the loop \"" + _opener->name() +
                                  "\" on the device: " + aqc_last_error(_C->ctx()));
+    const unsigned passes = 1 + (recorded ? hdr.iters : 0);
     _runs++;
-    _iterations += hdr.iters;
+    _iterations += passes;
     // reports, in the order they happened, each seeing the scalars of its moment
     auto load = [&](const char* tab) {
         for (auto v : _order) {
@@ -539,7 +557,7 @@ bool DeviceLoop::run()
     load(table.data());
     for (size_t i = _first; i < _last; i++)
         if (!dynamic_cast<Report*>(tools[i].get()))
-            tools[i]->account(hdr.iters);
+            tools[i]->account(passes);
     if (hdr.error) {
         const std::string where = "the loop \"" + _opener->name() + "\" (device side)";
         if (hdr.error >= 0x40000u)
@@ -557,7 +575,7 @@ bool DeviceLoop::run()
         }
         throw std::runtime_error("A value computed in " + where + " overflows its variable type");
     }
-    return true;
+    return recorded;
 }
 
 // ------------------------------------------------- the tools' side of it --
@@ -619,7 +637,8 @@ void Kernel::record(DeviceLoop& L)
 {
     if (_leader)
         return;
-    L.flush();
+    // (scalar programs queued so far run in front of the next kernel that READS the table: the
+    // order among programs is what matters to them, and nothing else touches the table)
     if (_fused_id >= 0) {
         _execute();
         return;
@@ -635,12 +654,14 @@ void Kernel::record(DeviceLoop& L)
             any = true;
         }
     }
+    if (any)
+        L.flush();
     check(aqc_launch_ex(_C->ctx(), _kid, N, args.data(), (int)args.size(), any ? dev.data() : nullptr));
 }
 
 void Copy::record(DeviceLoop& L)
 {
-    L.flush();
+    (void)L;
     _execute();
 }
 
@@ -661,7 +682,7 @@ bool Set::recordable(const DeviceLoop& L, std::string& why) const
 
 void Set::record(DeviceLoop& L)
 {
-    L.flush();
+    (void)L;
     _execute();
 }
 
@@ -718,7 +739,6 @@ bool Reduction::recordable(const DeviceLoop& L, std::string& why) const
 
 void Reduction::record(DeviceLoop& L)
 {
-    L.flush();
     const int raw = L.scratch(this, 0), ident = L.scratch(this, 1);
     check(aqc_reduce(_C->ctx(), _op, _atype, _in->dptr(), _in->length(), L.scratchDevice(raw), nullptr));
     // fold the user's null value in, in the array's own arithmetic (Reduction::_execute)
@@ -769,18 +789,25 @@ void While::planDeviceLoop()
         log(L_INFO, "The loop \"" + name() + "\" runs on the host: " + _why + "\n");
         return;
     }
-    log(L_INFO, "The loop \"" + name() + "\" runs on the device from its second pass on (" +
-                    std::to_string(last - first) + " tools recorded as a CUDA graph while-node)\n");
+    log(L_INFO, "The loop \"" + name() + "\" runs on the device (" + std::to_string(last - first) +
+                    " tools: first pass tool by tool without read-backs, the rest as a CUDA graph "
+                    "while-node)\n");
 }
 
 void While::_execute()
 {
     const bool again = _reentry;
     _reentry = false;
-    if (again && _dev && _dev->usable() && _dev->run()) {
+    Conditional::_execute();
+    if (again || !_result || !_dev || !_dev->usable())
+        return;
+    // entering the loop: all of it on the device
+    if (_dev->run()) {
         _result = false; // the loop is over: on to the tool behind its `end`
         return;
     }
+    // the body could not be recorded: its first pass did run (on device-resident scalars, now back
+    // on the host) and the loop goes on tool by tool from its condition
     Conditional::_execute();
 }
 

@@ -13,9 +13,12 @@
 //   * kernels that read a scalar the loop writes take it from the table (aqc_launch_ex),
 //   * report tools snapshot the table; the host prints the snapshots when the loop is over.
 // The first pass of every loop still runs tool by tool (it is the pass that builds the neighbour
-// lists and sizes every scratch buffer); the graph takes over at the first `end`.  A body that
-// cannot be recorded -- link-list, mpi-sync, python, nested conditionals, 64-bit scalars, or a
-// recording that fails at run time -- stays on the host path, unchanged.
+// lists and sizes every scratch buffer), but already on the device table: nothing is read back, so
+// the device is busy with it while the host records and instantiates the body for the passes that
+// follow; the graph starts from the condition the first pass left.  One synchronisation per loop.
+// A body that cannot be recorded -- link-list, mpi-sync, python, nested conditionals, 64-bit
+// scalars -- stays on the host path, unchanged; a recording that fails at run time hands the
+// scalars back after the first pass and the loop goes on tool by tool.
 #pragma once
 #include <map>
 #include <string>
@@ -62,11 +65,21 @@ class DeviceLoop {
     /// Classify the body and lay the table out.  false: the loop stays on the host (`why` says)
     bool plan(std::string& why);
     bool usable() const { return _usable; }
-    /// Run the loop from its condition on: true when it is over (variables updated, reports
-    /// printed); false when nothing ran and the host has to carry on tool by tool
+    /// Run the loop (the host found its condition true): true when it is over (variables updated,
+    /// reports printed); false when only the first pass ran and the host has to carry on tool by
+    /// tool from the condition
     bool run();
     uint64_t runs() const { return _runs; }
     uint64_t iterations() const { return _iterations; }
+    /// kernel / copy / memset nodes of the recorded body, host milliseconds of the last recording
+    /// and of the last instantiation
+    void timing(int& body_nodes, double& record_ms, double& instantiate_ms) const
+    {
+        body_nodes = 0;
+        record_ms = instantiate_ms = 0.0;
+        if (_loop)
+            aqc_loop_stats(_loop, &body_nodes, &record_ms, &instantiate_ms);
+    }
 
     // ---- what the tools see while they are asked (recordable) or recorded (record)
     bool contains(const Tool* t) const;
@@ -90,6 +103,7 @@ class DeviceLoop {
 
   private:
     static bool resolve(void* user, const std::string& id, SvmCompiler::Slot& out);
+    void pass();
     void record();
     CalcServer* _C;
     Tool* _opener;

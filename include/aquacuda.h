@@ -318,15 +318,24 @@ void* aqc_loop_table(aqc_loop* loop);
 /* starts recording the body; `entry` (n_entry ops, must hold one AQS_SETCOND) is the program run
  * once before the loop: the `while` tool's condition */
 int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* loop, const struct aqs_op* entry, int n_entry);
-/* queues a scalar program at this point of the body */
+/* while the loop records: queues a scalar program at this point of the body.  Otherwise the program
+ * RUNS now, in stream order, on the table aqc_loop_start uploaded: the way a caller makes the first
+ * pass of a loop tool by tool (the pass that builds neighbour lists and sizes scratch buffers)
+ * without reading anything back, so that the device is still busy with it while the body is
+ * recorded and instantiated. */
 int aqc_loop_svm(aqc_ctx* ctx, aqc_loop* loop, const struct aqs_op* prog, int n);
+/* clears the header and uploads the table (table_bytes of initial values, host) for programs run
+ * directly and for an aqc_loop_run with table_in == NULL.  Not while recording. */
+int aqc_loop_start(aqc_ctx* ctx, aqc_loop* loop, const void* table_in, uint32_t max_iters);
 /* ends the recording and instantiates the graph.  The body must have queued a program with
  * AQS_SETCOND (a loop that cannot end is refused). */
 int aqc_loop_end(aqc_ctx* ctx, aqc_loop* loop);
 /* gives a recording up (also what aqc_loop_end does on failure) */
 int aqc_loop_abort(aqc_ctx* ctx, aqc_loop* loop);
-/* table_in: table_bytes of initial values (host).  max_iters bounds the loop (error 0x30000 in
- * the header when reached).  hdr_out, table_out (table_bytes), hist_out (hist_rows rows of
+/* table_in: table_bytes of initial values (host), or NULL: header and table stay as aqc_loop_start
+ * and the programs run since left them (max_iters is then the one given there).  When no body is
+ * recorded (the recording failed) only the download happens.  max_iters bounds the loop (error
+ * 0x30000 in the header when reached).  hdr_out, table_out (table_bytes), hist_out (hist_rows rows of
  * 16 + table_bytes: tool id, padding, snapshot) are host buffers, any may be NULL.  Syncs once. */
 int aqc_loop_run(aqc_ctx* ctx, aqc_loop* loop, const void* table_in, uint32_t max_iters,
                  struct aqs_header* hdr_out, void* table_out, void* hist_out);

@@ -89,6 +89,9 @@ int aqh_eval_svm(int dims, const char* decls, const char* type, const char* expr
 unsigned aqh_device_loops(aqh_sim* sim);
 int aqh_device_loop_stats(aqh_sim* sim, uint64_t* runs, uint64_t* iterations);
 const char* aqh_loop_host_reason(aqh_sim* sim, int i);
+/* graph nodes of the recorded bodies, host milliseconds the last recording and the last
+ * cudaGraphInstantiate took (summed over the loops): the per-step host cost of the device loops */
+int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* record_ms, double* instantiate_ms);
 
 /* type="python" tools (aquagpusph/CalcServer/Python.cpp:295-325).  The reference embeds CPython in
  * its host; this host calls `fn(user, tool name, script path)` instead, once per execution of the

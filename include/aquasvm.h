@@ -38,8 +38,10 @@ enum {
                       imm packs op (AQC_OP_*), kind and ncomp: op + 4 * kindcode + 16 * ncomp */
     AQS_SNAP,      /* report tool `a`: append the table to the history */
     AQS_ASSERT,    /* pop, narrowed to int like the host's solve("int"); zero -> error code 0x10000 + a */
-    AQS_SETCOND    /* pop, narrowed to int -> loop condition; a true one counts one iteration (the
+    AQS_SETCOND,   /* pop, narrowed to int -> loop condition; a true one counts one iteration (the
                       body runs next), and ends the loop with error 0x30000 at max_iters */
+    AQS_RECOND     /* loop condition = the one the last AQS_SETCOND left in the header (nothing is
+                      counted): the entry program of a loop whose first pass ran before the graph */
 };
 
 enum {
@@ -267,6 +269,7 @@ AQS_HD int aqs_run(const aqs_op* prog, int n, char* tab, int table_bytes, aqs_he
                 hdr->cond = (uint32_t)cond;
                 break;
             }
+            case AQS_RECOND: cond = (hdr->cond != 0 && !hdr->error) ? 1 : 0; break;
             default: break;
         }
     }

@@ -15,7 +15,7 @@ import pytest
 
 from aquagpusph_b200 import _lib, cases, casegen, host
 from aquagpusph_b200._lib import (AQS_ADD, AQS_FOLD, AQS_IMM, AQS_LOAD, AQS_LT, AQS_MUL, AQS_SETCOND,
-                                  AQS_SNAP, AQS_STORE, AQS_ASSERT)
+                                  AQS_SNAP, AQS_STORE, AQS_ASSERT, AQS_RECOND)
 
 pytestmark = pytest.mark.gpu
 
@@ -98,6 +98,37 @@ def test_loop_c_abi_counts_reduces_and_reads_scalars_on_the_device():
     assert hdr.iters == 2 and struct.unpack_from("<f", out, 16)[0] == 4.0
     hdr, out, rows = loop.run(tab, max_iters=3)
     assert hdr.iters == 3 and hdr.error == 0x30000
+    loop.close()
+    # the way the host drives it: the first pass runs directly on the uploaded table (nothing read
+    # back), the graph starts from the condition that pass left
+    loop = ctx.loop(len(tab), hist_rows=8)
+    body = [(AQS_FOLD, 32, 48, 64, _lib.OP_SUM + 4 * 0 + 16 * 1),
+            (AQS_LOAD, 0, "u"), (AQS_IMM, 0, 0, 0, 1), (AQS_ADD,), (AQS_STORE, 0, "u"), (AQS_SNAP, 9)] + cond
+    before = ctx.launch_count()
+    loop.start(tab)
+    for recording in (False, True):
+        if recording:
+            loop.begin([(AQS_RECOND,)])
+        ctx.fill(b, np.float32(3.0).tobytes())
+        ctx.reduce(_lib.OP_SUM, a, out_dev=_Ptr(loop.table() + 48), host=False)
+        loop.svm(body)
+        if recording:
+            loop.end()
+    assert ctx.launch_count() - before == 4      # the direct pass only
+    hdr, out, rows = loop.run()
+    assert (hdr.iters, hdr.snaps, hdr.error, hdr.cond) == (4, 5, 0, 0)      # 1 direct + 4 graph passes
+    assert struct.unpack_from("<I", out, 0)[0] == 5 and struct.unpack_from("<f", out, 32)[0] == S
+    assert [struct.unpack_from("<I", r[1], 0)[0] for r in rows] == [1, 2, 3, 4, 5]
+    assert ctx.launch_count() - before == 4 + 1 + 4 * 4
+    # a recording that failed: run() hands back what the direct pass left
+    loop.start(tab)
+    loop.svm(body)
+    loop.begin([(AQS_RECOND,)])
+    with pytest.raises(_lib.AquaError, match="synchronises"):
+        ctx.reduce(_lib.OP_SUM, a)
+    loop.abort()
+    hdr, out, rows = loop.run()
+    assert (hdr.iters, hdr.snaps, hdr.cond) == (1, 1, 1) and struct.unpack_from("<I", out, 0)[0] == 1
     loop.close()
     ctx.close()
 
@@ -190,11 +221,9 @@ def test_dam_break_midpoint_loop_on_the_device_equals_the_host_loop(n, maxiter, 
     assert H["per_step"] == D["per_step"]
     assert H["report"] is not None and H["report"] == D["report"]
     # it did run there: once per step, every pass but the first
-    runs, iters = D["stats"]
-    passes = sum(p[0] for p in D["per_step"])   # iter_midpoint ends at iter_midpoint_max = passes + 0
-    assert runs == 5 and iters >= 5
     assert H["used"] == D["used"], {k: (H["used"][k], D["used"][k]) for k in H["used"] if H["used"][k] != D["used"][k]}
-    assert passes >= 10
+    # it did run there: once per step, every pass of it
+    assert D["stats"] == (5, D["used"]["midpoint relax"]) and D["used"]["midpoint relax"] >= 10
 
 
 def test_tld_midpoint_loop_on_the_device_equals_the_host_loop(monkeypatch):
@@ -211,5 +240,5 @@ def test_tld_midpoint_loop_on_the_device_equals_the_host_loop(monkeypatch):
                  "Force_elastic"))
     assert H["per_step"] == D["per_step"] and [p[0] for p in D["per_step"]] == [5, 5, 5]
     assert H["report"] == D["report"]
-    assert D["stats"] == (3, 12)            # passes 2..5 of every step
+    assert D["stats"] == (3, 15)            # five passes in every step
     assert H["used"] == D["used"]
