@@ -16,6 +16,7 @@
 // (cudaStreamBeginCaptureToGraph, relaxed mode: allocations made by a launcher on first use are
 // legal, anything that synchronises fails the capture and thereby the recording).
 #include <chrono>
+#include <stdlib.h>
 
 #include "aqc_common.cuh"
 #include "aquasvm.h"
@@ -152,6 +153,7 @@ extern "C" int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* L, const aqs_op* entry, in
     L->t_begin = std::chrono::steady_clock::now();
     // the previous graph may still be referenced by nothing: aqc_loop_run synchronises
     drop_graph(L);
+    const auto t_drop = std::chrono::steady_clock::now();
     L->body_has_cond = false;
     const int entry_at = L->arena_used;
     memcpy(L->arena_host + entry_at, entry, (size_t)n_entry * sizeof(aqs_op));
@@ -189,6 +191,12 @@ extern "C" int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* L, const aqs_op* entry, in
     L->recording = true;
     ctx->recording = L;
     L->launches_at_begin = ctx->launches;
+    if (getenv("AQC_LOOP_DEBUG")) {
+        const auto t_cap = std::chrono::steady_clock::now();
+        fprintf(stderr, "aqc_loop_begin: drop %.3f ms, graph + capture start %.3f ms\n",
+                std::chrono::duration<double, std::milli>(t_drop - L->t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_cap - t_drop).count());
+    }
     return AQC_OK;
 }
 
@@ -248,7 +256,12 @@ extern "C" int aqc_loop_end(aqc_ctx* ctx, aqc_loop* L)
         return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_end: the body never sets the loop condition");
     }
     cudaGraph_t g = nullptr;
+    const auto t_e0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (getenv("AQC_LOOP_DEBUG"))
+        fprintf(stderr, "aqc_loop_end: body recorded in %.3f ms since begin, end capture %.3f ms\n",
+                std::chrono::duration<double, std::milli>(t_e0 - L->t_begin).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_e0).count());
     L->recording = false;
     ctx->recording = nullptr;
     L->body_launches = ctx->launches - L->launches_at_begin;
@@ -330,7 +343,14 @@ extern "C" int aqc_loop_run(aqc_ctx* ctx, aqc_loop* L, const void* table_in, uin
     AQC_SYNC(ctx);
     L->started = false;
     const aqs_header* h = (const aqs_header*)L->host;
-    if (L->ready) // the entry program + the passes the graph made: one per condition that came out true
+    const bool ran = L->ready;
+    // a graph recorded for the table aqc_loop_start uploaded is used once (the scalars baked into
+    // its kernels belong to this time step): released now, while the device is idle anyway --
+    // destroying an executable graph can synchronise the device, which in front of the next
+    // recording would wait for the pass that is running
+    if (!table_in)
+        drop_graph(L);
+    if (ran) // the entry program + the passes the graph made: one per condition that came out true
         ctx->launches += 1 + (uint64_t)h->iters * L->body_launches; // (a first pass run directly counted itself)
     if (hdr_out)
         *hdr_out = *h;
