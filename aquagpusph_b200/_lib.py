@@ -31,7 +31,7 @@ SYMBOLS = [
     "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
     "aqc_loop_create", "aqc_loop_destroy", "aqc_loop_table", "aqc_loop_begin", "aqc_loop_svm",
     "aqc_loop_end", "aqc_loop_abort", "aqc_loop_run", "aqc_loop_start", "aqc_loop_stats", "aqc_kernel_dev_scalars",
-    "aqc_launch_ex",
+    "aqc_launch_ex", "aqc_lane_select", "aqc_lane_event", "aqc_lane_wait",
 ]
 
 OP_SUM, OP_MIN, OP_MAX = 0, 1, 2
@@ -160,6 +160,9 @@ def lib():
     L.aqc_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_allreduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.aqc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    L.aqc_lane_select.argtypes = [C.c_void_p, C.c_int]
+    L.aqc_lane_event.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.aqc_lane_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_loop_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.aqc_loop_destroy.argtypes = [C.c_void_p, C.c_void_p]
     L.aqc_loop_table.argtypes = [C.c_void_p]

@@ -38,8 +38,11 @@ extern "C" int aqc_ctx_create(int device, aqc_ctx** out)
     }
     aqc_ctx* ctx = new aqc_ctx();
     ctx->device = device;
+    // (the greatest priority: the branch lane of aqc_lane_select runs one class below)
+    int prio_least = 0, prio_greatest = 0;
     if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
         snprintf(g_create_err, sizeof(g_create_err), "cannot initialise device %d", device);
         delete ctx;
         return AQC_ERR_CUDA;
@@ -73,6 +76,14 @@ extern "C" void aqc_ctx_destroy(aqc_ctx* ctx)
     cudaFree(ctx->minmax_dev);
     cudaFree(ctx->cell_cls);
     cudaFree(ctx->pack_rows);
+    if (ctx->lane1_made) {
+        if (ctx->lane != 0)
+            aqc_lane_select(ctx, 0);
+        cudaStreamSynchronize(ctx->parked.stream);
+        cudaStreamDestroy(ctx->parked.stream);
+        cudaFree(ctx->parked.cell_cls);
+        cudaFree(ctx->parked.pack_rows);
+    }
     for (aqc_pair_cache* c : { &ctx->pc, &ctx->pcr }) {
         cudaFree(c->masks);
         cudaFree(c->chunks);
@@ -103,6 +114,8 @@ extern "C" int aqc_set_stream(aqc_ctx* ctx, void* s)
 {
     if (!ctx)
         return AQC_ERR_ARG;
+    if (ctx->lane != 0)
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_set_stream: the branch lane is selected");
     AQC_SYNC(ctx);
     if (ctx->own_stream) {
         cudaStreamDestroy(ctx->stream);
@@ -111,7 +124,9 @@ extern "C" int aqc_set_stream(aqc_ctx* ctx, void* s)
     if (s) {
         ctx->stream = (cudaStream_t)s;
     } else {
-        AQC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        AQC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest));
         ctx->own_stream = true;
     }
     return AQC_OK;
@@ -124,6 +139,62 @@ extern "C" int aqc_sync(aqc_ctx* ctx)
     if (!ctx)
         return AQC_ERR_ARG;
     AQC_SYNC(ctx);
+    return AQC_OK;
+}
+
+// ---- lanes: a second in-order queue for tools that do not depend on what the first is doing ----
+extern "C" int aqc_lane_select(aqc_ctx* ctx, int lane)
+{
+    if (!ctx || (lane != 0 && lane != 1))
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_lane_select: bad argument");
+    if (lane == ctx->lane)
+        return AQC_OK;
+    if (!ctx->lane1_made) {
+        // one step below the context's stream where the device has priorities: the branch usually
+        // carries the long sweep, and the short kernels of the main lane should find their way
+        // in between its CTAs (AQC_LANE1_PRIORITY overrides; lower number = served first)
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        int prio = least;
+        if (const char* e = getenv("AQC_LANE1_PRIORITY"))
+            prio = atoi(e);
+        AQC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->parked.stream, cudaStreamNonBlocking, prio));
+        ctx->lane1_made = true;
+    }
+    aqc_ctx::lane_state cur;
+    cur.stream = ctx->stream;
+    cur.cell_cls = ctx->cell_cls;
+    cur.cell_cls_cap = ctx->cell_cls_cap;
+    cur.pack_rows = ctx->pack_rows;
+    cur.pack_cap = ctx->pack_cap;
+    ctx->stream = ctx->parked.stream;
+    ctx->cell_cls = ctx->parked.cell_cls;
+    ctx->cell_cls_cap = ctx->parked.cell_cls_cap;
+    ctx->pack_rows = ctx->parked.pack_rows;
+    ctx->pack_cap = ctx->parked.pack_cap;
+    ctx->parked = cur;
+    ctx->lane = lane;
+    return AQC_OK;
+}
+
+extern "C" int aqc_lane_event(aqc_ctx* ctx, void** ev)
+{
+    if (!ctx || !ev)
+        return AQC_ERR_ARG;
+    if (!*ev) {
+        cudaEvent_t e;
+        AQC_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        *ev = (void*)e;
+    }
+    AQC_CUDA(ctx, cudaEventRecord((cudaEvent_t)*ev, ctx->stream));
+    return AQC_OK;
+}
+
+extern "C" int aqc_lane_wait(aqc_ctx* ctx, void* ev)
+{
+    if (!ctx || !ev)
+        return AQC_ERR_ARG;
+    AQC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)ev, 0));
     return AQC_OK;
 }
 

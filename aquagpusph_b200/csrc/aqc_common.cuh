@@ -138,7 +138,25 @@ struct aqc_ctx {
     // device addresses of the scalar arguments of the launch in flight (aqc_launch_ex)
     struct aqc_loop* recording = nullptr;
     const void* const* dev_scalars = nullptr;
+    // lanes (aqc_lane_*): `stream`, `cell_cls` and `pack_rows` above are those of the lane in use;
+    // the other lane's are parked here (the sweeps' scratch is per lane: two sweeps may be in
+    // flight at once)
+    struct lane_state {
+        cudaStream_t stream = nullptr;
+        uint8_t* cell_cls = nullptr;
+        size_t cell_cls_cap = 0;
+        void* pack_rows = nullptr;
+        size_t pack_cap = 0;
+    } parked;
+    int lane = 0;            // 0: the context's stream, 1: the branch stream
+    bool lane1_made = false; // parked / current holds the branch stream
 };
+// a build of the pair cache rewrites what sweeps on the other lane may be reading: let them finish
+static inline void aqc_lanes_drain_other(aqc_ctx* ctx)
+{
+    if (ctx->lane1_made && ctx->parked.stream && !ctx->recording)
+        cudaStreamSynchronize(ctx->parked.stream);
+}
 
 int aqc_comm_minmax(aqc_ctx* ctx, uint32_t* keys); // mpi.cu
 // Bounded wait for everything queued on the context's stream while a communicator is live: a

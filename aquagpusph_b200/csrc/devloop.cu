@@ -144,6 +144,8 @@ extern "C" int aqc_loop_begin(aqc_ctx* ctx, aqc_loop* L, const aqs_op* entry, in
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_begin: bad argument");
     if (ctx->recording)
         return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_begin: a loop is already being recorded");
+    if (ctx->lane != 0)
+        return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_begin: the branch lane is selected");
     if (!has_setcond(entry, n_entry))
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_loop_begin: the entry program holds no AQS_SETCOND");
     if (!L->started)
@@ -233,6 +235,8 @@ extern "C" int aqc_loop_abort(aqc_ctx* ctx, aqc_loop* L)
     if (!ctx || !L)
         return AQC_ERR_ARG;
     if (L->recording) {
+        if (ctx->lane != 0)
+            aqc_lane_select(ctx, 0);
         cudaGraph_t g = nullptr;
         cudaStreamEndCapture(ctx->stream, &g); // an invalidated capture reports its error here
         cudaGetLastError();
@@ -251,6 +255,8 @@ extern "C" int aqc_loop_end(aqc_ctx* ctx, aqc_loop* L)
         return AQC_ERR_ARG;
     if (!L->recording)
         return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_end: the loop is not being recorded");
+    if (ctx->lane != 0)
+        aqc_lane_select(ctx, 0);
     if (!L->body_has_cond) {
         aqc_loop_abort(ctx, L);
         return aqc_fail(ctx, AQC_ERR_STATE, "aqc_loop_end: the body never sets the loop condition");

@@ -1768,6 +1768,7 @@ int aqc_pc_prepare(aqc_ctx* ctx, const int* imove, const void* r, const void* rj
                       c.N == ll.N && c.nx == ll.nx && c.ny == ll.ny && c.nz == ll.nz && c.nw == ll.nw &&
                       c.dims == dims && c.cut2 == cut2 && !(icls & ~c.icls) && !(jcls & ~c.jcls);
     if (!same) {
+        aqc_lanes_drain_other(ctx); // (a reader of the lists on the other lane)
         if (c.cooldown) { // recent builds did not pay
             c.cooldown--;
             c.valid = false;

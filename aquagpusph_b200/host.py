@@ -22,7 +22,7 @@ SYMBOLS = [
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr", "aqh_set_script_runner", "aqh_variable_type",
     "aqh_eval_svm", "aqh_device_loops", "aqh_device_loop_stats", "aqh_loop_host_reason",
-    "aqh_device_loop_timing",
+    "aqh_device_loop_timing", "aqh_device_loop_branch_tools",
 ]
 
 
@@ -123,6 +123,8 @@ def lib():
     L.aqh_device_loop_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.aqh_device_loop_timing.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
+    L.aqh_device_loop_branch_tools.argtypes = [C.c_void_p]
+    L.aqh_device_loop_branch_tools.restype = C.c_uint
     L.aqh_loop_host_reason.argtypes = [C.c_void_p, C.c_int]
     L.aqh_loop_host_reason.restype = C.c_char_p
     L.aqh_scalar_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
@@ -321,6 +323,10 @@ class Simulation:
         runs, iters = C.c_uint64(0), C.c_uint64(0)
         _chk(lib().aqh_device_loop_stats(self.h, C.byref(runs), C.byref(iters)))
         return int(runs.value), int(iters.value)
+
+    def device_loop_branch_tools(self):
+        """Tools of the device loops that run on the second stream."""
+        return int(lib().aqh_device_loop_branch_tools(self.h))
 
     def device_loop_timing(self):
         """{graph nodes of the recorded bodies, host ms of the last recording / instantiation}."""

@@ -109,6 +109,11 @@ class Kernel : public Tool {
     void fuse_lead(int fused_id, const std::vector<Kernel*>& group) { _fused_id = fused_id; _group = group; }
     void fuse_follow(Kernel* leader) { _leader = leader; }
     bool fused() const { return _fused_id >= 0 || _leader; }
+    /// members of the fused group this kernel leads (empty: not a leader) / the leader it follows
+    const std::vector<Kernel*>& group() const { return _group; }
+    const Kernel* leader() const { return _leader; }
+    /// true when the kernel walks neighbours (it has the link-list's head-of-cell argument)
+    bool isSweep() const;
     bool recordable(const DeviceLoop& L, std::string& why) const override;
     void record(DeviceLoop& L) override;
   protected:
@@ -275,6 +280,13 @@ class Reduction : public Tool {
               const std::string& operation, const std::string& null_val, bool once)
       : Tool(C, name, once), _in_name(in), _out_name(out), _operation(operation), _null(null_val) {}
     void setup() override;
+    bool dependencies(std::vector<InputOutput::Variable*>& in,
+                      std::vector<InputOutput::Variable*>& out) const override
+    {
+        in.push_back(_in);
+        out.push_back(_out);
+        return true;
+    }
     bool recordable(const DeviceLoop& L, std::string& why) const override;
     void scalarOutputs(std::vector<InputOutput::Variable*>& out) const override { out.push_back(_out); }
     void record(DeviceLoop& L) override;

@@ -427,6 +427,17 @@ extern "C" int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* rec
     AQH_CATCH
 }
 
+extern "C" unsigned aqh_device_loop_branch_tools(aqh_sim* sim)
+{
+    unsigned n = 0;
+    if (sim && sim->C)
+        for (auto& t : sim->C->tools())
+            if (auto* w = dynamic_cast<CalcServer::While*>(t.get()))
+                if (w->deviceLoop())
+                    n += w->deviceLoop()->branchTools();
+    return n;
+}
+
 extern "C" const char* aqh_loop_host_reason(aqh_sim* sim, int i)
 {
     if (!sim || !sim->C || i < 0 || i >= (int)sim->C->tools().size())

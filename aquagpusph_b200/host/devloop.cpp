@@ -280,6 +280,153 @@ DeviceLoop::~DeviceLoop()
 {
     if (_loop)
         aqc_loop_destroy(_C->ctx(), _loop);
+    for (void* e : _events)
+        if (e)
+            aqc_event_destroy(_C->ctx(), e);
+    if (_ev_fork)
+        aqc_event_destroy(_C->ctx(), _ev_fork);
+}
+
+unsigned DeviceLoop::branchTools() const
+{
+    unsigned n = 0;
+    for (int l : _lane_of)
+        n += l == 1;
+    return _two_lanes ? n : 0;
+}
+
+// Which lane every tool of the body runs on, and the events it waits for.  Dependencies are whole
+// arrays (Tool::dependencies: what the fusion planner uses too): two tools conflict when one writes
+// what the other reads or writes.  Lanes come from list scheduling in pipeline order with a crude
+// cost (a neighbour sweep = 10 element-wise kernels): a tool goes to the branch lane when it could
+// start there clearly earlier.  Whatever the assignment, every conflicting pair on different lanes
+// is ordered by an event, so the result is the one of the pipeline order.
+void DeviceLoop::planLanes()
+{
+    auto& tools = _C->tools();
+    const size_t n = _last - _first;
+    _lane_of.assign(n, 0);
+    _waits.assign(n, {});
+    _marked.assign(n, 0);
+    _events.assign(n, nullptr);
+    _two_lanes = false;
+    _last_lane1 = -1;
+    if (const char* e = getenv("AQUA_DEVICE_LANES"))
+        if (!strcmp(e, "0"))
+            return;
+    struct Dep {
+        std::vector<const Variable*> r, w;
+        bool barrier = false, forced0 = false, launches = true;
+        double cost = 1.0;
+    };
+    std::vector<Dep> deps(n);
+    auto arrays = [](const std::vector<Variable*>& v, std::vector<const Variable*>& out) {
+        for (auto x : v)
+            if (x && x->isArray() && std::find(out.begin(), out.end(), x) == out.end())
+                out.push_back(x);
+    };
+    for (size_t k = 0; k < n; k++) {
+        Tool* t = tools[_first + k].get();
+        Dep& d = deps[k];
+        std::vector<Variable*> in, out;
+        if (Kernel* kt = dynamic_cast<Kernel*>(t)) {
+            if (kt->leader()) { // runs inside its leader's launch
+                d.launches = false;
+                d.cost = 0.0;
+                continue;
+            }
+            std::vector<Kernel*> members = kt->group();
+            if (members.empty())
+                members.push_back(kt);
+            d.cost = 0.0;
+            for (auto m : members) {
+                m->dependencies(in, out);
+                d.cost += m->isSweep() ? 10.0 : 1.0;
+                for (auto v : m->arguments())
+                    if (!v->isArray() && varying(v))
+                        d.forced0 = true; // reads the table: behind the scalar programs
+            }
+        } else if (dynamic_cast<Reduction*>(t)) {
+            t->dependencies(in, out);
+            d.forced0 = true; // (the reduction scratch and the table are lane 0's)
+        } else if (dynamic_cast<Copy*>(t) || dynamic_cast<Set*>(t)) {
+            t->dependencies(in, out);
+        } else if (dynamic_cast<ScalarExpression*>(t) || dynamic_cast<Report*>(t) || dynamic_cast<Dummy*>(t)) {
+            d.launches = false; // scalar programs: queued, run on lane 0
+            d.forced0 = true;
+            d.cost = 0.0;
+            continue;
+        } else {
+            d.barrier = true;
+            d.forced0 = true;
+        }
+        arrays(in, d.r);
+        arrays(out, d.w);
+        arrays(out, d.r); // (an output may be accumulated into)
+    }
+    auto meets = [](const std::vector<const Variable*>& a, const std::vector<const Variable*>& b) {
+        for (auto x : a)
+            if (std::find(b.begin(), b.end(), x) != b.end())
+                return true;
+        return false;
+    };
+    auto conflict = [&](const Dep& a, const Dep& b) {
+        return a.barrier || b.barrier || meets(a.w, b.r) || meets(a.w, b.w) || meets(a.r, b.w);
+    };
+    double free_at[2] = { 0.0, 0.0 };
+    std::vector<double> finish(n, 0.0);
+    for (size_t k = 0; k < n; k++) {
+        Dep& d = deps[k];
+        if (!d.launches)
+            continue;
+        double ready = 0.0;
+        for (size_t u = 0; u < k; u++)
+            if (deps[u].launches && conflict(deps[u], d))
+                ready = std::max(ready, finish[u]);
+        const double r0 = std::max(ready, free_at[0]), r1 = std::max(ready, free_at[1]);
+        const int l = (!d.forced0 && r1 + 3.0 <= r0) ? 1 : 0;
+        _lane_of[k] = l;
+        finish[k] = (l ? r1 : r0) + d.cost;
+        free_at[l] = finish[k];
+    }
+    // events: the last conflicting tool of the other lane, unless the lane already waited past it
+    int waited[2] = { -1, -1 }; // per lane: the newest tool of the OTHER lane it has waited for
+    for (size_t k = 0; k < n; k++) {
+        if (!deps[k].launches)
+            continue;
+        const int l = _lane_of[k];
+        int last = -1;
+        for (size_t u = 0; u < k; u++)
+            if (deps[u].launches && _lane_of[u] != l && conflict(deps[u], deps[k]))
+                last = (int)u;
+        if (last > waited[l]) {
+            _waits[k].push_back(last);
+            _marked[last] = 1;
+            waited[l] = last;
+        }
+        if (l == 1) {
+            _two_lanes = true;
+            _last_lane1 = (int)k;
+        }
+    }
+    if (_last_lane1 >= 0)
+        _marked[_last_lane1] = 1; // the join at the end of the pass
+    if (_two_lanes && logLevel() <= L_INFO) {
+        std::string msg = "The loop \"" + _opener->name() + "\" runs these tools on a second stream:";
+        for (size_t k = 0; k < n; k++)
+            if (deps[k].launches && _lane_of[k] == 1)
+                msg += " \"" + tools[_first + k]->name() + "\"";
+        log(L_INFO, msg + "\n");
+    }
+}
+
+void DeviceLoop::lane(int l)
+{
+    if (l == _cur_lane)
+        return;
+    if (aqc_lane_select(_C->ctx(), l))
+        throw std::runtime_error(aqc_last_error(_C->ctx()));
+    _cur_lane = l;
 }
 
 aqc_ctx* DeviceLoop::ctx() const { return _C->ctx(); }
@@ -449,6 +596,7 @@ bool DeviceLoop::plan(std::string& why)
         why = aqc_last_error(_C->ctx());
         return false;
     }
+    planLanes();
     _usable = true;
     return true;
 }
@@ -457,6 +605,8 @@ void DeviceLoop::flush()
 {
     if (_pending.empty())
         return;
+    if (_cur_lane != 0)
+        throw std::runtime_error("DeviceLoop::flush on the branch lane");
     if (aqc_loop_svm(_C->ctx(), _loop, _pending.data(), (int)_pending.size()))
         throw std::runtime_error(aqc_last_error(_C->ctx()));
     _pending.clear();
@@ -471,8 +621,41 @@ void DeviceLoop::pass()
     compile(_condition, cond);
     cond.push_back(mk(AQS_SETCOND));
     _pending.clear();
-    for (size_t i = _first; i < _last; i++)
-        tools[i]->record(*this);
+    auto chk = [&](int rc) {
+        if (rc)
+            throw std::runtime_error(aqc_last_error(_C->ctx()));
+    };
+    if (!_two_lanes) {
+        for (size_t i = _first; i < _last; i++)
+            tools[i]->record(*this);
+    } else {
+        try {
+            // fork: the branch lane starts behind everything queued so far (the pass before this one)
+            lane(0);
+            chk(aqc_lane_event(_C->ctx(), &_ev_fork));
+            lane(1);
+            chk(aqc_lane_wait(_C->ctx(), _ev_fork));
+            for (size_t i = _first; i < _last; i++) {
+                const size_t k = i - _first;
+                lane(_lane_of[k]);
+                for (int u : _waits[k])
+                    chk(aqc_lane_wait(_C->ctx(), _events[u]));
+                tools[i]->record(*this);
+                if (_marked[k])
+                    chk(aqc_lane_event(_C->ctx(), &_events[k]));
+            }
+            // join: lane 0 goes on behind the branch
+            lane(0);
+            if (_last_lane1 >= 0)
+                chk(aqc_lane_wait(_C->ctx(), _events[_last_lane1]));
+        } catch (...) {
+            try {
+                lane(0);
+            } catch (...) {
+            }
+            throw;
+        }
+    }
     emit(cond);
     flush();
 }
@@ -579,6 +762,14 @@ bool DeviceLoop::run()
 }
 
 // ------------------------------------------------- the tools' side of it --
+bool Kernel::isSweep() const
+{
+    for (auto v : _vars)
+        if (v->name() == "ihoc" || v->name() == "mpi_ihoc")
+            return true;
+    return false;
+}
+
 size_t Kernel::globalSize() const
 {
     // global size: n="" -> longest array argument (Kernel.cpp:558-594)

@@ -103,6 +103,8 @@ class DeviceLoop {
 
   private:
     static bool resolve(void* user, const std::string& id, SvmCompiler::Slot& out);
+    void planLanes();
+    void lane(int l);
     void pass();
     void record();
     CalcServer* _C;
@@ -121,6 +123,20 @@ class DeviceLoop {
     unsigned _failures = 0;
     uint64_t _runs = 0, _iterations = 0;
     uint32_t _max_iters = 65536;
+    // two lanes (aqc_lane_*): tools whose arrays do not meet run on a second stream, ordered against
+    // the first by events behind the tools they depend on -- what the reference's queue pool and
+    // per-variable events do (Tool.cpp:405-444), decided once, at plan time
+    bool _two_lanes = false;
+    int _cur_lane = 0;
+    std::vector<int> _lane_of;            // per body tool
+    std::vector<std::vector<int>> _waits; // per body tool: body tools (other lane) whose event it waits for
+    std::vector<char> _marked;            // per body tool: an event is recorded behind it
+    std::vector<void*> _events;           // per body tool (created on first use)
+    void* _ev_fork = nullptr;
+    int _last_lane1 = -1;
+  public:
+    /// tools of the body that run on the branch lane (0: single lane)
+    unsigned branchTools() const;
 };
 
 } // namespace CalcServer

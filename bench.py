@@ -410,6 +410,7 @@ def run_ours(a, rank, world, local_rank):
                    # made there since the set-up
                    "device_loops": {"loops": sim.device_loops(),
                                     "runs_and_passes": list(sim.device_loop_stats()),
+                                    "tools_on_second_stream": sim.device_loop_branch_tools(),
                                     "last_step_host_cost": sim.device_loop_timing()},
                    "l2": "inputs larger than L2 (%.0f MB of particle arrays)" % (560.0 * N / 1e6),
                    "multi_gpu": ("y-slab decomposition, mpi-sync over NCCL send/recv (halo of r, u, rho, m and of "

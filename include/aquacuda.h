@@ -292,6 +292,20 @@ int aqc_mpi_sync_stats(const aqc_ctx* ctx, int plan, uint64_t* full, uint64_t* r
 int aqc_allreduce(aqc_ctx* ctx, int op, int type, void* dev_inout, size_t count);
 int aqc_allreduce_host(aqc_ctx* ctx, int op, int type, void* host_inout, size_t count);
 
+/* ---- lanes.  The reference runs tools whose dependencies allow it on different OpenCL command
+ * queues (CalcServer.cpp:674-705: the queue pool; Tool.cpp:405-444: the events of the variables a tool
+ * reads and writes are what it waits for).  A context here is ONE in-order stream, plus a second one
+ * on request: aqc_lane_select(ctx, 1) sends every following call of the context to the BRANCH lane
+ * (own stream, lower priority, own sweep scratch) until aqc_lane_select(ctx, 0).  Ordering between
+ * the lanes is the caller's business: aqc_lane_event records an event (created when *ev is NULL) behind
+ * what was queued on the lane in use, aqc_lane_wait makes the lane in use wait for one.  Both work
+ * while a loop body records (the branch lane joins the capture through its first wait and must be
+ * waited for by lane 0 before aqc_loop_end).  Reductions, scalar programs, link-list, sort, mpi-sync
+ * and every call that synchronises belong on lane 0. ------------------------------------------- */
+int aqc_lane_select(aqc_ctx* ctx, int lane);
+int aqc_lane_event(aqc_ctx* ctx, void** ev);
+int aqc_lane_wait(aqc_ctx* ctx, void* ev);
+
 /* ---- device-side loops.  The reference evaluates `while` conditions and
  * set_scalar expressions on the host behind the events of the variables they read
  * (Conditional.cpp:85-96, SetScalar.cpp:146-195) and reads every reduction back before the host

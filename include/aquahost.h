@@ -91,6 +91,9 @@ int aqh_device_loop_stats(aqh_sim* sim, uint64_t* runs, uint64_t* iterations);
 const char* aqh_loop_host_reason(aqh_sim* sim, int i);
 /* graph nodes of the recorded bodies, host milliseconds the last recording and the last
  * cudaGraphInstantiate took (summed over the loops): the per-step host cost of the device loops */
+/* tools of the device loops' bodies that run on the second stream (aqc_lane_*: their arrays do not
+ * meet those of the tools running meanwhile on the first; AQUA_DEVICE_LANES=0: none) */
+unsigned aqh_device_loop_branch_tools(aqh_sim* sim);
 int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* record_ms, double* instantiate_ms);
 
 /* type="python" tools (aquagpusph/CalcServer/Python.cpp:295-325).  The reference embeds CPython in

@@ -169,7 +169,7 @@ def test_recording_refuses_what_synchronises_and_leaves_the_context_usable():
 def _run(template, case, nset, ov, steps, device_loops, monkeypatch, transform=None, dims=3):
     monkeypatch.setenv("AQUA_DEVICE_LOOPS", "1" if device_loops else "0")
     sim = casegen.load(template, case, nset, ov, keep_reports=True, transform=transform)
-    out = {"loops": sim.device_loops()}
+    out = {"loops": sim.device_loops(), "branch": sim.device_loop_branch_tools()}
     per_step = []
     for _ in range(steps):
         sim.step(1)
@@ -213,6 +213,8 @@ def test_dam_break_midpoint_loop_on_the_device_equals_the_host_loop(n, maxiter, 
     D = _run("spheric2_dambreak_3d", case, nset, ov, 5, True, monkeypatch)
     assert H["loops"] == 0 and H["why"] == ["AQUA_DEVICE_LOOPS=0"]
     assert D["loops"] == 1 and D["why"] == [""], D["why"]
+    # the delta-SPH correction sweep (and what only it depends on) overlaps the boundary chain
+    assert D["branch"] >= 2 and H["branch"] == 0
     keys = ("r", "u", "rho", "p", "dudt", "drhodt", "dudt_in", "drhodt_in", "Force_p", "Moment_p",
             "Force_elastic")
     _same(H, H2, keys)                      # the host path repeats itself bit for bit ...
