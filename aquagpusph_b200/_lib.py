@@ -26,7 +26,7 @@ SYMBOLS = [
     "aqc_event_destroy", "aqc_event_record", "aqc_event_sync", "aqc_event_elapsed_ms",
     "aqc_comm_unique_id", "aqc_comm_init", "aqc_comm_destroy", "aqc_comm_rank", "aqc_comm_size",
     "aqc_mpi_sync", "aqc_mpi_sync_plan", "aqc_mpi_sync_ex", "aqc_mpi_sync_stats", "aqc_allreduce", "aqc_allreduce_host", "aqc_fused_lookup", "aqc_launch_fused",
-    "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
+    "aqc_fused_prefix", "aqc_kernel_write_rows", "aqc_kernel_read_rows", "aqc_fused_read_rows", "aqc_sweep_engine_select",
     "aqc_pairs_cache_enable", "aqc_pairs_cache_invalidate", "aqc_pairs_cache_stats", "aqc_pairs_cache_stats_remote", "aqc_fp32_peak",
     "aqc_watch_create", "aqc_watch_dirty", "aqc_watch_reset",
     "aqc_loop_create", "aqc_loop_destroy", "aqc_loop_table", "aqc_loop_begin", "aqc_loop_svm",

@@ -2500,6 +2500,22 @@ extern "C" int aqc_kernel_write_rows(int kernel_id)
     return AQC_ROWS_ANY;
 }
 
+// rows of the arrays OTHER than the positions whose values a kernel uses
+extern "C" int aqc_kernel_read_rows(int kernel_id)
+{
+    const char* nm = aqc_kernel_name(kernel_id);
+    if (!nm)
+        return AQC_ROWS_ANY;
+    // cfd/Boundary/BIe/Interactions.cl:63-106: i is a fluid particle (imove == 1) of which only the
+    // position is read, j a boundary element (imove == -3): normal, u and m of boundary rows
+    if (!strcmp(nm, "cfd/Boundary/BIe/Interactions.cl::entry"))
+        return AQC_ROWS_BOUNDARY;
+    // ... :136-170: i a boundary element (position only), j a fluid particle: p, m, rho of fluid rows
+    if (!strcmp(nm, "cfd/Boundary/BIe/Interactions.cl::p_boundary"))
+        return AQC_ROWS_FLUID;
+    return AQC_ROWS_ANY;
+}
+
 extern "C" int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs)
 {
     if (!ctx)

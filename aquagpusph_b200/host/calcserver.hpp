@@ -112,6 +112,7 @@ class Kernel : public Tool {
     /// members of the fused group this kernel leads (empty: not a leader) / the leader it follows
     const std::vector<Kernel*>& group() const { return _group; }
     const Kernel* leader() const { return _leader; }
+    int fusedId() const { return _fused_id; }
     /// true when the kernel walks neighbours (it has the link-list's head-of-cell argument)
     bool isSweep() const;
     bool recordable(const DeviceLoop& L, std::string& why) const override;

@@ -314,17 +314,34 @@ void DeviceLoop::planLanes()
     if (const char* e = getenv("AQUA_DEVICE_LANES"))
         if (!strcmp(e, "0"))
             return;
+    // what a tool reads / writes: arrays with the particle classes (AQC_ROWS_*) of the rows involved
+    // -- cfd/Sensors.cl writes sensor rows only, the fused fluid sweep reads fluid rows only (what
+    // the fusion planner relies on as well), BIe interactions boundary rows ...
+    typedef std::vector<std::pair<const Variable*, unsigned>> Access;
     struct Dep {
-        std::vector<const Variable*> r, w;
+        Access r, w;
         bool barrier = false, forced0 = false, launches = true;
         double cost = 1.0;
     };
     std::vector<Dep> deps(n);
-    auto arrays = [](const std::vector<Variable*>& v, std::vector<const Variable*>& out) {
-        for (auto x : v)
-            if (x && x->isArray() && std::find(out.begin(), out.end(), x) == out.end())
-                out.push_back(x);
+    auto add = [](Access& a, const Variable* v, unsigned rows) {
+        if (!v || !v->isArray())
+            return;
+        for (auto& e : a)
+            if (e.first == v) {
+                e.second |= rows;
+                return;
+            }
+        a.emplace_back(v, rows);
     };
+    auto add_all = [&](Access& a, const std::vector<Variable*>& vs, unsigned rows) {
+        for (auto v : vs)
+            add(a, v, rows);
+    };
+    // (off by default: with the row classes the sensors, the BIe sets and BIe interactions move next
+    // to the fused fluid sweep, which loses more than they gain -- 25.14 against 24.87 ms per step at
+    // 1.2 M particles, 7.52 against 6.97 at 142 k; profiles/r2_lanes_assignment.txt)
+    const bool use_rows = getenv("AQUA_LANE_ROWS") && !strcmp(getenv("AQUA_LANE_ROWS"), "1");
     for (size_t k = 0; k < n; k++) {
         Tool* t = tools[_first + k].get();
         Dep& d = deps[k];
@@ -336,16 +353,36 @@ void DeviceLoop::planLanes()
                 continue;
             }
             std::vector<Kernel*> members = kt->group();
-            if (members.empty())
+            const bool fused = !members.empty();
+            if (!fused)
                 members.push_back(kt);
             d.cost = 0.0;
             for (auto m : members) {
+                in.clear();
+                out.clear();
                 m->dependencies(in, out);
                 d.cost += m->isSweep() ? 10.0 : 1.0;
+                unsigned rrows = AQC_ROWS_ANY, wrows = AQC_ROWS_ANY;
+                if (use_rows) {
+                    rrows = fused ? (unsigned)aqc_fused_read_rows(kt->fusedId())
+                                  : (unsigned)aqc_kernel_read_rows(m->kernel_id());
+                    wrows = fused ? (unsigned)AQC_ROWS_ANY : (unsigned)aqc_kernel_write_rows(m->kernel_id());
+                }
+                for (auto v : in) // (positions are read whatever the class)
+                    add(d.r, v, (v->name() == "r" || v->name() == "r_in") ? (unsigned)AQC_ROWS_ANY : rrows);
+                add_all(d.w, out, wrows);
+                add_all(d.r, out, AQC_ROWS_ANY); // (an output may be read back: accumulated into, or p[j] of p_boundary)
                 for (auto v : m->arguments())
                     if (!v->isArray() && varying(v))
                         d.forced0 = true; // reads the table: behind the scalar programs
             }
+            if (use_rows && !fused && aqc_kernel_read_rows(kt->kernel_id()) != AQC_ROWS_ANY)
+                for (auto& e : d.r) // a restricted reader reads its outputs' other rows the same way
+                    for (auto v : out)
+                        if (e.first == v)
+                            e.second = (unsigned)aqc_kernel_read_rows(kt->kernel_id()) |
+                                       (unsigned)aqc_kernel_write_rows(kt->kernel_id());
+            continue;
         } else if (dynamic_cast<Reduction*>(t)) {
             t->dependencies(in, out);
             d.forced0 = true; // (the reduction scratch and the table are lane 0's)
@@ -360,19 +397,29 @@ void DeviceLoop::planLanes()
             d.barrier = true;
             d.forced0 = true;
         }
-        arrays(in, d.r);
-        arrays(out, d.w);
-        arrays(out, d.r); // (an output may be accumulated into)
+        add_all(d.r, in, AQC_ROWS_ANY);
+        add_all(d.w, out, AQC_ROWS_ANY);
+        add_all(d.r, out, AQC_ROWS_ANY);
     }
-    auto meets = [](const std::vector<const Variable*>& a, const std::vector<const Variable*>& b) {
-        for (auto x : a)
-            if (std::find(b.begin(), b.end(), x) != b.end())
-                return true;
+    auto meets = [](const Access& a, const Access& b) {
+        for (auto& x : a)
+            for (auto& y : b)
+                if (x.first == y.first && (x.second & y.second))
+                    return true;
         return false;
     };
     auto conflict = [&](const Dep& a, const Dep& b) {
         return a.barrier || b.barrier || meets(a.w, b.r) || meets(a.w, b.w) || meets(a.r, b.w);
     };
+    // (tuning knobs; the defaults are what was measured best on the dam break at 1.2 M particles)
+    double gain = 3.0, sweep_cost = 10.0;
+    if (const char* e = getenv("AQUA_LANE_GAIN"))
+        gain = atof(e);
+    if (const char* e = getenv("AQUA_LANE_SWEEP_COST"))
+        sweep_cost = atof(e);
+    for (size_t k = 0; k < n; k++)
+        if (deps[k].cost >= 10.0)
+            deps[k].cost = deps[k].cost / 10.0 * sweep_cost;
     double free_at[2] = { 0.0, 0.0 };
     std::vector<double> finish(n, 0.0);
     for (size_t k = 0; k < n; k++) {
@@ -384,7 +431,7 @@ void DeviceLoop::planLanes()
             if (deps[u].launches && conflict(deps[u], d))
                 ready = std::max(ready, finish[u]);
         const double r0 = std::max(ready, free_at[0]), r1 = std::max(ready, free_at[1]);
-        const int l = (!d.forced0 && r1 + 3.0 <= r0) ? 1 : 0;
+        const int l = (!d.forced0 && r1 + gain <= r0) ? 1 : 0;
         _lane_of[k] = l;
         finish[k] = (l ? r1 : r0) + d.cost;
         free_at[l] = finish[k];

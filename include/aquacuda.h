@@ -200,6 +200,10 @@ int aqc_fused_prefix(const int* kernel_ids, int n, int dims);
  * disturb a sweep over fluid pairs */
 enum { AQC_ROWS_FLUID = 1, AQC_ROWS_SENSOR = 2, AQC_ROWS_BOUNDARY = 4, AQC_ROWS_ANY = 7 };
 int aqc_kernel_write_rows(int kernel_id);
+/* ... and the rows whose VALUES a stand-alone kernel uses in the arrays other than the positions
+ * (a kernel may still load rows it then discards by their class: a concurrent writer of those rows
+ * changes nothing it computes).  AQC_ROWS_ANY unless the script says otherwise. */
+int aqc_kernel_read_rows(int kernel_id);
 int aqc_fused_read_rows(int fused_id);
 int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, int nargs);
 /* Neighbour-sweep engine of the kernel-support sweeps (both are CUDA):
