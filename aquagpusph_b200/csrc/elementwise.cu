@@ -1518,6 +1518,167 @@ int l_h_sensor(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// ---- cfd/ideal_gas: the element-wise kernels of the ideal-gas presets (the internal energy next to
+// rho / u; examples/2D/shock_*).  One HBM pass each, the reference's operation order (-fmad=false) ----
+// cfd/ideal_gas/EOS.cl:56-70 (EXCLUDED_PARTICLE :32-34)
+__global__ void __launch_bounds__(256)
+k_ig_eos(const uint32_t* iset, const int* imove, const float* rho, const float* eint, float* p,
+         const float* gamma, uint32_t N)
+{
+    GID;
+    const int mv = imove[i];
+    if ((mv <= 0) && (mv != -1))
+        return;
+    p[i] = (gamma[iset[i]] - 1.0f) * rho[i] * eint[i];
+}
+int l_ig_eos(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    LAUNCH(c, k_ig_eos, N, (const uint32_t*)a[0], (const int*)a[1], (const float*)a[2], (const float*)a[3],
+           (float*)a[4], (const float*)a[5], N);
+    return AQC_OK;
+}
+
+// cfd/ideal_gas/Rates.cl:53-68
+__global__ void __launch_bounds__(256)
+k_ig_rates(const int* imove, const float* rho, const float* p, const float* div_u, float* deintdt, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    deintdt[i] = -p[i] / (rho[i] * rho[i]) * div_u[i];
+}
+int l_ig_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 6);
+    LAUNCH(c, k_ig_rates, N, (const int*)a[1], (const float*)a[2], (const float*)a[3], (const float*)a[4],
+           (float*)a[5], N);
+    return AQC_OK;
+}
+
+// cfd/ideal_gas/Sort.cl:43-58
+__global__ void __launch_bounds__(256)
+k_ig_sort(const float* eint_in, float* eint, const float* deintdt, float* deintdt_in, const uint32_t* id_sorted,
+          uint32_t N)
+{
+    GID;
+    const uint32_t o = id_sorted[i];
+    eint[o] = eint_in[i];
+    deintdt_in[o] = deintdt[i];
+}
+int l_ig_sort(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    LAUNCH(c, k_ig_sort, N, (const float*)a[0], (float*)a[1], (const float*)a[2], (float*)a[3],
+           (const uint32_t*)a[4], N);
+    return AQC_OK;
+}
+
+// cfd/ideal_gas/TimeStep.cl:62-97 (sound_speed.hcl:22-25; length() of a vec takes every component;
+// OpenCL min(x, y) = y < x ? y : x, max(x, y) = x < y ? y : x)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_ig_timestep(float* dt_var, const int* imove, const uint32_t* iset, const void* u, const float* rho,
+              const float* p, uint32_t N, float dt, float dt_min, float courant, const float* div_u,
+              const void* grad_p, const float* gamma, float H)
+{
+    GID;
+    if (imove[i] <= 0) {
+        dt_var[i] = dt;
+        return;
+    }
+    const float dxx = H;
+    const float s_i = sqrtf(gamma[iset[i]] * p[i] / rho[i]);
+    const V<D> G = V<D>::ld(grad_p, i), U = V<D>::ld(u, i);
+    const float lg = sqrtf(G.dot(G)), lu = sqrtf(U.dot(U));
+    const float a = 4.0f * dxx * div_u[i] / rho[i];
+    const float dt_u1 = courant * 0.4f * dxx / sqrtf(a * a + s_i * s_i);
+    const float dt_u2 = courant * sqrtf(dxx / lg);
+    const float dt_u3 = courant * 0.4f * dxx / sqrtf(lu * lu + s_i * s_i);
+    const float m12 = dt_u2 < dt_u1 ? dt_u2 : dt_u1;
+    const float dt_u = dt_u3 < m12 ? dt_u3 : m12;
+    const float lo = dt_u < dt ? dt_u : dt;
+    dt_var[i] = lo < dt_min ? dt_min : lo;
+}
+int l_ig_timestep(aqc_ctx* c, size_t, void* const* a)
+{
+    // (dudt, m and the scalar h are arguments of the script that its body never uses)
+    const uint32_t N = aqc_scalar<uint32_t>(a, 8);
+    DISPATCH(c, k_ig_timestep, N, (float*)a[0], (const int*)a[1], (const uint32_t*)a[2], a[3], (const float*)a[5],
+             (const float*)a[6], N, aqc_scalar<float>(a, 9), aqc_scalar<float>(a, 10), aqc_scalar<float>(a, 11),
+             (const float*)a[13], a[14], (const float*)a[15], c->defs.H);
+}
+
+// cfd/ideal_gas/riemann/Rates.cl:39-53
+__global__ void __launch_bounds__(256)
+k_ig_riemann_rates(const int* imove, const float* work_density, float* deintdt, uint32_t N)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    deintdt[i] = -work_density[i];
+}
+int l_ig_riemann_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_riemann_rates, N, (const int*)a[1], (const float*)a[2], (float*)a[3], N);
+    return AQC_OK;
+}
+
+// cfd/ideal_gas/time_scheme/midpoint.cl: predictor :47-59, midpoint :75-88, relax :101-115, corrector :131-144
+__global__ void __launch_bounds__(256)
+k_ig_mp_predictor(const float* eint, const float* deintdt, float* eint_in, float* deintdt_in, uint32_t N)
+{
+    GID;
+    deintdt_in[i] = deintdt[i];
+    eint_in[i] = eint[i];
+}
+int l_ig_mp_predictor(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_mp_predictor, N, (const float*)a[0], (const float*)a[1], (float*)a[2], (float*)a[3], N);
+    return AQC_OK;
+}
+// midpoint (f = 0.5) and corrector (f = 1): 0.5f * dt is exact, so f * dt * rate == the script's expression
+__global__ void __launch_bounds__(256)
+k_ig_mp_advance(const int* imove, const float* eint_in, const float* deintdt, float* eint, uint32_t N, float fdt)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    eint[i] = eint_in[i] + fdt * deintdt[i];
+}
+int l_ig_mp_midpoint(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_mp_advance, N, (const int*)a[0], (const float*)a[1], (const float*)a[2], (float*)a[3], N,
+           0.5f * aqc_scalar<float>(a, 5));
+    return AQC_OK;
+}
+int l_ig_mp_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_mp_advance, N, (const int*)a[0], (const float*)a[1], (const float*)a[2], (float*)a[3], N,
+           aqc_scalar<float>(a, 5));
+    return AQC_OK;
+}
+__global__ void __launch_bounds__(256)
+k_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, uint32_t N, aqc_sv<float> relax)
+{
+    GID;
+    if (imove[i] <= 0)
+        return;
+    const float f = relax.get(); // (inside a recorded loop: the value the loop's scalar program left)
+    deintdt[i] = f * deintdt_in[i] + (1.f - f) * deintdt[i];
+}
+int l_ig_mp_relax(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    LAUNCH(c, k_ig_mp_relax, N, (const int*)a[0], (const float*)a[1], (float*)a[2], N,
+           aqc_scalar_sv<float>(c, a, 4));
+    return AQC_OK;
+}
+
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define RO(n, t) { n, t, AQC_ARG_ARRAY_RO }
@@ -1773,5 +1934,35 @@ aqc_registrar r_sb_count("basic/SetBuffer.cl", "count", 0,
     { IN("imove", "int*"), OUT("ibuffer", "unsigned int*"), SC("N", "usize") }, l_setbuffer_count);
 aqc_registrar r_sb_set("basic/SetBuffer.cl", "set_imove", 0,
     { OUT("imove", "int*"), SC("N", "usize") }, l_setbuffer_set_imove);
+
+aqc_registrar r_ig_eos("cfd/ideal_gas/EOS.cl", "entry", 0,
+    { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("rho", "float*"), IN("eint", "float*"),
+      OUT("p", "float*"), IN("gamma", "float*"), SC("N", "usize") }, l_ig_eos);
+aqc_registrar r_ig_rates("cfd/ideal_gas/Rates.cl", "entry", 0,
+    { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("rho", "float*"), IN("p", "float*"),
+      IN("div_u", "float*"), OUT("deintdt", "float*"), SC("N", "usize") }, l_ig_rates);
+aqc_registrar r_ig_sort("cfd/ideal_gas/Sort.cl", "entry", 0,
+    { IN("eint_in", "float*"), OUT("eint", "float*"), IN("deintdt", "float*"), OUT("deintdt_in", "float*"),
+      IN("id_sorted", "usize*"), SC("N", "usize") }, l_ig_sort);
+aqc_registrar r_ig_dt("cfd/ideal_gas/TimeStep.cl", "entry", 0,
+    { OUT("dt_var", "float*"), IN("imove", "int*"), IN("iset", "unsigned int*"), IN("u", "vec*"),
+      IN("dudt", "vec*"), IN("rho", "float*"), IN("p", "float*"), IN("m", "float*"), SC("N", "usize"),
+      SC("dt", "float"), SC("dt_min", "float"), SC("courant", "float"), SC("h", "float"),
+      IN("div_u", "float*"), IN("grad_p", "vec*"), IN("gamma", "float*") }, l_ig_timestep);
+aqc_registrar r_ig_rrates("cfd/ideal_gas/riemann/Rates.cl", "entry", 0,
+    { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("work_density", "float*"), OUT("deintdt", "float*"),
+      SC("N", "usize") }, l_ig_riemann_rates);
+aqc_registrar r_ig_mp_p("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor", 0,
+    { IN("eint", "float*"), IN("deintdt", "float*"), OUT("eint_in", "float*"), OUT("deintdt_in", "float*"),
+      SC("N", "usize") }, l_ig_mp_predictor);
+aqc_registrar r_ig_mp_m("cfd/ideal_gas/time_scheme/midpoint.cl", "midpoint", 0,
+    { IN("imove", "int*"), IN("eint_in", "float*"), IN("deintdt", "float*"), OUT("eint", "float*"),
+      SC("N", "usize"), SC("dt", "float") }, l_ig_mp_midpoint);
+aqc_registrar r_ig_mp_c("cfd/ideal_gas/time_scheme/midpoint.cl", "corrector", 0,
+    { IN("imove", "int*"), IN("eint_in", "float*"), IN("deintdt", "float*"), OUT("eint", "float*"),
+      SC("N", "usize"), SC("dt", "float") }, l_ig_mp_corrector);
+aqc_registrar r_ig_mp_r("cfd/ideal_gas/time_scheme/midpoint.cl", "relax", 0,
+    { IN("imove", "int*"), IN("deintdt_in", "float*"), OUT("deintdt", "float*"), SC("N", "usize"),
+      SC("relax_midpoint", "float") }, l_ig_mp_relax, 1ull << 4);
 
 } // namespace

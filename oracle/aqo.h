@@ -290,4 +290,23 @@ void aqo_sym_set(const aqo_usize* mirror_src, float* m, float* u_in, float* dudt
                  float* drhodt_in, float* drhodt, aqo_usize N, const float* symmetry_n, int dims);
 void aqo_sym_sort(const aqo_usize* mirror_src_in, aqo_usize* mirror_src, const aqo_usize* id_sorted, aqo_usize N);
 
+/* cfd/ideal_gas: the element-wise kernels (EOS.cl:56-70, Rates.cl:53-68, Sort.cl:43-58, TimeStep.cl:62-97,
+ * riemann/Rates.cl:39-53, time_scheme/midpoint.cl:47-144) */
+void aqo_ig_eos(const aqo_usize* iset, const int* imove, const float* rho, const float* eint, float* p,
+                const float* gamma, aqo_usize N);
+void aqo_ig_rates(const int* imove, const float* rho, const float* p, const float* div_u, float* deintdt,
+                  aqo_usize N);
+void aqo_ig_sort(const float* eint_in, float* eint, const float* deintdt, float* deintdt_in,
+                 const aqo_usize* id_sorted, aqo_usize N);
+void aqo_ig_timestep(const aqo_defs* D, float* dt_var, const int* imove, const aqo_usize* iset, const float* u,
+                     const float* rho, const float* p, aqo_usize N, float dt, float dt_min, float courant,
+                     const float* div_u, const float* grad_p, const float* gamma);
+void aqo_ig_riemann_rates(const int* imove, const float* work_density, float* deintdt, aqo_usize N);
+void aqo_ig_mp_predictor(const float* eint, const float* deintdt, float* eint_in, float* deintdt_in, aqo_usize N);
+void aqo_ig_mp_midpoint(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
+                        float dt);
+void aqo_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, aqo_usize N, float relax_midpoint);
+void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
+                         float dt);
+
 #endif

@@ -1665,3 +1665,116 @@ void aqo_sym_sort(const aqo_usize* mirror_src_in, aqo_usize* mirror_src, const a
     AQO_FOR_I(N)
         mirror_src[id_sorted[i]] = mirror_src_in[i];
 }
+
+/* ================= cfd/ideal_gas: the element-wise kernels ================= *
+ * (the internal energy next to rho / u of the weakly compressible scheme: the presets under cfd/ideal_gas,
+ * examples/2D/shock_*) */
+
+/* cfd/ideal_gas/EOS.cl:56-70; EXCLUDED_PARTICLE :32-34 */
+void aqo_ig_eos(const aqo_usize* iset, const int* imove, const float* rho, const float* eint, float* p,
+                const float* gamma, aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        if ((imove[i] <= 0) && (imove[i] != -1))
+            continue;
+        p[i] = (gamma[iset[i]] - 1.0f) * rho[i] * eint[i];
+    }
+}
+
+/* cfd/ideal_gas/Rates.cl:53-68 */
+void aqo_ig_rates(const int* imove, const float* rho, const float* p, const float* div_u, float* deintdt,
+                  aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] != 1)
+            continue;
+        deintdt[i] = -p[i] / (rho[i] * rho[i]) * div_u[i];
+    }
+}
+
+/* cfd/ideal_gas/Sort.cl:43-58 */
+void aqo_ig_sort(const float* eint_in, float* eint, const float* deintdt, float* deintdt_in,
+                 const aqo_usize* id_sorted, aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        const aqo_usize o = id_sorted[i];
+        eint[o] = eint_in[i];
+        deintdt_in[o] = deintdt[i];
+    }
+}
+
+/* cfd/ideal_gas/TimeStep.cl:62-97; sound_speed.hcl:22-25; length() of a vec takes every component */
+void aqo_ig_timestep(const aqo_defs* D, float* dt_var, const int* imove, const aqo_usize* iset, const float* u,
+                     const float* rho, const float* p, aqo_usize N, float dt, float dt_min, float courant,
+                     const float* div_u, const float* grad_p, const float* gamma)
+{
+    const int vs = VS(D->dims);
+    AQO_FOR_I(N) {
+        if (imove[i] <= 0) {
+            dt_var[i] = dt;
+            continue;
+        }
+        const float dxx = D->H;
+        const float s_i = sqrtf(gamma[iset[i]] * p[i] / rho[i]);
+        float g2 = 0.f, u2 = 0.f;
+        for (int c = 0; c < vs; c++) {
+            g2 = c ? g2 + grad_p[vs * i + c] * grad_p[vs * i + c] : grad_p[vs * i] * grad_p[vs * i];
+            u2 = c ? u2 + u[vs * i + c] * u[vs * i + c] : u[vs * i] * u[vs * i];
+        }
+        const float lg = sqrtf(g2), lu = sqrtf(u2);
+        const float a = 4.0f * dxx * div_u[i] / rho[i];
+        const float dt_u1 = courant * 0.4f * dxx / sqrtf(a * a + s_i * s_i);
+        const float dt_u2 = courant * sqrtf(dxx / lg);
+        const float dt_u3 = courant * 0.4f * dxx / sqrtf(lu * lu + s_i * s_i);
+        /* OpenCL min(x, y) = y < x ? y : x, max(x, y) = x < y ? y : x */
+        float m12 = dt_u2 < dt_u1 ? dt_u2 : dt_u1;
+        const float dt_u = dt_u3 < m12 ? dt_u3 : m12;
+        const float lo = dt_u < dt ? dt_u : dt;
+        dt_var[i] = lo < dt_min ? dt_min : lo;
+    }
+}
+
+/* cfd/ideal_gas/riemann/Rates.cl:39-53 */
+void aqo_ig_riemann_rates(const int* imove, const float* work_density, float* deintdt, aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] != 1)
+            continue;
+        deintdt[i] = -work_density[i];
+    }
+}
+
+/* cfd/ideal_gas/time_scheme/midpoint.cl: predictor :47-59, midpoint :75-88, relax :101-115, corrector :131-144 */
+void aqo_ig_mp_predictor(const float* eint, const float* deintdt, float* eint_in, float* deintdt_in, aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        deintdt_in[i] = deintdt[i];
+        eint_in[i] = eint[i];
+    }
+}
+void aqo_ig_mp_midpoint(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
+                        float dt)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] <= 0)
+            continue;
+        eint[i] = eint_in[i] + 0.5f * dt * deintdt[i];
+    }
+}
+void aqo_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, aqo_usize N, float relax_midpoint)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] <= 0)
+            continue;
+        deintdt[i] = relax_midpoint * deintdt_in[i] + (1.f - relax_midpoint) * deintdt[i];
+    }
+}
+void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
+                         float dt)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] <= 0)
+            continue;
+        eint[i] = eint_in[i] + dt * deintdt[i];
+    }
+}

@@ -707,6 +707,34 @@ class Interpreter:
         elif key == ("cfd/Boundary/BI/NoSlip.cl", "entry"):
             c("bi_noslip", D, self.ll(), V["iset"], V["imove"], V["r"], V["normal"], V["u"], V["rho"], V["m"],
               V["lap_u"], int(V["noslip_iset"]), f32("dr"))
+        elif rel.startswith("cfd/ideal_gas/") and (rel, entry) in (
+                ("cfd/ideal_gas/EOS.cl", "entry"), ("cfd/ideal_gas/Rates.cl", "entry"),
+                ("cfd/ideal_gas/Sort.cl", "entry"), ("cfd/ideal_gas/TimeStep.cl", "entry"),
+                ("cfd/ideal_gas/riemann/Rates.cl", "entry"),
+                ("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor"),
+                ("cfd/ideal_gas/time_scheme/midpoint.cl", "midpoint"),
+                ("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"),
+                ("cfd/ideal_gas/time_scheme/midpoint.cl", "corrector")):
+            # the element-wise kernels of the ideal-gas presets (aqo_kernels.c, bit-identical to the scripts)
+            if rel.endswith("EOS.cl"):
+                c("ig_eos", V["iset"], V["imove"], V["rho"], V["eint"], V["p"], V["gamma"], N)
+            elif rel == "cfd/ideal_gas/Rates.cl":
+                c("ig_rates", V["imove"], V["rho"], V["p"], V["div_u"], V["deintdt"], N)
+            elif rel.endswith("Sort.cl"):
+                O.call("ig_sort", V["eint_in"], V["eint"], V["deintdt"], V["deintdt_in"], V["id_sorted"], N)
+            elif rel.endswith("TimeStep.cl"):
+                c("ig_timestep", D, V["dt_var"], V["imove"], V["iset"], V["u"], V["rho"], V["p"], N, f32("dt"),
+                  f32("dt_min"), f32("courant"), V["div_u"], V["grad_p"], V["gamma"])
+            elif rel.endswith("riemann/Rates.cl"):
+                c("ig_riemann_rates", V["imove"], V["work_density"], V["deintdt"], N)
+            elif entry == "predictor":
+                c("ig_mp_predictor", V["eint"], V["deintdt"], V["eint_in"], V["deintdt_in"], N)
+            elif entry == "midpoint":
+                c("ig_mp_midpoint", V["imove"], V["eint_in"], V["deintdt"], V["eint"], N, f32("dt"))
+            elif entry == "relax":
+                c("ig_mp_relax", V["imove"], V["deintdt_in"], V["deintdt"], N, f32("relax_midpoint"))
+            else:
+                c("ig_mp_corrector", V["imove"], V["eint_in"], V["deintdt"], V["eint"], N, f32("dt"))
         elif rel == "cfd/Boundary/Symmetry/Mirror.cl":
             # preset cfd/symmetry.xml: detect / feed / set / sort / drop (aqo_kernels.c, bit-identical to the script)
             if entry == "detect":

@@ -41,6 +41,8 @@ SCRIPTS = [
     "cfd/Energy/EnergyKin.cl", "cfd/Forces/Forces.cl", "basic/DensityClamp.cl", "basic/IdInverse.cl",
     "basic/time_scheme/adam_bashforth.cl", "cfd/Boundary/BI/NoSlip.cl",
     "cfd/Boundary/Symmetry/Mirror.cl",
+    "cfd/ideal_gas/EOS.cl", "cfd/ideal_gas/Rates.cl", "cfd/ideal_gas/Sort.cl", "cfd/ideal_gas/TimeStep.cl",
+    "cfd/ideal_gas/riemann/Rates.cl", "cfd/ideal_gas/time_scheme/midpoint.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

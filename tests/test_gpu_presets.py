@@ -538,3 +538,39 @@ def test_standing_wave_with_symmetry_planes_pipeline(oracle):
     # both planes mirrored something, and what they mirrored was dropped again
     assert (I.V["imove"] == -256).sum() > 0 and (I.V["mirror_src"] < N).sum() > 0
     sim.close()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_ideal_gas_elementwise_kernels(oracle, dims):
+    """cfd/ideal_gas/{EOS, Rates, Sort, TimeStep}.cl, riemann/Rates.cl and time_scheme/midpoint.cl::predictor /
+    midpoint / relax / corrector (the ideal-gas presets of examples/2D/shock_*) through the
+    Kernel-tool C-ABI against the oracle, which is bit-identical to the reference's scripts
+    (tests/test_oracle_vs_reference.py): products, quotients and square roots without contraction -- bit-exact."""
+    from test_oracle_vs_reference import _ideal_gas_state
+    import oracle.oracle as O
+    g, o, N = _ideal_gas_state(dims, 13)
+    D = O.make_defs(dims, o["h"])
+    ctx = _lib.Context(0, dims=dims, h=o["h"])
+    d = {k: (ctx.array(v) if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    oracle.call("ig_eos", o["iset"], o["imove"], o["rho"], o["eint"], o["p"], o["gamma"], N)
+    oracle.call("ig_rates", o["imove"], o["rho"], o["p"], o["div_u"], o["deintdt"], N)
+    oracle.call("ig_timestep", D, o["dt_var"], o["imove"], o["iset"], o["u"], o["rho"], o["p"], N, o["dt"],
+                o["dt_min"], o["courant"], o["div_u"], o["grad_p"], o["gamma"])
+    oracle.call("ig_mp_predictor", o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N)
+    oracle.call("ig_riemann_rates", o["imove"], o["work_density"], o["deintdt"], N)
+    oracle.call("ig_mp_midpoint", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
+    oracle.call("ig_mp_relax", o["imove"], o["deintdt_in"], o["deintdt"], N, o["relax_midpoint"])
+    oracle.call("ig_mp_corrector", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
+    o["eint_in"][...] = o["eint"]
+    oracle.call("ig_sort", o["eint_in"], o["eint"], o["deintdt"], o["deintdt_in"], o["id_sorted"], N)
+    for script, entry in (("EOS.cl", "entry"), ("Rates.cl", "entry"), ("TimeStep.cl", "entry"),
+                          ("time_scheme/midpoint.cl", "predictor"), ("riemann/Rates.cl", "entry"),
+                          ("time_scheme/midpoint.cl", "midpoint"), ("time_scheme/midpoint.cl", "relax"),
+                          ("time_scheme/midpoint.cl", "corrector")):
+        ctx.launch("cfd/ideal_gas/" + script, entry, d)
+    ctx.copy(d["eint_in"], d["eint"])
+    ctx.launch("cfd/ideal_gas/Sort.cl", "entry", d)
+    for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
+        assert np.array_equal(d[k].get(), o[k]), k
+    assert (1 << 4) == _lib.lib().aqc_kernel_dev_scalars(ctx.lookup("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"))
+    ctx.close()

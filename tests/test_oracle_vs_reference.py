@@ -455,3 +455,68 @@ def test_symmetry_mirror_kernels_match_reference_script(oracle, dims):
     dn = ((b["r_in"][twins] - sr) * sn).sum(1) + ((b["r_in"][src[twins]] - sr) * sn).sum(1)
     assert np.abs(dn).max() < 1e-5
     assert (b["imove"][twins][((b["r_in"][twins] - sr) * sn).sum(1) > 1e-6] == -256).all()
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_ideal_gas_elementwise_kernels_match_reference_scripts(oracle, dims):
+    """cfd/ideal_gas/{EOS, Rates, Sort, TimeStep}.cl, riemann/Rates.cl and time_scheme/midpoint.cl
+    (predictor, midpoint, relax, corrector): the C restatements are bit-identical to the reference's
+    scripts (products, quotients and square roots without contraction; OpenCL's min / max argument order)."""
+    a, b, N = _ideal_gas_state(dims, 13)
+    R = ref.Ref(dims, a["h"])
+    D = oracle.make_defs(dims, a["h"])
+    R.run("cfd/ideal_gas/EOS.cl", "entry", N, a)
+    oracle.call("ig_eos", b["iset"], b["imove"], b["rho"], b["eint"], b["p"], b["gamma"], N)
+    R.run("cfd/ideal_gas/Rates.cl", "entry", N, a)
+    oracle.call("ig_rates", b["imove"], b["rho"], b["p"], b["div_u"], b["deintdt"], N)
+    R.run("cfd/ideal_gas/TimeStep.cl", "entry", N, a)
+    oracle.call("ig_timestep", D, b["dt_var"], b["imove"], b["iset"], b["u"], b["rho"], b["p"], N, a["dt"],
+                a["dt_min"], a["courant"], b["div_u"], b["grad_p"], b["gamma"])
+    R.run("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor", N, a)
+    oracle.call("ig_mp_predictor", b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N)
+    R.run("cfd/ideal_gas/riemann/Rates.cl", "entry", N, a)
+    oracle.call("ig_riemann_rates", b["imove"], b["work_density"], b["deintdt"], N)
+    R.run("cfd/ideal_gas/time_scheme/midpoint.cl", "midpoint", N, a)
+    oracle.call("ig_mp_midpoint", b["imove"], b["eint_in"], b["deintdt"], b["eint"], N, a["dt"])
+    R.run("cfd/ideal_gas/time_scheme/midpoint.cl", "relax", N, a)
+    oracle.call("ig_mp_relax", b["imove"], b["deintdt_in"], b["deintdt"], N, a["relax_midpoint"])
+    R.run("cfd/ideal_gas/time_scheme/midpoint.cl", "corrector", N, a)
+    oracle.call("ig_mp_corrector", b["imove"], b["eint_in"], b["deintdt"], b["eint"], N, a["dt"])
+    # the sort reads the *_in / rate arrays of the step and scatters them (basic/Sort.cl's companion)
+    a["eint_in"][...] = a["eint"]
+    b["eint_in"][...] = b["eint"]
+    R.run("cfd/ideal_gas/Sort.cl", "entry", N, a)
+    oracle.call("ig_sort", b["eint_in"], b["eint"], b["deintdt"], b["deintdt_in"], b["id_sorted"], N)
+    for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
+        assert a[k].tobytes() == b[k].tobytes(), k
+    fl = a["imove"] == 1
+    assert np.isfinite(a["dt_var"]).all() and (a["dt_var"][~(a["imove"] > 0)] == np.float32(a["dt"])).all()
+    assert (a["dt_var"][fl] < np.float32(a["dt"])).any() and (a["dt_var"] >= np.float32(a["dt_min"])).all()
+
+
+def _ideal_gas_state(dims, seed):
+    """Two equal states (reference / restatement) of a gas: dam-break particle classes, positive rho, p, eint."""
+    case = cases.dam_break(dims, 10 if dims == 3 else 40, 2.0)
+    N, V = case["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(seed)
+
+    def pos(lo, hi):
+        return rng.uniform(lo, hi, N).astype(np.float32)
+
+    def vec(s):
+        v = (s * rng.normal(size=(N, V))).astype(np.float32)
+        if dims == 3:
+            v[:, 3] = 0
+        return v
+
+    imove = np.ascontiguousarray(case["imove"]).copy()
+    imove[rng.random(N) < 0.05] = -1          # (the class EXCLUDED_PARTICLE of the EOS lets through)
+    a = dict(imove=imove, iset=(rng.random(N) < 0.5).astype(np.uint32), rho=pos(0.5, 2.0), eint=pos(1.0, 3.0),
+             p=pos(0.5, 2.0), div_u=(3 * rng.normal(size=N)).astype(np.float32), deintdt=pos(-1.0, 1.0),
+             dt_var=np.zeros(N, np.float32), u=vec(1.0), dudt=vec(1.0), grad_p=vec(5.0), m=pos(0.1, 0.2),
+             gamma=np.array([1.4, 1.6667], np.float32), work_density=pos(-1.0, 1.0), eint_in=pos(1.0, 3.0),
+             deintdt_in=pos(-1.0, 1.0), id_sorted=rng.permutation(N).astype(np.uint32))
+    b = {k: v.copy() for k, v in a.items()}
+    for d in (a, b):
+        d.update(N=N, dt=2.5e-3, dt_min=1e-5, courant=0.25, h=case["h"], relax_midpoint=0.35)
+    return a, b, N

@@ -340,3 +340,76 @@ def test_symmetry_mirror_kernel_bodies_match_the_oracle(oracle, emu, dims):
     for k in e:
         assert e[k].tobytes() == o[k].tobytes(), k
     assert (o["mirror_src_in"] < N).sum() == int(o["imirror"].sum()) > 0 and (o["imove"] == -256).sum() > 0
+
+
+# ---- cfd/ideal_gas: the element-wise kernels ---------------------------------------------------------------
+IG_WRAP = r"""
+extern "C" void emu_ig(int dims, const uint32_t* iset, const int* imove, const float* rho, float* eint, float* p,
+                       const float* gamma, const float* div_u, float* deintdt, float* dt_var, const void* u,
+                       const void* grad_p, const float* work_density, float* eint_in, float* deintdt_in,
+                       const uint32_t* id_sorted, uint32_t N, float dt, float dt_min, float courant, float H,
+                       float relax)
+{
+    aqc_sv<float> rx{ nullptr, relax };
+    for (g_i = 0; g_i < N; g_i++) k_ig_eos(iset, imove, rho, eint, p, gamma, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_rates(imove, rho, p, div_u, deintdt, N);
+    FOR_ALL(k_ig_timestep<3>(dt_var, imove, iset, u, rho, p, N, dt, dt_min, courant, div_u, grad_p, gamma, H),
+            k_ig_timestep<2>(dt_var, imove, iset, u, rho, p, N, dt, dt_min, courant, div_u, grad_p, gamma, H))
+    for (g_i = 0; g_i < N; g_i++) k_ig_mp_predictor(eint, deintdt, eint_in, deintdt_in, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_riemann_rates(imove, work_density, deintdt, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_mp_advance(imove, eint_in, deintdt, eint, N, 0.5f * dt);
+    for (g_i = 0; g_i < N; g_i++) k_ig_mp_relax(imove, deintdt_in, deintdt, N, rx);
+    for (g_i = 0; g_i < N; g_i++) k_ig_mp_advance(imove, eint_in, deintdt, eint, N, dt);
+    memcpy(eint_in, eint, 4 * (size_t)N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_sort(eint_in, eint, deintdt, deintdt_in, id_sorted, N);
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def emu_ig(tmp_path_factory):
+    src = open(CU).read()
+    a = src.index("template <int D> struct V;")
+    helpers = src[a:src.index("#define GID")]
+    a = src.index("// ---- cfd/ideal_gas:")
+    body = src[a:src.index("#define IN(n, t)")]
+    body = re.sub(r"^int l_\w+\(aqc_ctx\*[^\n]*\n\{\n.*?^\}\n", "", body, flags=re.S | re.M)
+    assert "LAUNCH(" not in body and "DISPATCH" not in body and "k_ig_mp_relax" in body
+    sv = "template <typename T> struct aqc_sv { const T* p; T v; T get() const { return p ? *p : v; } };\n"
+    d = tmp_path_factory.mktemp("emu_ig")
+    cpp, so = str(d / "emu.cpp"), str(d / "libemu.so")
+    open(cpp, "w").write(SHIM + sv + helpers + body +
+                         "#define FOR_ALL(CALL3, CALL2) for (g_i = 0; g_i < N; g_i++) { if (dims == 3) { CALL3; } "
+                         "else { CALL2; } }\n" + IG_WRAP)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                           "-fno-fast-math", "-o", so, cpp])
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_ideal_gas_kernel_bodies_match_the_oracle(oracle, emu_ig, dims):
+    """k_ig_* of elementwise.cu (cfd/ideal_gas/{EOS, Rates, Sort, TimeStep}.cl, riemann/Rates.cl,
+    time_scheme/midpoint.cl) in the order of tests/test_oracle_vs_reference.py, which pins the oracle to
+    the reference's scripts: the same bits."""
+    from test_oracle_vs_reference import _ideal_gas_state
+    import oracle.oracle as O
+    e, o, N = _ideal_gas_state(dims, 13)
+    D = O.make_defs(dims, o["h"])
+    oracle.call("ig_eos", o["iset"], o["imove"], o["rho"], o["eint"], o["p"], o["gamma"], N)
+    oracle.call("ig_rates", o["imove"], o["rho"], o["p"], o["div_u"], o["deintdt"], N)
+    oracle.call("ig_timestep", D, o["dt_var"], o["imove"], o["iset"], o["u"], o["rho"], o["p"], N, o["dt"],
+                o["dt_min"], o["courant"], o["div_u"], o["grad_p"], o["gamma"])
+    oracle.call("ig_mp_predictor", o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N)
+    oracle.call("ig_riemann_rates", o["imove"], o["work_density"], o["deintdt"], N)
+    oracle.call("ig_mp_midpoint", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
+    oracle.call("ig_mp_relax", o["imove"], o["deintdt_in"], o["deintdt"], N, o["relax_midpoint"])
+    oracle.call("ig_mp_corrector", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
+    o["eint_in"][...] = o["eint"]
+    oracle.call("ig_sort", o["eint_in"], o["eint"], o["deintdt"], o["deintdt_in"], o["id_sorted"], N)
+    emu_ig.emu_ig(dims, _p(e["iset"]), _p(e["imove"]), _p(e["rho"]), _p(e["eint"]), _p(e["p"]), _p(e["gamma"]),
+                  _p(e["div_u"]), _p(e["deintdt"]), _p(e["dt_var"]), _p(e["u"]), _p(e["grad_p"]),
+                  _p(e["work_density"]), _p(e["eint_in"]), _p(e["deintdt_in"]), _p(e["id_sorted"]), N,
+                  C.c_float(e["dt"]), C.c_float(e["dt_min"]), C.c_float(e["courant"]), C.c_float(D.H),
+                  C.c_float(e["relax_midpoint"]))
+    for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
+        assert e[k].tobytes() == o[k].tobytes(), k
