@@ -1679,6 +1679,25 @@ int l_ig_mp_relax(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// cfd/ideal_gas/symmetry/Mirror.cl:32-48 (sources are never mirrored particles themselves: no row is both
+// read and written)
+__global__ void __launch_bounds__(256)
+k_ig_sym_set(const uint32_t* mirror_src, float* eint_in, float* deintdt_in, float* deintdt, uint32_t N)
+{
+    GID;
+    const uint32_t s = mirror_src[i];
+    if (s >= N)
+        return;
+    eint_in[i] = eint_in[s];
+    deintdt[i] = deintdt_in[i] = deintdt_in[s];
+}
+int l_ig_sym_set(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_sym_set, N, (const uint32_t*)a[0], (float*)a[1], (float*)a[2], (float*)a[3], N);
+    return AQC_OK;
+}
+
 #define IN(n, t) { n, t, AQC_ARG_ARRAY_IN }
 #define OUT(n, t) { n, t, AQC_ARG_ARRAY_OUT }
 #define RO(n, t) { n, t, AQC_ARG_ARRAY_RO }
@@ -1952,6 +1971,9 @@ aqc_registrar r_ig_dt("cfd/ideal_gas/TimeStep.cl", "entry", 0,
 aqc_registrar r_ig_rrates("cfd/ideal_gas/riemann/Rates.cl", "entry", 0,
     { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("work_density", "float*"), OUT("deintdt", "float*"),
       SC("N", "usize") }, l_ig_riemann_rates);
+aqc_registrar r_ig_sym("cfd/ideal_gas/symmetry/Mirror.cl", "set", 0,
+    { IN("mirror_src", "usize*"), OUT("eint_in", "float*"), OUT("deintdt_in", "float*"), OUT("deintdt", "float*"),
+      SC("N", "usize") }, l_ig_sym_set);
 aqc_registrar r_ig_mp_p("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor", 0,
     { IN("eint", "float*"), IN("deintdt", "float*"), OUT("eint_in", "float*"), OUT("deintdt_in", "float*"),
       SC("N", "usize") }, l_ig_mp_predictor);

@@ -308,5 +308,7 @@ void aqo_ig_mp_midpoint(const int* imove, const float* eint_in, const float* dei
 void aqo_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, aqo_usize N, float relax_midpoint);
 void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
                          float dt);
+/* cfd/ideal_gas/symmetry/Mirror.cl:32-48 */
+void aqo_ig_sym_set(const aqo_usize* mirror_src, float* eint_in, float* deintdt_in, float* deintdt, aqo_usize N);
 
 #endif

@@ -1778,3 +1778,15 @@ void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* de
         eint[i] = eint_in[i] + dt * deintdt[i];
     }
 }
+
+/* cfd/ideal_gas/symmetry/Mirror.cl:32-48 (a mirrored particle copies the energy of its source) */
+void aqo_ig_sym_set(const aqo_usize* mirror_src, float* eint_in, float* deintdt_in, float* deintdt, aqo_usize N)
+{
+    AQO_FOR_I(N) {
+        const aqo_usize s = mirror_src[i];
+        if (s >= N)
+            continue;
+        eint_in[i] = eint_in[s];
+        deintdt[i] = deintdt_in[i] = deintdt_in[s];
+    }
+}

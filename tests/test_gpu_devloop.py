@@ -244,3 +244,36 @@ def test_tld_midpoint_loop_on_the_device_equals_the_host_loop(monkeypatch):
     assert H["report"] == D["report"]
     assert D["stats"] == (3, 15)            # five passes in every step
     assert H["used"] == D["used"]
+
+
+def test_lanes_are_ordered_by_their_events():
+    """aqc_lane_select / aqc_lane_event / aqc_lane_wait: work on the branch lane starts behind the event it
+    waits for and lane 0 goes on behind the branch's; without a wait the lanes are independent queues."""
+    import ctypes as C
+    L = _lib.lib()
+    ctx = _lib.Context(0, dims=3, h=0.1)
+    n = 1 << 25                                     # 128 MB per array: a fill takes tens of microseconds
+    a, b, c = ctx.zeros(n, np.float32), ctx.zeros(n, np.float32), ctx.zeros(n, np.float32)
+    ev1, ev2 = C.c_void_p(), C.c_void_p()
+    for rep in range(3):
+        v = np.float32(rep + 1.0)
+        ctx.fill(a, v.tobytes())                    # lane 0
+        ctx._chk(L.aqc_lane_event(ctx.h, C.byref(ev1)))
+        ctx._chk(L.aqc_lane_select(ctx.h, 1))
+        ctx._chk(L.aqc_lane_wait(ctx.h, ev1))
+        ctx.copy(b, a)                              # lane 1, behind the fill
+        ctx._chk(L.aqc_lane_event(ctx.h, C.byref(ev2)))
+        ctx._chk(L.aqc_lane_select(ctx.h, 0))
+        ctx.fill(c, v.tobytes())                    # lane 0, next to the copy
+        ctx._chk(L.aqc_lane_wait(ctx.h, ev2))
+        ctx.copy(c, b)                              # lane 0, behind the copy on lane 1
+        assert ctx.reduce(_lib.OP_MIN, c) == v and ctx.reduce(_lib.OP_MAX, c) == v
+        assert ctx.reduce(_lib.OP_MIN, b) == v
+    # loops and their recordings belong on lane 0
+    loop = ctx.loop(16)
+    ctx._chk(L.aqc_lane_select(ctx.h, 1))
+    with pytest.raises(_lib.AquaError, match="branch lane"):
+        loop.begin([(AQS_LOAD, 0, "u"), (AQS_SETCOND,)])
+    ctx._chk(L.aqc_lane_select(ctx.h, 0))
+    loop.close()
+    ctx.close()

@@ -570,6 +570,8 @@ def test_ideal_gas_elementwise_kernels(oracle, dims):
         ctx.launch("cfd/ideal_gas/" + script, entry, d)
     ctx.copy(d["eint_in"], d["eint"])
     ctx.launch("cfd/ideal_gas/Sort.cl", "entry", d)
+    oracle.call("ig_sym_set", o["mirror_src"], o["eint_in"], o["deintdt_in"], o["deintdt"], N)
+    ctx.launch("cfd/ideal_gas/symmetry/Mirror.cl", "set", d)
     for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
         assert np.array_equal(d[k].get(), o[k]), k
     assert (1 << 4) == _lib.lib().aqc_kernel_dev_scalars(ctx.lookup("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"))

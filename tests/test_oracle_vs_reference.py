@@ -487,8 +487,13 @@ def test_ideal_gas_elementwise_kernels_match_reference_scripts(oracle, dims):
     b["eint_in"][...] = b["eint"]
     R.run("cfd/ideal_gas/Sort.cl", "entry", N, a)
     oracle.call("ig_sort", b["eint_in"], b["eint"], b["deintdt"], b["deintdt_in"], b["id_sorted"], N)
+    # cfd/ideal_gas/symmetry/Mirror.cl::set (cfd/ideal_gas/symmetry.xml): mirrored rows copy their source's energy
+    R.run("cfd/ideal_gas/symmetry/Mirror.cl", "set", N, a)
+    oracle.call("ig_sym_set", b["mirror_src"], b["eint_in"], b["deintdt_in"], b["deintdt"], N)
     for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
         assert a[k].tobytes() == b[k].tobytes(), k
+    ms = a["mirror_src"] < N
+    assert ms.sum() > 10 and np.array_equal(a["eint_in"][ms], a["eint_in"][a["mirror_src"][ms]])
     fl = a["imove"] == 1
     assert np.isfinite(a["dt_var"]).all() and (a["dt_var"][~(a["imove"] > 0)] == np.float32(a["dt"])).all()
     assert (a["dt_var"][fl] < np.float32(a["dt"])).any() and (a["dt_var"] >= np.float32(a["dt_min"])).all()
@@ -516,6 +521,11 @@ def _ideal_gas_state(dims, seed):
              dt_var=np.zeros(N, np.float32), u=vec(1.0), dudt=vec(1.0), grad_p=vec(5.0), m=pos(0.1, 0.2),
              gamma=np.array([1.4, 1.6667], np.float32), work_density=pos(-1.0, 1.0), eint_in=pos(1.0, 3.0),
              deintdt_in=pos(-1.0, 1.0), id_sorted=rng.permutation(N).astype(np.uint32))
+    # mirrored particles (a fifth of the rows) point at sources that are not mirrored themselves
+    src = np.full(N, N, np.uint32)
+    mirrored = rng.random(N) < 0.2
+    src[mirrored] = rng.choice(np.flatnonzero(~mirrored), int(mirrored.sum())).astype(np.uint32)
+    a["mirror_src"] = src
     b = {k: v.copy() for k, v in a.items()}
     for d in (a, b):
         d.update(N=N, dt=2.5e-3, dt_min=1e-5, courant=0.25, h=case["h"], relax_midpoint=0.35)

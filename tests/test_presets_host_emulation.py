@@ -347,8 +347,8 @@ IG_WRAP = r"""
 extern "C" void emu_ig(int dims, const uint32_t* iset, const int* imove, const float* rho, float* eint, float* p,
                        const float* gamma, const float* div_u, float* deintdt, float* dt_var, const void* u,
                        const void* grad_p, const float* work_density, float* eint_in, float* deintdt_in,
-                       const uint32_t* id_sorted, uint32_t N, float dt, float dt_min, float courant, float H,
-                       float relax)
+                       const uint32_t* id_sorted, const uint32_t* mirror_src, uint32_t N, float dt, float dt_min,
+                       float courant, float H, float relax)
 {
     aqc_sv<float> rx{ nullptr, relax };
     for (g_i = 0; g_i < N; g_i++) k_ig_eos(iset, imove, rho, eint, p, gamma, N);
@@ -362,6 +362,7 @@ extern "C" void emu_ig(int dims, const uint32_t* iset, const int* imove, const f
     for (g_i = 0; g_i < N; g_i++) k_ig_mp_advance(imove, eint_in, deintdt, eint, N, dt);
     memcpy(eint_in, eint, 4 * (size_t)N);
     for (g_i = 0; g_i < N; g_i++) k_ig_sort(eint_in, eint, deintdt, deintdt_in, id_sorted, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_sym_set(mirror_src, eint_in, deintdt_in, deintdt, N);
 }
 """
 
@@ -406,9 +407,10 @@ def test_ideal_gas_kernel_bodies_match_the_oracle(oracle, emu_ig, dims):
     oracle.call("ig_mp_corrector", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
     o["eint_in"][...] = o["eint"]
     oracle.call("ig_sort", o["eint_in"], o["eint"], o["deintdt"], o["deintdt_in"], o["id_sorted"], N)
+    oracle.call("ig_sym_set", o["mirror_src"], o["eint_in"], o["deintdt_in"], o["deintdt"], N)
     emu_ig.emu_ig(dims, _p(e["iset"]), _p(e["imove"]), _p(e["rho"]), _p(e["eint"]), _p(e["p"]), _p(e["gamma"]),
                   _p(e["div_u"]), _p(e["deintdt"]), _p(e["dt_var"]), _p(e["u"]), _p(e["grad_p"]),
-                  _p(e["work_density"]), _p(e["eint_in"]), _p(e["deintdt_in"]), _p(e["id_sorted"]), N,
+                  _p(e["work_density"]), _p(e["eint_in"]), _p(e["deintdt_in"]), _p(e["id_sorted"]), _p(e["mirror_src"]), N,
                   C.c_float(e["dt"]), C.c_float(e["dt_min"]), C.c_float(e["courant"]), C.c_float(D.H),
                   C.c_float(e["relax_midpoint"]))
     for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
