@@ -1417,6 +1417,85 @@ struct PBINoSlip : PBase {
     }
 };
 
+// cfd/ideal_gas/riemann/Interactions.cl:50-168 (examples/2D/shock_1d, shock_point_riemann): the acoustic
+// Riemann solver between fluid particles -- along the line of centres l_ij the pair meets at the star
+// state (u*, p*), which replaces the particle averages in the continuity, momentum and energy sums.
+// Per j: c_j = 2 m_j / (rho_j H) * wconF * CONW and rs_j = rho_j s_j are staged; per i the sums are
+// divided / multiplied by rho_i once, at the end.  The self pair (l_ij undefined) is left out by the
+// test, like the script's i == j.
+template <int D>
+struct PRiemann : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr int DIMS = D, NJ4 = 3;
+    const uint32_t* iset;
+    const void *r, *u;
+    const float *rho, *m, *p, *gamma;
+    void* grad_p;
+    float *div_u, *work_density;
+    float cF; // 2 / H * wconF * CONW
+    struct IState { float x, y, z, ux, uy, uz, p, rs, gx, gy, gz, du, wd; };
+    __device__ bool i_active(int mv) const { return mv == 1; }
+    __device__ float rs_of(uint32_t k) const
+    {
+        const float rho_k = __ldg(rho + k);
+        return rho_k * sqrtf(__ldg(gamma + __ldg(iset + k)) * __ldg(p + k) / rho_k); // sound_speed.hcl:22-25
+    }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.p = __ldg(p + i);
+        s.rs = rs_of(i);
+        s.gx = s.gy = s.gz = s.du = s.wd = 0.f;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec<D>(u, j);
+        const bool ok = __ldg(imove + j) == 1;
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cF * __ldg(m + j) / __ldg(rho + j));
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(p + j));
+        o[2] = make_float4(ok ? rs_of(j) : 1.f, 0.f, 0.f, 0.f);
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        const float d2 = dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z);
+        return d2 < cut2 && d2 > 0.f;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float rs_j = row[2 * stride].x;
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = D == 3 ? A.z - s.z : 0.f;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float il = 1.f / sqrtf(d2);
+        const float lx = dx * il, ly = dy * il, lz = dz * il;
+        const float q = sqrtf(d2) * invH;
+        float u_R_i = s.ux * lx + s.uy * ly, u_R_j = B.x * lx + B.y * ly;
+        if constexpr (D == 3) {
+            u_R_i += s.uz * lz;
+            u_R_j += B.z * lz;
+        }
+        const float inv = 1.f / (rs_j + s.rs);
+        const float u_star = (u_R_j * rs_j + u_R_i * s.rs - B.w + s.p) * inv;
+        const float p_star = (B.w * s.rs + s.p * rs_j - rs_j * s.rs * (u_R_j - u_R_i)) * inv;
+        const float t = 2.f - q;
+        const float w = -q * ((t * t) * (t * A.w)); // c_j * W'_ij
+        const float aux = (u_R_i - u_star) * w;
+        const float g = p_star * w;
+        s.du += aux;
+        s.gx -= g * lx; s.gy -= g * ly; s.gz -= g * lz;
+        s.wd += p_star * aux;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        stvec_xyz<D>(grad_p, i, s.gx * ir, s.gy * ir, s.gz * ir);
+        div_u[i] = s.du * rho_i;
+        work_density[i] = s.wd * ir;
+    }
+};
+
 // cfd/Boundary/ElasticBounce.cl:77-148 -- order dependent (u_i, dudt_i change inside the loop)
 template <int D>
 struct PElasticBounce : PBase {
@@ -2154,6 +2233,18 @@ template <int D> int run_bi_noslip(aqc_ctx* ctx, void* const* a)
     return launch_sweep(ctx, p, make_ll(a, 11, aqc_scalar<uint32_t>(a, 8)));
 }
 int l_bi_noslip(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_noslip, c, a); }
+template <int D> int run_ig_riemann(aqc_ctx* ctx, void* const* a)
+{
+    // (iset, imove, r, u, rho, m, p, grad_p, div_u, work_density, gamma, N, icell, ihoc, n_cells)
+    PRiemann<D> p;
+    set_base(p, ctx, a[1]);
+    p.iset = (const uint32_t*)a[0];
+    p.r = a[2]; p.u = a[3]; p.rho = (const float*)a[4]; p.m = (const float*)a[5]; p.p = (const float*)a[6];
+    p.grad_p = a[7]; p.div_u = (float*)a[8]; p.work_density = (float*)a[9]; p.gamma = (const float*)a[10];
+    p.cF = 2.f / ctx->defs.H * (Wend<D>::F * ctx->defs.CONW);
+    return launch_sweep(ctx, p, make_ll(a, 12, aqc_scalar<uint32_t>(a, 11)));
+}
+int l_ig_riemann(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_ig_riemann, c, a); }
 template <int D> int run_elastic_bounce(aqc_ctx* ctx, void* const* a)
 {
     PElasticBounce<D> p;
@@ -2395,6 +2486,10 @@ aqc_registrar r_bi_noslip("cfd/Boundary/BI/NoSlip.cl", "entry", 0,
     { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), IN("u", "vec*"),
       IN("rho", "float*"), IN("m", "float*"), OUT("lap_u", "vec*"), SC("N", "usize"),
       SC("noslip_iset", "uint"), SC("dr", "float"), LL_ARGS }, l_bi_noslip);
+aqc_registrar r_ig_riemann("cfd/ideal_gas/riemann/Interactions.cl", "entry", 0,
+    { IN("iset", "uint*"), IN("imove", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
+      IN("m", "float*"), IN("p", "float*"), OUT("grad_p", "vec*"), OUT("div_u", "float*"),
+      OUT("work_density", "float*"), IN("gamma", "float*"), SC("N", "usize"), LL_ARGS }, l_ig_riemann);
 aqc_registrar r_elastic("cfd/Boundary/ElasticBounce.cl", "entry", 0,
     { IN("imove", "int*"), IN("r", "vec*"), IN("normal", "vec*"), OUT("u", "vec*"),
       OUT("dudt", "vec*"), SC("N", "usize"), SC("dr", "float"), SC("dt", "float"), LL_ARGS },

@@ -308,6 +308,10 @@ void aqo_ig_mp_midpoint(const int* imove, const float* eint_in, const float* dei
 void aqo_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, aqo_usize N, float relax_midpoint);
 void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
                          float dt);
+/* cfd/ideal_gas/riemann/Interactions.cl:50-168 */
+void aqo_ig_riemann_interactions(const aqo_defs* D, const aqo_ll* L, const aqo_usize* iset, const int* imove,
+                                 const float* r, const float* u, const float* rho, const float* m, const float* p,
+                                 float* grad_p, float* div_u, float* work_density, const float* gamma);
 /* cfd/ideal_gas/symmetry/Mirror.cl:32-48 */
 void aqo_ig_sym_set(const aqo_usize* mirror_src, float* eint_in, float* deintdt_in, float* deintdt, aqo_usize N);
 

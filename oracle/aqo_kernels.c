@@ -1790,3 +1790,57 @@ void aqo_ig_sym_set(const aqo_usize* mirror_src, float* eint_in, float* deintdt_
         deintdt[i] = deintdt_in[i] = deintdt_in[s];
     }
 }
+
+/* cfd/ideal_gas/riemann/Interactions.cl:50-168: the pair terms of the acoustic Riemann solver between fluid
+ * particles (LOCAL_MEM_SIZE is always defined, Kernel.cpp:411: the sums start at zero and overwrite) */
+void aqo_ig_riemann_interactions(const aqo_defs* D, const aqo_ll* L, const aqo_usize* iset, const int* imove,
+                                 const float* r, const float* u, const float* rho, const float* m, const float* p,
+                                 float* grad_p, float* div_u, float* work_density, const float* gamma)
+{
+    const int dims = D->dims, vs = VS(dims);
+    const float H = D->H;
+    AQO_FOR_I(L->N) {
+        if (imove[i] != 1)
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* u_i = u + (size_t)i * vs;
+        const float p_i = p[i], rho_i = rho[i];
+        const float s_i = sqrtf(gamma[iset[i]] * p_i / rho_i);
+        const float rs_i = rho_i * s_i;
+        float gp[3] = { 0.f, 0.f, 0.f }, du = 0.f, wd = 0.f;
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if (i == j)
+                continue;
+            if (imove[j] != 1)
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float rho_j = rho[j], p_j = p[j], m_j = m[j];
+            const float s_j = sqrtf(gamma[iset[j]] * p_j / rho_j);
+            const float len = sqrtf(dotv(r_ij, r_ij, dims));
+            float l_ij[3];
+            for (int d = 0; d < dims; d++)
+                l_ij[d] = r_ij[d] / len;
+            const float u_R_i = dotv(u_i, l_ij, dims);
+            const float u_R_j = dotv(u + (size_t)j * vs, l_ij, dims);
+            const float rs_j = rho_j * s_j;
+            const float auxiliary_val = 1.0f / (rs_j + rs_i);
+            const float u_star = (u_R_j * rs_j + u_R_i * rs_i - p_j + p_i) * auxiliary_val;
+            const float p_star = (p_j * rs_i + p_i * rs_j - rs_j * rs_i * (u_R_j - u_R_i)) * auxiliary_val;
+            const float Wij_prima = -q * kernelF(q, dims) * D->CONW;
+            const float aux = 2.0f * m_j / (rho_j * H) * (u_R_i - u_star) * Wij_prima;
+            du += rho_i * aux;
+            const float g = 2.0f * m_j * p_star / (rho_j * rho_i * H) * Wij_prima;
+            for (int d = 0; d < dims; d++)
+                gp[d] -= g * l_ij[d];
+            wd += p_star / rho_i * aux;
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++)
+            grad_p[(size_t)i * vs + d] = gp[d];
+        work_density[i] = wd;
+        div_u[i] = du;
+    }
+}

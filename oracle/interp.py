@@ -711,6 +711,7 @@ class Interpreter:
                 ("cfd/ideal_gas/EOS.cl", "entry"), ("cfd/ideal_gas/Rates.cl", "entry"),
                 ("cfd/ideal_gas/Sort.cl", "entry"), ("cfd/ideal_gas/TimeStep.cl", "entry"),
                 ("cfd/ideal_gas/riemann/Rates.cl", "entry"), ("cfd/ideal_gas/symmetry/Mirror.cl", "set"),
+                ("cfd/ideal_gas/riemann/Interactions.cl", "entry"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "midpoint"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"),
@@ -725,6 +726,9 @@ class Interpreter:
             elif rel.endswith("TimeStep.cl"):
                 c("ig_timestep", D, V["dt_var"], V["imove"], V["iset"], V["u"], V["rho"], V["p"], N, f32("dt"),
                   f32("dt_min"), f32("courant"), V["div_u"], V["grad_p"], V["gamma"])
+            elif rel.endswith("riemann/Interactions.cl"):
+                c("ig_riemann_interactions", D, self.ll(), V["iset"], V["imove"], V["r"], V["u"], V["rho"], V["m"],
+                  V["p"], V["grad_p"], V["div_u"], V["work_density"], V["gamma"])
             elif rel.endswith("symmetry/Mirror.cl"):
                 c("ig_sym_set", V["mirror_src"], V["eint_in"], V["deintdt_in"], V["deintdt"], N)
             elif rel.endswith("riemann/Rates.cl"):

@@ -576,3 +576,40 @@ def test_ideal_gas_elementwise_kernels(oracle, dims):
         assert np.array_equal(d[k].get(), o[k]), k
     assert (1 << 4) == _lib.lib().aqc_kernel_dev_scalars(ctx.lookup("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"))
     ctx.close()
+
+
+@pytest.mark.parametrize("engine", [3, 2])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 60, 4.0)])
+def test_riemann_interactions_sweep(oracle, dims, n, hfac, engine):
+    """cfd/ideal_gas/riemann/Interactions.cl::entry (the acoustic Riemann solver of examples/2D/shock_1d and
+    shock_point_riemann) through the Kernel-tool C-ABI on both sweep engines vs the oracle, which is
+    bit-identical to the reference's script.  Tolerance of the sweep tests:
+    |gpu - oracle| <= 2e-6 max|oracle| + 2e-5 |oracle|; the rows of the other particle classes untouched."""
+    import pipeline
+    from test_oracle_vs_reference import riemann_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = riemann_inputs(s)
+    want = {k: x[k].copy() for k in ("grad_p", "div_u", "work_density")}
+    oracle.call("ig_riemann_interactions", oracle.make_defs(dims, s["h"]), pipeline._ll(s), x["iset"], s["imove"],
+                s["r"], x["u"], s["rho"], s["m"], x["p"], want["grad_p"], want["div_u"], want["work_density"],
+                x["gamma"])
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    c = pipeline.CudaState(ctx, s)
+    for k in ("u", "p", "iset", "grad_p", "div_u"):
+        c.set(k, x[k])
+    c.v["gamma"] = ctx.array(x["gamma"])
+    c.v["work_density"] = ctx.array(x["work_density"])
+    try:
+        assert _lib.lib().aqc_sweep_engine_select(engine) == engine
+        c.run("cfd/ideal_gas/riemann/Interactions.cl")
+        got = {k: c.get(k) for k in want}
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
+    ctx.close()
+    fl = s["imove"] == 1
+    for k in want:
+        a, b = want[k].astype(np.float64), got[k].astype(np.float64)
+        assert np.isfinite(b).all(), k
+        assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
+        assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 0, k

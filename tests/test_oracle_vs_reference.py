@@ -530,3 +530,42 @@ def _ideal_gas_state(dims, seed):
     for d in (a, b):
         d.update(N=N, dt=2.5e-3, dt_min=1e-5, courant=0.25, h=case["h"], relax_midpoint=0.35)
     return a, b, N
+
+
+def riemann_inputs(s, seed=6):
+    """A gas on the sorted dam-break particles: positive pressure, two heat-capacity ratios, random velocities;
+    outputs pre-filled (the script overwrites the fluid rows and leaves the others)."""
+    rng = np.random.default_rng(seed)
+    N, dims = s["N"], s["dims"]
+    V = 4 if dims == 3 else 2
+    u = np.zeros((N, V), np.float32)
+    u[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+    return dict(u=u, p=rng.uniform(0.5, 2.0, N).astype(np.float32), iset=(np.arange(N) % 2).astype(np.uint32),
+                gamma=np.array([1.4, 1.6667], np.float32), grad_p=np.full((N, V), 7.0, np.float32),
+                div_u=np.full(N, 7.0, np.float32), work_density=np.full(N, 7.0, np.float32))
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0)])
+def test_riemann_interactions_match_reference_script(oracle, dims, n, hfac):
+    """cfd/ideal_gas/riemann/Interactions.cl::entry (the acoustic Riemann solver between fluid particles,
+    examples/2D/shock_point_riemann, shock_1d): the C restatement is bit-identical to the script."""
+    import pipeline
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = riemann_inputs(s)
+    c = pipeline.RefState(ref.Ref(dims, case["h"]), s)
+    for k in ("u", "p", "iset", "grad_p", "div_u"):
+        c.set(k, x[k])
+    c.v["gamma"] = x["gamma"].copy()
+    c.v["work_density"] = x["work_density"].copy()
+    c.run("cfd/ideal_gas/riemann/Interactions.cl")
+    g, d, w = x["grad_p"].copy(), x["div_u"].copy(), x["work_density"].copy()
+    oracle.call("ig_riemann_interactions", oracle.make_defs(dims, s["h"]), pipeline._ll(s), x["iset"], s["imove"],
+                s["r"], x["u"], s["rho"], s["m"], x["p"], g, d, w, x["gamma"])
+    assert c.get("grad_p").tobytes() == g.tobytes()
+    assert c.get("div_u").tobytes() == d.tobytes() and c.get("work_density").tobytes() == w.tobytes()
+    fl = s["imove"] == 1
+    assert np.isfinite(g).all() and np.abs(g[fl][:, :dims]).max() > 1e-3 and np.abs(w[fl]).max() > 1e-3
+    assert (d[~fl] == 7.0).all() and (g[~fl] == 7.0).all()
+    if dims == 3:
+        assert (g[:, 3] == 7.0).all()     # only .XYZ is written

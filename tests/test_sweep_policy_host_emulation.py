@@ -97,6 +97,27 @@ extern "C" void emu_bi_inter(int dims, const int* imove, const void* r, const vo
     else
         run_inter<2>(imove, r, normal, u, rho, m, pp, grad_p, div_u, N, H, CONW, SUPPORT);
 }
+template <int D> static void run_riemann(const uint32_t* iset, const int* imove, const void* r, const void* u,
+                                         const float* rho, const float* m, const float* pp, void* grad_p, float* div_u,
+                                         float* work_density, const float* gamma, uint32_t N, float H, float CONW,
+                                         float SUPPORT)
+{
+    PRiemann<D> p;
+    sweep_all(p, imove, N, H, SUPPORT, [&](PRiemann<D>& q) {      // run_ig_riemann
+        q.iset = iset; q.r = r; q.u = u; q.rho = rho; q.m = m; q.p = pp; q.grad_p = grad_p; q.div_u = div_u;
+        q.work_density = work_density; q.gamma = gamma;
+        q.cF = 2.f / H * (Wend<D>::F * CONW);
+    });
+}
+extern "C" void emu_riemann(int dims, const uint32_t* iset, const int* imove, const void* r, const void* u,
+                            const float* rho, const float* m, const float* pp, void* grad_p, float* div_u,
+                            float* work_density, const float* gamma, uint32_t N, float H, float CONW, float SUPPORT)
+{
+    if (dims == 3)
+        run_riemann<3>(iset, imove, r, u, rho, m, pp, grad_p, div_u, work_density, gamma, N, H, CONW, SUPPORT);
+    else
+        run_riemann<2>(iset, imove, r, u, rho, m, pp, grad_p, div_u, work_density, gamma, N, H, CONW, SUPPORT);
+}
 extern "C" void emu_noslip(int dims, const uint32_t* iset, const int* imove, const void* r, const void* normal,
                            const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
                            uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
@@ -192,3 +213,30 @@ def test_harness_reproduces_a_gpu_verified_policy(oracle, emu, dims, n, hfac):
         a, b = a.astype(np.float64), b.astype(np.float64)
         assert np.all(np.abs(a - b) <= 5e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), np.abs(a - b).max()
     assert np.abs(want_g - gp).max() > 0
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 40, 4.0)])
+def test_riemann_policy_matches_the_oracle(oracle, emu, dims, n, hfac):
+    """PRiemann (cfd/ideal_gas/riemann/Interactions.cl): the policy, driven by the brute-force pair loop, against
+    the oracle (bit-identical to the script, tests/test_oracle_vs_reference.py) at the sweep tests' tolerance
+    -- the policy folds constants and divides by rho_i once per particle instead of once per pair."""
+    from test_oracle_vs_reference import riemann_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = riemann_inputs(s)
+    D = oracle.make_defs(dims, s["h"])
+    want = {k: x[k].copy() for k in ("grad_p", "div_u", "work_density")}
+    oracle.call("ig_riemann_interactions", D, pipeline._ll(s), x["iset"], s["imove"], s["r"], x["u"], s["rho"],
+                s["m"], x["p"], want["grad_p"], want["div_u"], want["work_density"], x["gamma"])
+    got = {k: x[k].copy() for k in want}
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)   # noqa: E731
+    arr = {k: np.ascontiguousarray(s[k]) for k in ("imove", "r", "rho", "m")}
+    emu.emu_riemann(dims, P(x["iset"]), P(arr["imove"]), P(arr["r"]), P(x["u"]), P(arr["rho"]), P(arr["m"]), P(x["p"]),
+                    P(got["grad_p"]), P(got["div_u"]), P(got["work_density"]), P(x["gamma"]), s["N"],
+                    C.c_float(D.H), C.c_float(D.CONW), C.c_float(D.SUPPORT))
+    fl = s["imove"] == 1
+    for k in want:
+        a, b = want[k].astype(np.float64), got[k].astype(np.float64)
+        assert np.isfinite(b).all(), k
+        assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
+        assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 1e-3, k
