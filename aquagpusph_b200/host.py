@@ -22,7 +22,7 @@ SYMBOLS = [
     "aqh_eval", "aqh_scalar_get", "aqh_scalar_set", "aqh_array_info", "aqh_array_download",
     "aqh_array_upload", "aqh_array_devptr", "aqh_set_script_runner", "aqh_variable_type",
     "aqh_eval_svm", "aqh_device_loops", "aqh_device_loop_stats", "aqh_loop_host_reason",
-    "aqh_device_loop_timing", "aqh_device_loop_branch_tools",
+    "aqh_device_loop_timing", "aqh_device_loop_branch_tools", "aqh_lane_schedule",
 ]
 
 

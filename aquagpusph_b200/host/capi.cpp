@@ -427,6 +427,41 @@ extern "C" int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* rec
     AQH_CATCH
 }
 
+extern "C" int aqh_lane_schedule(int n, const int* r_off, const int* r_var, const unsigned* r_rows, const int* w_off,
+                                 const int* w_var, const unsigned* w_rows, const double* cost,
+                                 const unsigned char* flags, double gain, int* lane_out, int* wait_out,
+                                 unsigned char* marked_out, int* last_lane1_out)
+{
+    AQH_TRY
+    if (n < 0 || !r_off || !w_off || !cost || !flags || !lane_out || !wait_out || !marked_out)
+        throw std::runtime_error("aqh_lane_schedule: NULL argument");
+    std::vector<CalcServer::LaneDep> deps(n);
+    for (int k = 0; k < n; k++) {
+        for (int e = r_off[k]; e < r_off[k + 1]; e++)
+            deps[k].r.emplace_back((const void*)(intptr_t)(r_var[e] + 1), r_rows[e]);
+        for (int e = w_off[k]; e < w_off[k + 1]; e++)
+            deps[k].w.emplace_back((const void*)(intptr_t)(w_var[e] + 1), w_rows[e]);
+        deps[k].cost = cost[k];
+        deps[k].forced0 = (flags[k] & 1) != 0;
+        deps[k].barrier = (flags[k] & 2) != 0;
+        deps[k].launches = (flags[k] & 4) == 0;
+    }
+    std::vector<int> lane;
+    std::vector<std::vector<int>> waits;
+    std::vector<char> marked;
+    int last1 = -1;
+    CalcServer::scheduleLanes(deps, gain, lane, waits, marked, last1);
+    for (int k = 0; k < n; k++) {
+        lane_out[k] = lane[k];
+        wait_out[k] = waits[k].empty() ? -1 : waits[k].back();
+        marked_out[k] = (unsigned char)marked[k];
+    }
+    if (last_lane1_out)
+        *last_lane1_out = last1;
+    return 0;
+    AQH_CATCH
+}
+
 extern "C" unsigned aqh_device_loop_branch_tools(aqh_sim* sim)
 {
     unsigned n = 0;

@@ -295,6 +295,67 @@ unsigned DeviceLoop::branchTools() const
     return _two_lanes ? n : 0;
 }
 
+// The schedule itself, free of tools and devices (tests/test_host_cpu.py checks it on random dependency
+// sets through aqh_lane_schedule: every conflicting pair ends up ordered).  List scheduling in pipeline
+// order: a tool that launches something goes to lane 1 when it could start there at least `gain` cost units
+// earlier than on lane 0; then, for every tool, the LAST conflicting tool of the other lane is the one
+// whose event it waits for (the lanes are in-order queues: that covers the earlier ones), unless its lane
+// has already waited for a later one.
+void scheduleLanes(const std::vector<LaneDep>& deps, double gain, std::vector<int>& lane_of,
+                   std::vector<std::vector<int>>& waits, std::vector<char>& marked, int& last_lane1)
+{
+    const size_t n = deps.size();
+    lane_of.assign(n, 0);
+    waits.assign(n, {});
+    marked.assign(n, 0);
+    last_lane1 = -1;
+    auto meets = [](const LaneDep::Access& a, const LaneDep::Access& b) {
+        for (auto& x : a)
+            for (auto& y : b)
+                if (x.first == y.first && (x.second & y.second))
+                    return true;
+        return false;
+    };
+    auto conflict = [&](const LaneDep& a, const LaneDep& b) {
+        return a.barrier || b.barrier || meets(a.w, b.r) || meets(a.w, b.w) || meets(a.r, b.w);
+    };
+    double free_at[2] = { 0.0, 0.0 };
+    std::vector<double> finish(n, 0.0);
+    for (size_t k = 0; k < n; k++) {
+        const LaneDep& d = deps[k];
+        if (!d.launches)
+            continue;
+        double ready = 0.0;
+        for (size_t u = 0; u < k; u++)
+            if (deps[u].launches && conflict(deps[u], d))
+                ready = std::max(ready, finish[u]);
+        const double r0 = std::max(ready, free_at[0]), r1 = std::max(ready, free_at[1]);
+        const int l = (!d.forced0 && !d.barrier && r1 + gain <= r0) ? 1 : 0;
+        lane_of[k] = l;
+        finish[k] = (l ? r1 : r0) + d.cost;
+        free_at[l] = finish[k];
+    }
+    int waited[2] = { -1, -1 }; // per lane: the newest tool of the OTHER lane it has waited for
+    for (size_t k = 0; k < n; k++) {
+        if (!deps[k].launches)
+            continue;
+        const int l = lane_of[k];
+        int last = -1;
+        for (size_t u = 0; u < k; u++)
+            if (deps[u].launches && lane_of[u] != l && conflict(deps[u], deps[k]))
+                last = (int)u;
+        if (last > waited[l]) {
+            waits[k].push_back(last);
+            marked[last] = 1;
+            waited[l] = last;
+        }
+        if (l == 1)
+            last_lane1 = (int)k;
+    }
+    if (last_lane1 >= 0)
+        marked[last_lane1] = 1; // the join at the end of the pass
+}
+
 // Which lane every tool of the body runs on, and the events it waits for.  Dependencies are whole
 // arrays (Tool::dependencies: what the fusion planner uses too): two tools conflict when one writes
 // what the other reads or writes.  Lanes come from list scheduling in pipeline order with a crude
@@ -401,63 +462,25 @@ void DeviceLoop::planLanes()
         add_all(d.w, out, AQC_ROWS_ANY);
         add_all(d.r, out, AQC_ROWS_ANY);
     }
-    auto meets = [](const Access& a, const Access& b) {
-        for (auto& x : a)
-            for (auto& y : b)
-                if (x.first == y.first && (x.second & y.second))
-                    return true;
-        return false;
-    };
-    auto conflict = [&](const Dep& a, const Dep& b) {
-        return a.barrier || b.barrier || meets(a.w, b.r) || meets(a.w, b.w) || meets(a.r, b.w);
-    };
     // (tuning knobs; the defaults are what was measured best on the dam break at 1.2 M particles)
     double gain = 3.0, sweep_cost = 10.0;
     if (const char* e = getenv("AQUA_LANE_GAIN"))
         gain = atof(e);
     if (const char* e = getenv("AQUA_LANE_SWEEP_COST"))
         sweep_cost = atof(e);
-    for (size_t k = 0; k < n; k++)
-        if (deps[k].cost >= 10.0)
-            deps[k].cost = deps[k].cost / 10.0 * sweep_cost;
-    double free_at[2] = { 0.0, 0.0 };
-    std::vector<double> finish(n, 0.0);
+    std::vector<LaneDep> ld(n);
     for (size_t k = 0; k < n; k++) {
-        Dep& d = deps[k];
-        if (!d.launches)
-            continue;
-        double ready = 0.0;
-        for (size_t u = 0; u < k; u++)
-            if (deps[u].launches && conflict(deps[u], d))
-                ready = std::max(ready, finish[u]);
-        const double r0 = std::max(ready, free_at[0]), r1 = std::max(ready, free_at[1]);
-        const int l = (!d.forced0 && r1 + gain <= r0) ? 1 : 0;
-        _lane_of[k] = l;
-        finish[k] = (l ? r1 : r0) + d.cost;
-        free_at[l] = finish[k];
+        for (auto& e : deps[k].r)
+            ld[k].r.emplace_back((const void*)e.first, e.second);
+        for (auto& e : deps[k].w)
+            ld[k].w.emplace_back((const void*)e.first, e.second);
+        ld[k].barrier = deps[k].barrier;
+        ld[k].forced0 = deps[k].forced0;
+        ld[k].launches = deps[k].launches;
+        ld[k].cost = deps[k].cost >= 10.0 ? deps[k].cost / 10.0 * sweep_cost : deps[k].cost;
     }
-    // events: the last conflicting tool of the other lane, unless the lane already waited past it
-    int waited[2] = { -1, -1 }; // per lane: the newest tool of the OTHER lane it has waited for
-    for (size_t k = 0; k < n; k++) {
-        if (!deps[k].launches)
-            continue;
-        const int l = _lane_of[k];
-        int last = -1;
-        for (size_t u = 0; u < k; u++)
-            if (deps[u].launches && _lane_of[u] != l && conflict(deps[u], deps[k]))
-                last = (int)u;
-        if (last > waited[l]) {
-            _waits[k].push_back(last);
-            _marked[last] = 1;
-            waited[l] = last;
-        }
-        if (l == 1) {
-            _two_lanes = true;
-            _last_lane1 = (int)k;
-        }
-    }
-    if (_last_lane1 >= 0)
-        _marked[_last_lane1] = 1; // the join at the end of the pass
+    scheduleLanes(ld, gain, _lane_of, _waits, _marked, _last_lane1);
+    _two_lanes = _last_lane1 >= 0;
     if (_two_lanes && logLevel() <= L_INFO) {
         std::string msg = "The loop \"" + _opener->name() + "\" runs these tools on a second stream:";
         for (size_t k = 0; k < n; k++)

@@ -57,6 +57,21 @@ class SvmCompiler {
     void* _user;
 };
 
+/// What one tool of a loop body reads and writes, for the two-lane schedule: opaque array keys with the
+/// particle classes (AQC_ROWS_*) of the rows involved
+struct LaneDep {
+    typedef std::vector<std::pair<const void*, unsigned>> Access;
+    Access r, w;
+    bool barrier = false;  ///< unknown dependencies: conflicts with everything
+    bool forced0 = false;  ///< must run on lane 0 (reductions, kernels reading the scalar table)
+    bool launches = true;  ///< false: nothing is enqueued at this position (scalar tools, fused followers)
+    double cost = 1.0;
+};
+/// lane_of[k] in {0, 1}; waits[k]: tools of the other lane whose event tool k waits for; marked[k]: an event is
+/// recorded behind tool k; last_lane1: the last tool on lane 1 (-1: none), joined at the end of the pass
+void scheduleLanes(const std::vector<LaneDep>& deps, double gain, std::vector<int>& lane_of,
+                   std::vector<std::vector<int>>& waits, std::vector<char>& marked, int& last_lane1);
+
 class DeviceLoop {
   public:
     /// body: the tools between the opening `while` (index `first` - 1) and its `end` (index `last`)

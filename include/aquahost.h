@@ -94,6 +94,17 @@ const char* aqh_loop_host_reason(aqh_sim* sim, int i);
 /* tools of the device loops' bodies that run on the second stream (aqc_lane_*: their arrays do not
  * meet those of the tools running meanwhile on the first; AQUA_DEVICE_LANES=0: none) */
 unsigned aqh_device_loop_branch_tools(aqh_sim* sim);
+/* The schedule behind it as a pure function (no device): n tools in pipeline order; tool k reads the arrays
+ * r_var[r_off[k] .. r_off[k+1]) (ids) in the rows r_rows[..] (AQC_ROWS_* masks) and writes w_var / w_rows
+ * likewise; cost[k] in element-wise-kernel units; flags[k]: 1 = must stay on lane 0, 2 = unknown dependencies
+ * (conflicts with everything), 4 = launches nothing.  Out: lane_out[k] in {0, 1}; wait_out[k] = the tool of
+ * the other lane whose event tool k waits for (-1: none); marked_out[k] = an event is recorded behind tool k.
+ * *last_lane1_out = the last tool on lane 1, joined at the end of the pass (-1: a single lane).
+ * tests/test_host_cpu.py checks on random instances that every conflicting pair is ordered by lane order
+ * and event waits. */
+int aqh_lane_schedule(int n, const int* r_off, const int* r_var, const unsigned* r_rows, const int* w_off,
+                      const int* w_var, const unsigned* w_rows, const double* cost, const unsigned char* flags,
+                      double gain, int* lane_out, int* wait_out, unsigned char* marked_out, int* last_lane1_out);
 int aqh_device_loop_timing(aqh_sim* sim, int* body_nodes, double* record_ms, double* instantiate_ms);
 
 /* type="python" tools (aquagpusph/CalcServer/Python.cpp:295-325).  The reference embeds CPython in

@@ -344,3 +344,146 @@ def test_svm_programs_equal_the_host_evaluator():
         sv("3e9", "int", dtype=np.int32)
     with pytest.raises(host.HostError, match="expects 2 arguments"):
         sv("atan2(1)")
+
+
+def _rand_expr(rng, names, depth=0):
+    """A random expression of the tokenizer's grammar (host/tokenizer.hpp)."""
+    r = rng.random()
+    if depth > 4 or r < 0.22:
+        if rng.random() < 0.5:
+            return str(rng.choice(names))
+        v = rng.choice([0, 1, 2, 3, 0.5, 0.25, 1.5, 7, 10, 1e-3, 2.5e2, 0.1, 3.7])
+        return rng.choice(["%r" % float(v), "%g" % v, "%gf" % v if "e" not in "%g" % v else "%r" % float(v)])
+    e = lambda: _rand_expr(rng, names, depth + 1)   # noqa: E731
+    if r < 0.55:
+        return "%s %s %s" % (e(), rng.choice(["+", "-", "*", "/", "+", "*"]), e())
+    if r < 0.62:
+        return "(%s)" % e()
+    if r < 0.68:
+        return "-%s" % e()
+    if r < 0.72:
+        return "!(%s)" % e()
+    if r < 0.80:
+        return "%s %s %s" % (e(), rng.choice(["<", ">", "<=", ">=", "==", "!="]), e())
+    if r < 0.85:
+        return "(%s) %s (%s)" % (e(), rng.choice(["&&", "||"]), e())
+    if r < 0.92:
+        return "(%s) ? %s : %s" % (e(), e(), e())
+    f = rng.choice(["sqrt(abs(%s))", "abs(%s)", "min(%s, %s)", "max(%s, %s, %s)", "floor(%s)", "ceil(%s)",
+                    "(%s)^2", "sign(%s)", "avg(%s, %s)", "7 %% (1 + abs(%s))"])
+    return f % tuple(e() for _ in range(f.count("%s")))
+
+
+def test_svm_programs_equal_the_host_evaluator_on_random_expressions():
+    """400 random expressions of the tokenizer's grammar over float / int / unsigned / vector-component
+    variables: SvmCompiler + aqs_run and Variables::solve give the same bits -- or fail together (a value
+    that overflows the target type)."""
+    rng = np.random.default_rng(2026)
+    d = ("float a=3;float b=-2.5;float c=0.125;int i=-7;int k=12;unsigned int u=4000000000;unsigned int n=17;"
+         "vec v=3.0, -4.0, 5.5, 6.0;float z=0;float big=3e9")
+    names = ["a", "b", "c", "i", "k", "u", "n", "v_x", "v_y", "v_z", "v_w", "z", "big"]
+    ran = failed = 0
+    for _ in range(400):
+        x = _rand_expr(rng, names)
+        for ty, dt in (("float", np.float32), ("int", np.int32), ("unsigned int", np.uint32)):
+            try:
+                want = host.evaluate(x, ty, d, dtype=dt)
+            except host.HostError:
+                with pytest.raises(host.HostError):
+                    host.evaluate_svm(x, ty, d, dtype=dt)
+                failed += 1
+                continue
+            got = host.evaluate_svm(x, ty, d, dtype=dt)
+            assert want.tobytes() == got.tobytes() or (np.isnan(want) and np.isnan(got)), (x, ty, want, got)
+            ran += 1
+    assert ran > 600 and failed > 20, (ran, failed)
+
+
+def test_lane_schedule_orders_every_conflicting_pair():
+    """The two-lane schedule of the device loops (host/devloop.cpp::scheduleLanes through
+    aqh_lane_schedule), on random dependency sets: whatever lanes it picks, every pair of tools of which one
+    writes what the other reads or writes (in rows of a common particle class) is ordered -- by the in-order
+    lane they share, or by a chain of recorded events and waits -- in pipeline order; tools flagged for lane
+    0 stay there; the last tool of lane 1 carries the event the pass joins on.  And it does use the second
+    lane: two independent chains of sweeps end up side by side."""
+    import ctypes as C
+    L = host.lib()
+    L.aqh_lane_schedule.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 4
+    rng = np.random.default_rng(7)
+
+    def schedule(R, W, cost, flags, gain=3.0):
+        n = len(R)
+
+        def csr(A):
+            off = np.zeros(n + 1, np.int32)
+            off[1:] = np.cumsum([len(a) for a in A])
+            var = np.array([v for a in A for v, _ in a] + [0], np.int32)
+            rows = np.array([m for a in A for _, m in a] + [0], np.uint32)
+            return off, var, rows
+        ro, rv, rr = csr(R)
+        wo, wv, wr = csr(W)
+        cost = np.asarray(cost, np.float64)
+        flags = np.asarray(flags, np.uint8)
+        lane, wait = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        marked = np.zeros(n, np.uint8)
+        last1 = C.c_int(-2)
+        p = lambda a: a.ctypes.data   # noqa: E731
+        assert L.aqh_lane_schedule(n, p(ro), p(rv), p(rr), p(wo), p(wv), p(wr), p(cost), p(flags), gain, p(lane),
+                                   p(wait), p(marked), C.addressof(last1)) == 0
+        return lane, wait, marked, last1.value
+
+    def conflict(a, b, R, W, flags):
+        if (flags[a] | flags[b]) & 2:
+            return True
+        hit = lambda X, Y: any(v == w and (m & q) for v, m in X for w, q in Y)   # noqa: E731
+        return hit(W[a], R[b]) or hit(W[a], W[b]) or hit(R[a], W[b])
+
+    used_lane1 = 0
+    for trial in range(300):
+        n = int(rng.integers(2, 40))
+        nv = int(rng.integers(2, 12))
+        R, W, cost, flags = [], [], [], []
+        for k in range(n):
+            acc = lambda m: [(int(v), int(rng.choice([7, 7, 1, 2, 4, 5]))) for v in   # noqa: E731
+                             rng.choice(nv, size=min(nv, int(rng.integers(0, m))), replace=False)]
+            R.append(acc(4))
+            W.append(acc(3))
+            R[-1] += W[-1]                   # (an output may be read back)
+            cost.append(float(rng.choice([1, 1, 1, 10, 10, 40])))
+            f = 0
+            if rng.random() < 0.15:
+                f |= 1
+            if rng.random() < 0.03:
+                f |= 2
+            if rng.random() < 0.15:
+                f |= 4
+            flags.append(f)
+        lane, wait, marked, last1 = schedule(R, W, cost, flags, gain=float(rng.choice([0.0, 1.0, 3.0, 8.0])))
+        live = [k for k in range(n) if not flags[k] & 4]
+        assert all(lane[k] == 0 for k in range(n) if flags[k] & 3)
+        on1 = [k for k in live if lane[k] == 1]
+        assert last1 == (on1[-1] if on1 else -1) and (not on1 or marked[last1])
+        used_lane1 += bool(on1)
+        # happens-before: lane order + recorded events that somebody waits for
+        hb = np.zeros((n, n), bool)
+        for l in (0, 1):
+            q = [k for k in live if lane[k] == l]
+            for a, b in zip(q, q[1:]):
+                hb[a, b] = True
+        for k in live:
+            if wait[k] >= 0:
+                u = int(wait[k])
+                assert u < k and lane[u] != lane[k] and marked[u] and not flags[u] & 4
+                hb[u, k] = True
+        for m in range(n):                   # transitive closure (indices are a topological order)
+            hb |= np.outer(hb[:, m], hb[m, :])
+        for b in live:
+            for a in live:
+                if a < b and conflict(a, b, R, W, flags):
+                    assert hb[a, b], (trial, a, b, lane.tolist(), wait.tolist())
+    assert used_lane1 > 100
+    # two independent chains of three sweeps: side by side, no waits between them
+    R = [[(0, 7)], [(0, 7)], [(0, 7)], [(1, 7)], [(1, 7)], [(1, 7)]]
+    W = [[(0, 7)], [(0, 7)], [(0, 7)], [(1, 7)], [(1, 7)], [(1, 7)]]
+    lane, wait, marked, last1 = schedule(R, W, [10] * 6, [0] * 6)
+    assert lane.tolist() == [0, 0, 0, 1, 1, 1] and (wait == -1).all() and last1 == 5
