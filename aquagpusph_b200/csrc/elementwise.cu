@@ -1679,6 +1679,55 @@ int l_ig_mp_relax(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// cfd/ideal_gas/time_scheme/euler.cl:70-83 (its predictor :44-56 is k_ig_mp_predictor), improved_euler.cl:49-97
+__global__ void __launch_bounds__(256)
+k_ig_euler_corrector(const int* imove, float* eint, const float* deintdt, uint32_t N, float dt)
+{
+    GID;
+    if (imove[i] > 0)
+        eint[i] += dt * deintdt[i];
+}
+int l_ig_euler_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    LAUNCH(c, k_ig_euler_corrector, N, (const int*)a[0], (float*)a[1], (const float*)a[2], N,
+           aqc_scalar<float>(a, 4));
+    return AQC_OK;
+}
+__global__ void __launch_bounds__(256)
+k_ig_ie_predictor(const int* imove, const float* eint, const float* deintdt, float* eint_in, float* deintdt_in,
+                  uint32_t N, float dt)
+{
+    GID;
+    const float DT = (imove[i] <= 0) ? 0.f : dt;
+    deintdt_in[i] = deintdt[i];
+    eint_in[i] = eint[i] + DT * deintdt[i];
+}
+int l_ig_ie_predictor(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    LAUNCH(c, k_ig_ie_predictor, N, (const int*)a[0], (const float*)a[1], (const float*)a[2], (float*)a[3],
+           (float*)a[4], N, aqc_scalar<float>(a, 6));
+    return AQC_OK;
+}
+__global__ void __launch_bounds__(256)
+k_ig_ie_corrector(const int* imove, const float* deintdt, const float* deintdt_in, float* eint, uint32_t N,
+                  float dt)
+{
+    GID;
+    if (imove[i] > 0) {
+        const float DT = 0.5f * dt;
+        eint[i] += DT * (deintdt[i] - deintdt_in[i]);
+    }
+}
+int l_ig_ie_corrector(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 4);
+    LAUNCH(c, k_ig_ie_corrector, N, (const int*)a[0], (const float*)a[1], (const float*)a[2], (float*)a[3], N,
+           aqc_scalar<float>(a, 5));
+    return AQC_OK;
+}
+
 // cfd/ideal_gas/symmetry/Mirror.cl:32-48 (sources are never mirrored particles themselves: no row is both
 // read and written)
 __global__ void __launch_bounds__(256)
@@ -1971,6 +2020,18 @@ aqc_registrar r_ig_dt("cfd/ideal_gas/TimeStep.cl", "entry", 0,
 aqc_registrar r_ig_rrates("cfd/ideal_gas/riemann/Rates.cl", "entry", 0,
     { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("work_density", "float*"), OUT("deintdt", "float*"),
       SC("N", "usize") }, l_ig_riemann_rates);
+aqc_registrar r_ig_eu_p("cfd/ideal_gas/time_scheme/euler.cl", "predictor", 0,
+    { IN("eint", "float*"), IN("deintdt", "float*"), OUT("eint_in", "float*"), OUT("deintdt_in", "float*"),
+      SC("N", "usize") }, l_ig_mp_predictor);
+aqc_registrar r_ig_eu_c("cfd/ideal_gas/time_scheme/euler.cl", "corrector", 0,
+    { IN("imove", "int*"), OUT("eint", "float*"), IN("deintdt", "float*"), SC("N", "uint"), SC("dt", "float") },
+    l_ig_euler_corrector);
+aqc_registrar r_ig_ie_p("cfd/ideal_gas/time_scheme/improved_euler.cl", "predictor", 0,
+    { RO("imove", "int*"), IN("eint", "float*"), IN("deintdt", "float*"), OUT("eint_in", "float*"),
+      OUT("deintdt_in", "float*"), SC("N", "usize"), SC("dt", "float") }, l_ig_ie_predictor);
+aqc_registrar r_ig_ie_c("cfd/ideal_gas/time_scheme/improved_euler.cl", "corrector", 0,
+    { IN("imove", "int*"), IN("deintdt", "float*"), IN("deintdt_in", "float*"), OUT("eint", "float*"),
+      SC("N", "usize"), SC("dt", "float") }, l_ig_ie_corrector);
 aqc_registrar r_ig_sym("cfd/ideal_gas/symmetry/Mirror.cl", "set", 0,
     { IN("mirror_src", "usize*"), OUT("eint_in", "float*"), OUT("deintdt_in", "float*"), OUT("deintdt", "float*"),
       SC("N", "usize") }, l_ig_sym_set);

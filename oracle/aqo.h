@@ -308,6 +308,12 @@ void aqo_ig_mp_midpoint(const int* imove, const float* eint_in, const float* dei
 void aqo_ig_mp_relax(const int* imove, const float* deintdt_in, float* deintdt, aqo_usize N, float relax_midpoint);
 void aqo_ig_mp_corrector(const int* imove, const float* eint_in, const float* deintdt, float* eint, aqo_usize N,
                          float dt);
+/* cfd/ideal_gas/time_scheme/euler.cl:70-83, improved_euler.cl:49-97 (euler.cl's predictor = aqo_ig_mp_predictor) */
+void aqo_ig_euler_corrector(const int* imove, float* eint, const float* deintdt, aqo_usize N, float dt);
+void aqo_ig_ie_predictor(const int* imove, const float* eint, const float* deintdt, float* eint_in,
+                         float* deintdt_in, aqo_usize N, float dt);
+void aqo_ig_ie_corrector(const int* imove, const float* deintdt, const float* deintdt_in, float* eint,
+                         aqo_usize N, float dt);
 /* cfd/ideal_gas/riemann/Interactions.cl:50-168 */
 void aqo_ig_riemann_interactions(const aqo_defs* D, const aqo_ll* L, const aqo_usize* iset, const int* imove,
                                  const float* r, const float* u, const float* rho, const float* m, const float* p,

@@ -1844,3 +1844,34 @@ void aqo_ig_riemann_interactions(const aqo_defs* D, const aqo_ll* L, const aqo_u
         div_u[i] = du;
     }
 }
+
+/* cfd/ideal_gas/time_scheme/euler.cl: predictor :44-56 (the same copies as midpoint.cl's), corrector :70-83;
+ * improved_euler.cl: predictor :49-66, corrector :82-97 */
+void aqo_ig_euler_corrector(const int* imove, float* eint, const float* deintdt, aqo_usize N, float dt)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] > 0)
+            eint[i] += dt * deintdt[i];
+    }
+}
+void aqo_ig_ie_predictor(const int* imove, const float* eint, const float* deintdt, float* eint_in,
+                         float* deintdt_in, aqo_usize N, float dt)
+{
+    AQO_FOR_I(N) {
+        float DT = dt;
+        if (imove[i] <= 0)
+            DT = 0.f;
+        deintdt_in[i] = deintdt[i];
+        eint_in[i] = eint[i] + DT * deintdt[i];
+    }
+}
+void aqo_ig_ie_corrector(const int* imove, const float* deintdt, const float* deintdt_in, float* eint,
+                         aqo_usize N, float dt)
+{
+    AQO_FOR_I(N) {
+        if (imove[i] > 0) {
+            const float DT = 0.5f * dt;
+            eint[i] += DT * (deintdt[i] - deintdt_in[i]);
+        }
+    }
+}

@@ -712,6 +712,9 @@ class Interpreter:
                 ("cfd/ideal_gas/Sort.cl", "entry"), ("cfd/ideal_gas/TimeStep.cl", "entry"),
                 ("cfd/ideal_gas/riemann/Rates.cl", "entry"), ("cfd/ideal_gas/symmetry/Mirror.cl", "set"),
                 ("cfd/ideal_gas/riemann/Interactions.cl", "entry"),
+                ("cfd/ideal_gas/time_scheme/euler.cl", "predictor"), ("cfd/ideal_gas/time_scheme/euler.cl", "corrector"),
+                ("cfd/ideal_gas/time_scheme/improved_euler.cl", "predictor"),
+                ("cfd/ideal_gas/time_scheme/improved_euler.cl", "corrector"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "predictor"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "midpoint"),
                 ("cfd/ideal_gas/time_scheme/midpoint.cl", "relax"),
@@ -733,6 +736,12 @@ class Interpreter:
                 c("ig_sym_set", V["mirror_src"], V["eint_in"], V["deintdt_in"], V["deintdt"], N)
             elif rel.endswith("riemann/Rates.cl"):
                 c("ig_riemann_rates", V["imove"], V["work_density"], V["deintdt"], N)
+            elif rel.endswith("time_scheme/euler.cl") and entry == "corrector":
+                c("ig_euler_corrector", V["imove"], V["eint"], V["deintdt"], N, f32("dt"))
+            elif rel.endswith("improved_euler.cl") and entry == "predictor":
+                c("ig_ie_predictor", V["imove"], V["eint"], V["deintdt"], V["eint_in"], V["deintdt_in"], N, f32("dt"))
+            elif rel.endswith("improved_euler.cl"):
+                c("ig_ie_corrector", V["imove"], V["deintdt"], V["deintdt_in"], V["eint"], N, f32("dt"))
             elif entry == "predictor":
                 c("ig_mp_predictor", V["eint"], V["deintdt"], V["eint_in"], V["deintdt_in"], N)
             elif entry == "midpoint":

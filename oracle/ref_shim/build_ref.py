@@ -44,6 +44,7 @@ SCRIPTS = [
     "cfd/ideal_gas/EOS.cl", "cfd/ideal_gas/Rates.cl", "cfd/ideal_gas/Sort.cl", "cfd/ideal_gas/TimeStep.cl",
     "cfd/ideal_gas/riemann/Rates.cl", "cfd/ideal_gas/time_scheme/midpoint.cl",
     "cfd/ideal_gas/symmetry/Mirror.cl", "cfd/ideal_gas/riemann/Interactions.cl",
+    "cfd/ideal_gas/time_scheme/euler.cl", "cfd/ideal_gas/time_scheme/improved_euler.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 

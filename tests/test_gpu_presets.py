@@ -570,6 +570,17 @@ def test_ideal_gas_elementwise_kernels(oracle, dims):
         ctx.launch("cfd/ideal_gas/" + script, entry, d)
     ctx.copy(d["eint_in"], d["eint"])
     ctx.launch("cfd/ideal_gas/Sort.cl", "entry", d)
+    # the other two time schemes (euler.cl, improved_euler.cl)
+    oracle.call("ig_mp_predictor", o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N)
+    oracle.call("ig_euler_corrector", o["imove"], o["eint"], o["deintdt"], N, o["dt"])
+    o["deintdt"][...] = o["work_density"]
+    oracle.call("ig_ie_corrector", o["imove"], o["deintdt"], o["deintdt_in"], o["eint"], N, o["dt"])
+    oracle.call("ig_ie_predictor", o["imove"], o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N, o["dt"])
+    ctx.launch("cfd/ideal_gas/time_scheme/euler.cl", "predictor", d)
+    ctx.launch("cfd/ideal_gas/time_scheme/euler.cl", "corrector", d)
+    ctx.copy(d["deintdt"], d["work_density"])
+    ctx.launch("cfd/ideal_gas/time_scheme/improved_euler.cl", "corrector", d)
+    ctx.launch("cfd/ideal_gas/time_scheme/improved_euler.cl", "predictor", d)
     oracle.call("ig_sym_set", o["mirror_src"], o["eint_in"], o["deintdt_in"], o["deintdt"], N)
     ctx.launch("cfd/ideal_gas/symmetry/Mirror.cl", "set", d)
     for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):

@@ -487,6 +487,17 @@ def test_ideal_gas_elementwise_kernels_match_reference_scripts(oracle, dims):
     b["eint_in"][...] = b["eint"]
     R.run("cfd/ideal_gas/Sort.cl", "entry", N, a)
     oracle.call("ig_sort", b["eint_in"], b["eint"], b["deintdt"], b["deintdt_in"], b["id_sorted"], N)
+    # the other two time schemes: euler.cl (predictor = the same copies, corrector) and improved_euler.cl
+    R.run("cfd/ideal_gas/time_scheme/euler.cl", "predictor", N, a)
+    oracle.call("ig_mp_predictor", b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N)
+    R.run("cfd/ideal_gas/time_scheme/euler.cl", "corrector", N, a)
+    oracle.call("ig_euler_corrector", b["imove"], b["eint"], b["deintdt"], N, a["dt"])
+    a["deintdt"][...] = a["work_density"]
+    b["deintdt"][...] = b["work_density"]
+    R.run("cfd/ideal_gas/time_scheme/improved_euler.cl", "corrector", N, a)
+    oracle.call("ig_ie_corrector", b["imove"], b["deintdt"], b["deintdt_in"], b["eint"], N, a["dt"])
+    R.run("cfd/ideal_gas/time_scheme/improved_euler.cl", "predictor", N, a)
+    oracle.call("ig_ie_predictor", b["imove"], b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N, a["dt"])
     # cfd/ideal_gas/symmetry/Mirror.cl::set (cfd/ideal_gas/symmetry.xml): mirrored rows copy their source's energy
     R.run("cfd/ideal_gas/symmetry/Mirror.cl", "set", N, a)
     oracle.call("ig_sym_set", b["mirror_src"], b["eint_in"], b["deintdt_in"], b["deintdt"], N)

@@ -362,6 +362,11 @@ extern "C" void emu_ig(int dims, const uint32_t* iset, const int* imove, const f
     for (g_i = 0; g_i < N; g_i++) k_ig_mp_advance(imove, eint_in, deintdt, eint, N, dt);
     memcpy(eint_in, eint, 4 * (size_t)N);
     for (g_i = 0; g_i < N; g_i++) k_ig_sort(eint_in, eint, deintdt, deintdt_in, id_sorted, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_mp_predictor(eint, deintdt, eint_in, deintdt_in, N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_euler_corrector(imove, eint, deintdt, N, dt);
+    memcpy(deintdt, work_density, 4 * (size_t)N);
+    for (g_i = 0; g_i < N; g_i++) k_ig_ie_corrector(imove, deintdt, deintdt_in, eint, N, dt);
+    for (g_i = 0; g_i < N; g_i++) k_ig_ie_predictor(imove, eint, deintdt, eint_in, deintdt_in, N, dt);
     for (g_i = 0; g_i < N; g_i++) k_ig_sym_set(mirror_src, eint_in, deintdt_in, deintdt, N);
 }
 """
@@ -407,6 +412,11 @@ def test_ideal_gas_kernel_bodies_match_the_oracle(oracle, emu_ig, dims):
     oracle.call("ig_mp_corrector", o["imove"], o["eint_in"], o["deintdt"], o["eint"], N, o["dt"])
     o["eint_in"][...] = o["eint"]
     oracle.call("ig_sort", o["eint_in"], o["eint"], o["deintdt"], o["deintdt_in"], o["id_sorted"], N)
+    oracle.call("ig_mp_predictor", o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N)
+    oracle.call("ig_euler_corrector", o["imove"], o["eint"], o["deintdt"], N, o["dt"])
+    o["deintdt"][...] = o["work_density"]
+    oracle.call("ig_ie_corrector", o["imove"], o["deintdt"], o["deintdt_in"], o["eint"], N, o["dt"])
+    oracle.call("ig_ie_predictor", o["imove"], o["eint"], o["deintdt"], o["eint_in"], o["deintdt_in"], N, o["dt"])
     oracle.call("ig_sym_set", o["mirror_src"], o["eint_in"], o["deintdt_in"], o["deintdt"], N)
     emu_ig.emu_ig(dims, _p(e["iset"]), _p(e["imove"]), _p(e["rho"]), _p(e["eint"]), _p(e["p"]), _p(e["gamma"]),
                   _p(e["div_u"]), _p(e["deintdt"]), _p(e["dt_var"]), _p(e["u"]), _p(e["grad_p"]),
