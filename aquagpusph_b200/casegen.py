@@ -469,6 +469,24 @@ def souto2012_standing_wave(ny=100, hfac=4.0, overrides=None, device=0, **kw):
     return sim, c
 
 
+def shock_point(n=50000, hfac=2.0, rim_script="bc.cl", overrides=None, device=0, **kw):
+    """The circular blast of examples/2D/shock_point through its unchanged 73-tool pipeline (midpoint scheme
+    with autostop / autorelax, the cfd presets, the ideal-gas EOS / energy rates / energy time scheme, and a
+    case-local script that freezes the rim: `rim_script` = the file the two `bc.cl` tools should read --
+    compiled at run time; needs AQUAGPUSPH_ROOT to hold resources/Scripts/types/types.h for its include)."""
+    from . import cases
+    c = cases.shock_point_2d(n, hfac)
+    tr = kw.pop("transform", None)
+
+    def transform(txt):
+        txt = txt.replace('path="bc.cl"', 'path="%s"' % rim_script)
+        return tr(txt) if tr else txt
+    sim = load("shock_point_2d", c, (c["N"],), overrides, device, transform=transform, **kw)
+    for k in ("eint", "deintdt"):
+        sim.upload(k, c[k])
+    return sim, c
+
+
 def spheric2(n=100000, hfac=3.0, overrides=None, device=0, seed=None, jitter=0.0, uscale=0.1, **kw):
     """BASELINE config 2 (3-D SPHERIC test 2 dam break) through the unchanged
     116-tool pipeline of examples/3D/spheric_testcase2_dambreak."""

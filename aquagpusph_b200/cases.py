@@ -480,6 +480,50 @@ def souto2012_standing_wave_2d(ny=100, hfac=4.0, periods=8):
     )
 
 
+def shock_point_2d(n=50000, hfac=2.0):
+    """The circular blast of an ideal gas of examples/2D/shock_point/src/Create.py:39-152: a disc of radius
+    R = 0.5 of particles on a square lattice of pitch dr = sqrt(pi R^2 / n) (x outer, y inner, both from -R),
+    gas at rest with rho = 1.00001 everywhere and the pressure 2e5 inside R0 = 0.2, 1e5 outside (internal
+    energy e = p / ((gamma - 1) rho), gamma = 1.4); one particles set, every particle fluid (imove = 1; the
+    case-local bc.cl freezes the rim while the time scheme runs)."""
+    courant, R, R0, gamma = 0.25, 0.5, 0.2, 1.4
+    p1, p2, rho1, rho2 = 2.0e5, 1.0e5, 1.00001, 1.00001
+    c1, c2 = math.sqrt(gamma * p1 / rho1), math.sqrt(gamma * p2 / rho2)
+    cs = max(c1, c2)
+    e1, e2 = p1 / ((gamma - 1.0) * rho1), p2 / ((gamma - 1.0) * rho2)
+    dr = (math.pi * R ** 2 / n) ** 0.5
+    h = hfac * dr
+    xs = []
+    x = -R
+    while x < R:          # (Create.py:118-133: repeated addition, not an index times dr)
+        xs.append(x)
+        x += dr
+    xs = np.array(xs, np.float64)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    rr = np.sqrt(X ** 2 + Y ** 2)
+    keep = ~(rr > R)
+    px, py, rad = X[keep], Y[keep], rr[keep]
+    N = int(keep.sum())
+    inner = rad < R0
+    rho = np.where(inner, rho1, rho2)
+    eint = np.where(inner, e1, e2)
+    Rd = R + 4.0 * h
+    hh = float(np.float32(h))
+    return dict(
+        dims=2, N=N, n_fluid=N, h=hh, dr=float(np.float32(dr)), hfac=hfac, cs=cs, p0=0.0, support=2.0,
+        refd=np.array([0.0], np.float32), visc_dyn=np.array([0.0], np.float32), delta=np.array([0.0], np.float32),
+        g=np.array([0.0, 0.0], np.float32), gamma=np.array([gamma], np.float32),
+        domain_min=np.array((-Rd, -Rd), np.float32), domain_max=np.array((Rd, Rd), np.float32), courant=courant,
+        t_end=R0 / cs, R=R, R0=R0, e1=e1, e2=e2, p1=p1, p2=p2,
+        placeholders={"H": repr(h), "GAMMA": repr(gamma), "R": repr(R)},
+        id=np.arange(N, dtype=np.uint32), r=np.stack([px, py], 1).astype(np.float32),
+        imove=np.ones(N, np.int32), iset=np.zeros(N, np.uint32), normal=np.zeros((N, 2), np.float32),
+        tangent=np.zeros((N, 2), np.float32), rho=rho.astype(np.float32), m=(rho * dr ** 2).astype(np.float32),
+        u=np.zeros((N, 2), np.float32), dudt=np.zeros((N, 2), np.float32), drhodt=np.zeros(N, np.float32),
+        eint=eint.astype(np.float32), deintdt=np.zeros(N, np.float32),
+    )
+
+
 def spheric2_dam_break_slab(n_total, hfac, rank, size, buffer_frac=0.1, boundary_margin=None, seed=None,
                             jitter=0.0, uscale=0.1):
     """BASELINE config 3 shape: the 3-D dam break cut in `size` slabs along y, the way

@@ -13,6 +13,8 @@ import math
 import re
 import xml.etree.ElementTree as ET
 
+import os
+
 import numpy as np
 
 from . import oracle as O
@@ -785,6 +787,17 @@ class Interpreter:
                 V["mpi_lap_p_corr"][V["mpi_id_sorted"][:N]] = V["mpi_lap_p_corr_in"][:N]
             else:
                 raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
+        elif os.path.basename(rel) in ("bc.cl", "BlastRim.cl") and entry in ("set_fixed", "unset_fixed"):
+            # the case-local script of examples/2D/shock_point (src/templates/bc.cl:44-66; tests/scripts/user/
+            # BlastRim.cl is this repository's own wording of it): the rim is frozen while the time scheme runs
+            f = np.float32
+            if entry == "set_fixed":
+                r = V["r"]
+                length = np.sqrt((r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1]).astype(f)).astype(f)
+                band = f(f(f(1.5) * f(D.SUPPORT)) * f(D.H))
+                V["imove"][length > f(f(V["R"]) - band)] = 0
+            else:
+                V["imove"][...] = 1
         elif rel.endswith("h_sensor.cl"):
             # examples/3D/spheric_testcase2_dambreak/src/templates/h_sensor.cl:1-60
             r, dr = V["r"], np.float32(V["dr"])

@@ -624,3 +624,48 @@ def test_riemann_interactions_sweep(oracle, dims, n, hfac, engine):
         assert np.isfinite(b).all(), k
         assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
         assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 0, k
+
+
+def test_shock_point_blast_pipeline(oracle, monkeypatch):
+    """examples/2D/shock_point: the unchanged 73-tool pipeline (midpoint scheme with autorelax, the cfd presets,
+    the ideal-gas EOS / energy rates / sort / energy time scheme -- all hand-written kernels -- and the case-local
+    rim script compiled at run time: tests/scripts/user/BlastRim.cl, this repository's wording of the example's
+    bc.cl) on the GPU against the oracle interpreter, three steps of ten midpoint passes (the residual threshold
+    is set to 0 so that a residual next to it cannot make the two sides stop on different passes).  The
+    midpoint loop runs as a CUDA graph while-node with two kernels reading relax_midpoint from the device table.
+    Neighbour structures and dt bit-exact; fields within ~20x the oracle's own sensitivity to a 1-ulp
+    perturbation of its inputs (measured: r 6e-8, u 6e-6, rho 4e-7, p 4e-7, eint 2e-7, rates 4e-6 .. 8e-6 of
+    the field's maximum)."""
+    import os
+    from oracle import interp
+    host.set_log_level(3)
+    here = os.path.dirname(os.path.abspath(__file__))
+    monkeypatch.setenv("AQUAGPUSPH_ROOT", os.path.join(here, "scripts"))
+    rim = os.path.join(here, "scripts", "user", "BlastRim.cl")
+    case = product_cases.shock_point_2d(3000)
+    ov = {"Residual_midpoint_max": "0.0"}
+    I = interp.Interpreter(casegen.instantiate("shock_point_2d", case, (case["N"],), ov), 2)
+    for k in casegen.STATE_FIELDS + ("eint", "deintdt"):
+        I.V[k][...] = case[k]
+    sim, _ = casegen.shock_point(3000, rim_script=rim, overrides=ov)
+    assert [t[0] for t in sim.tools()] == [t["name"] for t in I.tools] and len(I.tools) == 71
+    assert sim.device_loops() == 1, sim.loop_host_reason([t[1] for t in sim.tools()].index("while"))
+    tols = {"r": 1e-6, "u": 1e-4, "rho": 5e-6, "p": 1e-5, "eint": 5e-6, "dudt": 1e-4, "drhodt": 2e-4,
+            "deintdt": 2e-4}
+    for step in range(3):
+        I.step()
+        sim.step(1)
+        assert int(sim.scalar("iter_midpoint", np.uint32)) == int(I.V["iter_midpoint"]) == 10
+        assert np.array_equal(sim.scalar("n_cells", np.uint32, 4), I.V["n_cells"])
+        assert float(sim.scalar("dt")) == float(I.V["dt"])
+        assert np.array_equal(sim.download("imove", np.int32), I.V["imove"])
+        if step == 0:
+            for k in ("icell", "id_sorted", "id_unsorted"):
+                assert np.array_equal(sim.download(k, np.uint32), I.V[k]), k
+        for k, tol in tols.items():
+            a = I.unsorted(k).astype(np.float64)
+            b = sim.download(k, unsorted=True).astype(np.float64)
+            scale = max(np.abs(a).max(), 1e-30)
+            assert np.abs(a - b).max() <= tol * scale, "step %d field %s: %.3e" % (step, k, np.abs(a - b).max() / scale)
+    assert np.abs(I.V["u"]).max() > 10.0      # the blast is under way
+    sim.close()

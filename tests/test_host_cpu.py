@@ -181,6 +181,7 @@ def test_resolved_dam_break_3d_pipeline():
     ("spheric9_tld_2d", "examples/2D/spheric_testcase9_tld/src/templates", 2),
     ("spheric3_liddriven_2d", "examples/2D/spheric_testcase3_liddriven/src/templates", 2),
     ("souto2012_standingwave_2d", "examples/2D/souto_etal_2012_standingwave/src/templates", 2),
+    ("shock_point_2d", "examples/2D/shock_point/src/templates", 2),
 ])
 def test_committed_templates_match_the_reference_examples(name, src, dims):
     """The committed resolved templates are what our front-end makes of the

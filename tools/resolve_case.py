@@ -33,6 +33,9 @@ CASES = {
     # standing wave of Souto-Iglesias et al. 2012: improved Euler, delta-SPH full, BI bottom, two symmetry
     # planes (cfd/symmetry.xml twice: Symmetry/Mirror.cl) feeding on buffer particles, kinetic-energy report
     "souto2012_standingwave_2d": ("examples/2D/souto_etal_2012_standingwave/src/templates", 2),
+    # circular blast of an ideal gas (examples/2D/shock_point): midpoint scheme with autostop / autorelax, the
+    # ideal-gas presets (EOS, energy rates, energy time scheme) and a case-local bc.cl that freezes the rim
+    "shock_point_2d": ("examples/2D/shock_point/src/templates", 2),
     # the reference's own multi-device parity test (tests/2D/MPI_plane)
     "mpi_plane_2d_serial": ("tests/2D/MPI_plane/cMake", 2, "main_serial.xml"),
     "mpi_plane_2d_mpi": ("tests/2D/MPI_plane/cMake", 2, "main_mpi.xml"),
