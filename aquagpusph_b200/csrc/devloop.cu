@@ -34,6 +34,7 @@ struct aqc_loop {
     cudaGraph_t body = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaGraphConditionalHandle handle = 0;
+    cudaEvent_t join_ev = nullptr; // aqc_loop_abort: joins a branch lane left inside the capture
     int arena_graph_from = 0;     // first op of the recorded programs (direct ones sit in front)
     bool recording = false, ready = false, body_has_cond = false;
     bool started = false;         // aqc_loop_start uploaded the table: aqc_loop_run(table_in = NULL) may follow
@@ -132,6 +133,8 @@ extern "C" int aqc_loop_destroy(aqc_ctx* ctx, aqc_loop* L)
     cudaFree(L->arena_dev);
     cudaFreeHost(L->arena_host);
     cudaFree(L->max_iters_dev);
+    if (L->join_ev)
+        cudaEventDestroy(L->join_ev);
     delete L;
     return AQC_OK;
 }
@@ -237,6 +240,19 @@ extern "C" int aqc_loop_abort(aqc_ctx* ctx, aqc_loop* L)
     if (L->recording) {
         if (ctx->lane != 0)
             aqc_lane_select(ctx, 0);
+        // a branch lane that joined the capture and was not waited for yet would leave the capture
+        // "unjoined": join it, so that both streams leave capture mode cleanly
+        if (ctx->lane1_made && ctx->parked.stream) {
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(ctx->parked.stream, &st) == cudaSuccess &&
+                st == cudaStreamCaptureStatusActive) {
+                if (!L->join_ev)
+                    cudaEventCreateWithFlags(&L->join_ev, cudaEventDisableTiming);
+                if (L->join_ev && cudaEventRecord(L->join_ev, ctx->parked.stream) == cudaSuccess)
+                    cudaStreamWaitEvent(ctx->stream, L->join_ev, 0);
+            }
+            cudaGetLastError();
+        }
         cudaGraph_t g = nullptr;
         cudaStreamEndCapture(ctx->stream, &g); // an invalidated capture reports its error here
         cudaGetLastError();

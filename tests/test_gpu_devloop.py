@@ -269,6 +269,26 @@ def test_lanes_are_ordered_by_their_events():
         ctx.copy(c, b)                              # lane 0, behind the copy on lane 1
         assert ctx.reduce(_lib.OP_MIN, c) == v and ctx.reduce(_lib.OP_MAX, c) == v
         assert ctx.reduce(_lib.OP_MIN, b) == v
+    # a recording given up while the branch lane is inside the capture: both streams come back usable
+    loop = ctx.loop(16)
+    cond = [(AQS_LOAD, 0, "u"), (AQS_IMM, 0, 0, 0, 2), (AQS_LT,), (AQS_SETCOND,)]
+    for rep in range(2):
+        loop.begin(cond)
+        ctx._chk(L.aqc_lane_event(ctx.h, C.byref(ev1)))
+        ctx._chk(L.aqc_lane_select(ctx.h, 1))
+        ctx._chk(L.aqc_lane_wait(ctx.h, ev1))
+        ctx.fill(b, np.float32(-1.0).tobytes())       # recorded on the branch lane, never run
+        with pytest.raises(_lib.AquaError, match="synchronises"):
+            ctx.reduce(_lib.OP_MIN, b)
+        loop.abort()                                  # (selects lane 0 again)
+        assert ctx.reduce(_lib.OP_MIN, b) == 3.0
+        ctx._chk(L.aqc_lane_select(ctx.h, 1))
+        ctx.fill(a, np.float32(9.0).tobytes())        # the branch lane works outside a capture
+        ctx._chk(L.aqc_lane_event(ctx.h, C.byref(ev2)))
+        ctx._chk(L.aqc_lane_select(ctx.h, 0))
+        ctx._chk(L.aqc_lane_wait(ctx.h, ev2))
+        assert ctx.reduce(_lib.OP_MIN, a) == 9.0
+    loop.close()
     # loops and their recordings belong on lane 0
     loop = ctx.loop(16)
     ctx._chk(L.aqc_lane_select(ctx.h, 1))

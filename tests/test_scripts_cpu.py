@@ -118,3 +118,13 @@ def test_reference_scripts_compile_behind_the_dialect_header(tmp_path):
     assert [g[0] for g in got] == [w[0] for w in want]
     assert [g[1] for g in got] == [w[1] for w in want]
     assert [g[2] for g in got] == [w[2] for w in want]
+
+
+def test_the_blast_rim_script_compiles():
+    """tests/scripts/user/BlastRim.cl (this repository's wording of examples/2D/shock_point's bc.cl, used by
+    tests/test_gpu_presets.py::test_shock_point_blast_pipeline): both kernels compile for sm_100a behind the
+    dialect header with the problem's H and SUPPORT, and bind imove / r / N / R by name."""
+    rim = os.path.join(ROOT, "user", "BlastRim.cl")
+    defs = ("-DH=0.025f", "-DSUPPORT=2.f")
+    assert _lib.script_check(rim, "set_fixed", 2, ROOT, defs) == "int* imove (out); vec* r; usize N; float R; "
+    assert _lib.script_check(rim, "unset_fixed", 2, ROOT, defs) == "int* imove (out); usize N; "
