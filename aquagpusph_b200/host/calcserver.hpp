@@ -61,9 +61,10 @@ class Tool {
     }
     // ---- device-side loops (host/devloop.hpp).  recordable: one pass of the tool inside the loop
     // L only enqueues device work or is scalar arithmetic a program can do (no read-back, no host
-    // decision); scalarOutputs: the scalar variables it writes (they move into the loop's device
+    // decision) -- asked once, while the loop's table is laid out: a tool may reserve slots of its
+    // own there (DeviceLoop::scratch); scalarOutputs: the scalar variables it writes (they move into the loop's device
     // table); record: enqueue / emit that pass while the loop's body is being recorded.
-    virtual bool recordable(const DeviceLoop& L, std::string& why) const
+    virtual bool recordable(DeviceLoop& L, std::string& why) const
     {
         (void)L;
         why = "its tool type runs on the host";
@@ -115,7 +116,7 @@ class Kernel : public Tool {
     int fusedId() const { return _fused_id; }
     /// true when the kernel walks neighbours (it has the link-list's head-of-cell argument)
     bool isSweep() const;
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
@@ -144,7 +145,7 @@ class Copy : public Tool {
         out.push_back(_out);
         return true;
     }
-    bool recordable(const DeviceLoop&, std::string&) const override { return true; }
+    bool recordable(DeviceLoop&, std::string&) const override { return true; }
     void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
@@ -157,7 +158,7 @@ class Copy : public Tool {
 class Dummy : public Tool {
   public:
     using Tool::Tool;
-    bool recordable(const DeviceLoop&, std::string&) const override { return true; }
+    bool recordable(DeviceLoop&, std::string&) const override { return true; }
 };
 
 /// type="set" (Set.cpp:197-226, Set.cl.in:32-47)
@@ -174,7 +175,7 @@ class Set : public Tool {
         out.push_back(_var);
         return true;
     }
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
@@ -204,7 +205,7 @@ class SetScalar : public ScalarExpression {
     SetScalar(CalcServer* C, const std::string& name, const std::string& var, const std::string& value, bool once)
       : ScalarExpression(C, name, value, "float", once), _var_name(var) {}
     void setup() override;
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void scalarOutputs(std::vector<InputOutput::Variable*>& out) const override { out.push_back(_var); }
     void record(DeviceLoop& L) override;
   protected:
@@ -219,7 +220,7 @@ class Assert : public ScalarExpression {
   public:
     Assert(CalcServer* C, const std::string& name, const std::string& cond, bool once)
       : ScalarExpression(C, name, cond, "int", once) {}
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void record(DeviceLoop& L) override;
   protected:
     void _execute() override;
@@ -288,7 +289,7 @@ class Reduction : public Tool {
         out.push_back(_out);
         return true;
     }
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void scalarOutputs(std::vector<InputOutput::Variable*>& out) const override { out.push_back(_out); }
     void record(DeviceLoop& L) override;
   protected:
@@ -422,7 +423,7 @@ class Report : public Tool {
            const InputOutput::ProblemSetup::Tool& t, bool once);
     void setup() override;
     ~Report() override;
-    bool recordable(const DeviceLoop& L, std::string& why) const override;
+    bool recordable(DeviceLoop& L, std::string& why) const override;
     void record(DeviceLoop& L) override;
     const std::vector<InputOutput::Variable*>& fields() const { return _vars; }
   protected:

@@ -856,7 +856,7 @@ size_t Kernel::globalSize() const
     return N;
 }
 
-bool Kernel::recordable(const DeviceLoop& L, std::string& why) const
+bool Kernel::recordable(DeviceLoop& L, std::string& why) const
 {
     if (_leader) {
         if (!L.contains(_leader)) {
@@ -926,7 +926,7 @@ void Copy::record(DeviceLoop& L)
     _execute();
 }
 
-bool Set::recordable(const DeviceLoop& L, std::string& why) const
+bool Set::recordable(DeviceLoop& L, std::string& why) const
 {
     bool reads = false;
     try {
@@ -947,7 +947,7 @@ void Set::record(DeviceLoop& L)
     _execute();
 }
 
-bool SetScalar::recordable(const DeviceLoop& L, std::string& why) const
+bool SetScalar::recordable(DeviceLoop& L, std::string& why) const
 {
     if (!L.varying(_var)) {
         why = "its variable is not in the loop's table";
@@ -974,7 +974,7 @@ void SetScalar::record(DeviceLoop& L)
     L.emit(ops);
 }
 
-bool Assert::recordable(const DeviceLoop& L, std::string& why) const { return L.compilable(_expr, why); }
+bool Assert::recordable(DeviceLoop& L, std::string& why) const { return L.compilable(_expr, why); }
 
 void Assert::record(DeviceLoop& L)
 {
@@ -984,17 +984,16 @@ void Assert::record(DeviceLoop& L)
     L.emit(ops);
 }
 
-bool Reduction::recordable(const DeviceLoop& L, std::string& why) const
+bool Reduction::recordable(DeviceLoop& L, std::string& why) const
 {
     if (!L.varying(_out)) {
         why = "its output is not in the loop's table";
         return false;
     }
     // the table slots of its own are asked for here, while the table is still being laid out
-    DeviceLoop& M = const_cast<DeviceLoop&>(L);
-    M.scratch(this, 0);
-    const int ident = M.scratch(this, 1);
-    M.setInitial(ident, _identity.data(), std::min<size_t>(16, _identity.size()));
+    L.scratch(this, 0);
+    const int ident = L.scratch(this, 1);
+    L.setInitial(ident, _identity.data(), std::min<size_t>(16, _identity.size()));
     return true;
 }
 
@@ -1007,7 +1006,7 @@ void Reduction::record(DeviceLoop& L)
     L.emit(mk(AQS_FOLD, L.offset(_out), raw, ident, (double)(_op + 4 * kc + 16 * (int)_in->ncomp())));
 }
 
-bool Report::recordable(const DeviceLoop&, std::string& why) const
+bool Report::recordable(DeviceLoop&, std::string& why) const
 {
     if (_kind != "screen" && _kind != "file") {
         why = "report_" + _kind + " reads the device";
