@@ -143,3 +143,56 @@ def test_define_rounding(oracle):
     d = oracle.make_defs(3, 0.03)
     assert d.H == np.float32(0.03) and d.SUPPORT == 2.0
     assert d.CONW == np.float32(float("%#G" % (np.float32(1.0) / np.float32(0.03) ** 3)))
+
+
+# ---- value-level goldens of the ideal-gas family (tests/golden/ideal_gas_outputs.npz: outputs of the REFERENCE's
+# own scripts on seeded inputs, generated by tests/golden/make_golden_ideal_gas.py in the build container) ----
+def _ideal_gas_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ideal_gas_outputs.npz"))
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_ideal_gas_restatements_equal_the_reference_outputs(oracle, dims):
+    """The C restatements of resources/Scripts/cfd/ideal_gas (element-wise kernels, every time scheme, the
+    symmetry copy) against what the reference's scripts produced: the same bits, without the reference tree."""
+    import oracle.oracle as O
+    from test_oracle_vs_reference import _ideal_gas_state
+    G = _ideal_gas_golden()
+    _, b, N = _ideal_gas_state(dims, 13)
+    D = O.make_defs(dims, b["h"])
+    c = oracle.call
+    c("ig_eos", b["iset"], b["imove"], b["rho"], b["eint"], b["p"], b["gamma"], N)
+    c("ig_rates", b["imove"], b["rho"], b["p"], b["div_u"], b["deintdt"], N)
+    c("ig_timestep", D, b["dt_var"], b["imove"], b["iset"], b["u"], b["rho"], b["p"], N, b["dt"], b["dt_min"],
+      b["courant"], b["div_u"], b["grad_p"], b["gamma"])
+    c("ig_mp_predictor", b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N)
+    c("ig_riemann_rates", b["imove"], b["work_density"], b["deintdt"], N)
+    c("ig_mp_midpoint", b["imove"], b["eint_in"], b["deintdt"], b["eint"], N, b["dt"])
+    c("ig_mp_relax", b["imove"], b["deintdt_in"], b["deintdt"], N, b["relax_midpoint"])
+    c("ig_mp_corrector", b["imove"], b["eint_in"], b["deintdt"], b["eint"], N, b["dt"])
+    b["eint_in"][...] = b["eint"]
+    c("ig_sort", b["eint_in"], b["eint"], b["deintdt"], b["deintdt_in"], b["id_sorted"], N)
+    c("ig_mp_predictor", b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N)
+    c("ig_euler_corrector", b["imove"], b["eint"], b["deintdt"], N, b["dt"])
+    b["deintdt"][...] = b["work_density"]
+    c("ig_ie_corrector", b["imove"], b["deintdt"], b["deintdt_in"], b["eint"], N, b["dt"])
+    c("ig_ie_predictor", b["imove"], b["eint"], b["deintdt"], b["eint_in"], b["deintdt_in"], N, b["dt"])
+    c("ig_sym_set", b["mirror_src"], b["eint_in"], b["deintdt_in"], b["deintdt"], N)
+    for k in ("p", "deintdt", "dt_var", "eint", "eint_in", "deintdt_in"):
+        assert G["elementwise_%dD_%s" % (dims, k)].tobytes() == b[k].tobytes(), k
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0)])
+def test_riemann_restatement_equals_the_reference_outputs(oracle, dims, n, hfac):
+    import oracle.oracle as O
+    import pipeline
+    from test_oracle_vs_reference import riemann_inputs
+    G = _ideal_gas_golden()
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = riemann_inputs(s)
+    oracle.call("ig_riemann_interactions", O.make_defs(dims, s["h"]), pipeline._ll(s), x["iset"], s["imove"], s["r"],
+                x["u"], s["rho"], s["m"], x["p"], x["grad_p"], x["div_u"], x["work_density"], x["gamma"])
+    for k in ("grad_p", "div_u", "work_density"):
+        assert G["riemann_%dD_%s" % (dims, k)].tobytes() == x[k].tobytes(), k
