@@ -196,3 +196,23 @@ def test_riemann_restatement_equals_the_reference_outputs(oracle, dims, n, hfac)
                 x["u"], s["rho"], s["m"], x["p"], x["grad_p"], x["div_u"], x["work_density"], x["gamma"])
     for k in ("grad_p", "div_u", "work_density"):
         assert G["riemann_%dD_%s" % (dims, k)].tobytes() == x[k].tobytes(), k
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(3, 9, 3.0), (2, 36, 4.0)])
+def test_hot_path_restatement_equals_the_reference_outputs(oracle, dims, n, hfac):
+    """tests/golden/hotpath_sweeps_outputs.npz: what the reference's own scripts (behind oracle/ref_shim, build
+    container, tests/golden/make_golden_hotpath.py) produced for the hot-path sequence of tests/pipeline.py --
+    EOS, MLS, Shepard, Interactions, sensors, delta-SPH, the BIe boundary terms, Rates, residuals, TimeStep -- on
+    the cell-sorted dam-break state: the oracle gives the same bits, output by output, with neither the reference
+    tree nor oracle/_ref at hand (what tests/test_oracle_vs_reference.py checks live where they are)."""
+    import os
+    import pipeline
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_sweeps_outputs.npz"))
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    got = pipeline.oracle_sweeps(s)
+    keys = [k[len("sweeps_%dD_" % dims):] for k in G.files if k.startswith("sweeps_%dD_" % dims)]
+    assert len(keys) >= 30 and set(keys) == set(got)
+    bad = [k for k in keys if not np.array_equal(G["sweeps_%dD_%s" % (dims, k)], np.asarray(got[k]), equal_nan=True)]
+    assert not bad, bad
+    assert np.abs(got["grad_p"]).max() > 0 and np.abs(got["lap_p"]).max() > 0
