@@ -216,3 +216,26 @@ def test_hot_path_restatement_equals_the_reference_outputs(oracle, dims, n, hfac
     bad = [k for k in keys if not np.array_equal(G["sweeps_%dD_%s" % (dims, k)], np.asarray(got[k]), equal_nan=True)]
     assert not bad, bad
     assert np.abs(got["grad_p"]).max() > 0 and np.abs(got["lap_p"]).max() > 0
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_linklist_restatement_equals_the_reference_tool_kernels(oracle, dims):
+    """tests/golden/linklist_tool_outputs.npz: icell of every particle and the head-of-cell table as the reference's
+    own LinkList.cl.in kernels computed them (behind oracle/ref_shim, tests/golden/make_golden_linklist.py) for the
+    reference's LinkList test particles, a dam break and random positions.  The oracle's link-list (cell hash, stable
+    sort, heads) gives the same integers -- bit-exact, with neither the reference tree nor oracle/_ref at hand."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_linklist as mk
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "linklist_tool_outputs.npz"))
+    for name, r, h in mk.inputs(dims):
+        key = "%dD_%s" % (dims, name)
+        ll = oracle.linklist(r, dims, 2.0, h)
+        assert np.array_equal(ll["ncells"], G[key + "_ncells"]), key
+        want = G[key + "_icell_unsorted"]
+        assert np.array_equal(ll["icell"], want[ll["perm"]]), key                    # the same cells ...
+        assert np.array_equal(ll["perm"], np.argsort(want, kind="stable")), key    # ... in the stable order
+        ncw = int(ll["ncells"][3])
+        assert np.array_equal(ll["ihoc"][:ncw], G[key + "_ihoc"]), key
+        assert (G[key + "_ihoc"] < r.shape[0]).sum() == len(np.unique(want)), key
