@@ -239,3 +239,26 @@ def test_linklist_restatement_equals_the_reference_tool_kernels(oracle, dims):
         ncw = int(ll["ncells"][3])
         assert np.array_equal(ll["ihoc"][:ncw], G[key + "_ihoc"]), key
         assert (G[key + "_ihoc"] < r.shape[0]).sum() == len(np.unique(want)), key
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_time_scheme_restatements_equal_the_reference_outputs(oracle, dims):
+    """tests/golden/time_scheme_outputs.npz: the reference's basic/time_scheme/{midpoint, euler, improved_euler}.cl
+    and basic/Domain.cl (removal branch included: NaN and out-of-box positions) run one after the other on a seeded
+    state (tests/golden/make_golden_elementwise.py); the restatements, run the same way, leave the same bits."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_elementwise as mk
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "time_scheme_outputs.npz"))
+    v, N = mk.state(dims)
+    lit = {"N": N, "dt": mk.DT, "relax": mk.RELAX, "dims": dims}
+    for script, entry, outs, fn, args in mk.SEQUENCE:
+        if script is None:
+            mk.spoil(v)
+            continue
+        oracle.call(fn, *[lit[a] if a in lit else v[a] for a in args])
+        for k in outs:
+            want = G["%dD_%s_%s_%s" % (dims, os.path.basename(script)[:-3], entry, k)]
+            assert np.array_equal(want, v[k], equal_nan=True), (script, entry, k)
+    assert (v["imove"] == -256).any()        # Domain did remove particles
