@@ -191,3 +191,29 @@ def test_pair_mask_cache_is_dropped_when_its_inputs_change(oracle):
         assert a.tobytes() == b.tobytes()
     assert not np.array_equal(res[0][0], res[0][4]) and not np.array_equal(res[0][4], res[0][8])
     assert stats["builds"] == 5 and stats["hits"] == 8, stats  # step 0 builds twice (Shepard adds i classes)
+
+
+@pytest.mark.parametrize("engine", [3, 2])
+@pytest.mark.parametrize("dims,n,hfac", [(3, 10, 3.0), (2, 40, 4.0)])
+def test_sweeps_match_the_reference_outputs(dims, n, hfac, engine):
+    """The same sequence against tests/golden/hotpath_sweeps_outputs.npz: what the reference's OWN scripts produced
+    for these states (tests/golden/make_golden_hotpath.py) -- no oracle in between.  (The oracle equals those
+    outputs bit for bit, tests/test_oracle_golden.py, so the bar is the one of test_sweeps_match_oracle.)"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_sweeps_outputs.npz"))
+    pre = "sweeps_%dD_" % dims
+    ref = {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    if "dt" in ref:
+        ref["dt"] = np.float32(ref["dt"])
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)      # (the cell-sorted INPUT state: link-list of the test infrastructure)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    try:
+        assert _lib.lib().aqc_sweep_engine_select(engine) == engine
+        got = pipeline.cuda_sweeps(ctx, s)
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
+    ctx.close()
+    assert len(ref) >= 30 and set(ref) == set(got)
+    bad = [r for r in pipeline.compare(ref, got) if not r[3]]
+    assert not bad, "\n".join("%s: max err %.3e (scale %.3e)" % r[:3] for r in bad)

@@ -198,7 +198,7 @@ def test_riemann_restatement_equals_the_reference_outputs(oracle, dims, n, hfac)
         assert G["riemann_%dD_%s" % (dims, k)].tobytes() == x[k].tobytes(), k
 
 
-@pytest.mark.parametrize("dims,n,hfac", [(3, 9, 3.0), (2, 36, 4.0)])
+@pytest.mark.parametrize("dims,n,hfac", [(3, 10, 3.0), (2, 40, 4.0)])
 def test_hot_path_restatement_equals_the_reference_outputs(oracle, dims, n, hfac):
     """tests/golden/hotpath_sweeps_outputs.npz: what the reference's own scripts (behind oracle/ref_shim, build
     container, tests/golden/make_golden_hotpath.py) produced for the hot-path sequence of tests/pipeline.py --
