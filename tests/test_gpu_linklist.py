@@ -163,3 +163,26 @@ def test_reduce(ctx3):
         du = ctx3.array(u)
         assert ctx3.reduce(_lib.OP_MAX, du) == u.max()
         assert ctx3.reduce(_lib.OP_SUM, du) == u.sum(dtype=np.uint64) % 2 ** 32
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_linklist_matches_the_reference_tool_kernels(dims):
+    """aqc_linklist_build against tests/golden/linklist_tool_outputs.npz: the cell of every particle and the
+    head-of-cell table as the reference's OWN LinkList.cl.in kernels computed them (iCell, iHoc, linkList behind
+    oracle/ref_shim, tests/golden/make_golden_linklist.py) for the reference's LinkList test particles, a dam break
+    and random positions -- no oracle in between.  Bit-exact; the sorted order is the stable one."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_linklist as mk
+    G = np.load(os.path.join(here, "golden", "linklist_tool_outputs.npz"))
+    for name, r, h in mk.inputs(dims):
+        key = "%dD_%s" % (dims, name)
+        got = run_linklist(dims, r, 2.0, h)
+        want = G[key + "_icell_unsorted"]
+        assert np.array_equal(np.asarray(got["ncells"], np.uint32), G[key + "_ncells"]), key
+        assert np.array_equal(got["icell"], want[got["perm"]]), key
+        assert np.array_equal(got["perm"], np.argsort(want, kind="stable")), key
+        assert np.array_equal(got["inv_perm"][got["perm"]], np.arange(r.shape[0], dtype=np.uint32)), key
+        assert np.array_equal(got["ihoc"], G[key + "_ihoc"]), key
