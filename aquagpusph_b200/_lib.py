@@ -258,6 +258,8 @@ def _scalar_bytes(value, typ, dims):
         return np.asarray(value, np.uint32).reshape(4).tobytes()
     if t == "vec4":
         return np.asarray(value, np.float32).reshape(4).tobytes()
+    if t in ("svec2", "uivec2"):
+        return np.asarray(value, np.uint32).reshape(2).tobytes()
     raise AquaError("unsupported scalar type '%s'" % typ)
 
 

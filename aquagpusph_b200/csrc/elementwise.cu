@@ -827,6 +827,215 @@ int l_id_inverse(aqc_ctx* c, size_t, void* const* a)
     return AQC_OK;
 }
 
+// ---- cfd/Boundary/Inlet/Inlet.cl, Outlet/Outlet.cl, Portal/Mirror.cl (presets cfd/inlet.xml, cfd/outlet.xml,
+// cfd/portal.xml): the element-wise kernels of the open boundaries.  Vectors keep every stored component
+// (w in 3-D), sums run left to right like the scripts write them.
+template <int D> __device__ inline V<D> ob_vec_one();
+template <> __device__ inline V<3> ob_vec_one<3>() { return V<3>(make_float4(1.f, 1.f, 1.f, 0.f)); } // types/3D.h:38
+template <> __device__ inline V<2> ob_vec_one<2>() { return V<2>(make_float2(1.f, 1.f)); }
+// Inlet.cl::feed (:64-126): buffer rows become fluid particles on a lattice of the inlet plane
+template <int D>
+__global__ void __launch_bounds__(256)
+k_inlet_feed(int* imove, const uint32_t* iset, void* r, void* u, void* dudt, float* rho, float* drhodt, float* m,
+             float* p, const float* refd, uint32_t first, uint32_t N, float cs, float p0, aqc_f4 g,
+             float dr, aqc_f4 inlet_r, aqc_f4 inlet_ru, aqc_f4 inlet_rv, uint32_t inlet_Nx, uint32_t inlet_Ny,
+             aqc_f4 inlet_n, float inlet_U, aqc_f4 inlet_rFS, float off)
+{
+    GID; // (N: the rows to feed; first: the first buffer row, N_particles - nbuffer)
+    const size_t ii = (size_t)first + i;
+    float u_fac, v_fac;
+    if constexpr (D == 2) {
+        u_fac = ((float)(uint32_t)i + 0.5f) / (float)inlet_Nx;
+        v_fac = 0.f;
+    } else {
+        const uint32_t u_id = (uint32_t)i % inlet_Nx, v_id = (uint32_t)i / inlet_Nx;
+        u_fac = ((float)u_id + 0.5f) / (float)inlet_Nx;
+        v_fac = ((float)v_id + 0.5f) / (float)inlet_Ny;
+    }
+    const V<D> n = from_f4<D>(inlet_n);
+    const V<D> ri = from_f4<D>(inlet_r) + u_fac * from_f4<D>(inlet_ru) + v_fac * from_f4<D>(inlet_rv) + off * n;
+    ri.st(r, ii);
+    imove[ii] = 1;
+    V<D>::splat(0.f).st(dudt, ii);
+    drhodt[ii] = 0.f;
+    (inlet_U * n).st(u, ii);
+    const float rd = refd[iset[ii]];
+    const float ph = rd * from_f4<D>(g).dot(ri - from_f4<D>(inlet_rFS));
+    if constexpr (D == 3)
+        m[ii] = rd * dr * dr * dr;
+    else
+        m[ii] = rd * dr * dr;
+    rho[ii] = rd + ph / (cs * cs); // (reversed EOS)
+    p[ii] = ph + p0;
+}
+int l_inlet_feed(aqc_ctx* c, size_t, void* const* a)
+{
+    if (aqc_scalar<int>(a, 25) == 0) // inlet_starving
+        return AQC_OK;
+    const int d = c->defs.dims;
+    const uint32_t N = aqc_scalar<uint32_t>(a, 10), nbuffer = aqc_scalar<uint32_t>(a, 11);
+    uint32_t iN[2];
+    memcpy(iN, a[20], sizeof(iN)); // svec2
+    const uint64_t want = (uint64_t)iN[0] * iN[1];
+    const uint32_t count = (uint32_t)(want < nbuffer ? want : nbuffer);
+    if (!count)
+        return AQC_OK;
+    const float dr = aqc_scalar<float>(a, 16);
+    const float off = aqc_scalar<float>(a, 24) - c->defs.SUPPORT * c->defs.H - 0.5f * dr;
+    DISPATCH(c, k_inlet_feed, count, (int*)a[0], (const uint32_t*)a[1], a[2], a[3], a[4], (float*)a[5], (float*)a[6],
+             (float*)a[7], (float*)a[8], (const float*)a[9], N - nbuffer, count, aqc_scalar<float>(a, 13),
+             aqc_scalar<float>(a, 14), aqc_vec_scalar(a, 15, d), dr, aqc_vec_scalar(a, 17, d),
+             aqc_vec_scalar(a, 18, d), aqc_vec_scalar(a, 19, d), iN[0], iN[1], aqc_vec_scalar(a, 21, d),
+             aqc_scalar<float>(a, 22), aqc_vec_scalar(a, 23, d), off);
+}
+// Inlet.cl::rates (:148-176): what has not crossed the inlet plane yet moves with the inlet
+template <int D>
+__global__ void __launch_bounds__(256)
+k_inlet_rates(const int* imove, const void* r, void* u, void* dudt, float* drhodt, uint32_t N, aqc_f4 inlet_r,
+              float inlet_U, aqc_f4 inlet_n)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const V<D> n = from_f4<D>(inlet_n);
+    if ((V<D>::ld(r, i) - from_f4<D>(inlet_r)).dot(n) > 0.f)
+        return;
+    (inlet_U * n).st(u, i);
+    V<D>::splat(0.f).st(dudt, i);
+    drhodt[i] = 0.f;
+}
+int l_inlet_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 5);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_inlet_rates, N, (const int*)a[0], a[1], a[2], a[3], (float*)a[4], N, aqc_vec_scalar(a, 6, d),
+             aqc_scalar<float>(a, 7), aqc_vec_scalar(a, 8, d));
+}
+// Outlet.cl::rates (:53-96): beyond the outlet plane the particles move with it, hydrostatic
+template <int D>
+__global__ void __launch_bounds__(256)
+k_outlet_rates(const int* imove, const uint32_t* iset, const void* r, void* u, float* rho, float* p, void* dudt,
+               void* dudt_in, float* drhodt, float* drhodt_in, const float* refd, uint32_t N, float cs, float p0,
+               aqc_f4 g, aqc_f4 outlet_r, aqc_f4 outlet_n, float outlet_U, aqc_f4 outlet_rFS)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const V<D> ri = V<D>::ld(r, i), n = from_f4<D>(outlet_n);
+    if ((ri - from_f4<D>(outlet_r)).dot(n) < 0.f)
+        return;
+    drhodt[i] = 0.f;
+    drhodt_in[i] = 0.f;
+    V<D>::splat(0.f).st(dudt, i);
+    V<D>::splat(0.f).st(dudt_in, i);
+    (outlet_U * n).st(u, i);
+    const float rd = refd[iset[i]];
+    const float ph = rd * from_f4<D>(g).dot(ri - from_f4<D>(outlet_rFS));
+    rho[i] = rd + ph / (cs * cs);
+    p[i] = ph + p0;
+}
+int l_outlet_rates(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 11);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_outlet_rates, N, (const int*)a[0], (const uint32_t*)a[1], a[2], a[3], (float*)a[4], (float*)a[5],
+             a[6], a[7], (float*)a[8], (float*)a[9], (const float*)a[10], N, aqc_scalar<float>(a, 12),
+             aqc_scalar<float>(a, 13), aqc_vec_scalar(a, 14, d), aqc_vec_scalar(a, 15, d), aqc_vec_scalar(a, 16, d),
+             aqc_scalar<float>(a, 17), aqc_vec_scalar(a, 18, d));
+}
+// Outlet.cl::feed (:108-131): a kernel support beyond the outlet plane the particles go back to the buffer
+template <int D>
+__global__ void __launch_bounds__(256)
+k_outlet_feed(int* imove, void* r_in, uint32_t N, aqc_f4 domain_max, aqc_f4 outlet_r, aqc_f4 outlet_n,
+              float support_h)
+{
+    GID;
+    if (imove[i] != 1)
+        return;
+    const float dist = (V<D>::ld(r_in, i) - from_f4<D>(outlet_r)).dot(from_f4<D>(outlet_n));
+    if (dist < 0.f)
+        return;
+    if (dist > support_h) {
+        (from_f4<D>(domain_max) + ob_vec_one<D>()).st(r_in, i);
+        imove[i] = -256;
+    }
+}
+int l_outlet_feed(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_outlet_feed, N, (int*)a[0], a[1], N, aqc_vec_scalar(a, 3, d), aqc_vec_scalar(a, 4, d),
+             aqc_vec_scalar(a, 5, d), c->defs.SUPPORT * c->defs.H);
+}
+// Portal/Mirror.cl::mirror (:70-95; cell() :32-50 = the link-list's hash): what lies within a kernel support
+// of the out plane shows up at the in plane, in the cell it falls into there
+template <int D>
+__global__ void __launch_bounds__(256)
+k_portal_mirror(void* r, int* imirrored, uint32_t* icell, uint32_t N, aqc_f4 portal_in_r, aqc_f4 portal_out_r,
+                aqc_f4 portal_n, aqc_f4 r_min, uint32_t nx, uint32_t ny, float support_h, float idist)
+{
+    GID;
+    const V<D> r_ij = V<D>::ld(r, i) - from_f4<D>(portal_out_r);
+    if (fabsf(r_ij.dot(from_f4<D>(portal_n))) > support_h) {
+        imirrored[i] = 0;
+        return;
+    }
+    imirrored[i] = 1;
+    const V<D> q = from_f4<D>(portal_in_r) + r_ij;
+    q.st(r, i);
+    const uint32_t cx = (uint32_t)((q.v.x - r_min.x) * idist) + 3u;
+    const uint32_t cy = (uint32_t)((q.v.y - r_min.y) * idist) + 3u;
+    if constexpr (D == 3) {
+        const uint32_t cz = (uint32_t)((q.v.z - r_min.z) * idist) + 3u;
+        icell[i] = cx - 1u + (cy - 1u) * nx + (cz - 1u) * nx * ny;
+    } else {
+        icell[i] = cx - 1u + (cy - 1u) * nx;
+    }
+}
+int l_portal_mirror(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 3);
+    const int d = c->defs.dims;
+    uint32_t nc[2];
+    memcpy(nc, a[8], sizeof(nc)); // n_cells.x, .y of the uivec4
+    const float sh = c->defs.SUPPORT * c->defs.H;
+    DISPATCH(c, k_portal_mirror, N, a[0], (int*)a[1], (uint32_t*)a[2], N, aqc_vec_scalar(a, 4, d),
+             aqc_vec_scalar(a, 5, d), aqc_vec_scalar(a, 6, d), aqc_vec_scalar(a, 7, d), nc[0], nc[1], sh, 1.f / sh);
+}
+// Portal/Mirror.cl::unmirror (:108-124)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_portal_unmirror(void* r, const int* imirrored, uint32_t N, aqc_f4 portal_in_r, aqc_f4 portal_out_r)
+{
+    GID;
+    if (!imirrored[i])
+        return;
+    (from_f4<D>(portal_out_r) + (V<D>::ld(r, i) - from_f4<D>(portal_in_r))).st(r, i);
+}
+int l_portal_unmirror(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 2);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_portal_unmirror, N, a[0], (const int*)a[1], N, aqc_vec_scalar(a, 3, d), aqc_vec_scalar(a, 4, d));
+}
+// Portal/Mirror.cl::teleport (:136-153): what crossed the out plane re-enters at the in plane
+template <int D>
+__global__ void __launch_bounds__(256)
+k_portal_teleport(void* r, uint32_t N, aqc_f4 portal_in_r, aqc_f4 portal_out_r, aqc_f4 portal_n)
+{
+    GID;
+    const V<D> r_ij = V<D>::ld(r, i) - from_f4<D>(portal_out_r);
+    if (r_ij.dot(from_f4<D>(portal_n)) < 0.f)
+        return;
+    (from_f4<D>(portal_in_r) + r_ij).st(r, i);
+}
+int l_portal_teleport(aqc_ctx* c, size_t, void* const* a)
+{
+    const uint32_t N = aqc_scalar<uint32_t>(a, 1);
+    const int d = c->defs.dims;
+    DISPATCH(c, k_portal_teleport, N, a[0], N, aqc_vec_scalar(a, 2, d), aqc_vec_scalar(a, 3, d),
+             aqc_vec_scalar(a, 4, d));
+}
 // ---- basic/Sort.cl:57-78 (stage1) and :102-124 (stage2) ----------------------------
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -2002,6 +2211,37 @@ aqc_registrar r_sb_count("basic/SetBuffer.cl", "count", 0,
     { IN("imove", "int*"), OUT("ibuffer", "unsigned int*"), SC("N", "usize") }, l_setbuffer_count);
 aqc_registrar r_sb_set("basic/SetBuffer.cl", "set_imove", 0,
     { OUT("imove", "int*"), SC("N", "usize") }, l_setbuffer_set_imove);
+
+// cfd/Boundary/Inlet/Inlet.cl, Outlet/Outlet.cl, Portal/Mirror.cl (presets cfd/inlet.xml, outlet.xml, portal.xml)
+aqc_registrar r_inlet_feed("cfd/Boundary/Inlet/Inlet.cl", "feed", 0,
+    { OUT("imove", "int*"), RO("iset", "unsigned int*"), OUT("r", "vec*"), OUT("u", "vec*"), OUT("dudt", "vec*"),
+      OUT("rho", "float*"), OUT("drhodt", "float*"), OUT("m", "float*"), OUT("p", "float*"), IN("refd", "float*"),
+      SC("N", "usize"), SC("nbuffer", "usize"), SC("dt", "float"), SC("cs", "float"), SC("p0", "float"),
+      SC("g", "vec"), SC("dr", "float"), SC("inlet_r", "vec"), SC("inlet_ru", "vec"), SC("inlet_rv", "vec"),
+      SC("inlet_N", "svec2"), SC("inlet_n", "vec"), SC("inlet_U", "float"), SC("inlet_rFS", "vec"),
+      SC("inlet_R", "float"), SC("inlet_starving", "int") }, l_inlet_feed);
+aqc_registrar r_inlet_rates("cfd/Boundary/Inlet/Inlet.cl", "rates", 0,
+    { RO("imove", "int*"), RO("r", "vec*"), OUT("u", "vec*"), OUT("dudt", "vec*"), OUT("drhodt", "float*"),
+      SC("N", "usize"), SC("inlet_r", "vec"), SC("inlet_U", "float"), SC("inlet_n", "vec") }, l_inlet_rates);
+aqc_registrar r_outlet_rates("cfd/Boundary/Outlet/Outlet.cl", "rates", 0,
+    { RO("imove", "int*"), RO("iset", "unsigned int*"), RO("r", "vec*"), OUT("u", "vec*"), OUT("rho", "float*"),
+      OUT("p", "float*"), OUT("dudt", "vec*"), OUT("dudt_in", "vec*"), OUT("drhodt", "float*"),
+      OUT("drhodt_in", "float*"), IN("refd", "float*"), SC("N", "usize"), SC("cs", "float"), SC("p0", "float"),
+      SC("g", "vec"), SC("outlet_r", "vec"), SC("outlet_n", "vec"), SC("outlet_U", "float"),
+      SC("outlet_rFS", "vec") }, l_outlet_rates);
+aqc_registrar r_outlet_feed("cfd/Boundary/Outlet/Outlet.cl", "feed", 0,
+    { OUT("imove", "int*"), OUT("r_in", "vec*"), SC("N", "usize"), SC("domain_max", "vec"), SC("outlet_r", "vec"),
+      SC("outlet_n", "vec") }, l_outlet_feed);
+aqc_registrar r_portal_mirror("cfd/Boundary/Portal/Mirror.cl", "mirror", 0,
+    { OUT("r", "vec*"), OUT("imirrored", "int*"), OUT("icell", "usize*"), SC("N", "usize"), SC("portal_in_r", "vec"),
+      SC("portal_out_r", "vec"), SC("portal_n", "vec"), SC("r_min", "vec"), SC("n_cells", "uivec4") },
+    l_portal_mirror);
+aqc_registrar r_portal_unmirror("cfd/Boundary/Portal/Mirror.cl", "unmirror", 0,
+    { OUT("r", "vec*"), IN("imirrored", "int*"), SC("N", "usize"), SC("portal_in_r", "vec"),
+      SC("portal_out_r", "vec"), SC("portal_n", "vec") }, l_portal_unmirror);
+aqc_registrar r_portal_teleport("cfd/Boundary/Portal/Mirror.cl", "teleport", 0,
+    { OUT("r", "vec*"), SC("N", "usize"), SC("portal_in_r", "vec"), SC("portal_out_r", "vec"),
+      SC("portal_n", "vec") }, l_portal_teleport);
 
 aqc_registrar r_ig_eos("cfd/ideal_gas/EOS.cl", "entry", 0,
     { IN("iset", "unsigned int*"), IN("imove", "int*"), IN("rho", "float*"), IN("eint", "float*"),

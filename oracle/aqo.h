@@ -321,4 +321,26 @@ void aqo_ig_riemann_interactions(const aqo_defs* D, const aqo_ll* L, const aqo_u
 /* cfd/ideal_gas/symmetry/Mirror.cl:32-48 */
 void aqo_ig_sym_set(const aqo_usize* mirror_src, float* eint_in, float* deintdt_in, float* deintdt, aqo_usize N);
 
+/* cfd/Boundary/Inlet/Inlet.cl:64-176, cfd/Boundary/Outlet/Outlet.cl:53-131, cfd/Boundary/Portal/Mirror.cl:70-153 */
+void aqo_inlet_feed(const aqo_defs* D, int* imove, const aqo_usize* iset, float* r, float* u, float* dudt,
+                    float* rho, float* drhodt, float* m, float* p, const float* refd, aqo_usize N,
+                    aqo_usize nbuffer, float cs, float p0, const float* g, float dr, const float* inlet_r,
+                    const float* inlet_ru, const float* inlet_rv, const aqo_usize* inlet_N, const float* inlet_n,
+                    float inlet_U, const float* inlet_rFS, float inlet_R, int inlet_starving);
+void aqo_inlet_rates(const int* imove, const float* r, float* u, float* dudt, float* drhodt, aqo_usize N,
+                     const float* inlet_r, float inlet_U, const float* inlet_n, int dims);
+void aqo_outlet_rates(const int* imove, const aqo_usize* iset, const float* r, float* u, float* rho, float* p,
+                      float* dudt, float* dudt_in, float* drhodt, float* drhodt_in, const float* refd, aqo_usize N,
+                      float cs, float p0, const float* g, const float* outlet_r, const float* outlet_n,
+                      float outlet_U, const float* outlet_rFS, int dims);
+void aqo_outlet_feed(const aqo_defs* D, int* imove, float* r_in, aqo_usize N, const float* domain_max,
+                     const float* outlet_r, const float* outlet_n);
+void aqo_portal_mirror(const aqo_defs* D, float* r, int* imirrored, aqo_usize* icell, aqo_usize N,
+                       const float* portal_in_r, const float* portal_out_r, const float* portal_n,
+                       const float* r_min, const aqo_usize* n_cells);
+void aqo_portal_unmirror(float* r, const int* imirrored, aqo_usize N, const float* portal_in_r,
+                         const float* portal_out_r, int dims);
+void aqo_portal_teleport(float* r, aqo_usize N, const float* portal_in_r, const float* portal_out_r,
+                         const float* portal_n, int dims);
+
 #endif

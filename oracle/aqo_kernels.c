@@ -1875,3 +1875,187 @@ void aqo_ig_ie_corrector(const int* imove, const float* deintdt, const float* de
         }
     }
 }
+
+/* ---- cfd/Boundary/Inlet/Inlet.cl, cfd/Boundary/Outlet/Outlet.cl, cfd/Boundary/Portal/Mirror.cl: the
+ * element-wise kernels of the open-boundary presets (cfd/inlet.xml, cfd/outlet.xml, cfd/portal.xml).
+ * Vectors keep every stored component (w in 3-D), sums run left to right like the scripts write them. */
+
+/* Inlet.cl:64-126.  inlet_N: (usize, usize). */
+void aqo_inlet_feed(const aqo_defs* D, int* imove, const aqo_usize* iset, float* r, float* u, float* dudt,
+                    float* rho, float* drhodt, float* m, float* p, const float* refd, aqo_usize N,
+                    aqo_usize nbuffer, float cs, float p0, const float* g, float dr, const float* inlet_r,
+                    const float* inlet_ru, const float* inlet_rv, const aqo_usize* inlet_N, const float* inlet_n,
+                    float inlet_U, const float* inlet_rFS, float inlet_R, int inlet_starving)
+{
+    const int dims = D->dims, vs = VS(dims);
+    if (inlet_starving == 0)
+        return;
+    const float off = inlet_R - D->SUPPORT * D->H - 0.5f * dr;
+    aqo_usize n = nbuffer;
+    if (inlet_N[0] * inlet_N[1] < n)
+        n = inlet_N[0] * inlet_N[1];
+    AQO_FOR_I(n) {
+        const aqo_usize ii = N - nbuffer + i;
+        float u_fac, v_fac;
+        if (dims == 2) {
+            u_fac = ((float)i + 0.5f) / (float)inlet_N[0];
+            v_fac = 0.f;
+        } else {
+            const aqo_usize u_id = i % inlet_N[0], v_id = i / inlet_N[0];
+            u_fac = ((float)u_id + 0.5f) / (float)inlet_N[0];
+            v_fac = ((float)v_id + 0.5f) / (float)inlet_N[1];
+        }
+        float d[4];
+        for (int k = 0; k < vs; k++) {
+            const float rk = inlet_r[k] + u_fac * inlet_ru[k] + v_fac * inlet_rv[k] + off * inlet_n[k];
+            r[(size_t)ii * vs + k] = rk;
+            dudt[(size_t)ii * vs + k] = 0.f;
+            u[(size_t)ii * vs + k] = inlet_U * inlet_n[k];
+            d[k] = rk - inlet_rFS[k];
+        }
+        imove[ii] = 1;
+        drhodt[ii] = 0.f;
+        const float rd = refd[iset[ii]];
+        const float ph = rd * aqo_dotv(g, d, vs);
+        m[ii] = (dims == 3) ? rd * dr * dr * dr : rd * dr * dr;
+        rho[ii] = rd + ph / (cs * cs);
+        p[ii] = ph + p0;
+    }
+}
+
+/* Inlet.cl:148-176 */
+void aqo_inlet_rates(const int* imove, const float* r, float* u, float* dudt, float* drhodt, aqo_usize N,
+                     const float* inlet_r, float inlet_U, const float* inlet_n, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1)
+            continue;
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = r[(size_t)i * vs + k] - inlet_r[k];
+        if (aqo_dotv(d, inlet_n, vs) > 0.f)
+            continue;
+        for (int k = 0; k < vs; k++) {
+            u[(size_t)i * vs + k] = inlet_U * inlet_n[k];
+            dudt[(size_t)i * vs + k] = 0.f;
+        }
+        drhodt[i] = 0.f;
+    }
+}
+
+/* Outlet.cl:53-96 */
+void aqo_outlet_rates(const int* imove, const aqo_usize* iset, const float* r, float* u, float* rho, float* p,
+                      float* dudt, float* dudt_in, float* drhodt, float* drhodt_in, const float* refd, aqo_usize N,
+                      float cs, float p0, const float* g, const float* outlet_r, const float* outlet_n,
+                      float outlet_U, const float* outlet_rFS, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1)
+            continue;
+        float d[4], e[4];
+        for (int k = 0; k < vs; k++) {
+            d[k] = r[(size_t)i * vs + k] - outlet_r[k];
+            e[k] = r[(size_t)i * vs + k] - outlet_rFS[k];
+        }
+        if (aqo_dotv(d, outlet_n, vs) < 0.f)
+            continue;
+        drhodt[i] = 0.f;
+        drhodt_in[i] = 0.f;
+        for (int k = 0; k < vs; k++) {
+            dudt[(size_t)i * vs + k] = 0.f;
+            dudt_in[(size_t)i * vs + k] = 0.f;
+            u[(size_t)i * vs + k] = outlet_U * outlet_n[k];
+        }
+        const float rd = refd[iset[i]];
+        const float ph = rd * aqo_dotv(g, e, vs);
+        rho[i] = rd + ph / (cs * cs);
+        p[i] = ph + p0;
+    }
+}
+
+/* Outlet.cl:108-131 */
+void aqo_outlet_feed(const aqo_defs* D, int* imove, float* r_in, aqo_usize N, const float* domain_max,
+                     const float* outlet_r, const float* outlet_n)
+{
+    const int dims = D->dims, vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (imove[i] != 1)
+            continue;
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = r_in[(size_t)i * vs + k] - outlet_r[k];
+        const float dist = aqo_dotv(d, outlet_n, vs);
+        if (dist < 0.f)
+            continue;
+        if (dist > D->SUPPORT * D->H) {
+            for (int k = 0; k < vs; k++) /* VEC_ONE: w = 0 in 3-D (types/3D.h:38) */
+                r_in[(size_t)i * vs + k] = domain_max[k] + ((k < dims) ? 1.f : 0.f);
+            imove[i] = -256;
+        }
+    }
+}
+
+/* Portal/Mirror.cl:32-50: the cell of a moved particle, LinkList.cl.in's formula */
+static aqo_usize aqo_portal_cell(const aqo_defs* D, const float* r, const float* r_min, const aqo_usize* n_cells)
+{
+    const float idist = 1.f / (D->SUPPORT * D->H);
+    const aqo_usize cx = (aqo_usize)((r[0] - r_min[0]) * idist) + 3u;
+    const aqo_usize cy = (aqo_usize)((r[1] - r_min[1]) * idist) + 3u;
+    if (D->dims == 3) {
+        const aqo_usize cz = (aqo_usize)((r[2] - r_min[2]) * idist) + 3u;
+        return cx - 1u + (cy - 1u) * n_cells[0] + (cz - 1u) * n_cells[0] * n_cells[1];
+    }
+    return cx - 1u + (cy - 1u) * n_cells[0];
+}
+
+/* Portal/Mirror.cl:70-95 */
+void aqo_portal_mirror(const aqo_defs* D, float* r, int* imirrored, aqo_usize* icell, aqo_usize N,
+                       const float* portal_in_r, const float* portal_out_r, const float* portal_n,
+                       const float* r_min, const aqo_usize* n_cells)
+{
+    const int vs = VS(D->dims);
+    AQO_FOR_I(N) {
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = r[(size_t)i * vs + k] - portal_out_r[k];
+        if (fabsf(aqo_dotv(d, portal_n, vs)) > D->SUPPORT * D->H) {
+            imirrored[i] = 0;
+            continue;
+        }
+        imirrored[i] = 1;
+        for (int k = 0; k < vs; k++)
+            r[(size_t)i * vs + k] = portal_in_r[k] + d[k];
+        icell[i] = aqo_portal_cell(D, r + (size_t)i * vs, r_min, n_cells);
+    }
+}
+
+/* Portal/Mirror.cl:108-124 */
+void aqo_portal_unmirror(float* r, const int* imirrored, aqo_usize N, const float* portal_in_r,
+                         const float* portal_out_r, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        if (!imirrored[i])
+            continue;
+        for (int k = 0; k < vs; k++)
+            r[(size_t)i * vs + k] = portal_out_r[k] + (r[(size_t)i * vs + k] - portal_in_r[k]);
+    }
+}
+
+/* Portal/Mirror.cl:136-153 */
+void aqo_portal_teleport(float* r, aqo_usize N, const float* portal_in_r, const float* portal_out_r,
+                         const float* portal_n, int dims)
+{
+    const int vs = VS(dims);
+    AQO_FOR_I(N) {
+        float d[4];
+        for (int k = 0; k < vs; k++)
+            d[k] = r[(size_t)i * vs + k] - portal_out_r[k];
+        if (aqo_dotv(d, portal_n, vs) < 0.f)
+            continue;
+        for (int k = 0; k < vs; k++)
+            r[(size_t)i * vs + k] = portal_in_r[k] + d[k];
+    }
+}

@@ -769,6 +769,33 @@ class Interpreter:
                 c("sym_drop", V["imove"], V["r"], N, V["symmetry_r"], V["symmetry_n"], V["domain_max"], d)
             else:
                 raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
+        elif rel in ("cfd/Boundary/Inlet/Inlet.cl", "cfd/Boundary/Outlet/Outlet.cl", "cfd/Boundary/Portal/Mirror.cl"):
+            # presets cfd/inlet.xml, cfd/outlet.xml, cfd/portal.xml: the element-wise kernels of the open
+            # boundaries (aqo_kernels.c, bit-identical to the scripts)
+            vec = lambda n: np.ascontiguousarray(V[n], np.float32)  # noqa: E731
+            if rel.endswith("Inlet.cl") and entry == "feed":
+                c("inlet_feed", D, V["imove"], V["iset"], V["r"], V["u"], V["dudt"], V["rho"], V["drhodt"], V["m"],
+                  V["p"], V["refd"], N, int(V["nbuffer"]), f32("cs"), f32("p0"), vec("g"), f32("dr"), vec("inlet_r"),
+                  vec("inlet_ru"), vec("inlet_rv"), np.ascontiguousarray(V["inlet_N"], np.uint32), vec("inlet_n"),
+                  f32("inlet_U"), vec("inlet_rFS"), f32("inlet_R"), int(V["inlet_starving"]))
+            elif rel.endswith("Inlet.cl") and entry == "rates":
+                c("inlet_rates", V["imove"], V["r"], V["u"], V["dudt"], V["drhodt"], N, vec("inlet_r"),
+                  f32("inlet_U"), vec("inlet_n"), d)
+            elif rel.endswith("Outlet.cl") and entry == "rates":
+                c("outlet_rates", V["imove"], V["iset"], V["r"], V["u"], V["rho"], V["p"], V["dudt"], V["dudt_in"],
+                  V["drhodt"], V["drhodt_in"], V["refd"], N, f32("cs"), f32("p0"), vec("g"), vec("outlet_r"),
+                  vec("outlet_n"), f32("outlet_U"), vec("outlet_rFS"), d)
+            elif rel.endswith("Outlet.cl") and entry == "feed":
+                c("outlet_feed", D, V["imove"], V["r_in"], N, vec("domain_max"), vec("outlet_r"), vec("outlet_n"))
+            elif entry == "mirror":
+                c("portal_mirror", D, V["r"], V["imirrored"], V["icell"], N, vec("portal_in_r"), vec("portal_out_r"),
+                  vec("portal_n"), vec("r_min"), np.ascontiguousarray(V["n_cells"], np.uint32))
+            elif entry == "unmirror":
+                c("portal_unmirror", V["r"], V["imirrored"], N, vec("portal_in_r"), vec("portal_out_r"), d)
+            elif entry == "teleport":
+                c("portal_teleport", V["r"], N, vec("portal_in_r"), vec("portal_out_r"), vec("portal_n"), d)
+            else:
+                raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
         elif rel == "aqua/MPIdeltaSPH.cl":
             # remote (halo) terms of MLS / delta-SPH: ours, not reference scripts (aqo_kernels.c)
             rl = O.make_ll(V["mpi_icell"], V["mpi_ihoc"], V["n_cells"], N)

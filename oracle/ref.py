@@ -48,6 +48,10 @@ class _U4(C.Structure):
     _fields_ = [("x", C.c_uint32), ("y", C.c_uint32), ("z", C.c_uint32), ("w", C.c_uint32)]
 
 
+class _U2(C.Structure):
+    _fields_ = [("x", C.c_uint32), ("y", C.c_uint32)]
+
+
 def _mangle(script):
     import re
     return re.sub(r"\W", "_", script[:-3])
@@ -107,6 +111,9 @@ class Ref:
             elif kind == "svec4":
                 a = np.asarray(v, np.uint32).ravel()
                 args.append(_U4(*[int(x) for x in a[:4]]))
+            elif kind == "svec2":
+                a = np.asarray(v, np.uint32).ravel()
+                args.append(_U2(int(a[0]), int(a[1])))
             else:
                 raise ValueError(kind)
         fn(*args)

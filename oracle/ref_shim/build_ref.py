@@ -45,6 +45,7 @@ SCRIPTS = [
     "cfd/ideal_gas/riemann/Rates.cl", "cfd/ideal_gas/time_scheme/midpoint.cl",
     "cfd/ideal_gas/symmetry/Mirror.cl", "cfd/ideal_gas/riemann/Interactions.cl",
     "cfd/ideal_gas/time_scheme/euler.cl", "cfd/ideal_gas/time_scheme/improved_euler.cl",
+    "cfd/Boundary/Inlet/Inlet.cl", "cfd/Boundary/Outlet/Outlet.cl", "cfd/Boundary/Portal/Mirror.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 
@@ -156,7 +157,7 @@ def wrapper(script, dims, header=None):
             else:
                 t = " ".join(p_.replace("const", "").split()[:-1])
                 kinds.append({"float": "float", "usize": "uint", "uint": "uint", "unsigned int": "uint",
-                              "int": "int", "vec": "vec", "svec4": "svec4", "uivec4": "svec4",
+                              "int": "int", "vec": "vec", "svec4": "svec4", "uivec4": "svec4", "svec2": "svec2",
                               "vec4": "vec4"}[t.strip()])
         out.append((entry, names, kinds))
     return "\n".join(lines) + "\n", out

@@ -262,3 +262,22 @@ def test_time_scheme_restatements_equal_the_reference_outputs(oracle, dims):
             want = G["%dD_%s_%s_%s" % (dims, os.path.basename(script)[:-3], entry, k)]
             assert np.array_equal(want, v[k], equal_nan=True), (script, entry, k)
     assert (v["imove"] == -256).any()        # Domain did remove particles
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_open_boundary_kernels_match_the_reference_outputs(oracle, dims):
+    """oracle/aqo_kernels.c: aqo_inlet_* / aqo_outlet_* / aqo_portal_* against the committed outputs of the
+    reference's own scripts (cfd/Boundary/Inlet/Inlet.cl, Outlet/Outlet.cl, Portal/Mirror.cl run behind
+    oracle/ref_shim by tests/golden/make_golden_open_boundary.py): the same bits after every kernel, without
+    the reference tree."""
+    import os
+    import open_boundary_common as ob
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "open_boundary_outputs.npz"))
+    case, v = ob.state(dims)
+    D = oracle.make_defs(dims, case["h"])
+    b = ob.args_of(v)
+    for step, key in enumerate(ob.STEPS):
+        ob.oracle_step(oracle, D, dims, key, b)
+        for k in ob.WRITES[key]:
+            assert b[k].tobytes() == G["%dD_step%d_%s" % (dims, step, k)].tobytes(), (key, k)
+    ob.checks(v, b, dims)

@@ -580,3 +580,31 @@ def test_riemann_interactions_match_reference_script(oracle, dims, n, hfac):
     assert (d[~fl] == 7.0).all() and (g[~fl] == 7.0).all()
     if dims == 3:
         assert (g[:, 3] == 7.0).all()     # only .XYZ is written
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_open_boundary_kernels_match_reference_scripts(oracle, dims):
+    """cfd/Boundary/Inlet/Inlet.cl::feed / rates, Outlet/Outlet.cl::rates / feed, Portal/Mirror.cl::mirror /
+    unmirror / teleport (presets cfd/inlet.xml, cfd/outlet.xml, cfd/portal.xml): the C
+    restatement gives the reference script's bits after every kernel of the sequence."""
+    import open_boundary_common as ob
+    case, v = ob.state(dims)
+    R = ref.Ref(dims, case["h"])
+    D = oracle.make_defs(dims, case["h"])
+    a, b = ob.args_of(v), ob.args_of(v)
+    for key in ob.STEPS:
+        n = v["N"] if key != (ob.INLET, "feed") else v["nbuffer"] + 13   # (more work items than buffer rows)
+        R.run(key[0], key[1], n, a)
+        ob.oracle_step(oracle, D, dims, key, b)
+        for k in ob.WRITES[key]:
+            assert a[k].tobytes() == b[k].tobytes(), (key, k)
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert a[k].tobytes() == b[k].tobytes(), k
+    ob.checks(v, b, dims)
+    # a starving flag of 0 leaves everything alone
+    c = ob.args_of(v)
+    c["inlet_starving"] = 0
+    ob.oracle_step(oracle, D, dims, (ob.INLET, "feed"), c)
+    R.run(ob.INLET, "feed", v["nbuffer"], ob.args_of(v), inlet_starving=0)
+    assert all(c[k].tobytes() == v[k].tobytes() for k in ob.WRITES[(ob.INLET, "feed")])

@@ -107,6 +107,50 @@ void emu_small(int dims, float* ekin, void* ff, float4* fm, float* rho_in, const
     }
 }
 /* cfd/Boundary/Symmetry/Mirror.cl: detect, (the preset's radix sort happens outside), feed, set, sort, drop */
+void emu_open_boundary(int dims, int step, int* imove, const uint32_t* iset, void* r, void* r_in, void* u, void* dudt,
+                       void* dudt_in, float* rho, float* drhodt, float* drhodt_in, float* m, float* p,
+                       const float* refd, int* imirrored, uint32_t* icell, uint32_t N_, uint32_t nbuffer,
+                       const float* vecs, const float* fl, const uint32_t* un, float support_h)
+{
+    // vecs: g, domain_max, inlet_r, inlet_ru, inlet_rv, inlet_n, inlet_rFS, outlet_r, outlet_n, outlet_rFS,
+    //       portal_in_r, portal_out_r, portal_n, r_min (4 floats each)
+    // fl: cs, p0, dr, inlet_U, inlet_R, outlet_U;  un: inlet_N.x, inlet_N.y, n_cells.x, n_cells.y
+    const int w = dims == 3 ? 4 : 2;
+#define VV(k) f4(vecs + 4 * (k), w)
+    uint32_t N = N_;
+    if (step == 0) { // the launcher's arithmetic (l_inlet_feed)
+        const uint64_t want = (uint64_t)un[0] * un[1];
+        const uint32_t count = (uint32_t)(want < nbuffer ? want : nbuffer);
+        const float off = fl[4] - support_h - 0.5f * fl[2];
+        const uint32_t first = N_ - nbuffer;
+        N = count;
+        FOR_ALL(k_inlet_feed<3>(imove, iset, r, u, dudt, rho, drhodt, m, p, refd, first, N, fl[0], fl[1], VV(0), fl[2],
+                                VV(2), VV(3), VV(4), un[0], un[1], VV(5), fl[3], VV(6), off),
+                k_inlet_feed<2>(imove, iset, r, u, dudt, rho, drhodt, m, p, refd, first, N, fl[0], fl[1], VV(0), fl[2],
+                                VV(2), VV(3), VV(4), un[0], un[1], VV(5), fl[3], VV(6), off))
+    } else if (step == 1) {
+        FOR_ALL(k_inlet_rates<3>(imove, r, u, dudt, drhodt, N, VV(2), fl[3], VV(5)),
+                k_inlet_rates<2>(imove, r, u, dudt, drhodt, N, VV(2), fl[3], VV(5)))
+    } else if (step == 2) {
+        FOR_ALL(k_outlet_rates<3>(imove, iset, r, u, rho, p, dudt, dudt_in, drhodt, drhodt_in, refd, N, fl[0], fl[1],
+                                  VV(0), VV(7), VV(8), fl[5], VV(9)),
+                k_outlet_rates<2>(imove, iset, r, u, rho, p, dudt, dudt_in, drhodt, drhodt_in, refd, N, fl[0], fl[1],
+                                  VV(0), VV(7), VV(8), fl[5], VV(9)))
+    } else if (step == 3) {
+        FOR_ALL(k_outlet_feed<3>(imove, r_in, N, VV(1), VV(7), VV(8), support_h),
+                k_outlet_feed<2>(imove, r_in, N, VV(1), VV(7), VV(8), support_h))
+    } else if (step == 4) {
+        FOR_ALL(k_portal_mirror<3>(r, imirrored, icell, N, VV(10), VV(11), VV(12), VV(13), un[2], un[3], support_h,
+                                   1.f / support_h),
+                k_portal_mirror<2>(r, imirrored, icell, N, VV(10), VV(11), VV(12), VV(13), un[2], un[3], support_h,
+                                   1.f / support_h))
+    } else if (step == 5) {
+        FOR_ALL(k_portal_unmirror<3>(r, imirrored, N, VV(10), VV(11)), k_portal_unmirror<2>(r, imirrored, N, VV(10), VV(11)))
+    } else {
+        FOR_ALL(k_portal_teleport<3>(r, N, VV(10), VV(11), VV(12)), k_portal_teleport<2>(r, N, VV(10), VV(11), VV(12)))
+    }
+#undef VV
+}
 void emu_sym_detect(int dims, const int* imove, const void* r_in, uint32_t* imirror, uint32_t N, const float* sr_,
                     const float* sn_, float support_h)
 {
@@ -147,7 +191,8 @@ def _lift():
     # launchers: 'int l_xxx(aqc_ctx* c, ...)\n{ ... \n}\n' at column 0
     body = re.sub(r"^int l_\w+\(aqc_ctx\*[^\n]*\n\{\n.*?^\}\n", "", body, flags=re.S | re.M)
     assert "DISPATCH" not in body and "LAUNCH(" not in body
-    assert all(k in body for k in ("k_energy_energy", "k_motion_rate", "k_forces", "k_id_inverse", "k_ab_corrector"))
+    assert all(k in body for k in ("k_energy_energy", "k_motion_rate", "k_forces", "k_id_inverse", "k_ab_corrector",
+                                   "k_inlet_feed", "k_outlet_rates", "k_portal_mirror"))
     return helpers + body
 
 
@@ -340,6 +385,41 @@ def test_symmetry_mirror_kernel_bodies_match_the_oracle(oracle, emu, dims):
     for k in e:
         assert e[k].tobytes() == o[k].tobytes(), k
     assert (o["mirror_src_in"] < N).sum() == int(o["imirror"].sum()) > 0 and (o["imove"] == -256).sum() > 0
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_open_boundary_kernel_bodies_match_the_oracle(oracle, emu, dims):
+    """k_inlet_* / k_outlet_* / k_portal_* of elementwise.cu (cfd/Boundary/Inlet/Inlet.cl, Outlet/Outlet.cl,
+    Portal/Mirror.cl) with their launchers' arithmetic, on the state and in the order of
+    tests/test_oracle_vs_reference.py::test_open_boundary_kernels_match_reference_scripts, which pins the
+    oracle to the reference's scripts: the same bits after every kernel."""
+    import open_boundary_common as ob
+    case, v = ob.state(dims)
+    D = oracle.make_defs(dims, case["h"])
+    e, o = ob.args_of(v), ob.args_of(v)
+
+    def pad(x):
+        a = np.zeros(4, np.float32)
+        a[:len(x)] = x
+        return a
+    vecs = np.concatenate([pad(v[k]) for k in ("g", "domain_max", "inlet_r", "inlet_ru", "inlet_rv", "inlet_n",
+                                               "inlet_rFS", "outlet_r", "outlet_n", "outlet_rFS", "portal_in_r",
+                                               "portal_out_r", "portal_n", "r_min")])
+    fl = np.array([v["cs"], v["p0"], v["dr"], v["inlet_U"], v["inlet_R"], v["outlet_U"]], np.float32)
+    un = np.array([v["inlet_N"][0], v["inlet_N"][1], v["n_cells"][0], v["n_cells"][1]], np.uint32)
+    for step, key in enumerate(ob.STEPS):
+        emu.emu_open_boundary(dims, step, _p(e["imove"]), _p(e["iset"]), _p(e["r"]), _p(e["r_in"]), _p(e["u"]),
+                              _p(e["dudt"]), _p(e["dudt_in"]), _p(e["rho"]), _p(e["drhodt"]), _p(e["drhodt_in"]),
+                              _p(e["m"]), _p(e["p"]), _p(e["refd"]), _p(e["imirrored"]), _p(e["icell"]),
+                              C.c_uint32(v["N"]), C.c_uint32(v["nbuffer"]), _p(vecs), _p(fl), _p(un),
+                              C.c_float(D.SUPPORT * D.H))
+        ob.oracle_step(oracle, D, dims, key, o)
+        for k in ob.WRITES[key]:
+            assert e[k].tobytes() == o[k].tobytes(), (key, k)
+    for k in e:
+        if isinstance(e[k], np.ndarray):
+            assert e[k].tobytes() == o[k].tobytes(), k
+    ob.checks(v, o, dims)
 
 
 # ---- cfd/ideal_gas: the element-wise kernels ---------------------------------------------------------------
