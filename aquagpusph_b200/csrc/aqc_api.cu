@@ -288,9 +288,13 @@ extern "C" int aqc_set_define(aqc_ctx* ctx, const char* name, const char* value)
             return aqc_fail(ctx, AQC_ERR_ARG, "KERNEL_NAME=%s: only the Wendland kernel is built",
                             v.c_str());
     } else if (n == "__LAP_FORMULATION__") {
-        if (v != "1" && v != "__LAP_MONAGHAN__")
+        if (v == "2" || v == "__LAP_MORRIS__")
+            ctx->lap_morris = true; // cfd/Interactions.cl runs PInteractionsMorris, nothing is fused
+        else if (v == "1" || v == "__LAP_MONAGHAN__")
+            ctx->lap_morris = false;
+        else
             return aqc_fail(ctx, AQC_ERR_ARG,
-                            "__LAP_FORMULATION__=%s: only __LAP_MONAGHAN__ is built", v.c_str());
+                            "__LAP_FORMULATION__=%s: __LAP_MONAGHAN__ and __LAP_MORRIS__ are built", v.c_str());
     } else
         return 1;
     return AQC_OK;

@@ -95,6 +95,7 @@ struct aqc_ctx {
     float dr_factor = 0.5f;
     float min_bound_dist = 0.f;
     float elastic_factor = 0.f;
+    bool lap_morris = false;        // __LAP_FORMULATION__ = __LAP_MORRIS__ (cfd/Interactions.cl:130-131)
     bool has_dr_factor = false, has_min_bound_dist = false;
     // TSCHEME_ADAMS_BASHFORTH_STEPS (adam_bashforth.cl:66-68: 5u unless the problem defines it)
     unsigned ab_steps = 5u;

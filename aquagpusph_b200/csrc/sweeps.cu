@@ -268,6 +268,42 @@ struct PInteractions : PBase {
     }
 };
 
+// cfd/Interactions.cl:60-145 compiled with __LAP_FORMULATION__ = __LAP_MORRIS__ (:130-131; the <Define> of
+// examples/2D/taylor_green and cylinder_inside_channel): lap_u takes f_ij * 2 / (rho_i rho_j) * (u_j - u_i)
+// instead of the Cleary term along r_ij; grad_p and div_u are the Monaghan build's.  Never fused
+// (aqc_launch_fused refuses under this definition): the fused groups are built for the default.
+template <int D>
+struct PInteractionsMorris : PInteractions<D> {
+    using IState = typename PInteractions<D>::IState;
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float t = 2.f - q_of(d2, this->invH);
+        const float fr = (t * t) * (t * A.w); // kernelF(q)*CONF*m_j / rho_j
+        const float dux = B.x - s.ux, duy = B.y - s.uy, duz = B.z - s.uz;
+        float udr = dux * dx + duy * dy;
+        if constexpr (D == 3)
+            udr += duz * dz;
+        const float a = (s.p + B.w) * fr;
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        s.lx += fr * dux; s.ly += fr * duy;
+        if constexpr (D == 3)
+            s.lz += fr * duz;
+        s.du += udr * fr;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        const float rho_i = __ldg(this->rho + i);
+        const float ir = 1.f / rho_i;
+        const float c2 = 2.f * ir;
+        stvec_xyz<D>(this->grad_p, i, s.gx * ir, s.gy * ir, s.gz * ir);
+        stvec_xyz<D>(this->lap_u, i, s.lx * c2, s.ly * c2, s.lz * c2);
+        this->div_u[i] = s.du * rho_i;
+    }
+};
+
 // ------------------------------------------------------------------------
 // basic/Shepard.cl:76-125 (MODE 0) and cfd/Shepard.cl:29-35 (MODE 1)
 template <int D, int MODE>
@@ -2031,9 +2067,9 @@ void set_base(P& p, const aqc_ctx* ctx, const void* imove)
 #define DIMS_DISPATCH(ctx, FN, ...)                                            \
     ((ctx)->defs.dims == 3 ? FN<3>(__VA_ARGS__) : FN<2>(__VA_ARGS__))
 
-template <int D> int run_interactions(aqc_ctx* ctx, size_t n, void* const* a)
+template <int D, class P> int run_interactions(aqc_ctx* ctx, size_t n, void* const* a)
 {
-    PInteractions<D> p;
+    P p;
     set_base(p, ctx, a[0]);
     p.r = a[1]; p.u = a[2]; p.rho = (const float*)a[3]; p.m = (const float*)a[4];
     p.p = (const float*)a[5]; p.grad_p = a[6]; p.lap_u = a[7]; p.div_u = (float*)a[8];
@@ -2043,7 +2079,14 @@ template <int D> int run_interactions(aqc_ctx* ctx, size_t n, void* const* a)
     (void)n;
     return launch_sweep(ctx, p, make_ll(a, 10, N));
 }
-int l_interactions(aqc_ctx* c, size_t n, void* const* a) { return DIMS_DISPATCH(c, run_interactions, c, n, a); }
+int l_interactions(aqc_ctx* c, size_t n, void* const* a)
+{
+    if (c->lap_morris) // <Define name="__LAP_FORMULATION__" value="__LAP_MORRIS__"/>
+        return c->defs.dims == 3 ? run_interactions<3, PInteractionsMorris<3>>(c, n, a)
+                                 : run_interactions<2, PInteractionsMorris<2>>(c, n, a);
+    return c->defs.dims == 3 ? run_interactions<3, PInteractions<3>>(c, n, a)
+                             : run_interactions<2, PInteractions<2>>(c, n, a);
+}
 
 template <int D, int MODE> int run_shepard(aqc_ctx* ctx, void* const* a)
 {
@@ -2190,7 +2233,12 @@ template <int D> int run_bi_lapu(aqc_ctx* ctx, void* const* a)
     p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
     return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 6)));
 }
-int l_bi_lapu(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_lapu, c, a); }
+int l_bi_lapu(aqc_ctx* c, size_t, void* const* a)
+{
+    if (c->lap_morris) // (the host runs the script itself under this definition: Kernel::setup)
+        return aqc_fail(c, AQC_ERR_ARG, "%s: the hand-written kernel holds the __LAP_MONAGHAN__ branch only", "cfd/Boundary/BI/LapU.cl::freeslip");
+    return DIMS_DISPATCH(c, run_bi_lapu, c, a);
+}
 template <int D> int run_bi_interp(aqc_ctx* ctx, void* const* a)
 {
     PBIInterpolation<D> p;
@@ -2232,7 +2280,12 @@ template <int D> int run_bi_noslip(aqc_ctx* ctx, void* const* a)
     p.H2 = ctx->defs.H * ctx->defs.H;
     return launch_sweep(ctx, p, make_ll(a, 11, aqc_scalar<uint32_t>(a, 8)));
 }
-int l_bi_noslip(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_bi_noslip, c, a); }
+int l_bi_noslip(aqc_ctx* c, size_t, void* const* a)
+{
+    if (c->lap_morris) // (the host runs the script itself under this definition: Kernel::setup)
+        return aqc_fail(c, AQC_ERR_ARG, "%s: the hand-written kernel holds the __LAP_MONAGHAN__ branch only", "cfd/Boundary/BI/NoSlip.cl::entry");
+    return DIMS_DISPATCH(c, run_bi_noslip, c, a);
+}
 template <int D> int run_ig_riemann(aqc_ctx* ctx, void* const* a)
 {
     // (iset, imove, r, u, rho, m, p, grad_p, div_u, work_density, gamma, N, icell, ihoc, n_cells)
@@ -2293,7 +2346,12 @@ template <int D> int run_mpi_inter(aqc_ctx* ctx, void* const* a)
     p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
     return launch_sweep(ctx, p, make_ll_remote(a, 14, aqc_scalar<uint32_t>(a, 13)));
 }
-int l_mpi_inter(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_mpi_inter, c, a); }
+int l_mpi_inter(aqc_ctx* c, size_t, void* const* a)
+{
+    if (c->lap_morris) // (the host runs the script itself under this definition: Kernel::setup)
+        return aqc_fail(c, AQC_ERR_ARG, "%s: the hand-written kernel holds the __LAP_MONAGHAN__ branch only", "cfd/MPI.cl::interactions");
+    return DIMS_DISPATCH(c, run_mpi_inter, c, a);
+}
 
 // aqua/MPIdeltaSPH.cl (ours): remote terms of MLS and delta-SPH
 template <int D> int run_mpi_mls(aqc_ctx* ctx, void* const* a)
@@ -2626,6 +2684,9 @@ extern "C" int aqc_launch_fused(aqc_ctx* ctx, int fused_id, void* const* args, i
     }
     if (nargs != want)
         return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: expected %d args, got %d", want, nargs);
+    if (ctx->lap_morris)
+        return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: the fused sweeps are built for "
+                                          "__LAP_FORMULATION__ = __LAP_MONAGHAN__ only; launch the members one by one");
     for (int k = 0; k < nargs; k++)
         if (!args[k])
             return aqc_fail(ctx, AQC_ERR_ARG, "aqc_launch_fused: argument %d is NULL", k);

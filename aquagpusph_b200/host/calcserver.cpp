@@ -66,6 +66,17 @@ Kernel::Kernel(CalcServer* C, const std::string& name, const std::string& path,
 void Kernel::setup()
 {
     _kid = aqc_kernel_lookup(_path.c_str(), _entry.c_str(), _C->dims());
+    // Under __LAP_FORMULATION__ = __LAP_MORRIS__ only cfd/Interactions.cl has a hand-written build of that
+    // branch: the other scripts whose Laplacian term depends on it run as the scripts themselves
+    if (_kid >= 0 && _C->lapMorris()) {
+        auto ends = [&](const char* tail) {
+            const size_t n = strlen(tail);
+            return _path.size() >= n && _path.compare(_path.size() - n, n, tail) == 0;
+        };
+        if (ends("cfd/Boundary/BI/LapU.cl") || ends("cfd/Boundary/BI/NoSlip.cl") ||
+            (ends("cfd/MPI.cl") && _entry == "interactions"))
+            _kid = -1;
+    }
     if (_kid < 0) {
         // not a hand-written kernel: the script itself, compiled at run time like the reference compiles
         // every script (Kernel.cpp:354-420) -- here by NVRTC for sm_100a (csrc/clc.cu)
@@ -990,7 +1001,10 @@ void CalcServer::buildDefinitions()
             throw std::runtime_error(aqc_last_error(_ctx));
     }
     for (auto& kv : _defs) {
-        const int rc = aqc_set_define(_ctx, kv.first.c_str(), lookup(kv.first).c_str());
+        const std::string val = lookup(kv.first);
+        if (kv.first == "__LAP_FORMULATION__")
+            _lap_morris = (val == "2" || val == "__LAP_MORRIS__");
+        const int rc = aqc_set_define(_ctx, kv.first.c_str(), val.c_str());
         if (rc < 0)
             throw std::runtime_error(std::string("Unsupported definition: ") + aqc_last_error(_ctx));
     }
@@ -1106,7 +1120,7 @@ void CalcServer::setup()
 // one by one exactly as listed.
 void CalcServer::planFusion()
 {
-    if (getenv("AQUA_NO_FUSION"))
+    if (getenv("AQUA_NO_FUSION") || _lap_morris) // (the fused groups hold the Monaghan build of cfd/Interactions.cl)
         return;
     auto has = [](const std::vector<Variable*>& v, Variable* x) {
         return std::find(v.begin(), v.end(), x) != v.end();

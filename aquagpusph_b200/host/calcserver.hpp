@@ -514,6 +514,7 @@ class CalcServer {
     int mpi_rank() const { return _mpi_rank; }
     int mpi_size() const { return _mpi_size; }
     const std::vector<std::pair<std::string, std::string>>& definitions() const { return _defs; }
+    bool lapMorris() const { return _lap_morris; }
     /// Download an array in the ORIGINAL particle order (CalcServer::getUnsortedMem,
     /// CalcServer.cpp:772-830); `out` must hold length*typesize bytes
     void getUnsortedMem(const std::string& var, void* out);
@@ -539,6 +540,7 @@ class CalcServer {
     std::unique_ptr<InputOutput::Variables> _vars;
     std::vector<std::unique_ptr<Tool>> _tools;
     std::vector<std::pair<std::string, std::string>> _defs; // name -> value as "-D" text
+    bool _lap_morris = false; // __LAP_FORMULATION__ = __LAP_MORRIS__: cfd/Interactions.cl is never fused
     int _mpi_rank, _mpi_size;
     uint64_t _steps = 0;
     unsigned _fused_groups = 0;

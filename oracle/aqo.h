@@ -343,4 +343,9 @@ void aqo_portal_unmirror(float* r, const int* imirrored, aqo_usize N, const floa
 void aqo_portal_teleport(float* r, aqo_usize N, const float* portal_in_r, const float* portal_out_r,
                          const float* portal_n, int dims);
 
+/* cfd/Interactions.cl:60-145 under __LAP_FORMULATION__ == __LAP_MORRIS__ (:130-131) */
+void aqo_interactions_morris(const aqo_defs* D, const aqo_ll* L, const int* imove, const float* r, const float* u,
+                             const float* rho, const float* m, const float* p, float* grad_p, float* lap_u,
+                             float* div_u);
+
 #endif

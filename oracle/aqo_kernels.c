@@ -423,10 +423,10 @@ void aqo_mp_corrector(const int* imove, const float* r_in, float* r,
  * (cfd.xml:52-54), __CLEARY__ = 8 (2D) / 10 (3D) (:33-39).  Built with
  * LOCAL_MEM_SIZE, i.e. the outputs are overwritten, not accumulated
  * (:140-144); only the XYZ components are written (w untouched). */
-void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
-                      const float* r, const float* u, const float* rho,
-                      const float* m, const float* p, float* grad_p,
-                      float* lap_u, float* div_u)
+static void interactions_impl(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                              const float* r, const float* u, const float* rho,
+                              const float* m, const float* p, float* grad_p,
+                              float* lap_u, float* div_u, int morris)
 {
     const int dims = D->dims, vs = VS(dims);
     const float cleary = (dims == 3) ? 10.f : 8.f;
@@ -454,11 +454,19 @@ void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
             const float udr = dotv(u_ij, r_ij, dims);
             const float f_ij = kernelF(q, dims) * D->CONF * m[j];
             const float pf = (p_i + p_j) / (rho_i * rho_j) * f_ij;
-            const float r2 = (q * q + 0.01f) * H * H;
-            const float lf = f_ij * cleary * udr / (r2 * rho_i * rho_j);
-            for (int d = 0; d < dims; d++) {
-                gp[d] += pf * r_ij[d];
-                lu[d] += lf * r_ij[d];
+            if (morris) { /* :130-131 */
+                const float lf = f_ij * 2.f / (rho_i * rho_j);
+                for (int d = 0; d < dims; d++) {
+                    gp[d] += pf * r_ij[d];
+                    lu[d] += lf * u_ij[d];
+                }
+            } else { /* :127-129 */
+                const float r2 = (q * q + 0.01f) * H * H;
+                const float lf = f_ij * cleary * udr / (r2 * rho_i * rho_j);
+                for (int d = 0; d < dims; d++) {
+                    gp[d] += pf * r_ij[d];
+                    lu[d] += lf * r_ij[d];
+                }
             }
             du += udr * f_ij * rho_i / rho_j;
         }
@@ -469,6 +477,24 @@ void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
         }
         div_u[i] = du;
     }
+}
+
+void aqo_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                      const float* r, const float* u, const float* rho,
+                      const float* m, const float* p, float* grad_p,
+                      float* lap_u, float* div_u)
+{
+    interactions_impl(D, L, imove, r, u, rho, m, p, grad_p, lap_u, div_u, 0);
+}
+
+/* cfd/Interactions.cl:60-145 with __LAP_FORMULATION__ == __LAP_MORRIS__ (:130-131; the <Define> of
+ * examples/2D/taylor_green and cylinder_inside_channel) */
+void aqo_interactions_morris(const aqo_defs* D, const aqo_ll* L, const int* imove,
+                             const float* r, const float* u, const float* rho,
+                             const float* m, const float* p, float* grad_p,
+                             float* lap_u, float* div_u)
+{
+    interactions_impl(D, L, imove, r, u, rho, m, p, grad_p, lap_u, div_u, 1);
 }
 
 /* basic/Shepard.cl:76-125 (cfd_mode 0, EXCLUDED = imove >= 3) and

@@ -615,8 +615,12 @@ class Interpreter:
         elif key == ("cfd/Shepard.cl", "entry"):
             c("shepard", D, self.ll(), 1, V["imove"], V["r"], V["rho"], V["m"], V["shepard"])
         elif key == ("cfd/Interactions.cl", "entry"):
-            c("interactions", D, self.ll(), V["imove"], V["r"], V["u"], V["rho"], V["m"], V["p"],
-              V["grad_p"], V["lap_u"], V["div_u"])
+            lap = str(self.defs.get("__LAP_FORMULATION__", "__LAP_MONAGHAN__")).strip()
+            lap = str(self.defs.get(lap, lap)).strip()      # (__LAP_MORRIS__ -> 2)
+            if lap not in ("1", "2", "__LAP_MONAGHAN__", "__LAP_MORRIS__"):
+                raise NotImplementedError("oracle interpreter: __LAP_FORMULATION__=" + lap)
+            c("interactions_morris" if lap in ("2", "__LAP_MORRIS__") else "interactions", D, self.ll(), V["imove"],
+              V["r"], V["u"], V["rho"], V["m"], V["p"], V["grad_p"], V["lap_u"], V["div_u"])
         elif key == ("cfd/Sensors.cl", "entry"):
             c("sensors", D, self.ll(), V["imove"], V["r"], V["m"], V["u"], V["rho"], V["p"])
         elif key == ("cfd/SensorsRenormalization.cl", "entry"):

@@ -55,6 +55,10 @@ SCRIPTS = [
 # between barriers and stays pinned by the reference's own property tests.
 TOOL_SCRIPTS = [("aquagpusph/CalcServer/LinkList.cl.in", "aquagpusph/CalcServer/LinkList.hcl.in")]
 
+# The same script under other compile-time definitions (the <Define>s of a case): (script, name it is
+# indexed under, lines in front of the shim header)
+VARIANTS = [("cfd/Interactions.cl", "cfd/Interactions@morris.cl", ["#define __LAP_FORMULATION__ 2"])]
+
 VEC_LITERAL = re.compile(r"\(\s*(float2|float3|float4|float16|matrix|vec|vec2|vec3|vec4|vec_xyz)\s*\)\s*\(")
 MACRO_PARAMS = {
     "LINKLIST_LOCAL_PARAMS": ["icell", "ihoc", "n_cells"],
@@ -123,12 +127,13 @@ def mangle(script):
     return re.sub(r"\W", "_", script[:-3])
 
 
-def wrapper(script, dims, header=None):
+def wrapper(script, dims, header=None, alias=None, predef=()):
     """header: a tool-layer script (path relative to the reference root) and the .hcl.in the
-    reference's build prepends to it."""
-    tag = mangle(os.path.basename(script)[:-3] if header else script)
+    reference's build prepends to it.  alias / predef: the same script under another name with
+    other compile-time definitions (VARIANTS)."""
+    tag = mangle(os.path.basename(script)[:-3] if header else (alias or script))
     ks = kernels_of(os.path.join(REF, script) if header else os.path.join(REF, "resources", "Scripts", script))
-    lines = ["#define HAVE_%dD 1" % dims, '#include "cl_shim.hpp"']
+    lines = ["#define HAVE_%dD 1" % dims] + list(predef) + ['#include "cl_shim.hpp"']
     for entry, _, _ in ks:
         lines.append("#define %s aqrefk_%s__%s" % (entry, tag, entry))
     # the type headers define non-inline helpers (outer, det, inv): keep them TU-local
@@ -199,6 +204,12 @@ def build(verbose=False):
                 open(src, "w").write(txt)
                 jobs.append((src, src[:-4] + ".o"))
                 index[s] = ks
+            for s, alias, predef in VARIANTS:
+                txt, ks = wrapper(s, dims, alias=alias, predef=predef)
+                src = os.path.join(d, mangle(alias) + ".cpp")
+                open(src, "w").write(txt)
+                jobs.append((src, src[:-4] + ".o"))
+                index[alias] = ks
             for s, hdr in TOOL_SCRIPTS:
                 txt, ks = wrapper(s, dims, hdr)
                 src = os.path.join(d, "tool_" + mangle(os.path.basename(s)[:-3]) + ".cpp")

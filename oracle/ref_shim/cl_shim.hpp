@@ -294,5 +294,7 @@ extern clshim_defs clshim_D;
 #define LOCAL_MEM_SIZE 1
 #define __LAP_MONAGHAN__ 1
 #define __LAP_MORRIS__ 2
+#ifndef __LAP_FORMULATION__ // (build_ref.py VARIANTS: cfd/Interactions@morris.cl)
 #define __LAP_FORMULATION__ __LAP_MONAGHAN__
+#endif
 #define NDEBUG

@@ -50,3 +50,44 @@ def test_open_boundary_kernels(oracle, dims):
     ctx.launch(ob.INLET, "feed", d2)
     assert ctx.launch_count() == before
     ctx.close()
+
+
+@pytest.mark.parametrize("engine", [3, 2])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 40, 4.0)])
+def test_interactions_morris_laplacian_sweep(oracle, dims, n, hfac, engine):
+    """cfd/Interactions.cl::entry under <Define name="__LAP_FORMULATION__" value="__LAP_MORRIS__"/> (examples/2D/
+    taylor_green, cylinder_inside_channel; Interactions.cl:130-131) through the Kernel-tool C-ABI on both sweep
+    engines vs the oracle, which is bit-identical to the reference's script compiled with that definition
+    (tests/test_oracle_vs_reference.py).  Tolerance of the sweep tests:
+    |gpu - oracle| <= 2e-6 max|oracle| + 2e-5 |oracle|; the rows of the other particle classes untouched.  The
+    CPU half is tests/test_sweep_policy_host_emulation.py::test_interactions_policies_match_the_oracle."""
+    import cases
+    import pipeline
+    from test_oracle_vs_reference import morris_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = morris_inputs(s)
+    want = {k: x[k].copy() for k in ("grad_p", "lap_u", "div_u")}
+    oracle.call("interactions_morris", oracle.make_defs(dims, s["h"]), pipeline._ll(s), s["imove"], s["r"], x["u"],
+                s["rho"], s["m"], x["p"], want["grad_p"], want["lap_u"], want["div_u"])
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    assert _lib.lib().aqc_set_define(ctx.h, b"__LAP_FORMULATION__", b"__LAP_MORRIS__") == 0
+    c = pipeline.CudaState(ctx, s)
+    for k in ("u", "p", "grad_p", "lap_u", "div_u"):
+        c.set(k, x[k])
+    try:
+        assert _lib.lib().aqc_sweep_engine_select(engine) == engine
+        c.run("cfd/Interactions.cl")
+        got = {k: c.get(k) for k in want}
+        # the fused groups hold the Monaghan build: refused under this definition, loudly
+        with pytest.raises(_lib.AquaError, match="__LAP_MONAGHAN__"):
+            ctx.launch_fused([("cfd/Shepard.cl", "entry"), ("cfd/Interactions.cl", "entry")], c.v)
+    finally:
+        _lib.lib().aqc_sweep_engine_select(-1)
+    ctx.close()
+    fl = s["imove"] == 1
+    for k in want:
+        a, b = want[k].astype(np.float64), got[k].astype(np.float64)
+        assert np.isfinite(b).all(), k
+        assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
+        assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 0, k

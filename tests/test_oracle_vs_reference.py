@@ -608,3 +608,42 @@ def test_open_boundary_kernels_match_reference_scripts(oracle, dims):
     ob.oracle_step(oracle, D, dims, (ob.INLET, "feed"), c)
     R.run(ob.INLET, "feed", v["nbuffer"], ob.args_of(v), inlet_starving=0)
     assert all(c[k].tobytes() == v[k].tobytes() for k in ob.WRITES[(ob.INLET, "feed")])
+
+
+def morris_inputs(s, seed=8):
+    """Random velocities and pressures on the sorted dam-break particles; outputs pre-filled (the script
+    overwrites the XYZ components of the fluid rows and leaves everything else)."""
+    rng = np.random.default_rng(seed)
+    N, dims = s["N"], s["dims"]
+    V = 4 if dims == 3 else 2
+    u = np.zeros((N, V), np.float32)
+    u[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+    return dict(u=u, p=rng.uniform(-50.0, 300.0, N).astype(np.float32), grad_p=np.full((N, V), 7.0, np.float32),
+                lap_u=np.full((N, V), 7.0, np.float32), div_u=np.full(N, 7.0, np.float32))
+
+
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 36, 4.0)])
+def test_interactions_morris_laplacian_matches_reference_script(oracle, dims, n, hfac):
+    """cfd/Interactions.cl::entry compiled with __LAP_FORMULATION__ = __LAP_MORRIS__ (the <Define> of
+    examples/2D/taylor_green and cylinder_inside_channel; Interactions.cl:130-131): the C restatement is
+    bit-identical to the script, and only lap_u differs from the Monaghan build."""
+    import pipeline
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = morris_inputs(s)
+    c = pipeline.RefState(ref.Ref(dims, case["h"]), s)
+    for k in ("u", "p", "grad_p", "lap_u", "div_u"):
+        c.set(k, x[k])
+    c.run("cfd/Interactions@morris.cl")
+    g, l, d = x["grad_p"].copy(), x["lap_u"].copy(), x["div_u"].copy()
+    D = oracle.make_defs(dims, s["h"])
+    oracle.call("interactions_morris", D, pipeline._ll(s), s["imove"], s["r"], x["u"], s["rho"], s["m"], x["p"],
+                g, l, d)
+    assert c.get("grad_p").tobytes() == g.tobytes() and c.get("lap_u").tobytes() == l.tobytes()
+    assert c.get("div_u").tobytes() == d.tobytes()
+    g2, l2, d2 = x["grad_p"].copy(), x["lap_u"].copy(), x["div_u"].copy()
+    oracle.call("interactions", D, pipeline._ll(s), s["imove"], s["r"], x["u"], s["rho"], s["m"], x["p"], g2, l2, d2)
+    fl = s["imove"] == 1
+    assert g2.tobytes() == g.tobytes() and d2.tobytes() == d.tobytes()
+    assert np.isfinite(l).all() and np.abs(l[fl][:, :dims] - l2[fl][:, :dims]).max() > 1e-3
+    assert (l[~fl] == 7.0).all() and (dims == 2 or (l[:, 3] == 7.0).all())

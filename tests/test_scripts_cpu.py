@@ -108,6 +108,13 @@ def test_reference_scripts_compile_behind_the_dialect_header(tmp_path):
             ("cfd/Boundary/BI/Shepard.cl", ("compute",), 2), ("basic/time_scheme/adam_bashforth.cl", ("corrector",), 3)):
         for e in entries:
             ok(S + script, e, dims)
+    # under <Define name="__LAP_FORMULATION__" value="__LAP_MORRIS__"/> (examples/2D/cylinder_inside_channel,
+    # taylor_green) the host sends the scripts whose hand-written kernel holds the Monaghan branch only to this
+    # path (Kernel::setup): they compile with that definition
+    morris = tuple(d for d in REF_DEFS if not d.startswith("-D__LAP_FORMULATION__")) + ("-D__LAP_FORMULATION__=__LAP_MORRIS__",)
+    for script, e, dims in (("cfd/Boundary/BI/LapU.cl", "freeslip", 2), ("cfd/Boundary/BI/NoSlip.cl", "entry", 2),
+                            ("cfd/MPI.cl", "interactions", 3), ("cfd/Boundary/Portal/Interactions.cl", "entry", 2)):
+        _lib.script_check(S + script, e, dims, str(root), ("-DDIMS=%d" % dims,) + morris)
     # the argument list equals what the reference's compiler reports (tests/golden/kernel_signatures.json)
     import json
     gold = json.load(open(os.path.join(HERE, "golden", "kernel_signatures.json")))

@@ -118,6 +118,30 @@ extern "C" void emu_riemann(int dims, const uint32_t* iset, const int* imove, co
     else
         run_riemann<2>(iset, imove, r, u, rho, m, pp, grad_p, div_u, work_density, gamma, N, H, CONW, SUPPORT);
 }
+template <int D, class P> static void run_fluid(const int* imove, const void* r, const void* u, const float* rho,
+                                                 const float* m, const float* pp, void* grad_p, void* lap_u,
+                                                 float* div_u, uint32_t N, float H, float CONF, float SUPPORT)
+{
+    P p;
+    sweep_all(p, imove, N, H, SUPPORT, [&](P& q) {      // run_interactions
+        q.r = r; q.u = u; q.rho = rho; q.m = m; q.p = pp; q.grad_p = grad_p; q.lap_u = lap_u; q.div_u = div_u;
+        q.cF = Wend<D>::F * CONF;
+        q.eps2 = 0.01f * H * H;
+    });
+}
+extern "C" void emu_interactions(int dims, int morris, const int* imove, const void* r, const void* u,
+                                 const float* rho, const float* m, const float* pp, void* grad_p, void* lap_u,
+                                 float* div_u, uint32_t N, float H, float CONF, float SUPPORT)
+{
+    if (dims == 3 && morris)
+        run_fluid<3, PInteractionsMorris<3>>(imove, r, u, rho, m, pp, grad_p, lap_u, div_u, N, H, CONF, SUPPORT);
+    else if (dims == 3)
+        run_fluid<3, PInteractions<3>>(imove, r, u, rho, m, pp, grad_p, lap_u, div_u, N, H, CONF, SUPPORT);
+    else if (morris)
+        run_fluid<2, PInteractionsMorris<2>>(imove, r, u, rho, m, pp, grad_p, lap_u, div_u, N, H, CONF, SUPPORT);
+    else
+        run_fluid<2, PInteractions<2>>(imove, r, u, rho, m, pp, grad_p, lap_u, div_u, N, H, CONF, SUPPORT);
+}
 extern "C" void emu_noslip(int dims, const uint32_t* iset, const int* imove, const void* r, const void* normal,
                            const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
                            uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
@@ -148,7 +172,10 @@ def _lift():
     policy = _between(cu, "template <int D>\nstruct PBINoSlip : PBase {", "// cfd/Boundary/ElasticBounce.cl:77-148")
     # a policy that IS verified on the GPU (tests/test_gpu_bi.py), to validate this harness itself
     known = _between(cu, "template <int D>\nstruct PBIInteractions : PBase {", "// BI/NoSlip.cl:52-130")
-    return far + "\n" + dist2 + helpers + known + policy
+    fluid = _between(cu, "template <int D>\nstruct PInteractions : PBase {",
+                     "// ------------------------------------------------------------------------\n// basic/Shepard.cl")
+    assert "struct PInteractionsMorris : PInteractions<D>" in fluid
+    return far + "\n" + dist2 + helpers + known + policy + fluid
 
 
 @pytest.fixture(scope="module")
@@ -240,3 +267,32 @@ def test_riemann_policy_matches_the_oracle(oracle, emu, dims, n, hfac):
         assert np.isfinite(b).all(), k
         assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
         assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 1e-3, k
+
+
+@pytest.mark.parametrize("morris", [0, 1])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 40, 3.0), (3, 10, 2.0), (2, 40, 4.0)])
+def test_interactions_policies_match_the_oracle(oracle, emu, dims, n, hfac, morris):
+    """PInteractions (GPU-verified: tests/test_gpu_kernels.py) and PInteractionsMorris (cfd/Interactions.cl under
+    __LAP_FORMULATION__ = __LAP_MORRIS__, written without a GPU at hand), driven by the brute-force pair loop,
+    against the oracle (both bit-identical to the reference's script under the respective definition,
+    tests/test_oracle_vs_reference.py) at the sweep tests' tolerance."""
+    from test_oracle_vs_reference import morris_inputs
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    x = morris_inputs(s)
+    D = oracle.make_defs(dims, s["h"])
+    want = {k: x[k].copy() for k in ("grad_p", "lap_u", "div_u")}
+    oracle.call("interactions_morris" if morris else "interactions", D, pipeline._ll(s), s["imove"], s["r"], x["u"],
+                s["rho"], s["m"], x["p"], want["grad_p"], want["lap_u"], want["div_u"])
+    got = {k: x[k].copy() for k in want}
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)   # noqa: E731
+    arr = {k: np.ascontiguousarray(s[k]) for k in ("imove", "r", "rho", "m")}
+    emu.emu_interactions(dims, morris, P(arr["imove"]), P(arr["r"]), P(x["u"]), P(arr["rho"]), P(arr["m"]), P(x["p"]),
+                         P(got["grad_p"]), P(got["lap_u"]), P(got["div_u"]), s["N"], C.c_float(D.H),
+                         C.c_float(D.CONF), C.c_float(D.SUPPORT))
+    fl = s["imove"] == 1
+    for k in want:
+        a, b = want[k].astype(np.float64), got[k].astype(np.float64)
+        assert np.isfinite(b).all(), k
+        assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
+        assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - 7.0).max() > 1e-3, k

@@ -66,8 +66,10 @@ def scan(jit=True):
                           and L.aqc_kernel_lookup(k[0].encode(), k[1].encode(), dims) < 0)
             other = sorted(set(re.findall(r'<Tool [^>]*type="([^"]*)"', txt)) - HOST_TYPES)
             # definitions the hand-written kernels do not honour (aqc_set_define refuses them at load): another
-            # SPH kernel function than Wendland, another Laplacian than Monaghan's
-            for dname, ok in (("KERNEL_NAME", ("Wendland",)), ("__LAP_FORMULATION__", ("__LAP_MONAGHAN__", "1"))):
+            # SPH kernel function than Wendland, another Laplacian than Monaghan's or Morris' (under the latter
+            # cfd/Interactions.cl has a hand-written build, the other scripts with a Laplacian term run as scripts)
+            for dname, ok in (("KERNEL_NAME", ("Wendland",)),
+                              ("__LAP_FORMULATION__", ("__LAP_MONAGHAN__", "1", "__LAP_MORRIS__", "2"))):
                 vals = re.findall(r'<Define name="%s" value="([^"]*)"' % dname, txt)
                 if vals and vals[-1] not in ok:
                     other.append("definition %s=%s" % (dname, vals[-1]))
