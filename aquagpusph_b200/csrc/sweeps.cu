@@ -347,6 +347,127 @@ struct PShepard : PBase {
 };
 
 // ------------------------------------------------------------------------
+// cfd/Boundary/Portal/Shepard.cl:44-113 and Portal/Interactions.cl:47-146 (preset cfd/portal.xml): the particles
+// Portal/Mirror.cl::mirror has moved to the in portal (imirrored) ADD what they see there to their sums.  A
+// mirrored particle keeps its row of the sorted arrays while icell[i] names the cell it fell into, so these
+// sweeps stay on the per-warp engine, whose lanes take their cell from icell[i] (SPARSE_I; the mirrored
+// particles are few as well).  PBase::imove points at imirrored -- the engine's i filter -- and the
+// particle class is read from `mv`.
+template <int D>
+struct PPortalShepard : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 1;
+    const int* mv; // imove
+    const void* r;
+    const float *rho, *m;
+    float* shepard;
+    float cW; // wconW * CONW
+    struct IState { float x, y, z, s; bool ok; };
+    __device__ bool i_active(int mirrored) const { return mirrored != 0; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i);
+        const int c = __ldg(mv + i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.s = 0.f;
+        s.ok = !((c < -3) || (c > 1));
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j);
+        const bool ok = (__ldg(mv + j) == 1) && !__ldg(imove + j);
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, cW * __ldg(m + j) / __ldg(rho + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int) const
+    {
+        const float4 A = row[0];
+        const float q = q_of(dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z), invH);
+        const float t = 2.f - q, t2 = t * t;
+        s.s += (1.f + 2.f * q) * (t2 * t2) * A.w;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if (s.ok)
+            shepard[i] = shepard[i] + s.s;
+    }
+};
+
+template <int D, bool MORRIS>
+struct PPortalInteractions : PBase {
+    static constexpr bool SPHERE = true;
+    static constexpr bool SPARSE_I = true;
+    static constexpr int DIMS = D, NJ4 = 2;
+    const int* mv; // imove
+    const void *r, *u;
+    const float *rho, *m, *p;
+    void *grad_p, *lap_u;
+    float* div_u;
+    float cF;     // wconF * CONF
+    float eps2;   // 0.01 * H * H
+    struct IState { float x, y, z, ux, uy, uz, p, gx, gy, gz, lx, ly, lz, du; bool ok; };
+    __device__ bool i_active(int mirrored) const { return mirrored != 0; }
+    __device__ void load_i(IState& s, uint32_t i) const
+    {
+        const float4 a = ldvec<D>(r, i), b = ldvec<D>(u, i);
+        s.x = a.x; s.y = a.y; s.z = a.z; s.ux = b.x; s.uy = b.y; s.uz = b.z;
+        s.p = __ldg(p + i);
+        s.gx = s.gy = s.gz = s.lx = s.ly = s.lz = s.du = 0.f;
+        s.ok = __ldg(mv + i) == 1;
+    }
+    __device__ void stage_j(uint32_t j, float4* o) const
+    {
+        const float4 a = ldvec<D>(r, j), b = ldvec<D>(u, j);
+        const int c = __ldg(mv + j);
+        const bool ok = !__ldg(imove + j) && (c == 1 || c == -1);
+        const float w = cF * __ldg(m + j) / __ldg(rho + j);
+        o[0] = make_float4(ok ? a.x : AQC_FAR, a.y, a.z, w);
+        o[1] = make_float4(b.x, b.y, b.z, __ldg(p + j));
+    }
+    __device__ bool test(const IState& s, const float4& A) const
+    {
+        return dist2<D>(A.x - s.x, A.y - s.y, A.z - s.z) < cut2;
+    }
+    __device__ void body(IState& s, const float4* row, int stride) const
+    {
+        const float4 A = row[0], B = row[stride];
+        const float dx = A.x - s.x, dy = A.y - s.y, dz = A.z - s.z;
+        const float d2 = dist2<D>(dx, dy, dz);
+        const float t = 2.f - q_of(d2, invH);
+        const float fr = (t * t) * (t * A.w); // kernelF(q)*CONF*m_j / rho_j
+        const float dux = B.x - s.ux, duy = B.y - s.uy, duz = B.z - s.uz;
+        float udr = dux * dx + duy * dy;
+        if constexpr (D == 3)
+            udr += duz * dz;
+        const float a = (s.p + B.w) * fr;
+        const float b0 = udr * fr;
+        s.gx += a * dx; s.gy += a * dy; s.gz += a * dz;
+        if constexpr (MORRIS) {
+            s.lx += fr * dux; s.ly += fr * duy; s.lz += fr * duz;
+        } else {
+            const float b = b0 * rcp_fast(d2 + eps2);
+            s.lx += b * dx; s.ly += b * dy; s.lz += b * dz;
+        }
+        s.du += b0;
+    }
+    __device__ void store_i(const IState& s, uint32_t i) const
+    {
+        if (!s.ok)
+            return;
+        const float rho_i = __ldg(rho + i);
+        const float ir = 1.f / rho_i;
+        const float cl = (MORRIS ? 2.f : Wend<D>::CLEARY) * ir;
+        const float4 g = ldvec<D>(grad_p, i), l = ldvec<D>(lap_u, i);
+        stvec_xyz<D>(grad_p, i, g.x + s.gx * ir, g.y + s.gy * ir, g.z + s.gz * ir);
+        stvec_xyz<D>(lap_u, i, l.x + s.lx * cl, l.y + s.ly * cl, l.z + s.lz * cl);
+        div_u[i] = div_u[i] + s.du * rho_i;
+    }
+};
+
+// ------------------------------------------------------------------------
 // basic/deltaSPH.cl:94-145 (full, VECOUT) and :191-242 (lapp); EXCLUDED = imove != 1
 template <int D, bool VECOUT>
 struct PDeltaGrad : PBase {
@@ -2105,6 +2226,36 @@ int l_shepard_cfd(aqc_ctx* c, size_t, void* const* a)
     return c->defs.dims == 3 ? run_shepard<3, 1>(c, a) : run_shepard<2, 1>(c, a);
 }
 
+// cfd/Boundary/Portal/Shepard.cl: (imove, imirrored, r, rho, m, shepard, N, icell, ihoc, n_cells)
+template <int D> int run_portal_shepard(aqc_ctx* ctx, void* const* a)
+{
+    PPortalShepard<D> p;
+    set_base(p, ctx, a[1]); // (the engine's i filter reads imirrored)
+    p.mv = (const int*)a[0];
+    p.r = a[2]; p.rho = (const float*)a[3]; p.m = (const float*)a[4]; p.shepard = (float*)a[5];
+    p.cW = Wend<D>::W * ctx->defs.CONW;
+    return launch_sweep(ctx, p, make_ll(a, 7, aqc_scalar<uint32_t>(a, 6)));
+}
+int l_portal_shepard(aqc_ctx* c, size_t, void* const* a) { return DIMS_DISPATCH(c, run_portal_shepard, c, a); }
+// cfd/Boundary/Portal/Interactions.cl: (imove, imirrored, r, u, rho, m, p, grad_p, lap_u, div_u, N, icell, ihoc, n_cells)
+template <int D, bool MORRIS> int run_portal_inter(aqc_ctx* ctx, void* const* a)
+{
+    PPortalInteractions<D, MORRIS> p;
+    set_base(p, ctx, a[1]);
+    p.mv = (const int*)a[0];
+    p.r = a[2]; p.u = a[3]; p.rho = (const float*)a[4]; p.m = (const float*)a[5]; p.p = (const float*)a[6];
+    p.grad_p = a[7]; p.lap_u = a[8]; p.div_u = (float*)a[9];
+    p.cF = Wend<D>::F * ctx->defs.CONF;
+    p.eps2 = 0.01f * ctx->defs.H * ctx->defs.H;
+    return launch_sweep(ctx, p, make_ll(a, 11, aqc_scalar<uint32_t>(a, 10)));
+}
+int l_portal_inter(aqc_ctx* c, size_t, void* const* a)
+{
+    if (c->lap_morris)
+        return c->defs.dims == 3 ? run_portal_inter<3, true>(c, a) : run_portal_inter<2, true>(c, a);
+    return c->defs.dims == 3 ? run_portal_inter<3, false>(c, a) : run_portal_inter<2, false>(c, a);
+}
+
 template <int D, bool V> int run_deltagrad(aqc_ctx* ctx, void* const* a)
 {
     PDeltaGrad<D, V> p;
@@ -2493,6 +2644,13 @@ aqc_registrar r_shep_b("basic/Shepard.cl", "entry", 0,
 aqc_registrar r_shep_c("cfd/Shepard.cl", "entry", 0,
     { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
       OUT("shepard", "float*"), SC("N", "usize"), LL_ARGS }, l_shepard_cfd);
+aqc_registrar r_portal_shep("cfd/Boundary/Portal/Shepard.cl", "entry", 0,
+    { IN("imove", "int*"), IN("imirrored", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"),
+      OUT("shepard", "float*"), SC("N", "usize"), LL_ARGS }, l_portal_shepard);
+aqc_registrar r_portal_inter("cfd/Boundary/Portal/Interactions.cl", "entry", 0,
+    { IN("imove", "int*"), IN("imirrored", "int*"), IN("r", "vec*"), IN("u", "vec*"), IN("rho", "float*"),
+      IN("m", "float*"), IN("p", "float*"), OUT("grad_p", "vec*"), OUT("lap_u", "vec*"), OUT("div_u", "float*"),
+      SC("N", "usize"), LL_ARGS }, l_portal_inter);
 #define DSPH_GRAD_ARGS(outname, outtype)                                       \
     { IN("imove", "int*"), IN("r", "vec*"), IN("rho", "float*"), IN("m", "float*"), \
       IN("p", "float*"), OUT(outname, outtype), SC("N", "usize"), LL_ARGS }

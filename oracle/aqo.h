@@ -348,4 +348,11 @@ void aqo_interactions_morris(const aqo_defs* D, const aqo_ll* L, const int* imov
                              const float* rho, const float* m, const float* p, float* grad_p, float* lap_u,
                              float* div_u);
 
+/* cfd/Boundary/Portal/Shepard.cl:44-113, Portal/Interactions.cl:47-146 (morris: the __LAP_MORRIS__ branch) */
+void aqo_portal_shepard(const aqo_defs* D, const aqo_ll* L, const int* imove, const int* imirrored,
+                        const float* r, const float* rho, const float* m, float* shepard);
+void aqo_portal_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove, const int* imirrored,
+                             const float* r, const float* u, const float* rho, const float* m, const float* p,
+                             float* grad_p, float* lap_u, float* div_u, int morris);
+
 #endif

@@ -2085,3 +2085,87 @@ void aqo_portal_teleport(float* r, aqo_usize N, const float* portal_in_r, const 
             r[(size_t)i * vs + k] = portal_in_r[k] + d[k];
     }
 }
+
+/* cfd/Boundary/Portal/Shepard.cl:44-113: the particles mirrored to the in portal (imirrored) add the fluid
+ * they see there to their Shepard factor.  LOCAL_MEM_SIZE build: starts from shepard[i], stored at the end. */
+void aqo_portal_shepard(const aqo_defs* D, const aqo_ll* L, const int* imove, const int* imirrored,
+                        const float* r, const float* rho, const float* m, float* shepard)
+{
+    const int dims = D->dims, vs = VS(dims);
+    AQO_FOR_I(L->N) {
+        if ((imove[i] < -3) || (imove[i] > 1) || (!imirrored[i]))
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        float s = shepard[i];
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((imove[j] != 1) || (imirrored[j]))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            s += kernelW(q, dims) * D->CONW * m[j] / rho[j];
+        }
+        NEIGHS_END
+        shepard[i] = s;
+    }
+}
+
+/* cfd/Boundary/Portal/Interactions.cl:47-146 (morris: the __LAP_MORRIS__ branch, :128-129): the mirrored
+ * fluid particles add the interactions with what they see at the in portal to grad_p / lap_u / div_u. */
+void aqo_portal_interactions(const aqo_defs* D, const aqo_ll* L, const int* imove, const int* imirrored,
+                             const float* r, const float* u, const float* rho, const float* m, const float* p,
+                             float* grad_p, float* lap_u, float* div_u, int morris)
+{
+    const int dims = D->dims, vs = VS(dims);
+    const float cleary = (dims == 3) ? 10.f : 8.f;
+    const float H = D->H;
+    AQO_FOR_I(L->N) {
+        if ((!imirrored[i]) || (imove[i] != 1))
+            continue;
+        const float* r_i = r + (size_t)i * vs;
+        const float* u_i = u + (size_t)i * vs;
+        const float p_i = p[i], rho_i = rho[i];
+        float gp[3], lu[3], du = div_u[i];
+        for (int d = 0; d < dims; d++) {
+            gp[d] = grad_p[(size_t)i * vs + d];
+            lu[d] = lap_u[(size_t)i * vs + d];
+        }
+        NEIGHS_BEGIN(L, i, dims)
+        {
+            if ((imirrored[j]) || ((imove[j] != 1) && (imove[j] != -1)))
+                continue;
+            float r_ij[3], q;
+            if (!pair_q(D, r_i, r + (size_t)j * vs, r_ij, &q))
+                continue;
+            const float rho_j = rho[j], m_j = m[j], p_j = p[j];
+            float u_ij[3];
+            for (int d = 0; d < dims; d++)
+                u_ij[d] = u[(size_t)j * vs + d] - u_i[d];
+            const float udr = dotv(u_ij, r_ij, dims);
+            const float f_ij = kernelF(q, dims) * D->CONF * m_j;
+            const float pf = (p_i + p_j) / (rho_i * rho_j) * f_ij;
+            if (morris) {
+                const float lf = f_ij * 2.f / (rho_i * rho_j);
+                for (int d = 0; d < dims; d++) {
+                    gp[d] += pf * r_ij[d];
+                    lu[d] += lf * u_ij[d];
+                }
+            } else {
+                const float r2 = (q * q + 0.01f) * H * H;
+                const float lf = f_ij * cleary * udr / (r2 * rho_i * rho_j);
+                for (int d = 0; d < dims; d++) {
+                    gp[d] += pf * r_ij[d];
+                    lu[d] += lf * r_ij[d];
+                }
+            }
+            du += udr * f_ij * rho_i / rho_j;
+        }
+        NEIGHS_END
+        for (int d = 0; d < dims; d++) {
+            grad_p[(size_t)i * vs + d] = gp[d];
+            lap_u[(size_t)i * vs + d] = lu[d];
+        }
+        div_u[i] = du;
+    }
+}

@@ -773,6 +773,15 @@ class Interpreter:
                 c("sym_drop", V["imove"], V["r"], N, V["symmetry_r"], V["symmetry_n"], V["domain_max"], d)
             else:
                 raise NotImplementedError("oracle interpreter: kernel %s::%s" % (rel, entry))
+        elif key == ("cfd/Boundary/Portal/Shepard.cl", "entry"):
+            c("portal_shepard", D, self.ll(), V["imove"], V["imirrored"], V["r"], V["rho"], V["m"], V["shepard"])
+        elif key == ("cfd/Boundary/Portal/Interactions.cl", "entry"):
+            lap = str(self.defs.get("__LAP_FORMULATION__", "__LAP_MONAGHAN__")).strip()
+            lap = str(self.defs.get(lap, lap)).strip()
+            if lap not in ("1", "2", "__LAP_MONAGHAN__", "__LAP_MORRIS__"):
+                raise NotImplementedError("oracle interpreter: __LAP_FORMULATION__=" + lap)
+            c("portal_interactions", D, self.ll(), V["imove"], V["imirrored"], V["r"], V["u"], V["rho"], V["m"],
+              V["p"], V["grad_p"], V["lap_u"], V["div_u"], 1 if lap in ("2", "__LAP_MORRIS__") else 0)
         elif rel in ("cfd/Boundary/Inlet/Inlet.cl", "cfd/Boundary/Outlet/Outlet.cl", "cfd/Boundary/Portal/Mirror.cl"):
             # presets cfd/inlet.xml, cfd/outlet.xml, cfd/portal.xml: the element-wise kernels of the open
             # boundaries (aqo_kernels.c, bit-identical to the scripts)

@@ -46,6 +46,7 @@ SCRIPTS = [
     "cfd/ideal_gas/symmetry/Mirror.cl", "cfd/ideal_gas/riemann/Interactions.cl",
     "cfd/ideal_gas/time_scheme/euler.cl", "cfd/ideal_gas/time_scheme/improved_euler.cl",
     "cfd/Boundary/Inlet/Inlet.cl", "cfd/Boundary/Outlet/Outlet.cl", "cfd/Boundary/Portal/Mirror.cl",
+    "cfd/Boundary/Portal/Shepard.cl", "cfd/Boundary/Portal/Interactions.cl",
 ]
 # basic/Shepard.cl and basic/deltaSPH.cl are compiled through their cfd/ wrappers
 
@@ -57,7 +58,9 @@ TOOL_SCRIPTS = [("aquagpusph/CalcServer/LinkList.cl.in", "aquagpusph/CalcServer/
 
 # The same script under other compile-time definitions (the <Define>s of a case): (script, name it is
 # indexed under, lines in front of the shim header)
-VARIANTS = [("cfd/Interactions.cl", "cfd/Interactions@morris.cl", ["#define __LAP_FORMULATION__ 2"])]
+VARIANTS = [("cfd/Interactions.cl", "cfd/Interactions@morris.cl", ["#define __LAP_FORMULATION__ 2"]),
+            ("cfd/Boundary/Portal/Interactions.cl", "cfd/Boundary/Portal/Interactions@morris.cl",
+             ["#define __LAP_FORMULATION__ 2"])]
 
 VEC_LITERAL = re.compile(r"\(\s*(float2|float3|float4|float16|matrix|vec|vec2|vec3|vec4|vec_xyz)\s*\)\s*\(")
 MACRO_PARAMS = {

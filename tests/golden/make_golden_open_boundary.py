@@ -4,7 +4,7 @@ of tests/open_boundary_common.py: every array a kernel writes, after that kernel
 
     python tests/golden/make_golden_open_boundary.py      ->  tests/golden/open_boundary_outputs.npz
 
-tests/test_oracle_golden.py holds the oracle's restatement to these bits and tests/test_gpu_zz_open_boundary.py
+tests/test_oracle_golden.py holds the oracle's restatement to these bits and tests/test_zz_gpu_open_boundary.py
 the CUDA kernels, without the reference tree."""
 import os
 import sys

@@ -127,3 +127,71 @@ def checks(v0, b, dims):
     assert 0 < (b["imirrored"] == 1).sum() < N and set(np.unique(b["imirrored"])) == {0, 1}
     assert (b["icell"][b["imirrored"] == 1] < b["n_cells"][3]).all()
     assert (b["r"] != v0["r"]).any(1).sum() > nin      # teleported rows
+
+
+# ---- the two pair sweeps of the portal (cfd/Boundary/Portal/Shepard.cl, Interactions.cl) --------------------
+def portal_sweep_state(oracle, dims, n, hfac, seed=12):
+    """A sorted dam break whose fluid is cut by an out portal (normal +x) three quarters along and an in portal
+    one quarter along: Portal/Mirror.cl::mirror (the oracle's, bit-identical to the script) has moved the
+    particles within a kernel support of the out plane to the in plane and re-hashed their cells -- the state
+    the preset runs the portal sweeps on (cfd/portal.xml).  Outputs pre-filled with noise: the sweeps add."""
+    import pipeline
+    case = cases.dam_break(dims, n, hfac)
+    s = pipeline.oracle_linklist_and_sort(case)
+    N, V = s["N"], (4 if dims == 3 else 2)
+    rng = np.random.default_rng(seed)
+    fl = s["imove"] == 1
+    x = s["r"][fl][:, 0]
+    lo, hi = float(x.min()), float(x.max())
+    ctr = np.median(s["r"][fl], 0).astype(np.float32)
+    pin, pout, pn = ctr.copy(), ctr.copy(), np.zeros(V, np.float32)
+    pin[0], pout[0], pn[0] = lo + 0.25 * (hi - lo), lo + 0.75 * (hi - lo), 1.0
+    # The planes lie more than four kernel supports apart, so that no cell a mirrored particle looks into holds a
+    # mirrored particle: the reference's walk of a cell ends at the first row whose icell differs (BEGIN_NEIGHS),
+    # i.e. AT a mirrored row that still sits in the run of its old cell, where the engines here go on to the
+    # end of the 32-row tile -- a difference only a portal pair closer than that could show
+    assert pout[0] - pin[0] > 8.5 * float(s["h"]), (pout[0] - pin[0]) / float(s["h"])
+    D = oracle.make_defs(dims, s["h"])
+    r = np.ascontiguousarray(s["r"]).copy()
+    icell = np.ascontiguousarray(s["icell"]).copy()
+    imirrored = np.full(N, 7, np.int32)
+    rmin = np.zeros(V, np.float32)
+    rmin[:len(s["r_min"][:V])] = np.asarray(s["r_min"], np.float32)[:V]
+    oracle.call("portal_mirror", D, r, imirrored, icell, N, pin, pout, pn, rmin,
+                np.ascontiguousarray(s["n_cells"], np.uint32))
+    assert 0 < (imirrored[fl] == 1).sum() < fl.sum() and (icell < s["n_cells"][3]).all()
+    u = np.zeros((N, V), np.float32)
+    u[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+
+    def noise_vec():
+        a = np.zeros((N, V), np.float32)
+        a[:, :dims] = rng.normal(size=(N, dims)).astype(np.float32)
+        if dims == 3:
+            a[:, 3] = 7.0
+        return a
+    x = dict(r=r, icell=icell, imirrored=imirrored, u=u, p=rng.uniform(-50.0, 300.0, N).astype(np.float32),
+             grad_p=noise_vec(), lap_u=noise_vec(), div_u=rng.normal(size=N).astype(np.float32),
+             shepard=rng.uniform(0.2, 0.9, N).astype(np.float32))
+    return case, s, D, x
+
+
+def portal_sweeps_oracle(oracle, s, D, x, morris):
+    """The oracle's portal sweeps on a copy of the outputs; returns them."""
+    import oracle.oracle as O
+    L = O.make_ll(x["icell"], np.ascontiguousarray(s["ihoc"]), s["n_cells"], s["N"])
+    w = {k: x[k].copy() for k in ("shepard", "grad_p", "lap_u", "div_u")}
+    imove = np.ascontiguousarray(s["imove"])
+    rho, m = np.ascontiguousarray(s["rho"]), np.ascontiguousarray(s["m"])
+    oracle.call("portal_shepard", D, L, imove, x["imirrored"], x["r"], rho, m, w["shepard"])
+    oracle.call("portal_interactions", D, L, imove, x["imirrored"], x["r"], x["u"], rho, m, x["p"], w["grad_p"],
+                w["lap_u"], w["div_u"], int(morris))
+    return w
+
+
+def portal_rows(s, x, k):
+    """The rows a portal sweep may change: mirrored fluid particles (Interactions.cl:65), mirrored particles
+    of the classes -3 .. 1 for the Shepard factor (Shepard.cl:57)."""
+    mv = np.asarray(s["imove"])
+    if k == "shepard":
+        return (x["imirrored"] == 1) & (mv >= -3) & (mv <= 1)
+    return (x["imirrored"] == 1) & (mv == 1)

@@ -647,3 +647,27 @@ def test_interactions_morris_laplacian_matches_reference_script(oracle, dims, n,
     assert g2.tobytes() == g.tobytes() and d2.tobytes() == d.tobytes()
     assert np.isfinite(l).all() and np.abs(l[fl][:, :dims] - l2[fl][:, :dims]).max() > 1e-3
     assert (l[~fl] == 7.0).all() and (dims == 2 or (l[:, 3] == 7.0).all())
+
+
+@pytest.mark.parametrize("morris", [0, 1])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 60, 3.0), (3, 24, 1.3), (2, 80, 4.0)])
+def test_portal_sweeps_match_reference_scripts(oracle, dims, n, hfac, morris):
+    """cfd/Boundary/Portal/Shepard.cl::entry and Portal/Interactions.cl::entry (the latter under both Laplacian
+    definitions; preset cfd/portal.xml, examples/2D/taylor_green) on a state Portal/Mirror.cl::mirror has prepared:
+    the C restatements are bit-identical to the scripts; only mirrored rows change."""
+    import pipeline
+    import open_boundary_common as ob
+    case, s, D, x = ob.portal_sweep_state(oracle, dims, n, hfac)
+    c = pipeline.RefState(ref.Ref(dims, case["h"]), s)
+    for k in ("r", "icell", "u", "p", "grad_p", "lap_u", "div_u", "shepard"):
+        c.set(k, x[k])
+    c.v["imirrored"] = x["imirrored"].copy()
+    c.run("cfd/Boundary/Portal/Shepard.cl")
+    c.run("cfd/Boundary/Portal/Interactions@morris.cl" if morris else "cfd/Boundary/Portal/Interactions.cl")
+    w = ob.portal_sweeps_oracle(oracle, s, D, x, morris)
+    for k in w:
+        assert c.get(k).tobytes() == w[k].tobytes(), k
+    for k in w:
+        mir = ob.portal_rows(s, x, k)
+        assert np.array_equal(w[k][~mir], x[k][~mir]), k
+        assert np.isfinite(w[k]).all() and np.abs(w[k][mir].astype(np.float64) - x[k][mir]).max() > 1e-3, k

@@ -142,6 +142,33 @@ extern "C" void emu_interactions(int dims, int morris, const int* imove, const v
     else
         run_fluid<2, PInteractions<2>>(imove, r, u, rho, m, pp, grad_p, lap_u, div_u, N, H, CONF, SUPPORT);
 }
+template <int D, class P, class Set> static void sweep_portal(P& p, const int* imirrored, uint32_t N, float H,
+                                                              float SUPPORT, Set set)
+{
+    sweep_all(p, imirrored, N, H, SUPPORT, set);      // set_base(p, ctx, imirrored): the i filter reads imirrored
+}
+extern "C" void emu_portal(int dims, int morris, const int* imove, const int* imirrored, const void* r, const void* u,
+                           const float* rho, const float* m, const float* pp, void* grad_p, void* lap_u, float* div_u,
+                           float* shepard, uint32_t N, float H, float CONW, float CONF, float SUPPORT)
+{
+#define PORTAL(D, MO)                                                                                       \
+    {                                                                                                       \
+        PPortalShepard<D> a;                                                                                \
+        sweep_portal<D>(a, imirrored, N, H, SUPPORT, [&](PPortalShepard<D>& q) {                            \
+            q.mv = imove; q.r = r; q.rho = rho; q.m = m; q.shepard = shepard; q.cW = Wend<D>::W * CONW;     \
+        });                                                                                                 \
+        PPortalInteractions<D, MO> b;                                                                       \
+        sweep_portal<D>(b, imirrored, N, H, SUPPORT, [&](PPortalInteractions<D, MO>& q) {                   \
+            q.mv = imove; q.r = r; q.u = u; q.rho = rho; q.m = m; q.p = pp; q.grad_p = grad_p;              \
+            q.lap_u = lap_u; q.div_u = div_u; q.cF = Wend<D>::F * CONF; q.eps2 = 0.01f * H * H;             \
+        });                                                                                                 \
+    }
+    if (dims == 3 && morris) PORTAL(3, true)
+    else if (dims == 3) PORTAL(3, false)
+    else if (morris) PORTAL(2, true)
+    else PORTAL(2, false)
+#undef PORTAL
+}
 extern "C" void emu_noslip(int dims, const uint32_t* iset, const int* imove, const void* r, const void* normal,
                            const void* u, const float* rho, const float* m, void* lap_u, uint32_t N,
                            uint32_t noslip_iset, float dr, float H, float CONW, float SUPPORT)
@@ -175,6 +202,8 @@ def _lift():
     fluid = _between(cu, "template <int D>\nstruct PInteractions : PBase {",
                      "// ------------------------------------------------------------------------\n// basic/Shepard.cl")
     assert "struct PInteractionsMorris : PInteractions<D>" in fluid
+    fluid += _between(cu, "template <int D>\nstruct PPortalShepard : PBase {",
+                      "// ------------------------------------------------------------------------\n// basic/deltaSPH.cl")
     return far + "\n" + dist2 + helpers + known + policy + fluid
 
 
@@ -296,3 +325,30 @@ def test_interactions_policies_match_the_oracle(oracle, emu, dims, n, hfac, morr
         assert np.isfinite(b).all(), k
         assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
         assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - 7.0).max() > 1e-3, k
+
+
+@pytest.mark.parametrize("morris", [0, 1])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 60, 3.0), (3, 24, 1.3), (2, 80, 4.0)])
+def test_portal_policies_match_the_oracle(oracle, emu, dims, n, hfac, morris):
+    """PPortalShepard / PPortalInteractions (cfd/Boundary/Portal/Shepard.cl, Interactions.cl under both Laplacian
+    definitions; written without a GPU at hand), driven by the brute-force pair loop with imirrored as the i
+    filter like their launchers set it, against the oracle (bit-identical to the scripts,
+    tests/test_oracle_vs_reference.py) on a state Portal/Mirror.cl::mirror prepared: the sweeps ADD to what the
+    arrays hold, so the tolerance is the sweep tests' on the added part; rows that are not mirrored keep their bits."""
+    import open_boundary_common as ob
+    case, s, D, x = ob.portal_sweep_state(oracle, dims, n, hfac)
+    want = ob.portal_sweeps_oracle(oracle, s, D, x, morris)
+    got = {k: x[k].copy() for k in want}
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)   # noqa: E731
+    arr = {k: np.ascontiguousarray(s[k]) for k in ("imove", "rho", "m")}
+    emu.emu_portal(dims, morris, P(arr["imove"]), P(x["imirrored"]), P(x["r"]), P(x["u"]), P(arr["rho"]), P(arr["m"]),
+                   P(x["p"]), P(got["grad_p"]), P(got["lap_u"]), P(got["div_u"]), P(got["shepard"]), s["N"],
+                   C.c_float(D.H), C.c_float(D.CONW), C.c_float(D.CONF), C.c_float(D.SUPPORT))
+    for k in want:
+        rows = ob.portal_rows(s, x, k)
+        add_w = want[k].astype(np.float64) - x[k]
+        add_g = got[k].astype(np.float64) - x[k]
+        assert np.isfinite(got[k]).all() and np.array_equal(got[k][~rows], x[k][~rows]), k
+        tol = 2e-6 * max(np.abs(add_w).max(), np.abs(x[k]).max()) + 2e-5 * np.abs(add_w)
+        assert np.all(np.abs(add_w - add_g) <= tol), (k, np.abs(add_w - add_g).max())
+        assert np.abs(add_w[rows]).max() > 1e-3, k

@@ -91,3 +91,36 @@ def test_interactions_morris_laplacian_sweep(oracle, dims, n, hfac, engine):
         assert np.isfinite(b).all(), k
         assert np.all(np.abs(a - b) <= 2e-6 * np.abs(a[fl]).max() + 2e-5 * np.abs(a)), (k, np.abs(a - b).max())
         assert np.array_equal(got[k][~fl], x[k][~fl]) and np.abs(want[k][fl] - x[k][fl]).max() > 0, k
+
+
+@pytest.mark.parametrize("morris", [0, 1])
+@pytest.mark.parametrize("dims,n,hfac", [(2, 60, 3.0), (3, 24, 1.3), (2, 80, 4.0)])
+def test_portal_sweeps(oracle, dims, n, hfac, morris):
+    """cfd/Boundary/Portal/Shepard.cl::entry and Portal/Interactions.cl::entry (under both Laplacian definitions;
+    preset cfd/portal.xml, examples/2D/taylor_green) through the Kernel-tool C-ABI on a state
+    Portal/Mirror.cl::mirror prepared (mirrored particles keep their rows, icell names their new cells) vs the
+    oracle, which is bit-identical to the reference's scripts.  The sweeps ADD to what the arrays hold: the sweep
+    tests' tolerance on the added part, |d_gpu - d_oracle| <= 2e-6 max(|d_oracle|, |array|) + 2e-5 |d_oracle|;
+    rows that are not mirrored keep their bits.  CPU half: tests/test_sweep_policy_host_emulation.py::
+    test_portal_policies_match_the_oracle."""
+    import pipeline
+    case, s, D, x = ob.portal_sweep_state(oracle, dims, n, hfac)
+    want = ob.portal_sweeps_oracle(oracle, s, D, x, morris)
+    ctx = _lib.Context(0, dims=dims, h=case["h"])
+    if morris:
+        assert _lib.lib().aqc_set_define(ctx.h, b"__LAP_FORMULATION__", b"__LAP_MORRIS__") == 0
+    c = pipeline.CudaState(ctx, s)
+    for k in ("r", "icell", "u", "p", "grad_p", "lap_u", "div_u", "shepard"):
+        c.set(k, x[k])
+    c.v["imirrored"] = ctx.array(x["imirrored"])
+    c.run("cfd/Boundary/Portal/Shepard.cl")
+    c.run("cfd/Boundary/Portal/Interactions.cl")
+    got = {k: c.get(k) for k in want}
+    ctx.close()
+    for k in want:
+        rows = ob.portal_rows(s, x, k)
+        add_w = want[k].astype(np.float64) - x[k]
+        add_g = got[k].astype(np.float64) - x[k]
+        assert np.isfinite(got[k]).all() and np.array_equal(got[k][~rows], x[k][~rows]), k
+        tol = 2e-6 * max(np.abs(add_w).max(), np.abs(x[k]).max()) + 2e-5 * np.abs(add_w)
+        assert np.all(np.abs(add_w - add_g) <= tol), (k, np.abs(add_w - add_g).max())
